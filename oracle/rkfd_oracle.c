@@ -1,0 +1,1002 @@
+/* rkfd_oracle.c - CPU oracle for the RoKi-FD step path.  TEST INFRASTRUCTURE, NOT PRODUCT.
+ * See rkfd_oracle.h for the status of this file (parity unpinned, what may load it).
+ *
+ * Every function cites the reference (mi-lib/roki-fd v1.7.9) file:line it restates, or the
+ * [EXT] assumption (DESIGN.md "EXT assumptions", tags A-k as in SURVEY.md Appendix A) it
+ * fixes when the arithmetic lives in RoKi/ZM/Zeo, which are not in the reference tree.
+ *
+ * Conventions: 3x3 matrices row-major m[3*r+c]; 6-D vectors (linear[3], angular[3]) (A-1);
+ * link velocities/accelerations are those of the link origin expressed in the link frame,
+ * accelerations are classical (A-2); gravity is applied as a force m*g at each COM (A-4).
+ */
+#include "rkfd_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------ */
+/* small dense helpers */
+static void v3_set(double *a, double x, double y, double z){ a[0]=x; a[1]=y; a[2]=z; }
+static void v3_copy(const double *a, double *b){ b[0]=a[0]; b[1]=a[1]; b[2]=a[2]; }
+static void v3_add(const double *a, const double *b, double *c){ c[0]=a[0]+b[0]; c[1]=a[1]+b[1]; c[2]=a[2]+b[2]; }
+static void v3_sub(const double *a, const double *b, double *c){ c[0]=a[0]-b[0]; c[1]=a[1]-b[1]; c[2]=a[2]-b[2]; }
+static void v3_cat(double *a, double k, const double *b){ a[0]+=k*b[0]; a[1]+=k*b[1]; a[2]+=k*b[2]; }
+static double v3_dot(const double *a, const double *b){ return a[0]*b[0]+a[1]*b[1]+a[2]*b[2]; }
+static void v3_cross(const double *a, const double *b, double *c)
+{
+  double x = a[1]*b[2]-a[2]*b[1], y = a[2]*b[0]-a[0]*b[2], z = a[0]*b[1]-a[1]*b[0];
+  c[0]=x; c[1]=y; c[2]=z;
+}
+static double v3_norm(const double *a){ return sqrt(v3_dot(a,a)); }
+/* y = M x */
+static void m3_mulv(const double *m, const double *x, double *y)
+{
+  double a = m[0]*x[0]+m[1]*x[1]+m[2]*x[2];
+  double b = m[3]*x[0]+m[4]*x[1]+m[5]*x[2];
+  double c = m[6]*x[0]+m[7]*x[1]+m[8]*x[2];
+  y[0]=a; y[1]=b; y[2]=c;
+}
+/* y = M^T x */
+static void m3_tmulv(const double *m, const double *x, double *y)
+{
+  double a = m[0]*x[0]+m[3]*x[1]+m[6]*x[2];
+  double b = m[1]*x[0]+m[4]*x[1]+m[7]*x[2];
+  double c = m[2]*x[0]+m[5]*x[1]+m[8]*x[2];
+  y[0]=a; y[1]=b; y[2]=c;
+}
+static void m3_mul(const double *a, const double *b, double *c)
+{
+  double t[9]; int i,j,k;
+  for(i=0;i<3;i++) for(j=0;j<3;j++){ t[3*i+j]=0; for(k=0;k<3;k++) t[3*i+j]+=a[3*i+k]*b[3*k+j]; }
+  memcpy(c,t,sizeof t);
+}
+static void m3_ident(double *m){ memset(m,0,9*sizeof(double)); m[0]=m[4]=m[8]=1.0; }
+static void m3_skew(const double *p, double *s)
+{
+  s[0]=0; s[1]=-p[2]; s[2]=p[1]; s[3]=p[2]; s[4]=0; s[5]=-p[0]; s[6]=-p[1]; s[7]=p[0]; s[8]=0;
+}
+
+/* [EXT A-3] angle-axis vector -> rotation matrix (Rodrigues; Zeo zMat3DFromAA) */
+static void aa_to_mat(const double *aa, double *R)
+{
+  double th2 = v3_dot(aa,aa), A, B, K[9], K2[9]; int i;
+  if( th2 < 1.0e-24 ){ A = 1.0; B = 0.5; }
+  else { double th = sqrt(th2); A = sin(th)/th; B = (1.0-cos(th))/th2; }
+  m3_skew(aa,K); m3_mul(K,K,K2); m3_ident(R);
+  for(i=0;i<9;i++) R[i] += A*K[i] + B*K2[i];
+}
+/* [EXT A-3/A-9] aa <- log( R(w) R(aa) ): world(org)-frame angular increment (Zeo zAACascade),
+ * evaluated through unit quaternions */
+static void aa_cascade(double *aa, const double *w)
+{
+  double q1[4], q2[4], q[4], th, s, n;
+  th = v3_norm(aa);
+  if( th < 1.0e-12 ){ q1[0]=1.0; q1[1]=0.5*aa[0]; q1[2]=0.5*aa[1]; q1[3]=0.5*aa[2]; }
+  else { s = sin(0.5*th)/th; q1[0]=cos(0.5*th); q1[1]=s*aa[0]; q1[2]=s*aa[1]; q1[3]=s*aa[2]; }
+  th = v3_norm(w);
+  if( th < 1.0e-12 ){ q2[0]=1.0; q2[1]=0.5*w[0]; q2[2]=0.5*w[1]; q2[3]=0.5*w[2]; }
+  else { s = sin(0.5*th)/th; q2[0]=cos(0.5*th); q2[1]=s*w[0]; q2[2]=s*w[1]; q2[3]=s*w[2]; }
+  /* q = q2 * q1 */
+  q[0] = q2[0]*q1[0] - q2[1]*q1[1] - q2[2]*q1[2] - q2[3]*q1[3];
+  q[1] = q2[0]*q1[1] + q2[1]*q1[0] + q2[2]*q1[3] - q2[3]*q1[2];
+  q[2] = q2[0]*q1[2] - q2[1]*q1[3] + q2[2]*q1[0] + q2[3]*q1[1];
+  q[3] = q2[0]*q1[3] + q2[1]*q1[2] - q2[2]*q1[1] + q2[3]*q1[0];
+  if( q[0] < 0 ){ q[0]=-q[0]; q[1]=-q[1]; q[2]=-q[2]; q[3]=-q[3]; }
+  n = sqrt(q[1]*q[1]+q[2]*q[2]+q[3]*q[3]);
+  if( n < 1.0e-12 ){ aa[0]=2.0*q[1]; aa[1]=2.0*q[2]; aa[2]=2.0*q[3]; }
+  else { th = 2.0*atan2(n,q[0]); aa[0]=th*q[1]/n; aa[1]=th*q[2]/n; aa[2]=th*q[3]/n; }
+}
+
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+  int parent, jtype, mtype, stuff;
+  double org_R[9], org_p[3];
+  double mass, com[3], inertia[9];
+  double stiffness, viscosity, coulomb, sfriction;
+  double mk, madm, mgear, mrotor, mgearin, mmin, mmax;
+  int qofs, ndof;
+  double M[36];   /* rigid-body 6x6 inertia at the link origin (A-4) */
+} ork_link;
+
+typedef struct { int link, nvert, vofs; } ork_cell;
+typedef struct { double R[9], p[3], half[3]; int stuff; } ork_box;
+typedef struct { int type; double K, L, E, V, SF, KF; } ork_cinfo;
+typedef struct { int sa, sb; ork_cinfo ci; } ork_cinfo_ent;
+typedef struct { int cell, box, sofs; ork_cinfo ci; } ork_pair;
+
+struct ork_world {
+  int nl, nq;
+  ork_link *link;
+  int ncell, nvert; ork_cell *cell; double *vert;
+  int nbox; ork_box *box;
+  int nci; ork_cinfo_ent *ci; ork_cinfo cidef;
+  int npair, nslot; ork_pair *pair;
+  double dt, friction_weight; int pyramid, max_iter, solver;
+  double sc_table[2][64];   /* sin/cos pyramid table (rkfd_util.c:199-214) */
+};
+
+/* per-link working set of one dynamics evaluation */
+typedef struct {
+  double Rrel[9], prel[3];  /* link frame w.r.t. parent frame */
+  double Rw[9], pw[3];      /* world frame */
+  double v[6];              /* link velocity (lin, ang) in link frame */
+  double zeta[6];           /* velocity-product acceleration */
+  double S[36];             /* motion subspace, 6 x ndof, row-major with row stride 6 */
+  double X[36];             /* acceleration transform parent -> link */
+  double IA[36], pA[6];     /* articulated inertia / bias */
+  double U[36], Dinv[36], u[6];
+  double wext[6];           /* external wrench at origin, link frame */
+  double a[6];              /* link acceleration */
+  double a0[6];             /* saved acceleration (rkChainSaveABIAccBias) */
+  double du[6];             /* probe increments of u */
+  double dp[6];             /* probe increments of pA */
+} ork_lw;
+
+struct ork_env {
+  const ork_world *w;
+  double t;
+  double *q, *qd, *qdd;       /* committed state (fd->dis, fd->vel, fd->acc) */
+  double *min;                /* motor input per link */
+  int *piv_type; double *piv_prev;   /* joint friction pivot (A-8) per dof */
+  double *tf, *tdrive, *jm;   /* per-dof friction torque, driving torque, motor inertia */
+  int *c_active, *c_type; double *c_ref, *c_f, *c_pro;   /* per contact slot */
+  double *c_norm, *c_axis, *c_vert, *c_refw, *c_vel;     /* per slot, current evaluation */
+  ork_lw *lw;
+  /* rigid system of the last evaluation */
+  int rn; double *rA, *rb, *rf;
+  /* RKG workspace */
+  double *k[4][2], *xs[2];
+};
+
+/* ------------------------------------------------------------------------------------ */
+static int jtype_ndof(int jt)
+{
+  switch(jt){ case ORK_JOINT_REVOL: case ORK_JOINT_PRISM: return 1;
+              case ORK_JOINT_SPHER: return 3; case ORK_JOINT_FLOAT: return 6; default: return 0; }
+}
+
+static void link_build_inertia(ork_link *l)
+{
+  /* [EXT A-4] M = [[m E, -m[c x]],[m[c x], Ic - m[c x][c x]]] acting on (lin acc, ang acc) */
+  double C[9], C2[9]; int r,c;
+  memset(l->M,0,sizeof l->M);
+  m3_skew(l->com,C); m3_mul(C,C,C2);
+  for(r=0;r<3;r++){
+    l->M[6*r+r] = l->mass;
+    for(c=0;c<3;c++){
+      l->M[6*r+3+c]     = -l->mass*C[3*r+c];
+      l->M[6*(3+r)+c]   =  l->mass*C[3*r+c];
+      l->M[6*(3+r)+3+c] =  l->inertia[3*r+c] - l->mass*C2[3*r+c];
+    }
+  }
+}
+
+ork_world *ork_world_new(int nl, const int *li, const double *ld)
+{
+  ork_world *w = (ork_world*)calloc(1,sizeof *w); int i;
+  w->nl = nl; w->link = (ork_link*)calloc(nl,sizeof(ork_link));
+  w->nq = 0;
+  for(i=0;i<nl;i++){
+    ork_link *l = &w->link[i]; const double *d = ld + ORK_LINK_ND*i;
+    l->parent = li[4*i]; l->jtype = li[4*i+1]; l->mtype = li[4*i+2]; l->stuff = li[4*i+3];
+    memcpy(l->org_R,d,9*sizeof(double)); memcpy(l->org_p,d+9,3*sizeof(double));
+    l->mass = d[12]; memcpy(l->com,d+13,3*sizeof(double)); memcpy(l->inertia,d+16,9*sizeof(double));
+    l->stiffness=d[25]; l->viscosity=d[26]; l->coulomb=d[27]; l->sfriction=d[28];
+    l->mk=d[29]; l->madm=d[30]; l->mgear=d[31]; l->mrotor=d[32]; l->mgearin=d[33]; l->mmin=d[34]; l->mmax=d[35];
+    l->ndof = jtype_ndof(l->jtype); l->qofs = w->nq; w->nq += l->ndof;
+    link_build_inertia(l);
+  }
+  /* reference defaults: rkfd_property.c:10-18, rkfd_defs.h:15-23 */
+  ork_world_set_prp(w, 0.001, 8, 100.0, 10);
+  ork_world_set_solver(w, ORK_SOLVER_VERT);   /* rkfd_sim.c:52 */
+  return w;
+}
+void ork_world_free(ork_world *w)
+{
+  if(!w) return;
+  free(w->link); free(w->cell); free(w->vert); free(w->box); free(w->ci); free(w->pair); free(w);
+}
+int ork_world_add_cell(ork_world *w, int link, int nvert, const double *verts)
+{
+  w->cell = (ork_cell*)realloc(w->cell,(w->ncell+1)*sizeof(ork_cell));
+  w->vert = (double*)realloc(w->vert,3*(w->nvert+nvert)*sizeof(double));
+  w->cell[w->ncell].link = link; w->cell[w->ncell].nvert = nvert; w->cell[w->ncell].vofs = w->nvert;
+  memcpy(w->vert+3*w->nvert, verts, 3*nvert*sizeof(double));
+  w->nvert += nvert;
+  return w->ncell++;
+}
+int ork_world_add_box(ork_world *w, const double *R, const double *p, const double *half, int stuff)
+{
+  ork_box *b;
+  w->box = (ork_box*)realloc(w->box,(w->nbox+1)*sizeof(ork_box));
+  b = &w->box[w->nbox];
+  memcpy(b->R,R,9*sizeof(double)); memcpy(b->p,p,3*sizeof(double)); memcpy(b->half,half,3*sizeof(double));
+  b->stuff = stuff;
+  return w->nbox++;
+}
+void ork_world_add_contact_info(ork_world *w, int sa, int sb, int type,
+                                double K, double L, double E, double V, double SF, double KF)
+{
+  ork_cinfo_ent *e;
+  w->ci = (ork_cinfo_ent*)realloc(w->ci,(w->nci+1)*sizeof(ork_cinfo_ent));
+  e = &w->ci[w->nci++];
+  e->sa=sa; e->sb=sb; e->ci.type=type; e->ci.K=K; e->ci.L=L; e->ci.E=E; e->ci.V=V; e->ci.SF=SF; e->ci.KF=KF;
+}
+void ork_world_set_prp(ork_world *w, double dt, int pyramid, double fw, int max_iter)
+{
+  int i; double th, dth, off;
+  w->dt=dt; w->pyramid=pyramid; w->friction_weight=fw; w->max_iter=max_iter;
+  /* rkFDCrateSinCosTable (rkfd_util.c:199-214) with the Vert offset -pi/pyramid (rkfd_vert.c:369) */
+  off = -M_PI / pyramid; dth = 2.0*M_PI / pyramid;
+  for( i=0,th=0.0; i<pyramid && i<64; i++,th+=dth ){
+    w->sc_table[0][i] = sin(th+off); w->sc_table[1][i] = cos(th+off);
+  }
+}
+void ork_world_set_solver(ork_world *w, int solver)
+{
+  w->solver = solver;
+  /* default contact info: rkfd_vert.c:340-348, rkfd_mlcp.c:301-310, rkfd_volume.c:961-969 */
+  w->cidef.type = ORK_CONTACT_RIGID;
+  w->cidef.K = 1000.0; w->cidef.L = 1.0; w->cidef.SF = 0.5; w->cidef.KF = 0.3;
+  w->cidef.E = 0.0; w->cidef.V = 0.0;
+}
+void ork_world_finalize(ork_world *w)
+{
+  /* pairs in registration order: (moving cell) x (static box); contact info by stuff pair with
+   * fallback to the solver default (rkfd_sim.c:200-207, :266-271) */
+  int c,b,k,sofs=0;
+  free(w->pair); w->npair = w->ncell*w->nbox;
+  w->pair = (ork_pair*)calloc(w->npair>0?w->npair:1,sizeof(ork_pair));
+  k = 0;
+  for(c=0;c<w->ncell;c++) for(b=0;b<w->nbox;b++){
+    ork_pair *p = &w->pair[k++]; int i, sa = w->link[w->cell[c].link].stuff, sb = w->box[b].stuff;
+    p->cell=c; p->box=b; p->sofs=sofs; sofs += w->cell[c].nvert;
+    p->ci = w->cidef;
+    for(i=0;i<w->nci;i++)
+      if( (w->ci[i].sa==sa && w->ci[i].sb==sb) || (w->ci[i].sa==sb && w->ci[i].sb==sa) ){ p->ci = w->ci[i].ci; break; }
+  }
+  w->nslot = sofs;
+}
+int ork_world_nq(const ork_world *w){ return w->nq; }
+int ork_world_nslot(const ork_world *w){ return w->nslot; }
+int ork_world_nl(const ork_world *w){ return w->nl; }
+
+/* ------------------------------------------------------------------------------------ */
+ork_env *ork_env_new(const ork_world *w)
+{
+  ork_env *e = (ork_env*)calloc(1,sizeof *e); int nq = w->nq>0?w->nq:1, ns = w->nslot>0?w->nslot:1, i, j;
+  e->w = w; e->t = 0.0;
+  e->q=(double*)calloc(nq,8); e->qd=(double*)calloc(nq,8); e->qdd=(double*)calloc(nq,8);
+  e->min=(double*)calloc(w->nl,8);
+  /* friction pivot init {SF, q, 0} (rkfd_sim.c:157-175) */
+  e->piv_type=(int*)calloc(nq,sizeof(int)); e->piv_prev=(double*)calloc(nq,8);
+  e->tf=(double*)calloc(nq,8); e->tdrive=(double*)calloc(nq,8); e->jm=(double*)calloc(nq,8);
+  e->c_active=(int*)calloc(ns,sizeof(int)); e->c_type=(int*)calloc(ns,sizeof(int));
+  e->c_ref=(double*)calloc(3*ns,8); e->c_f=(double*)calloc(3*ns,8); e->c_pro=(double*)calloc(3*ns,8);
+  e->c_norm=(double*)calloc(3*ns,8); e->c_axis=(double*)calloc(9*ns,8); e->c_vert=(double*)calloc(3*ns,8);
+  e->c_refw=(double*)calloc(3*ns,8); e->c_vel=(double*)calloc(3*ns,8);
+  e->lw=(ork_lw*)calloc(w->nl,sizeof(ork_lw));
+  e->rn=0; e->rA=(double*)calloc(9*ns*ns,8); e->rb=(double*)calloc(3*ns,8); e->rf=(double*)calloc(3*ns,8);
+  for(i=0;i<4;i++) for(j=0;j<2;j++) e->k[i][j]=(double*)calloc(nq,8);
+  e->xs[0]=(double*)calloc(nq,8); e->xs[1]=(double*)calloc(nq,8);
+  return e;
+}
+void ork_env_free(ork_env *e)
+{
+  int i,j; if(!e) return;
+  free(e->q); free(e->qd); free(e->qdd); free(e->min); free(e->piv_type); free(e->piv_prev);
+  free(e->tf); free(e->tdrive); free(e->jm);
+  free(e->c_active); free(e->c_type); free(e->c_ref); free(e->c_f); free(e->c_pro);
+  free(e->c_norm); free(e->c_axis); free(e->c_vert); free(e->c_refw); free(e->c_vel);
+  free(e->lw); free(e->rA); free(e->rb); free(e->rf);
+  for(i=0;i<4;i++) for(j=0;j<2;j++) free(e->k[i][j]);
+  free(e->xs[0]); free(e->xs[1]); free(e);
+}
+void ork_env_set_state(ork_env *e, const double *q, const double *qd)
+{ /* rkFDChainSetDis / SetVel (rkfd_sim.c:277-287) */
+  if(q)  memcpy(e->q, q, e->w->nq*8);
+  if(qd) memcpy(e->qd,qd,e->w->nq*8);
+}
+void ork_env_get_state(const ork_env *e, double *q, double *qd, double *qdd)
+{
+  if(q)   memcpy(q,  e->q,  e->w->nq*8);
+  if(qd)  memcpy(qd, e->qd, e->w->nq*8);
+  if(qdd) memcpy(qdd,e->qdd,e->w->nq*8);
+}
+void ork_env_set_motor_input(ork_env *e, const double *u){ memcpy(e->min,u,e->w->nl*8); }
+void ork_env_get_pivot(const ork_env *e, int *type, double *prev)
+{ memcpy(type,e->piv_type,e->w->nq*sizeof(int)); memcpy(prev,e->piv_prev,e->w->nq*8); }
+void ork_env_set_pivot(ork_env *e, const int *type, const double *prev)
+{ memcpy(e->piv_type,type,e->w->nq*sizeof(int)); memcpy(e->piv_prev,prev,e->w->nq*8); }
+void ork_env_get_contact(const ork_env *e, int *active, int *type, double *ref, double *f)
+{
+  int ns = e->w->nslot;
+  if(active) memcpy(active,e->c_active,ns*sizeof(int));
+  if(type)   memcpy(type,e->c_type,ns*sizeof(int));
+  if(ref)    memcpy(ref,e->c_ref,3*ns*8);
+  if(f)      memcpy(f,e->c_f,3*ns*8);
+}
+void ork_env_set_contact(ork_env *e, const int *active, const int *type, const double *ref)
+{
+  int ns = e->w->nslot;
+  memcpy(e->c_active,active,ns*sizeof(int)); memcpy(e->c_type,type,ns*sizeof(int)); memcpy(e->c_ref,ref,3*ns*8);
+}
+double ork_env_time(const ork_env *e){ return e->t; }
+
+/* ------------------------------------------------------------------------------------ */
+/* outward pass 1: rkChainFK + rkChainSetJointVelAll + rkChainUpdateVel
+ * (call site rkfd_sim.c:298-300; [EXT A-2, A-3]) */
+static void eval_kinematics(ork_env *e, const double *q, const double *qd)
+{
+  const ork_world *w = e->w; int i, r, c;
+  for(i=0;i<w->nl;i++){
+    const ork_link *l = &w->link[i]; ork_lw *x = &e->lw[i];
+    const double *qi = q + l->qofs, *qdi = qd + l->qofs;
+    double RJ[9], pJ[3] = {0,0,0}, vJ[6] = {0,0,0,0,0,0};
+    double wp[3] = {0,0,0}, vp[3] = {0,0,0};     /* parent velocity in parent frame */
+    double wpl[3], t1[3], t2[3];
+    m3_ident(RJ); memset(x->S,0,sizeof x->S);
+    switch(l->jtype){
+    case ORK_JOINT_REVOL: { double s = sin(qi[0]), co = cos(qi[0]);
+      RJ[0]=co; RJ[1]=-s; RJ[3]=s; RJ[4]=co; x->S[6*5+0]=1.0; vJ[5]=qdi[0]; } break;
+    case ORK_JOINT_PRISM: pJ[2]=qi[0]; x->S[6*2+0]=1.0; vJ[2]=qdi[0]; break;
+    case ORK_JOINT_SPHER: aa_to_mat(qi,RJ);
+      for(r=0;r<3;r++) for(c=0;c<3;c++) x->S[6*(3+r)+c] = RJ[3*c+r];   /* S = RJ^T (angular) */
+      m3_tmulv(RJ,qdi,vJ+3); break;
+    case ORK_JOINT_FLOAT: v3_copy(qi,pJ); aa_to_mat(qi+3,RJ);
+      for(r=0;r<3;r++) for(c=0;c<3;c++){ x->S[6*r+c] = RJ[3*c+r]; x->S[6*(3+r)+3+c] = RJ[3*c+r]; }
+      m3_tmulv(RJ,qdi,vJ); m3_tmulv(RJ,qdi+3,vJ+3); break;
+    default: break;
+    }
+    m3_mul(l->org_R,RJ,x->Rrel);
+    m3_mulv(l->org_R,pJ,x->prel); v3_add(x->prel,l->org_p,x->prel);
+    if( l->parent >= 0 ){
+      const ork_lw *p = &e->lw[l->parent];
+      m3_mul(p->Rw,x->Rrel,x->Rw); m3_mulv(p->Rw,x->prel,x->pw); v3_add(x->pw,p->pw,x->pw);
+      v3_copy(p->v,vp); v3_copy(p->v+3,wp);
+    } else { memcpy(x->Rw,x->Rrel,sizeof x->Rw); v3_copy(x->prel,x->pw); }
+    /* velocity: w_i = R^T w_p + w_J ; v_i = R^T (v_p + w_p x p) + v_J */
+    m3_tmulv(x->Rrel,wp,wpl);
+    v3_cross(wp,x->prel,t1); v3_add(vp,t1,t1); m3_tmulv(x->Rrel,t1,x->v);
+    v3_add(x->v,vJ,x->v); v3_add(wpl,vJ+3,x->v+3);
+    /* velocity-product acceleration: lin = R^T( w_p x (w_p x p) ) + 2 (R^T w_p) x v_J ; ang = (R^T w_p) x w_J */
+    v3_cross(wp,x->prel,t1); v3_cross(wp,t1,t2); m3_tmulv(x->Rrel,t2,x->zeta);
+    v3_cross(wpl,vJ,t1); v3_cat(x->zeta,2.0,t1);
+    v3_cross(wpl,vJ+3,x->zeta+3);
+    /* acceleration transform X = [[R^T, -R^T [p x]],[0, R^T]] */
+    { double P[9], RtP[9], Rt[9];
+      for(r=0;r<3;r++) for(c=0;c<3;c++) Rt[3*r+c] = x->Rrel[3*c+r];
+      m3_skew(x->prel,P); m3_mul(Rt,P,RtP); memset(x->X,0,sizeof x->X);
+      for(r=0;r<3;r++) for(c=0;c<3;c++){
+        x->X[6*r+c] = Rt[3*r+c]; x->X[6*r+3+c] = -RtP[3*r+c]; x->X[6*(3+r)+3+c] = Rt[3*r+c]; } }
+    memset(x->wext,0,sizeof x->wext);
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* rkFDLinkPointWldVel (rkfd_util.c:14-24): world velocity of world point p carried by link */
+static void link_point_wld_vel(const ork_lw *x, const double *p, double *v)
+{
+  double lin[3], ang[3], r[3], t[3];
+  m3_mulv(x->Rw,x->v,lin); m3_mulv(x->Rw,x->v+3,ang);
+  v3_sub(p,x->pw,r); v3_cross(ang,r,t); v3_add(lin,t,v);
+}
+/* rkFDLinkPointWldAcc (rkfd_util.c:92-101) with [EXT] rkLinkPointAcc = a + alpha x r + w x (w x r) */
+static void link_point_wld_acc(const ork_lw *x, const double *p, double *a)
+{
+  double r[3], t[3], t2[3], al[3];
+  v3_sub(p,x->pw,r); m3_tmulv(x->Rw,r,r);
+  v3_copy(x->a,al);
+  v3_cross(x->a+3,r,t); v3_add(al,t,al);
+  v3_cross(x->v+3,r,t); v3_cross(x->v+3,t,t2); v3_add(al,t2,al);
+  m3_mulv(x->Rw,al,a);
+}
+
+/* [EXT A-10] rkCDColChkVert restricted to (moving vertex cloud) x (static box), followed by
+ * the elastic/rigid partition of rkFDCDUpdate (rkfd_cd.c:33-49).  Persistent per-vertex state:
+ * active / type / anchor _ref (box frame); new contacts start {SF, _ref=_pro}. */
+static void eval_collision(ork_env *e)
+{
+  const ork_world *w = e->w; int pi, k, a;
+  for(pi=0;pi<w->npair;pi++){
+    const ork_pair *p = &w->pair[pi]; const ork_cell *cl = &w->cell[p->cell]; const ork_box *bx = &w->box[p->box];
+    const ork_lw *x = &e->lw[cl->link];
+    for(k=0;k<cl->nvert;k++){
+      int s = p->sofs + k, amin = 0, inside = 1; double vw[3], vb[3], d[3], dep, depmin = 0, sg;
+      double nb[3] = {0,0,0}, t1b[3] = {0,0,0}, t2b[3] = {0,0,0}, prob[3];
+      m3_mulv(x->Rw,w->vert+3*(cl->vofs+k),vw); v3_add(vw,x->pw,vw);
+      v3_sub(vw,bx->p,d); m3_tmulv(bx->R,d,vb);
+      for(a=0;a<3;a++){
+        dep = bx->half[a] - fabs(vb[a]);
+        if( dep <= -ORK_TOL ) inside = 0;
+        if( a==0 || dep < depmin ){ depmin = dep; amin = a; }
+      }
+      v3_copy(vw,e->c_vert+3*s);
+      if( !inside ){ e->c_active[s] = 0; continue; }
+      sg = vb[amin] >= 0 ? 1.0 : -1.0;
+      nb[amin] = sg; t1b[(amin+1)%3] = 1.0; t2b[(amin+2)%3] = sg;
+      v3_copy(vb,prob); prob[amin] = sg*bx->half[amin];
+      m3_mulv(bx->R,nb,e->c_norm+3*s);
+      m3_mulv(bx->R,nb,e->c_axis+9*s); m3_mulv(bx->R,t1b,e->c_axis+9*s+3); m3_mulv(bx->R,t2b,e->c_axis+9*s+6);
+      v3_copy(prob,e->c_pro+3*s);
+      if( !e->c_active[s] ){ e->c_active[s] = 1; e->c_type[s] = ORK_SF; v3_copy(prob,e->c_ref+3*s); }
+      m3_mulv(bx->R,e->c_ref+3*s,e->c_refw+3*s); v3_add(e->c_refw+3*s,bx->p,e->c_refw+3*s);
+    }
+  }
+}
+
+/* rkFDKineticFrictionWeight (rkfd_util.c:193-196) */
+static double kinetic_friction_weight(double w, double fs){ return 1.0 - exp(-1.0*w*fs); }
+
+/* rkFDContactForcePushWrench (rkfd_util.c:268-282); the static partner's wrench is dropped */
+static void push_wrench(ork_env *e, int link, const double *vert, const double *f)
+{
+  ork_lw *x = &e->lw[link]; double pos[3], fl[3], n[3];
+  v3_sub(vert,x->pw,pos); m3_tmulv(x->Rw,pos,pos);     /* zXform3DInv */
+  m3_tmulv(x->Rw,f,fl);
+  v3_cross(pos,fl,n);                                   /* [EXT A-4] wrench at origin: (f, pos x f) */
+  v3_add(x->wext,fl,x->wext); v3_add(x->wext+3,n,x->wext+3);
+}
+
+/* rkFDContactForceModifyFriction (rkfd_util.c:239-266); v passed by value */
+static void modify_friction(ork_env *e, const ork_cinfo *ci, int s, const double *vin, int do_up_ref)
+{
+  double *f = e->c_f+3*s, *ax = e->c_axis+9*s, v[3], fn, fs, vs, mu;
+  v3_copy(vin,v);
+  fn = v3_dot(f,ax);
+  fs = sqrt( v3_dot(f,ax+3)*v3_dot(f,ax+3) + v3_dot(f,ax+6)*v3_dot(f,ax+6) );
+  mu = e->c_type[s]==ORK_SF ? ci->SF : ci->KF;
+  if( !(fabs(fs) < ORK_TOL) && fs > mu*fn ){
+    v3_cat(v,-v3_dot(v,ax),ax);
+    vs = v3_norm(v);
+    f[0]=fn*ax[0]; f[1]=fn*ax[1]; f[2]=fn*ax[2];
+    if( !(fabs(vs) < ORK_TOL) ){
+      v[0]/=vs; v[1]/=vs; v[2]/=vs;
+      v3_cat(f, -kinetic_friction_weight(e->w->friction_weight,vs)*ci->KF*fn, v);
+    }
+    if( do_up_ref ){ e->c_type[s] = ORK_KF; v3_copy(e->c_pro+3*s,e->c_ref+3*s); }
+  } else {
+    if( do_up_ref ) e->c_type[s] = ORK_SF;   /* rkFDUpdateRefSlide: slide mode out of scope */
+  }
+}
+
+/* rkFDSolverPenalty (rkfd_penalty.c:11-31) */
+static void solver_penalty(ork_env *e, int do_up_ref)
+{
+  const ork_world *w = e->w; int pi, k;
+  for(pi=0;pi<w->npair;pi++){
+    const ork_pair *p = &w->pair[pi]; const ork_cell *cl = &w->cell[p->cell];
+    if( p->ci.type != ORK_CONTACT_ELASTIC ) continue;
+    for(k=0;k<cl->nvert;k++){
+      int s = p->sofs+k; double d[3], vr[3], *f = e->c_f+3*s;
+      if( !e->c_active[s] ) continue;
+      v3_sub(e->c_vert+3*s,e->c_refw+3*s,d);
+      link_point_wld_vel(&e->lw[cl->link],e->c_vert+3*s,vr);    /* rkFDChainPointRelativeVel, STAT partner = 0 */
+      f[0] = -p->ci.E*d[0]; f[1] = -p->ci.E*d[1]; f[2] = -p->ci.E*d[2];
+      v3_cat(f, -1.0*(p->ci.V + p->ci.E*w->dt), vr);
+      if( v3_dot(f,e->c_axis+9*s) < 0.0 ) continue;
+      modify_friction(e,&p->ci,s,vr,do_up_ref);
+      push_wrench(e,cl->link,e->c_vert+3*s,f);
+    }
+  }
+}
+
+/* [EXT A-6] DC / torque motor */
+static void motor_eval(const ork_link *l, double in, double qd, double *tin, double *treg, double *jm)
+{
+  double ecl = in < l->mmin ? l->mmin : ( in > l->mmax ? l->mmax : in );
+  switch(l->mtype){
+  case ORK_MOTOR_DC:
+    *tin = l->mgear*l->mk*l->madm*ecl;
+    *treg = (l->mgear*l->mk)*(l->mgear*l->mk)*l->madm*qd;
+    *jm = l->mgear*l->mgear*(l->mrotor+l->mgearin); break;
+  case ORK_MOTOR_TRQ: *tin = ecl; *treg = 0; *jm = 0; break;
+  default: *tin = 0; *treg = 0; *jm = 0; break;
+  }
+}
+
+/* rkFDJointFriction (rkfd_util.c:366-387) + rkFDJointFrictionRevolDC (:330-364) +
+ * rkFDJointFrictionAll (:318-328); also evaluates the motor driving torque used by the ABA */
+static void joint_friction(ork_env *e, const double *q, const double *qd, int do_up_ref)
+{
+  const ork_world *w = e->w; int i, j;
+  for(i=0;i<w->nl;i++){
+    const ork_link *l = &w->link[i];
+    if( l->ndof == 1 ){
+      int o = l->qofs; double tin, treg, jm, tf, fmax, v = qd[o];
+      motor_eval(l,e->min[i],v,&tin,&treg,&jm);
+      e->tdrive[o] = tin - treg; e->jm[o] = jm;
+      if( l->mtype == ORK_MOTOR_DC ){
+        tf = jm; tf *= -v / w->dt; tf -= tin; tf += treg; tf += e->piv_prev[o];
+        if( e->piv_type[o] == ORK_SF ) fmax = l->sfriction;
+        else{ /* [EXT A-7] rkJointGetKFriction */
+          double sg = v > 0 ? 1.0 : ( v < 0 ? -1.0 : 0.0 );
+          fmax = -l->stiffness*q[o] - l->viscosity*v - l->coulomb*sg;
+        }
+        fmax = fabs(fmax);
+        if( fabs(tf) > fmax ){
+          tf = tf > 0 ? fmax : -fmax;
+          if( do_up_ref ) e->piv_type[o] = ORK_KF;
+        } else if( do_up_ref ) e->piv_type[o] = ORK_SF;
+        e->tf[o] = tf;
+      }
+      /* 1-DoF joints without a DC motor: friction is never set (rkfd_util.c:379-383) -> stays 0 */
+    } else {
+      /* multi-DoF: kf_i (1 - exp(-w |v_i|)); spherical/float joints carry no passive torque -> 0 */
+      for(j=0;j<l->ndof;j++){ e->tf[l->qofs+j] = 0.0*kinetic_friction_weight(w->friction_weight,fabs(qd[l->qofs+j]));
+                              e->tdrive[l->qofs+j] = 0.0; e->jm[l->qofs+j] = 0.0; }
+    }
+  }
+}
+
+/* rkFDUpdateJointPrevDrivingTrq (rkfd_util.c:289-311) */
+static void update_prev_driving_trq(ork_env *e)
+{
+  int i; for(i=0;i<e->w->nq;i++) e->piv_prev[i] = e->tdrive[i] + e->tf[i];
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* dense 6x6 helpers for the ABA */
+static void m6_mulv(const double *m, const double *x, double *y)
+{ double t[6]; int r,c; for(r=0;r<6;r++){ t[r]=0; for(c=0;c<6;c++) t[r]+=m[6*r+c]*x[c]; } memcpy(y,t,sizeof t); }
+static void m6_tmulv(const double *m, const double *x, double *y)
+{ double t[6]; int r,c; for(r=0;r<6;r++){ t[r]=0; for(c=0;c<6;c++) t[r]+=m[6*c+r]*x[c]; } memcpy(y,t,sizeof t); }
+
+/* in-place inverse of a symmetric positive definite n x n (n<=6) matrix stored with stride 6 */
+static void spd_inverse(double *a, int n)
+{
+  double L[36], Li[36]; int i,j,k;
+  memset(L,0,sizeof L); memset(Li,0,sizeof Li);
+  for(j=0;j<n;j++){
+    double s = a[6*j+j];
+    for(k=0;k<j;k++) s -= L[6*j+k]*L[6*j+k];
+    L[6*j+j] = sqrt(s);
+    for(i=j+1;i<n;i++){
+      s = a[6*i+j];
+      for(k=0;k<j;k++) s -= L[6*i+k]*L[6*j+k];
+      L[6*i+j] = s / L[6*j+j];
+    }
+  }
+  for(j=0;j<n;j++){
+    Li[6*j+j] = 1.0 / L[6*j+j];
+    for(i=j+1;i<n;i++){
+      double s = 0; for(k=j;k<i;k++) s -= L[6*i+k]*Li[6*k+j];
+      Li[6*i+j] = s / L[6*i+i];
+    }
+  }
+  for(i=0;i<n;i++) for(j=0;j<n;j++){
+    double s = 0; for(k=(i>j?i:j);k<n;k++) s += Li[6*k+i]*Li[6*k+j];
+    a[6*i+j] = s;
+  }
+}
+
+/* [EXT A-4] rkChainUpdateABI: init + inward articulated-inertia pass + outward acceleration pass
+ * (call sites rkfd_sim.c:509-520, rkfd_util.c:156) */
+static void aba_backward(ork_env *e)
+{
+  const ork_world *w = e->w; int i, r, c, k, j;
+  for(i=0;i<w->nl;i++){
+    const ork_link *l = &w->link[i]; ork_lw *x = &e->lw[i];
+    double *om = x->v+3, t1[3], t2[3], Io[9], fg[3], ng[3], gl[3], gw[3] = {0,0,-ORK_G};
+    memcpy(x->IA,l->M,sizeof x->IA);
+    /* bias: ( m w x (w x c) ; w x (Io w) ) */
+    v3_cross(om,l->com,t1); v3_cross(om,t1,t2);
+    x->pA[0]=l->mass*t2[0]; x->pA[1]=l->mass*t2[1]; x->pA[2]=l->mass*t2[2];
+    for(r=0;r<3;r++) for(c=0;c<3;c++) Io[3*r+c] = l->M[6*(3+r)+3+c];
+    m3_mulv(Io,om,t1); v3_cross(om,t1,x->pA+3);
+    /* gravity as a force at the COM */
+    m3_tmulv(x->Rw,gw,gl); fg[0]=l->mass*gl[0]; fg[1]=l->mass*gl[1]; fg[2]=l->mass*gl[2];
+    v3_cross(l->com,fg,ng);
+    for(r=0;r<3;r++){ x->pA[r] -= fg[r] + x->wext[r]; x->pA[3+r] -= ng[r] + x->wext[3+r]; }
+  }
+  for(i=w->nl-1;i>=0;i--){
+    const ork_link *l = &w->link[i]; ork_lw *x = &e->lw[i]; int nd = l->ndof;
+    double pz[6], Ia[36], pa[6], t6[6];
+    m6_mulv(x->IA,x->zeta,pz); for(r=0;r<6;r++) pz[r] += x->pA[r];     /* p' = pA + IA zeta */
+    memcpy(Ia,x->IA,sizeof Ia); memcpy(pa,pz,sizeof pa);
+    if( nd > 0 ){
+      /* U = IA S (6 x nd) ; D = S^T U + Jm ; u = tau - S^T p' */
+      for(r=0;r<6;r++) for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += x->IA[6*r+k]*x->S[6*k+j]; x->U[6*r+j]=s; }
+      memset(x->Dinv,0,sizeof x->Dinv);
+      for(r=0;r<nd;r++) for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += x->S[6*k+r]*x->U[6*k+j]; x->Dinv[6*r+j]=s; }
+      for(j=0;j<nd;j++) x->Dinv[6*j+j] += e->jm[l->qofs+j];
+      if( nd == 1 ) x->Dinv[0] = 1.0/x->Dinv[0]; else spd_inverse(x->Dinv,nd);
+      for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += x->S[6*k+j]*pz[k];
+        x->u[j] = e->tdrive[l->qofs+j] + e->tf[l->qofs+j] - s; }
+      /* Ia = IA - U Dinv U^T ; pa = p' + U Dinv u */
+      for(j=0;j<nd;j++){ t6[j]=0; for(k=0;k<nd;k++) t6[j] += x->Dinv[6*j+k]*x->u[k]; }
+      for(r=0;r<6;r++) for(j=0;j<nd;j++) pa[r] += x->U[6*r+j]*t6[j];
+      for(r=0;r<6;r++) for(c=0;c<6;c++){ double s=0;
+        for(j=0;j<nd;j++) for(k=0;k<nd;k++) s += x->U[6*r+j]*x->Dinv[6*j+k]*x->U[6*c+k];
+        Ia[6*r+c] -= s; }
+    }
+    if( l->parent >= 0 ){
+      ork_lw *p = &e->lw[l->parent]; double T[36];
+      /* IA_p += X^T Ia X ; pA_p += X^T pa */
+      for(r=0;r<6;r++) for(c=0;c<6;c++){ double s=0; for(k=0;k<6;k++) s += Ia[6*r+k]*x->X[6*k+c]; T[6*r+c]=s; }
+      for(r=0;r<6;r++) for(c=0;c<6;c++){ double s=0; for(k=0;k<6;k++) s += x->X[6*k+r]*T[6*k+c]; p->IA[6*r+c]+=s; }
+      m6_tmulv(x->X,pa,t6); for(r=0;r<6;r++) p->pA[r] += t6[r];
+    }
+  }
+}
+/* outward acceleration pass; du = optional per-dof increment of u (cached-ABA probes) */
+static void aba_forward(ork_env *e, double *qdd, int use_du)
+{
+  const ork_world *w = e->w; int i, j, k, r;
+  for(i=0;i<w->nl;i++){
+    const ork_link *l = &w->link[i]; ork_lw *x = &e->lw[i]; int nd = l->ndof;
+    double ap[6] = {0,0,0,0,0,0}, rhs[6], qa[6] = {0,0,0,0,0,0};
+    if( l->parent >= 0 ) m6_mulv(x->X,e->lw[l->parent].a,ap);
+    for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += x->U[6*k+j]*ap[k];
+      rhs[j] = x->u[j] + ( use_du ? x->du[j] : 0.0 ) - s; }
+    for(j=0;j<nd;j++){ qa[j]=0; for(k=0;k<nd;k++) qa[j] += x->Dinv[6*j+k]*rhs[k]; }
+    for(r=0;r<6;r++){ double s = ap[r] + x->zeta[r]; for(j=0;j<nd;j++) s += x->S[6*r+j]*qa[j]; x->a[r] = s; }
+    if( qdd ) for(j=0;j<nd;j++) qdd[l->qofs+j] = qa[j];
+  }
+}
+
+/* [EXT A-5] rkChainUpdateCachedABIPair: unit test wrench (f at world point vert) on `link`;
+ * bias-only inward propagation with the cached articulated inertias, then the outward pass */
+static void aba_probe(ork_env *e, int link, const double *vert, const double *fw)
+{
+  const ork_world *w = e->w; int i, j, k, r; ork_lw *x = &e->lw[link]; double pos[3], fl[3], n[3];
+  for(i=0;i<w->nl;i++){ memset(e->lw[i].du,0,sizeof e->lw[i].du); memset(e->lw[i].dp,0,sizeof e->lw[i].dp); }
+  v3_sub(vert,x->pw,pos); m3_tmulv(x->Rw,pos,pos); m3_tmulv(x->Rw,fw,fl); v3_cross(pos,fl,n);
+  for(r=0;r<3;r++){ x->dp[r] = -fl[r]; x->dp[3+r] = -n[r]; }
+  for(i=link;i>=0;i=w->link[i].parent){
+    const ork_link *l = &w->link[i]; ork_lw *y = &e->lw[i]; int nd = l->ndof; double pa[6], t6[6];
+    memcpy(pa,y->dp,sizeof pa);
+    for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += y->S[6*k+j]*y->dp[k]; y->du[j] = -s; }
+    for(j=0;j<nd;j++){ t6[j]=0; for(k=0;k<nd;k++) t6[j] += y->Dinv[6*j+k]*y->du[k]; }
+    for(r=0;r<6;r++) for(j=0;j<nd;j++) pa[r] += y->U[6*r+j]*t6[j];
+    if( l->parent < 0 ) break;
+    m6_tmulv(y->X,pa,t6); for(r=0;r<6;r++) e->lw[l->parent].dp[r] += t6[r];
+  }
+  aba_forward(e,NULL,1);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* zLESolveMP restatement for a symmetric matrix: x = pinv(a) b through a cyclic Jacobi
+ * eigen-decomposition ([EXT A-14]; the KKT matrix of rkfd_opt_qp.c:82-106 is symmetric) */
+void ork_le_solve_mp_sym(int n, const double *a, const double *b, double *x)
+{
+  double *A = (double*)malloc(n*n*8), *V = (double*)malloc(n*n*8); int i,j,k,sweep; double lmax = 0;
+  memcpy(A,a,n*n*8);
+  for(i=0;i<n;i++) for(j=0;j<n;j++) V[n*i+j] = i==j;
+  for(sweep=0;sweep<60;sweep++){
+    double off = 0; for(i=0;i<n;i++) for(j=i+1;j<n;j++) off += A[n*i+j]*A[n*i+j];
+    if( off < 1e-300 ) break;
+    for(i=0;i<n;i++) for(j=i+1;j<n;j++){
+      double apq = A[n*i+j], th, t, c, s;
+      if( fabs(apq) < 1e-300 ) continue;
+      th = (A[n*j+j]-A[n*i+i])/(2.0*apq);
+      t = (th>=0?1.0:-1.0)/(fabs(th)+sqrt(th*th+1.0)); c = 1.0/sqrt(t*t+1.0); s = t*c;
+      for(k=0;k<n;k++){ double akp=A[n*k+i], akq=A[n*k+j]; A[n*k+i]=c*akp-s*akq; A[n*k+j]=s*akp+c*akq; }
+      for(k=0;k<n;k++){ double apk=A[n*i+k], aqk=A[n*j+k]; A[n*i+k]=c*apk-s*aqk; A[n*j+k]=s*apk+c*aqk; }
+      for(k=0;k<n;k++){ double vkp=V[n*k+i], vkq=V[n*k+j]; V[n*k+i]=c*vkp-s*vkq; V[n*k+j]=s*vkp+c*vkq; }
+    }
+  }
+  for(i=0;i<n;i++) if( fabs(A[n*i+i]) > lmax ) lmax = fabs(A[n*i+i]);
+  for(i=0;i<n;i++) x[i] = 0;
+  for(k=0;k<n;k++){
+    double lam = A[n*k+k], s = 0;
+    if( fabs(lam) <= 1.0e-11*lmax ) continue;
+    for(i=0;i<n;i++) s += V[n*i+k]*b[i];
+    s /= lam;
+    for(i=0;i<n;i++) x[i] += s*V[n*i+k];
+  }
+  free(A); free(V);
+}
+
+/* rkFDQPSolveASM (rkfd_opt_qp.c:43-181): min 1/2 x^T Q x + c^T x  s.t.  a x >= b.
+ * `cond` is always row.x here: the Vert callback (rkfd_vert.c:246-250) is the same dot product
+ * restricted to the only three non-zero entries of the row. */
+static double qp_cond(int n, const double *a, const double *x, int i)
+{ double s = 0; int j; for(j=0;j<n;j++) s += a[n*i+j]*x[j]; return s; }
+#define ORK_QP_ASM_TOL 1.0e-8
+#define ORK_QP_MAX_ITER 10000
+int ork_qp_solve_asm(int n, int m, const double *q, const double *c, const double *a,
+                     const double *b, const double *init, double *ans, int *idx)
+{
+  int nmax = n+m, i, j, k, ma, nm, iter = 0, nhist = 0, caph = 16;
+  double *qa = (double*)malloc(nmax*nmax*8), *xy = (double*)malloc(nmax*8), *cb = (double*)malloc(nmax*8);
+  double *d = (double*)malloc(n*8), tempd, tempd2, objv;
+  int *hist = (int*)malloc(caph*(m>0?m:1)*sizeof(int)); double *hmin = (double*)malloc(caph*8);
+  for(i=0;i<n;i++) ans[i] = init ? init[i] : 0.0;
+  /* _rkFDQPSolveASMInitIndex (rkfd_opt_qp.c:27-40) */
+  for(ma=0,i=0;i<m;i++){ idx[i] = fabs(qp_cond(n,a,ans,i)-b[i]) < ORK_TOL; ma += idx[i]; }
+  for(;;){
+    int stepped = 0;
+    if( ++iter > ORK_QP_MAX_ITER ) break;    /* safety net; the reference loop is unbounded */
+    nm = n + ma;
+    for(i=0;i<n;i++) for(j=0;j<n;j++) qa[nm*i+j] = -q[n*i+j];
+    for(k=0,j=n;j<nm;j++){ while( k<m && !idx[k] ) k++; for(i=0;i<n;i++){ qa[nm*i+j] = a[n*k+i]; qa[nm*j+i] = a[n*k+i]; } k++; }
+    for(i=n;i<nm;i++) for(j=n;j<nm;j++) qa[nm*i+j] = 0.0;
+    for(i=0;i<n;i++) cb[i] = c[i];
+    for(k=0,i=n;i<nm;i++){ while( k<m && !idx[k] ) k++; cb[i] = b[k]; k++; }
+    ork_le_solve_mp_sym(nm,qa,cb,xy);
+    for(i=0;i<n;i++) if( !(fabs(xy[i]-ans[i]) < ORK_TOL) ){ stepped = 1; break; }
+    if( !stepped ){
+      int neg = 0;
+      for(i=0;i<n;i++) ans[i] = xy[i];
+      for(i=0;i<ma;i++) if( xy[n+i] < 0 ){ neg = 1; break; }
+      if( !neg ) break;                        /* optimal */
+      tempd = xy[n]; for(i=1;i<ma;i++) if( xy[n+i] < tempd ) tempd = xy[n+i];
+      for(k=0,i=0;i<m;i++) if( idx[i] ){
+        if( fabs(xy[k+n]-tempd) < ORK_QP_ASM_TOL ){ idx[i] = 0; }
+        k++; }
+      for(ma=0,i=0;i<m;i++) ma += idx[i];
+      continue;
+    }
+    /* STEP2: feasible direction and step length */
+    for(i=0;i<n;i++) d[i] = xy[i]-ans[i];
+    tempd = 1.0;
+    for(i=0;i<m;i++){
+      tempd2 = qp_cond(n,a,d,i);
+      if( idx[i]==0 && tempd2 < 0 ){ tempd2 = ( b[i] - qp_cond(n,a,ans,i) ) / tempd2; if( tempd2 < tempd ) tempd = tempd2; }
+    }
+    for(i=0;i<n;i++) ans[i] += tempd*d[i];
+    for(i=0;i<m;i++) if( idx[i]==0 && fabs(qp_cond(n,a,ans,i)-b[i]) < ORK_TOL ){ idx[i] = 1; ma++; }
+    /* anti-cycling (rkfd_opt_qp.c:152-171) */
+    objv = 0; for(i=0;i<n;i++){ double s=0; for(j=0;j<n;j++) s += q[n*i+j]*ans[j]; objv += 0.5*ans[i]*s + c[i]*ans[i]; }
+    { int end = 0;
+      for(k=0;k<nhist;k++){ int same = 1; for(i=0;i<m;i++) if( idx[i] != hist[m*k+i] ){ same = 0; break; }
+        if( !same ) continue;
+        if( fabs(hmin[k]/objv - 1.0) > ORK_QP_ASM_TOL ) continue;
+        end = 1; break; }
+      if( end ) break; }
+    if( nhist == caph ){ caph *= 2; hist = (int*)realloc(hist,caph*(m>0?m:1)*sizeof(int)); hmin = (double*)realloc(hmin,caph*8); }
+    for(i=0;i<m;i++) hist[m*nhist+i] = idx[i];
+    hmin[nhist++] = objv;
+  }
+  free(qa); free(xy); free(cb); free(d); free(hist); free(hmin);
+  return iter;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* rigid contact: Vert (rkfd_vert.c:327-336) and MLCP (rkfd_mlcp.c:287-297) */
+static void solver_rigid(ork_env *e, int do_up_ref)
+{
+  const ork_world *w = e->w; int pi, k, N = 0, n, i, j, col;
+  int *slot = (int*)malloc((w->nslot>0?w->nslot:1)*sizeof(int)), *plink = (int*)malloc((w->nslot>0?w->nslot:1)*sizeof(int));
+  const ork_cinfo **pci = (const ork_cinfo**)malloc((w->nslot>0?w->nslot:1)*sizeof(void*));
+  double *A = e->rA, *b = e->rb, *f = e->rf, dt = w->dt;
+  /* _rkFDSolverCountContacts (rkfd_vert.c:22-29): contacts in (pair, vertex) order */
+  for(pi=0;pi<w->npair;pi++){
+    const ork_pair *p = &w->pair[pi]; const ork_cell *cl = &w->cell[p->cell];
+    if( p->ci.type != ORK_CONTACT_RIGID ) continue;
+    for(k=0;k<cl->nvert;k++) if( e->c_active[p->sofs+k] ){ slot[N]=p->sofs+k; plink[N]=cl->link; pci[N]=&p->ci; N++; }
+  }
+  e->rn = 0;
+  if( N == 0 ){ free(slot); free(plink); free(pci); return; }
+  n = 3*N; e->rn = n;
+  /* rkFDUpdateAccBias (rkfd_util.c:149-161): full ABA with the friction / penalty wrenches, save */
+  aba_backward(e); aba_forward(e,NULL,0);
+  for(i=0;i<w->nl;i++) memcpy(e->lw[i].a0,e->lw[i].a,sizeof e->lw[i].a);
+  /* _rkFDSolverBiasAcc (rkfd_vert.c:107-123 / rkfd_mlcp.c:58-74) */
+  for(k=0;k<N;k++){ double av[3]; link_point_wld_acc(&e->lw[plink[k]],e->c_vert+3*slot[k],av);
+    for(i=0;i<3;i++) b[3*k+i] = v3_dot(e->c_axis+9*slot[k]+3*i,av); }
+  /* _rkFDSolverRelationAccForce (rkfd_vert.c:153-185 / rkfd_mlcp.c:104-142): 3N cached-ABA probes */
+  for(k=0;k<N;k++) for(i=0;i<3;i++){
+    col = 3*k+i;
+    aba_probe(e,plink[k],e->c_vert+3*slot[k],e->c_axis+9*slot[k]+3*i);
+    for(j=0;j<N;j++){ double av[3]; int ii; link_point_wld_acc(&e->lw[plink[j]],e->c_vert+3*slot[j],av);
+      for(ii=0;ii<3;ii++) A[n*(3*j+ii)+col] = v3_dot(e->c_axis+9*slot[j]+3*ii,av) - b[3*j+ii]; }
+  }
+  /* rkFDChainRestoreABIAccBiasPair */
+  for(i=0;i<w->nl;i++) memcpy(e->lw[i].a,e->lw[i].a0,sizeof e->lw[i].a);
+  /* _rkFDSolverBiasVel (rkfd_vert.c:189-206 / rkfd_mlcp.c:146-162) */
+  for(i=0;i<n;i++) b[i] *= dt;
+  for(k=0;k<N;k++){ double *vel = e->c_vel+3*slot[k];
+    link_point_wld_vel(&e->lw[plink[k]],e->c_vert+3*slot[k],vel);
+    for(i=0;i<3;i++) b[3*k+i] += v3_dot(vel,e->c_axis+9*slot[k]+3*i); }
+
+  if( w->solver == ORK_SOLVER_MLCP ){
+    int cnt; double ff[2], fs, fnorm;
+    /* _rkFDSolverRelaxationCompensation (rkfd_mlcp.c:164-188) */
+    for(k=0;k<N;k++){ double d[3], mu; int s = slot[k];
+      v3_sub(e->c_vert+3*s,e->c_refw+3*s,d);
+      for(i=0;i<3;i++) A[n*(3*k+i)+3*k+i] += pci[k]->L;
+      mu = e->c_type[s]==ORK_SF ? pci[k]->SF : pci[k]->KF;
+      b[3*k  ] += pci[k]->K      * v3_dot(d,e->c_axis+9*s);
+      b[3*k+1] += pci[k]->K * mu * v3_dot(d,e->c_axis+9*s+3);
+      b[3*k+2] += pci[k]->K * mu * v3_dot(d,e->c_axis+9*s+6); }
+    /* _rkFDSolverMLCP (rkfd_mlcp.c:190-249): projected Gauss-Seidel.  The friction sweep reads
+     * rows offset+0 and offset+1 (NOT +1,+2) exactly as the reference does (:219-225). */
+    for(i=0;i<n;i++) f[i] = 0.0;
+    for(cnt=0;cnt<w->max_iter;cnt++){
+      for(k=0;k<N;k++){ int o = 3*k; double s = 0; for(j=0;j<n;j++) s += A[n*o+j]*f[j];
+        ff[0] = -( b[o] + s - A[n*o+o]*f[o] ) / A[n*o+o];
+        f[o] = ff[0] < ORK_TOL ? 0.0 : ff[0]; }
+      for(k=0;k<N;k++){ int o = 3*k;
+        for(i=0;i<2;i++){
+          if( fabs(A[n*(o+i)+o+i]) < ORK_TOL ) ff[i] = 0;
+          else{ double s = 0; for(j=0;j<n;j++) s += A[n*(o+i)+j]*f[j];
+            ff[i] = -( b[o+i] + s - A[n*(o+i)+o+i]*f[o+i] ) / A[n*(o+i)+o+i]; }
+        }
+        fnorm = ff[0]*ff[0] + ff[1]*ff[1];
+        fs = e->c_type[slot[k]]==ORK_SF ? (pci[k]->SF*f[o])*(pci[k]->SF*f[o]) : (pci[k]->KF*f[o])*(pci[k]->KF*f[o]);
+        if( fnorm < ORK_TOL || fs < ORK_TOL ){ f[o+1] = 0.0; f[o+2] = 0.0; }
+        else if( fnorm > fs ){ fs /= fnorm; f[o+1] = ff[0]*fs; f[o+2] = ff[1]*fs; }
+        else { f[o+1] = ff[0]; f[o+2] = ff[1]; }
+      }
+    }
+    for(i=0;i<n;i++) f[i] /= dt;
+    /* _rkFDSolverSetForce (rkfd_mlcp.c:252-284): commits the friction type regardless of doUpRef and
+     * tests WORLD components of f (f.e[0] as "normal") - both mirrored */
+    for(k=0;k<N;k++){ int s = slot[k]; double *fw = e->c_f+3*s, fn, fss, mu;
+      fw[0]=fw[1]=fw[2]=0; for(i=0;i<3;i++) v3_cat(fw,f[3*k+i],e->c_axis+9*s+3*i);
+      push_wrench(e,plink[k],e->c_vert+3*s,fw);
+      fn = fw[0]; fss = sqrt(fw[1]*fw[1]+fw[2]*fw[2]);
+      mu = e->c_type[s]==ORK_SF ? pci[k]->SF : pci[k]->KF;
+      if( fss > mu*fn - ORK_TOL ){ e->c_type[s] = ORK_KF; v3_copy(e->c_pro+3*s,e->c_ref+3*s); }
+      else e->c_type[s] = ORK_SF; }
+  } else {
+    /* Vert: _rkFDSolverFrictionConstraint (rkfd_vert.c:73-103), _rkFDSolverCompensateDepth (:208-232),
+     * _rkFDSolverQP (:258-283) */
+    int pyr = w->pyramid, m = pyr*N; double *nf = (double*)calloc(m*n,8), *dz = (double*)calloc(m,8);
+    double *Q = (double*)malloc(n*n*8), *c = (double*)malloc(n*8), *c2 = (double*)malloc(n*8), *init = (double*)calloc(n,8);
+    int *idx = (int*)calloc(m,sizeof(int));
+    for(k=0;k<N;k++){ double fric = ( e->c_type[slot[k]]==ORK_KF ? pci[k]->KF : pci[k]->SF ) * w->sc_table[1][0];
+      for(i=0;i<pyr;i++){ nf[n*(pyr*k+i)+3*k] = fric; nf[n*(pyr*k+i)+3*k+1] = w->sc_table[0][i]; nf[n*(pyr*k+i)+3*k+2] = w->sc_table[1][i]; } }
+    for(k=0;k<N;k++){ double d[3], fric, K; int s = slot[k];
+      v3_sub(e->c_vert+3*s,e->c_refw+3*s,d);
+      fric = e->c_type[s]==ORK_KF ? pci[k]->KF : pci[k]->SF; K = pci[k]->K;
+      c[3*k  ] = b[3*k  ] + K        * v3_dot(d,e->c_axis+9*s);
+      c[3*k+1] = b[3*k+1] + K * fric * v3_dot(d,e->c_axis+9*s+3);
+      c[3*k+2] = b[3*k+2] + K * fric * v3_dot(d,e->c_axis+9*s+6); }
+    for(i=0;i<n;i++) for(j=0;j<n;j++){ double s=0; int kk; for(kk=0;kk<n;kk++) s += A[n*kk+i]*A[n*kk+j]; Q[n*i+j]=s; }
+    for(i=0;i<n;i++){ double s=0; for(j=0;j<n;j++) s += A[n*j+i]*c[j]; c2[i]=s; }
+    for(k=0;k<N;k++) for(i=0;i<3;i++) Q[n*(3*k+i)+3*k+i] += pci[k]->L;
+    for(k=0;k<N;k++) init[3*k] = 1.0;          /* _rkFDSolverQPASMInit (rkfd_vert.c:234-244) */
+    ork_qp_solve_asm(n,m,Q,c2,nf,dz,init,f,idx);
+    for(i=0;i<n;i++) f[i] /= dt;
+    /* _rkFDSolverSetForce (rkfd_vert.c:286-324) */
+    for(k=0;k<N;k++){ int s = slot[k], flag = 0; double *fw = e->c_f+3*s;
+      fw[0]=fw[1]=fw[2]=0; for(i=0;i<3;i++) v3_cat(fw,f[3*k+i],e->c_axis+9*s+3*i);
+      push_wrench(e,plink[k],e->c_vert+3*s,fw);
+      if( do_up_ref ){
+        for(i=0;i<pyr;i++) if( idx[pyr*k+i] ){ flag = 1; break; }
+        if( flag ){ e->c_type[s] = ORK_KF; v3_copy(e->c_pro+3*s,e->c_ref+3*s); }
+        else e->c_type[s] = ORK_SF; } }
+    free(nf); free(dz); free(Q); free(c); free(c2); free(init); free(idx);
+  }
+  free(slot); free(plink); free(pci);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* one dynamics evaluation: _rkFDUpdate body / _rkFDUpdateRef (rkfd_sim.c:525-549) */
+static void eval_dynamics(ork_env *e, const double *q, const double *qd, double *qdd, int do_up_ref)
+{
+  const ork_world *w = e->w; int pi, has_elastic = 0, has_rigid = 0, k;
+  memset(qdd,0,(w->nq>0?w->nq:1)*8);                  /* zVecZero(acc) */
+  eval_kinematics(e,q,qd);                            /* _rkFDConnectJointState (:290-302) */
+  /* _rkFDUpdateReset (:445-453): wrench lists cleared in eval_kinematics */
+  eval_collision(e);                                  /* _rkFDUpdateCD (:466-471) */
+  for(pi=0;pi<w->npair;pi++){ const ork_pair *p = &w->pair[pi]; int col = 0;
+    for(k=0;k<w->cell[p->cell].nvert;k++) col |= e->c_active[p->sofs+k];
+    if( col ){ if( p->ci.type==ORK_CONTACT_ELASTIC ) has_elastic = 1; else has_rigid = 1; } }
+  /* solver->_update (rkfd_vert.c:380-388 / rkfd_mlcp.c:335-343) */
+  joint_friction(e,q,qd,do_up_ref);
+  if( has_elastic ) solver_penalty(e,do_up_ref);
+  e->rn = 0;
+  if( has_rigid && w->solver != ORK_SOLVER_VOLUME ) solver_rigid(e,do_up_ref);
+  /* _rkFDUpdateAcc (:502-523) */
+  aba_backward(e); aba_forward(e,qdd,0);
+  if( do_up_ref ) update_prev_driving_trq(e);         /* solver->_update_ref (:548) */
+}
+
+void ork_env_eval(ork_env *e, int do_up_ref){ eval_dynamics(e,e->q,e->qd,e->qdd,do_up_ref); }
+void ork_env_update_init(ork_env *e){ eval_dynamics(e,e->q,e->qd,e->qdd,1); }
+
+/* rkFDODECatDefault (rkfd_sim.c:306-320) + [EXT] rkChainCatJointDisAll: q <- q (+) k v */
+static void cat_dis(const ork_world *w, double *q, double k, const double *v)
+{
+  int i, j;
+  for(i=0;i<w->nl;i++){ const ork_link *l = &w->link[i]; double *qi = q+l->qofs; const double *vi = v+l->qofs;
+    switch(l->jtype){
+    case ORK_JOINT_SPHER: { double dw[3] = {k*vi[0],k*vi[1],k*vi[2]}; aa_cascade(qi,dw); } break;
+    case ORK_JOINT_FLOAT: { double dw[3] = {k*vi[3],k*vi[4],k*vi[5]};
+      for(j=0;j<3;j++){ qi[j] += k*vi[j]; }
+      aa_cascade(qi+3,dw); } break;
+    default: for(j=0;j<l->ndof;j++) qi[j] += k*vi[j]; break; } }
+}
+
+/* rkFDUpdate (rkfd_sim.c:560-566): zODE2Update with Runge-Kutta-Gill on the regularised system
+ * x = (dis, vel) ([EXT A-9]), t += dt, then the committing reference evaluation */
+void ork_env_update(ork_env *e)
+{
+  const ork_world *w = e->w; int nq = w->nq, i; double dt = w->dt;
+  const double r2 = sqrt(2.0);
+  const double c21 = 0.5, c31 = (r2-1.0)/2.0, c32 = 1.0-1.0/r2, c42 = -1.0/r2, c43 = 1.0+1.0/r2;
+  const double b1 = 1.0/6.0, b2 = (2.0-r2)/6.0, b3 = (2.0+r2)/6.0, b4 = 1.0/6.0;
+  double *xq = e->xs[0], *xv = e->xs[1];
+  /* k1 */
+  memcpy(e->k[0][0],e->qd,nq*8); eval_dynamics(e,e->q,e->qd,e->k[0][1],0);
+  /* k2 */
+  memcpy(xq,e->q,nq*8); memcpy(xv,e->qd,nq*8);
+  cat_dis(w,xq,c21*dt,e->k[0][0]); for(i=0;i<nq;i++) xv[i] += c21*dt*e->k[0][1][i];
+  memcpy(e->k[1][0],xv,nq*8); eval_dynamics(e,xq,xv,e->k[1][1],0);
+  /* k3 */
+  memcpy(xq,e->q,nq*8); memcpy(xv,e->qd,nq*8);
+  cat_dis(w,xq,c31*dt,e->k[0][0]); cat_dis(w,xq,c32*dt,e->k[1][0]);
+  for(i=0;i<nq;i++){ xv[i] += c31*dt*e->k[0][1][i]; xv[i] += c32*dt*e->k[1][1][i]; }
+  memcpy(e->k[2][0],xv,nq*8); eval_dynamics(e,xq,xv,e->k[2][1],0);
+  /* k4 */
+  memcpy(xq,e->q,nq*8); memcpy(xv,e->qd,nq*8);
+  cat_dis(w,xq,c42*dt,e->k[1][0]); cat_dis(w,xq,c43*dt,e->k[2][0]);
+  for(i=0;i<nq;i++){ xv[i] += c42*dt*e->k[1][1][i]; xv[i] += c43*dt*e->k[2][1][i]; }
+  memcpy(e->k[3][0],xv,nq*8); eval_dynamics(e,xq,xv,e->k[3][1],0);
+  /* combination */
+  cat_dis(w,e->q,b1*dt,e->k[0][0]); cat_dis(w,e->q,b2*dt,e->k[1][0]);
+  cat_dis(w,e->q,b3*dt,e->k[2][0]); cat_dis(w,e->q,b4*dt,e->k[3][0]);
+  for(i=0;i<nq;i++){
+    e->qd[i] += b1*dt*e->k[0][1][i]; e->qd[i] += b2*dt*e->k[1][1][i];
+    e->qd[i] += b3*dt*e->k[2][1][i]; e->qd[i] += b4*dt*e->k[3][1][i]; }
+  e->t += dt;
+  eval_dynamics(e,e->q,e->qd,e->qdd,1);               /* _rkFDUpdateRef */
+}
+
+/* ------------------------------------------------------------------------------------ */
+void ork_env_get_link_frames(const ork_env *e, double *fr)
+{ int i; for(i=0;i<e->w->nl;i++){ memcpy(fr+12*i,e->lw[i].Rw,72); memcpy(fr+12*i+9,e->lw[i].pw,24); } }
+void ork_env_get_link_vel(const ork_env *e, double *v)
+{ int i; for(i=0;i<e->w->nl;i++) memcpy(v+6*i,e->lw[i].v,48); }
+void ork_env_get_link_acc(const ork_env *e, double *a)
+{ int i; for(i=0;i<e->w->nl;i++) memcpy(a+6*i,e->lw[i].a,48); }
+double ork_env_energy(const ork_env *e)
+{
+  const ork_world *w = e->w; int i, j; double E = 0; ork_env *m = (ork_env*)e;
+  eval_kinematics(m,e->q,e->qd);
+  for(i=0;i<w->nl;i++){ const ork_link *l = &w->link[i]; const ork_lw *x = &e->lw[i];
+    double vc[3], t[3], Iw[3], cw[3], Ic[9]; int r, c;
+    v3_cross(x->v+3,l->com,t); v3_add(x->v,t,vc);
+    for(r=0;r<3;r++) for(c=0;c<3;c++) Ic[3*r+c] = l->inertia[3*r+c];
+    m3_mulv(Ic,x->v+3,Iw);
+    E += 0.5*l->mass*v3_dot(vc,vc) + 0.5*v3_dot(x->v+3,Iw);
+    m3_mulv(x->Rw,l->com,cw); E += l->mass*ORK_G*(x->pw[2]+cw[2]);
+    if( l->ndof==1 ){ double tin,treg,jm; motor_eval(l,0.0,e->qd[l->qofs],&tin,&treg,&jm); E += 0.5*jm*e->qd[l->qofs]*e->qd[l->qofs]; }
+    (void)j; }
+  return E;
+}
+int ork_env_get_rigid_system(const ork_env *e, double *A, double *b, double *f, int cap)
+{
+  int n = e->rn; if( n > cap ) return -n;
+  if(A) memcpy(A,e->rA,n*n*8);
+  if(b) memcpy(b,e->rb,n*8);
+  if(f) memcpy(f,e->rf,n*8);
+  return n;
+}
+
+/* ------------------------------------------------------------------------------------ */
+int ork_batch_run(const ork_world *w, int B, double *q, double *qd, const double *u,
+                  int nsteps, int nthreads, double *qdd_out)
+{
+  int used = 1, nq = w->nq, nl = w->nl;
+#ifdef _OPENMP
+  if( nthreads > 0 ) omp_set_num_threads(nthreads);
+  used = omp_get_max_threads();
+#endif
+#pragma omp parallel
+  {
+    ork_env *e = ork_env_new(w); int b, s;
+#pragma omp for schedule(static)
+    for(b=0;b<B;b++){
+      int i;
+      e->t = 0;
+      for(i=0;i<nq;i++){ e->piv_type[i] = ORK_SF; e->piv_prev[i] = 0; e->tf[i] = 0; }
+      for(i=0;i<w->nslot;i++) e->c_active[i] = 0;
+      ork_env_set_state(e,q+(size_t)nq*b,qd+(size_t)nq*b);
+      if( u ) ork_env_set_motor_input(e,u+(size_t)nl*b); else memset(e->min,0,nl*8);
+      ork_env_update_init(e);
+      for(s=0;s<nsteps;s++) ork_env_update(e);
+      ork_env_get_state(e,q+(size_t)nq*b,qd+(size_t)nq*b,qdd_out?qdd_out+(size_t)nq*b:NULL);
+    }
+    ork_env_free(e);
+  }
+  return used;
+}

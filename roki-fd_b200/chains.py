@@ -1,0 +1,344 @@
+"""Chain / world descriptions (host side, plain data).
+
+These mirror what the reference reads from its ZTK model files ([roki::chain], [roki::link],
+[roki::motor], [zeo::shape], [roki::contact]; reference example/model/*.ztk) and are the inputs
+handed to the C-ABI (`rkFDChainReg` through the `rkChainB200*` builder calls).  Conventions:
+revolute/prismatic axis = link-local z; `org_R`/`org_p` = the ZTK `frame:` of the link w.r.t. its
+parent; inertia about the COM in link axes.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+NDOF = {"fixed": 0, "revolute": 1, "prismatic": 1, "spherical": 3, "float": 6}
+
+
+def rot_x(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[1, 0, 0], [0, c, -s], [0, s, c]], float)
+
+
+def rot_y(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], float)
+
+
+def rot_z(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], float)
+
+
+def box_verts(depth, width, height, center=(0.0, 0.0, 0.0)):
+    """8 corners of a zeo box (depth=x, width=y, height=z); vertex k has sign bits (x: k&1, y: k&2, z: k&4)."""
+    c = np.asarray(center, float)
+    v = np.array([[(1 if k & 1 else -1) * depth / 2, (1 if k & 2 else -1) * width / 2,
+                   (1 if k & 4 else -1) * height / 2] for k in range(8)], float)
+    return v + c
+
+
+@dataclass
+class Motor:
+    type: str = "dc"               # "dc" | "trq"
+    k: float = 0.0                 # motorconstant
+    admittance: float = 0.0
+    gear: float = 1.0              # gearratio
+    rotor_inertia: float = 0.0
+    gear_inertia: float = 0.0
+    min: float = -1e300
+    max: float = 1e300
+
+
+@dataclass
+class Link:
+    name: str = "link"
+    parent: int = -1               # index within the chain, -1 = root
+    jtype: str = "fixed"
+    org_R: np.ndarray = field(default_factory=lambda: np.eye(3))
+    org_p: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    mass: float = 1.0
+    com: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    inertia: np.ndarray = field(default_factory=lambda: np.eye(3))
+    stuff: str = ""
+    stiffness: float = 0.0
+    viscosity: float = 0.0
+    coulomb: float = 0.0
+    sfriction: float = 0.0
+    motor: Optional[Motor] = None
+    shapes: List[np.ndarray] = field(default_factory=list)   # vertex clouds (n x 3, link frame)
+    # static links only: boxes as (center(3), depth, width, height) in the link frame
+    boxes: List[tuple] = field(default_factory=list)
+
+
+@dataclass
+class ChainModel:
+    name: str
+    links: List[Link]
+
+    @property
+    def joint_size(self):
+        return sum(NDOF[l.jtype] for l in self.links)
+
+    @property
+    def is_static(self):
+        return self.joint_size == 0
+
+
+@dataclass
+class StaticBox:
+    R: np.ndarray
+    p: np.ndarray
+    half: np.ndarray
+    stuff: str
+
+
+@dataclass
+class ContactInfo:
+    stuff_a: str
+    stuff_b: str
+    type: str = "rigid"            # "rigid" (compensation/relaxation) | "elastic" (elasticity/viscosity)
+    K: float = 0.0
+    L: float = 0.0
+    E: float = 0.0
+    V: float = 0.0
+    SF: float = 0.5
+    KF: float = 0.3
+
+
+@dataclass
+class World:
+    """One environment's content: chains registered in order + contact table + properties
+    (reference rkfd_property.c:10-18 defaults)."""
+    chains: List[ChainModel] = field(default_factory=list)
+    contact_info: List[ContactInfo] = field(default_factory=list)
+    dt: float = 0.001
+    pyramid: int = 8
+    friction_weight: float = 100.0
+    max_iter: int = 10
+    solver: str = "Vert"
+
+    def __post_init__(self):
+        self._stuff = {}
+
+    def stuff_id(self, name):
+        if not hasattr(self, "_stuff"):
+            self._stuff = {}
+        return self._stuff.setdefault(name, len(self._stuff))
+
+    def moving_chains(self):
+        return [c for c in self.chains if not c.is_static]
+
+    def flat_links(self):
+        """Links of all moving chains concatenated in registration order, parents re-indexed."""
+        out = []
+        for ch in self.moving_chains():
+            base = len(out)
+            for l in ch.links:
+                ll = Link(**{**l.__dict__})
+                ll.parent = l.parent + base if l.parent >= 0 else -1
+                out.append(ll)
+        return out
+
+    @property
+    def boxes(self):
+        """Static boxes in world coordinates from the all-fixed chains (e.g. floor.ztk)."""
+        out = []
+        for ch in self.chains:
+            if not ch.is_static:
+                continue
+            frames = []
+            for l in ch.links:
+                R, p = np.asarray(l.org_R, float), np.asarray(l.org_p, float)
+                if l.parent >= 0:
+                    Rp, pp = frames[l.parent]
+                    R, p = Rp @ R, pp + Rp @ p
+                frames.append((R, p))
+                for (c, d, w, h) in l.boxes:
+                    out.append(StaticBox(R=R, p=p + R @ np.asarray(c, float),
+                                         half=np.array([d / 2, w / 2, h / 2], float), stuff=l.stuff))
+        return out
+
+    @property
+    def nq(self):
+        return sum(c.joint_size for c in self.moving_chains())
+
+    @property
+    def nl(self):
+        return sum(len(c.links) for c in self.moving_chains())
+
+    @property
+    def nslot(self):
+        nv = sum(v.shape[0] for l in self.flat_links() for v in l.shapes)
+        return nv * len(self.boxes)
+
+
+# ---------------------------------------------------------------------------------------------
+# models of the reference's example/model directory (values transcribed from the ZTK files)
+
+def motor_arm2dof():
+    """[roki::motor] motor1 of reference example/model/arm_2DoF.ztk:131-140."""
+    return Motor(type="dc", k=2.58e-2, admittance=0.42373, gear=120.0, rotor_inertia=1.65e-6,
+                 gear_inertia=5.38e-6, min=-24.0, max=24.0)
+
+
+def box(name="box"):
+    """reference example/model/box.ztk: one float link, m=0.5, 0.1 m cube, stuff body."""
+    return ChainModel(name, [Link(name="link#00", jtype="float", mass=0.5, stuff="body",
+                                  inertia=np.eye(3) * 8.33e-4, shapes=[box_verts(0.1, 0.1, 0.1)])])
+
+
+def floor():
+    """reference example/model/floor.ztk: fixed link, 5 x 5 x 0.4 box, top face at z=0, stuff ground."""
+    return ChainModel("floor", [Link(name="link#00", jtype="fixed", mass=99.9, stuff="ground",
+                                     inertia=np.eye(3) * 0.999, boxes=[((0, 0, -0.2), 5.0, 5.0, 0.4)])])
+
+
+def floor_soft():
+    """floor.ztk with `stuff: soft`."""
+    f = floor()
+    f.links[0].stuff = "soft"
+    return f
+
+
+def floor_hardsoft():
+    """reference example/model/floor_hardsoft.ztk:31-75: two 5 x 2.5 x 0.4 boxes, y>0 `ground`, y<0 `soft`."""
+    l0 = Link(name="link#00", jtype="fixed", mass=99.9, stuff="ground", inertia=np.eye(3) * 0.999,
+              org_p=np.array([0, 1.25, 0.0]), boxes=[((0, 0, -0.2), 5.0, 2.5, 0.4)])
+    l1 = Link(name="link#01", jtype="fixed", parent=0, mass=99.9, stuff="soft", inertia=np.eye(3) * 0.999,
+              org_p=np.array([0, -2.5, 0.0]), boxes=[((0, 0, -0.2), 5.0, 2.5, 0.4)])
+    return ChainModel("floor", [l0, l1])
+
+
+def contact_info_table():
+    """reference example/model/contactinfo.ztk (all seven records)."""
+    return [
+        ContactInfo("ground", "body", "rigid", K=1000.0, L=0.0001, SF=0.5, KF=0.3),
+        ContactInfo("body", "body", "rigid", K=1000.0, L=0.05, SF=0.5, KF=0.3),
+        ContactInfo("wall", "wall", "rigid", K=500.0, L=0.001, SF=0.5, KF=0.3),
+        ContactInfo("wall", "ground", "rigid", K=500.0, L=0.001, SF=0.5, KF=0.3),
+        ContactInfo("ground", "crawler", "rigid", K=100.0, L=10.0, SF=10.0, KF=7.0),
+        ContactInfo("soft", "body", "elastic", E=100.0, V=1.0, SF=0.5, KF=0.3),
+        ContactInfo("soft", "crawler", "elastic", E=1000.0, V=10.0, SF=10.0, KF=7.0),
+    ]
+
+
+def arm_2dof(motors=True):
+    """reference example/model/arm_2DoF.ztk:142-212: fixed base + 2 revolute links with DC motors."""
+    m = motor_arm2dof if motors else (lambda: None)
+    base = Link(name="link#00", jtype="fixed", mass=1.5, stuff="body", com=np.array([0.067, 0, 0]),
+                inertia=np.diag([7.395833e-03, 8.645833e-03, 8.541667e-03]),
+                org_R=np.array([[0, 0, -1], [0, 1, 0], [1, 0, 0]], float))
+    l1 = Link(name="link#01", jtype="revolute", parent=0, mass=1.5, stuff="body", com=np.array([0.267, 0, 0]),
+              inertia=np.diag([0.00239583, 0.02239583, 0.02229167]), org_p=np.array([0.15, 0, 0]),
+              viscosity=2.2, coulomb=4.32, sfriction=4.92, motor=m())
+    l2 = Link(name="link#02", jtype="revolute", parent=1, mass=1.0, stuff="body", com=np.array([0.2, 0, 0]),
+              inertia=np.diag([0.0016667, 0.0083333, 0.0083333]), org_p=np.array([0.4, 0, 0]),
+              viscosity=2.2, coulomb=4.32, sfriction=4.92, motor=m())
+    return ChainModel("arm_2DoF", [base, l1, l2])
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic models of BASELINE.json / SURVEY.md section 8d
+
+ARM7_MASS = [4.0, 4.0, 3.0, 2.7, 1.7, 1.8, 0.3]
+
+
+def arm7(base_z=0.6, contact_cube=False, motors=True, stuff="body"):
+    """The 7-DoF arm of BASELINE.json configs C2/C3/C5: fixed base + 7 revolute
+    links, joint axis local z, link frame (0,0,0.2) + Rot_x(-/+90 deg) alternating, DC motor + joint
+    friction constants of arm_2DoF.ztk on every joint.  `contact_cube` hangs the 0.1 m cube of box.ztk
+    (8 vertices) on link 7."""
+    links = [Link(name="base", jtype="fixed", mass=5.0, stuff=stuff, inertia=np.eye(3) * 0.05,
+                  org_p=np.array([0, 0, base_z]))]
+    for i in range(1, 8):
+        m = ARM7_MASS[i - 1]
+        l = Link(name="link#%02d" % i, jtype="revolute", parent=i - 1, mass=m, stuff=stuff,
+                 com=np.array([0, 0, 0.1]), inertia=np.diag([m * 0.01, m * 0.01, m * 0.002]),
+                 org_p=np.array([0, 0, 0.2]),
+                 org_R=rot_x(-np.pi / 2) if i % 2 else rot_x(np.pi / 2))
+        if motors:
+            l.motor = motor_arm2dof()
+            l.viscosity, l.coulomb, l.sfriction = 2.2, 4.32, 4.92
+        links.append(l)
+    if contact_cube:
+        links[7].shapes = [box_verts(0.1, 0.1, 0.1, center=(0, 0, 0.1))]
+    return ChainModel("arm7", links)
+
+
+def world_c2():
+    """C2: arm7, no contact (pure ABA + joint friction)."""
+    return World(chains=[arm7()])
+
+
+def world_c3(base_z=0.45):
+    """C3: arm7 + end-effector cube on a soft (elastic E=1000, V=10, SF=.5, KF=.3) floor, Vert solver."""
+    return World(chains=[arm7(base_z=base_z, contact_cube=True), floor_soft()],
+                 contact_info=[ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0, SF=0.5, KF=0.3)])
+
+
+def world_c5(base_z=0.45, solver="MLCP"):
+    """C5: arm7 + cube on the rigid `ground` floor (K=1000, L=1e-4), MLCP or Vert-QP."""
+    return World(chains=[arm7(base_z=base_z, contact_cube=True), floor()],
+                 contact_info=[ContactInfo("ground", "body", "rigid", K=1000.0, L=0.0001, SF=0.5, KF=0.3)],
+                 solver=solver)
+
+
+def world_c1_box(solver="Vert"):
+    """C1: box.ztk dropped on floor_hardsoft.ztk with contactinfo.ztk (boxdrop_hardsoft_test.c)."""
+    return World(chains=[box(), floor_hardsoft()], contact_info=contact_info_table(), solver=solver)
+
+
+def world_c1_serial():
+    """C1 variant: arm_2DoF.ztk falling under gravity with motors at 0 V, no ground."""
+    return World(chains=[arm_2dof()])
+
+
+def sample_state(world, B, seed=20260418):
+    """Synthetic randomised states of SURVEY.md section 8d: q ~ U(-pi/2, pi/2), qd ~ U(-1, 1),
+    motor voltage ~ U(-6, 6); float joints get position z lifted by +0.3."""
+    rng = np.random.default_rng(seed)
+    nq, nl = world.nq, world.nl
+    q = rng.uniform(-np.pi / 2, np.pi / 2, (B, nq))
+    qd = rng.uniform(-1.0, 1.0, (B, nq))
+    u = rng.uniform(-6.0, 6.0, (B, nl))
+    o = 0
+    for l in world.flat_links():
+        if l.jtype == "float":
+            q[:, o:o + 3] = rng.uniform(-0.2, 0.2, (B, 3))
+            q[:, o + 2] += 0.3
+        o += NDOF[l.jtype]
+    return q, qd, u
+
+
+# ---------------------------------------------------------------------------------------------
+# random chains for property tests
+
+def random_chain(rng, n_links=5, jtypes=("revolute",), root="fixed", branching=False, motors=False,
+                 shapes=False, name="rnd"):
+    def rnd_rot():
+        a = rng.normal(size=3)
+        th = np.linalg.norm(a)
+        k = a / th
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+    def rnd_inertia(m):
+        A = rng.normal(size=(3, 3))
+        return (A @ A.T + 0.5 * np.eye(3)) * 0.01 * m
+
+    links = []
+    for i in range(n_links):
+        m = rng.uniform(0.5, 3.0)
+        jt = root if i == 0 else jtypes[rng.integers(len(jtypes))]
+        parent = -1 if i == 0 else (int(rng.integers(0, i)) if branching else i - 1)
+        l = Link(name="l%d" % i, parent=parent, jtype=jt, mass=m, com=rng.uniform(-0.1, 0.1, 3),
+                 inertia=rnd_inertia(m), org_R=rnd_rot(), org_p=rng.uniform(-0.3, 0.3, 3), stuff="body")
+        if i == 0 and root == "fixed":
+            l.org_p = np.array([0, 0, 1.0])
+        if motors and NDOF[jt] == 1:
+            l.motor = motor_arm2dof()
+            l.viscosity, l.coulomb, l.sfriction = 2.2, 4.32, 4.92
+        if shapes and i == n_links - 1:
+            l.shapes = [box_verts(0.1, 0.1, 0.1)]
+        links.append(l)
+    return ChainModel(name, links)
