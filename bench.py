@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py - env-steps/s of the batched FD+contact step (BASELINE.json metric) on N B200s.
+
+Workload (config.workload): C3 of SURVEY.md section 8d - 7-DoF arm with an 8-vertex end-effector on a soft
+floor (vertex penalty contact + joint friction + DC motors), 262,144 environments per GPU, synthetic
+randomised initial states (numpy default_rng(20260418)), dt = 1e-3, Runge-Kutta-Gill.  One "step" =
+one rkFDUpdate for every environment (5 dynamics evaluations + RKG combination, one kernel launch).
+
+  python bench.py --gpus N --steps K --warmup W              the CUDA engine (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...    the CPU restatement of the reference on all
+                                                             host cores (the reference itself is un-buildable
+                                                             here: ZEDA/ZM/Zeo/RoKi absent)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 262144
+METRIC = "env-steps/sec (batched FD+contact step)"
+UNIT = "env-steps/s"
+WORKLOAD = "C3: arm7 (7-DoF, DC motors, joint friction) + 8-vertex penalty ground contact, %d envs/GPU" % B_PER_GPU
+# algorithmic work per env-step (restated in DESIGN.md)
+ALG_BYTES = 1054.0
+ALG_FLOP = 20471.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline_run(world, ch, n_envs, n_steps, threads=0, seed=20260418):
+    """The oracle (CPU restatement of the reference's algorithm) on the host cores: env-steps/s."""
+    from oracle import oracle as orc
+    ow = orc.OracleWorld(world)
+    q, qd, u = ch.sample_state(world, n_envs, seed=seed)
+    t0 = time.perf_counter()
+    _, _, _, used = ow.batch_run(q, qd, u, nsteps=n_steps, nthreads=threads)
+    dt = time.perf_counter() - t0
+    # batch_run also performs rkFDUpdateInit's evaluation per env: count it as 1/5 of a step
+    return n_envs * (n_steps + 0.2) / dt, used, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be
+    compiled (its dependencies are absent), so this times the oracle port with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import rokifd_b200  # noqa: F401
+    from rokifd_b200 import chains as ch
+    world = ch.world_c3()
+    cores = os.cpu_count() or 1
+    n_envs = 1024 * cores
+    for _ in range(args.warmup):
+        cpu_baseline_run(world, ch, n_envs, 1)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        v, used, _ = cpu_baseline_run(world, ch, n_envs, 1)
+        vals.append(v)
+    dt = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    sample = "%d envs x 1 rkFDUpdate (+UpdateInit evaluation) per step, %d timed steps" % (n_envs, args.steps)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "cpu_sample": sample},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
+                            "note": "CPU restatement of RoKi-FD's algorithm; reference un-buildable (ZEDA/ZM/Zeo/RoKi absent)"},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=B_PER_GPU, help="environments per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import rokifd_b200  # noqa: F401
+    from rokifd_b200 import capi, chains as ch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    world = ch.world_c3()
+    B = args.envs
+    q, qd, u = ch.sample_state(world, B, seed=20260418 + rank)
+    fd, _ = capi.create_world(world, B=B, devices=[local_rank])
+    fd.batch_set_state(q, qd)
+    fd.batch_set_motor_input(u)
+    fd.update_init()
+    stream = torch.cuda.current_stream()
+    fd.batch_set_stream(stream.cuda_stream)       # kernels run on torch's current stream: torch events bracket them
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") --------------------------------------------------------
+    for _ in range(args.warmup):
+        fd.update()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = fd.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for s in range(args.steps):
+        fd.update()
+        ev[s + 1].record(stream)
+    barrier()
+    launches = fd.launch_count - l0
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = B * world_size * args.steps / (total_ms * 1e-3)
+    assert (fd.batch_get_status() == 0).all(), "non-finite accelerations in the timed run"
+
+    # ---- end to end through the C-ABI with HOST buffers ("e2e") -----------------------------------------
+    nq, nl = world.nq, world.nl
+    hq = torch.from_numpy(q.copy()).pin_memory(); hqd = torch.from_numpy(qd.copy()).pin_memory()
+    hu = torch.from_numpy(u.copy()).pin_memory()
+    oq = torch.empty((B, nq), dtype=torch.float64).pin_memory(); oqd = torch.empty_like(oq).pin_memory()
+    oqdd = torch.empty_like(oq).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        fd.batch_set_state(hq.data_ptr(), hqd.data_ptr())
+        fd.batch_set_motor_input(hu.data_ptr())
+        fd.update()
+        fd.batch_get_state(oq.data_ptr(), oqd.data_ptr(), oqdd.data_ptr())
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world_size * e2e_steps / (float(t.item()) * 1e-3)
+    h2d = B * (2 * nq + nl) * 8
+    d2h = B * 3 * nq * 8
+
+    # ---- roofline of the dominant kernel (rkfd_step_kernel: the only kernel of a step) ------------------
+    hbm_peak, peak_src = load_peaks()
+    k_ms = float(np.mean(per_launch_ms))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    ach_gbs = ALG_BYTES * B / (k_ms * 1e-3) / 1e9
+    fp64_peak = capi.measure_fp64_tflops()
+    ach_tf = ALG_FLOP * B / (k_ms * 1e-3) / 1e12
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "envs_per_gpu": B, "dt": world.dt, "integrator": "RKG", "solver": world.solver,
+                      "l2": "per-GPU state (%.0f MB) is larger than the 126 MB L2" % (B * 8 * 140 / 1e6)},
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+           "gpu_launches": int(launches),
+           "clocks": clocks,
+           "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                        "traffic": traffic, "peak_source": peak_src, "kernel": "rkfd_step_kernel", "kernel_ms": k_ms,
+                        "algorithmic_bytes_per_env_step": ALG_BYTES},
+           "roofline_fp64": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": ach_tf / fp64_peak if fp64_peak else None, "peak_source": "measured in this run (DFMA loop)",
+                             "algorithmic_flop_per_env_step": ALG_FLOP}}
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_envs, n_steps = 2048 * cores, 10
+        v, used, dt = cpu_baseline_run(world, ch, n_envs, n_steps)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": "port",
+                               "sample": "%d envs x %d steps of the same workload (%.1f s)" % (n_envs, n_steps, dt),
+                               "note": "CPU restatement of RoKi-FD's algorithm; reference un-buildable (ZEDA/ZM/Zeo/RoKi absent)"}
+    fd.destroy()
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,25 @@ def _i(a):
     return a, a.ctypes.data_as(_ip)
 
 
+def pack_links(world, links):
+    """Flat link description (layout in rkfd_oracle.h): li (nl x 4 int32), ld (nl x LINK_ND float64)."""
+    nl = len(links)
+    li = np.zeros((nl, 4), np.int32)
+    ld = np.zeros((nl, LINK_ND), np.float64)
+    for k, l in enumerate(links):
+        m = l.motor
+        li[k] = (l.parent, JOINT[l.jtype], MOTOR[m.type if m else None], world.stuff_id(l.stuff))
+        ld[k, 0:9] = np.asarray(l.org_R, float).reshape(9)
+        ld[k, 9:12] = l.org_p
+        ld[k, 12] = l.mass
+        ld[k, 13:16] = l.com
+        ld[k, 16:25] = np.asarray(l.inertia, float).reshape(9)
+        ld[k, 25:29] = (l.stiffness, l.viscosity, l.coulomb, l.sfriction)
+        if m:
+            ld[k, 29:36] = (m.k, m.admittance, m.gear, m.rotor_inertia, m.gear_inertia, m.min, m.max)
+    return li, ld
+
+
 class OracleWorld:
     """Builds an oracle world from a rokifd_b200.chains.World description."""
 
@@ -92,19 +111,7 @@ class OracleWorld:
         self.desc = world
         links = world.flat_links()
         nl = len(links)
-        li = np.zeros((nl, 4), np.int32)
-        ld = np.zeros((nl, LINK_ND), np.float64)
-        for k, l in enumerate(links):
-            m = l.motor
-            li[k] = (l.parent, JOINT[l.jtype], MOTOR[m.type if m else None], world.stuff_id(l.stuff))
-            ld[k, 0:9] = np.asarray(l.org_R, float).reshape(9)
-            ld[k, 9:12] = l.org_p
-            ld[k, 12] = l.mass
-            ld[k, 13:16] = l.com
-            ld[k, 16:25] = np.asarray(l.inertia, float).reshape(9)
-            ld[k, 25:29] = (l.stiffness, l.viscosity, l.coulomb, l.sfriction)
-            if m:
-                ld[k, 29:36] = (m.k, m.admittance, m.gear, m.rotor_inertia, m.gear_inertia, m.min, m.max)
+        li, ld = pack_links(world, links)
         _, pi = _i(li)
         _, pd = _d(ld)
         self.h = L.ork_world_new(nl, pi, pd)

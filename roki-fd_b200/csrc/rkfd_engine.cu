@@ -1,0 +1,403 @@
+/* rkfd_engine.cu - sm_100a kernels + device engine of the batched RoKi-FD step path.
+ *
+ * Kernel rkfd_step_kernel: one thread = one environment (reference rkFDUpdate for one rkFD,
+ * src/rkfd_sim.c:560-566); the five dynamics evaluations and the Runge-Kutta-Gill combination of a
+ * step are fused in one launch, `nsteps` steps per launch.  Model tables in __constant__ memory
+ * (warp-uniform operands), per-env state as env-fastest structure-of-arrays in HBM (every access
+ * is a fully coalesced 256-byte warp request), inter-pass link data in a shared-memory column per
+ * thread.  fp64 throughout (the reference is double precision).
+ */
+#include "rkfd_engine.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "rkfd_core.cuh"
+
+namespace rkfd {
+
+__constant__ ModelDev c_model;
+
+void cuda_check(int err, const char *what)
+{
+  if( err != (int)cudaSuccess ){
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "rokifd_b200: %s failed: %s", what, cudaGetErrorString((cudaError_t)err));
+    throw std::runtime_error(buf);
+  }
+}
+#define CK(x) cuda_check((int)(x), #x)
+
+int device_count(){ int n = 0; if( cudaGetDeviceCount(&n) != cudaSuccess ) return 0; return n; }
+
+template <int BLOCK, bool GSCR>
+struct DevCtx {
+  StateDev st; int e, cur; double *sm;
+  __device__ __forceinline__ double &S(int k){
+    if( GSCR ) return st.scratch[(size_t)k*st.ld + e];
+    return sm[k*BLOCK];
+  }
+  __device__ __forceinline__ double gld(const double *p, int k) const { return p[(size_t)k*st.ld + e]; }
+  __device__ __forceinline__ void gst(double *p, int k, double v){ p[(size_t)k*st.ld + e] = v; }
+};
+
+/* mode 0: nsteps x rkFDUpdate; 1: one non-committing evaluation; 2: one committing evaluation */
+template <int BLOCK, bool GSCR>
+__global__ void __launch_bounds__(BLOCK) rkfd_step_kernel(StateDev st, int cur, int mode, int nsteps)
+{
+  extern __shared__ double rkfd_smem[];
+  const int e = blockIdx.x*BLOCK + threadIdx.x;
+  if( e >= st.B ) return;
+  DevCtx<BLOCK,GSCR> ctx; ctx.st = st; ctx.e = e; ctx.cur = cur; ctx.sm = rkfd_smem + threadIdx.x;
+  Core<DevCtx<BLOCK,GSCR>> core(ctx);
+  if( mode == 0 ) core.run_steps(c_model, nsteps);
+  else core.run_eval(c_model, mode == 2);
+}
+
+/* env-major host layout [B][n] <-> device SoA [n][ld] */
+__global__ void rkfd_scatter_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld)
+{
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  if( e >= B ) return;
+  for(int k=0;k<n;k++) dst[(size_t)k*ld + e] = src[(size_t)e*n + k];
+}
+__global__ void rkfd_gather_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld)
+{
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  if( e >= B ) return;
+  for(int k=0;k<n;k++) dst[(size_t)e*n + k] = src[(size_t)k*ld + e];
+}
+
+/* register-resident DFMA loop on every SM: the measured fp64 roofline denominator (MEASURED_PEAKS.json
+ * carries HBM and bf16 only).  8 independent accumulators per thread, 2 flop per DFMA. */
+__global__ void __launch_bounds__(256) rkfd_fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+  double x0 = threadIdx.x*1e-3, x1 = x0+1, x2 = x0+2, x3 = x0+3, x4 = x0+4, x5 = x0+5, x6 = x0+6, x7 = x0+7;
+#pragma unroll 1
+  for(int i=0;i<iters;i++){
+#pragma unroll
+    for(int k=0;k<16;k++){
+      x0 = fma(x0,a,b); x1 = fma(x1,a,b); x2 = fma(x2,a,b); x3 = fma(x3,a,b);
+      x4 = fma(x4,a,b); x5 = fma(x5,a,b); x6 = fma(x6,a,b); x7 = fma(x7,a,b);
+    }
+  }
+  out[blockIdx.x*blockDim.x + threadIdx.x] = x0+x1+x2+x3+x4+x5+x6+x7;
+}
+
+double measure_fp64_tflops()
+{
+  int dev = 0, sms = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms*8, threads = 256, iters = 4096;
+  double *out = nullptr; CK(cudaMalloc(&out, (size_t)blocks*threads*sizeof(double)));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0;
+  for(int rep=0; rep<5; rep++){
+    CK(cudaEventRecord(e0));
+    rkfd_fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-7);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0*8*16*(double)iters*blocks*threads;
+    if( rep > 0 && flop/(ms*1e-3)/1e12 > best ) best = flop/(ms*1e-3)/1e12;
+  }
+  CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1)); CK(cudaFree(out));
+  return best;
+}
+
+struct Shard {
+  int dev = 0, e0 = 0, B = 0, ld = 0, cur = 0;
+  StateDev st;
+  cudaStream_t stream = nullptr; bool own_stream = true;
+  double *dstage = nullptr; size_t nstage = 0;
+  int block = 64; bool gscr = false; size_t smem = 0;
+  std::vector<void*> allocs;
+};
+
+static int g_next_engine_id = 1;
+static int g_model_owner[64] = {0};
+
+template <class T> static T *dalloc(Shard &s, size_t n)
+{
+  void *p = nullptr; if( n == 0 ) n = 1;
+  CK(cudaMalloc(&p, n*sizeof(T))); CK(cudaMemset(p, 0, n*sizeof(T)));
+  s.allocs.push_back(p); return (T*)p;
+}
+
+template <int BLOCK, bool GSCR>
+static bool try_config(Shard &s, int nscratch, int &best_threads)
+{
+  const size_t smem = GSCR ? 0 : (size_t)nscratch*BLOCK*sizeof(double);
+  if( smem > 227*1024 ) return false;
+  if( cudaFuncSetAttribute(rkfd_step_kernel<BLOCK,GSCR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ){ cudaGetLastError(); return false; }
+  int nb = 0;
+  if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rkfd_step_kernel<BLOCK,GSCR>, BLOCK, smem) != cudaSuccess ){ cudaGetLastError(); return false; }
+  if( nb*BLOCK > best_threads ){ best_threads = nb*BLOCK; s.block = BLOCK; s.gscr = GSCR; s.smem = smem; return true; }
+  return false;
+}
+
+Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : model_(model), B_(B), id_(g_next_engine_id++)
+{
+  if( B <= 0 ) throw std::runtime_error("rokifd_b200: environment count must be positive");
+  if( device_count() <= 0 ) throw std::runtime_error("rokifd_b200: no CUDA device (there is no CPU fallback)");
+  std::vector<int> devs = devices;
+  if( devs.empty() ){ int d = 0; CK(cudaGetDevice(&d)); devs.push_back(d); }
+  const int G = (int)devs.size();
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(int g=0; g<G; g++){
+    /* contiguous env blocks: env e -> shard floor(e*G/B) */
+    const int e0 = (int)((long long)B*g/G), e1 = (int)((long long)B*(g+1)/G);
+    if( e1 <= e0 ) continue;
+    Shard *s = new Shard; shards_.push_back(s);
+    s->dev = devs[g]; s->e0 = e0; s->B = e1-e0; s->ld = (s->B + 31) & ~31;
+    CK(cudaSetDevice(s->dev));
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    const int nq = model.nq > 0 ? model.nq : 1, nl = model.nl > 0 ? model.nl : 1, ns = model.nslot > 0 ? model.nslot : 1;
+    StateDev &st = s->st; std::memset(&st, 0, sizeof st);
+    st.B = s->B; st.ld = s->ld;
+    for(int k=0;k<2;k++){ st.q[k] = dalloc<double>(*s, (size_t)nq*s->ld); st.qd[k] = dalloc<double>(*s, (size_t)nq*s->ld); }
+    st.qdd = dalloc<double>(*s, (size_t)nq*s->ld);
+    st.u = dalloc<double>(*s, (size_t)nl*s->ld);
+    st.piv_prev = dalloc<double>(*s, (size_t)nq*s->ld);
+    st.piv_type = dalloc<unsigned int>(*s, s->ld);
+    st.cflags = dalloc<unsigned long long>(*s, s->ld);
+    st.cref = dalloc<double>(*s, (size_t)3*ns*s->ld);
+    st.cf = dalloc<double>(*s, (size_t)3*ns*s->ld);
+    st.status = dalloc<int>(*s, s->ld);
+    int nmax = nq; if( nl > nmax ) nmax = nl; if( 3*ns > nmax ) nmax = 3*ns;
+    s->nstage = (size_t)nmax*s->B; s->dstage = dalloc<double>(*s, s->nstage);
+    /* launch configuration: the block size that keeps most environments resident per SM */
+    int best = 0;
+    try_config<128,false>(*s, model.nscratch, best);
+    try_config<64,false>(*s, model.nscratch, best);
+    try_config<32,false>(*s, model.nscratch, best);
+    if( best == 0 ){
+      try_config<64,true>(*s, model.nscratch, best);
+      st.scratch = dalloc<double>(*s, (size_t)model.nscratch*s->ld);
+    }
+    if( best == 0 ) throw std::runtime_error("rokifd_b200: no launch configuration fits this model");
+  }
+  CK(cudaSetDevice(prev));
+}
+
+Engine::~Engine()
+{
+  int prev = 0; cudaGetDevice(&prev);
+  for(Shard *s : shards_){
+    cudaSetDevice(s->dev);
+    cudaStreamSynchronize(s->stream);
+    if( g_model_owner[s->dev & 63] == id_ ) g_model_owner[s->dev & 63] = 0;
+    for(void *p : s->allocs) cudaFree(p);
+    if( s->own_stream && s->stream ) cudaStreamDestroy(s->stream);
+    delete s;
+  }
+  cudaSetDevice(prev);
+}
+
+void Engine::upload_model(Shard &s)
+{
+  if( g_model_owner[s.dev & 63] == id_ ) return;
+  /* another engine's kernels may still read the constant table on this device */
+  if( g_model_owner[s.dev & 63] != 0 ) CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyToSymbolAsync(c_model, &model_, sizeof(ModelDev), 0, cudaMemcpyHostToDevice, s.stream));
+  g_model_owner[s.dev & 63] = id_;
+}
+
+template <int BLOCK, bool GSCR>
+static void launch_cfg(Shard &s, int mode, int nsteps)
+{
+  const int grid = (s.B + BLOCK - 1)/BLOCK;
+  rkfd_step_kernel<BLOCK,GSCR><<<grid, BLOCK, s.smem, s.stream>>>(s.st, s.cur, mode, nsteps);
+}
+
+void Engine::launch(Shard &s, int mode, int nsteps)
+{
+  CK(cudaSetDevice(s.dev));
+  upload_model(s);
+  if( s.gscr ) launch_cfg<64,true>(s, mode, nsteps);
+  else if( s.block == 128 ) launch_cfg<128,false>(s, mode, nsteps);
+  else if( s.block == 64 ) launch_cfg<64,false>(s, mode, nsteps);
+  else launch_cfg<32,false>(s, mode, nsteps);
+  CK(cudaGetLastError());
+  launches_++;
+  if( mode == 0 && (nsteps & 1) ) s.cur ^= 1;
+}
+
+void Engine::step(int nsteps)
+{
+  if( nsteps <= 0 ) return;
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_) launch(*s, 0, nsteps);
+  CK(cudaSetDevice(prev));
+}
+void Engine::eval(bool ref)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_) launch(*s, ref ? 2 : 1, 0);
+  CK(cudaSetDevice(prev));
+}
+void Engine::sync()
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream)); }
+  CK(cudaSetDevice(prev));
+}
+void Engine::set_stream(void *stream)
+{
+  if( shards_.size() != 1 ) throw std::runtime_error("rokifd_b200: set_stream needs a single-device engine");
+  Shard *s = shards_[0];
+  CK(cudaSetDevice(s->dev));
+  CK(cudaStreamSynchronize(s->stream));
+  if( s->own_stream && s->stream ) CK(cudaStreamDestroy(s->stream));
+  s->stream = (cudaStream_t)stream; s->own_stream = false;
+}
+void *Engine::device_ptr(int si, int which, int *ld, int *B)
+{
+  if( si < 0 || si >= (int)shards_.size() ) return nullptr;
+  Shard *s = shards_[si];
+  if( ld ) *ld = s->ld; if( B ) *B = s->B;
+  switch(which){ case 0: return s->st.q[s->cur]; case 1: return s->st.qd[s->cur]; case 2: return s->st.qdd; case 3: return s->st.u; default: return nullptr; }
+}
+
+/* ---- host <-> device state movement ------------------------------------------------------ */
+static void h2d_scatter(Shard &s, const double *src, int n, double *dst)
+{
+  if( n <= 0 ) return;
+  CK(cudaMemcpyAsync(s.dstage, src + (size_t)s.e0*n, (size_t)s.B*n*sizeof(double), cudaMemcpyHostToDevice, s.stream));
+  rkfd_scatter_kernel<<<(s.B+255)/256, 256, 0, s.stream>>>(s.dstage, dst, s.B, n, s.ld);
+  CK(cudaGetLastError());
+}
+static void d2h_gather(Shard &s, const double *src, int n, double *dst)
+{
+  if( n <= 0 ) return;
+  rkfd_gather_kernel<<<(s.B+255)/256, 256, 0, s.stream>>>(src, s.dstage, s.B, n, s.ld);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst + (size_t)s.e0*n, s.dstage, (size_t)s.B*n*sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+}
+
+void Engine::set_state(const double *q, const double *qd)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev));
+    if( q )  h2d_scatter(*s, q,  model_.nq, s->st.q[s->cur]);
+    if( qd ) h2d_scatter(*s, qd, model_.nq, s->st.qd[s->cur]);
+  }
+  /* the staging copy reads caller memory asynchronously when it is pinned: finish before returning */
+  for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream)); }
+  CK(cudaSetDevice(prev));
+}
+void Engine::get_state(double *q, double *qd, double *qdd)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev));
+    if( q )   d2h_gather(*s, s->st.q[s->cur],  model_.nq, q);
+    if( qd )  d2h_gather(*s, s->st.qd[s->cur], model_.nq, qd);
+    if( qdd ) d2h_gather(*s, s->st.qdd,        model_.nq, qdd);
+  }
+  for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream)); }
+  CK(cudaSetDevice(prev));
+}
+void Engine::set_motor_input(const double *u)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); h2d_scatter(*s, u, model_.nl, s->st.u); }
+  for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream)); }
+  CK(cudaSetDevice(prev));
+}
+void Engine::set_motor_input_one(int env, int link, double value)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){
+    if( env < s->e0 || env >= s->e0 + s->B ) continue;
+    CK(cudaSetDevice(s->dev));
+    CK(cudaMemcpyAsync(s->st.u + (size_t)link*s->ld + (env - s->e0), &value, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  CK(cudaSetDevice(prev));
+}
+
+void Engine::get_pivot(int *type, double *prev_trq)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  const int nq = model_.nq;
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev));
+    if( prev_trq ) d2h_gather(*s, s->st.piv_prev, nq, prev_trq);
+    CK(cudaStreamSynchronize(s->stream));
+    if( type ){
+      std::vector<unsigned int> bits(s->B);
+      CK(cudaMemcpy(bits.data(), s->st.piv_type, s->B*sizeof(unsigned int), cudaMemcpyDeviceToHost));
+      for(int e=0;e<s->B;e++) for(int j=0;j<nq;j++) type[(size_t)(s->e0+e)*nq + j] = (bits[e] >> j) & 1u;
+    }
+  }
+  CK(cudaSetDevice(prev));
+}
+void Engine::set_pivot(const int *type, const double *prev_trq)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  const int nq = model_.nq;
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev));
+    if( prev_trq ) h2d_scatter(*s, prev_trq, nq, s->st.piv_prev);
+    CK(cudaStreamSynchronize(s->stream));
+    if( type ){
+      std::vector<unsigned int> bits(s->B, 0u);
+      for(int e=0;e<s->B;e++) for(int j=0;j<nq;j++) if( type[(size_t)(s->e0+e)*nq + j] ) bits[e] |= 1u << j;
+      CK(cudaMemcpy(s->st.piv_type, bits.data(), s->B*sizeof(unsigned int), cudaMemcpyHostToDevice));
+    }
+  }
+  CK(cudaSetDevice(prev));
+}
+void Engine::get_contact(int *active, int *type, double *ref, double *f)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  const int ns = model_.nslot;
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev));
+    if( ref ) d2h_gather(*s, s->st.cref, 3*ns, ref);
+    if( f )   d2h_gather(*s, s->st.cf,   3*ns, f);
+    CK(cudaStreamSynchronize(s->stream));
+    if( active || type ){
+      std::vector<unsigned long long> bits(s->B);
+      CK(cudaMemcpy(bits.data(), s->st.cflags, s->B*sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      for(int e=0;e<s->B;e++) for(int k=0;k<ns;k++){
+        if( active ) active[(size_t)(s->e0+e)*ns + k] = (int)((bits[e] >> (2*k)) & 1ull);
+        if( type )   type[(size_t)(s->e0+e)*ns + k]   = (int)((bits[e] >> (2*k+1)) & 1ull);
+      }
+    }
+  }
+  CK(cudaSetDevice(prev));
+}
+void Engine::set_contact(const int *active, const int *type, const double *ref)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  const int ns = model_.nslot;
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev));
+    if( ref ) h2d_scatter(*s, ref, 3*ns, s->st.cref);
+    CK(cudaStreamSynchronize(s->stream));
+    if( active && type ){
+      std::vector<unsigned long long> bits(s->B, 0ull);
+      for(int e=0;e<s->B;e++) for(int k=0;k<ns;k++){
+        if( active[(size_t)(s->e0+e)*ns + k] ) bits[e] |= 1ull << (2*k);
+        if( type[(size_t)(s->e0+e)*ns + k] )   bits[e] |= 2ull << (2*k);
+      }
+      CK(cudaMemcpy(s->st.cflags, bits.data(), s->B*sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+  }
+  CK(cudaSetDevice(prev));
+}
+void Engine::get_status(int *status)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy(status + s->e0, s->st.status, s->B*sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  CK(cudaSetDevice(prev));
+}
+
+}  // namespace rkfd

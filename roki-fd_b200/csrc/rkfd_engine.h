@@ -1,0 +1,66 @@
+/* rkfd_engine.h - batched device engine: B independent environments of one model, sharded over the
+ * devices of one process in contiguous env blocks (no inter-device traffic on the step path,
+ * SURVEY.md section 8e).  No CUDA type appears in this header. */
+#ifndef RKFD_ENGINE_H
+#define RKFD_ENGINE_H
+
+#include <string>
+#include <vector>
+
+#include "rkfd_types.h"
+
+namespace rkfd {
+
+struct Shard;
+
+class Engine {
+ public:
+  /* devices empty -> the current device */
+  Engine(const ModelDev &model, int B, const std::vector<int> &devices);
+  ~Engine();
+  Engine(const Engine&) = delete;
+  Engine &operator=(const Engine&) = delete;
+
+  int B() const { return B_; }
+  const ModelDev &model() const { return model_; }
+  int num_shards() const { return (int)shards_.size(); }
+
+  /* host arrays are env-major: q[B][nq], u[B][nl], contact arrays [B][nslot](x3) */
+  void set_state(const double *q, const double *qd);
+  void get_state(double *q, double *qd, double *qdd);
+  void set_motor_input(const double *u);
+  void set_motor_input_one(int env, int link, double value);
+  void get_pivot(int *type, double *prev_trq);
+  void set_pivot(const int *type, const double *prev_trq);
+  void get_contact(int *active, int *type, double *ref, double *f);
+  void set_contact(const int *active, const int *type, const double *ref);
+  void get_status(int *status);
+
+  void eval(bool ref);        /* one dynamics evaluation on the committed state */
+  void step(int nsteps);      /* rkFDUpdate x nsteps, asynchronous */
+  void sync();
+
+  /* single-shard only: run on a caller-owned stream (so that the caller's events bracket the kernels) */
+  void set_stream(void *cuda_stream);
+  /* device pointers of shard `s` (SoA [k][ld], see StateDev): 0 q, 1 qd, 2 qdd, 3 u */
+  void *device_ptr(int s, int which, int *ld, int *B);
+  long long launches() const { return launches_; }
+
+ private:
+  void upload_model(Shard &s);
+  void launch(Shard &s, int mode, int nsteps);
+  ModelDev model_;
+  int B_;
+  std::vector<Shard*> shards_;
+  long long launches_ = 0;
+  int id_;
+};
+
+/* throws std::runtime_error with the CUDA error string */
+void cuda_check(int err, const char *what);
+int device_count();
+/* sustained fp64 FMA throughput of the current device, TFLOP/s (register-resident DFMA loop on all SMs) */
+double measure_fp64_tflops();
+
+}  // namespace rkfd
+#endif

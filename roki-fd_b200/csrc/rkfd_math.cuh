@@ -1,0 +1,100 @@
+/* rkfd_math.cuh - register-resident 3-D / 6-D helpers for the fused step kernel.
+ * Everything is fp64 and fully unrolled by construction (named members, no indexed arrays) so that
+ * nothing is demoted to local memory. */
+#ifndef RKFD_MATH_CUH
+#define RKFD_MATH_CUH
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define RKFD_HD __host__ __device__ __forceinline__
+#else
+#define RKFD_HD inline
+#endif
+
+namespace rkfd {
+
+struct V3 { double x, y, z; };
+struct M3 { double xx, xy, xz, yx, yy, yz, zx, zy, zz; };   /* row-major names: first index = row */
+struct S3 { double xx, xy, xz, yy, yz, zz; };               /* symmetric */
+struct V6 { V3 l, a; };                                      /* (linear, angular) */
+
+RKFD_HD V3 v3(double x, double y, double z){ V3 r; r.x=x; r.y=y; r.z=z; return r; }
+RKFD_HD V3 operator+(V3 a, V3 b){ return v3(a.x+b.x, a.y+b.y, a.z+b.z); }
+RKFD_HD V3 operator-(V3 a, V3 b){ return v3(a.x-b.x, a.y-b.y, a.z-b.z); }
+RKFD_HD V3 operator-(V3 a){ return v3(-a.x,-a.y,-a.z); }
+RKFD_HD V3 operator*(double k, V3 a){ return v3(k*a.x, k*a.y, k*a.z); }
+RKFD_HD double dot(V3 a, V3 b){ return a.x*b.x + a.y*b.y + a.z*b.z; }
+RKFD_HD V3 cross(V3 a, V3 b){ return v3(a.y*b.z-a.z*b.y, a.z*b.x-a.x*b.z, a.x*b.y-a.y*b.x); }
+RKFD_HD double norm(V3 a){ return sqrt(dot(a,a)); }
+
+RKFD_HD V3 mul(const M3 &m, V3 v){ return v3(m.xx*v.x+m.xy*v.y+m.xz*v.z, m.yx*v.x+m.yy*v.y+m.yz*v.z, m.zx*v.x+m.zy*v.y+m.zz*v.z); }
+RKFD_HD V3 tmul(const M3 &m, V3 v){ return v3(m.xx*v.x+m.yx*v.y+m.zx*v.z, m.xy*v.x+m.yy*v.y+m.zy*v.z, m.xz*v.x+m.yz*v.y+m.zz*v.z); }
+RKFD_HD V3 mul(const S3 &m, V3 v){ return v3(m.xx*v.x+m.xy*v.y+m.xz*v.z, m.xy*v.x+m.yy*v.y+m.yz*v.z, m.xz*v.x+m.yz*v.y+m.zz*v.z); }
+RKFD_HD V3 col0(const M3 &m){ return v3(m.xx,m.yx,m.zx); }
+RKFD_HD V3 col1(const M3 &m){ return v3(m.xy,m.yy,m.zy); }
+RKFD_HD V3 col2(const M3 &m){ return v3(m.xz,m.yz,m.zz); }
+RKFD_HD M3 from_cols(V3 a, V3 b, V3 c){ M3 m; m.xx=a.x; m.yx=a.y; m.zx=a.z; m.xy=b.x; m.yy=b.y; m.zy=b.z; m.xz=c.x; m.yz=c.y; m.zz=c.z; return m; }
+RKFD_HD M3 ident3(){ M3 m; m.xx=1; m.xy=0; m.xz=0; m.yx=0; m.yy=1; m.yz=0; m.zx=0; m.zy=0; m.zz=1; return m; }
+RKFD_HD M3 transpose(const M3 &a){ M3 m; m.xx=a.xx; m.xy=a.yx; m.xz=a.zx; m.yx=a.xy; m.yy=a.yy; m.yz=a.zy; m.zx=a.xz; m.zy=a.yz; m.zz=a.zz; return m; }
+RKFD_HD M3 mm(const M3 &a, const M3 &b){
+  M3 m;
+  m.xx=a.xx*b.xx+a.xy*b.yx+a.xz*b.zx; m.xy=a.xx*b.xy+a.xy*b.yy+a.xz*b.zy; m.xz=a.xx*b.xz+a.xy*b.yz+a.xz*b.zz;
+  m.yx=a.yx*b.xx+a.yy*b.yx+a.yz*b.zx; m.yy=a.yx*b.xy+a.yy*b.yy+a.yz*b.zy; m.yz=a.yx*b.xz+a.yy*b.yz+a.yz*b.zz;
+  m.zx=a.zx*b.xx+a.zy*b.yx+a.zz*b.zx; m.zy=a.zx*b.xy+a.zy*b.yy+a.zz*b.zy; m.zz=a.zx*b.xz+a.zy*b.yz+a.zz*b.zz;
+  return m; }
+/* a^T b */
+RKFD_HD M3 tmm(const M3 &a, const M3 &b){ return mm(transpose(a), b); }
+RKFD_HD M3 ms(const M3 &a, const S3 &b){
+  M3 m;
+  m.xx=a.xx*b.xx+a.xy*b.xy+a.xz*b.xz; m.xy=a.xx*b.xy+a.xy*b.yy+a.xz*b.yz; m.xz=a.xx*b.xz+a.xy*b.yz+a.xz*b.zz;
+  m.yx=a.yx*b.xx+a.yy*b.xy+a.yz*b.xz; m.yy=a.yx*b.xy+a.yy*b.yy+a.yz*b.yz; m.yz=a.yx*b.xz+a.yy*b.yz+a.yz*b.zz;
+  m.zx=a.zx*b.xx+a.zy*b.xy+a.zz*b.xz; m.zy=a.zx*b.xy+a.zy*b.yy+a.zz*b.yz; m.zz=a.zx*b.xz+a.zy*b.yz+a.zz*b.zz;
+  return m; }
+/* R A R^T for symmetric A (only the 6 distinct entries of the result) */
+RKFD_HD S3 rot_sym(const M3 &R, const S3 &A){
+  M3 t = ms(R, A); S3 s;
+  s.xx=t.xx*R.xx+t.xy*R.xy+t.xz*R.xz; s.xy=t.xx*R.yx+t.xy*R.yy+t.xz*R.yz; s.xz=t.xx*R.zx+t.xy*R.zy+t.xz*R.zz;
+  s.yy=t.yx*R.yx+t.yy*R.yy+t.yz*R.yz; s.yz=t.yx*R.zx+t.yy*R.zy+t.yz*R.zz;
+  s.zz=t.zx*R.zx+t.zy*R.zy+t.zz*R.zz;
+  return s; }
+/* R B R^T for general B */
+RKFD_HD M3 rot_gen(const M3 &R, const M3 &B){ return mm(mm(R,B), transpose(R)); }
+/* [p x] M  (rows of the result are cross products of p with the columns of M) */
+RKFD_HD M3 skew_mul(V3 p, const M3 &m){ return from_cols(cross(p,col0(m)), cross(p,col1(m)), cross(p,col2(m))); }
+/* M [p x] : column j = M (p x e_j) */
+RKFD_HD M3 mul_skew(const S3 &m, V3 p){
+  return from_cols(mul(m, v3(0, p.z, -p.y)), mul(m, v3(-p.z, 0, p.x)), mul(m, v3(p.y, -p.x, 0))); }
+
+/* angle-axis vector -> rotation matrix (Rodrigues) */
+RKFD_HD M3 aa_to_mat(V3 aa){
+  double th2 = dot(aa,aa), A, B;
+  if( th2 < 1.0e-24 ){ A = 1.0; B = 0.5; }
+  else { double th = sqrt(th2); A = sin(th)/th; B = (1.0-cos(th))/th2; }
+  /* R = I + A K + B K^2, K = [aa x] ; K^2 = aa aa^T - th2 I */
+  M3 m;
+  m.xx = 1.0 + B*(aa.x*aa.x - th2); m.yy = 1.0 + B*(aa.y*aa.y - th2); m.zz = 1.0 + B*(aa.z*aa.z - th2);
+  m.xy = -A*aa.z + B*aa.x*aa.y; m.yx =  A*aa.z + B*aa.x*aa.y;
+  m.xz =  A*aa.y + B*aa.x*aa.z; m.zx = -A*aa.y + B*aa.x*aa.z;
+  m.yz = -A*aa.x + B*aa.y*aa.z; m.zy =  A*aa.x + B*aa.y*aa.z;
+  return m; }
+
+/* aa <- log( R(w) R(aa) ) through unit quaternions */
+RKFD_HD V3 aa_cascade(V3 aa, V3 w){
+  double th, s, q10, q20; V3 q1, q2;
+  th = norm(aa);
+  if( th < 1.0e-12 ){ q10 = 1.0; q1 = 0.5*aa; } else { s = sin(0.5*th)/th; q10 = cos(0.5*th); q1 = s*aa; }
+  th = norm(w);
+  if( th < 1.0e-12 ){ q20 = 1.0; q2 = 0.5*w; } else { s = sin(0.5*th)/th; q20 = cos(0.5*th); q2 = s*w; }
+  double q0 = q20*q10 - q2.x*q1.x - q2.y*q1.y - q2.z*q1.z;
+  V3 q = v3( q20*q1.x + q2.x*q10 + q2.y*q1.z - q2.z*q1.y,
+             q20*q1.y - q2.x*q1.z + q2.y*q10 + q2.z*q1.x,
+             q20*q1.z + q2.x*q1.y - q2.y*q1.x + q2.z*q10 );
+  if( q0 < 0 ){ q0 = -q0; q = -q; }
+  double n = norm(q);
+  if( n < 1.0e-12 ) return 2.0*q;
+  th = 2.0*atan2(n,q0);
+  return (th/n)*q; }
+
+}  // namespace rkfd
+#endif

@@ -1,0 +1,143 @@
+/* rkfd_model.cpp - flattening of registered chains into the device tables (host only). */
+#include "rkfd_model.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "rkfd_core.cuh"
+
+namespace rkfd {
+
+static void mat3_mul(const double *a, const double *b, double *c){
+  double t[9];
+  for(int i=0;i<3;i++) for(int j=0;j<3;j++){ t[3*i+j] = 0; for(int k=0;k<3;k++) t[3*i+j] += a[3*i+k]*b[3*k+j]; }
+  std::memcpy(c, t, sizeof t);
+}
+static void mat3_mulv(const double *a, const double *x, double *y){
+  double t[3];
+  for(int i=0;i<3;i++) t[i] = a[3*i]*x[0] + a[3*i+1]*x[1] + a[3*i+2]*x[2];
+  std::memcpy(y, t, sizeof t);
+}
+
+bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
+{
+  std::memset(&m, 0, sizeof m);
+  m.dt = w.dt; m.friction_weight = w.friction_weight; m.pyramid = w.pyramid; m.max_iter = w.max_iter; m.solver = w.solver;
+  if( w.pyramid > MAX_PYRAMID || w.pyramid < 1 ){ err = "pyramid order out of range"; return false; }
+  { /* rkFDCrateSinCosTable (reference rkfd_util.c:199-214) with the Vert offset -pi/pyramid (rkfd_vert.c:369) */
+    const double off = -M_PI / w.pyramid, dth = 2.0*M_PI / w.pyramid; double th = 0.0;
+    for(int i=0;i<w.pyramid;i++, th+=dth){ m.sc_sin[i] = std::sin(th+off); m.sc_cos[i] = std::cos(th+off); }
+  }
+
+  std::vector<std::string> link_stuff;
+  struct StatBox { BoxDev b; std::string stuff; };
+  std::vector<StatBox> boxes;
+
+  /* ---- moving chains -> forest of links (registration order); static chains -> world boxes */
+  int nl = 0, nq = 0;
+  for(const ChainHost *ch : w.chains){
+    if( ch->is_static() ){
+      std::vector<std::vector<double>> fr(ch->links.size(), std::vector<double>(12));
+      for(size_t i=0;i<ch->links.size();i++){
+        const LinkHost &l = ch->links[i]; double R[9], p[3];
+        std::memcpy(R, l.Ro, sizeof R); std::memcpy(p, l.po, sizeof p);
+        if( l.parent >= 0 ){
+          if( l.parent >= (int)i ){ err = "link order: parent must precede child"; return false; }
+          const double *Rp = fr[l.parent].data(), *pp = Rp + 9; double t[3];
+          mat3_mul(Rp, l.Ro, R); mat3_mulv(Rp, l.po, t); for(int k=0;k<3;k++) p[k] = pp[k] + t[k];
+        }
+        std::memcpy(fr[i].data(), R, sizeof R); std::memcpy(fr[i].data()+9, p, sizeof p);
+        for(const BoxShape &bs : l.boxes){
+          StatBox sb; double c[3];
+          std::memcpy(sb.b.R, R, sizeof R); mat3_mulv(R, bs.center, c);
+          for(int k=0;k<3;k++) sb.b.p[k] = p[k] + c[k];
+          sb.b.half[0] = 0.5*bs.depth; sb.b.half[1] = 0.5*bs.width; sb.b.half[2] = 0.5*bs.height;
+          sb.stuff = l.stuff; boxes.push_back(sb);
+        }
+      }
+      continue;
+    }
+    const int base = nl;
+    for(size_t i=0;i<ch->links.size();i++){
+      const LinkHost &l = ch->links[i];
+      if( nl >= MAX_LINKS ){ err = "too many links (MAX_LINKS)"; return false; }
+      if( l.parent >= (int)i ){ err = "link order: parent must precede child"; return false; }
+      LinkDev &d = m.link[nl];
+      std::memcpy(d.Ro, l.Ro, sizeof d.Ro); std::memcpy(d.po, l.po, sizeof d.po);
+      d.mass = l.mass;
+      for(int k=0;k<3;k++){ d.com[k] = l.com[k]; d.mc[k] = l.mass*l.com[k]; }
+      { /* Io = Ic - m [c x]^2 = Ic + m (|c|^2 E - c c^T) */
+        const double *c = l.com, c2 = c[0]*c[0]+c[1]*c[1]+c[2]*c[2]; double Io[9];
+        for(int r=0;r<3;r++) for(int q=0;q<3;q++) Io[3*r+q] = l.inertia[3*r+q] + l.mass*((r==q?c2:0.0) - c[r]*c[q]);
+        d.Io[0]=Io[0]; d.Io[1]=0.5*(Io[1]+Io[3]); d.Io[2]=0.5*(Io[2]+Io[6]); d.Io[3]=Io[4]; d.Io[4]=0.5*(Io[5]+Io[7]); d.Io[5]=Io[8];
+      }
+      d.stiffness = l.stiffness; d.viscosity = l.viscosity; d.coulomb = l.coulomb; d.sfriction = l.sfriction;
+      d.mtype = l.motor.type;
+      /* [EXT A-6] DC motor constants folded once on the host */
+      d.m_tin = l.motor.gear*l.motor.k*l.motor.admittance;
+      d.m_reg = (l.motor.gear*l.motor.k)*(l.motor.gear*l.motor.k)*l.motor.admittance;
+      d.m_jm  = l.motor.gear*l.motor.gear*(l.motor.rotor_inertia + l.motor.gear_inertia);
+      d.m_min = l.motor.min; d.m_max = l.motor.max;
+      if( d.mtype == M_TRQ ){ d.m_jm = 0; }
+      d.parent = l.parent >= 0 ? l.parent + base : -1;
+      d.jtype = l.jtype; d.ndof = jtype_ndof(l.jtype); d.qofs = nq; nq += d.ndof;
+      if( d.ndof != 1 ) d.mtype = M_NONE;
+      d.cell_begin = m.ncell;
+      for(const auto &sh : l.shapes){
+        const int nv = (int)sh.size()/3;
+        if( m.ncell >= MAX_CELLS ){ err = "too many collision cells (MAX_CELLS)"; return false; }
+        if( m.nvert + nv > MAX_VERTS ){ err = "too many collision vertices (MAX_VERTS)"; return false; }
+        CellDev &c = m.cell[m.ncell++]; c.link = nl; c.vofs = m.nvert; c.nvert = nv;
+        std::memcpy(m.vert + 3*m.nvert, sh.data(), 3*nv*sizeof(double)); m.nvert += nv;
+      }
+      d.cell_end = m.ncell;
+      link_stuff.push_back(l.stuff);
+      nl++;
+    }
+  }
+  m.nl = nl; m.nq = nq;
+  if( nq > 32 ){ err = "too many joint dofs for the pivot bitmask (32)"; return false; }
+  if( (int)boxes.size() > MAX_BOXES ){ err = "too many static boxes (MAX_BOXES)"; return false; }
+  m.nbox = (int)boxes.size();
+  for(int b=0;b<m.nbox;b++) m.box[b] = boxes[b].b;
+
+  /* ---- contact pairs (cell x box) with their contact info (reference rkfd_sim.c:200-207, :266-271) */
+  int sofs = 0;
+  for(int c=0;c<m.ncell;c++){
+    m.cell[c].pair_begin = m.npair;
+    for(int b=0;b<m.nbox;b++){
+      if( m.npair >= MAX_PAIRS ){ err = "too many contact pairs (MAX_PAIRS)"; return false; }
+      PairDev &p = m.pair[m.npair++];
+      p.cell = c; p.box = b; p.sofs = sofs; sofs += m.cell[c].nvert;
+      const ContactInfoHost *ci = &w.cidef;
+      const std::string &sa = link_stuff[m.cell[c].link], &sb = boxes[b].stuff;
+      for(const auto &e : w.ci) if( (e.a==sa && e.b==sb) || (e.a==sb && e.b==sa) ){ ci = &e; break; }
+      p.type = ci->type; p.K = ci->K; p.L = ci->L; p.E = ci->E; p.V = ci->V; p.SF = ci->SF; p.KF = ci->KF;
+      if( p.type == C_ELASTIC ) m.has_elastic = 1; else m.has_rigid = 1;
+    }
+    m.cell[c].pair_end = m.npair;
+  }
+  m.nslot = sofs;
+  if( m.nslot > MAX_SLOTS ){ err = "too many contact slots (MAX_SLOTS)"; return false; }
+  m.need_world = m.npair > 0;
+
+  /* ---- topology flags and the scratch slot map */
+  for(int i=0;i<nl;i++) if( m.link[i].parent >= 0 ) m.link[m.link[i].parent].nchild++;
+  for(int i=0;i<nl;i++){ LinkDev &d = m.link[i]; d.serial = ( d.parent >= 0 && d.parent == i-1 && m.link[d.parent].nchild == 1 ) ? 1 : 0;
+    d.branch_slot = d.accum_slot = d.wext_slot = -1; }
+  int slot = 0;
+  for(int i=0;i<nl;i++){ m.link[i].slot = slot; slot += link_slot_count(m.link[i].jtype, m.has_rigid); }
+  for(int i=0;i<nl;i++){
+    LinkDev &d = m.link[i];
+    if( d.parent >= 0 && !d.serial ){
+      LinkDev &p = m.link[d.parent];
+      if( p.branch_slot < 0 ){ p.branch_slot = slot; slot += BRANCH_SLOTS; p.accum_slot = slot; slot += ACCUM_SLOTS; }
+    }
+    if( d.cell_end > d.cell_begin ){ d.wext_slot = slot; slot += WEXT_SLOTS; }
+  }
+  m.rk_slot = slot; slot += 4*nq;
+  m.nscratch = slot;
+  return true;
+}
+
+}  // namespace rkfd

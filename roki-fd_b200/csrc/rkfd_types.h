@@ -1,0 +1,95 @@
+/* rkfd_types.h - plain-data tables shared by the host engine and the sm_100a kernels.
+ *
+ * One `ModelDev` describes what every environment has in common (the registered chains flattened
+ * into a forest of links, collision vertex clouds, static boxes, contact pairs, properties).  It
+ * lives in __constant__ memory: all threads of a warp read the same entry, so the constant cache
+ * broadcasts it and most entries are consumed directly as DFMA operands.
+ * Reference data model: rkFD / rkFDCellDat (reference include/roki_fd/rkfd_sim.h:24-52),
+ * rkFDPrp (rkfd_property.h:15-22).
+ */
+#ifndef RKFD_TYPES_H
+#define RKFD_TYPES_H
+
+#include <stdint.h>
+
+namespace rkfd {
+
+constexpr int MAX_LINKS = 32;
+constexpr int MAX_CELLS = 8;
+constexpr int MAX_VERTS = 64;
+constexpr int MAX_BOXES = 4;
+constexpr int MAX_PAIRS = 16;
+constexpr int MAX_SLOTS = 32;      /* contact slots per env handled by the fused kernel (2 flag bits each) */
+constexpr int MAX_PYRAMID = 16;
+
+enum JointType : int { J_FIXED = 0, J_REVOL = 1, J_PRISM = 2, J_SPHER = 3, J_FLOAT = 4 };
+enum MotorType : int { M_NONE = 0, M_DC = 1, M_TRQ = 2 };
+enum ContactType : int { C_RIGID = 0, C_ELASTIC = 1 };
+enum FricType : int { F_SF = 0, F_KF = 1 };
+enum SolverType : int { S_VERT = 0, S_MLCP = 1, S_VOLUME = 2 };
+
+constexpr double GRAVITY = 9.80665;   /* RoKi RK_G */
+constexpr double ZTOL = 1.0e-12;      /* ZM zTOL */
+
+struct LinkDev {
+  double Ro[9];        /* org frame rotation w.r.t. parent, row-major */
+  double po[3];        /* org frame position */
+  double mass;
+  double com[3];
+  double mc[3];        /* mass * com */
+  double Io[6];        /* inertia about the link origin (xx,xy,xz,yy,yz,zz) = Ic - m [c x]^2 */
+  double stiffness, viscosity, coulomb, sfriction;
+  double m_tin;        /* gear*k*admittance  (input torque per volt) */
+  double m_reg;        /* (gear*k)^2*admittance (back-EMF resistance per rad/s) */
+  double m_jm;         /* gear^2*(rotor+gear inertia) */
+  double m_min, m_max;
+  int parent, jtype, mtype, ndof, qofs;
+  int slot;            /* first scratch slot of this link */
+  int serial;          /* 1: parent == index-1 and the parent has no other child (carry in registers) */
+  int nchild;          /* number of children */
+  int branch_slot;     /* >=0: slots where this link publishes frame/velocity/acceleration for non-serial children */
+  int accum_slot;      /* >=0: slots where non-serial children accumulate articulated inertia/bias (27) */
+  int wext_slot;       /* >=0: slots of the external wrench (6) (links that carry collision cells) */
+  int cell_begin, cell_end;
+};
+
+struct CellDev { int link, vofs, nvert, pair_begin, pair_end; };
+struct BoxDev { double R[9], p[3], half[3]; };
+struct PairDev { int cell, box, sofs, type; double K, L, E, V, SF, KF; };
+
+struct ModelDev {
+  int nl, nq, ncell, nbox, npair, nslot, nvert;
+  int need_world;      /* any collision cell: world frames must be propagated */
+  int has_rigid, has_elastic;
+  int solver, pyramid, max_iter;
+  int nscratch;        /* scratch slots (doubles) per env */
+  int rk_slot;         /* first slot of the RKG stage state: QS[nq], QDS[nq], PQ[nq], PQD[nq] */
+  double dt, friction_weight;
+  double sc_sin[MAX_PYRAMID], sc_cos[MAX_PYRAMID];
+  LinkDev link[MAX_LINKS];
+  CellDev cell[MAX_CELLS];
+  BoxDev box[MAX_BOXES];
+  PairDev pair[MAX_PAIRS];
+  double vert[3 * MAX_VERTS];
+};
+
+/* Per-environment state in HBM, structure-of-arrays with the environment index fastest:
+ * element (k, e) of an array lives at base[k*ld + e].  Thread e of a warp therefore reads
+ * consecutive 8-byte words: every load/store is one fully coalesced 256-byte request. */
+struct StateDev {
+  int B;               /* environments on this device */
+  int ld;              /* leading dimension (B rounded up to 32) */
+  double *q[2], *qd[2];   /* double-buffered committed state [nq][ld] */
+  double *qdd;            /* [nq][ld] acceleration of the last reference evaluation */
+  double *u;              /* [nl][ld] motor input per link */
+  double *piv_prev;       /* [nq][ld] previous driving torque per dof */
+  unsigned int *piv_type; /* [ld] bit j: dof j pivot is kinetic   (nq <= 32) */
+  unsigned long long *cflags; /* [ld] 2 bits per slot: bit 2s active, bit 2s+1 kinetic */
+  double *cref;           /* [nslot*3][ld] anchor _ref in the box frame */
+  double *cf;             /* [nslot*3][ld] contact force (world) of the last reference evaluation */
+  double *scratch;        /* optional global scratch [nscratch][ld] when shared memory is too small */
+  int *status;            /* [ld] per-env status word (bit0: non-finite acceleration) */
+};
+
+}  // namespace rkfd
+#endif

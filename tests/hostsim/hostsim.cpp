@@ -1,0 +1,124 @@
+/* hostsim.cpp - TEST-ONLY host harness: compiles the kernel core (roki-fd_b200/csrc/rkfd_core.cuh)
+ * with g++ and runs it one environment at a time on the CPU, so that the arithmetic of the sm_100a
+ * kernel can be checked against the oracle where no GPU exists (`-m "not gpu"` tests).
+ * It is NOT part of the product: librokifd_b200.so does not contain it and nothing under
+ * roki-fd_b200/ loads it.  The product path has no CPU fallback. */
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rkfd_core.cuh"
+#include "rkfd_model.h"
+
+using namespace rkfd;
+
+namespace {
+void sincos(double x, double *s, double *c){ *s = std::sin(x); *c = std::cos(x); }
+}
+
+struct HostCtx {
+  StateDev st; int e, cur; std::vector<double> scr;
+  double &S(int k){ return scr[k]; }
+  double gld(const double *p, int k) const { return p[(size_t)k*st.ld + e]; }
+  void gst(double *p, int k, double v){ p[(size_t)k*st.ld + e] = v; }
+};
+
+struct HostSim {
+  ModelDev model; WorldHost world; std::vector<ChainHost*> chains; std::string err;
+  int B = 0, cur = 0; StateDev st; std::vector<void*> allocs;
+};
+
+template <class T> static T *halloc(HostSim *h, size_t n){ void *p = std::calloc(n ? n : 1, sizeof(T)); h->allocs.push_back(p); return (T*)p; }
+
+extern "C" {
+
+/* flat description: same packing as oracle/rkfd_oracle.h (ORK_LINK_ND doubles, 4 ints per link);
+ * chain_nl[c] links per chain; stuff ids are turned into names "s<id>" */
+HostSim *hostsim_new(int nchain, const int *chain_nl, const int *li, const double *ld)
+{
+  HostSim *h = new HostSim; int k = 0;
+  for(int c=0;c<nchain;c++){
+    ChainHost *ch = new ChainHost; ch->name = "chain";
+    for(int i=0;i<chain_nl[c];i++,k++){
+      LinkHost l; const double *d = ld + 37*k;
+      l.parent = li[4*k]; l.jtype = li[4*k+1]; l.motor.type = li[4*k+2]; l.stuff = "s" + std::to_string(li[4*k+3]);
+      std::memcpy(l.Ro, d, 72); std::memcpy(l.po, d+9, 24); l.mass = d[12]; std::memcpy(l.com, d+13, 24); std::memcpy(l.inertia, d+16, 72);
+      l.stiffness = d[25]; l.viscosity = d[26]; l.coulomb = d[27]; l.sfriction = d[28];
+      l.motor.k = d[29]; l.motor.admittance = d[30]; l.motor.gear = d[31]; l.motor.rotor_inertia = d[32];
+      l.motor.gear_inertia = d[33]; l.motor.min = d[34]; l.motor.max = d[35];
+      ch->links.push_back(l);
+    }
+    h->chains.push_back(ch); h->world.chains.push_back(ch);
+  }
+  h->world.cidef.type = C_RIGID; h->world.cidef.K = 1000.0; h->world.cidef.L = 1.0; h->world.cidef.SF = 0.5; h->world.cidef.KF = 0.3;
+  return h;
+}
+void hostsim_add_cell(HostSim *h, int chain, int link, int nvert, const double *v)
+{ h->chains[chain]->links[link].shapes.push_back(std::vector<double>(v, v+3*nvert)); }
+void hostsim_add_box(HostSim *h, int chain, int link, const double *center, double d, double w, double ht)
+{ BoxShape b; std::memcpy(b.center, center, 24); b.depth = d; b.width = w; b.height = ht; h->chains[chain]->links[link].boxes.push_back(b); }
+void hostsim_add_contact_info(HostSim *h, int sa, int sb, int type, double K, double L, double E, double V, double SF, double KF)
+{ ContactInfoHost c; c.a = "s"+std::to_string(sa); c.b = "s"+std::to_string(sb); c.type = type; c.K=K; c.L=L; c.E=E; c.V=V; c.SF=SF; c.KF=KF; h->world.ci.push_back(c); }
+void hostsim_set_prp(HostSim *h, double dt, int pyramid, double fw, int max_iter, int solver)
+{ h->world.dt = dt; h->world.pyramid = pyramid; h->world.friction_weight = fw; h->world.max_iter = max_iter; h->world.solver = solver; }
+
+/* returns 0 on success */
+int hostsim_finalize(HostSim *h, int B)
+{
+  if( !build_model(h->world, h->model, h->err) ) return 1;
+  const ModelDev &m = h->model; h->B = B;
+  const int nq = m.nq > 0 ? m.nq : 1, nl = m.nl > 0 ? m.nl : 1, ns = m.nslot > 0 ? m.nslot : 1;
+  StateDev &st = h->st; std::memset(&st, 0, sizeof st); st.B = B; st.ld = B;
+  for(int k=0;k<2;k++){ st.q[k] = halloc<double>(h, (size_t)nq*B); st.qd[k] = halloc<double>(h, (size_t)nq*B); }
+  st.qdd = halloc<double>(h, (size_t)nq*B); st.u = halloc<double>(h, (size_t)nl*B); st.piv_prev = halloc<double>(h, (size_t)nq*B);
+  st.piv_type = halloc<unsigned int>(h, B); st.cflags = halloc<unsigned long long>(h, B);
+  st.cref = halloc<double>(h, (size_t)3*ns*B); st.cf = halloc<double>(h, (size_t)3*ns*B); st.status = halloc<int>(h, B);
+  return 0;
+}
+const char *hostsim_error(HostSim *h){ return h->err.c_str(); }
+int hostsim_nq(HostSim *h){ return h->model.nq; }
+int hostsim_nl(HostSim *h){ return h->model.nl; }
+int hostsim_nslot(HostSim *h){ return h->model.nslot; }
+int hostsim_nscratch(HostSim *h){ return h->model.nscratch; }
+void hostsim_free(HostSim *h){ for(void *p : h->allocs) std::free(p); for(auto *c : h->chains) delete c; delete h; }
+
+void hostsim_set_state(HostSim *h, const double *q, const double *qd, const double *u)
+{
+  const int nq = h->model.nq, nl = h->model.nl, B = h->B;
+  for(int e=0;e<B;e++){
+    for(int j=0;j<nq;j++){ h->st.q[h->cur][(size_t)j*B+e] = q[(size_t)e*nq+j]; h->st.qd[h->cur][(size_t)j*B+e] = qd[(size_t)e*nq+j]; }
+    if( u ) for(int j=0;j<nl;j++) h->st.u[(size_t)j*B+e] = u[(size_t)e*nl+j];
+  }
+}
+void hostsim_get_state(HostSim *h, double *q, double *qd, double *qdd)
+{
+  const int nq = h->model.nq, B = h->B;
+  for(int e=0;e<B;e++) for(int j=0;j<nq;j++){
+    q[(size_t)e*nq+j] = h->st.q[h->cur][(size_t)j*B+e]; qd[(size_t)e*nq+j] = h->st.qd[h->cur][(size_t)j*B+e];
+    qdd[(size_t)e*nq+j] = h->st.qdd[(size_t)j*B+e]; }
+}
+void hostsim_get_contact(HostSim *h, int *active, int *type, double *ref, double *f)
+{
+  const int ns = h->model.nslot, B = h->B;
+  for(int e=0;e<B;e++) for(int k=0;k<ns;k++){
+    active[(size_t)e*ns+k] = (int)((h->st.cflags[e] >> (2*k)) & 1ull); type[(size_t)e*ns+k] = (int)((h->st.cflags[e] >> (2*k+1)) & 1ull);
+    for(int a=0;a<3;a++){ ref[((size_t)e*ns+k)*3+a] = h->st.cref[(size_t)(3*k+a)*B+e]; f[((size_t)e*ns+k)*3+a] = h->st.cf[(size_t)(3*k+a)*B+e]; } }
+}
+void hostsim_get_pivot(HostSim *h, int *type, double *prev)
+{
+  const int nq = h->model.nq, B = h->B;
+  for(int e=0;e<B;e++) for(int j=0;j<nq;j++){ type[(size_t)e*nq+j] = (h->st.piv_type[e] >> j) & 1u; prev[(size_t)e*nq+j] = h->st.piv_prev[(size_t)j*B+e]; }
+}
+/* mode 0: nsteps steps; 1: eval; 2: committing eval */
+void hostsim_run(HostSim *h, int mode, int nsteps)
+{
+  for(int e=0;e<h->B;e++){
+    HostCtx ctx; ctx.st = h->st; ctx.e = e; ctx.cur = h->cur; ctx.scr.assign(h->model.nscratch + 1, 0.0);
+    Core<HostCtx> core(ctx);
+    if( mode == 0 ) core.run_steps(h->model, nsteps); else core.run_eval(h->model, mode == 2);
+  }
+  if( mode == 0 && (nsteps & 1) ) h->cur ^= 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI (librokifd_b200.so via
+rokifd_b200.capi), against the CPU oracle on the same seeded inputs.  Tolerances follow
+BASELINE.json's north_star: accelerations and contact forces within 1e-9 relative per evaluation/step;
+short-horizon trajectories within the tolerance stated in each test."""
+import numpy as np
+import pytest
+
+import rokifd_b200  # noqa: F401
+from rokifd_b200 import chains as ch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from rokifd_b200 import capi as c
+    assert c.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return c
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def gpu_world(capi, world, q, qd, u):
+    fd, cells = capi.create_world(world, B=q.shape[0])
+    fd.batch_set_state(q, qd)
+    fd.batch_set_motor_input(u)
+    fd.update_init()
+    return fd
+
+
+WORLDS = {
+    "c2_arm7": lambda: ch.world_c2(),
+    "c3_arm7_penalty": lambda: ch.world_c3(base_z=0.1),
+    "c1_box_hardsoft": lambda: ch.World(chains=[ch.box(), ch.floor_hardsoft()],
+                                        contact_info=[c for c in ch.contact_info_table() if c.type == "elastic"]
+                                        + [ch.ContactInfo("ground", "body", "elastic", E=500.0, V=5.0)]),
+    "c1_serial_arm2dof": lambda: ch.world_c1_serial(),
+    "arm_and_box": lambda: ch.World(chains=[ch.arm_2dof(), ch.box(), ch.floor_soft()],
+                                    contact_info=[ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0)]),
+}
+
+
+@pytest.mark.parametrize("name", list(WORLDS))
+def test_init_evaluation_matches_oracle(capi, oracle, name):
+    """rkFDUpdateInit's committing evaluation: q'', contact forces/state, friction pivots (1e-9 relative)."""
+    w = WORLDS[name]()
+    B = 256
+    q, qd, u = ch.sample_state(w, B, seed=7)
+    if "box" in name:
+        o = w.nq - 6
+        q[:, o + 2] = np.linspace(-0.02, 0.12, B)
+    fd = gpu_world(capi, w, q, qd, u)
+    gq, gqd, gqdd = fd.batch_get_state()
+    a, t, r, f = fd.batch_get_contact()
+    pt, pp = fd.batch_get_pivot()
+    assert (fd.batch_get_status() == 0).all()
+    ow = oracle.OracleWorld(w)
+    worst = 0.0
+    for b in range(B):
+        e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
+        ref = e.eval(True)
+        worst = max(worst, relerr(gqdd[b], ref))
+        oa, ot, orr, of = e.get_contact()
+        if w.nslot:
+            assert (a[b] == oa).all() and (t[b][oa == 1] == ot[oa == 1]).all(), (name, b)
+            assert np.allclose(f[b][oa == 1], of[oa == 1], rtol=1e-9, atol=1e-9)
+            assert np.allclose(r[b][oa == 1], orr[oa == 1], rtol=1e-12, atol=1e-12)
+        opt, opp = e.get_pivot()
+        assert (pt[b] == opt).all() and np.allclose(pp[b], opp, rtol=1e-9, atol=1e-9)
+    assert worst < 1e-9, (name, worst)
+    fd.destroy()
+
+
+@pytest.mark.parametrize("name", list(WORLDS))
+def test_teacher_forced_steps_match_oracle(capi, oracle, name):
+    """Per-step parity with the GPU state reset to the oracle state every step (level 3)."""
+    w = WORLDS[name]()
+    B, nsteps = 64, 5
+    q, qd, u = ch.sample_state(w, B, seed=13)
+    if "box" in name:
+        o = w.nq - 6
+        q[:, o + 2] = np.linspace(0.0, 0.12, B)
+    fd = gpu_world(capi, w, q, qd, u)
+    ow = oracle.OracleWorld(w)
+    envs = []
+    for b in range(B):
+        e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b]); e.update_init(); envs.append(e)
+    for s in range(nsteps):
+        fd.update()
+        gq, gqd, gqdd = fd.batch_get_state()
+        oq = np.zeros_like(gq); oqd = np.zeros_like(gq); oqdd = np.zeros_like(gq)
+        oa = np.zeros((B, max(w.nslot, 1)), np.int32); ot = oa.copy(); orr = np.zeros((B, max(w.nslot, 1), 3))
+        opt = np.zeros((B, w.nq), np.int32); opp = np.zeros((B, w.nq))
+        for b, e in enumerate(envs):
+            e.update()
+            oq[b], oqd[b], oqdd[b] = e.get_state()
+            if w.nslot:
+                oa[b], ot[b], orr[b], _ = e.get_contact()
+            opt[b], opp[b] = e.get_pivot()
+        assert relerr(gq, oq) < 1e-9 and relerr(gqd, oqd) < 1e-9, (name, s)
+        for b in range(B):
+            assert relerr(gqdd[b], oqdd[b]) < 1e-7, (name, s, b, relerr(gqdd[b], oqdd[b]))
+        # teacher forcing: put the oracle's full state on the device
+        fd.batch_set_state(oq, oqd)
+        fd.batch_set_pivot(opt, opp)
+        if w.nslot:
+            fd.batch_set_contact(oa[:, :w.nslot], ot[:, :w.nslot], orr[:, :w.nslot])
+    fd.destroy()
+
+
+@pytest.mark.parametrize("name,tol", [("c2_arm7", 1e-8), ("c3_arm7_penalty", 1e-6), ("c1_box_hardsoft", 1e-6)])
+def test_free_running_trajectory(capi, oracle, name, tol):
+    """100 free-running steps: <=1e-8 relative on q without contact, <=1e-6 with contact, for >= 99% of the
+    environments (contact/friction mode flips at zTOL-sized margins are counted and reported, not hidden)."""
+    w = WORLDS[name]()
+    B, nsteps = 128, 100
+    q, qd, u = ch.sample_state(w, B, seed=21)
+    if "box" in name:
+        q[:, 2] = np.linspace(0.03, 0.15, B)
+    fd = gpu_world(capi, w, q, qd, u)
+    fd.update_n(nsteps)
+    gq, gqd, _ = fd.batch_get_state()
+    oq, oqd, _, _ = oracle.OracleWorld(w).batch_run(q, qd, u, nsteps=nsteps)
+    err = np.array([relerr(gq[b], oq[b]) for b in range(B)])
+    frac_ok = (err < tol).mean()
+    print("free-running %s: %d/%d envs within %.0e (max err %.2e)" % (name, (err < tol).sum(), B, tol, err.max()))
+    assert frac_ok >= 0.99
+    fd.destroy()
+
+
+@pytest.mark.parametrize("kind", ["branching", "float_root_tree", "spherical", "prismatic_mix"])
+def test_random_topologies(capi, oracle, kind):
+    rng = np.random.default_rng({"branching": 1, "float_root_tree": 2, "spherical": 3, "prismatic_mix": 4}[kind])
+    for trial in range(3):
+        if kind == "branching":
+            c = ch.random_chain(rng, 9, jtypes=("revolute", "prismatic"), branching=True, motors=True)
+        elif kind == "float_root_tree":
+            c = ch.random_chain(rng, 8, jtypes=("revolute", "fixed", "spherical"), root="float", branching=True)
+        elif kind == "spherical":
+            c = ch.random_chain(rng, 5, jtypes=("spherical", "revolute"))
+        else:
+            c = ch.random_chain(rng, 6, jtypes=("revolute", "prismatic", "fixed"), motors=True)
+        w = ch.World(chains=[c])
+        B = 32
+        q = rng.uniform(-1.5, 1.5, (B, w.nq)); qd = rng.uniform(-2, 2, (B, w.nq)); u = rng.uniform(-6, 6, (B, w.nl))
+        fd = gpu_world(capi, w, q, qd, u)
+        _, _, gqdd = fd.batch_get_state()
+        ow = oracle.OracleWorld(w)
+        for b in range(B):
+            e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
+            assert relerr(gqdd[b], e.eval(True)) < 1e-9, (kind, trial, b)
+        fd.update_n(5)
+        gq, gqd, _ = fd.batch_get_state()
+        oq, oqd, _, _ = ow.batch_run(q, qd, u, nsteps=5)
+        assert relerr(gq, oq) < 1e-9 and relerr(gqd, oqd) < 1e-8, (kind, trial)
+        fd.destroy()
+
+
+def test_scalar_api_drop_in(capi, oracle):
+    """B=1 through the scalar reference call sequence of example/chain/boxdrop_hardsoft_test.c:
+    Create, ContactInfo, ChainReg, SetDis, SetSolver, UpdateInit, Update..., reading fd->dis/vel/acc."""
+    w = ch.World(chains=[ch.box(), ch.floor_soft()], contact_info=[ch.ContactInfo("soft", "body", "elastic", E=100.0, V=1.0)])
+    fd = capi.RkFD()
+    for ci in w.contact_info:
+        fd.contact_info_add(ci)
+    cell = fd.chain_reg(w.chains[0])
+    fd.chain_reg(w.chains[1])
+    dis = np.array([0.0, 0.0, 0.3, 0.3, -0.2, 0.1])
+    fd.chain_set_dis(cell, dis)
+    fd.prp_set(dt=0.001)
+    fd.set_solver("Vert")
+    fd.update_init()
+    e = oracle.OracleWorld(w).env()
+    e.set_state(dis, np.zeros(6)); e.update_init()
+    assert relerr(fd.acc, e.get_state()[2]) < 1e-9
+    for s in range(300):
+        fd.update(); e.update()
+    oq, oqd, oqdd = e.get_state()
+    assert abs(fd.time - 0.3) < 1e-12
+    assert relerr(fd.dis, oq) < 1e-8 and relerr(fd.vel, oqd) < 1e-7
+    fd.update_destroy()
+    fd.destroy()
+
+
+def test_shard_count_invariance_and_full_size(capi):
+    """C3 at BASELINE.json's full batch (262,144 envs): results do not depend on how the batch is cut
+    (two engines with different B see bit-identical per-env results), and every env stays finite."""
+    w = ch.world_c3()
+    B = 262144
+    q, qd, u = ch.sample_state(w, B, seed=20260418)
+    fd = gpu_world(capi, w, q, qd, u)
+    fd.update_n(10)
+    gq, gqd, gqdd = fd.batch_get_state()
+    assert (fd.batch_get_status() == 0).all()
+    assert np.isfinite(gq).all() and np.isfinite(gqd).all() and np.isfinite(gqdd).all()
+    fd.destroy()
+    lo, hi = 100000, 100000 + 4096
+    fd2 = gpu_world(capi, w, q[lo:hi], qd[lo:hi], u[lo:hi])
+    fd2.update_n(10)
+    sq, sqd, sqdd = fd2.batch_get_state()
+    assert np.array_equal(sq, gq[lo:hi]) and np.array_equal(sqd, gqd[lo:hi]) and np.array_equal(sqdd, gqdd[lo:hi])
+    fd2.destroy()
+
+
+def test_multi_device_sharding(capi, oracle):
+    """env e -> device floor(e*G/B); per-env results identical to the single-device run."""
+    G = capi.device_count()
+    if G < 2:
+        pytest.skip("needs >= 2 GPUs")
+    w = ch.world_c3()
+    B = 8192
+    q, qd, u = ch.sample_state(w, B, seed=5)
+    fd1 = gpu_world(capi, w, q, qd, u)
+    fd1.update_n(10)
+    ref = fd1.batch_get_state()
+    fd1.destroy()
+    fd, _ = capi.create_world(w, B=B, devices=list(range(G)))
+    fd.batch_set_state(q, qd); fd.batch_set_motor_input(u); fd.update_init(); fd.update_n(10)
+    got = fd.batch_get_state()
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    fd.destroy()

@@ -1,0 +1,131 @@
+"""The sm_100a kernel core (roki-fd_b200/csrc/rkfd_core.cuh) compiled for the host by the test-only
+harness tests/hostsim, against the oracle.  This checks the kernel ARITHMETIC where no GPU exists;
+the GPU parity tests proper are in test_gpu_parity.py (-m gpu) and go through the C-ABI."""
+import numpy as np
+import pytest
+
+import rokifd_b200  # noqa: F401
+from rokifd_b200 import chains as ch
+from hostsim_py import HostSim
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def oracle_run(oracle, world, q, qd, u, nsteps, init=True):
+    ow = oracle.OracleWorld(world)
+    out = []
+    for b in range(q.shape[0]):
+        e = ow.env()
+        e.set_state(q[b], qd[b])
+        e.set_motor_input(u[b])
+        if init:
+            e.update_init()
+        for _ in range(nsteps):
+            e.update()
+        out.append((e.get_state(), e.get_contact(), e.get_pivot()))
+    return out
+
+
+WORLDS = {
+    "c2_arm7": lambda: ch.world_c2(),
+    "c3_arm7_penalty": lambda: ch.world_c3(base_z=0.1),
+    "c1_box_hardsoft": lambda: ch.World(chains=[ch.box(), ch.floor_hardsoft()],
+                                        contact_info=[c for c in ch.contact_info_table() if c.type == "elastic"]
+                                        + [ch.ContactInfo("ground", "body", "elastic", E=500.0, V=5.0)]),
+    "c1_serial_arm2dof": lambda: ch.world_c1_serial(),
+}
+
+
+@pytest.mark.parametrize("name", list(WORLDS))
+def test_eval_matches_oracle(oracle, name):
+    w = WORLDS[name]()
+    B = 24
+    q, qd, u = ch.sample_state(w, B, seed=7)
+    if name == "c1_box_hardsoft":
+        q[:, 2] = np.linspace(-0.02, 0.12, B)
+    hs = HostSim(w, B)
+    hs.set_state(q, qd, u)
+    hs.eval(ref=True)
+    _, _, qdd = hs.get_state()
+    a, t, r, f = hs.get_contact()
+    pt, pp = hs.get_pivot()
+    ow = oracle.OracleWorld(w)
+    for b in range(B):
+        e = ow.env()
+        e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
+        ref = e.eval(True)
+        assert relerr(qdd[b, :w.nq], ref) < 1e-9, (name, b)
+        oa, ot, orr, of = e.get_contact()
+        if w.nslot:
+            assert (a[b] == oa).all() and (t[b][oa == 1] == ot[oa == 1]).all()
+            assert np.allclose(f[b][oa == 1], of[oa == 1], rtol=1e-9, atol=1e-9)
+            assert np.allclose(r[b][oa == 1], orr[oa == 1], rtol=1e-12, atol=1e-12)
+        opt, opp = e.get_pivot()
+        assert (pt[b, :w.nq] == opt).all() and np.allclose(pp[b, :w.nq], opp, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", list(WORLDS))
+def test_steps_match_oracle(oracle, name):
+    w = WORLDS[name]()
+    B, nsteps = 12, 20
+    q, qd, u = ch.sample_state(w, B, seed=11)
+    if name == "c1_box_hardsoft":
+        q[:, 2] = np.linspace(0.0, 0.12, B)
+    hs = HostSim(w, B)
+    hs.set_state(q, qd, u)
+    hs.eval(ref=True)          # rkFDUpdateInit
+    hs.step(nsteps)
+    hq, hqd, hqdd = hs.get_state()
+    ref = oracle_run(oracle, w, q, qd, u, nsteps)
+    for b in range(B):
+        (oq, oqd, oqdd), (oa, ot, orr, of), _ = ref[b]
+        assert relerr(hq[b, :w.nq], oq) < 1e-8, (name, b)
+        assert relerr(hqd[b, :w.nq], oqd) < 1e-7, (name, b)
+
+
+@pytest.mark.parametrize("kind", ["branching", "float_root_tree", "spherical", "prismatic_mix"])
+def test_random_topologies_match_oracle(oracle, kind):
+    rng = np.random.default_rng({"branching": 1, "float_root_tree": 2, "spherical": 3, "prismatic_mix": 4}[kind])
+    for trial in range(4):
+        if kind == "branching":
+            c = ch.random_chain(rng, 9, jtypes=("revolute", "prismatic"), branching=True, motors=True)
+        elif kind == "float_root_tree":
+            c = ch.random_chain(rng, 8, jtypes=("revolute", "fixed", "spherical"), root="float", branching=True)
+        elif kind == "spherical":
+            c = ch.random_chain(rng, 5, jtypes=("spherical", "revolute"))
+        else:
+            c = ch.random_chain(rng, 6, jtypes=("revolute", "prismatic", "fixed"), motors=True)
+        w = ch.World(chains=[c])
+        B = 4
+        q = rng.uniform(-1.5, 1.5, (B, w.nq)); qd = rng.uniform(-2, 2, (B, w.nq)); u = rng.uniform(-6, 6, (B, w.nl))
+        hs = HostSim(w, B)
+        hs.set_state(q, qd, u)
+        hs.eval(ref=True)
+        _, _, qdd = hs.get_state()
+        ow = oracle.OracleWorld(w)
+        for b in range(B):
+            e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
+            assert relerr(qdd[b, :w.nq], e.eval(True)) < 1e-9, (kind, trial, b)
+        hs.step(5)
+        hq, hqd, _ = hs.get_state()
+        ref = oracle_run(oracle, w, q, qd, u, 5)
+        for b in range(B):
+            assert relerr(hq[b, :w.nq], ref[b][0][0]) < 1e-9 and relerr(hqd[b, :w.nq], ref[b][0][1]) < 1e-8, (kind, trial, b)
+
+
+def test_two_chains_in_one_world(oracle):
+    """arm + free box registered in one rkFD (forest with two roots), like arm_box_test.c minus the arm-box pairs."""
+    w = ch.World(chains=[ch.arm_2dof(), ch.box(), ch.floor_soft()],
+                 contact_info=[ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0)])
+    B = 6
+    q, qd, u = ch.sample_state(w, B, seed=3)
+    q[:, 4] = np.linspace(0.0, 0.1, B)
+    hs = HostSim(w, B)
+    hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(10)
+    hq, hqd, _ = hs.get_state()
+    ref = oracle_run(oracle, w, q, qd, u, 10)
+    for b in range(B):
+        assert relerr(hq[b], ref[b][0][0]) < 1e-9
