@@ -1,0 +1,117 @@
+"""Host-side tests of the C-ABI library that need no GPU: the library loads, exports every symbol
+include/roki_fd/rkfd_b200.h declares, mirrors the reference's registration bookkeeping, reads ZTK
+files, and fails loudly (no CPU fallback) when no device exists."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rokifd_b200  # noqa: F401
+from rokifd_b200 import capi, chains as ch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "roki_fd", "rkfd_b200.h")).read()
+    hdr = "\n".join(l for l in hdr.splitlines() if not l.lstrip().startswith("#"))
+    names = re.findall(r"__ROKI_FD_EXPORT\s+[^;(]*?\b(\w+)\s*\(", hdr)
+    assert len(names) > 80
+    L = C.CDLL(capi.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_registration_bookkeeping():
+    """fd->size, cell offsets and state windows after Reg / Unreg (reference rkfd_sim.c:79-155, 188-255)."""
+    fd = capi.RkFD()
+    c_arm = fd.chain_reg(ch.arm_2dof())
+    c_box = fd.chain_reg(ch.box())
+    c_flr = fd.chain_reg(ch.floor())
+    assert fd.size == 2 + 6 and fd.link_num == 3 + 1
+    fd.chain_set_dis(c_arm, [0.1, 0.2])
+    fd.chain_set_dis(c_box, [1, 2, 3, 4, 5, 6])
+    fd.chain_set_vel(c_box, [6, 5, 4, 3, 2, 1])
+    assert np.allclose(fd.dis, [0.1, 0.2, 1, 2, 3, 4, 5, 6])
+    assert np.allclose(fd.vel, [0, 0, 6, 5, 4, 3, 2, 1])
+    assert fd.chain_unreg(c_arm)
+    assert fd.size == 6 and np.allclose(fd.dis, [1, 2, 3, 4, 5, 6])     # state of the remaining chains is kept
+    assert not fd.chain_unreg(capi.RkFDCell(c_flr.h + 8))                # unknown handle -> false
+    fd.destroy()
+
+
+def test_defaults_and_solver_table():
+    """rkFDCreate defaults (rkfd_property.c:10-18) and the per-solver default contact info."""
+    L = capi.lib()
+    fd = capi.RkFD()
+
+    class Prp(C.Structure):
+        _fields_ = [("dt", C.c_double), ("pyramid", C.c_int), ("fw", C.c_double), ("max_iter", C.c_int), ("vel_eps", C.c_double)]
+
+    class Head(C.Structure):
+        _fields_ = [("t", C.c_double), ("prp", Prp)]
+
+    h = C.cast(fd.h, C.POINTER(Head)).contents
+    assert (h.t, h.prp.dt, h.prp.pyramid, h.prp.fw, h.prp.max_iter, h.prp.vel_eps) == (0.0, 0.001, 8, 100.0, 10, 1e-8)
+    for s in ("Vert", "MLCP", "Volume"):
+        fd.set_solver(s)
+    fd.prp_set(dt=0.002, pyramid=6)
+    h = C.cast(fd.h, C.POINTER(Head)).contents
+    assert h.prp.dt == 0.002 and h.prp.pyramid == 6
+    fd.destroy()
+
+
+def test_no_cpu_fallback():
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    fd, _ = capi.create_world(ch.world_c2(), B=4)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        fd.update_init()
+    fd.update()            # rkFDUpdate cannot fail (returns fd); it must not crash without an engine
+    with pytest.raises(RuntimeError):
+        fd.batch_get_state()
+    fd.destroy()
+
+
+def test_ztk_reader():
+    c = capi.RkChain(ztk=os.path.join(GOLD, "arm2.ztk"))
+    assert c.link_num == 3 and c.joint_size == 2
+    L = capi.lib()
+    v = L.zVecAlloc(2)
+    L.rkChainGetJointDisAll.restype = C.c_void_p
+    L.rkChainGetJointDisAll.argtypes = [C.c_void_p, C.c_void_p]
+    L.rkChainGetJointDisAll(c.h, v)
+    buf = C.cast(C.cast(v, C.POINTER(C.c_void_p))[1], C.POINTER(C.c_double))
+    assert np.allclose([buf[0], buf[1]], np.deg2rad([30, -45]))
+    L.zVecFree(v)
+    c.destroy()
+    with pytest.raises(RuntimeError):
+        capi.RkChain(ztk=os.path.join(GOLD, "missing.ztk"))
+    fd = capi.RkFD()
+    assert fd.contact_info_scan_file(os.path.join(GOLD, "contacts.ztk"))
+    assert not fd.contact_info_scan_file(os.path.join(GOLD, "missing.ztk"))
+    assert fd.chain_reg_file(os.path.join(GOLD, "cube.ztk")) is not None
+    assert fd.chain_reg_file(os.path.join(GOLD, "softfloor.ztk")) is not None
+    assert fd.chain_reg_file(os.path.join(GOLD, "missing.ztk")) is None
+    assert fd.size == 6
+    assert np.allclose(fd.dis, [0.1, -0.2, 0.3] + list(np.deg2rad([10, 20, 30])))
+    fd.destroy()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/example/model"), reason="reference tree not present")
+def test_ztk_reader_on_reference_models():
+    """The reader accepts the reference's own model files unmodified."""
+    d = "/root/reference/example/model"
+    expect = {"box.ztk": (1, 6), "floor.ztk": (1, 0), "floor_hardsoft.ztk": (2, 0), "arm_2DoF.ztk": (3, 2),
+              "arm_2DoF_trq.ztk": (3, 2), "puma.ztk": (7, 6), "mighty.ztk": (25, 26), "arm.ztk": (6, 12), "dualarm.ztk": (None, None)}
+    for f, (nl, nq) in expect.items():
+        c = capi.RkChain(ztk=os.path.join(d, f))
+        if nl is not None:
+            assert (c.link_num, c.joint_size) == (nl, nq), f
+        c.destroy()
+    fd = capi.RkFD()
+    assert fd.contact_info_scan_file(os.path.join(d, "contactinfo.ztk"))
+    fd.destroy()
