@@ -548,23 +548,23 @@ struct Core {
     const bool ref = (stage == ST_REF) || (stage == ST_EVAL_REF);
     pass1(m, ref); pass2(m, ref); pass3(m, stage);
   }
-  /* rkFDUpdate x nsteps (reference rkfd_sim.c:560-566) */
-  RKFD_HD void run_steps(const ModelDev &m, int nsteps){
+  /* mode 0: rkFDUpdate x nsteps (reference rkfd_sim.c:560-566); mode 1 / 2: a single non-committing /
+   * committing evaluation on the committed state (2 = rkFDUpdateInit's t=0 evaluation).  One stage loop so
+   * that the evaluation body is instantiated once. */
+  RKFD_HD void run(const ModelDev &m, int mode, int nsteps){
     load_flags();
+    const int first = mode == 0 ? ST_K1 : ( mode == 2 ? ST_EVAL_REF : ST_EVAL );
+    const int last  = mode == 0 ? ST_REF : first;
+    if( mode != 0 ) nsteps = 1;
+#pragma unroll 1
     for(int s=0;s<nsteps;s++){
       load_stage_state(m);
 #pragma unroll 1
-      for(int stage=ST_K1; stage<=ST_REF; stage++){
+      for(int stage=first; stage<=last; stage++){
         if( stage == ST_REF ) c.cur ^= 1;   /* the output buffer now holds the committed state */
         evaluate(m, stage);
       }
     }
-    store_flags();
-  }
-  /* a single evaluation on the committed state (rkFDUpdateInit's t=0 evaluation when ref) */
-  RKFD_HD void run_eval(const ModelDev &m, bool ref){
-    load_flags(); load_stage_state(m);
-    evaluate(m, ref ? ST_EVAL_REF : ST_EVAL);
     store_flags();
   }
 };

@@ -33,12 +33,15 @@ void cuda_check(int err, const char *what)
 
 int device_count(){ int n = 0; if( cudaGetDeviceCount(&n) != cudaSuccess ) return 0; return n; }
 
+extern __shared__ double rkfd_smem[];
+
 template <int BLOCK, bool GSCR>
 struct DevCtx {
-  StateDev st; int e, cur; double *sm;
+  StateDev st; int e, cur, tid;
+  /* scratch element k of this thread: shared-memory column [k*BLOCK + tid] (LDS/STS, conflict-free) */
   __device__ __forceinline__ double &S(int k){
     if( GSCR ) return st.scratch[(size_t)k*st.ld + e];
-    return sm[k*BLOCK];
+    return rkfd_smem[k*BLOCK + tid];
   }
   __device__ __forceinline__ double gld(const double *p, int k) const { return p[(size_t)k*st.ld + e]; }
   __device__ __forceinline__ void gst(double *p, int k, double v){ p[(size_t)k*st.ld + e] = v; }
@@ -48,13 +51,11 @@ struct DevCtx {
 template <int BLOCK, bool GSCR>
 __global__ void __launch_bounds__(BLOCK) rkfd_step_kernel(StateDev st, int cur, int mode, int nsteps)
 {
-  extern __shared__ double rkfd_smem[];
   const int e = blockIdx.x*BLOCK + threadIdx.x;
   if( e >= st.B ) return;
-  DevCtx<BLOCK,GSCR> ctx; ctx.st = st; ctx.e = e; ctx.cur = cur; ctx.sm = rkfd_smem + threadIdx.x;
+  DevCtx<BLOCK,GSCR> ctx; ctx.st = st; ctx.e = e; ctx.cur = cur; ctx.tid = threadIdx.x;
   Core<DevCtx<BLOCK,GSCR>> core(ctx);
-  if( mode == 0 ) core.run_steps(c_model, nsteps);
-  else core.run_eval(c_model, mode == 2);
+  core.run(c_model, mode, nsteps);
 }
 
 /* env-major host layout [B][n] <-> device SoA [n][ld] */

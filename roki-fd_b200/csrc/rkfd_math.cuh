@@ -8,8 +8,10 @@
 
 #if defined(__CUDACC__)
 #define RKFD_HD __host__ __device__ __forceinline__
+#define RKFD_RARE __host__ __device__ __noinline__     /* rare paths (multi-DoF joints): keep them out of the hot code */
 #else
 #define RKFD_HD inline
+#define RKFD_RARE inline
 #endif
 
 namespace rkfd {
@@ -67,7 +69,7 @@ RKFD_HD M3 mul_skew(const S3 &m, V3 p){
   return from_cols(mul(m, v3(0, p.z, -p.y)), mul(m, v3(-p.z, 0, p.x)), mul(m, v3(p.y, -p.x, 0))); }
 
 /* angle-axis vector -> rotation matrix (Rodrigues) */
-RKFD_HD M3 aa_to_mat(V3 aa){
+RKFD_RARE M3 aa_to_mat(V3 aa){
   double th2 = dot(aa,aa), A, B;
   if( th2 < 1.0e-24 ){ A = 1.0; B = 0.5; }
   else { double th = sqrt(th2); A = sin(th)/th; B = (1.0-cos(th))/th2; }
@@ -80,7 +82,7 @@ RKFD_HD M3 aa_to_mat(V3 aa){
   return m; }
 
 /* aa <- log( R(w) R(aa) ) through unit quaternions */
-RKFD_HD V3 aa_cascade(V3 aa, V3 w){
+RKFD_RARE V3 aa_cascade(V3 aa, V3 w){
   double th, s, q10, q20; V3 q1, q2;
   th = norm(aa);
   if( th < 1.0e-12 ){ q10 = 1.0; q1 = 0.5*aa; } else { s = sin(0.5*th)/th; q10 = cos(0.5*th); q1 = s*aa; }

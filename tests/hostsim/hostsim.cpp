@@ -116,7 +116,7 @@ void hostsim_run(HostSim *h, int mode, int nsteps)
   for(int e=0;e<h->B;e++){
     HostCtx ctx; ctx.st = h->st; ctx.e = e; ctx.cur = h->cur; ctx.scr.assign(h->model.nscratch + 1, 0.0);
     Core<HostCtx> core(ctx);
-    if( mode == 0 ) core.run_steps(h->model, nsteps); else core.run_eval(h->model, mode == 2);
+    core.run(h->model, mode, nsteps);
   }
   if( mode == 0 && (nsteps & 1) ) h->cur ^= 1;
 }
