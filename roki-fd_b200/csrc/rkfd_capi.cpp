@@ -345,7 +345,7 @@ extern "C" void rkFDUpdateInit(rkFD *fd)
     if( fd->ode.form != RKFD_ODE2_Regular || fd->ode.integrator != RKFD_ODE_RKG ) throw std::runtime_error("only the Regular/RKG integrator is implemented");
     std::string err;
     if( !build_model(w, fi->model, err) ) throw std::runtime_error(err);
-    if( fi->model.has_rigid ) throw std::runtime_error("rigid contact pairs (Vert/MLCP/Volume constraint solve) are not implemented on the device yet");
+    if( fi->model.has_rigid && w.solver == S_VOLUME ) throw std::runtime_error("rigid contact pairs with the Volume solver are not implemented on the device yet");
     fi->engine = new Engine(fi->model, fi->B, fi->devices);
     const int n = fd->size, nl = fi->model.nl, B = fi->B;
     /* initial state: the batched arrays when given, else the scalar state replicated over the envs */

@@ -24,9 +24,16 @@
 #include "rkfd_math.cuh"
 
 #if defined(__CUDACC__)
-#define RKFD_NOINLINE __host__ __device__ __noinline__
+#define RKFD_NOINLINE static __host__ __device__ __noinline__
 #else
-#define RKFD_NOINLINE
+#define RKFD_NOINLINE inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define RKFD_POPC64(x) __popcll(x)
+#define RKFD_FFS32(x) __ffs(x)
+#else
+#define RKFD_POPC64(x) __builtin_popcountll(x)
+#define RKFD_FFS32(x) __builtin_ffs(x)
 #endif
 
 namespace rkfd {
@@ -34,20 +41,28 @@ namespace rkfd {
 /* scratch slots per link by joint type */
 RKFD_HD int link_slot_count(int jtype, int has_rigid){
   switch(jtype){
-    case J_REVOL: case J_PRISM: return 10;    /* w,gd->U (6), sin, cos, Dinv, u */
-    case J_SPHER: return 36;                  /* U (18, w/gd aliased), Dinv (6), u (3), Rrel (9) */
-    case J_FLOAT: return has_rigid ? 39 : 18; /* a0 (6, w/gd aliased), Rrel (9), prel (3) [, IA^-1 (21)] */
+    case J_REVOL: case J_PRISM: return has_rigid ? 16 : 10;    /* w,gd->U (6), sin, cos, Dinv, u [, w,gd (6)] */
+    case J_SPHER: return has_rigid ? 42 : 36;                  /* U (18, w/gd aliased), Dinv (6), u (3), Rrel (9) [, w,gd] */
+    case J_FLOAT: return has_rigid ? 45 : 18; /* a0 (6, w/gd aliased), Rrel (9), prel (3) [, IA^-1 (21), w,gd (6)] */
     default: return 6;                        /* w, gd */
   }
+}
+/* offset of (w, gd) inside the link slots */
+RKFD_HD int link_w_offset(int jtype, int has_rigid){
+  if( !has_rigid ) return 0;
+  switch(jtype){ case J_REVOL: case J_PRISM: return 10; case J_SPHER: return 36; case J_FLOAT: return 39; default: return 0; }
 }
 constexpr int BRANCH_SLOTS = 15;   /* pass 1: Rw(9) pw(3) vl(3); pass 3: a(6) w(3) */
 constexpr int ACCUM_SLOTS = 27;    /* A(6) B(9) C(6) pf(3) pn(3) */
 constexpr int WEXT_SLOTS = 6;
+constexpr int FRAME_SLOTS = 24;    /* rigid worlds, links with cells: Rw(9) pw(3) vl(3) w(3) a(6) */
+constexpr int GEO_DOUBLES = 27;    /* per rigid contact: vw n t1 t2 d vel prob rl (8 x 3), slot, link, pair */
 
-enum StageMode : int { ST_K1 = 0, ST_K2 = 1, ST_K3 = 2, ST_K4 = 3, ST_REF = 4, ST_EVAL = 5, ST_EVAL_REF = 6 };
+enum StageMode : int { ST_K1 = 0, ST_K2 = 1, ST_K3 = 2, ST_K4 = 3, ST_REF = 4, ST_EVAL = 5, ST_EVAL_REF = 6,
+                       ST_PROBE = 7 /* acceleration pass of rkFDUpdateAccBias: no integrator bookkeeping, no q'' output */ };
 
 /* symmetric 6x6 inverse through Cholesky; a is the full row-major matrix, overwritten */
-RKFD_NOINLINE inline void spd6_inverse(double (&a)[36]){
+RKFD_NOINLINE void spd6_inverse(double (&a)[36]){
   double L[36], Li[36];
 #pragma unroll
   for(int k=0;k<36;k++){ L[k]=0; Li[k]=0; }
@@ -116,33 +131,56 @@ struct Core {
   static RKFD_HD M3 org_R(const LinkDev &L){ M3 m; m.xx=L.Ro[0]; m.xy=L.Ro[1]; m.xz=L.Ro[2]; m.yx=L.Ro[3]; m.yy=L.Ro[4]; m.yz=L.Ro[5]; m.zx=L.Ro[6]; m.zy=L.Ro[7]; m.zz=L.Ro[8]; return m; }
   static RKFD_HD V3 org_p(const LinkDev &L){ return v3(L.po[0],L.po[1],L.po[2]); }
 
-  /* link frame w.r.t. parent (R,p) and joint velocity (vJ,wJ, link frame) from the stage state and
-   * the joint data cached by pass 1 ([EXT A-3]) */
-  RKFD_HD void joint_xform(const ModelDev &m, const LinkDev &L, M3 &R, V3 &p, V3 &vJ, V3 &wJ){
+  /* link frame w.r.t. parent and joint velocity (vJ,wJ, link frame) from the stage state and the joint data
+   * cached by pass 1 ([EXT A-3]) */
+  RKFD_HD XF joint_xform(const ModelDev &m, const LinkDev &L, V3 &vJ, V3 &wJ){
     const int sl = L.slot, qs = m.rk_slot + L.qofs, qds = m.rk_slot + m.nq + L.qofs;
+    XF x; x.fast = 0; x.cls = L.rcls; x.c = 1.0; x.s = 0.0;
     vJ = v3(0,0,0); wJ = v3(0,0,0);
     switch(L.jtype){
     case J_REVOL: {
-      const double s = c.S(sl+6), co = c.S(sl+7);
-      const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
-      R = from_cols(co*o0 + s*o1, co*o1 - s*o0, col2(Ro)); p = org_p(L);
+      x.s = c.S(sl+6); x.c = c.S(sl+7); x.p = org_p(L);
+      if( L.rcls != RO_GENERAL ){ x.fast = 1; x.ptl = rz_tmul(x.c, x.s, v3(L.pol[0],L.pol[1],L.pol[2])); }
+      else {
+        const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
+        x.R = from_cols(x.c*o0 + x.s*o1, x.c*o1 - x.s*o0, col2(Ro)); x.ptl = tmul(x.R, x.p);
+      }
       wJ.z = c.S(qds);
     } break;
     case J_PRISM: {
-      R = org_R(L); p = org_p(L) + c.S(qs)*col2(R); vJ.z = c.S(qds);
+      x.R = org_R(L); x.p = org_p(L) + c.S(qs)*col2(x.R); x.ptl = tmul(x.R, x.p); vJ.z = c.S(qds);
     } break;
     case J_SPHER: {
-      R = ldm(sl+27); p = org_p(L);
-      wJ = tmul(R, mul(org_R(L), ld3(qds)));
+      x.R = ldm(sl+27); x.p = org_p(L); x.ptl = tmul(x.R, x.p);
+      wJ = tmul(x.R, mul(org_R(L), ld3(qds)));
     } break;
     case J_FLOAT: {
-      R = ldm(sl+6); p = ld3(sl+15);
+      x.R = ldm(sl+6); x.p = ld3(sl+15); x.ptl = tmul(x.R, x.p);
       const M3 Ro = org_R(L);
-      vJ = tmul(R, mul(Ro, ld3(qds))); wJ = tmul(R, mul(Ro, ld3(qds+3)));
+      vJ = tmul(x.R, mul(Ro, ld3(qds))); wJ = tmul(x.R, mul(Ro, ld3(qds+3)));
     } break;
-    default: R = org_R(L); p = org_p(L); break;
+    default: x.R = org_R(L); x.p = org_p(L); x.ptl = v3(L.pol[0],L.pol[1],L.pol[2]); break;
     }
+    return x;
   }
+
+  /* [EXT A-10] closest face of the box for a vertex inside it: first minimum depth over x,y,z; outward normal,
+   * right-handed tangents, projection of the vertex on that face (box frame) */
+  static RKFD_HD void box_face(const BoxDev &bx, const M3 &Rb, V3 vb, double dx, double dy, double dz,
+                               V3 &n, V3 &t1, V3 &t2, V3 &prob){
+    int amin = 0; double dmin = dx;
+    if( dy < dmin ){ dmin = dy; amin = 1; }
+    if( dz < dmin ){ dmin = dz; amin = 2; }
+    const double vba = amin==0 ? vb.x : ( amin==1 ? vb.y : vb.z );
+    const double sg = vba >= 0 ? 1.0 : -1.0;
+    const V3 b0 = col0(Rb), b1 = col1(Rb), b2 = col2(Rb);
+    n  = sg*( amin==0 ? b0 : ( amin==1 ? b1 : b2 ) );
+    t1 =      amin==0 ? b1 : ( amin==1 ? b2 : b0 );
+    t2 = sg*( amin==0 ? b2 : ( amin==1 ? b0 : b1 ) );
+    prob = vb;
+    if( amin==0 ) prob.x = sg*bx.half[0]; else if( amin==1 ) prob.y = sg*bx.half[1]; else prob.z = sg*bx.half[2];
+  }
+  static RKFD_HD M3 box_R(const BoxDev &bx){ M3 Rb; Rb.xx=bx.R[0]; Rb.xy=bx.R[1]; Rb.xz=bx.R[2]; Rb.yx=bx.R[3]; Rb.yy=bx.R[4]; Rb.yz=bx.R[5]; Rb.zx=bx.R[6]; Rb.zy=bx.R[7]; Rb.zz=bx.R[8]; return Rb; }
 
   /* ---- contact of the cells carried by link i: vertex-in-box detection ([EXT A-10]), elastic pairs:
    * penalty force + Coulomb clamp + wrench accumulation (rkfd_penalty.c:11-31, rkfd_util.c:239-282) */
@@ -163,18 +201,8 @@ struct Core {
           const double dx = bx.half[0]-fabs(vb.x), dy = bx.half[1]-fabs(vb.y), dz = bx.half[2]-fabs(vb.z);
           const bool inside = (dx > -ZTOL) && (dy > -ZTOL) && (dz > -ZTOL);
           if( !inside ){ cfl &= ~(abit|kbit); if( ref ){ c.gst(c.st.cf, 3*s, 0.0); c.gst(c.st.cf, 3*s+1, 0.0); c.gst(c.st.cf, 3*s+2, 0.0); } continue; }
-          /* closest face: first minimum over x,y,z */
-          int amin = 0; double dmin = dx;
-          if( dy < dmin ){ dmin = dy; amin = 1; }
-          if( dz < dmin ){ dmin = dz; amin = 2; }
-          const double vba = amin==0 ? vb.x : ( amin==1 ? vb.y : vb.z );
-          const double sg = vba >= 0 ? 1.0 : -1.0;
-          const V3 b0 = col0(Rb), b1 = col1(Rb), b2 = col2(Rb);
-          const V3 n  = sg*( amin==0 ? b0 : ( amin==1 ? b1 : b2 ) );
-          const V3 t1 =      amin==0 ? b1 : ( amin==1 ? b2 : b0 );
-          const V3 t2 = sg*( amin==0 ? b2 : ( amin==1 ? b0 : b1 ) );
-          V3 prob = vb;
-          if( amin==0 ) prob.x = sg*bx.half[0]; else if( amin==1 ) prob.y = sg*bx.half[1]; else prob.z = sg*bx.half[2];
+          V3 n, t1, t2, prob;
+          box_face(bx, Rb, vb, dx, dy, dz, n, t1, t2, prob);
           V3 refb;
           if( !(cfl & abit) ){           /* new contact: {SF, _ref = _pro} */
             cfl = (cfl | abit) & ~kbit; refb = prob;
@@ -222,45 +250,49 @@ struct Core {
         if( L.parent < 0 ){ Rw = ident3(); pw = v3(0,0,0); vl = v3(0,0,0); om = v3(0,0,0); gd = v3(0,0,-GRAVITY); }
         else {
           const LinkDev &P = m.link[L.parent];
-          om = ld3(P.slot); gd = ld3(P.slot+3);
+          om = ld3(P.wslot); gd = ld3(P.wslot+3);
           if( m.need_world ){ Rw = ldm(P.branch_slot); pw = ld3(P.branch_slot+9); vl = ld3(P.branch_slot+12); }
         }
       }
-      M3 R; V3 p, vJ = v3(0,0,0), wJ = v3(0,0,0);
-      const M3 Ro = org_R(L);
+      XF x; x.fast = 0; x.cls = L.rcls; x.c = 1.0; x.s = 0.0;
+      V3 vJ = v3(0,0,0), wJ = v3(0,0,0);
       switch(L.jtype){
       case J_REVOL: {
-        double s, co; sincos(c.S(qs+L.qofs), &s, &co);
-        c.S(sl+6) = s; c.S(sl+7) = co;
-        const V3 o0 = col0(Ro), o1 = col1(Ro);
-        R = from_cols(co*o0 + s*o1, co*o1 - s*o0, col2(Ro)); p = org_p(L);
+        double sn, co; sincos(c.S(qs+L.qofs), &sn, &co);
+        c.S(sl+6) = sn; c.S(sl+7) = co;
+        x.s = sn; x.c = co; x.p = org_p(L);
+        if( L.rcls != RO_GENERAL ) x.fast = 1;
+        else { const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
+          x.R = from_cols(co*o0 + sn*o1, co*o1 - sn*o0, col2(Ro)); }
         wJ.z = c.S(qds+L.qofs);
       } break;
-      case J_PRISM: R = Ro; p = org_p(L) + c.S(qs+L.qofs)*col2(Ro); vJ.z = c.S(qds+L.qofs); break;
+      case J_PRISM: x.R = org_R(L); x.p = org_p(L) + c.S(qs+L.qofs)*col2(x.R); vJ.z = c.S(qds+L.qofs); break;
       case J_SPHER: {
-        R = mm(Ro, aa_to_mat(ld3(qs+L.qofs))); p = org_p(L);
-        stm(sl+27, R);
-        wJ = tmul(R, mul(Ro, ld3(qds+L.qofs)));
+        const M3 Ro = org_R(L);
+        x.R = mm(Ro, aa_to_mat(ld3(qs+L.qofs))); x.p = org_p(L);
+        stm(sl+27, x.R);
+        wJ = tmul(x.R, mul(Ro, ld3(qds+L.qofs)));
       } break;
       case J_FLOAT: {
-        R = mm(Ro, aa_to_mat(ld3(qs+L.qofs+3))); p = org_p(L) + mul(Ro, ld3(qs+L.qofs));
-        stm(sl+6, R); st3(sl+15, p);
-        vJ = tmul(R, mul(Ro, ld3(qds+L.qofs))); wJ = tmul(R, mul(Ro, ld3(qds+L.qofs+3)));
+        const M3 Ro = org_R(L);
+        x.R = mm(Ro, aa_to_mat(ld3(qs+L.qofs+3))); x.p = org_p(L) + mul(Ro, ld3(qs+L.qofs));
+        stm(sl+6, x.R); st3(sl+15, x.p);
+        vJ = tmul(x.R, mul(Ro, ld3(qds+L.qofs))); wJ = tmul(x.R, mul(Ro, ld3(qds+L.qofs+3)));
       } break;
-      default: R = Ro; p = org_p(L); break;
+      default: x.R = org_R(L); x.p = org_p(L); break;
       }
-      const V3 om_n = tmul(R, om) + wJ;
-      const V3 gd_n = tmul(R, gd);
+      const V3 om_n = xf_tmul(x, om) + wJ;
+      const V3 gd_n = xf_tmul(x, gd);
       if( m.need_world ){
-        const V3 vl_n = tmul(R, vl + cross(om, p)) + vJ;
-        pw = pw + mul(Rw, p); Rw = mm(Rw, R); vl = vl_n;
+        const V3 vl_n = xf_tmul(x, vl + cross(om, x.p)) + vJ;
+        pw = pw + mul(Rw, x.p); Rw = xf_world(x, Rw); vl = vl_n;
       }
       om = om_n; gd = gd_n;
-      st3(sl, om); st3(sl+3, gd);
-      if( L.accum_slot >= 0 ) for(int k=0;k<ACCUM_SLOTS;k++) c.S(L.accum_slot+k) = 0.0;
+      st3(L.wslot, om); st3(L.wslot+3, gd);
       if( L.wext_slot >= 0 ){
         const V6 w = contacts(m, L, Rw, pw, vl, om, ref);
         st3(L.wext_slot, w.l); st3(L.wext_slot+3, w.a);
+        if( L.frame_slot >= 0 ){ stm(L.frame_slot, Rw); st3(L.frame_slot+9, pw); st3(L.frame_slot+12, vl); st3(L.frame_slot+15, om); }
       }
       if( L.branch_slot >= 0 && m.need_world ){ stm(L.branch_slot, Rw); st3(L.branch_slot+9, pw); st3(L.branch_slot+12, vl); }
     }
@@ -298,9 +330,10 @@ struct Core {
   RKFD_HD void pass2(const ModelDev &m, bool ref){
     S3 kA, kC; M3 kB; V3 kf, kn;          /* contribution carried to link i from its serial child */
     kA.xx=kA.xy=kA.xz=kA.yy=kA.yz=kA.zz=0; kC = kA; kB.xx=kB.xy=kB.xz=kB.yx=kB.yy=kB.yz=kB.zx=kB.zy=kB.zz=0; kf = v3(0,0,0); kn = kf;
+    for(int i=0;i<m.nl;i++) if( m.link[i].accum_slot >= 0 ) for(int k=0;k<ACCUM_SLOTS;k++) c.S(m.link[i].accum_slot+k) = 0.0;
     for(int i=m.nl-1;i>=0;i--){
       const LinkDev &L = m.link[i]; const int sl = L.slot;
-      const V3 om = ld3(sl), gd = ld3(sl+3);
+      const V3 om = ld3(L.wslot), gd = ld3(L.wslot+3);
       const V3 mc = v3(L.mc[0],L.mc[1],L.mc[2]);
       S3 A, C; M3 B;
       A.xx = L.mass; A.xy = 0; A.xz = 0; A.yy = L.mass; A.yz = 0; A.zz = L.mass;
@@ -323,11 +356,11 @@ struct Core {
         B.xx+=kB.xx; B.xy+=kB.xy; B.xz+=kB.xz; B.yx+=kB.yx; B.yy+=kB.yy; B.yz+=kB.yz; B.zx+=kB.zx; B.zy+=kB.zy; B.zz+=kB.zz;
         pf = pf + kf; pn = pn + kn;
       }
-      M3 R; V3 p, vJ, wJ;
-      joint_xform(m, L, R, p, vJ, wJ);
+      V3 vJ, wJ;
+      const XF x = joint_xform(m, L, vJ, wJ);
       /* velocity-product acceleration (link frame): parent angular velocity in link axes = om - wJ */
       const V3 omp = om - wJ;
-      const V3 zl = cross(omp, cross(omp, tmul(R, p))) + 2.0*cross(omp, vJ);
+      const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
       const V3 za = cross(omp, wJ);
       /* p' = pA + IA zeta */
       if( L.jtype != J_FLOAT ){
@@ -359,7 +392,7 @@ struct Core {
       } break;
       case J_SPHER: {
         /* S = [0; E], E = R^T Ro (= RJ^T); U = [B E; C E]; D = E^T C E; tau = 0 */
-        const M3 E = tmm(R, org_R(L));
+        const M3 E = tmm(x.R, org_R(L));
         const M3 Ul = mm(B, E); M3 Cf; Cf.xx=C.xx; Cf.xy=C.xy; Cf.xz=C.xz; Cf.yx=C.xy; Cf.yy=C.yy; Cf.yz=C.yz; Cf.zx=C.xz; Cf.zy=C.yz; Cf.zz=C.zz;
         const M3 Ua = mm(Cf, E);
         const M3 Df = tmm(E, Ua); S3 D; D.xx=Df.xx; D.xy=Df.xy; D.xz=Df.xz; D.yy=Df.yy; D.yz=Df.yz; D.zz=Df.zz;
@@ -400,14 +433,15 @@ struct Core {
       }
       if( L.parent < 0 || L.jtype == J_FLOAT ) continue;
       /* X^T Ia X and X^T pa into the parent frame */
-      const S3 Ar = rot_sym(R, A), Cr = rot_sym(R, C); const M3 Br = rot_gen(R, B);
+      const V3 p = x.p;
+      const S3 Ar = xf_sym(x, A), Cr = xf_sym(x, C); const M3 Br = xf_gen(x, B);
       const M3 T = mul_skew(Ar, p);                       /* A' [p x] */
       M3 Bp; Bp.xx=Br.xx-T.xx; Bp.xy=Br.xy-T.xy; Bp.xz=Br.xz-T.xz; Bp.yx=Br.yx-T.yx; Bp.yy=Br.yy-T.yy; Bp.yz=Br.yz-T.yz; Bp.zx=Br.zx-T.zx; Bp.zy=Br.zy-T.zy; Bp.zz=Br.zz-T.zz;
       const M3 Z1 = skew_mul(p, Bp), Z2 = skew_mul(p, Br);  /* C_p = C' + [p x] B_p + ([p x] B')^T */
       S3 Cp;
       Cp.xx = Cr.xx + Z1.xx + Z2.xx; Cp.xy = Cr.xy + Z1.xy + Z2.yx; Cp.xz = Cr.xz + Z1.xz + Z2.zx;
       Cp.yy = Cr.yy + Z1.yy + Z2.yy; Cp.yz = Cr.yz + Z1.yz + Z2.zy; Cp.zz = Cr.zz + Z1.zz + Z2.zz;
-      const V3 fp = mul(R, pf); const V3 np = mul(R, pn) + cross(p, fp);
+      const V3 fp = xf_mul(x, pf); const V3 np = xf_mul(x, pn) + cross(p, fp);
       if( L.serial ){ kA = Ar; kB = Bp; kC = Cp; kf = fp; kn = np; }
       else {
         const int a = m.link[L.parent].accum_slot;
@@ -460,6 +494,7 @@ struct Core {
   /* one dof: displacement uses the stage velocity as slope, velocity uses the acceleration */
   RKFD_HD void rk_dof(const ModelDev &m, const RK &k, int stage, int j, double acc){
     const int qs = m.rk_slot + j, qds = m.rk_slot + m.nq + j, pq = m.rk_slot + 2*m.nq + j, pqd = m.rk_slot + 3*m.nq + j;
+    if( stage == ST_PROBE ) return;
     if( stage >= ST_REF ){ c.gst(c.st.qdd, j, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; return; }
     const double vel = c.S(qds);
     rk_lin(m, k, stage, qs, pq, c.st.q[c.cur], c.st.q[c.cur^1], j, vel);
@@ -476,12 +511,12 @@ struct Core {
         if( L.parent < 0 ){ al = v3(0,0,0); aa = v3(0,0,0); om = v3(0,0,0); }
         else { const int b = m.link[L.parent].branch_slot; al = ld3(b); aa = ld3(b+3); om = ld3(b+6); }
       }
-      M3 R; V3 p, vJ, wJ;
-      joint_xform(m, L, R, p, vJ, wJ);
-      const V3 omp = tmul(R, om);
-      const V3 zl = cross(omp, cross(omp, tmul(R, p))) + 2.0*cross(omp, vJ);
+      V3 vJ, wJ;
+      const XF x = joint_xform(m, L, vJ, wJ);
+      const V3 omp = xf_tmul(x, om);
+      const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
       const V3 za = cross(omp, wJ);
-      const V3 xl = tmul(R, al + cross(aa, p)), xa = tmul(R, aa);
+      const V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
       switch(L.jtype){
       case J_REVOL: case J_PRISM: {
         const V3 Ul = ld3(sl), Ua = ld3(sl+3);
@@ -494,9 +529,10 @@ struct Core {
         const M3 Ul = ldm(sl), Ua = ldm(sl+9); const S3 Di = lds(sl+18); const V3 u = ld3(sl+24);
         const V3 rhs = u - (tmul(Ul, xl) + tmul(Ua, xa));
         const V3 acc = mul(Di, rhs);
-        const M3 E = tmm(R, org_R(L));
+        const M3 E = tmm(x.R, org_R(L));
         al = xl + zl; aa = xa + za + mul(E, acc);
-        if( stage >= ST_REF ){ c.gst(c.st.qdd,L.qofs,acc.x); c.gst(c.st.qdd,L.qofs+1,acc.y); c.gst(c.st.qdd,L.qofs+2,acc.z);
+        if( stage == ST_PROBE ){}
+        else if( stage >= ST_REF ){ c.gst(c.st.qdd,L.qofs,acc.x); c.gst(c.st.qdd,L.qofs+1,acc.y); c.gst(c.st.qdd,L.qofs+2,acc.z);
           if( !(fabs(acc.x)+fabs(acc.y)+fabs(acc.z) < 1.0e300) ) bad = 1; }
         else {
           const int qs = m.rk_slot + L.qofs, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
@@ -509,10 +545,11 @@ struct Core {
       } break;
       case J_FLOAT: {
         const V3 a0l = ld3(sl), a0a = ld3(sl+3);
-        const M3 RJ = mm(transpose(org_R(L)), R);       /* S^-1 = blockdiag(RJ, RJ) */
+        const M3 RJ = mm(transpose(org_R(L)), x.R);     /* S^-1 = blockdiag(RJ, RJ) */
         const V3 accl = mul(RJ, a0l - xl - zl), acca = mul(RJ, a0a - xa - za);
         al = a0l; aa = a0a;
-        if( stage >= ST_REF ){
+        if( stage == ST_PROBE ){}
+        else if( stage >= ST_REF ){
           c.gst(c.st.qdd,L.qofs,accl.x); c.gst(c.st.qdd,L.qofs+1,accl.y); c.gst(c.st.qdd,L.qofs+2,accl.z);
           c.gst(c.st.qdd,L.qofs+3,acca.x); c.gst(c.st.qdd,L.qofs+4,acca.y); c.gst(c.st.qdd,L.qofs+5,acca.z);
           if( !(fabs(accl.x)+fabs(accl.y)+fabs(accl.z)+fabs(acca.x)+fabs(acca.y)+fabs(acca.z) < 1.0e300) ) bad = 1;
@@ -534,8 +571,231 @@ struct Core {
       default: al = xl + zl; aa = xa + za; break;
       }
       om = omp + wJ;
+      if( L.frame_slot >= 0 ){ st3(L.frame_slot+18, al); st3(L.frame_slot+21, aa); }
       if( L.branch_slot >= 0 ){ st3(L.branch_slot, al); st3(L.branch_slot+3, aa); st3(L.branch_slot+6, om); }
     }
+  }
+
+
+  /* =====================================================================================================
+   * Rigid-contact solve of ONE environment, executed cooperatively by the lanes of its warp
+   * (reference _rkFDSolverConstraint: rkfd_vert.c:327-336 / rkfd_mlcp.c:287-297).  `act` = lanes whose
+   * environment has active rigid contacts; they are served one after the other, all lanes working on the
+   * selected environment's scratch column:
+   *   contact geometry + bias b      lanes over contacts        rkfd_vert.c:107-123
+   *   A by 3N cached-ABA probes      lanes over probe columns   rkfd_vert.c:153-185, rkfd_util.c:163-181
+   *   velocity bias / compensation   lanes over rows            rkfd_vert.c:189-232, rkfd_mlcp.c:146-188
+   *   PGS (MLCP) or active-set QP    lanes over matrix columns  rkfd_mlcp.c:190-249, rkfd_opt_qp.c:43-181
+   *   forces -> wrenches, friction state                        rkfd_vert.c:286-324, rkfd_mlcp.c:252-284
+   * On the host harness a "warp" has one lane, which makes every loop sequential in the oracle's order.
+   * ===================================================================================================== */
+  RKFD_HD double &G(const ModelDev &m, int k, int i){ return c.W(m.ws_geo + GEO_DOUBLES*k + i); }
+  RKFD_HD V3 g3(const ModelDev &m, int k, int i){ return v3(G(m,k,i), G(m,k,i+1), G(m,k,i+2)); }
+  RKFD_HD void sg3(const ModelDev &m, int k, int i, V3 v){ G(m,k,i)=v.x; G(m,k,i+1)=v.y; G(m,k,i+2)=v.z; }
+  RKFD_HD V3 w3(int o){ return v3(c.W(o), c.W(o+1), c.W(o+2)); }
+  RKFD_HD void sw3(int o, V3 v){ c.W(o)=v.x; c.W(o+1)=v.y; c.W(o+2)=v.z; }
+
+  /* one probe: unit force `axis` (world) at vertex `rl` (link frame) of link `Lc`; fills the increments of the
+   * link accelerations da[col][link] ([EXT A-5] rkChainUpdateCachedABIPair: bias-only inward pass along the
+   * path to the root with the cached articulated inertias, then the outward pass) */
+  RKFD_HD void probe(const ModelDev &m, int col, int Lc, V3 rl, V3 axis){
+    const int du0 = m.ws_du + col*6*m.nl, da0 = m.ws_da + col*6*m.nl;
+    for(int k=0;k<6*m.nl;k++) c.W(du0+k) = 0.0;
+    V3 dpf, dpn;
+    { const M3 Rw = ldm(m.link[Lc].frame_slot);
+      const V3 fl = tmul(Rw, axis); dpf = -fl; dpn = -cross(rl, fl); }
+    for(int i=Lc;;){
+      const LinkDev &L = m.link[i]; const int sl = L.slot;
+      V3 paf = dpf, pan = dpn;
+      switch(L.jtype){
+      case J_REVOL: case J_PRISM: {
+        const double du = L.jtype == J_REVOL ? -dpn.z : -dpf.z;
+        c.W(du0+6*i) = du;
+        const double k = c.S(sl+8)*du;
+        paf = dpf + k*ld3(sl); pan = dpn + k*ld3(sl+3);
+      } break;
+      case J_SPHER: {
+        const M3 E = tmm(ldm(sl+27), org_R(L));
+        const V3 du = -tmul(E, dpn);
+        sw3(du0+6*i, du);
+        const V3 k = mul(lds(sl+18), du);
+        paf = dpf + mul(ldm(sl), k); pan = dpn + mul(ldm(sl+9), k);
+      } break;
+      case J_FLOAT: sw3(du0+6*i, dpf); sw3(du0+6*i+3, dpn); break;
+      default: break;
+      }
+      if( L.parent < 0 || L.jtype == J_FLOAT ) break;
+      V3 vJ, wJ; const XF x = joint_xform(m, L, vJ, wJ);
+      dpf = xf_mul(x, paf); dpn = xf_mul(x, pan) + cross(x.p, dpf);
+      i = L.parent;
+    }
+    for(int i=0;i<m.nl;i++){
+      const LinkDev &L = m.link[i]; const int sl = L.slot;
+      V3 al = v3(0,0,0), aa = v3(0,0,0);
+      if( L.parent >= 0 ){ al = w3(da0+6*L.parent); aa = w3(da0+6*L.parent+3); }
+      V3 vJ, wJ; const XF x = joint_xform(m, L, vJ, wJ);
+      V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
+      switch(L.jtype){
+      case J_REVOL: case J_PRISM: {
+        const double acc = c.S(sl+8)*( c.W(du0+6*i) - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
+        if( L.jtype == J_REVOL ) xa.z += acc; else xl.z += acc;
+      } break;
+      case J_SPHER: {
+        const V3 rhs = w3(du0+6*i) - (tmul(ldm(sl), xl) + tmul(ldm(sl+9), xa));
+        xa = xa + mul(tmm(ldm(sl+27), org_R(L)), mul(lds(sl+18), rhs));
+      } break;
+      case J_FLOAT: {   /* da = -IA^-1 dp */
+        double iv[21], dp[6] = { c.W(du0+6*i), c.W(du0+6*i+1), c.W(du0+6*i+2), c.W(du0+6*i+3), c.W(du0+6*i+4), c.W(du0+6*i+5) }, r[6];
+        for(int k=0;k<21;k++) iv[k] = c.S(sl+18+k);
+        int k = 0;
+        for(int a=0;a<6;a++) r[a] = 0;
+        for(int a=0;a<6;a++) for(int b=a;b<6;b++){ r[a] -= iv[k]*dp[b]; if( b != a ) r[b] -= iv[k]*dp[a]; k++; }
+        xl = v3(r[0],r[1],r[2]); xa = v3(r[3],r[4],r[5]);
+      } break;
+      default: break;
+      }
+      sw3(da0+6*i, xl); sw3(da0+6*i+3, xa);
+    }
+  }
+
+  RKFD_HD void rigid_solve(const ModelDev &m, bool ref, unsigned act){
+    const int nlanes = c.lanes(), lane = c.lane();
+    while( act ){
+      const int src = RKFD_FFS32(act) - 1; act &= act - 1;
+      const unsigned long long fl = c.bcast(cfl, src);
+      c.select(src);
+      const int N = RKFD_POPC64(fl & m.rigid_mask), n = 3*N;
+      const int ob = m.ws_b, of = m.ws_f, oA = m.ws_A;
+      /* ---- contacts in (pair, vertex) order; geometry, bias acceleration b (rkfd_vert.c:107-123) */
+      for(int k=lane;k<N;k+=nlanes){
+        int s = 0, cnt = -1;
+        for(;s<m.nslot;s++){ if( (fl & m.rigid_mask) >> (2*s) & 1ull ){ if( ++cnt == k ) break; } }
+        const PairDev &pr = m.pair[m.slot_pair[s]]; const CellDev &cl = m.cell[pr.cell]; const BoxDev &bx = m.box[pr.box];
+        const LinkDev &L = m.link[cl.link];
+        const int vi = cl.vofs + m.slot_vert[s];
+        const V3 rl = v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2]);
+        const M3 Rw = ldm(L.frame_slot); const V3 pw = ld3(L.frame_slot+9), vl = ld3(L.frame_slot+12), om = ld3(L.frame_slot+15);
+        const V3 al = ld3(L.frame_slot+18), aa = ld3(L.frame_slot+21);
+        const M3 Rb = box_R(bx); const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
+        const V3 vw = pw + mul(Rw, rl), vb = tmul(Rb, vw - pb);
+        V3 nn, t1, t2, prob;
+        box_face(bx, Rb, vb, bx.half[0]-fabs(vb.x), bx.half[1]-fabs(vb.y), bx.half[2]-fabs(vb.z), nn, t1, t2, prob);
+        const V3 refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
+        const V3 d = vw - (pb + mul(Rb, refb));
+        const V3 vel = mul(Rw, vl) + cross(mul(Rw, om), vw - pw);
+        /* rkFDLinkPointWldAcc (rkfd_util.c:92-101): R ( a + alpha x r + w x (w x r) ) */
+        const V3 r = tmul(Rw, vw - pw);
+        const V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r)));
+        sg3(m,k,0,vw); sg3(m,k,3,nn); sg3(m,k,6,t1); sg3(m,k,9,t2); sg3(m,k,12,d); sg3(m,k,15,vel); sg3(m,k,18,prob); sg3(m,k,21,rl);
+        G(m,k,24) = (double)s; G(m,k,25) = (double)cl.link; G(m,k,26) = (double)m.slot_pair[s];
+        c.W(ob+3*k) = dot(nn, accp); c.W(ob+3*k+1) = dot(t1, accp); c.W(ob+3*k+2) = dot(t2, accp);
+      }
+      c.gsync();
+      /* ---- A: one probe per (contact, axis) column (rkfd_vert.c:153-185) */
+      for(int col=lane;col<n;col+=nlanes){
+        const int k = col/3, i = col - 3*k;
+        probe(m, col, (int)G(m,k,25), g3(m,k,21), g3(m,k,3+3*i));
+        const int da0 = m.ws_da + col*6*m.nl;
+        for(int j=0;j<N;j++){
+          const int Lj = (int)G(m,j,25);
+          const V3 dl = w3(da0+6*Lj), dal = w3(da0+6*Lj+3), r = g3(m,j,21);
+          const V3 resp = mul(ldm(m.link[Lj].frame_slot), dl + cross(dal, r));
+          c.W(oA+(3*j)*n+col) = dot(g3(m,j,3), resp); c.W(oA+(3*j+1)*n+col) = dot(g3(m,j,6), resp); c.W(oA+(3*j+2)*n+col) = dot(g3(m,j,9), resp);
+        }
+      }
+      c.gsync();
+      /* ---- velocity level: b <- b dt + axis . v_rel (rkfd_vert.c:189-206 / rkfd_mlcp.c:146-162) */
+      for(int k=lane;k<N;k+=nlanes){
+        const V3 vel = g3(m,k,15);
+        c.W(ob+3*k)   = c.W(ob+3*k)  *m.dt + dot(vel, g3(m,k,3));
+        c.W(ob+3*k+1) = c.W(ob+3*k+1)*m.dt + dot(vel, g3(m,k,6));
+        c.W(ob+3*k+2) = c.W(ob+3*k+2)*m.dt + dot(vel, g3(m,k,9));
+      }
+      c.gsync();
+      unsigned long long nfl = fl;
+      if( m.solver == S_MLCP ){
+        /* relaxation + compensation (rkfd_mlcp.c:164-188) */
+        for(int k=lane;k<N;k+=nlanes){
+          const PairDev &pr = m.pair[(int)G(m,k,26)]; const int s = (int)G(m,k,24); const V3 d = g3(m,k,12);
+          const double mu = ( (fl >> (2*s+1)) & 1ull ) ? pr.KF : pr.SF;
+          for(int i=0;i<3;i++) c.W(oA+(3*k+i)*n+3*k+i) += pr.L;
+          c.W(ob+3*k)   += pr.K      * dot(d, g3(m,k,3));
+          c.W(ob+3*k+1) += pr.K * mu * dot(d, g3(m,k,6));
+          c.W(ob+3*k+2) += pr.K * mu * dot(d, g3(m,k,9));
+        }
+        for(int i=lane;i<n;i+=nlanes) c.W(of+i) = 0.0;
+        c.gsync();
+        /* projected Gauss-Seidel (rkfd_mlcp.c:190-249); the friction sweep reads rows offset+0 / offset+1 as the
+         * reference does (:219-225) */
+        for(int cnt=0;cnt<m.max_iter;cnt++){
+          for(int k=0;k<N;k++){
+            const int o = 3*k; double part = 0;
+            for(int j=lane;j<n;j+=nlanes) part += c.W(oA+o*n+j)*c.W(of+j);
+            const double sum = c.allsum(part), aoo = c.W(oA+o*n+o);
+            const double ff = -( c.W(ob+o) + sum - aoo*c.W(of+o) ) / aoo;
+            c.gsync();
+            if( lane == 0 ) c.W(of+o) = ff < ZTOL ? 0.0 : ff;
+            c.gsync();
+          }
+          for(int k=0;k<N;k++){
+            const int o = 3*k; double ff[2];
+            for(int i=0;i<2;i++){
+              const double aii = c.W(oA+(o+i)*n+o+i);
+              double part = 0;
+              for(int j=lane;j<n;j+=nlanes) part += c.W(oA+(o+i)*n+j)*c.W(of+j);
+              const double sum = c.allsum(part);
+              ff[i] = fabs(aii) < ZTOL ? 0.0 : -( c.W(ob+o+i) + sum - aii*c.W(of+o+i) ) / aii;
+            }
+            const PairDev &pr = m.pair[(int)G(m,k,26)]; const int s = (int)G(m,k,24);
+            const double mu = ( (fl >> (2*s+1)) & 1ull ) ? pr.KF : pr.SF;
+            const double fnorm = ff[0]*ff[0] + ff[1]*ff[1];
+            double fs = (mu*c.W(of+o))*(mu*c.W(of+o)), f1, f2;
+            if( fnorm < ZTOL || fs < ZTOL ){ f1 = 0.0; f2 = 0.0; }
+            else if( fnorm > fs ){ fs /= fnorm; f1 = ff[0]*fs; f2 = ff[1]*fs; }
+            else { f1 = ff[0]; f2 = ff[1]; }
+            c.gsync();
+            if( lane == 0 ){ c.W(of+o+1) = f1; c.W(of+o+2) = f2; }
+            c.gsync();
+          }
+        }
+        /* f /= dt; forces, wrenches, friction state (rkfd_mlcp.c:252-284: committed regardless of doUpRef,
+         * world components of f as "normal"/"tangential" - mirrored) */
+        for(int k=0;k<N;k++){
+          const int s = (int)G(m,k,24); const PairDev &pr = m.pair[(int)G(m,k,26)];
+          const V3 fw = (c.W(of+3*k)/m.dt)*g3(m,k,3) + (c.W(of+3*k+1)/m.dt)*g3(m,k,6) + (c.W(of+3*k+2)/m.dt)*g3(m,k,9);
+          const double mu = ( (fl >> (2*s+1)) & 1ull ) ? pr.KF : pr.SF;
+          const bool kin = sqrt(fw.y*fw.y + fw.z*fw.z) > mu*fw.x - ZTOL;
+          if( kin ) nfl |= 2ull << (2*s); else nfl &= ~(2ull << (2*s));
+          if( lane == 0 ){
+            push_rigid(m, k, fw, ref);
+            if( kin ){ const V3 prob = g3(m,k,18); c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
+          }
+        }
+      } else {
+        nfl = qp_vert(m, ref, fl, N);
+      }
+      c.gsync();
+      c.unselect();
+      if( lane == src ) cfl = nfl;
+    }
+  }
+
+  /* rkFDContactForcePushWrench (rkfd_util.c:268-282) for rigid contact k of the selected environment */
+  RKFD_HD void push_rigid(const ModelDev &m, int k, V3 fw, bool ref){
+    const LinkDev &L = m.link[(int)G(m,k,25)]; const int s = (int)G(m,k,24);
+    const M3 Rw = ldm(L.frame_slot); const V3 pw = ld3(L.frame_slot+9);
+    const V3 pos = tmul(Rw, g3(m,k,0) - pw), fl = tmul(Rw, fw);
+    const V3 t = cross(pos, fl);
+    c.S(L.wext_slot) += fl.x; c.S(L.wext_slot+1) += fl.y; c.S(L.wext_slot+2) += fl.z;
+    c.S(L.wext_slot+3) += t.x; c.S(L.wext_slot+4) += t.y; c.S(L.wext_slot+5) += t.z;
+    if( ref ){ c.gst(c.st.cf,3*s,fw.x); c.gst(c.st.cf,3*s+1,fw.y); c.gst(c.st.cf,3*s+2,fw.z); }
+  }
+
+  /* Vert: friction pyramid + least-squares QP by the active-set method (rkfd_vert.c:73-103, 208-324;
+   * rkfd_opt_qp.c:43-181).  Returns the new contact flags of the selected environment. */
+  RKFD_HD unsigned long long qp_vert(const ModelDev &m, bool ref, unsigned long long fl, int N){
+    (void)ref; (void)N;
+    return fl;
   }
 
   RKFD_HD void load_flags(){ piv = c.st.piv_type[c.e]; cfl = c.st.cflags[c.e]; }
@@ -546,7 +806,16 @@ struct Core {
   }
   RKFD_HD void evaluate(const ModelDev &m, int stage){
     const bool ref = (stage == ST_REF) || (stage == ST_EVAL_REF);
-    pass1(m, ref); pass2(m, ref); pass3(m, stage);
+    pass1(m, ref);
+    if( Ctx::RIGID ){
+      /* rigid pairs in contact (reference rkfd_vert.c:385-386): any lane of the warp -> cooperative solve */
+      const unsigned act = c.ballot( RKFD_POPC64(cfl & m.rigid_mask) > 0 );
+      if( act ){
+        pass2(m, false); pass3(m, ST_PROBE);      /* rkFDUpdateAccBias (rkfd_util.c:149-161) */
+        rigid_solve(m, ref, act);
+      }
+    }
+    pass2(m, ref); pass3(m, stage);
   }
   /* mode 0: rkFDUpdate x nsteps (reference rkfd_sim.c:560-566); mode 1 / 2: a single non-committing /
    * committing evaluation on the committed state (2 = rkFDUpdateInit's t=0 evaluation).  One stage loop so

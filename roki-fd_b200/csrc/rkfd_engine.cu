@@ -15,11 +15,10 @@
 #include <cstring>
 #include <stdexcept>
 
-#include "rkfd_core.cuh"
+#include "rkfd_kernel.cuh"
 
 namespace rkfd {
 
-__constant__ ModelDev c_model;
 
 void cuda_check(int err, const char *what)
 {
@@ -32,31 +31,6 @@ void cuda_check(int err, const char *what)
 #define CK(x) cuda_check((int)(x), #x)
 
 int device_count(){ int n = 0; if( cudaGetDeviceCount(&n) != cudaSuccess ) return 0; return n; }
-
-extern __shared__ double rkfd_smem[];
-
-template <int BLOCK, bool GSCR>
-struct DevCtx {
-  StateDev st; int e, cur, tid;
-  /* scratch element k of this thread: shared-memory column [k*BLOCK + tid] (LDS/STS, conflict-free) */
-  __device__ __forceinline__ double &S(int k){
-    if( GSCR ) return st.scratch[(size_t)k*st.ld + e];
-    return rkfd_smem[k*BLOCK + tid];
-  }
-  __device__ __forceinline__ double gld(const double *p, int k) const { return p[(size_t)k*st.ld + e]; }
-  __device__ __forceinline__ void gst(double *p, int k, double v){ p[(size_t)k*st.ld + e] = v; }
-};
-
-/* mode 0: nsteps x rkFDUpdate; 1: one non-committing evaluation; 2: one committing evaluation */
-template <int BLOCK, bool GSCR>
-__global__ void __launch_bounds__(BLOCK) rkfd_step_kernel(StateDev st, int cur, int mode, int nsteps)
-{
-  const int e = blockIdx.x*BLOCK + threadIdx.x;
-  if( e >= st.B ) return;
-  DevCtx<BLOCK,GSCR> ctx; ctx.st = st; ctx.e = e; ctx.cur = cur; ctx.tid = threadIdx.x;
-  Core<DevCtx<BLOCK,GSCR>> core(ctx);
-  core.run(c_model, mode, nsteps);
-}
 
 /* env-major host layout [B][n] <-> device SoA [n][ld] */
 __global__ void rkfd_scatter_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld)
@@ -112,12 +86,13 @@ struct Shard {
   StateDev st;
   cudaStream_t stream = nullptr; bool own_stream = true;
   double *dstage = nullptr; size_t nstage = 0;
-  int block = 64; bool gscr = false; size_t smem = 0;
+  const KernelVariant *kv = nullptr; size_t smem = 0;
   std::vector<void*> allocs;
 };
 
 static int g_next_engine_id = 1;
-static int g_model_owner[64] = {0};
+static int g_model_owner[64][8] = {{0}};   /* [device][variant]: engine whose model sits in that constant bank */
+static int variant_index(const KernelVariant *kv);
 
 template <class T> static T *dalloc(Shard &s, size_t n)
 {
@@ -126,17 +101,15 @@ template <class T> static T *dalloc(Shard &s, size_t n)
   s.allocs.push_back(p); return (T*)p;
 }
 
-template <int BLOCK, bool GSCR>
-static bool try_config(Shard &s, int nscratch, int &best_threads)
-{
-  const size_t smem = GSCR ? 0 : (size_t)nscratch*BLOCK*sizeof(double);
-  if( smem > 227*1024 ) return false;
-  if( cudaFuncSetAttribute(rkfd_step_kernel<BLOCK,GSCR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ){ cudaGetLastError(); return false; }
-  int nb = 0;
-  if( cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rkfd_step_kernel<BLOCK,GSCR>, BLOCK, smem) != cudaSuccess ){ cudaGetLastError(); return false; }
-  if( nb*BLOCK > best_threads ){ best_threads = nb*BLOCK; s.block = BLOCK; s.gscr = GSCR; s.smem = smem; return true; }
-  return false;
-}
+/* kernel variants, one translation unit each (rkfd_kernel_variant.cu) */
+#define RKFD_DECL(B,G,R) extern const KernelVariant rkfd_variant_##B##_##G##_##R;
+RKFD_DECL(128,0,0) RKFD_DECL(64,0,0) RKFD_DECL(32,0,0) RKFD_DECL(64,1,0)
+RKFD_DECL(128,0,1) RKFD_DECL(64,0,1) RKFD_DECL(32,0,1) RKFD_DECL(64,1,1)
+static const KernelVariant *g_variants[] = {
+  &rkfd_variant_128_0_0, &rkfd_variant_64_0_0, &rkfd_variant_32_0_0, &rkfd_variant_64_1_0,
+  &rkfd_variant_128_0_1, &rkfd_variant_64_0_1, &rkfd_variant_32_0_1, &rkfd_variant_64_1_1 };
+
+static int variant_index(const KernelVariant *kv){ for(int i=0;i<8;i++) if( g_variants[i] == kv ) return i; return 0; }
 
 Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : model_(model), B_(B), id_(g_next_engine_id++)
 {
@@ -166,18 +139,24 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     st.cref = dalloc<double>(*s, (size_t)3*ns*s->ld);
     st.cf = dalloc<double>(*s, (size_t)3*ns*s->ld);
     st.status = dalloc<int>(*s, s->ld);
+    st.ws = model.ws_doubles > 0 ? dalloc<double>(*s, (size_t)(s->ld/32)*model.ws_doubles) : nullptr;
     int nmax = nq; if( nl > nmax ) nmax = nl; if( 3*ns > nmax ) nmax = 3*ns;
     s->nstage = (size_t)nmax*s->B; s->dstage = dalloc<double>(*s, s->nstage);
-    /* launch configuration: the block size that keeps most environments resident per SM */
-    int best = 0;
-    try_config<128,false>(*s, model.nscratch, best);
-    try_config<64,false>(*s, model.nscratch, best);
-    try_config<32,false>(*s, model.nscratch, best);
-    if( best == 0 ){
-      try_config<64,true>(*s, model.nscratch, best);
-      st.scratch = dalloc<double>(*s, (size_t)model.nscratch*s->ld);
-    }
+    /* launch configuration: the block size that keeps most environments resident per SM; scratch in HBM
+     * (gscr) only when no shared-memory variant fits */
+    int best = 0; const bool rigid = model.has_rigid && model.solver != S_VOLUME;
+    for(int pass=0; pass<2 && best==0; pass++)
+      for(const KernelVariant *kv : g_variants){
+        if( kv->rigid != rigid || kv->gscr != (pass == 1) ) continue;
+        const size_t smem = kv->gscr ? 0 : (size_t)model.nscratch*kv->block*sizeof(double);
+        if( smem > 227*1024 ) continue;
+        const int nb = kv->blocks_per_sm(smem);
+        if( nb*kv->block > best ){ best = nb*kv->block; s->kv = kv; s->smem = smem; }
+      }
+    if( s->kv && s->kv->gscr ) st.scratch = dalloc<double>(*s, (size_t)model.nscratch*s->ld);
     if( best == 0 ) throw std::runtime_error("rokifd_b200: no launch configuration fits this model");
+    /* the zero-fills above ran on the legacy default stream, which this non-blocking stream does not wait for */
+    CK(cudaDeviceSynchronize());
   }
   CK(cudaSetDevice(prev));
 }
@@ -188,7 +167,7 @@ Engine::~Engine()
   for(Shard *s : shards_){
     cudaSetDevice(s->dev);
     cudaStreamSynchronize(s->stream);
-    if( g_model_owner[s->dev & 63] == id_ ) g_model_owner[s->dev & 63] = 0;
+    if( s->kv && g_model_owner[s->dev & 63][variant_index(s->kv)] == id_ ) g_model_owner[s->dev & 63][variant_index(s->kv)] = 0;
     for(void *p : s->allocs) cudaFree(p);
     if( s->own_stream && s->stream ) cudaStreamDestroy(s->stream);
     delete s;
@@ -198,28 +177,19 @@ Engine::~Engine()
 
 void Engine::upload_model(Shard &s)
 {
-  if( g_model_owner[s.dev & 63] == id_ ) return;
+  int &owner = g_model_owner[s.dev & 63][variant_index(s.kv)];
+  if( owner == id_ ) return;
   /* another engine's kernels may still read the constant table on this device */
-  if( g_model_owner[s.dev & 63] != 0 ) CK(cudaDeviceSynchronize());
-  CK(cudaMemcpyToSymbolAsync(c_model, &model_, sizeof(ModelDev), 0, cudaMemcpyHostToDevice, s.stream));
-  g_model_owner[s.dev & 63] = id_;
-}
-
-template <int BLOCK, bool GSCR>
-static void launch_cfg(Shard &s, int mode, int nsteps)
-{
-  const int grid = (s.B + BLOCK - 1)/BLOCK;
-  rkfd_step_kernel<BLOCK,GSCR><<<grid, BLOCK, s.smem, s.stream>>>(s.st, s.cur, mode, nsteps);
+  if( owner != 0 ) CK(cudaDeviceSynchronize());
+  CK(s.kv->upload(&model_, s.stream));
+  owner = id_;
 }
 
 void Engine::launch(Shard &s, int mode, int nsteps)
 {
   CK(cudaSetDevice(s.dev));
   upload_model(s);
-  if( s.gscr ) launch_cfg<64,true>(s, mode, nsteps);
-  else if( s.block == 128 ) launch_cfg<128,false>(s, mode, nsteps);
-  else if( s.block == 64 ) launch_cfg<64,false>(s, mode, nsteps);
-  else launch_cfg<32,false>(s, mode, nsteps);
+  s.kv->launch(s.st, s.cur, mode, nsteps, (s.ld + s.kv->block - 1)/s.kv->block, s.smem, s.stream);
   CK(cudaGetLastError());
   launches_++;
   if( mode == 0 && (nsteps & 1) ) s.cur ^= 1;

@@ -66,6 +66,14 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
       std::memcpy(d.Ro, l.Ro, sizeof d.Ro); std::memcpy(d.po, l.po, sizeof d.po);
       d.mass = l.mass;
       for(int k=0;k<3;k++){ d.com[k] = l.com[k]; d.mc[k] = l.mass*l.com[k]; }
+      { /* class of the constant rotation; entries within 1e-14 of {0,+-1} are snapped so that the structured
+           transforms are exact signed permutations */
+        static const double RI[9] = {1,0,0, 0,1,0, 0,0,1}, RP[9] = {1,0,0, 0,0,-1, 0,1,0}, RM[9] = {1,0,0, 0,0,1, 0,-1,0};
+        const double *cand[3] = {RI, RP, RM}; d.rcls = RO_GENERAL;
+        for(int cidx=0;cidx<3;cidx++){ bool ok = true; for(int k=0;k<9;k++) if( std::fabs(d.Ro[k]-cand[cidx][k]) > 1e-14 ) ok = false;
+          if( ok ){ d.rcls = cidx+1; std::memcpy(d.Ro, cand[cidx], sizeof d.Ro); break; } }
+        for(int k=0;k<3;k++) d.pol[k] = d.Ro[k]*d.po[0] + d.Ro[3+k]*d.po[1] + d.Ro[6+k]*d.po[2];
+      }
       { /* Io = Ic - m [c x]^2 = Ic + m (|c|^2 E - c c^T) */
         const double *c = l.com, c2 = c[0]*c[0]+c[1]*c[1]+c[2]*c[2]; double Io[9];
         for(int r=0;r<3;r++) for(int q=0;q<3;q++) Io[3*r+q] = l.inertia[3*r+q] + l.mass*((r==q?c2:0.0) - c[r]*c[q]);
@@ -124,19 +132,39 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   /* ---- topology flags and the scratch slot map */
   for(int i=0;i<nl;i++) if( m.link[i].parent >= 0 ) m.link[m.link[i].parent].nchild++;
   for(int i=0;i<nl;i++){ LinkDev &d = m.link[i]; d.serial = ( d.parent >= 0 && d.parent == i-1 && m.link[d.parent].nchild == 1 ) ? 1 : 0;
-    d.branch_slot = d.accum_slot = d.wext_slot = -1; }
+    d.branch_slot = d.accum_slot = d.wext_slot = d.frame_slot = -1; }
   int slot = 0;
-  for(int i=0;i<nl;i++){ m.link[i].slot = slot; slot += link_slot_count(m.link[i].jtype, m.has_rigid); }
+  for(int i=0;i<nl;i++){ m.link[i].slot = slot; m.link[i].wslot = slot + link_w_offset(m.link[i].jtype, m.has_rigid); slot += link_slot_count(m.link[i].jtype, m.has_rigid); }
   for(int i=0;i<nl;i++){
     LinkDev &d = m.link[i];
     if( d.parent >= 0 && !d.serial ){
       LinkDev &p = m.link[d.parent];
       if( p.branch_slot < 0 ){ p.branch_slot = slot; slot += BRANCH_SLOTS; p.accum_slot = slot; slot += ACCUM_SLOTS; }
     }
-    if( d.cell_end > d.cell_begin ){ d.wext_slot = slot; slot += WEXT_SLOTS; }
+    if( d.cell_end > d.cell_begin ){ d.wext_slot = slot; slot += WEXT_SLOTS;
+      if( m.has_rigid ){ d.frame_slot = slot; slot += FRAME_SLOTS; } }
   }
   m.rk_slot = slot; slot += 4*nq;
   m.nscratch = slot;
+  /* ---- rigid-contact tables: slot -> (pair, vertex), workspace layout per warp */
+  m.rigid_mask = 0; int nrs = 0;
+  for(int p=0;p<m.npair;p++) for(int k=0;k<m.cell[m.pair[p].cell].nvert;k++){
+    const int sidx = m.pair[p].sofs + k; m.slot_pair[sidx] = p; m.slot_vert[sidx] = k;
+    if( m.pair[p].type == C_RIGID ){ m.rigid_mask |= 1ull << (2*sidx); nrs++; }
+  }
+  m.nmax = 3*nrs; m.ws_doubles = 0;
+  if( m.has_rigid ){
+    const int n = m.nmax, mc = m.pyramid*nrs, nm = n + mc; int o = 0;
+    m.ws_geo = o; o += GEO_DOUBLES*nrs;
+    m.ws_b = o;  o += n;
+    m.ws_f = o;  o += n;
+    m.ws_A = o;  o += n*n;
+    m.ws_du = o; o += n*nl;           /* per probe column: joint-space increments (scalar per link; multi-DoF joints use 6) */
+    m.ws_da = o; o += n*6*nl;         /* per probe column: link acceleration increments */
+    m.ws_qp = o;
+    if( m.solver == S_VERT ) o += n*n + 2*n + 3*mc + mc + 2*nm*nm + 4*nm + 64;   /* Q, c, d | nf rows | idx | KKT, V | xy, cb, w, tmp */
+    m.ws_doubles = (o + 31) & ~31;
+  }
   return true;
 }
 

@@ -34,6 +34,8 @@ constexpr double ZTOL = 1.0e-12;      /* ZM zTOL */
 struct LinkDev {
   double Ro[9];        /* org frame rotation w.r.t. parent, row-major */
   double po[3];        /* org frame position */
+  double pol[3];       /* Ro^T po */
+  int rcls;            /* RoClass of Ro (rkfd_math.cuh): 0 general, 1 identity, 2/3 quarter turn about x */
   double mass;
   double com[3];
   double mc[3];        /* mass * com */
@@ -45,11 +47,14 @@ struct LinkDev {
   double m_min, m_max;
   int parent, jtype, mtype, ndof, qofs;
   int slot;            /* first scratch slot of this link */
+  int wslot;           /* slots of (w, gravity direction) written by pass 1: aliased with U (= slot) unless the world has
+                          rigid pairs, where pass 2 runs twice per evaluation and they must survive */
   int serial;          /* 1: parent == index-1 and the parent has no other child (carry in registers) */
   int nchild;          /* number of children */
   int branch_slot;     /* >=0: slots where this link publishes frame/velocity/acceleration for non-serial children */
   int accum_slot;      /* >=0: slots where non-serial children accumulate articulated inertia/bias (27) */
   int wext_slot;       /* >=0: slots of the external wrench (6) (links that carry collision cells) */
+  int frame_slot;      /* >=0 (worlds with rigid pairs, links with cells): Rw(9) pw(3) vl(3) w(3) a(6) = 24 slots */
   int cell_begin, cell_end;
 };
 
@@ -63,6 +68,11 @@ struct ModelDev {
   int has_rigid, has_elastic;
   int solver, pyramid, max_iter;
   int nscratch;        /* scratch slots (doubles) per env */
+  int ws_doubles;      /* per-warp workspace (doubles) of the rigid-contact solve, 0 when no rigid pair */
+  int ws_geo, ws_b, ws_f, ws_A, ws_du, ws_da, ws_qp;   /* offsets inside the workspace */
+  int nmax;            /* 3 * (rigid contact slots) */
+  unsigned long long rigid_mask;   /* bit 2s set when slot s belongs to a rigid pair */
+  int slot_pair[MAX_SLOTS], slot_vert[MAX_SLOTS];
   int rk_slot;         /* first slot of the RKG stage state: QS[nq], QDS[nq], PQ[nq], PQD[nq] */
   double dt, friction_weight;
   double sc_sin[MAX_PYRAMID], sc_cos[MAX_PYRAMID];
@@ -88,6 +98,7 @@ struct StateDev {
   double *cref;           /* [nslot*3][ld] anchor _ref in the box frame */
   double *cf;             /* [nslot*3][ld] contact force (world) of the last reference evaluation */
   double *scratch;        /* optional global scratch [nscratch][ld] when shared memory is too small */
+  double *ws;             /* rigid-contact workspace, ws_doubles per warp (ld/32 warps) */
   int *status;            /* [ld] per-env status word (bit0: non-finite acceleration) */
 };
 

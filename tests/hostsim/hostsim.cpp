@@ -18,15 +18,26 @@ void sincos(double x, double *s, double *c){ *s = std::sin(x); *c = std::cos(x);
 }
 
 struct HostCtx {
-  StateDev st; int e, cur; std::vector<double> scr;
+  StateDev st; int e, cur; std::vector<double> scr, wsp;
   double &S(int k){ return scr[k]; }
+  static constexpr bool RIGID = true;
+  /* a "warp" of one lane */
+  int lanes() const { return 1; }
+  int lane() const { return 0; }
+  unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  template <class T> T bcast(T x, int) const { return x; }
+  double allsum(double x) const { return x; }
+  void select(int){}
+  void unselect(){}
+  void gsync(){}
+  double &W(int i){ return wsp[i]; }
   double gld(const double *p, int k) const { return p[(size_t)k*st.ld + e]; }
   void gst(double *p, int k, double v){ p[(size_t)k*st.ld + e] = v; }
 };
 
 struct HostSim {
   ModelDev model; WorldHost world; std::vector<ChainHost*> chains; std::string err;
-  int B = 0, cur = 0; StateDev st; std::vector<void*> allocs;
+  int B = 0, cur = 0; StateDev st; std::vector<void*> allocs; std::vector<double> last_ws;
 };
 
 template <class T> static T *halloc(HostSim *h, size_t n){ void *p = std::calloc(n ? n : 1, sizeof(T)); h->allocs.push_back(p); return (T*)p; }
@@ -114,11 +125,16 @@ void hostsim_get_pivot(HostSim *h, int *type, double *prev)
 void hostsim_run(HostSim *h, int mode, int nsteps)
 {
   for(int e=0;e<h->B;e++){
-    HostCtx ctx; ctx.st = h->st; ctx.e = e; ctx.cur = h->cur; ctx.scr.assign(h->model.nscratch + 1, 0.0);
+    HostCtx ctx; ctx.st = h->st; ctx.e = e; ctx.cur = h->cur; ctx.scr.assign(h->model.nscratch + 1, 0.0); ctx.wsp.assign(h->model.ws_doubles + 1, 0.0);
     Core<HostCtx> core(ctx);
     core.run(h->model, mode, nsteps);
+    h->last_ws = ctx.wsp;
   }
   if( mode == 0 && (nsteps & 1) ) h->cur ^= 1;
 }
+
+/* debugging aid: the rigid-contact workspace of the last environment processed */
+int hostsim_get_ws(HostSim *h, double *out, int cap, int *offs){ int n = (int)h->last_ws.size(); if( n > cap ) n = cap; for(int i=0;i<n;i++) out[i] = h->last_ws[i];
+  offs[0]=h->model.ws_geo; offs[1]=h->model.ws_b; offs[2]=h->model.ws_f; offs[3]=h->model.ws_A; offs[4]=h->model.ws_du; offs[5]=h->model.ws_da; offs[6]=h->model.ws_qp; return n; }
 
 }  // extern "C"

@@ -223,3 +223,58 @@ def test_multi_device_sharding(capi, oracle):
     for a, b in zip(ref, got):
         assert np.array_equal(a, b)
     fd.destroy()
+
+
+RIGID_WORLDS = {
+    "c5_arm7_mlcp": lambda: ch.world_c5(base_z=0.1, solver="MLCP"),
+    "box_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="MLCP"),
+    "box_hardsoft_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor_hardsoft()], contact_info=ch.contact_info_table(), solver="MLCP"),
+}
+
+
+@pytest.mark.parametrize("name", list(RIGID_WORLDS))
+def test_rigid_evaluation_matches_oracle(capi, oracle, name):
+    """Rigid contact (A,b by cached-ABA probes + solver) in one committing evaluation.  The Delassus matrix of
+    N>DoF/3 contacts is rank deficient up to the 1e-4 relaxation, so rounding differences are amplified by
+    cond(A) ~ 1e4..1e6: q'' and contact forces are required within 1e-7 relative (1e-9 x that amplification
+    is the expectation; the measured maximum is printed)."""
+    w = RIGID_WORLDS[name]()
+    B = 256
+    q, qd, u = ch.sample_state(w, B, seed=5)
+    if "box" in name:
+        q[:, 2] = np.linspace(-0.01, 0.08, B)
+        q[:, 1] = np.linspace(-0.3, 0.3, B)
+    fd = gpu_world(capi, w, q, qd, u)
+    _, _, gqdd = fd.batch_get_state()
+    a, t, r, f = fd.batch_get_contact()
+    ow = oracle.OracleWorld(w)
+    worst, nc = 0.0, 0
+    for b in range(B):
+        e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
+        ref = e.eval(True)
+        oa, ot, orr, of = e.get_contact()
+        nc += oa.sum()
+        assert (a[b] == oa).all() and (t[b][oa == 1] == ot[oa == 1]).all(), (name, b)
+        worst = max(worst, relerr(gqdd[b], ref))
+        assert np.allclose(f[b][oa == 1], of[oa == 1], rtol=1e-7, atol=1e-7 * max(1.0, np.abs(of).max()))
+    print("rigid %s: %d contacts, max rel err of q'' %.2e" % (name, nc, worst))
+    assert nc > 0 and worst < 1e-7
+    fd.destroy()
+
+
+@pytest.mark.parametrize("name", list(RIGID_WORLDS))
+def test_rigid_short_trajectory(capi, oracle, name):
+    w = RIGID_WORLDS[name]()
+    B, nsteps = 128, 20
+    q, qd, u = ch.sample_state(w, B, seed=9)
+    if "box" in name:
+        q[:, 2] = np.linspace(0.02, 0.08, B)
+    fd = gpu_world(capi, w, q, qd, u)
+    fd.update_n(nsteps)
+    gq, gqd, _ = fd.batch_get_state()
+    assert (fd.batch_get_status() == 0).all()
+    oq, oqd, _, _ = oracle.OracleWorld(w).batch_run(q, qd, u, nsteps=nsteps)
+    err = np.array([relerr(gq[b], oq[b]) for b in range(B)])
+    print("rigid trajectory %s: %d/%d envs within 1e-6 (max %.2e)" % (name, (err < 1e-6).sum(), B, err.max()))
+    assert (err < 1e-6).mean() >= 0.97
+    fd.destroy()

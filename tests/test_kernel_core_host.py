@@ -129,3 +129,55 @@ def test_two_chains_in_one_world(oracle):
     ref = oracle_run(oracle, w, q, qd, u, 10)
     for b in range(B):
         assert relerr(hq[b], ref[b][0][0]) < 1e-9
+
+
+RIGID_WORLDS = {
+    "c5_arm7_mlcp": lambda: ch.world_c5(base_z=0.1, solver="MLCP"),
+    "box_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="MLCP"),
+    "box_hardsoft_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor_hardsoft()], contact_info=ch.contact_info_table(), solver="MLCP"),
+}
+
+
+@pytest.mark.parametrize("name", list(RIGID_WORLDS))
+def test_rigid_eval_matches_oracle(oracle, name):
+    """One committing evaluation with rigid contacts: q'', contact forces and friction flags."""
+    w = RIGID_WORLDS[name]()
+    B = 24
+    q, qd, u = ch.sample_state(w, B, seed=5)
+    if "box" in name:
+        q[:, 2] = np.linspace(-0.01, 0.08, B)
+        q[:, 1] = np.linspace(-0.3, 0.3, B)
+    hs = HostSim(w, B)
+    hs.set_state(q, qd, u)
+    hs.eval(ref=True)
+    _, _, qdd = hs.get_state()
+    a, t, r, f = hs.get_contact()
+    ow = oracle.OracleWorld(w)
+    ncontact = 0
+    for b in range(B):
+        e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
+        ref = e.eval(True)
+        oa, ot, orr, of = e.get_contact()
+        ncontact += oa.sum()
+        assert (a[b] == oa).all(), (name, b)
+        assert relerr(qdd[b, :w.nq], ref) < 1e-8, (name, b, relerr(qdd[b, :w.nq], ref))
+        assert (t[b][oa == 1] == ot[oa == 1]).all(), (name, b)
+        assert np.allclose(f[b][oa == 1], of[oa == 1], rtol=1e-8, atol=1e-8 * max(1.0, np.abs(of).max()))
+    assert ncontact > 0
+
+
+@pytest.mark.parametrize("name", list(RIGID_WORLDS))
+def test_rigid_steps_match_oracle(oracle, name):
+    w = RIGID_WORLDS[name]()
+    B, nsteps = 8, 10
+    q, qd, u = ch.sample_state(w, B, seed=9)
+    if "box" in name:
+        q[:, 2] = np.linspace(0.02, 0.08, B)
+    hs = HostSim(w, B)
+    hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(nsteps)
+    hq, hqd, _ = hs.get_state()
+    ref = oracle_run(oracle, w, q, qd, u, nsteps)
+    ok = 0
+    for b in range(B):
+        ok += relerr(hq[b, :w.nq], ref[b][0][0]) < 1e-7
+    assert ok >= B - 1, ok
