@@ -792,10 +792,197 @@ struct Core {
   }
 
   /* Vert: friction pyramid + least-squares QP by the active-set method (rkfd_vert.c:73-103, 208-324;
-   * rkfd_opt_qp.c:43-181).  Returns the new contact flags of the selected environment. */
+   * rkFDQPSolveASM rkfd_opt_qp.c:43-181).  The KKT system [[-Q, Aw^T],[Aw, 0]] [x; l] = [c; 0] of every
+   * iteration is solved through its Schur complement S = Aw Q^-1 Aw^T: l = S^+ (Aw Q^-1 c) (pseudo-inverse of
+   * the small PSD matrix by cyclic Jacobi), x = Q^-1 (Aw^T l - c), which is the minimum-norm solution the
+   * reference obtains from zLESolveMP on the full KKT matrix ([EXT A-14]; redundant active rows only make
+   * the multipliers non-unique).  Returns the new contact flags of the selected environment. */
   RKFD_HD unsigned long long qp_vert(const ModelDev &m, bool ref, unsigned long long fl, int N){
-    (void)ref; (void)N;
-    return fl;
+    const int nlanes = c.lanes(), lane = c.lane();
+    const int n = 3*N, pyr = m.pyramid, mc = pyr*N;
+    const int nx = m.nmax, mx = m.pyramid*(m.nmax/3);
+    const int ob = m.ws_b, of = m.ws_f, oA = m.ws_A;
+    int o = m.ws_qp;
+    const int oQ = o; o += nx*nx; const int oQi = o; o += nx*nx; const int oc = o; o += nx; const int og = o; o += nx;
+    const int ox = o; o += nx; const int oxs = o; o += nx; const int onf = o; o += 3*mx; const int oidx = o; o += mx;
+    const int oY = o; o += nx*mx; const int oS = o; o += mx*mx; const int oV = o; o += mx*mx; const int olam = o; o += mx;
+    const int orhs = o; o += mx; const int oact = o; o += mx; const int ohist = o;     /* history: QP_HIST x (mx+1) */
+    const int QP_HIST = 32, QP_MAXIT = 256;
+    /* pyramid rows and compensated bias c (rkfd_vert.c:73-103, 208-232) */
+    for(int k=lane;k<N;k+=nlanes){
+      const PairDev &pr = m.pair[(int)G(m,k,26)]; const int sidx = (int)G(m,k,24); const V3 d = g3(m,k,12);
+      const double mu = ( (fl >> (2*sidx+1)) & 1ull ) ? pr.KF : pr.SF;
+      const double fric = mu*m.sc_cos[0];
+      for(int i=0;i<pyr;i++){ c.W(onf+3*(pyr*k+i)) = fric; c.W(onf+3*(pyr*k+i)+1) = m.sc_sin[i]; c.W(onf+3*(pyr*k+i)+2) = m.sc_cos[i]; }
+      c.W(of+3*k)   = c.W(ob+3*k)   + pr.K      * dot(d, g3(m,k,3));
+      c.W(of+3*k+1) = c.W(ob+3*k+1) + pr.K * mu * dot(d, g3(m,k,6));
+      c.W(of+3*k+2) = c.W(ob+3*k+2) + pr.K * mu * dot(d, g3(m,k,9));
+    }
+    c.gsync();
+    /* Q = A^T A + L, c <- A^T c (rkfd_vert.c:267-279) */
+    for(int e=lane;e<n*n;e+=nlanes){
+      const int i = e/n, j = e - i*n; double sum = 0;
+      for(int k=0;k<n;k++) sum += c.W(oA+k*n+i)*c.W(oA+k*n+j);
+      if( i == j ) sum += m.pair[(int)G(m,i/3,26)].L;
+      c.W(oQ+e) = sum; c.W(oQi+e) = (i == j) ? 1.0 : 0.0;
+    }
+    for(int i=lane;i<n;i+=nlanes){ double sum = 0; for(int j=0;j<n;j++) sum += c.W(oA+j*n+i)*c.W(of+j); c.W(oc+i) = sum; }
+    c.gsync();
+    /* Q^-1 by Gauss-Jordan on [Q | I] (Q is symmetric positive definite); the copy of Q is consumed */
+    for(int e=lane;e<n*n;e+=nlanes) c.W(oY+e) = c.W(oQ+e);
+    c.gsync();
+    for(int k=0;k<n;k++){
+      const double piv = 1.0/c.W(oY+k*n+k);
+      c.gsync();
+      for(int j=lane;j<n;j+=nlanes){ c.W(oY+k*n+j) *= piv; c.W(oQi+k*n+j) *= piv; }
+      c.gsync();
+      for(int e=lane;e<n*n;e+=nlanes){
+        const int i = e/n, j = e - i*n;
+        if( i == k ) continue;
+        const double fac = c.W(oY+i*n+k);
+        if( j != k ) c.W(oY+i*n+j) -= fac*c.W(oY+k*n+j);
+        c.W(oQi+i*n+j) -= fac*c.W(oQi+k*n+j);
+      }
+      c.gsync();
+      for(int i=lane;i<n;i+=nlanes) if( i != k ) c.W(oY+i*n+k) = 0.0;
+      c.gsync();
+    }
+    /* g = Q^-1 c ; initial point f_n = 1 per vertex (rkfd_vert.c:234-244); initial active set (rkfd_opt_qp.c:27-40) */
+    for(int i=lane;i<n;i+=nlanes){ double sum = 0; for(int j=0;j<n;j++) sum += c.W(oQi+i*n+j)*c.W(oc+j); c.W(og+i) = sum; c.W(ox+i) = (i%3 == 0) ? 1.0 : 0.0; }
+    c.gsync();
+    for(int r=lane;r<mc;r+=nlanes){
+      const int k = r/pyr;
+      const double cond = c.W(onf+3*r)*c.W(ox+3*k) + c.W(onf+3*r+1)*c.W(ox+3*k+1) + c.W(onf+3*r+2)*c.W(ox+3*k+2);
+      c.W(oidx+r) = fabs(cond) < ZTOL ? 1.0 : 0.0;
+    }
+    c.gsync();
+    int nhist = 0;
+    for(int iter=0; iter<QP_MAXIT; iter++){
+      /* active list in ascending order */
+      int ma = 0;
+      for(int r=0;r<mc;r++) if( c.W(oidx+r) != 0.0 ){ if( lane == 0 ) c.W(oact+ma) = (double)r; ma++; }
+      c.gsync();
+      /* Y_t = Q^-1 nf_t^T ; rhs_t = nf_t . g ; S = Aw Y */
+      for(int e=lane;e<ma*n;e+=nlanes){
+        const int t = e/n, i = e - t*n, r = (int)c.W(oact+t), k = r/pyr;
+        c.W(oY+t*n+i) = c.W(oQi+i*n+3*k)*c.W(onf+3*r) + c.W(oQi+i*n+3*k+1)*c.W(onf+3*r+1) + c.W(oQi+i*n+3*k+2)*c.W(onf+3*r+2);
+      }
+      for(int t=lane;t<ma;t+=nlanes){ const int r = (int)c.W(oact+t), k = r/pyr;
+        c.W(orhs+t) = c.W(onf+3*r)*c.W(og+3*k) + c.W(onf+3*r+1)*c.W(og+3*k+1) + c.W(onf+3*r+2)*c.W(og+3*k+2); }
+      c.gsync();
+      for(int e=lane;e<ma*ma;e+=nlanes){
+        const int t = e/ma, u = e - t*ma, r = (int)c.W(oact+t), k = r/pyr;
+        c.W(oS+e) = c.W(onf+3*r)*c.W(oY+u*n+3*k) + c.W(onf+3*r+1)*c.W(oY+u*n+3*k+1) + c.W(onf+3*r+2)*c.W(oY+u*n+3*k+2);
+        c.W(oV+e) = (t == u) ? 1.0 : 0.0;
+      }
+      c.gsync();
+      /* l = S^+ rhs: cyclic Jacobi eigen-decomposition of the symmetric S (ma x ma) */
+      for(int sweep=0; sweep<40 && ma>1; sweep++){
+        double part = 0;
+        for(int e=lane;e<ma*ma;e+=nlanes){ const int t = e/ma, u = e - t*ma; if( u > t ) part += c.W(oS+e)*c.W(oS+e); }
+        const double off = c.allsum(part);
+        if( off < 1.0e-300 ) break;
+        for(int p=0;p<ma-1;p++) for(int q=p+1;q<ma;q++){
+          const double apq = c.W(oS+p*ma+q);
+          if( fabs(apq) < 1.0e-300 ) continue;
+          const double th = (c.W(oS+q*ma+q) - c.W(oS+p*ma+p))/(2.0*apq);
+          const double tt = (th >= 0 ? 1.0 : -1.0)/(fabs(th) + sqrt(th*th + 1.0)), cs = 1.0/sqrt(tt*tt + 1.0), sn = tt*cs;
+          c.gsync();
+          for(int k=lane;k<ma;k+=nlanes){ const double akp = c.W(oS+k*ma+p), akq = c.W(oS+k*ma+q); c.W(oS+k*ma+p) = cs*akp - sn*akq; c.W(oS+k*ma+q) = sn*akp + cs*akq; }
+          c.gsync();
+          for(int k=lane;k<ma;k+=nlanes){ const double apk = c.W(oS+p*ma+k), aqk = c.W(oS+q*ma+k); c.W(oS+p*ma+k) = cs*apk - sn*aqk; c.W(oS+q*ma+k) = sn*apk + cs*aqk;
+                                           const double vkp = c.W(oV+k*ma+p), vkq = c.W(oV+k*ma+q); c.W(oV+k*ma+p) = cs*vkp - sn*vkq; c.W(oV+k*ma+q) = sn*vkp + cs*vkq; }
+          c.gsync();
+        }
+      }
+      double lmax = 0;
+      for(int t=0;t<ma;t++) lmax = fmax(lmax, fabs(c.W(oS+t*ma+t)));
+      for(int t=lane;t<ma;t+=nlanes){
+        double sum = 0;
+        for(int e=0;e<ma;e++){
+          const double ev = c.W(oS+e*ma+e);
+          if( fabs(ev) <= 1.0e-11*lmax ) continue;
+          double pr = 0; for(int u=0;u<ma;u++) pr += c.W(oV+u*ma+e)*c.W(orhs+u);
+          sum += c.W(oV+t*ma+e)*pr/ev;
+        }
+        c.W(olam+t) = sum;
+      }
+      c.gsync();
+      /* x* = sum_t l_t Y_t - g */
+      for(int i=lane;i<n;i+=nlanes){ double sum = -c.W(og+i); for(int t=0;t<ma;t++) sum += c.W(olam+t)*c.W(oY+t*n+i); c.W(oxs+i) = sum; }
+      c.gsync();
+      bool same = true;
+      for(int i=0;i<n;i++) if( !(fabs(c.W(oxs+i) - c.W(ox+i)) < ZTOL) ){ same = false; break; }
+#ifdef RKFD_QP_DEBUG
+      { double mincond = 1e300, maxres = 0; for(int r=0;r<mc;r++){ const int k=r/pyr; const double cd = c.W(onf+3*r)*c.W(ox+3*k)+c.W(onf+3*r+1)*c.W(ox+3*k+1)+c.W(onf+3*r+2)*c.W(ox+3*k+2); if(cd<mincond) mincond=cd; }
+        for(int t=0;t<ma;t++){ const int r=(int)c.W(oact+t), k=r/pyr; const double cd = c.W(onf+3*r)*c.W(oxs+3*k)+c.W(onf+3*r+1)*c.W(oxs+3*k+1)+c.W(onf+3*r+2)*c.W(oxs+3*k+2); if(fabs(cd)>maxres) maxres=fabs(cd); }
+        double lmn=1e300; for(int t=0;t<ma;t++) if(c.W(olam+t)<lmn) lmn=c.W(olam+t);
+        printf("iter %d ma %d same %d mincond(x) %.3e  |Aw x*| %.3e  lmin %.3e lmax_eig %.3e\n", iter, ma, (int)same, mincond, maxres, lmn, lmax); }
+#endif
+      if( same ){
+        c.gsync();
+        for(int i=lane;i<n;i+=nlanes) c.W(ox+i) = c.W(oxs+i);
+        bool neg = false; double lmin = 0;
+        for(int t=0;t<ma;t++){ const double l = c.W(olam+t); if( l < 0 ) neg = true; if( t == 0 || l < lmin ) lmin = l; }
+        if( !neg ){ c.gsync(); break; }                                  /* optimal */
+        c.gsync();
+        for(int t=lane;t<ma;t+=nlanes) if( fabs(c.W(olam+t) - lmin) < 1.0e-8 ) c.W(oidx+(int)c.W(oact+t)) = 0.0;
+        c.gsync();
+        continue;
+      }
+      /* STEP2: step length to the first blocking constraint, new active constraints (rkfd_opt_qp.c:133-151) */
+      double alpha = 1.0;
+      for(int r=0;r<mc;r++){
+        if( c.W(oidx+r) != 0.0 ) continue;
+        const int k = r/pyr;
+        const double ad = c.W(onf+3*r)*(c.W(oxs+3*k)-c.W(ox+3*k)) + c.W(onf+3*r+1)*(c.W(oxs+3*k+1)-c.W(ox+3*k+1)) + c.W(onf+3*r+2)*(c.W(oxs+3*k+2)-c.W(ox+3*k+2));
+        if( ad < 0 ){
+          const double cond = c.W(onf+3*r)*c.W(ox+3*k) + c.W(onf+3*r+1)*c.W(ox+3*k+1) + c.W(onf+3*r+2)*c.W(ox+3*k+2);
+          const double t2 = (0.0 - cond)/ad; if( t2 < alpha ) alpha = t2;
+        }
+      }
+      c.gsync();
+      for(int i=lane;i<n;i+=nlanes) c.W(ox+i) += alpha*(c.W(oxs+i) - c.W(ox+i));
+      c.gsync();
+      for(int r=lane;r<mc;r+=nlanes){
+        if( c.W(oidx+r) != 0.0 ) continue;
+        const int k = r/pyr;
+        const double cond = c.W(onf+3*r)*c.W(ox+3*k) + c.W(onf+3*r+1)*c.W(ox+3*k+1) + c.W(onf+3*r+2)*c.W(ox+3*k+2);
+        if( fabs(cond) < ZTOL ) c.W(oidx+r) = 1.0;
+      }
+      c.gsync();
+      /* anti-cycling: same active set with the same objective value -> stop (rkfd_opt_qp.c:152-171) */
+      double objv = 0;
+      for(int i=0;i<n;i++){ double sum = 0; for(int j=0;j<n;j++) sum += c.W(oQ+i*n+j)*c.W(ox+j); objv += 0.5*c.W(ox+i)*sum + c.W(oc+i)*c.W(ox+i); }
+      bool endflag = false;
+      for(int h=0;h<nhist && !endflag;h++){
+        bool eq = true;
+        for(int r=0;r<mc;r++) if( c.W(oidx+r) != c.W(ohist+h*(mx+1)+r) ){ eq = false; break; }
+        if( eq && !(fabs(c.W(ohist+h*(mx+1)+mx)/objv - 1.0) > 1.0e-8) ) endflag = true;
+      }
+      if( endflag ) break;
+      if( nhist < QP_HIST ){
+        c.gsync();
+        for(int r=lane;r<mc;r+=nlanes) c.W(ohist+nhist*(mx+1)+r) = c.W(oidx+r);
+        if( lane == 0 ) c.W(ohist+nhist*(mx+1)+mx) = objv;
+        nhist++;
+        c.gsync();
+      } else { bad |= 2; break; }
+    }
+    /* f = x / dt ; forces, wrenches, friction state from the final active set (rkfd_vert.c:282, 286-324) */
+    unsigned long long nfl = fl;
+    for(int k=0;k<N;k++){
+      const int sidx = (int)G(m,k,24);
+      const V3 fw = (c.W(ox+3*k)/m.dt)*g3(m,k,3) + (c.W(ox+3*k+1)/m.dt)*g3(m,k,6) + (c.W(ox+3*k+2)/m.dt)*g3(m,k,9);
+      bool flag = false;
+      for(int i=0;i<pyr;i++) if( c.W(oidx+pyr*k+i) != 0.0 ){ flag = true; break; }
+      if( ref ){ if( flag ) nfl |= 2ull << (2*sidx); else nfl &= ~(2ull << (2*sidx)); }
+      if( lane == 0 ){
+        push_rigid(m, k, fw, ref);
+        if( ref && flag ){ const V3 prob = g3(m,k,18); c.gst(c.st.cref,3*sidx,prob.x); c.gst(c.st.cref,3*sidx+1,prob.y); c.gst(c.st.cref,3*sidx+2,prob.z); }
+      }
+    }
+    return nfl;
   }
 
   RKFD_HD void load_flags(){ piv = c.st.piv_type[c.e]; cfl = c.st.cflags[c.e]; }

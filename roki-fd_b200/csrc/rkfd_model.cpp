@@ -162,7 +162,8 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
     m.ws_du = o; o += n*nl;           /* per probe column: joint-space increments (scalar per link; multi-DoF joints use 6) */
     m.ws_da = o; o += n*6*nl;         /* per probe column: link acceleration increments */
     m.ws_qp = o;
-    if( m.solver == S_VERT ) o += n*n + 2*n + 3*mc + mc + 2*nm*nm + 4*nm + 64;   /* Q, c, d | nf rows | idx | KKT, V | xy, cb, w, tmp */
+    (void)nm;
+    if( m.solver == S_VERT ) o += 2*n*n + 4*n + 3*mc + mc + n*mc + 2*mc*mc + 3*mc + 32*(mc+1) + 64;   /* layout in Core::qp_vert */
     m.ws_doubles = (o + 31) & ~31;
   }
   return true;
