@@ -172,11 +172,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") --------------------------------------------------------
-    for _ in range(args.warmup):
-        fd.update()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_pre = time.perf_counter()
+    for _ in range(args.warmup):
+        fd.update()
+    # keep the GPU under the same load until nvidia-smi has delivered a few samples (its start-up takes ~0.3 s):
+    # extra untimed warm-up steps, so the clocks reported are those of the loaded device
+    while time.perf_counter() - t_pre < 1.0:
+        for _ in range(10):
+            fd.update()
+        torch.cuda.synchronize()
+    barrier()
     l0 = fd.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record(stream)
@@ -188,6 +195,8 @@ def main():
     clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
+    if os.environ.get("RKFD_BENCH_DEBUG"):
+        print("rank %d: total %.3f ms, per-launch min/median/max %.3f/%.3f/%.3f ms" % (rank, total_ms, min(per_launch_ms), float(np.median(per_launch_ms)), max(per_launch_ms)), file=sys.stderr)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -246,6 +246,7 @@ struct Core {
     const int qs = m.rk_slot, qds = m.rk_slot + m.nq;
     for(int i=0;i<m.nl;i++){
       const LinkDev &L = m.link[i]; const int sl = L.slot;
+      if( !Ctx::RIGID ) c.phase_sync(3);
       if( !L.serial ){
         if( L.parent < 0 ){ Rw = ident3(); pw = v3(0,0,0); vl = v3(0,0,0); om = v3(0,0,0); gd = v3(0,0,-GRAVITY); }
         else {
@@ -333,6 +334,7 @@ struct Core {
     for(int i=0;i<m.nl;i++) if( m.link[i].accum_slot >= 0 ) for(int k=0;k<ACCUM_SLOTS;k++) c.S(m.link[i].accum_slot+k) = 0.0;
     for(int i=m.nl-1;i>=0;i--){
       const LinkDev &L = m.link[i]; const int sl = L.slot;
+      if( !Ctx::RIGID ) c.phase_sync(3);
       const V3 om = ld3(L.wslot), gd = ld3(L.wslot+3);
       const V3 mc = v3(L.mc[0],L.mc[1],L.mc[2]);
       S3 A, C; M3 B;
@@ -507,6 +509,7 @@ struct Core {
     V3 al = v3(0,0,0), aa = v3(0,0,0), om = v3(0,0,0);
     for(int i=0;i<m.nl;i++){
       const LinkDev &L = m.link[i]; const int sl = L.slot;
+      if( !Ctx::RIGID ) c.phase_sync(3);
       if( !L.serial ){
         if( L.parent < 0 ){ al = v3(0,0,0); aa = v3(0,0,0); om = v3(0,0,0); }
         else { const int b = m.link[L.parent].branch_slot; al = ld3(b); aa = ld3(b+3); om = ld3(b+6); }
@@ -993,7 +996,11 @@ struct Core {
   }
   RKFD_HD void evaluate(const ModelDev &m, int stage){
     const bool ref = (stage == ST_REF) || (stage == ST_EVAL_REF);
+    /* keep the warps of a block in the same pass: the instruction working set of the SM is then one pass, not
+     * the union of all passes (the kernel is far larger than the instruction cache) */
+    c.phase_sync(1);
     pass1(m, ref);
+    if( !Ctx::RIGID ) c.phase_sync(2);
     if( Ctx::RIGID ){
       /* rigid pairs in contact (reference rkfd_vert.c:385-386): any lane of the warp -> cooperative solve */
       const unsigned act = c.ballot( RKFD_POPC64(cfl & m.rigid_mask) > 0 );
@@ -1002,7 +1009,9 @@ struct Core {
         rigid_solve(m, ref, act);
       }
     }
-    pass2(m, ref); pass3(m, stage);
+    pass2(m, ref);
+    if( !Ctx::RIGID ) c.phase_sync(2);
+    pass3(m, stage);
   }
   /* mode 0: rkFDUpdate x nsteps (reference rkfd_sim.c:560-566); mode 1 / 2: a single non-committing /
    * committing evaluation on the committed state (2 = rkFDUpdateInit's t=0 evaluation).  One stage loop so

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -91,7 +92,7 @@ struct Shard {
 };
 
 static int g_next_engine_id = 1;
-static int g_model_owner[64][8] = {{0}};   /* [device][variant]: engine whose model sits in that constant bank */
+static int g_model_owner[64][16] = {{0}};   /* [device][variant]: engine whose model sits in that constant bank */
 static int variant_index(const KernelVariant *kv);
 
 template <class T> static T *dalloc(Shard &s, size_t n)
@@ -103,13 +104,16 @@ template <class T> static T *dalloc(Shard &s, size_t n)
 
 /* kernel variants, one translation unit each (rkfd_kernel_variant.cu) */
 #define RKFD_DECL(B,G,R) extern const KernelVariant rkfd_variant_##B##_##G##_##R;
-RKFD_DECL(128,0,0) RKFD_DECL(64,0,0) RKFD_DECL(32,0,0) RKFD_DECL(64,1,0)
-RKFD_DECL(128,0,1) RKFD_DECL(64,0,1) RKFD_DECL(32,0,1) RKFD_DECL(64,1,1)
-static const KernelVariant *g_variants[] = {
-  &rkfd_variant_128_0_0, &rkfd_variant_64_0_0, &rkfd_variant_32_0_0, &rkfd_variant_64_1_0,
-  &rkfd_variant_128_0_1, &rkfd_variant_64_0_1, &rkfd_variant_32_0_1, &rkfd_variant_64_1_1 };
+RKFD_DECL(256,0,0) RKFD_DECL(128,0,0) RKFD_DECL(64,0,0) RKFD_DECL(32,0,0) RKFD_DECL(64,1,0)
+RKFD_DECL(256,0,1) RKFD_DECL(128,0,1) RKFD_DECL(64,0,1) RKFD_DECL(32,0,1) RKFD_DECL(64,1,1)
+constexpr int NVARIANTS = 10;
+/* order = preference among variants that keep the same number of environments resident (measured on B200,
+ * profiles/r01_sync_sweep.md: 128-thread blocks with per-pass barriers are the best compromise) */
+static const KernelVariant *g_variants[NVARIANTS] = {
+  &rkfd_variant_128_0_0, &rkfd_variant_256_0_0, &rkfd_variant_64_0_0, &rkfd_variant_32_0_0, &rkfd_variant_64_1_0,
+  &rkfd_variant_128_0_1, &rkfd_variant_256_0_1, &rkfd_variant_64_0_1, &rkfd_variant_32_0_1, &rkfd_variant_64_1_1 };
 
-static int variant_index(const KernelVariant *kv){ for(int i=0;i<8;i++) if( g_variants[i] == kv ) return i; return 0; }
+static int variant_index(const KernelVariant *kv){ for(int i=0;i<NVARIANTS;i++) if( g_variants[i] == kv ) return i; return 0; }
 
 Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : model_(model), B_(B), id_(g_next_engine_id++)
 {
@@ -124,7 +128,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     const int e0 = (int)((long long)B*g/G), e1 = (int)((long long)B*(g+1)/G);
     if( e1 <= e0 ) continue;
     Shard *s = new Shard; shards_.push_back(s);
-    s->dev = devs[g]; s->e0 = e0; s->B = e1-e0; s->ld = (s->B + 31) & ~31;
+    s->dev = devs[g]; s->e0 = e0; s->B = e1-e0; s->ld = (s->B + 255) & ~255;   /* whole blocks of any variant: no thread exits early */
     CK(cudaSetDevice(s->dev));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     const int nq = model.nq > 0 ? model.nq : 1, nl = model.nl > 0 ? model.nl : 1, ns = model.nslot > 0 ? model.nslot : 1;
@@ -148,6 +152,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     for(int pass=0; pass<2 && best==0; pass++)
       for(const KernelVariant *kv : g_variants){
         if( kv->rigid != rigid || kv->gscr != (pass == 1) ) continue;
+        if( const char *fb = std::getenv("RKFD_FORCE_BLOCK") ) if( std::atoi(fb) != kv->block ) continue;   /* tuning aid */
         const size_t smem = kv->gscr ? 0 : (size_t)model.nscratch*kv->block*sizeof(double);
         if( smem > 227*1024 ) continue;
         const int nb = kv->blocks_per_sm(smem);

@@ -37,6 +37,11 @@ struct DevCtx {
   __device__ __forceinline__ void select(int src){ tid = (tid0 & ~31) | src; e = (e0 & ~31) | src; }
   __device__ __forceinline__ void unselect(){ tid = tid0; e = e0; }
   __device__ __forceinline__ void gsync() const { __syncwarp(); }
+#ifndef RKFD_SYNC_LEVEL
+#define RKFD_SYNC_LEVEL 2
+#endif
+  /* level 1: once per evaluation, 2: per pass, 3: per link iteration */
+  __device__ __forceinline__ void phase_sync(int level) const { if( level <= RKFD_SYNC_LEVEL ) __syncthreads(); }
   __device__ __forceinline__ double &W(int i){ return st.ws[(size_t)(e0 >> 5)*wsd + i]; }
   /* per-env state in HBM: element k of the selected environment (global address space asserted: LDG/STG, not generic) */
   __device__ __forceinline__ double gld(const double *p, int k) const { const double *a = p + ((size_t)k*st.ld + e); __builtin_assume(__isGlobal(a)); return *a; }

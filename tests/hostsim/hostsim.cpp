@@ -30,6 +30,7 @@ struct HostCtx {
   void select(int){}
   void unselect(){}
   void gsync(){}
+  void phase_sync(int){}
   double &W(int i){ return wsp[i]; }
   double gld(const double *p, int k) const { return p[(size_t)k*st.ld + e]; }
   void gst(double *p, int k, double v){ p[(size_t)k*st.ld + e] = v; }

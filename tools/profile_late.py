@@ -1,0 +1,17 @@
+"""Runs C3 for N steps (arms fall onto the floor) so that a profiler can capture the step kernel in the
+contact-rich regime: ncu -k regex:rkfd_step_kernel -s <N> -c 1 python tools/profile_late.py <N>"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, rokifd_b200
+from rokifd_b200 import capi, chains as ch
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 700
+w = ch.world_c3()
+B = 262144
+q, qd, u = ch.sample_state(w, B, seed=20260418)
+fd, _ = capi.create_world(w, B=B); fd.batch_set_state(q, qd); fd.batch_set_motor_input(u); fd.update_init()
+for _ in range(n + 4):
+    fd.update()
+fd.batch_sync()
+a, t, r, f = fd.batch_get_contact()
+print("envs in contact %.3f, mean active vertices %.2f" % ((a.sum(1) > 0).mean(), a.sum(1).mean()))
+fd.destroy()
