@@ -26,9 +26,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_PER_GPU = 262144
+SETTLE_STEPS = 700      # untimed: the arms fall from the random initial states until ~40-50 % of them touch the floor
 METRIC = "env-steps/sec (batched FD+contact step)"
 UNIT = "env-steps/s"
-WORKLOAD = "C3: arm7 (7-DoF, DC motors, joint friction) + 8-vertex penalty ground contact, %d envs/GPU" % B_PER_GPU
+WORKLOAD = ("C3: arm7 (7-DoF, DC motors, joint friction) + 8-vertex penalty ground contact, %d envs/GPU, states after "
+            "%d settle steps from the random initial states" % (B_PER_GPU, SETTLE_STEPS))
 # algorithmic work per env-step (restated in DESIGN.md)
 ALG_BYTES = 1054.0
 ALG_FLOP = 20471.0
@@ -85,16 +87,23 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline_run(world, ch, n_envs, n_steps, threads=0, seed=20260418):
-    """The oracle (CPU restatement of the reference's algorithm) on the host cores: env-steps/s."""
+def cpu_settled_state(world, ch, n_envs, seed=20260418, settle=SETTLE_STEPS):
+    """Initial states of the CPU sample: the same synthetic states, settled by the oracle itself (untimed)."""
     from oracle import oracle as orc
     ow = orc.OracleWorld(world)
     q, qd, u = ch.sample_state(world, n_envs, seed=seed)
+    if settle > 0:
+        q, qd, _, _ = ow.batch_run(q, qd, u, nsteps=settle)
+    return ow, q, qd, u
+
+
+def cpu_baseline_run(ow, q, qd, u, n_steps, threads=0):
+    """The oracle (CPU restatement of the reference's algorithm) on the host cores: env-steps/s."""
     t0 = time.perf_counter()
     _, _, _, used = ow.batch_run(q, qd, u, nsteps=n_steps, nthreads=threads)
     dt = time.perf_counter() - t0
     # batch_run also performs rkFDUpdateInit's evaluation per env: count it as 1/5 of a step
-    return n_envs * (n_steps + 0.2) / dt, used, dt
+    return q.shape[0] * (n_steps + 0.2) / dt, used, dt
 
 
 def run_reference(args):
@@ -107,13 +116,14 @@ def run_reference(args):
     from rokifd_b200 import chains as ch
     world = ch.world_c3()
     cores = os.cpu_count() or 1
-    n_envs = 1024 * cores
+    n_envs = 512 * cores
+    ow, q, qd, u = cpu_settled_state(world, ch, n_envs)
     for _ in range(args.warmup):
-        cpu_baseline_run(world, ch, n_envs, 1)
+        cpu_baseline_run(ow, q, qd, u, 1)
     t0 = time.perf_counter()
     vals = []
     for _ in range(args.steps):
-        v, used, _ = cpu_baseline_run(world, ch, n_envs, 1)
+        v, used, _ = cpu_baseline_run(ow, q, qd, u, 1)
         vals.append(v)
     dt = time.perf_counter() - t0
     value = float(np.mean(vals))
@@ -174,15 +184,12 @@ def main():
     # ---- device-resident throughput ("value") --------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    t_pre = time.perf_counter()
+    # settle (untimed, ~1 s of GPU load: also lets nvidia-smi deliver samples of the loaded device), then warm-up
+    fd.update_n(SETTLE_STEPS // 2)
+    torch.cuda.synchronize()
+    fd.update_n(SETTLE_STEPS - SETTLE_STEPS // 2)
     for _ in range(args.warmup):
         fd.update()
-    # keep the GPU under the same load until nvidia-smi has delivered a few samples (its start-up takes ~0.3 s):
-    # extra untimed warm-up steps, so the clocks reported are those of the loaded device
-    while time.perf_counter() - t_pre < 1.0:
-        for _ in range(10):
-            fd.update()
-        torch.cuda.synchronize()
     barrier()
     l0 = fd.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -203,6 +210,9 @@ def main():
     total_ms = float(t.item())
     value = B * world_size * args.steps / (total_ms * 1e-3)
     assert (fd.batch_get_status() == 0).all(), "non-finite accelerations in the timed run"
+    ca, _, _, _ = fd.batch_get_contact()
+    contact_frac, mean_active = float((ca.sum(1) > 0).mean()), float(ca.sum(1).mean())
+    q, qd, _ = (np.ascontiguousarray(x) for x in fd.batch_get_state())     # settled states: inputs of the e2e leg
 
     # ---- end to end through the C-ABI with HOST buffers ("e2e") -----------------------------------------
     nq, nl = world.nq, world.nl
@@ -250,6 +260,7 @@ def main():
            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": WORKLOAD, "envs_per_gpu": B, "dt": world.dt, "integrator": "RKG", "solver": world.solver,
+                      "settle_steps": SETTLE_STEPS, "envs_in_contact": contact_frac, "mean_active_vertices": mean_active,
                       "l2": "per-GPU state (%.0f MB) is larger than the 126 MB L2" % (B * 8 * 140 / 1e6)},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
            "gpu_launches": int(launches),
@@ -262,10 +273,11 @@ def main():
                              "algorithmic_flop_per_env_step": ALG_FLOP}}
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_envs, n_steps = 2048 * cores, 10
-        v, used, dt = cpu_baseline_run(world, ch, n_envs, n_steps)
+        n_envs, n_steps = 512 * cores, 20
+        ow, cq, cqd, cu = cpu_settled_state(world, ch, n_envs)
+        v, used, dt = cpu_baseline_run(ow, cq, cqd, cu, n_steps)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": "port",
-                               "sample": "%d envs x %d steps of the same workload (%.1f s)" % (n_envs, n_steps, dt),
+                               "sample": "%d envs x %d steps of the same workload, settled %d steps first (timed %.1f s)" % (n_envs, n_steps, SETTLE_STEPS, dt),
                                "note": "CPU restatement of RoKi-FD's algorithm; reference un-buildable (ZEDA/ZM/Zeo/RoKi absent)"}
     fd.destroy()
     if rank == 0:
