@@ -287,6 +287,13 @@ __ROKI_FD_EXPORT int rkFDBatchGetStatus(rkFD *fd, int *status);                 
 __ROKI_FD_EXPORT int rkFDBatchEval(rkFD *fd, int do_up_ref);                    /* one evaluation on the committed state */
 __ROKI_FD_EXPORT rkFD *rkFDUpdateN(rkFD *fd, int k);                            /* k steps in one launch, asynchronous */
 __ROKI_FD_EXPORT int rkFDBatchSync(rkFD *fd);
+/* asynchronous transfers for pipelined callers: host buffers must be pinned and stay valid until rkFDBatchSync;
+ * copies run on dedicated streams and overlap the step kernels of neighbouring steps.  rkFDBatchJoin makes the
+ * compute stream wait for all queued copies. */
+__ROKI_FD_EXPORT int rkFDBatchSetStateAsync(rkFD *fd, const double *q, const double *qd);
+__ROKI_FD_EXPORT int rkFDBatchSetMotorInputAsync(rkFD *fd, const double *u);
+__ROKI_FD_EXPORT int rkFDBatchGetStateAsync(rkFD *fd, double *q, double *qd, double *qdd);
+__ROKI_FD_EXPORT int rkFDBatchJoin(rkFD *fd);
 __ROKI_FD_EXPORT void *rkFDBatchDevicePtr(rkFD *fd, int shard, int which, int *ld, int *B);  /* 0 q, 1 qd, 2 qdd, 3 u; SoA [k][ld] */
 __ROKI_FD_EXPORT long long rkFDBatchLaunchCount(rkFD *fd);
 __ROKI_FD_EXPORT const char *rkFDBatchLastError(void);

@@ -76,6 +76,8 @@ def lib():
         "rkFDBatchSetMotorInput": (ci, [vp, vp]), "rkFDBatchGetContactForce": (ci, [vp, vp]),
         "rkFDBatchGetContactState": (ci, [vp, vp, vp, vp]), "rkFDBatchSetContactState": (ci, [vp, vp, vp, vp]),
         "rkFDBatchGetPivot": (ci, [vp, vp, vp]), "rkFDBatchSetPivot": (ci, [vp, vp, vp]),
+        "rkFDBatchSetStateAsync": (ci, [vp, vp, vp]), "rkFDBatchSetMotorInputAsync": (ci, [vp, vp]),
+        "rkFDBatchGetStateAsync": (ci, [vp, vp, vp, vp]), "rkFDBatchJoin": (ci, [vp]),
         "rkFDBatchGetStatus": (ci, [vp, vp]), "rkFDBatchEval": (ci, [vp, ci]), "rkFDBatchSync": (ci, [vp]),
         "rkFDBatchDevicePtr": (vp, [vp, ci, ci, _ip, _ip]), "rkFDBatchLaunchCount": (C.c_longlong, [vp]),
         "rkFDBatchLastError": (C.c_char_p, []), "rkFDBatchDeviceCount": (ci, []), "rkFDB200MeasureFp64": (ci, [_dp]),
@@ -332,6 +334,19 @@ class RkFD:
             return q[:, :n], qd[:, :n], qdd[:, :n]
         self._ck(lib().rkFDBatchGetState(self.h, _ptr(q), _ptr(qd), _ptr(qdd)))
         return q, qd, qdd
+
+    def batch_set_state_async(self, q, qd):
+        """pinned host buffers (numpy arrays or raw addresses); valid until batch_sync()"""
+        self._ck(lib().rkFDBatchSetStateAsync(self.h, _ptr(q), _ptr(qd)))
+
+    def batch_set_motor_input_async(self, u):
+        self._ck(lib().rkFDBatchSetMotorInputAsync(self.h, _ptr(u)))
+
+    def batch_get_state_async(self, q, qd, qdd):
+        self._ck(lib().rkFDBatchGetStateAsync(self.h, _ptr(q), _ptr(qd), _ptr(qdd)))
+
+    def batch_join(self):
+        self._ck(lib().rkFDBatchJoin(self.h))
 
     def batch_set_motor_input(self, u):
         if isinstance(u, np.ndarray):

@@ -301,17 +301,17 @@ struct Core {
 
   /* motor + joint friction of a 1-DoF joint: returns tau = driving torque + friction, jm = rotor inertia
    * (rkfd_util.c:330-364, [EXT A-6, A-7]); at the reference stage commits pivot type and prev_trq */
-  RKFD_HD double joint_torque(const ModelDev &m, const LinkDev &L, int i, bool ref, double &jm){
-    const int j = L.qofs;
+  RKFD_HD double joint_torque(const ModelDev &m, const LinkDev &L, int i, bool ref, double &jm, double u_in, double prev_in){
+    const int j = L.qofs; (void)i;
     const double v = c.S(m.rk_slot + m.nq + j);
     double tdrive = 0.0, tf = 0.0; jm = 0.0;
     if( L.mtype != M_NONE ){
-      double e = c.gld(c.st.u, i);
+      double e = u_in;
       e = e < L.m_min ? L.m_min : ( e > L.m_max ? L.m_max : e );
       if( L.mtype == M_DC ){
         const double tin = L.m_tin*e, treg = L.m_reg*v;
         jm = L.m_jm; tdrive = tin - treg;
-        tf = jm; tf *= -v / m.dt; tf -= tin; tf += treg; tf += c.gld(c.st.piv_prev, j);
+        tf = jm; tf *= -v / m.dt; tf -= tin; tf += treg; tf += prev_in;
         double fmax;
         if( !(piv & (1u<<j)) ) fmax = L.sfriction;
         else {
@@ -332,9 +332,15 @@ struct Core {
     S3 kA, kC; M3 kB; V3 kf, kn;          /* contribution carried to link i from its serial child */
     kA.xx=kA.xy=kA.xz=kA.yy=kA.yz=kA.zz=0; kC = kA; kB.xx=kB.xy=kB.xz=kB.yx=kB.yy=kB.yz=kB.zx=kB.zy=kB.zz=0; kf = v3(0,0,0); kn = kf;
     for(int i=0;i<m.nl;i++) if( m.link[i].accum_slot >= 0 ) for(int k=0;k<ACCUM_SLOTS;k++) c.S(m.link[i].accum_slot+k) = 0.0;
+    /* motor input and previous driving torque of the NEXT link to be processed are requested one iteration
+     * ahead, so that their HBM/L2 latency overlaps the articulated-inertia arithmetic of the current link */
+    double nx_u = 0.0, nx_prev = 0.0;
+    if( m.nl > 0 && m.link[m.nl-1].mtype != M_NONE ){ nx_u = c.gld(c.st.u, m.nl-1); nx_prev = c.gld(c.st.piv_prev, m.link[m.nl-1].qofs); }
     for(int i=m.nl-1;i>=0;i--){
       const LinkDev &L = m.link[i]; const int sl = L.slot;
       if( !Ctx::RIGID ) c.phase_sync(3);
+      const double pf_u = nx_u, pf_prev = nx_prev;
+      if( i > 0 && m.link[i-1].mtype != M_NONE ){ nx_u = c.gld(c.st.u, i-1); nx_prev = c.gld(c.st.piv_prev, m.link[i-1].qofs); }
       const V3 om = ld3(L.wslot), gd = ld3(L.wslot+3);
       const V3 mc = v3(L.mc[0],L.mc[1],L.mc[2]);
       S3 A, C; M3 B;
@@ -371,7 +377,7 @@ struct Core {
       }
       switch(L.jtype){
       case J_REVOL: {
-        double jm; const double tau = joint_torque(m, L, i, ref, jm);
+        double jm; const double tau = joint_torque(m, L, i, ref, jm, pf_u, pf_prev);
         const V3 Ul = col2(B), Ua = v3(C.xz, C.yz, C.zz);
         const double Dinv = 1.0/(C.zz + jm), u = tau - pn.z;
         st3(sl, Ul); st3(sl+3, Ua); c.S(sl+8) = Dinv; c.S(sl+9) = u;
@@ -382,7 +388,7 @@ struct Core {
         pf = pf + u*Wl; pn = pn + u*Wa;
       } break;
       case J_PRISM: {
-        double jm; const double tau = joint_torque(m, L, i, ref, jm);
+        double jm; const double tau = joint_torque(m, L, i, ref, jm, pf_u, pf_prev);
         const V3 Ul = v3(A.xz, A.yz, A.zz), Ua = v3(B.zx, B.zy, B.zz);
         const double Dinv = 1.0/(A.zz + jm), u = tau - pf.z;
         st3(sl, Ul); st3(sl+3, Ua); c.S(sl+8) = Dinv; c.S(sl+9) = u;
@@ -467,11 +473,16 @@ struct Core {
   }
   /* velocity-like (vector-space) component j */
   RKFD_HD void rk_lin(const ModelDev &m, const RK &k, int stage, int slotS, int slotP, double *gin, double *gout, int j, double slope){
+    const double F = ( stage >= ST_K2 && stage <= ST_K4 ) ? c.gld(gout, j) : 0.0, x0 = stage == ST_K2 ? c.gld(gin, j) : 0.0;
+    rk_lin_pf(k, stage, slotS, slotP, gout, j, slope, F, x0);
+  }
+  /* F = running combination and x0 = committed value, fetched by the caller (possibly one link ahead) */
+  RKFD_HD void rk_lin_pf(const RK &k, int stage, int slotS, int slotP, double *gout, int j, double slope, double F, double x0g){
     switch(stage){
     case ST_K1: { const double x0 = c.S(slotS); c.gst(gout, j, x0 + k.b1*slope); c.S(slotP) = x0 + k.c31*slope; c.S(slotS) = x0 + k.c21*slope; } break;
-    case ST_K2: { const double x0 = c.gld(gin, j); c.gst(gout, j, c.gld(gout, j) + k.b2*slope); c.S(slotS) = c.S(slotP) + k.c32*slope; c.S(slotP) = x0 + k.c42*slope; } break;
-    case ST_K3: { c.gst(gout, j, c.gld(gout, j) + k.b3*slope); c.S(slotS) = c.S(slotP) + k.c43*slope; } break;
-    case ST_K4: { const double x = c.gld(gout, j) + k.b4*slope; c.gst(gout, j, x); c.S(slotS) = x; } break;
+    case ST_K2: { c.gst(gout, j, F + k.b2*slope); c.S(slotS) = c.S(slotP) + k.c32*slope; c.S(slotP) = x0g + k.c42*slope; } break;
+    case ST_K3: { c.gst(gout, j, F + k.b3*slope); c.S(slotS) = c.S(slotP) + k.c43*slope; } break;
+    case ST_K4: { const double x = F + k.b4*slope; c.gst(gout, j, x); c.S(slotS) = x; } break;
     default: break;
     }
   }
@@ -507,9 +518,22 @@ struct Core {
   RKFD_HD void pass3(const ModelDev &m, int stage){
     const RK k = rk_coef(m.dt);
     V3 al = v3(0,0,0), aa = v3(0,0,0), om = v3(0,0,0);
+    /* running combination (and, at stage 2, the committed state) of the next 1-DoF joint are requested one link ahead */
+    double nxq[4] = {0,0,0,0};
+    const bool pfF = stage >= ST_K2 && stage <= ST_K4, pfX = stage == ST_K2;
     for(int i=0;i<m.nl;i++){
       const LinkDev &L = m.link[i]; const int sl = L.slot;
       if( !Ctx::RIGID ) c.phase_sync(3);
+      if( i == 0 && L.ndof == 1 ){
+        if( pfF ){ nxq[0] = c.gld(c.st.q[c.cur^1], L.qofs); nxq[1] = c.gld(c.st.qd[c.cur^1], L.qofs); }
+        if( pfX ){ nxq[2] = c.gld(c.st.q[c.cur], L.qofs); nxq[3] = c.gld(c.st.qd[c.cur], L.qofs); }
+      }
+      const double pfq[4] = { nxq[0], nxq[1], nxq[2], nxq[3] };
+      if( i+1 < m.nl && m.link[i+1].ndof == 1 ){
+        const int jn = m.link[i+1].qofs;
+        if( pfF ){ nxq[0] = c.gld(c.st.q[c.cur^1], jn); nxq[1] = c.gld(c.st.qd[c.cur^1], jn); }
+        if( pfX ){ nxq[2] = c.gld(c.st.q[c.cur], jn); nxq[3] = c.gld(c.st.qd[c.cur], jn); }
+      }
       if( !L.serial ){
         if( L.parent < 0 ){ al = v3(0,0,0); aa = v3(0,0,0); om = v3(0,0,0); }
         else { const int b = m.link[L.parent].branch_slot; al = ld3(b); aa = ld3(b+3); om = ld3(b+6); }
@@ -526,7 +550,14 @@ struct Core {
         const double acc = c.S(sl+8)*( c.S(sl+9) - (dot(Ul,xl) + dot(Ua,xa)) );
         al = xl + zl; aa = xa + za;
         if( L.jtype == J_REVOL ) aa.z += acc; else al.z += acc;
-        rk_dof(m, k, stage, L.qofs, acc);
+        if( stage == ST_PROBE ){}
+        else if( stage >= ST_REF ){ c.gst(c.st.qdd, L.qofs, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; }
+        else {
+          const int j = L.qofs, qs = m.rk_slot + j, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
+          const double vel = c.S(qds);
+          rk_lin_pf(k, stage, qs,  pq,  c.st.q[c.cur^1],  j, vel, pfq[0], pfq[2]);
+          rk_lin_pf(k, stage, qds, pqd, c.st.qd[c.cur^1], j, acc, pfq[1], pfq[3]);
+        }
       } break;
       case J_SPHER: {
         const M3 Ul = ldm(sl), Ua = ldm(sl+9); const S3 Di = lds(sl+18); const V3 u = ld3(sl+24);

@@ -87,6 +87,11 @@ struct Shard {
   StateDev st;
   cudaStream_t stream = nullptr; bool own_stream = true;
   double *dstage = nullptr; size_t nstage = 0;
+  /* asynchronous transfers: copy streams + a ring of staging buffers, each guarded by a "consumed" event */
+  static constexpr int NRING = 8;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  double *ring[NRING] = {nullptr}; cudaEvent_t ring_done[NRING] = {nullptr}; cudaEvent_t ring_ready[NRING] = {nullptr};
+  int ring_next = 0; bool ring_init = false;
   const KernelVariant *kv = nullptr; size_t smem = 0;
   std::vector<void*> allocs;
 };
@@ -173,6 +178,9 @@ Engine::~Engine()
     cudaSetDevice(s->dev);
     cudaStreamSynchronize(s->stream);
     if( s->kv && g_model_owner[s->dev & 63][variant_index(s->kv)] == id_ ) g_model_owner[s->dev & 63][variant_index(s->kv)] = 0;
+    if( s->ring_init ){ cudaStreamSynchronize(s->h2d_stream); cudaStreamSynchronize(s->d2h_stream);
+      for(int i=0;i<Shard::NRING;i++){ cudaEventDestroy(s->ring_done[i]); cudaEventDestroy(s->ring_ready[i]); }
+      cudaStreamDestroy(s->h2d_stream); cudaStreamDestroy(s->d2h_stream); }
     for(void *p : s->allocs) cudaFree(p);
     if( s->own_stream && s->stream ) cudaStreamDestroy(s->stream);
     delete s;
@@ -216,7 +224,8 @@ void Engine::eval(bool ref)
 void Engine::sync()
 {
   int prev = 0; CK(cudaGetDevice(&prev));
-  for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream)); }
+  for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream));
+    if( s->ring_init ){ CK(cudaStreamSynchronize(s->h2d_stream)); CK(cudaStreamSynchronize(s->d2h_stream)); } }
   CK(cudaSetDevice(prev));
 }
 void Engine::set_stream(void *stream)
@@ -250,6 +259,89 @@ static void d2h_gather(Shard &s, const double *src, int n, double *dst)
   rkfd_gather_kernel<<<(s.B+255)/256, 256, 0, s.stream>>>(src, s.dstage, s.B, n, s.ld);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(dst + (size_t)s.e0*n, s.dstage, (size_t)s.B*n*sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+}
+
+/* ---- asynchronous host <-> device movement (pinned host memory; the host buffers must stay valid and
+ * unmodified until sync()).  H2D copies run on their own stream into a staging ring, the transposing scatter
+ * runs on the compute stream after the copy; gathers run on the compute stream, D2H copies on a third stream:
+ * transfers of step k+1 / k-1 overlap the step kernel of step k. */
+static void ring_setup(Shard &s)
+{
+  if( s.ring_init ) return;
+  CK(cudaStreamCreateWithFlags(&s.h2d_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s.d2h_stream, cudaStreamNonBlocking));
+  for(int i=0;i<Shard::NRING;i++){
+    void *p = nullptr; CK(cudaMalloc(&p, s.nstage*sizeof(double))); s.allocs.push_back(p); s.ring[i] = (double*)p;
+    CK(cudaEventCreateWithFlags(&s.ring_done[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ring_ready[i], cudaEventDisableTiming));
+  }
+  s.ring_init = true;
+}
+static void h2d_scatter_async(Shard &s, const double *src, int n, double *dst)
+{
+  if( n <= 0 ) return;
+  ring_setup(s);
+  const int b = s.ring_next; s.ring_next = (b+1) % Shard::NRING;
+  CK(cudaStreamWaitEvent(s.h2d_stream, s.ring_done[b], 0));              /* the previous user of this buffer is done */
+  CK(cudaMemcpyAsync(s.ring[b], src + (size_t)s.e0*n, (size_t)s.B*n*sizeof(double), cudaMemcpyHostToDevice, s.h2d_stream));
+  CK(cudaEventRecord(s.ring_ready[b], s.h2d_stream));
+  CK(cudaStreamWaitEvent(s.stream, s.ring_ready[b], 0));
+  rkfd_scatter_kernel<<<(s.B+255)/256, 256, 0, s.stream>>>(s.ring[b], dst, s.B, n, s.ld);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(s.ring_done[b], s.stream));
+}
+static void d2h_gather_async(Shard &s, const double *src, int n, double *dst)
+{
+  if( n <= 0 ) return;
+  ring_setup(s);
+  const int b = s.ring_next; s.ring_next = (b+1) % Shard::NRING;
+  CK(cudaStreamWaitEvent(s.stream, s.ring_done[b], 0));
+  rkfd_gather_kernel<<<(s.B+255)/256, 256, 0, s.stream>>>(src, s.ring[b], s.B, n, s.ld);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(s.ring_ready[b], s.stream));
+  CK(cudaStreamWaitEvent(s.d2h_stream, s.ring_ready[b], 0));
+  CK(cudaMemcpyAsync(dst + (size_t)s.e0*n, s.ring[b], (size_t)s.B*n*sizeof(double), cudaMemcpyDeviceToHost, s.d2h_stream));
+  CK(cudaEventRecord(s.ring_done[b], s.d2h_stream));
+}
+void Engine::set_state_async(const double *q, const double *qd)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev));
+    if( q )  h2d_scatter_async(*s, q,  model_.nq, s->st.q[s->cur]);
+    if( qd ) h2d_scatter_async(*s, qd, model_.nq, s->st.qd[s->cur]);
+  }
+  CK(cudaSetDevice(prev));
+}
+void Engine::set_motor_input_async(const double *u)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); h2d_scatter_async(*s, u, model_.nl, s->st.u); }
+  CK(cudaSetDevice(prev));
+}
+void Engine::get_state_async(double *q, double *qd, double *qdd)
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev));
+    if( q )   d2h_gather_async(*s, s->st.q[s->cur],  model_.nq, q);
+    if( qd )  d2h_gather_async(*s, s->st.qd[s->cur], model_.nq, qd);
+    if( qdd ) d2h_gather_async(*s, s->st.qdd,        model_.nq, qdd);
+  }
+  CK(cudaSetDevice(prev));
+}
+/* makes the compute stream wait for everything queued on the copy streams (so that an event recorded on the
+ * compute stream afterwards covers the transfers) */
+void Engine::join()
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(Shard *s : shards_){
+    if( !s->ring_init ) continue;
+    CK(cudaSetDevice(s->dev));
+    CK(cudaEventRecord(s->ring_ready[0], s->h2d_stream)); CK(cudaStreamWaitEvent(s->stream, s->ring_ready[0], 0));
+    CK(cudaEventRecord(s->ring_ready[1], s->d2h_stream)); CK(cudaStreamWaitEvent(s->stream, s->ring_ready[1], 0));
+  }
+  CK(cudaSetDevice(prev));
 }
 
 void Engine::set_state(const double *q, const double *qd)

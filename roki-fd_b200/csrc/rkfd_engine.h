@@ -30,6 +30,11 @@ class Engine {
   void get_state(double *q, double *qd, double *qdd);
   void set_motor_input(const double *u);
   void set_motor_input_one(int env, int link, double value);
+  /* asynchronous variants (pinned host memory, valid until sync()); transfers overlap the step kernels */
+  void set_state_async(const double *q, const double *qd);
+  void set_motor_input_async(const double *u);
+  void get_state_async(double *q, double *qd, double *qdd);
+  void join();
   void get_pivot(int *type, double *prev_trq);
   void set_pivot(const int *type, const double *prev_trq);
   void get_contact(int *active, int *type, double *ref, double *f);

@@ -317,3 +317,30 @@ def test_rigid_short_trajectory(capi, oracle, name):
     print("rigid trajectory %s: %d/%d envs within 1e-6 (max %.2e)" % (name, (err < 1e-6).sum(), B, err.max()))
     assert (err < 1e-6).mean() >= 0.97
     fd.destroy()
+
+
+def test_async_transfers_match_synchronous(capi):
+    """rkFDBatchSet*Async / GetStateAsync (copy streams + staging ring) give the same result as the blocking calls."""
+    import torch
+    w = ch.world_c3(base_z=0.1)
+    B = 4096
+    q, qd, u = ch.sample_state(w, B, seed=3)
+    fd = gpu_world(capi, w, q, qd, u)
+    fd.update_n(3)
+    ref = fd.batch_get_state()
+    fd.destroy()
+    fd = gpu_world(capi, w, q, qd, u)
+    hq, hqd, hu = (torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (q, qd, u))
+    oq, oqd, oqdd = (torch.empty((B, w.nq), dtype=torch.float64).pin_memory() for _ in range(3))
+    for rep in range(4):          # more transfers than ring buffers in flight
+        fd.batch_set_state_async(hq.data_ptr(), hqd.data_ptr())
+        fd.batch_set_motor_input_async(hu.data_ptr())
+        fd.batch_set_contact(np.zeros((B, w.nslot), np.int32), np.zeros((B, w.nslot), np.int32), np.zeros((B, w.nslot, 3)))
+        fd.batch_set_pivot(np.zeros((B, w.nq), np.int32), np.zeros((B, w.nq)))
+        fd.batch_eval(True)
+        fd.update_n(3)
+        fd.batch_get_state_async(oq.data_ptr(), oqd.data_ptr(), oqdd.data_ptr())
+    fd.batch_sync()
+    for a, b in zip(ref, (oq.numpy(), oqd.numpy(), oqdd.numpy())):
+        assert np.array_equal(a, b)
+    fd.destroy()
