@@ -113,14 +113,97 @@ RKFD_HD S3 sym3_inverse(const S3 &d){
   return c;
 }
 
-template <class Ctx>
+/* ---- model specialisation -------------------------------------------------------------------------
+ * The generic kernel interprets the link table at run time (loop over links, switch on the joint type,
+ * scratch slots read from the table).  For the common robot-arm shape - fixed base + serial revolute links
+ * whose constant frame rotations are quarter turns about x or the identity, collision cells on the last link
+ * only, elastic pairs only - `SpecSerialRev<NL,CLS>` makes topology, joint types, rotation classes and the
+ * scratch map compile-time constants: the link loops unroll completely, every table entry becomes a
+ * constant-bank operand with an immediate offset, every scratch access an LDS/STS with an immediate offset,
+ * and the joint-type switches disappear.  Same arithmetic, same order of operations: results are bit-identical
+ * to the generic kernel.  The host picks a compiled specialisation when the model matches (spec_match). */
+struct SpecGeneric {
+  static constexpr int ID = 0, NL = 0, UNROLL = 1, NSCRATCH = 0;
+  static RKFD_HD int nl(const ModelDev &m){ return m.nl; }
+  static RKFD_HD int jtype(int, const LinkDev &L){ return L.jtype; }
+  static RKFD_HD int parent(int, const LinkDev &L){ return L.parent; }
+  static RKFD_HD int serial(int, const LinkDev &L){ return L.serial; }
+  static RKFD_HD int slot(int, const LinkDev &L){ return L.slot; }
+  static RKFD_HD int wslot(int, const LinkDev &L){ return L.wslot; }
+  static RKFD_HD int rcls(int, const LinkDev &L){ return L.rcls; }
+  static RKFD_HD int qofs(int, const LinkDev &L){ return L.qofs; }
+  static RKFD_HD int ndof(int, const LinkDev &L){ return L.ndof; }
+  static RKFD_HD int branch_slot(int, const LinkDev &L){ return L.branch_slot; }
+  static RKFD_HD int accum_slot(int, const LinkDev &L){ return L.accum_slot; }
+  static RKFD_HD int wext_slot(int, const LinkDev &L){ return L.wext_slot; }
+  static RKFD_HD int frame_slot(int, const LinkDev &L){ return L.frame_slot; }
+  static RKFD_HD int rk_slot(const ModelDev &m){ return m.rk_slot; }
+  static RKFD_HD int nq(const ModelDev &m){ return m.nq; }
+};
+/* link 0 = fixed root, links 1..NL-1 revolute and serial; CLS: 2 bits per revolute link (RoClass 1..3) */
+template <int ID_, int NL_, unsigned CLS_>
+struct SpecSerialRev {
+  static constexpr int ID = ID_, NL = NL_, UNROLL = NL_;
+  static constexpr int WEXT = 6 + 10*(NL_-1), RK = WEXT + 6, NSCRATCH = RK + 4*(NL_-1);
+  static RKFD_HD int nl(const ModelDev &){ return NL_; }
+  static RKFD_HD int jtype(int i, const LinkDev &){ return i == 0 ? J_FIXED : J_REVOL; }
+  static RKFD_HD int parent(int i, const LinkDev &){ return i - 1; }
+  static RKFD_HD int serial(int i, const LinkDev &){ return i > 0 ? 1 : 0; }
+  static RKFD_HD int slot(int i, const LinkDev &){ return i == 0 ? 0 : 6 + 10*(i-1); }
+  static RKFD_HD int wslot(int i, const LinkDev &L){ return slot(i, L); }
+  static RKFD_HD int rcls(int i, const LinkDev &){ return i == 0 ? 0 : (int)((CLS_ >> (2*(i-1))) & 3u); }
+  static RKFD_HD int qofs(int i, const LinkDev &){ return i > 0 ? i - 1 : 0; }
+  static RKFD_HD int ndof(int i, const LinkDev &){ return i > 0 ? 1 : 0; }
+  static RKFD_HD int branch_slot(int, const LinkDev &){ return -1; }
+  static RKFD_HD int accum_slot(int, const LinkDev &){ return -1; }
+  static RKFD_HD int wext_slot(int i, const LinkDev &L){ return ( i == NL_-1 && L.cell_end > L.cell_begin ) ? WEXT : -1; }
+  static RKFD_HD int frame_slot(int, const LinkDev &){ return -1; }
+  static RKFD_HD int rk_slot(const ModelDev &){ return RK; }
+  static RKFD_HD int nq(const ModelDev &){ return NL_ - 1; }
+};
+/* does the flattened model have the shape SpecSerialRev<.,NL,CLS> assumes? (host side) */
+inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
+  if( m.has_rigid || m.nl != NL || NL < 2 ) return false;
+  for(int i=0;i<NL;i++){
+    const LinkDev &L = m.link[i];
+    if( i == 0 ){ if( L.parent >= 0 || L.jtype != J_FIXED || L.cell_end > L.cell_begin ) return false; continue; }
+    if( L.jtype != J_REVOL || L.parent != i-1 || !L.serial || L.qofs != i-1 ) return false;
+    if( L.rcls == RO_GENERAL || L.rcls != (int)((CLS >> (2*(i-1))) & 3u) ) return false;
+    if( i != NL-1 && L.cell_end > L.cell_begin ) return false;
+  }
+  return true;
+}
+
+/* compiled specialisations: (id, links, rotation classes).  1: the 7-DoF arm of BASELINE.json (fixed base + 7
+ * revolute links, frames alternating Rx(-90)/Rx(+90)); 2: fixed base + 2 parallel revolute links (arm_2DoF.ztk) */
+#define RKFD_SPEC_TABLE(X) X(1, 8, 0x3BBBu) X(2, 3, 0x5u)
+template <int ID> struct SpecOf { using type = SpecGeneric; };
+#define RKFD_SPEC_X(id, nl, cls) template <> struct SpecOf<id> { using type = SpecSerialRev<id, nl, cls>; };
+RKFD_SPEC_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+/* specialisation id the model is eligible for (0: generic kernel only), and its scratch size */
+inline int spec_match(const ModelDev &m){
+#define RKFD_SPEC_X(id, nl, cls) if( spec_serial_rev_match(m, nl, cls) ) return id;
+  RKFD_SPEC_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+  return 0;
+}
+inline int spec_nscratch(int id){
+#define RKFD_SPEC_X(sid, nl, cls) if( id == sid ) return SpecSerialRev<sid, nl, cls>::NSCRATCH;
+  RKFD_SPEC_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+  return 0;
+}
+
+template <class Ctx, class Spec = SpecGeneric>
 struct Core {
   Ctx &c;
   unsigned int piv;             /* joint friction pivot: bit j = dof j kinetic */
   unsigned long long cfl;       /* contact flags: bit 2s active, bit 2s+1 kinetic */
   int bad;
+  int rk0;                      /* first slot of the integrator stage state (QS, QDS, PQ, PQD) */
 
-  RKFD_HD explicit Core(Ctx &ctx) : c(ctx), piv(0), cfl(0), bad(0) {}
+  RKFD_HD explicit Core(Ctx &ctx) : c(ctx), piv(0), cfl(0), bad(0), rk0(0) {}
 
   RKFD_HD V3 ld3(int k){ return v3(c.S(k), c.S(k+1), c.S(k+2)); }
   RKFD_HD void st3(int k, V3 v){ c.S(k)=v.x; c.S(k+1)=v.y; c.S(k+2)=v.z; }
@@ -133,14 +216,14 @@ struct Core {
 
   /* link frame w.r.t. parent and joint velocity (vJ,wJ, link frame) from the stage state and the joint data
    * cached by pass 1 ([EXT A-3]) */
-  RKFD_HD XF joint_xform(const ModelDev &m, const LinkDev &L, V3 &vJ, V3 &wJ){
-    const int sl = L.slot, qs = m.rk_slot + L.qofs, qds = m.rk_slot + m.nq + L.qofs;
-    XF x; x.fast = 0; x.cls = L.rcls; x.c = 1.0; x.s = 0.0;
+  RKFD_HD XF joint_xform(const ModelDev &m, const LinkDev &L, int i, V3 &vJ, V3 &wJ){
+    const int sl = Spec::slot(i,L), qs = rk0 + Spec::qofs(i,L), qds = rk0 + Spec::nq(m) + Spec::qofs(i,L);
+    XF x; x.fast = 0; x.cls = Spec::rcls(i,L); x.c = 1.0; x.s = 0.0;
     vJ = v3(0,0,0); wJ = v3(0,0,0);
-    switch(L.jtype){
+    switch(Spec::jtype(i,L)){
     case J_REVOL: {
       x.s = c.S(sl+6); x.c = c.S(sl+7); x.p = org_p(L);
-      if( L.rcls != RO_GENERAL ){ x.fast = 1; x.ptl = rz_tmul(x.c, x.s, v3(L.pol[0],L.pol[1],L.pol[2])); }
+      if( Spec::rcls(i,L) != RO_GENERAL ){ x.fast = 1; x.ptl = rz_tmul(x.c, x.s, v3(L.pol[0],L.pol[1],L.pol[2])); }
       else {
         const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
         x.R = from_cols(x.c*o0 + x.s*o1, x.c*o1 - x.s*o0, col2(Ro)); x.ptl = tmul(x.R, x.p);
@@ -243,42 +326,44 @@ struct Core {
   /* ---- pass 1: outward kinematics + collision + penalty */
   RKFD_HD void pass1(const ModelDev &m, bool ref){
     M3 Rw = ident3(); V3 pw = v3(0,0,0), vl = v3(0,0,0), om = v3(0,0,0), gd = v3(0,0,-GRAVITY);
-    const int qs = m.rk_slot, qds = m.rk_slot + m.nq;
-    for(int i=0;i<m.nl;i++){
-      const LinkDev &L = m.link[i]; const int sl = L.slot;
+    const int qs = rk0, qds = rk0 + Spec::nq(m);
+    const int NLc = Spec::nl(m);
+#pragma unroll (Spec::UNROLL)
+    for(int i=0;i<NLc;i++){
+      const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), qo = Spec::qofs(i,L);
       if( !Ctx::RIGID ) c.phase_sync(3);
-      if( !L.serial ){
-        if( L.parent < 0 ){ Rw = ident3(); pw = v3(0,0,0); vl = v3(0,0,0); om = v3(0,0,0); gd = v3(0,0,-GRAVITY); }
+      if( !Spec::serial(i,L) ){
+        if( Spec::parent(i,L) < 0 ){ Rw = ident3(); pw = v3(0,0,0); vl = v3(0,0,0); om = v3(0,0,0); gd = v3(0,0,-GRAVITY); }
         else {
           const LinkDev &P = m.link[L.parent];
           om = ld3(P.wslot); gd = ld3(P.wslot+3);
           if( m.need_world ){ Rw = ldm(P.branch_slot); pw = ld3(P.branch_slot+9); vl = ld3(P.branch_slot+12); }
         }
       }
-      XF x; x.fast = 0; x.cls = L.rcls; x.c = 1.0; x.s = 0.0;
+      XF x; x.fast = 0; x.cls = Spec::rcls(i,L); x.c = 1.0; x.s = 0.0;
       V3 vJ = v3(0,0,0), wJ = v3(0,0,0);
-      switch(L.jtype){
+      switch(Spec::jtype(i,L)){
       case J_REVOL: {
-        double sn, co; sincos(c.S(qs+L.qofs), &sn, &co);
+        double sn, co; sincos(c.S(qs+qo), &sn, &co);
         c.S(sl+6) = sn; c.S(sl+7) = co;
         x.s = sn; x.c = co; x.p = org_p(L);
-        if( L.rcls != RO_GENERAL ) x.fast = 1;
+        if( Spec::rcls(i,L) != RO_GENERAL ) x.fast = 1;
         else { const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
           x.R = from_cols(co*o0 + sn*o1, co*o1 - sn*o0, col2(Ro)); }
-        wJ.z = c.S(qds+L.qofs);
+        wJ.z = c.S(qds+qo);
       } break;
-      case J_PRISM: x.R = org_R(L); x.p = org_p(L) + c.S(qs+L.qofs)*col2(x.R); vJ.z = c.S(qds+L.qofs); break;
+      case J_PRISM: x.R = org_R(L); x.p = org_p(L) + c.S(qs+qo)*col2(x.R); vJ.z = c.S(qds+qo); break;
       case J_SPHER: {
         const M3 Ro = org_R(L);
-        x.R = mm(Ro, aa_to_mat(ld3(qs+L.qofs))); x.p = org_p(L);
+        x.R = mm(Ro, aa_to_mat(ld3(qs+qo))); x.p = org_p(L);
         stm(sl+27, x.R);
-        wJ = tmul(x.R, mul(Ro, ld3(qds+L.qofs)));
+        wJ = tmul(x.R, mul(Ro, ld3(qds+qo)));
       } break;
       case J_FLOAT: {
         const M3 Ro = org_R(L);
-        x.R = mm(Ro, aa_to_mat(ld3(qs+L.qofs+3))); x.p = org_p(L) + mul(Ro, ld3(qs+L.qofs));
+        x.R = mm(Ro, aa_to_mat(ld3(qs+qo+3))); x.p = org_p(L) + mul(Ro, ld3(qs+qo));
         stm(sl+6, x.R); st3(sl+15, x.p);
-        vJ = tmul(x.R, mul(Ro, ld3(qds+L.qofs))); wJ = tmul(x.R, mul(Ro, ld3(qds+L.qofs+3)));
+        vJ = tmul(x.R, mul(Ro, ld3(qds+qo))); wJ = tmul(x.R, mul(Ro, ld3(qds+qo+3)));
       } break;
       default: x.R = org_R(L); x.p = org_p(L); break;
       }
@@ -289,21 +374,22 @@ struct Core {
         pw = pw + mul(Rw, x.p); Rw = xf_world(x, Rw); vl = vl_n;
       }
       om = om_n; gd = gd_n;
-      st3(L.wslot, om); st3(L.wslot+3, gd);
-      if( L.wext_slot >= 0 ){
+      st3(Spec::wslot(i,L), om); st3(Spec::wslot(i,L)+3, gd);
+      const int wx = Spec::wext_slot(i,L), fs = Spec::frame_slot(i,L), bs = Spec::branch_slot(i,L);
+      if( wx >= 0 ){
         const V6 w = contacts(m, L, Rw, pw, vl, om, ref);
-        st3(L.wext_slot, w.l); st3(L.wext_slot+3, w.a);
-        if( L.frame_slot >= 0 ){ stm(L.frame_slot, Rw); st3(L.frame_slot+9, pw); st3(L.frame_slot+12, vl); st3(L.frame_slot+15, om); }
+        st3(wx, w.l); st3(wx+3, w.a);
+        if( fs >= 0 ){ stm(fs, Rw); st3(fs+9, pw); st3(fs+12, vl); st3(fs+15, om); }
       }
-      if( L.branch_slot >= 0 && m.need_world ){ stm(L.branch_slot, Rw); st3(L.branch_slot+9, pw); st3(L.branch_slot+12, vl); }
+      if( bs >= 0 && m.need_world ){ stm(bs, Rw); st3(bs+9, pw); st3(bs+12, vl); }
     }
   }
 
   /* motor + joint friction of a 1-DoF joint: returns tau = driving torque + friction, jm = rotor inertia
    * (rkfd_util.c:330-364, [EXT A-6, A-7]); at the reference stage commits pivot type and prev_trq */
   RKFD_HD double joint_torque(const ModelDev &m, const LinkDev &L, int i, bool ref, double &jm, double u_in, double prev_in){
-    const int j = L.qofs; (void)i;
-    const double v = c.S(m.rk_slot + m.nq + j);
+    const int j = Spec::qofs(i,L);
+    const double v = c.S(rk0 + Spec::nq(m) + j);
     double tdrive = 0.0, tf = 0.0; jm = 0.0;
     if( L.mtype != M_NONE ){
       double e = u_in;
@@ -316,7 +402,7 @@ struct Core {
         if( !(piv & (1u<<j)) ) fmax = L.sfriction;
         else {
           const double sg = v > 0 ? 1.0 : ( v < 0 ? -1.0 : 0.0 );
-          fmax = -L.stiffness*c.S(m.rk_slot + j) - L.viscosity*v - L.coulomb*sg;
+          fmax = -L.stiffness*c.S(rk0 + j) - L.viscosity*v - L.coulomb*sg;
         }
         fmax = fabs(fmax);
         if( fabs(tf) > fmax ){ tf = tf > 0 ? fmax : -fmax; if( ref ) piv |= (1u<<j); }
@@ -331,17 +417,20 @@ struct Core {
   RKFD_HD void pass2(const ModelDev &m, bool ref){
     S3 kA, kC; M3 kB; V3 kf, kn;          /* contribution carried to link i from its serial child */
     kA.xx=kA.xy=kA.xz=kA.yy=kA.yz=kA.zz=0; kC = kA; kB.xx=kB.xy=kB.xz=kB.yx=kB.yy=kB.yz=kB.zx=kB.zy=kB.zz=0; kf = v3(0,0,0); kn = kf;
-    for(int i=0;i<m.nl;i++) if( m.link[i].accum_slot >= 0 ) for(int k=0;k<ACCUM_SLOTS;k++) c.S(m.link[i].accum_slot+k) = 0.0;
+    const int NLc = Spec::nl(m);
+#pragma unroll (Spec::UNROLL)
+    for(int i=0;i<NLc;i++) if( Spec::accum_slot(i,m.link[i]) >= 0 ) for(int k=0;k<ACCUM_SLOTS;k++) c.S(m.link[i].accum_slot+k) = 0.0;
     /* motor input and previous driving torque of the NEXT link to be processed are requested one iteration
      * ahead, so that their HBM/L2 latency overlaps the articulated-inertia arithmetic of the current link */
     double nx_u = 0.0, nx_prev = 0.0;
-    if( m.nl > 0 && m.link[m.nl-1].mtype != M_NONE ){ nx_u = c.gld(c.st.u, m.nl-1); nx_prev = c.gld(c.st.piv_prev, m.link[m.nl-1].qofs); }
-    for(int i=m.nl-1;i>=0;i--){
-      const LinkDev &L = m.link[i]; const int sl = L.slot;
+    if( NLc > 0 && m.link[NLc-1].mtype != M_NONE ){ nx_u = c.gld(c.st.u, NLc-1); nx_prev = c.gld(c.st.piv_prev, Spec::qofs(NLc-1, m.link[NLc-1])); }
+#pragma unroll (Spec::UNROLL)
+    for(int i=NLc-1;i>=0;i--){
+      const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L);
       if( !Ctx::RIGID ) c.phase_sync(3);
       const double pf_u = nx_u, pf_prev = nx_prev;
-      if( i > 0 && m.link[i-1].mtype != M_NONE ){ nx_u = c.gld(c.st.u, i-1); nx_prev = c.gld(c.st.piv_prev, m.link[i-1].qofs); }
-      const V3 om = ld3(L.wslot), gd = ld3(L.wslot+3);
+      if( i > 0 && m.link[i-1].mtype != M_NONE ){ nx_u = c.gld(c.st.u, i-1); nx_prev = c.gld(c.st.piv_prev, Spec::qofs(i-1, m.link[i-1])); }
+      const V3 om = ld3(Spec::wslot(i,L)), gd = ld3(Spec::wslot(i,L)+3);
       const V3 mc = v3(L.mc[0],L.mc[1],L.mc[2]);
       S3 A, C; M3 B;
       A.xx = L.mass; A.xy = 0; A.xz = 0; A.yy = L.mass; A.yz = 0; A.zz = L.mass;
@@ -350,32 +439,32 @@ struct Core {
       /* bias ( w x (w x mc) ; w x (Io w) ) minus gravity (m gd ; mc x gd) minus external wrench */
       V3 pf = cross(om, cross(om, mc)) - L.mass*gd;
       V3 pn = cross(om, mul(C, om)) - cross(mc, gd);
-      if( L.wext_slot >= 0 ){ pf = pf - ld3(L.wext_slot); pn = pn - ld3(L.wext_slot+3); }
-      if( L.accum_slot >= 0 ){
+      if( Spec::wext_slot(i,L) >= 0 ){ pf = pf - ld3(Spec::wext_slot(i,L)); pn = pn - ld3(Spec::wext_slot(i,L)+3); }
+      if( Spec::accum_slot(i,L) >= 0 ){
         const int a = L.accum_slot; const S3 aA = lds(a), aC = lds(a+15); const M3 aB = ldm(a+6);
         A.xx+=aA.xx; A.xy+=aA.xy; A.xz+=aA.xz; A.yy+=aA.yy; A.yz+=aA.yz; A.zz+=aA.zz;
         C.xx+=aC.xx; C.xy+=aC.xy; C.xz+=aC.xz; C.yy+=aC.yy; C.yz+=aC.yz; C.zz+=aC.zz;
         B.xx+=aB.xx; B.xy+=aB.xy; B.xz+=aB.xz; B.yx+=aB.yx; B.yy+=aB.yy; B.yz+=aB.yz; B.zx+=aB.zx; B.zy+=aB.zy; B.zz+=aB.zz;
         pf = pf + ld3(a+21); pn = pn + ld3(a+24);
       }
-      if( i+1 < m.nl && m.link[i+1].serial ){
+      if( i+1 < NLc && Spec::serial(i+1, m.link[i+1]) ){
         A.xx+=kA.xx; A.xy+=kA.xy; A.xz+=kA.xz; A.yy+=kA.yy; A.yz+=kA.yz; A.zz+=kA.zz;
         C.xx+=kC.xx; C.xy+=kC.xy; C.xz+=kC.xz; C.yy+=kC.yy; C.yz+=kC.yz; C.zz+=kC.zz;
         B.xx+=kB.xx; B.xy+=kB.xy; B.xz+=kB.xz; B.yx+=kB.yx; B.yy+=kB.yy; B.yz+=kB.yz; B.zx+=kB.zx; B.zy+=kB.zy; B.zz+=kB.zz;
         pf = pf + kf; pn = pn + kn;
       }
       V3 vJ, wJ;
-      const XF x = joint_xform(m, L, vJ, wJ);
+      const XF x = joint_xform(m, L, i, vJ, wJ);
       /* velocity-product acceleration (link frame): parent angular velocity in link axes = om - wJ */
       const V3 omp = om - wJ;
       const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
       const V3 za = cross(omp, wJ);
       /* p' = pA + IA zeta */
-      if( L.jtype != J_FLOAT ){
+      if( Spec::jtype(i,L) != J_FLOAT ){
         pf = pf + mul(A, zl) + mul(B, za);
         pn = pn + tmul(B, zl) + mul(C, za);
       }
-      switch(L.jtype){
+      switch(Spec::jtype(i,L)){
       case J_REVOL: {
         double jm; const double tau = joint_torque(m, L, i, ref, jm, pf_u, pf_prev);
         const V3 Ul = col2(B), Ua = v3(C.xz, C.yz, C.zz);
@@ -439,7 +528,7 @@ struct Core {
       } break;
       default: break;
       }
-      if( L.parent < 0 || L.jtype == J_FLOAT ) continue;
+      if( Spec::parent(i,L) < 0 || Spec::jtype(i,L) == J_FLOAT ) continue;
       /* X^T Ia X and X^T pa into the parent frame */
       const V3 p = x.p;
       const S3 Ar = xf_sym(x, A), Cr = xf_sym(x, C); const M3 Br = xf_gen(x, B);
@@ -450,7 +539,7 @@ struct Core {
       Cp.xx = Cr.xx + Z1.xx + Z2.xx; Cp.xy = Cr.xy + Z1.xy + Z2.yx; Cp.xz = Cr.xz + Z1.xz + Z2.zx;
       Cp.yy = Cr.yy + Z1.yy + Z2.yy; Cp.yz = Cr.yz + Z1.yz + Z2.zy; Cp.zz = Cr.zz + Z1.zz + Z2.zz;
       const V3 fp = xf_mul(x, pf); const V3 np = xf_mul(x, pn) + cross(p, fp);
-      if( L.serial ){ kA = Ar; kB = Bp; kC = Cp; kf = fp; kn = np; }
+      if( Spec::serial(i,L) ){ kA = Ar; kB = Bp; kC = Cp; kf = fp; kn = np; }
       else {
         const int a = m.link[L.parent].accum_slot;
         c.S(a)+=Ar.xx; c.S(a+1)+=Ar.xy; c.S(a+2)+=Ar.xz; c.S(a+3)+=Ar.yy; c.S(a+4)+=Ar.yz; c.S(a+5)+=Ar.zz;
@@ -506,7 +595,7 @@ struct Core {
   }
   /* one dof: displacement uses the stage velocity as slope, velocity uses the acceleration */
   RKFD_HD void rk_dof(const ModelDev &m, const RK &k, int stage, int j, double acc){
-    const int qs = m.rk_slot + j, qds = m.rk_slot + m.nq + j, pq = m.rk_slot + 2*m.nq + j, pqd = m.rk_slot + 3*m.nq + j;
+    const int qs = rk0 + j, qds = rk0 + m.nq + j, pq = rk0 + 2*m.nq + j, pqd = rk0 + 3*m.nq + j;
     if( stage == ST_PROBE ) return;
     if( stage >= ST_REF ){ c.gst(c.st.qdd, j, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; return; }
     const double vel = c.S(qds);
@@ -521,39 +610,41 @@ struct Core {
     /* running combination (and, at stage 2, the committed state) of the next 1-DoF joint are requested one link ahead */
     double nxq[4] = {0,0,0,0};
     const bool pfF = stage >= ST_K2 && stage <= ST_K4, pfX = stage == ST_K2;
-    for(int i=0;i<m.nl;i++){
-      const LinkDev &L = m.link[i]; const int sl = L.slot;
+    const int NLc = Spec::nl(m), NQc = Spec::nq(m);
+#pragma unroll (Spec::UNROLL)
+    for(int i=0;i<NLc;i++){
+      const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), qo = Spec::qofs(i,L);
       if( !Ctx::RIGID ) c.phase_sync(3);
-      if( i == 0 && L.ndof == 1 ){
-        if( pfF ){ nxq[0] = c.gld(c.st.q[c.cur^1], L.qofs); nxq[1] = c.gld(c.st.qd[c.cur^1], L.qofs); }
-        if( pfX ){ nxq[2] = c.gld(c.st.q[c.cur], L.qofs); nxq[3] = c.gld(c.st.qd[c.cur], L.qofs); }
+      if( i == 0 && Spec::ndof(i,L) == 1 ){
+        if( pfF ){ nxq[0] = c.gld(c.st.q[c.cur^1], qo); nxq[1] = c.gld(c.st.qd[c.cur^1], qo); }
+        if( pfX ){ nxq[2] = c.gld(c.st.q[c.cur], qo); nxq[3] = c.gld(c.st.qd[c.cur], qo); }
       }
       const double pfq[4] = { nxq[0], nxq[1], nxq[2], nxq[3] };
-      if( i+1 < m.nl && m.link[i+1].ndof == 1 ){
-        const int jn = m.link[i+1].qofs;
+      if( i+1 < NLc && Spec::ndof(i+1, m.link[i+1]) == 1 ){
+        const int jn = Spec::qofs(i+1, m.link[i+1]);
         if( pfF ){ nxq[0] = c.gld(c.st.q[c.cur^1], jn); nxq[1] = c.gld(c.st.qd[c.cur^1], jn); }
         if( pfX ){ nxq[2] = c.gld(c.st.q[c.cur], jn); nxq[3] = c.gld(c.st.qd[c.cur], jn); }
       }
-      if( !L.serial ){
-        if( L.parent < 0 ){ al = v3(0,0,0); aa = v3(0,0,0); om = v3(0,0,0); }
+      if( !Spec::serial(i,L) ){
+        if( Spec::parent(i,L) < 0 ){ al = v3(0,0,0); aa = v3(0,0,0); om = v3(0,0,0); }
         else { const int b = m.link[L.parent].branch_slot; al = ld3(b); aa = ld3(b+3); om = ld3(b+6); }
       }
       V3 vJ, wJ;
-      const XF x = joint_xform(m, L, vJ, wJ);
+      const XF x = joint_xform(m, L, i, vJ, wJ);
       const V3 omp = xf_tmul(x, om);
       const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
       const V3 za = cross(omp, wJ);
       const V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
-      switch(L.jtype){
+      switch(Spec::jtype(i,L)){
       case J_REVOL: case J_PRISM: {
         const V3 Ul = ld3(sl), Ua = ld3(sl+3);
         const double acc = c.S(sl+8)*( c.S(sl+9) - (dot(Ul,xl) + dot(Ua,xa)) );
         al = xl + zl; aa = xa + za;
-        if( L.jtype == J_REVOL ) aa.z += acc; else al.z += acc;
+        if( Spec::jtype(i,L) == J_REVOL ) aa.z += acc; else al.z += acc;
         if( stage == ST_PROBE ){}
-        else if( stage >= ST_REF ){ c.gst(c.st.qdd, L.qofs, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; }
+        else if( stage >= ST_REF ){ c.gst(c.st.qdd, qo, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; }
         else {
-          const int j = L.qofs, qs = m.rk_slot + j, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
+          const int j = qo, qs = rk0 + j, qds = qs + NQc, pq = qs + 2*NQc, pqd = qs + 3*NQc;
           const double vel = c.S(qds);
           rk_lin_pf(k, stage, qs,  pq,  c.st.q[c.cur^1],  j, vel, pfq[0], pfq[2]);
           rk_lin_pf(k, stage, qds, pqd, c.st.qd[c.cur^1], j, acc, pfq[1], pfq[3]);
@@ -569,7 +660,7 @@ struct Core {
         else if( stage >= ST_REF ){ c.gst(c.st.qdd,L.qofs,acc.x); c.gst(c.st.qdd,L.qofs+1,acc.y); c.gst(c.st.qdd,L.qofs+2,acc.z);
           if( !(fabs(acc.x)+fabs(acc.y)+fabs(acc.z) < 1.0e300) ) bad = 1; }
         else {
-          const int qs = m.rk_slot + L.qofs, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
+          const int qs = rk0 + L.qofs, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
           const V3 w = ld3(qds);
           rk_rot(m, k, stage, qs, pq, c.st.q[c.cur], c.st.q[c.cur^1], L.qofs, w);
           rk_lin(m, k, stage, qds,   pqd,   c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs,   acc.x);
@@ -588,7 +679,7 @@ struct Core {
           c.gst(c.st.qdd,L.qofs+3,acca.x); c.gst(c.st.qdd,L.qofs+4,acca.y); c.gst(c.st.qdd,L.qofs+5,acca.z);
           if( !(fabs(accl.x)+fabs(accl.y)+fabs(accl.z)+fabs(acca.x)+fabs(acca.y)+fabs(acca.z) < 1.0e300) ) bad = 1;
         } else {
-          const int qs = m.rk_slot + L.qofs, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
+          const int qs = rk0 + L.qofs, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
           const V3 v = ld3(qds), w = ld3(qds+3);
           rk_lin(m, k, stage, qs,   pq,   c.st.q[c.cur], c.st.q[c.cur^1], L.qofs,   v.x);
           rk_lin(m, k, stage, qs+1, pq+1, c.st.q[c.cur], c.st.q[c.cur^1], L.qofs+1, v.y);
@@ -605,8 +696,8 @@ struct Core {
       default: al = xl + zl; aa = xa + za; break;
       }
       om = omp + wJ;
-      if( L.frame_slot >= 0 ){ st3(L.frame_slot+18, al); st3(L.frame_slot+21, aa); }
-      if( L.branch_slot >= 0 ){ st3(L.branch_slot, al); st3(L.branch_slot+3, aa); st3(L.branch_slot+6, om); }
+      if( Spec::frame_slot(i,L) >= 0 ){ st3(L.frame_slot+18, al); st3(L.frame_slot+21, aa); }
+      if( Spec::branch_slot(i,L) >= 0 ){ st3(L.branch_slot, al); st3(L.branch_slot+3, aa); st3(L.branch_slot+6, om); }
     }
   }
 
@@ -659,7 +750,7 @@ struct Core {
       default: break;
       }
       if( L.parent < 0 || L.jtype == J_FLOAT ) break;
-      V3 vJ, wJ; const XF x = joint_xform(m, L, vJ, wJ);
+      V3 vJ, wJ; const XF x = joint_xform(m, L, i, vJ, wJ);
       dpf = xf_mul(x, paf); dpn = xf_mul(x, pan) + cross(x.p, dpf);
       i = L.parent;
     }
@@ -667,7 +758,7 @@ struct Core {
       const LinkDev &L = m.link[i]; const int sl = L.slot;
       V3 al = v3(0,0,0), aa = v3(0,0,0);
       if( L.parent >= 0 ){ al = w3(da0+6*L.parent); aa = w3(da0+6*L.parent+3); }
-      V3 vJ, wJ; const XF x = joint_xform(m, L, vJ, wJ);
+      V3 vJ, wJ; const XF x = joint_xform(m, L, i, vJ, wJ);
       V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
       switch(L.jtype){
       case J_REVOL: case J_PRISM: {
@@ -1023,7 +1114,9 @@ struct Core {
   RKFD_HD void store_flags(){ c.st.piv_type[c.e] = piv; c.st.cflags[c.e] = cfl; if( bad ) c.st.status[c.e] |= 1; }
   /* committed state (buffer `cur`) -> stage state */
   RKFD_HD void load_stage_state(const ModelDev &m){
-    for(int j=0;j<m.nq;j++){ c.S(m.rk_slot+j) = c.gld(c.st.q[c.cur], j); c.S(m.rk_slot+m.nq+j) = c.gld(c.st.qd[c.cur], j); }
+    const int NQc = Spec::nq(m);
+#pragma unroll (Spec::UNROLL)
+    for(int j=0;j<NQc;j++){ c.S(rk0+j) = c.gld(c.st.q[c.cur], j); c.S(rk0+NQc+j) = c.gld(c.st.qd[c.cur], j); }
   }
   RKFD_HD void evaluate(const ModelDev &m, int stage){
     const bool ref = (stage == ST_REF) || (stage == ST_EVAL_REF);
@@ -1048,6 +1141,7 @@ struct Core {
    * committing evaluation on the committed state (2 = rkFDUpdateInit's t=0 evaluation).  One stage loop so
    * that the evaluation body is instantiated once. */
   RKFD_HD void run(const ModelDev &m, int mode, int nsteps){
+    rk0 = Spec::rk_slot(m);
     load_flags();
     const int first = mode == 0 ? ST_K1 : ( mode == 2 ? ST_EVAL_REF : ST_EVAL );
     const int last  = mode == 0 ? ST_REF : first;

@@ -97,7 +97,6 @@ struct Shard {
 };
 
 static int g_next_engine_id = 1;
-static int g_model_owner[64][16] = {{0}};   /* [device][variant]: engine whose model sits in that constant bank */
 static int variant_index(const KernelVariant *kv);
 
 template <class T> static T *dalloc(Shard &s, size_t n)
@@ -107,16 +106,20 @@ template <class T> static T *dalloc(Shard &s, size_t n)
   s.allocs.push_back(p); return (T*)p;
 }
 
-/* kernel variants, one translation unit each (rkfd_kernel_variant.cu) */
-#define RKFD_DECL(B,G,R) extern const KernelVariant rkfd_variant_##B##_##G##_##R;
-RKFD_DECL(256,0,0) RKFD_DECL(128,0,0) RKFD_DECL(64,0,0) RKFD_DECL(32,0,0) RKFD_DECL(64,1,0)
-RKFD_DECL(256,0,1) RKFD_DECL(128,0,1) RKFD_DECL(64,0,1) RKFD_DECL(32,0,1) RKFD_DECL(64,1,1)
-constexpr int NVARIANTS = 10;
+/* kernel variants, one translation unit each (rkfd_kernel_variant.cu): BLOCK_GSCR_RIGID_SPEC */
+#define RKFD_DECL(B,G,R,S) extern const KernelVariant rkfd_variant_##B##_##G##_##R##_##S;
+RKFD_DECL(128,0,0,1) RKFD_DECL(256,0,0,1) RKFD_DECL(64,0,0,1) RKFD_DECL(128,0,0,2)
+RKFD_DECL(256,0,0,0) RKFD_DECL(128,0,0,0) RKFD_DECL(64,0,0,0) RKFD_DECL(32,0,0,0) RKFD_DECL(64,1,0,0)
+RKFD_DECL(256,0,1,0) RKFD_DECL(128,0,1,0) RKFD_DECL(64,0,1,0) RKFD_DECL(32,0,1,0) RKFD_DECL(64,1,1,0)
+constexpr int NVARIANTS = 14;
 /* order = preference among variants that keep the same number of environments resident (measured on B200,
- * profiles/r01_sync_sweep.md: 128-thread blocks with per-pass barriers are the best compromise) */
+ * profiles/r01_sync_sweep.md: 128-thread blocks with per-pass barriers are the best compromise); model
+ * specialisations (spec > 0) come first and are taken whenever the model matches */
 static const KernelVariant *g_variants[NVARIANTS] = {
-  &rkfd_variant_128_0_0, &rkfd_variant_256_0_0, &rkfd_variant_64_0_0, &rkfd_variant_32_0_0, &rkfd_variant_64_1_0,
-  &rkfd_variant_128_0_1, &rkfd_variant_256_0_1, &rkfd_variant_64_0_1, &rkfd_variant_32_0_1, &rkfd_variant_64_1_1 };
+  &rkfd_variant_128_0_0_1, &rkfd_variant_256_0_0_1, &rkfd_variant_64_0_0_1, &rkfd_variant_128_0_0_2,
+  &rkfd_variant_128_0_0_0, &rkfd_variant_256_0_0_0, &rkfd_variant_64_0_0_0, &rkfd_variant_32_0_0_0, &rkfd_variant_64_1_0_0,
+  &rkfd_variant_128_0_1_0, &rkfd_variant_256_0_1_0, &rkfd_variant_64_0_1_0, &rkfd_variant_32_0_1_0, &rkfd_variant_64_1_1_0 };
+static int g_model_owner[64][NVARIANTS] = {{0}};   /* [device][variant]: engine whose model sits in that constant bank */
 
 static int variant_index(const KernelVariant *kv){ for(int i=0;i<NVARIANTS;i++) if( g_variants[i] == kv ) return i; return 0; }
 
@@ -154,11 +157,17 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     /* launch configuration: the block size that keeps most environments resident per SM; scratch in HBM
      * (gscr) only when no shared-memory variant fits */
     int best = 0; const bool rigid = model.has_rigid && model.solver != S_VOLUME;
-    for(int pass=0; pass<2 && best==0; pass++)
+    /* model specialisation (RKFD_SPEC=0 forces the generic kernel: tuning / comparison aid) */
+    int spec = spec_match(model);
+    if( const char *fs = std::getenv("RKFD_SPEC") ) if( std::atoi(fs) == 0 ) spec = 0;
+    for(int pass=0; pass<3 && best==0; pass++)
       for(const KernelVariant *kv : g_variants){
-        if( kv->rigid != rigid || kv->gscr != (pass == 1) ) continue;
+        /* pass 0: the matching specialisation; 1: generic, shared-memory scratch; 2: generic, scratch in HBM */
+        if( kv->rigid != rigid || kv->gscr != (pass == 2) || kv->spec != (pass == 0 ? spec : 0) ) continue;
+        if( pass == 0 && spec == 0 ) continue;
         if( const char *fb = std::getenv("RKFD_FORCE_BLOCK") ) if( std::atoi(fb) != kv->block ) continue;   /* tuning aid */
-        const size_t smem = kv->gscr ? 0 : (size_t)model.nscratch*kv->block*sizeof(double);
+        const int nscr = kv->spec ? spec_nscratch(kv->spec) : model.nscratch;
+        const size_t smem = kv->gscr ? 0 : (size_t)nscr*kv->block*sizeof(double);
         if( smem > 227*1024 ) continue;
         const int nb = kv->blocks_per_sm(smem);
         if( nb*kv->block > best ){ best = nb*kv->block; s->kv = kv; s->smem = smem; }

@@ -1,4 +1,4 @@
-/* rkfd_kernel.cuh - the fused step kernel template and its device context.  Each (BLOCK, GSCR, RIGID)
+/* rkfd_kernel.cuh - the fused step kernel template and its device context.  Each (BLOCK, GSCR, RIGID, SPEC)
  * variant is compiled in its own translation unit (rkfd_kernel_variant.cu with -D flags) so that the
  * variants build in parallel and the penalty-only kernels carry no rigid-solver code. */
 #ifndef RKFD_KERNEL_CUH
@@ -49,20 +49,20 @@ struct DevCtx {
 };
 
 /* mode 0: nsteps x rkFDUpdate; 1: one non-committing evaluation; 2: one committing evaluation */
-template <int BLOCK, bool GSCR, bool RIGID>
+template <int BLOCK, bool GSCR, bool RIGID, int SPEC>
 __global__ void __launch_bounds__(BLOCK) rkfd_step_kernel(StateDev st, int cur, int mode, int nsteps)
 {
   const int e = blockIdx.x*BLOCK + threadIdx.x;
   if( e >= st.ld ) return;            /* whole warps only: the padding environments [B, ld) hold a valid zero state */
   DevCtx<BLOCK,GSCR,RIGID> ctx; ctx.st = st; ctx.e = ctx.e0 = e; ctx.cur = cur; ctx.tid = ctx.tid0 = threadIdx.x; ctx.wsd = c_model.ws_doubles;
-  Core<DevCtx<BLOCK,GSCR,RIGID>> core(ctx);
+  Core<DevCtx<BLOCK,GSCR,RIGID>, typename SpecOf<SPEC>::type> core(ctx);
   core.run(c_model, mode, nsteps);
 }
 
 
 /* one compiled variant: launch + occupancy query */
 struct KernelVariant {
-  int block; bool gscr, rigid;
+  int block; bool gscr, rigid; int spec;     /* spec: model specialisation id (rkfd_core.cuh), 0 = generic */
   void (*launch)(const StateDev &st, int cur, int mode, int nsteps, int grid, size_t smem, cudaStream_t stream);
   int (*blocks_per_sm)(size_t smem);      /* sets the dynamic shared memory attribute; <0 on error */
   int (*upload)(const ModelDev *m, cudaStream_t stream);   /* model table -> this variant's constant bank */

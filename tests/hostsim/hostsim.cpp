@@ -38,7 +38,7 @@ struct HostCtx {
 
 struct HostSim {
   ModelDev model; WorldHost world; std::vector<ChainHost*> chains; std::string err;
-  int B = 0, cur = 0; StateDev st; std::vector<void*> allocs; std::vector<double> last_ws;
+  int B = 0, cur = 0, spec = 0; StateDev st; std::vector<void*> allocs; std::vector<double> last_ws;
 };
 
 template <class T> static T *halloc(HostSim *h, size_t n){ void *p = std::calloc(n ? n : 1, sizeof(T)); h->allocs.push_back(p); return (T*)p; }
@@ -91,6 +91,9 @@ int hostsim_finalize(HostSim *h, int B)
 const char *hostsim_error(HostSim *h){ return h->err.c_str(); }
 int hostsim_nq(HostSim *h){ return h->model.nq; }
 int hostsim_nl(HostSim *h){ return h->model.nl; }
+/* model specialisation the kernel would pick (0: generic); hostsim_use_spec makes hostsim_run use it */
+int hostsim_spec_match(HostSim *h){ return spec_match(h->model); }
+void hostsim_use_spec(HostSim *h, int on){ h->spec = on ? spec_match(h->model) : 0; }
 int hostsim_nslot(HostSim *h){ return h->model.nslot; }
 int hostsim_nscratch(HostSim *h){ return h->model.nscratch; }
 void hostsim_free(HostSim *h){ for(void *p : h->allocs) std::free(p); for(auto *c : h->chains) delete c; delete h; }
@@ -126,9 +129,14 @@ void hostsim_get_pivot(HostSim *h, int *type, double *prev)
 void hostsim_run(HostSim *h, int mode, int nsteps)
 {
   for(int e=0;e<h->B;e++){
-    HostCtx ctx; ctx.st = h->st; ctx.e = e; ctx.cur = h->cur; ctx.scr.assign(h->model.nscratch + 1, 0.0); ctx.wsp.assign(h->model.ws_doubles + 1, 0.0);
-    Core<HostCtx> core(ctx);
-    core.run(h->model, mode, nsteps);
+    HostCtx ctx; ctx.st = h->st; ctx.e = e; ctx.cur = h->cur; ctx.wsp.assign(h->model.ws_doubles + 1, 0.0);
+    ctx.scr.assign((h->spec ? spec_nscratch(h->spec) : h->model.nscratch) + 1, 0.0);
+    switch(h->spec){
+#define RKFD_SPEC_X(id, nl, cls) case id: { Core<HostCtx, SpecOf<id>::type> core(ctx); core.run(h->model, mode, nsteps); } break;
+    RKFD_SPEC_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+    default: { Core<HostCtx> core(ctx); core.run(h->model, mode, nsteps); } break;
+    }
     h->last_ws = ctx.wsp;
   }
   if( mode == 0 && (nsteps & 1) ) h->cur ^= 1;

@@ -34,7 +34,8 @@ def lib():
         L.hostsim_finalize.argtypes = [C.c_void_p, C.c_int]
         L.hostsim_error.restype = C.c_char_p
         L.hostsim_error.argtypes = [C.c_void_p]
-        for f in ("hostsim_nq", "hostsim_nl", "hostsim_nslot", "hostsim_nscratch", "hostsim_free"):
+        L.hostsim_use_spec.argtypes = [C.c_void_p, C.c_int]
+        for f in ("hostsim_nq", "hostsim_nl", "hostsim_nslot", "hostsim_nscratch", "hostsim_free", "hostsim_spec_match"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.hostsim_set_state.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.hostsim_get_state.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -51,7 +52,7 @@ def _d(a):
 
 
 class HostSim:
-    def __init__(self, world, B):
+    def __init__(self, world, B, spec=False):
         L = lib()
         links, nls = [], []
         for ch in world.chains:          # all chains (static ones included), chain-local parents
@@ -76,6 +77,10 @@ class HostSim:
             raise RuntimeError(L.hostsim_error(self.h).decode())
         self.B, self.nq, self.nl, self.nslot = B, L.hostsim_nq(self.h), L.hostsim_nl(self.h), L.hostsim_nslot(self.h)
         self.nscratch = L.hostsim_nscratch(self.h)
+        self.spec = L.hostsim_spec_match(self.h)      # model specialisation the kernel would pick (0: generic)
+        if spec:
+            assert self.spec > 0, "model matches no compiled specialisation"
+            L.hostsim_use_spec(self.h, 1)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -197,3 +197,36 @@ def test_rigid_steps_match_oracle(oracle, name):
     for b in range(B):
         ok += relerr(hq[b, :w.nq], ref[b][0][0]) < 1e-7
     assert ok >= (B - 1 if name not in STATISTICAL else B // 2), ok
+
+
+SPEC_WORLDS = {
+    "c2_arm7": (lambda: ch.world_c2(), 1),
+    "c3_arm7_penalty": (lambda: ch.world_c3(base_z=0.1), 1),
+    "c1_serial_arm2dof": (lambda: ch.world_c1_serial(), 2),
+}
+
+
+@pytest.mark.parametrize("name", list(SPEC_WORLDS))
+def test_specialised_core_is_bit_identical(name):
+    """The compile-time model specialisation (SpecSerialRev) is the same arithmetic in the same order as the
+    generic table-driven core: states, accelerations, contact and pivot state must be bit-identical."""
+    mk, spec_id = SPEC_WORLDS[name]
+    w = mk()
+    B, nsteps = 16, 30
+    q, qd, u = ch.sample_state(w, B, seed=13)
+    out = []
+    for spec in (False, True):
+        hs = HostSim(w, B, spec=spec)
+        assert hs.spec == spec_id
+        hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(nsteps)
+        out.append((hs.get_state(), hs.get_contact(), hs.get_pivot()))
+    for a, b in zip(out[0], out[1]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
+def test_specialisation_not_picked_for_other_shapes():
+    assert HostSim(ch.world_c5(base_z=0.1), 1).spec == 0                      # rigid pairs
+    assert HostSim(ch.World(chains=[ch.box(), ch.floor_soft()]), 1).spec == 0  # float joint
+    rng = np.random.default_rng(0)
+    assert HostSim(ch.World(chains=[ch.random_chain(rng, 8, jtypes=("revolute",))]), 1).spec == 0   # general frames
