@@ -139,17 +139,29 @@ struct SpecGeneric {
   static RKFD_HD int frame_slot(int, const LinkDev &L){ return L.frame_slot; }
   static RKFD_HD int rk_slot(const ModelDev &m){ return m.rk_slot; }
   static RKFD_HD int nq(const ModelDev &m){ return m.nq; }
+  /* 1-DoF joints: slots of (sin, cos, 1/D, u) in the "T space" (Ctx::TL/TS) - the scratch column itself here */
+  static RKFD_HD int sc(int, const LinkDev &L){ return L.slot + 6; }
+  static constexpr int TM = 0, NTSPACE = 0;
 };
 /* link 0 = fixed root, links 1..NL-1 revolute and serial; CLS: 2 bits per revolute link (RoClass 1..3) */
-template <int ID_, int NL_, unsigned CLS_>
+/* TM_ = 1: the integrator stage state and (sin, cos, 1/D, u) of every joint live in TENSOR MEMORY (tcgen05.st/ld,
+ * one TMEM lane per thread, 8 bytes per element) instead of the shared-memory column, which then holds 6 doubles per
+ * link + the external wrench: 54 instead of 110 doubles per environment for the 7-DoF arm -> 16 instead of 8 resident
+ * warps per SM (the kernel is latency bound, profiles/).  T-space accesses are warp-collective: they only appear
+ * in warp-uniform code. */
+template <int ID_, int NL_, unsigned CLS_, int TM_>
 struct SpecSerialRev {
-  static constexpr int ID = ID_, NL = NL_, UNROLL = NL_;
-  static constexpr int WEXT = 6 + 10*(NL_-1), RK = WEXT + 6, NSCRATCH = RK + 4*(NL_-1);
+  static constexpr int ID = ID_, NL = NL_, UNROLL = NL_, TM = TM_;
+  static constexpr int WEXT = TM_ ? 6*NL_ : 6 + 10*(NL_-1);
+  static constexpr int RK = TM_ ? 4*(NL_-1) : WEXT + 6;                 /* T space when TM_ */
+  static constexpr int NSCRATCH = TM_ ? WEXT + 6 : RK + 4*(NL_-1);     /* shared-memory doubles per environment */
+  static constexpr int NTSPACE = TM_ ? 8*(NL_-1) : 0;                   /* tensor-memory doubles per environment */
+  static RKFD_HD int sc(int i, const LinkDev &L){ return TM_ ? 4*(i-1) : slot(i, L) + 6; }
   static RKFD_HD int nl(const ModelDev &){ return NL_; }
   static RKFD_HD int jtype(int i, const LinkDev &){ return i == 0 ? J_FIXED : J_REVOL; }
   static RKFD_HD int parent(int i, const LinkDev &){ return i - 1; }
   static RKFD_HD int serial(int i, const LinkDev &){ return i > 0 ? 1 : 0; }
-  static RKFD_HD int slot(int i, const LinkDev &){ return i == 0 ? 0 : 6 + 10*(i-1); }
+  static RKFD_HD int slot(int i, const LinkDev &){ return TM_ ? 6*i : ( i == 0 ? 0 : 6 + 10*(i-1) ); }
   static RKFD_HD int wslot(int i, const LinkDev &L){ return slot(i, L); }
   static RKFD_HD int rcls(int i, const LinkDev &){ return i == 0 ? 0 : (int)((CLS_ >> (2*(i-1))) & 3u); }
   static RKFD_HD int qofs(int i, const LinkDev &){ return i > 0 ? i - 1 : 0; }
@@ -176,20 +188,33 @@ inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
 
 /* compiled specialisations: (id, links, rotation classes).  1: the 7-DoF arm of BASELINE.json (fixed base + 7
  * revolute links, frames alternating Rx(-90)/Rx(+90)); 2: fixed base + 2 parallel revolute links (arm_2DoF.ztk) */
-#define RKFD_SPEC_TABLE(X) X(1, 8, 0x3BBBu) X(2, 3, 0x5u)
+#define RKFD_SPEC_TABLE(X) X(3, 8, 0x3BBBu, 1) X(4, 3, 0x5u, 1) X(1, 8, 0x3BBBu, 0) X(2, 3, 0x5u, 0)
 template <int ID> struct SpecOf { using type = SpecGeneric; };
-#define RKFD_SPEC_X(id, nl, cls) template <> struct SpecOf<id> { using type = SpecSerialRev<id, nl, cls>; };
+#define RKFD_SPEC_X(id, nl, cls, tm) template <> struct SpecOf<id> { using type = SpecSerialRev<id, nl, cls, tm>; };
 RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-/* specialisation id the model is eligible for (0: generic kernel only), and its scratch size */
-inline int spec_match(const ModelDev &m){
-#define RKFD_SPEC_X(id, nl, cls) if( spec_serial_rev_match(m, nl, cls) ) return id;
+/* specialisation ids the model is eligible for (bit id set; 0: generic kernel only), and their scratch sizes */
+inline unsigned spec_match_mask(const ModelDev &m){
+  unsigned mask = 0;
+#define RKFD_SPEC_X(id, nl, cls, tm) if( spec_serial_rev_match(m, nl, cls) ) mask |= 1u << id;
+  RKFD_SPEC_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+  return mask;
+}
+inline int spec_match(const ModelDev &m, int want_tm = 1){     /* preferred id: first in table order with tm == want_tm */
+#define RKFD_SPEC_X(id, nl, cls, tm) if( tm == want_tm && spec_serial_rev_match(m, nl, cls) ) return id;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return 0;
 }
 inline int spec_nscratch(int id){
-#define RKFD_SPEC_X(sid, nl, cls) if( id == sid ) return SpecSerialRev<sid, nl, cls>::NSCRATCH;
+#define RKFD_SPEC_X(sid, nl, cls, tm) if( id == sid ) return SpecSerialRev<sid, nl, cls, tm>::NSCRATCH;
+  RKFD_SPEC_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+  return 0;
+}
+inline int spec_ntspace(int id){
+#define RKFD_SPEC_X(sid, nl, cls, tm) if( id == sid ) return SpecSerialRev<sid, nl, cls, tm>::NTSPACE;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return 0;
@@ -205,6 +230,12 @@ struct Core {
 
   RKFD_HD explicit Core(Ctx &ctx) : c(ctx), piv(0), cfl(0), bad(0), rk0(0) {}
 
+  /* T space: integrator stage state and per-joint (sin, cos, 1/D, u) - tensor memory in the TM specialisations,
+   * the scratch column otherwise */
+  RKFD_HD double T(int k){ return c.TL(k); }
+  RKFD_HD void Tw(int k, double v){ c.TS(k, v); }
+  RKFD_HD V3 t3(int k){ double x, y, z; c.TL2(k, x, y); z = c.TL(k+2); return v3(x, y, z); }
+  RKFD_HD void tw3(int k, V3 v){ c.TS(k, v.x); c.TS(k+1, v.y); c.TS(k+2, v.z); }
   RKFD_HD V3 ld3(int k){ return v3(c.S(k), c.S(k+1), c.S(k+2)); }
   RKFD_HD void st3(int k, V3 v){ c.S(k)=v.x; c.S(k+1)=v.y; c.S(k+2)=v.z; }
   RKFD_HD M3 ldm(int k){ M3 m; m.xx=c.S(k); m.xy=c.S(k+1); m.xz=c.S(k+2); m.yx=c.S(k+3); m.yy=c.S(k+4); m.yz=c.S(k+5); m.zx=c.S(k+6); m.zy=c.S(k+7); m.zz=c.S(k+8); return m; }
@@ -222,25 +253,25 @@ struct Core {
     vJ = v3(0,0,0); wJ = v3(0,0,0);
     switch(Spec::jtype(i,L)){
     case J_REVOL: {
-      x.s = c.S(sl+6); x.c = c.S(sl+7); x.p = org_p(L);
+      c.TL2(Spec::sc(i,L), x.s, x.c); x.p = org_p(L);
       if( Spec::rcls(i,L) != RO_GENERAL ){ x.fast = 1; x.ptl = rz_tmul(x.c, x.s, v3(L.pol[0],L.pol[1],L.pol[2])); }
       else {
         const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
         x.R = from_cols(x.c*o0 + x.s*o1, x.c*o1 - x.s*o0, col2(Ro)); x.ptl = tmul(x.R, x.p);
       }
-      wJ.z = c.S(qds);
+      wJ.z = T(qds);
     } break;
     case J_PRISM: {
-      x.R = org_R(L); x.p = org_p(L) + c.S(qs)*col2(x.R); x.ptl = tmul(x.R, x.p); vJ.z = c.S(qds);
+      x.R = org_R(L); x.p = org_p(L) + T(qs)*col2(x.R); x.ptl = tmul(x.R, x.p); vJ.z = T(qds);
     } break;
     case J_SPHER: {
       x.R = ldm(sl+27); x.p = org_p(L); x.ptl = tmul(x.R, x.p);
-      wJ = tmul(x.R, mul(org_R(L), ld3(qds)));
+      wJ = tmul(x.R, mul(org_R(L), t3(qds)));
     } break;
     case J_FLOAT: {
       x.R = ldm(sl+6); x.p = ld3(sl+15); x.ptl = tmul(x.R, x.p);
       const M3 Ro = org_R(L);
-      vJ = tmul(x.R, mul(Ro, ld3(qds))); wJ = tmul(x.R, mul(Ro, ld3(qds+3)));
+      vJ = tmul(x.R, mul(Ro, t3(qds))); wJ = tmul(x.R, mul(Ro, t3(qds+3)));
     } break;
     default: x.R = org_R(L); x.p = org_p(L); x.ptl = v3(L.pol[0],L.pol[1],L.pol[2]); break;
     }
@@ -344,26 +375,26 @@ struct Core {
       V3 vJ = v3(0,0,0), wJ = v3(0,0,0);
       switch(Spec::jtype(i,L)){
       case J_REVOL: {
-        double sn, co; sincos(c.S(qs+qo), &sn, &co);
-        c.S(sl+6) = sn; c.S(sl+7) = co;
+        double sn, co; sincos(T(qs+qo), &sn, &co);
+        Tw(Spec::sc(i,L), sn); Tw(Spec::sc(i,L)+1, co);
         x.s = sn; x.c = co; x.p = org_p(L);
         if( Spec::rcls(i,L) != RO_GENERAL ) x.fast = 1;
         else { const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
           x.R = from_cols(co*o0 + sn*o1, co*o1 - sn*o0, col2(Ro)); }
-        wJ.z = c.S(qds+qo);
+        wJ.z = T(qds+qo);
       } break;
-      case J_PRISM: x.R = org_R(L); x.p = org_p(L) + c.S(qs+qo)*col2(x.R); vJ.z = c.S(qds+qo); break;
+      case J_PRISM: x.R = org_R(L); x.p = org_p(L) + T(qs+qo)*col2(x.R); vJ.z = T(qds+qo); break;
       case J_SPHER: {
         const M3 Ro = org_R(L);
-        x.R = mm(Ro, aa_to_mat(ld3(qs+qo))); x.p = org_p(L);
+        x.R = mm(Ro, aa_to_mat(t3(qs+qo))); x.p = org_p(L);
         stm(sl+27, x.R);
-        wJ = tmul(x.R, mul(Ro, ld3(qds+qo)));
+        wJ = tmul(x.R, mul(Ro, t3(qds+qo)));
       } break;
       case J_FLOAT: {
         const M3 Ro = org_R(L);
-        x.R = mm(Ro, aa_to_mat(ld3(qs+qo+3))); x.p = org_p(L) + mul(Ro, ld3(qs+qo));
+        x.R = mm(Ro, aa_to_mat(t3(qs+qo+3))); x.p = org_p(L) + mul(Ro, t3(qs+qo));
         stm(sl+6, x.R); st3(sl+15, x.p);
-        vJ = tmul(x.R, mul(Ro, ld3(qds+qo))); wJ = tmul(x.R, mul(Ro, ld3(qds+qo+3)));
+        vJ = tmul(x.R, mul(Ro, t3(qds+qo))); wJ = tmul(x.R, mul(Ro, t3(qds+qo+3)));
       } break;
       default: x.R = org_R(L); x.p = org_p(L); break;
       }
@@ -389,7 +420,8 @@ struct Core {
    * (rkfd_util.c:330-364, [EXT A-6, A-7]); at the reference stage commits pivot type and prev_trq */
   RKFD_HD double joint_torque(const ModelDev &m, const LinkDev &L, int i, bool ref, double &jm, double u_in, double prev_in){
     const int j = Spec::qofs(i,L);
-    const double v = c.S(rk0 + Spec::nq(m) + j);
+    const double v = T(rk0 + Spec::nq(m) + j);
+    const double qj = L.stiffness != 0.0 ? T(rk0 + j) : 0.0;      /* warp-uniform condition: T-space reads stay collective */
     double tdrive = 0.0, tf = 0.0; jm = 0.0;
     if( L.mtype != M_NONE ){
       double e = u_in;
@@ -402,7 +434,7 @@ struct Core {
         if( !(piv & (1u<<j)) ) fmax = L.sfriction;
         else {
           const double sg = v > 0 ? 1.0 : ( v < 0 ? -1.0 : 0.0 );
-          fmax = -L.stiffness*c.S(rk0 + j) - L.viscosity*v - L.coulomb*sg;
+          fmax = -L.stiffness*qj - L.viscosity*v - L.coulomb*sg;
         }
         fmax = fabs(fmax);
         if( fabs(tf) > fmax ){ tf = tf > 0 ? fmax : -fmax; if( ref ) piv |= (1u<<j); }
@@ -469,7 +501,7 @@ struct Core {
         double jm; const double tau = joint_torque(m, L, i, ref, jm, pf_u, pf_prev);
         const V3 Ul = col2(B), Ua = v3(C.xz, C.yz, C.zz);
         const double Dinv = 1.0/(C.zz + jm), u = tau - pn.z;
-        st3(sl, Ul); st3(sl+3, Ua); c.S(sl+8) = Dinv; c.S(sl+9) = u;
+        st3(sl, Ul); st3(sl+3, Ua); Tw(Spec::sc(i,L)+2, Dinv); Tw(Spec::sc(i,L)+3, u);
         const V3 Wl = Dinv*Ul, Wa = Dinv*Ua;
         A.xx-=Wl.x*Ul.x; A.xy-=Wl.x*Ul.y; A.xz-=Wl.x*Ul.z; A.yy-=Wl.y*Ul.y; A.yz-=Wl.y*Ul.z; A.zz-=Wl.z*Ul.z;
         C.xx-=Wa.x*Ua.x; C.xy-=Wa.x*Ua.y; C.xz-=Wa.x*Ua.z; C.yy-=Wa.y*Ua.y; C.yz-=Wa.y*Ua.z; C.zz-=Wa.z*Ua.z;
@@ -480,7 +512,7 @@ struct Core {
         double jm; const double tau = joint_torque(m, L, i, ref, jm, pf_u, pf_prev);
         const V3 Ul = v3(A.xz, A.yz, A.zz), Ua = v3(B.zx, B.zy, B.zz);
         const double Dinv = 1.0/(A.zz + jm), u = tau - pf.z;
-        st3(sl, Ul); st3(sl+3, Ua); c.S(sl+8) = Dinv; c.S(sl+9) = u;
+        st3(sl, Ul); st3(sl+3, Ua); Tw(Spec::sc(i,L)+2, Dinv); Tw(Spec::sc(i,L)+3, u);
         const V3 Wl = Dinv*Ul, Wa = Dinv*Ua;
         A.xx-=Wl.x*Ul.x; A.xy-=Wl.x*Ul.y; A.xz-=Wl.x*Ul.z; A.yy-=Wl.y*Ul.y; A.yz-=Wl.y*Ul.z; A.zz-=Wl.z*Ul.z;
         C.xx-=Wa.x*Ua.x; C.xy-=Wa.x*Ua.y; C.xz-=Wa.x*Ua.z; C.yy-=Wa.y*Ua.y; C.yz-=Wa.y*Ua.z; C.zz-=Wa.z*Ua.z;
@@ -568,28 +600,28 @@ struct Core {
   /* F = running combination and x0 = committed value, fetched by the caller (possibly one link ahead) */
   RKFD_HD void rk_lin_pf(const RK &k, int stage, int slotS, int slotP, double *gout, int j, double slope, double F, double x0g){
     switch(stage){
-    case ST_K1: { const double x0 = c.S(slotS); c.gst(gout, j, x0 + k.b1*slope); c.S(slotP) = x0 + k.c31*slope; c.S(slotS) = x0 + k.c21*slope; } break;
-    case ST_K2: { c.gst(gout, j, F + k.b2*slope); c.S(slotS) = c.S(slotP) + k.c32*slope; c.S(slotP) = x0g + k.c42*slope; } break;
-    case ST_K3: { c.gst(gout, j, F + k.b3*slope); c.S(slotS) = c.S(slotP) + k.c43*slope; } break;
-    case ST_K4: { const double x = F + k.b4*slope; c.gst(gout, j, x); c.S(slotS) = x; } break;
+    case ST_K1: { const double x0 = T(slotS); c.gst(gout, j, x0 + k.b1*slope); Tw(slotP, x0 + k.c31*slope); Tw(slotS, x0 + k.c21*slope); } break;
+    case ST_K2: { c.gst(gout, j, F + k.b2*slope); Tw(slotS, T(slotP) + k.c32*slope); Tw(slotP, x0g + k.c42*slope); } break;
+    case ST_K3: { c.gst(gout, j, F + k.b3*slope); Tw(slotS, T(slotP) + k.c43*slope); } break;
+    case ST_K4: { const double x = F + k.b4*slope; c.gst(gout, j, x); Tw(slotS, x); } break;
     default: break;
     }
   }
   /* rotation (angle-axis) component triple starting at j: increments compose on SO(3) */
   RKFD_HD void rk_rot(const ModelDev &m, const RK &k, int stage, int slotS, int slotP, double *gin, double *gout, int j, V3 w){
     switch(stage){
-    case ST_K1: { const V3 x0 = ld3(slotS); const V3 F = aa_cascade(x0, k.b1*w);
+    case ST_K1: { const V3 x0 = t3(slotS); const V3 F = aa_cascade(x0, k.b1*w);
       c.gst(gout,j,F.x); c.gst(gout,j+1,F.y); c.gst(gout,j+2,F.z);
-      st3(slotP, aa_cascade(x0, k.c31*w)); st3(slotS, aa_cascade(x0, k.c21*w)); } break;
+      tw3(slotP, aa_cascade(x0, k.c31*w)); tw3(slotS, aa_cascade(x0, k.c21*w)); } break;
     case ST_K2: { const V3 x0 = v3(c.gld(gin,j), c.gld(gin,j+1), c.gld(gin,j+2));
       const V3 F = aa_cascade(v3(c.gld(gout,j), c.gld(gout,j+1), c.gld(gout,j+2)), k.b2*w);
       c.gst(gout,j,F.x); c.gst(gout,j+1,F.y); c.gst(gout,j+2,F.z);
-      st3(slotS, aa_cascade(ld3(slotP), k.c32*w)); st3(slotP, aa_cascade(x0, k.c42*w)); } break;
+      tw3(slotS, aa_cascade(t3(slotP), k.c32*w)); tw3(slotP, aa_cascade(x0, k.c42*w)); } break;
     case ST_K3: { const V3 F = aa_cascade(v3(c.gld(gout,j), c.gld(gout,j+1), c.gld(gout,j+2)), k.b3*w);
       c.gst(gout,j,F.x); c.gst(gout,j+1,F.y); c.gst(gout,j+2,F.z);
-      st3(slotS, aa_cascade(ld3(slotP), k.c43*w)); } break;
+      tw3(slotS, aa_cascade(t3(slotP), k.c43*w)); } break;
     case ST_K4: { const V3 F = aa_cascade(v3(c.gld(gout,j), c.gld(gout,j+1), c.gld(gout,j+2)), k.b4*w);
-      c.gst(gout,j,F.x); c.gst(gout,j+1,F.y); c.gst(gout,j+2,F.z); st3(slotS, F); } break;
+      c.gst(gout,j,F.x); c.gst(gout,j+1,F.y); c.gst(gout,j+2,F.z); tw3(slotS, F); } break;
     default: break;
     }
   }
@@ -598,7 +630,7 @@ struct Core {
     const int qs = rk0 + j, qds = rk0 + m.nq + j, pq = rk0 + 2*m.nq + j, pqd = rk0 + 3*m.nq + j;
     if( stage == ST_PROBE ) return;
     if( stage >= ST_REF ){ c.gst(c.st.qdd, j, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; return; }
-    const double vel = c.S(qds);
+    const double vel = T(qds);
     rk_lin(m, k, stage, qs, pq, c.st.q[c.cur], c.st.q[c.cur^1], j, vel);
     rk_lin(m, k, stage, qds, pqd, c.st.qd[c.cur], c.st.qd[c.cur^1], j, acc);
   }
@@ -638,14 +670,15 @@ struct Core {
       switch(Spec::jtype(i,L)){
       case J_REVOL: case J_PRISM: {
         const V3 Ul = ld3(sl), Ua = ld3(sl+3);
-        const double acc = c.S(sl+8)*( c.S(sl+9) - (dot(Ul,xl) + dot(Ua,xa)) );
+        double Dinv, uu; c.TL2(Spec::sc(i,L)+2, Dinv, uu);
+        const double acc = Dinv*( uu - (dot(Ul,xl) + dot(Ua,xa)) );
         al = xl + zl; aa = xa + za;
         if( Spec::jtype(i,L) == J_REVOL ) aa.z += acc; else al.z += acc;
         if( stage == ST_PROBE ){}
         else if( stage >= ST_REF ){ c.gst(c.st.qdd, qo, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; }
         else {
           const int j = qo, qs = rk0 + j, qds = qs + NQc, pq = qs + 2*NQc, pqd = qs + 3*NQc;
-          const double vel = c.S(qds);
+          const double vel = T(qds);
           rk_lin_pf(k, stage, qs,  pq,  c.st.q[c.cur^1],  j, vel, pfq[0], pfq[2]);
           rk_lin_pf(k, stage, qds, pqd, c.st.qd[c.cur^1], j, acc, pfq[1], pfq[3]);
         }
@@ -661,7 +694,7 @@ struct Core {
           if( !(fabs(acc.x)+fabs(acc.y)+fabs(acc.z) < 1.0e300) ) bad = 1; }
         else {
           const int qs = rk0 + L.qofs, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
-          const V3 w = ld3(qds);
+          const V3 w = t3(qds);
           rk_rot(m, k, stage, qs, pq, c.st.q[c.cur], c.st.q[c.cur^1], L.qofs, w);
           rk_lin(m, k, stage, qds,   pqd,   c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs,   acc.x);
           rk_lin(m, k, stage, qds+1, pqd+1, c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs+1, acc.y);
@@ -680,7 +713,7 @@ struct Core {
           if( !(fabs(accl.x)+fabs(accl.y)+fabs(accl.z)+fabs(acca.x)+fabs(acca.y)+fabs(acca.z) < 1.0e300) ) bad = 1;
         } else {
           const int qs = rk0 + L.qofs, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
-          const V3 v = ld3(qds), w = ld3(qds+3);
+          const V3 v = t3(qds), w = t3(qds+3);
           rk_lin(m, k, stage, qs,   pq,   c.st.q[c.cur], c.st.q[c.cur^1], L.qofs,   v.x);
           rk_lin(m, k, stage, qs+1, pq+1, c.st.q[c.cur], c.st.q[c.cur^1], L.qofs+1, v.y);
           rk_lin(m, k, stage, qs+2, pq+2, c.st.q[c.cur], c.st.q[c.cur^1], L.qofs+2, v.z);
@@ -736,7 +769,7 @@ struct Core {
       case J_REVOL: case J_PRISM: {
         const double du = L.jtype == J_REVOL ? -dpn.z : -dpf.z;
         c.W(du0+6*i) = du;
-        const double k = c.S(sl+8)*du;
+        const double k = T(Spec::sc(i,L)+2)*du;
         paf = dpf + k*ld3(sl); pan = dpn + k*ld3(sl+3);
       } break;
       case J_SPHER: {
@@ -762,7 +795,7 @@ struct Core {
       V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
       switch(L.jtype){
       case J_REVOL: case J_PRISM: {
-        const double acc = c.S(sl+8)*( c.W(du0+6*i) - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
+        const double acc = T(Spec::sc(i,L)+2)*( c.W(du0+6*i) - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
         if( L.jtype == J_REVOL ) xa.z += acc; else xl.z += acc;
       } break;
       case J_SPHER: {
@@ -1116,15 +1149,17 @@ struct Core {
   RKFD_HD void load_stage_state(const ModelDev &m){
     const int NQc = Spec::nq(m);
 #pragma unroll (Spec::UNROLL)
-    for(int j=0;j<NQc;j++){ c.S(rk0+j) = c.gld(c.st.q[c.cur], j); c.S(rk0+NQc+j) = c.gld(c.st.qd[c.cur], j); }
+    for(int j=0;j<NQc;j++){ Tw(rk0+j, c.gld(c.st.q[c.cur], j)); Tw(rk0+NQc+j, c.gld(c.st.qd[c.cur], j)); }
   }
   RKFD_HD void evaluate(const ModelDev &m, int stage){
     const bool ref = (stage == ST_REF) || (stage == ST_EVAL_REF);
     /* keep the warps of a block in the same pass: the instruction working set of the SM is then one pass, not
      * the union of all passes (the kernel is far larger than the instruction cache) */
     c.phase_sync(1);
+    c.tfence();               /* T-space stores of the previous pass are complete before this pass loads them */
     pass1(m, ref);
     if( !Ctx::RIGID ) c.phase_sync(2);
+    c.tfence();
     if( Ctx::RIGID ){
       /* rigid pairs in contact (reference rkfd_vert.c:385-386): any lane of the warp -> cooperative solve */
       const unsigned act = c.ballot( RKFD_POPC64(cfl & m.rigid_mask) > 0 );
@@ -1135,6 +1170,7 @@ struct Core {
     }
     pass2(m, ref);
     if( !Ctx::RIGID ) c.phase_sync(2);
+    c.tfence();
     pass3(m, stage);
   }
   /* mode 0: rkFDUpdate x nsteps (reference rkfd_sim.c:560-566); mode 1 / 2: a single non-committing /

@@ -106,19 +106,22 @@ template <class T> static T *dalloc(Shard &s, size_t n)
   s.allocs.push_back(p); return (T*)p;
 }
 
-/* kernel variants, one translation unit each (rkfd_kernel_variant.cu): BLOCK_GSCR_RIGID_SPEC */
-#define RKFD_DECL(B,G,R,S) extern const KernelVariant rkfd_variant_##B##_##G##_##R##_##S;
-RKFD_DECL(128,0,0,1) RKFD_DECL(256,0,0,1) RKFD_DECL(64,0,0,1) RKFD_DECL(128,0,0,2)
-RKFD_DECL(256,0,0,0) RKFD_DECL(128,0,0,0) RKFD_DECL(64,0,0,0) RKFD_DECL(32,0,0,0) RKFD_DECL(64,1,0,0)
-RKFD_DECL(256,0,1,0) RKFD_DECL(128,0,1,0) RKFD_DECL(64,0,1,0) RKFD_DECL(32,0,1,0) RKFD_DECL(64,1,1,0)
-constexpr int NVARIANTS = 14;
+/* kernel variants, one translation unit each (rkfd_kernel_variant.cu): BLOCK_GSCR_RIGID_SPEC_MINB */
+#define RKFD_VARIANT_LIST(X) \
+  X(256,0,0,3,2) X(512,0,0,3,1) X(128,0,0,3,4) X(128,0,0,3,3) X(128,0,0,4,4) X(128,0,0,1,1) X(256,0,0,1,1) X(128,0,0,2,1) \
+  X(128,0,0,0,1) X(256,0,0,0,1) X(64,0,0,0,1) X(32,0,0,0,1) X(64,1,0,0,1) \
+  X(128,0,1,0,1) X(256,0,1,0,1) X(64,0,1,0,1) X(32,0,1,0,1) X(64,1,1,0,1)
+#define RKFD_DECL(B,G,R,S,M) extern const KernelVariant rkfd_variant_##B##_##G##_##R##_##S##_##M;
+RKFD_VARIANT_LIST(RKFD_DECL)
+#undef RKFD_DECL
 /* order = preference among variants that keep the same number of environments resident (measured on B200,
- * profiles/r01_sync_sweep.md: 128-thread blocks with per-pass barriers are the best compromise); model
- * specialisations (spec > 0) come first and are taken whenever the model matches */
-static const KernelVariant *g_variants[NVARIANTS] = {
-  &rkfd_variant_128_0_0_1, &rkfd_variant_256_0_0_1, &rkfd_variant_64_0_0_1, &rkfd_variant_128_0_0_2,
-  &rkfd_variant_128_0_0_0, &rkfd_variant_256_0_0_0, &rkfd_variant_64_0_0_0, &rkfd_variant_32_0_0_0, &rkfd_variant_64_1_0_0,
-  &rkfd_variant_128_0_1_0, &rkfd_variant_256_0_1_0, &rkfd_variant_64_0_1_0, &rkfd_variant_32_0_1_0, &rkfd_variant_64_1_1_0 };
+ * profiles/): model specialisations (spec > 0) come first and are taken whenever the model matches; among the
+ * tensor-memory specialisations (16 resident warps per SM) two 256-thread CTAs beat one 512-thread CTA (barrier
+ * stalls) and four 128-thread CTAs (four independent instruction streams through the instruction cache) */
+#define RKFD_REF(B,G,R,S,M) &rkfd_variant_##B##_##G##_##R##_##S##_##M,
+static const KernelVariant *g_variants[] = { RKFD_VARIANT_LIST(RKFD_REF) };
+#undef RKFD_REF
+constexpr int NVARIANTS = (int)(sizeof g_variants / sizeof g_variants[0]);
 static int g_model_owner[64][NVARIANTS] = {{0}};   /* [device][variant]: engine whose model sits in that constant bank */
 
 static int variant_index(const KernelVariant *kv){ for(int i=0;i<NVARIANTS;i++) if( g_variants[i] == kv ) return i; return 0; }
@@ -136,7 +139,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     const int e0 = (int)((long long)B*g/G), e1 = (int)((long long)B*(g+1)/G);
     if( e1 <= e0 ) continue;
     Shard *s = new Shard; shards_.push_back(s);
-    s->dev = devs[g]; s->e0 = e0; s->B = e1-e0; s->ld = (s->B + 255) & ~255;   /* whole blocks of any variant: no thread exits early */
+    s->dev = devs[g]; s->e0 = e0; s->B = e1-e0; s->ld = (s->B + 511) & ~511;   /* whole blocks of any variant (<= 512 threads): no thread exits early */
     CK(cudaSetDevice(s->dev));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     const int nq = model.nq > 0 ? model.nq : 1, nl = model.nl > 0 ? model.nl : 1, ns = model.nslot > 0 ? model.nslot : 1;
@@ -158,18 +161,20 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
      * (gscr) only when no shared-memory variant fits */
     int best = 0; const bool rigid = model.has_rigid && model.solver != S_VOLUME;
     /* model specialisation (RKFD_SPEC=0 forces the generic kernel: tuning / comparison aid) */
-    int spec = spec_match(model);
-    if( const char *fs = std::getenv("RKFD_SPEC") ) if( std::atoi(fs) == 0 ) spec = 0;
+    unsigned specs = spec_match_mask(model);
+    if( const char *fs = std::getenv("RKFD_SPEC") ) specs &= 1u << std::atoi(fs);    /* 0: generic kernel only */
     for(int pass=0; pass<3 && best==0; pass++)
       for(const KernelVariant *kv : g_variants){
-        /* pass 0: the matching specialisation; 1: generic, shared-memory scratch; 2: generic, scratch in HBM */
-        if( kv->rigid != rigid || kv->gscr != (pass == 2) || kv->spec != (pass == 0 ? spec : 0) ) continue;
-        if( pass == 0 && spec == 0 ) continue;
-        if( const char *fb = std::getenv("RKFD_FORCE_BLOCK") ) if( std::atoi(fb) != kv->block ) continue;   /* tuning aid */
+        /* pass 0: a matching specialisation; 1: generic, shared-memory scratch; 2: generic, scratch in HBM */
+        if( kv->rigid != rigid || kv->gscr != (pass == 2) ) continue;
+        if( pass == 0 ? !( kv->spec > 0 && (specs >> kv->spec & 1u) ) : kv->spec != 0 ) continue;
+        if( const char *fb = std::getenv("RKFD_FORCE_BLOCK") ) if( std::atoi(fb) != kv->block ) continue;   /* tuning aids */
+        if( const char *fm = std::getenv("RKFD_FORCE_MINB") ) if( std::atoi(fm) != kv->minb ) continue;
         const int nscr = kv->spec ? spec_nscratch(kv->spec) : model.nscratch;
-        const size_t smem = kv->gscr ? 0 : (size_t)nscr*kv->block*sizeof(double);
+        size_t smem = kv->gscr ? 0 : (size_t)nscr*kv->block*sizeof(double);
+        if( const char *pad = std::getenv("RKFD_SMEM_PAD") ) smem += (size_t)std::atoi(pad);   /* tuning aid: lowers occupancy */
         if( smem > 227*1024 ) continue;
-        const int nb = kv->blocks_per_sm(smem);
+        int nb = kv->blocks_per_sm(smem);
         if( nb*kv->block > best ){ best = nb*kv->block; s->kv = kv; s->smem = smem; }
       }
     if( s->kv && s->kv->gscr ) st.scratch = dalloc<double>(*s, (size_t)model.nscratch*s->ld);

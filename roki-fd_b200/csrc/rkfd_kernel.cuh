@@ -5,6 +5,7 @@
 #define RKFD_KERNEL_CUH
 
 #include <cuda_runtime.h>
+#include <cstdio>
 
 #include "rkfd_core.cuh"
 
@@ -15,11 +16,44 @@ static __constant__ ModelDev c_model;
 
 extern __shared__ double rkfd_smem[];
 
-template <int BLOCK, bool GSCR, bool RIGID_>
+/* tensor memory as per-thread scratch: one TMEM lane per thread (warp w of the CTA owns lanes 32*(w%4)..+31),
+ * element k of the thread = 32-bit columns 2k, 2k+1.  tcgen05.ld/st are warp-collective (.sync.aligned): every
+ * T-space access sits in warp-uniform code. */
+constexpr int TMEM_COLS_PER_WARPGROUP = 128;     /* 64 doubles per thread */
+
+template <int BLOCK, bool GSCR, bool RIGID_, bool TM>
 struct DevCtx {
   static constexpr bool RIGID = RIGID_;
   StateDev st; int e, cur, tid;     /* e / tid: the SELECTED environment / scratch column (own, except in cooperative sections) */
   int e0, tid0, wsd;
+  unsigned tbase;                   /* tensor-memory address of element 0 of this thread's lane (TM variants) */
+  __device__ __forceinline__ double TL(int k){
+    if( !TM ) return S(k);
+    unsigned lo, hi;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(tbase + 2u*(unsigned)k));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(lo), "+r"(hi) :: "memory");
+    return __hiloint2double((int)hi, (int)lo);
+  }
+  /* elements k, k+1 with one instruction */
+  __device__ __forceinline__ void TL2(int k, double &a, double &b){
+    if( !TM ){ a = S(k); b = S(k+1); return; }
+    unsigned r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(tbase + 2u*(unsigned)k));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3) :: "memory");
+    a = __hiloint2double((int)r1, (int)r0); b = __hiloint2double((int)r3, (int)r2);
+  }
+  __device__ __forceinline__ void TS(int k, double v){
+    if( !TM ){ S(k) = v; return; }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" :: "r"(tbase + 2u*(unsigned)k), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+  }
+  __device__ __forceinline__ void tfence(){
+    if( TM ){
+#ifdef RKFD_TM_SYNCWARP
+      __syncwarp();
+#endif
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+  }
   /* scratch element k of this thread: shared-memory column [k*BLOCK + tid] (LDS/STS, conflict-free) */
   __device__ __forceinline__ double &S(int k){
     if( GSCR ) return st.scratch[(size_t)k*st.ld + e];
@@ -49,20 +83,61 @@ struct DevCtx {
 };
 
 /* mode 0: nsteps x rkFDUpdate; 1: one non-committing evaluation; 2: one committing evaluation */
-template <int BLOCK, bool GSCR, bool RIGID, int SPEC>
-__global__ void __launch_bounds__(BLOCK) rkfd_step_kernel(StateDev st, int cur, int mode, int nsteps)
+/* MINB (minimum resident blocks per SM, i.e. the register cap) is a template parameter so that every compiled
+ * variant has its own kernel symbol: two translation units instantiating the same template arguments with
+ * different launch bounds would collide at link time and launch each other's module (and constant bank). */
+template <int BLOCK, bool GSCR, bool RIGID, int SPEC, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) rkfd_step_kernel(StateDev st, int cur, int mode, int nsteps)
 {
+  using Spec = typename SpecOf<SPEC>::type;
+  constexpr bool TM = Spec::TM != 0;
   const int e = blockIdx.x*BLOCK + threadIdx.x;
-  if( e >= st.ld ) return;            /* whole warps only: the padding environments [B, ld) hold a valid zero state */
-  DevCtx<BLOCK,GSCR,RIGID> ctx; ctx.st = st; ctx.e = ctx.e0 = e; ctx.cur = cur; ctx.tid = ctx.tid0 = threadIdx.x; ctx.wsd = c_model.ws_doubles;
-  Core<DevCtx<BLOCK,GSCR,RIGID>, typename SpecOf<SPEC>::type> core(ctx);
+  /* the engine pads the environment count to whole blocks (ld): no thread exits early, which the block barriers
+   * and the tensor-memory allocation below rely on; the padding environments hold a valid zero state */
+  DevCtx<BLOCK,GSCR,RIGID,TM> ctx; ctx.st = st; ctx.e = ctx.e0 = e; ctx.cur = cur; ctx.tid = ctx.tid0 = threadIdx.x; ctx.wsd = c_model.ws_doubles;
+  ctx.tbase = 0;
+  constexpr unsigned TCOLS = TMEM_COLS_PER_WARPGROUP*((BLOCK + 127)/128);
+  __shared__ unsigned tmem_addr;
+  if( TM ){
+    static_assert(!TM || ((TCOLS & (TCOLS-1)) == 0 && TCOLS >= 32 && TCOLS <= 512), "tensor-memory columns: power of two in [32, 512]");
+    static_assert(!TM || 2*Spec::NTSPACE <= TMEM_COLS_PER_WARPGROUP, "T space does not fit the tensor-memory lane");
+    if( threadIdx.x < 32 ){
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(&tmem_addr)), "r"(TCOLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned warp = threadIdx.x >> 5;
+    ctx.tbase = tmem_addr + (((warp & 3u)*32u) << 16) + (warp >> 2)*TMEM_COLS_PER_WARPGROUP;
+  }
+  Core<DevCtx<BLOCK,GSCR,RIGID,TM>, Spec> core(ctx);
+#ifdef RKFD_TM_ZERO
+  if( TM ){ for(int k=0;k<64;k++) ctx.TS(k, 0.0); ctx.tfence(); }
+#endif
+#ifdef RKFD_TM_DEBUG
+  if( TM ){   /* write/read-back self test of the thread's T space before the real work */
+    for(int k=0;k<Spec::NTSPACE;k++) ctx.TS(k, 1000.0*e + k);
+    ctx.tfence();
+    int nbad = 0; for(int k=0;k<Spec::NTSPACE;k++) if( ctx.TL(k) != 1000.0*e + k ) nbad++;
+    unsigned smid, wid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    if( (threadIdx.x & 31) == 0 && blockIdx.x < 4 ) printf("[tm] block %d warp %d smid %u warpid %u tmem_addr %x tbase %x selftest bad %d\n", blockIdx.x, threadIdx.x>>5, smid, wid, tmem_addr, ctx.tbase, nbad);
+  }
+#endif
   core.run(c_model, mode, nsteps);
+  if( TM ){
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if( threadIdx.x < 32 )
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_addr), "r"(TCOLS) : "memory");
+  }
 }
 
 
 /* one compiled variant: launch + occupancy query */
 struct KernelVariant {
   int block; bool gscr, rigid; int spec;     /* spec: model specialisation id (rkfd_core.cuh), 0 = generic */
+  int minb;                                  /* __launch_bounds__ minimum blocks per SM the variant was compiled for */
   void (*launch)(const StateDev &st, int cur, int mode, int nsteps, int grid, size_t smem, cudaStream_t stream);
   int (*blocks_per_sm)(size_t smem);      /* sets the dynamic shared memory attribute; <0 on error */
   int (*upload)(const ModelDev *m, cudaStream_t stream);   /* model table -> this variant's constant bank */

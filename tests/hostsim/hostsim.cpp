@@ -3,6 +3,7 @@
  * kernel can be checked against the oracle where no GPU exists (`-m "not gpu"` tests).
  * It is NOT part of the product: librokifd_b200.so does not contain it and nothing under
  * roki-fd_b200/ loads it.  The product path has no CPU fallback. */
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -18,8 +19,13 @@ void sincos(double x, double *s, double *c){ *s = std::sin(x); *c = std::cos(x);
 }
 
 struct HostCtx {
-  StateDev st; int e, cur; std::vector<double> scr, wsp;
+  StateDev st; int e, cur; std::vector<double> scr, wsp, tsp; bool tm = false;
   double &S(int k){ return scr[k]; }
+  /* T space: a separate array when the specialisation keeps it in tensor memory, the scratch column otherwise */
+  double TL(int k){ return tm ? tsp[k] : scr[k]; }
+  void TL2(int k, double &a, double &b){ a = TL(k); b = TL(k+1); }
+  void TS(int k, double v){ if( tm ) tsp[k] = v; else scr[k] = v; }
+  void tfence(){}
   static constexpr bool RIGID = true;
   /* a "warp" of one lane */
   int lanes() const { return 1; }
@@ -92,8 +98,8 @@ const char *hostsim_error(HostSim *h){ return h->err.c_str(); }
 int hostsim_nq(HostSim *h){ return h->model.nq; }
 int hostsim_nl(HostSim *h){ return h->model.nl; }
 /* model specialisation the kernel would pick (0: generic); hostsim_use_spec makes hostsim_run use it */
-int hostsim_spec_match(HostSim *h){ return spec_match(h->model); }
-void hostsim_use_spec(HostSim *h, int on){ h->spec = on ? spec_match(h->model) : 0; }
+int hostsim_spec_match(HostSim *h, int tm){ return spec_match(h->model, tm); }
+void hostsim_use_spec(HostSim *h, int id){ h->spec = ( id > 0 && (spec_match_mask(h->model) >> id & 1u) ) ? id : 0; }
 int hostsim_nslot(HostSim *h){ return h->model.nslot; }
 int hostsim_nscratch(HostSim *h){ return h->model.nscratch; }
 void hostsim_free(HostSim *h){ for(void *p : h->allocs) std::free(p); for(auto *c : h->chains) delete c; delete h; }
@@ -130,9 +136,9 @@ void hostsim_run(HostSim *h, int mode, int nsteps)
 {
   for(int e=0;e<h->B;e++){
     HostCtx ctx; ctx.st = h->st; ctx.e = e; ctx.cur = h->cur; ctx.wsp.assign(h->model.ws_doubles + 1, 0.0);
-    ctx.scr.assign((h->spec ? spec_nscratch(h->spec) : h->model.nscratch) + 1, 0.0);
+    ctx.scr.assign((h->spec ? spec_nscratch(h->spec) : h->model.nscratch) + 1, std::nan(""));   /* read-before-write shows up as NaN */
     switch(h->spec){
-#define RKFD_SPEC_X(id, nl, cls) case id: { Core<HostCtx, SpecOf<id>::type> core(ctx); core.run(h->model, mode, nsteps); } break;
+#define RKFD_SPEC_X(id, nl, cls, tmv) case id: { ctx.tm = tmv != 0; ctx.tsp.assign(spec_ntspace(id) + 1, std::nan("")); Core<HostCtx, SpecOf<id>::type> core(ctx); core.run(h->model, mode, nsteps); } break;
     RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
     default: { Core<HostCtx> core(ctx); core.run(h->model, mode, nsteps); } break;

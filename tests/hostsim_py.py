@@ -35,7 +35,8 @@ def lib():
         L.hostsim_error.restype = C.c_char_p
         L.hostsim_error.argtypes = [C.c_void_p]
         L.hostsim_use_spec.argtypes = [C.c_void_p, C.c_int]
-        for f in ("hostsim_nq", "hostsim_nl", "hostsim_nslot", "hostsim_nscratch", "hostsim_free", "hostsim_spec_match"):
+        L.hostsim_spec_match.argtypes = [C.c_void_p, C.c_int]
+        for f in ("hostsim_nq", "hostsim_nl", "hostsim_nslot", "hostsim_nscratch", "hostsim_free"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.hostsim_set_state.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.hostsim_get_state.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -52,7 +53,7 @@ def _d(a):
 
 
 class HostSim:
-    def __init__(self, world, B, spec=False):
+    def __init__(self, world, B, spec=None):
         L = lib()
         links, nls = [], []
         for ch in world.chains:          # all chains (static ones included), chain-local parents
@@ -77,10 +78,12 @@ class HostSim:
             raise RuntimeError(L.hostsim_error(self.h).decode())
         self.B, self.nq, self.nl, self.nslot = B, L.hostsim_nq(self.h), L.hostsim_nl(self.h), L.hostsim_nslot(self.h)
         self.nscratch = L.hostsim_nscratch(self.h)
-        self.spec = L.hostsim_spec_match(self.h)      # model specialisation the kernel would pick (0: generic)
-        if spec:
-            assert self.spec > 0, "model matches no compiled specialisation"
-            L.hostsim_use_spec(self.h, 1)
+        # model specialisations the kernel could pick (0: generic): scratch in shared memory / in tensor memory
+        self.spec, self.spec_tm = L.hostsim_spec_match(self.h, 0), L.hostsim_spec_match(self.h, 1)
+        if spec:                                   # "smem" | "tmem": run that specialisation's code path
+            sid = self.spec_tm if spec == "tmem" else self.spec
+            assert sid > 0, "model matches no compiled specialisation"
+            L.hostsim_use_spec(self.h, sid)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -215,14 +215,15 @@ def test_specialised_core_is_bit_identical(name):
     B, nsteps = 16, 30
     q, qd, u = ch.sample_state(w, B, seed=13)
     out = []
-    for spec in (False, True):
+    for spec in (None, "smem", "tmem"):
         hs = HostSim(w, B, spec=spec)
-        assert hs.spec == spec_id
+        assert hs.spec == spec_id and hs.spec_tm == spec_id + 2
         hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(nsteps)
         out.append((hs.get_state(), hs.get_contact(), hs.get_pivot()))
-    for a, b in zip(out[0], out[1]):
-        for x, y in zip(a, b):
-            assert np.array_equal(x, y)
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
 
 
 def test_specialisation_not_picked_for_other_shapes():
