@@ -31,9 +31,11 @@
 #if defined(__CUDA_ARCH__)
 #define RKFD_POPC64(x) __popcll(x)
 #define RKFD_FFS32(x) __ffs(x)
+#define RKFD_FFS64(x) __ffsll((long long)(x))
 #else
 #define RKFD_POPC64(x) __builtin_popcountll(x)
 #define RKFD_FFS32(x) __builtin_ffs(x)
+#define RKFD_FFS64(x) __builtin_ffsll((long long)(x))
 #endif
 
 namespace rkfd {
@@ -122,8 +124,13 @@ RKFD_HD S3 sym3_inverse(const S3 &d){
  * constant-bank operand with an immediate offset, every scratch access an LDS/STS with an immediate offset,
  * and the joint-type switches disappear.  Same arithmetic, same order of operations: results are bit-identical
  * to the generic kernel.  The host picks a compiled specialisation when the model matches (spec_match). */
+/* compile-time description of one link handed to the pass bodies: joint type, rotation class, root flag;
+ * -1 = not known at compile time (the Spec accessor / the link table decides) */
+template <int JT_, int CLS_, int ROOT_> struct LinkTag { static constexpr int jt = JT_, cls = CLS_, root = ROOT_; };
+using TagRT = LinkTag<-1, -1, -1>;
+
 struct SpecGeneric {
-  static constexpr int ID = 0, NL = 0, UNROLL = 1, NSCRATCH = 0;
+  static constexpr int ID = 0, NL = 0, UNROLL = 1, NSCRATCH = 0, ROLL = 0;
   static RKFD_HD int nl(const ModelDev &m){ return m.nl; }
   static RKFD_HD int jtype(int, const LinkDev &L){ return L.jtype; }
   static RKFD_HD int parent(int, const LinkDev &L){ return L.parent; }
@@ -151,7 +158,7 @@ struct SpecGeneric {
  * in warp-uniform code. */
 template <int ID_, int NL_, unsigned CLS_, int TM_>
 struct SpecSerialRev {
-  static constexpr int ID = ID_, NL = NL_, UNROLL = NL_, TM = TM_;
+  static constexpr int ID = ID_, NL = NL_, UNROLL = NL_, TM = TM_, ROLL = 0;
   static constexpr int WEXT = TM_ ? 6*NL_ : 6 + 10*(NL_-1);
   static constexpr int RK = TM_ ? 4*(NL_-1) : WEXT + 6;                 /* T space when TM_ */
   static constexpr int NSCRATCH = TM_ ? WEXT + 6 : RK + 4*(NL_-1);     /* shared-memory doubles per environment */
@@ -173,6 +180,46 @@ struct SpecSerialRev {
   static RKFD_HD int rk_slot(const ModelDev &){ return RK; }
   static RKFD_HD int nq(const ModelDev &){ return NL_ - 1; }
 };
+/* Same model shape, ROLLED link loops: the base link is peeled off, the revolute links run through ONE loop body per
+ * pass whose link index is a run-time (warp-uniform) value.  Every revolute frame must be a quarter turn about x; its
+ * sign comes from the link table, so any pattern of +-90 degree twists shares the code.  Why: the fully unrolled
+ * kernel is ~110 KB of straight-line code per evaluation, streamed through the 32 KB L1.5 / 6 KB L0 instruction caches
+ * by every warp (ncu: no_instruction is its second largest stall); the rolled bodies are ~7 KB per pass and stay
+ * cached.  Costs: table entries are fetched through uniform registers instead of immediate constant operands, and a
+ * handful of multiplications by the sign.  Scratch layout = the tensor-memory layout of SpecSerialRev<.,.,.,1>. */
+template <int ID_, int NL_>
+struct SpecSerialRevRolled {
+  static constexpr int ID = ID_, NL = NL_, UNROLL = 1, TM = 1, ROLL = 1;
+  static constexpr int WEXT = 6*NL_, RK = 4*(NL_-1), NSCRATCH = WEXT + 6, NTSPACE = 8*(NL_-1);
+  static RKFD_HD int nl(const ModelDev &){ return NL_; }
+  static RKFD_HD int jtype(int i, const LinkDev &){ return i == 0 ? J_FIXED : J_REVOL; }
+  static RKFD_HD int parent(int i, const LinkDev &){ return i - 1; }
+  static RKFD_HD int serial(int i, const LinkDev &){ return i > 0 ? 1 : 0; }
+  static RKFD_HD int slot(int i, const LinkDev &){ return 6*i; }
+  static RKFD_HD int wslot(int i, const LinkDev &){ return 6*i; }
+  static RKFD_HD int rcls(int i, const LinkDev &){ return i == 0 ? RO_GENERAL : RO_RXS; }
+  static RKFD_HD int qofs(int i, const LinkDev &){ return i > 0 ? i - 1 : 0; }
+  static RKFD_HD int ndof(int i, const LinkDev &){ return i > 0 ? 1 : 0; }
+  static RKFD_HD int branch_slot(int, const LinkDev &){ return -1; }
+  static RKFD_HD int accum_slot(int, const LinkDev &){ return -1; }
+  static RKFD_HD int wext_slot(int i, const LinkDev &L){ return ( i == NL_-1 && L.cell_end > L.cell_begin ) ? WEXT : -1; }
+  static RKFD_HD int frame_slot(int, const LinkDev &){ return -1; }
+  static RKFD_HD int rk_slot(const ModelDev &){ return RK; }
+  static RKFD_HD int nq(const ModelDev &){ return NL_ - 1; }
+  static RKFD_HD int sc(int i, const LinkDev &){ return 4*(i-1); }
+};
+inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL){
+  if( m.has_rigid || m.nl != NL || NL < 2 ) return false;
+  for(int i=0;i<NL;i++){
+    const LinkDev &L = m.link[i];
+    if( i == 0 ){ if( L.parent >= 0 || L.jtype != J_FIXED || L.cell_end > L.cell_begin ) return false; continue; }
+    if( L.jtype != J_REVOL || L.parent != i-1 || !L.serial || L.qofs != i-1 ) return false;
+    if( L.rcls != RO_RXP && L.rcls != RO_RXM ) return false;
+    if( i != NL-1 && L.cell_end > L.cell_begin ) return false;
+  }
+  return true;
+}
+
 /* does the flattened model have the shape SpecSerialRev<.,NL,CLS> assumes? (host side) */
 inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
   if( m.has_rigid || m.nl != NL || NL < 2 ) return false;
@@ -189,9 +236,14 @@ inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
 /* compiled specialisations: (id, links, rotation classes).  1: the 7-DoF arm of BASELINE.json (fixed base + 7
  * revolute links, frames alternating Rx(-90)/Rx(+90)); 2: fixed base + 2 parallel revolute links (arm_2DoF.ztk) */
 #define RKFD_SPEC_TABLE(X) X(3, 8, 0x3BBBu, 1) X(4, 3, 0x5u, 1) X(1, 8, 0x3BBBu, 0) X(2, 3, 0x5u, 0)
+/* rolled specialisations: (id, links); 5: fixed base + 7 revolute links, 6: + 6 revolute links */
+#define RKFD_SPEC_ROLLED_TABLE(X) X(5, 8) X(6, 7)
 template <int ID> struct SpecOf { using type = SpecGeneric; };
 #define RKFD_SPEC_X(id, nl, cls, tm) template <> struct SpecOf<id> { using type = SpecSerialRev<id, nl, cls, tm>; };
 RKFD_SPEC_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+#define RKFD_SPEC_X(id, nl) template <> struct SpecOf<id> { using type = SpecSerialRevRolled<id, nl>; };
+RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
 /* specialisation ids the model is eligible for (bit id set; 0: generic kernel only), and their scratch sizes */
 inline unsigned spec_match_mask(const ModelDev &m){
@@ -199,7 +251,16 @@ inline unsigned spec_match_mask(const ModelDev &m){
 #define RKFD_SPEC_X(id, nl, cls, tm) if( spec_serial_rev_match(m, nl, cls) ) mask |= 1u << id;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
+#define RKFD_SPEC_X(id, nl) if( spec_serial_rev_rolled_match(m, nl) ) mask |= 1u << id;
+  RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
   return mask;
+}
+inline int spec_match_rolled(const ModelDev &m){
+#define RKFD_SPEC_X(id, nl) if( spec_serial_rev_rolled_match(m, nl) ) return id;
+  RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+  return 0;
 }
 inline int spec_match(const ModelDev &m, int want_tm = 1){     /* preferred id: first in table order with tm == want_tm */
 #define RKFD_SPEC_X(id, nl, cls, tm) if( tm == want_tm && spec_serial_rev_match(m, nl, cls) ) return id;
@@ -211,11 +272,17 @@ inline int spec_nscratch(int id){
 #define RKFD_SPEC_X(sid, nl, cls, tm) if( id == sid ) return SpecSerialRev<sid, nl, cls, tm>::NSCRATCH;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
+#define RKFD_SPEC_X(sid, nl) if( id == sid ) return SpecSerialRevRolled<sid, nl>::NSCRATCH;
+  RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
   return 0;
 }
 inline int spec_ntspace(int id){
 #define RKFD_SPEC_X(sid, nl, cls, tm) if( id == sid ) return SpecSerialRev<sid, nl, cls, tm>::NTSPACE;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+#define RKFD_SPEC_X(sid, nl) if( id == sid ) return SpecSerialRevRolled<sid, nl>::NTSPACE;
+  RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return 0;
 }
@@ -229,6 +296,35 @@ struct Core {
   int rk0;                      /* first slot of the integrator stage state (QS, QDS, PQ, PQD) */
 
   RKFD_HD explicit Core(Ctx &ctx) : c(ctx), piv(0), cfl(0), bad(0), rk0(0) {}
+
+  /* link properties: the compile-time tag when it knows, the Spec accessor (table / unrolled index) otherwise */
+  template <class Kt> static RKFD_HD int JT(int i, const LinkDev &L){ return Kt::jt >= 0 ? Kt::jt : Spec::jtype(i,L); }
+  template <class Kt> static RKFD_HD int CLS(int i, const LinkDev &L){ return Kt::cls >= 0 ? Kt::cls : Spec::rcls(i,L); }
+  template <class Kt> static RKFD_HD bool ROOT(int i, const LinkDev &L){ return Kt::root >= 0 ? Kt::root != 0 : Spec::parent(i,L) < 0; }
+  template <class Kt> static RKFD_HD bool SER(int i, const LinkDev &L){ return Kt::root >= 0 ? Kt::root == 0 : Spec::serial(i,L) != 0; }
+  /* link loops: base -> tip and tip -> base.  f(i, tag) is the pass body */
+  template <class F> RKFD_HD void links_fwd(const ModelDev &m, F &&f){
+    if constexpr ( Spec::ROLL != 0 ){
+      f(0, LinkTag<J_FIXED, RO_GENERAL, 1>{});
+#pragma unroll 1
+      for(int i=1;i<Spec::NL;i++) f(i, LinkTag<J_REVOL, RO_RXS, 0>{});
+    } else {
+      const int NLc = Spec::nl(m);
+#pragma unroll (Spec::UNROLL)
+      for(int i=0;i<NLc;i++) f(i, TagRT{});
+    }
+  }
+  template <class F> RKFD_HD void links_bwd(const ModelDev &m, F &&f){
+    if constexpr ( Spec::ROLL != 0 ){
+#pragma unroll 1
+      for(int i=Spec::NL-1;i>=1;i--) f(i, LinkTag<J_REVOL, RO_RXS, 0>{});
+      f(0, LinkTag<J_FIXED, RO_GENERAL, 1>{});
+    } else {
+      const int NLc = Spec::nl(m);
+#pragma unroll (Spec::UNROLL)
+      for(int i=NLc-1;i>=0;i--) f(i, TagRT{});
+    }
+  }
 
   /* T space: integrator stage state and per-joint (sin, cos, 1/D, u) - tensor memory in the TM specialisations,
    * the scratch column otherwise */
@@ -247,14 +343,15 @@ struct Core {
 
   /* link frame w.r.t. parent and joint velocity (vJ,wJ, link frame) from the stage state and the joint data
    * cached by pass 1 ([EXT A-3]) */
+  template <class Kt>
   RKFD_HD XF joint_xform(const ModelDev &m, const LinkDev &L, int i, V3 &vJ, V3 &wJ){
     const int sl = Spec::slot(i,L), qs = rk0 + Spec::qofs(i,L), qds = rk0 + Spec::nq(m) + Spec::qofs(i,L);
-    XF x; x.fast = 0; x.cls = Spec::rcls(i,L); x.c = 1.0; x.s = 0.0;
+    XF x; x.fast = 0; x.cls = CLS<Kt>(i,L); x.sg = ro_sign(x.cls, L.rsg); x.c = 1.0; x.s = 0.0;
     vJ = v3(0,0,0); wJ = v3(0,0,0);
-    switch(Spec::jtype(i,L)){
+    switch(JT<Kt>(i,L)){
     case J_REVOL: {
       c.TL2(Spec::sc(i,L), x.s, x.c); x.p = org_p(L);
-      if( Spec::rcls(i,L) != RO_GENERAL ){ x.fast = 1; x.ptl = rz_tmul(x.c, x.s, v3(L.pol[0],L.pol[1],L.pol[2])); }
+      if( CLS<Kt>(i,L) != RO_GENERAL ){ x.fast = 1; x.ptl = rz_tmul(x.c, x.s, v3(L.pol[0],L.pol[1],L.pol[2])); }
       else {
         const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
         x.R = from_cols(x.c*o0 + x.s*o1, x.c*o1 - x.s*o0, col2(Ro)); x.ptl = tmul(x.R, x.p);
@@ -297,24 +394,43 @@ struct Core {
   static RKFD_HD M3 box_R(const BoxDev &bx){ M3 Rb; Rb.xx=bx.R[0]; Rb.xy=bx.R[1]; Rb.xz=bx.R[2]; Rb.yx=bx.R[3]; Rb.yy=bx.R[4]; Rb.yz=bx.R[5]; Rb.zx=bx.R[6]; Rb.zy=bx.R[7]; Rb.zz=bx.R[8]; return Rb; }
 
   /* ---- contact of the cells carried by link i: vertex-in-box detection ([EXT A-10]), elastic pairs:
-   * penalty force + Coulomb clamp + wrench accumulation (rkfd_penalty.c:11-31, rkfd_util.c:239-282) */
+   * penalty force + Coulomb clamp + wrench accumulation (rkfd_penalty.c:11-31, rkfd_util.c:239-282).
+   * Two phases per (cell, box) pair so that a warp does not walk through the expensive force code once per
+   * candidate vertex: (A) the cheap inside test of every vertex, all lanes in lockstep, gives each lane the bit
+   * mask of its vertices in contact; (B) every lane then serves its own vertices in ascending order - the warp
+   * iterates max-over-lanes(#contacts) times (typically 1-4) instead of #vertices (8) times.  The order of the
+   * wrench summation per environment is unchanged (pair, vertex). */
   RKFD_HD V6 contacts(const ModelDev &m, const LinkDev &L, const M3 &Rw, V3 pw, V3 vl, V3 om, bool ref){
     V6 w; w.l = v3(0,0,0); w.a = v3(0,0,0);
+    const V3 vlw = mul(Rw, vl), omw = mul(Rw, om);     /* rkFDLinkPointWldVel (rkfd_util.c:14-24): world velocity of the link origin, world angular velocity */
     for(int ci=L.cell_begin; ci<L.cell_end; ci++){
       const CellDev &cl = m.cell[ci];
       for(int pi=cl.pair_begin; pi<cl.pair_end; pi++){
         const PairDev &pr = m.pair[pi]; const BoxDev &bx = m.box[pr.box];
-        M3 Rb; Rb.xx=bx.R[0]; Rb.xy=bx.R[1]; Rb.xz=bx.R[2]; Rb.yx=bx.R[3]; Rb.yy=bx.R[4]; Rb.yz=bx.R[5]; Rb.zx=bx.R[6]; Rb.zy=bx.R[7]; Rb.zz=bx.R[8];
+        const M3 Rb = box_R(bx);
         const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
+        /* (A) detection */
+        unsigned long long in = 0;
         for(int k=0;k<cl.nvert;k++){
+          const int s = pr.sofs + k;
+          const V3 vloc = v3(m.vert[3*(cl.vofs+k)], m.vert[3*(cl.vofs+k)+1], m.vert[3*(cl.vofs+k)+2]);
+          const V3 vw = pw + mul(Rw, vloc);
+          const V3 vb = tmul(Rb, vw - pb);
+          const double dx = bx.half[0]-fabs(vb.x), dy = bx.half[1]-fabs(vb.y), dz = bx.half[2]-fabs(vb.z);
+          const bool inside = (dx > -ZTOL) && (dy > -ZTOL) && (dz > -ZTOL);
+          if( inside ) in |= 1ull << k;
+          else { cfl &= ~(3ull << (2*s)); if( ref ){ c.gst(c.st.cf, 3*s, 0.0); c.gst(c.st.cf, 3*s+1, 0.0); c.gst(c.st.cf, 3*s+2, 0.0); } }
+        }
+        /* (B) the lane's own contacts */
+        while( c.any(in != 0) ){
+          if( in == 0 ) continue;
+          const int k = RKFD_FFS64(in) - 1; in &= in - 1;
           const int s = pr.sofs + k;
           const unsigned long long abit = 1ull << (2*s), kbit = 2ull << (2*s);
           const V3 vloc = v3(m.vert[3*(cl.vofs+k)], m.vert[3*(cl.vofs+k)+1], m.vert[3*(cl.vofs+k)+2]);
           const V3 vw = pw + mul(Rw, vloc);
           const V3 vb = tmul(Rb, vw - pb);
           const double dx = bx.half[0]-fabs(vb.x), dy = bx.half[1]-fabs(vb.y), dz = bx.half[2]-fabs(vb.z);
-          const bool inside = (dx > -ZTOL) && (dy > -ZTOL) && (dz > -ZTOL);
-          if( !inside ){ cfl &= ~(abit|kbit); if( ref ){ c.gst(c.st.cf, 3*s, 0.0); c.gst(c.st.cf, 3*s+1, 0.0); c.gst(c.st.cf, 3*s+2, 0.0); } continue; }
           V3 n, t1, t2, prob;
           box_face(bx, Rb, vb, dx, dy, dz, n, t1, t2, prob);
           V3 refb;
@@ -326,7 +442,7 @@ struct Core {
           const V3 refw = pb + mul(Rb, refb);
           const V3 d = vw - refw;
           /* rkFDLinkPointWldVel (rkfd_util.c:14-24); the static partner contributes 0 */
-          const V3 vr = mul(Rw, vl) + cross(mul(Rw, om), vw - pw);
+          const V3 vr = vlw + cross(omw, vw - pw);
           V3 f = (-pr.E)*d + (-1.0*(pr.V + pr.E*m.dt))*vr;
           if( dot(f,n) < 0.0 ){ if( ref ){ c.gst(c.st.cf,3*s,f.x); c.gst(c.st.cf,3*s+1,f.y); c.gst(c.st.cf,3*s+2,f.z); } continue; }
           /* rkFDContactForceModifyFriction */
@@ -358,27 +474,26 @@ struct Core {
   RKFD_HD void pass1(const ModelDev &m, bool ref){
     M3 Rw = ident3(); V3 pw = v3(0,0,0), vl = v3(0,0,0), om = v3(0,0,0), gd = v3(0,0,-GRAVITY);
     const int qs = rk0, qds = rk0 + Spec::nq(m);
-    const int NLc = Spec::nl(m);
-#pragma unroll (Spec::UNROLL)
-    for(int i=0;i<NLc;i++){
+    auto body = [&](const int i, auto Ktag){
+      using Kt = decltype(Ktag);
       const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), qo = Spec::qofs(i,L);
       if( !Ctx::RIGID ) c.phase_sync(3);
-      if( !Spec::serial(i,L) ){
-        if( Spec::parent(i,L) < 0 ){ Rw = ident3(); pw = v3(0,0,0); vl = v3(0,0,0); om = v3(0,0,0); gd = v3(0,0,-GRAVITY); }
+      if( !SER<Kt>(i,L) ){
+        if( ROOT<Kt>(i,L) ){ Rw = ident3(); pw = v3(0,0,0); vl = v3(0,0,0); om = v3(0,0,0); gd = v3(0,0,-GRAVITY); }
         else {
           const LinkDev &P = m.link[L.parent];
           om = ld3(P.wslot); gd = ld3(P.wslot+3);
           if( m.need_world ){ Rw = ldm(P.branch_slot); pw = ld3(P.branch_slot+9); vl = ld3(P.branch_slot+12); }
         }
       }
-      XF x; x.fast = 0; x.cls = Spec::rcls(i,L); x.c = 1.0; x.s = 0.0;
+      XF x; x.fast = 0; x.cls = CLS<Kt>(i,L); x.sg = ro_sign(x.cls, L.rsg); x.c = 1.0; x.s = 0.0;
       V3 vJ = v3(0,0,0), wJ = v3(0,0,0);
-      switch(Spec::jtype(i,L)){
+      switch(JT<Kt>(i,L)){
       case J_REVOL: {
         double sn, co; sincos(T(qs+qo), &sn, &co);
         Tw(Spec::sc(i,L), sn); Tw(Spec::sc(i,L)+1, co);
         x.s = sn; x.c = co; x.p = org_p(L);
-        if( Spec::rcls(i,L) != RO_GENERAL ) x.fast = 1;
+        if( CLS<Kt>(i,L) != RO_GENERAL ) x.fast = 1;
         else { const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
           x.R = from_cols(co*o0 + sn*o1, co*o1 - sn*o0, col2(Ro)); }
         wJ.z = T(qds+qo);
@@ -413,7 +528,8 @@ struct Core {
         if( fs >= 0 ){ stm(fs, Rw); st3(fs+9, pw); st3(fs+12, vl); st3(fs+15, om); }
       }
       if( bs >= 0 && m.need_world ){ stm(bs, Rw); st3(bs+9, pw); st3(bs+12, vl); }
-    }
+    };
+    links_fwd(m, body);
   }
 
   /* motor + joint friction of a 1-DoF joint: returns tau = driving torque + friction, jm = rotor inertia
@@ -456,8 +572,8 @@ struct Core {
      * ahead, so that their HBM/L2 latency overlaps the articulated-inertia arithmetic of the current link */
     double nx_u = 0.0, nx_prev = 0.0;
     if( NLc > 0 && m.link[NLc-1].mtype != M_NONE ){ nx_u = c.gld(c.st.u, NLc-1); nx_prev = c.gld(c.st.piv_prev, Spec::qofs(NLc-1, m.link[NLc-1])); }
-#pragma unroll (Spec::UNROLL)
-    for(int i=NLc-1;i>=0;i--){
+    auto body = [&](const int i, auto Ktag){
+      using Kt = decltype(Ktag);
       const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L);
       if( !Ctx::RIGID ) c.phase_sync(3);
       const double pf_u = nx_u, pf_prev = nx_prev;
@@ -479,24 +595,25 @@ struct Core {
         B.xx+=aB.xx; B.xy+=aB.xy; B.xz+=aB.xz; B.yx+=aB.yx; B.yy+=aB.yy; B.yz+=aB.yz; B.zx+=aB.zx; B.zy+=aB.zy; B.zz+=aB.zz;
         pf = pf + ld3(a+21); pn = pn + ld3(a+24);
       }
-      if( i+1 < NLc && Spec::serial(i+1, m.link[i+1]) ){
+      /* rolled loops: every link but the tip has a serial child, and the tip adds the zero carry */
+      if( Spec::ROLL != 0 || ( i+1 < NLc && Spec::serial(i+1, m.link[i+1]) ) ){
         A.xx+=kA.xx; A.xy+=kA.xy; A.xz+=kA.xz; A.yy+=kA.yy; A.yz+=kA.yz; A.zz+=kA.zz;
         C.xx+=kC.xx; C.xy+=kC.xy; C.xz+=kC.xz; C.yy+=kC.yy; C.yz+=kC.yz; C.zz+=kC.zz;
         B.xx+=kB.xx; B.xy+=kB.xy; B.xz+=kB.xz; B.yx+=kB.yx; B.yy+=kB.yy; B.yz+=kB.yz; B.zx+=kB.zx; B.zy+=kB.zy; B.zz+=kB.zz;
         pf = pf + kf; pn = pn + kn;
       }
       V3 vJ, wJ;
-      const XF x = joint_xform(m, L, i, vJ, wJ);
+      const XF x = joint_xform<Kt>(m, L, i, vJ, wJ);
       /* velocity-product acceleration (link frame): parent angular velocity in link axes = om - wJ */
       const V3 omp = om - wJ;
       const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
       const V3 za = cross(omp, wJ);
       /* p' = pA + IA zeta */
-      if( Spec::jtype(i,L) != J_FLOAT ){
+      if( JT<Kt>(i,L) != J_FLOAT ){
         pf = pf + mul(A, zl) + mul(B, za);
         pn = pn + tmul(B, zl) + mul(C, za);
       }
-      switch(Spec::jtype(i,L)){
+      switch(JT<Kt>(i,L)){
       case J_REVOL: {
         double jm; const double tau = joint_torque(m, L, i, ref, jm, pf_u, pf_prev);
         const V3 Ul = col2(B), Ua = v3(C.xz, C.yz, C.zz);
@@ -560,7 +677,7 @@ struct Core {
       } break;
       default: break;
       }
-      if( Spec::parent(i,L) < 0 || Spec::jtype(i,L) == J_FLOAT ) continue;
+      if( ROOT<Kt>(i,L) || JT<Kt>(i,L) == J_FLOAT ) return;
       /* X^T Ia X and X^T pa into the parent frame */
       const V3 p = x.p;
       const S3 Ar = xf_sym(x, A), Cr = xf_sym(x, C); const M3 Br = xf_gen(x, B);
@@ -571,7 +688,7 @@ struct Core {
       Cp.xx = Cr.xx + Z1.xx + Z2.xx; Cp.xy = Cr.xy + Z1.xy + Z2.yx; Cp.xz = Cr.xz + Z1.xz + Z2.zx;
       Cp.yy = Cr.yy + Z1.yy + Z2.yy; Cp.yz = Cr.yz + Z1.yz + Z2.zy; Cp.zz = Cr.zz + Z1.zz + Z2.zz;
       const V3 fp = xf_mul(x, pf); const V3 np = xf_mul(x, pn) + cross(p, fp);
-      if( Spec::serial(i,L) ){ kA = Ar; kB = Bp; kC = Cp; kf = fp; kn = np; }
+      if( SER<Kt>(i,L) ){ kA = Ar; kB = Bp; kC = Cp; kf = fp; kn = np; }
       else {
         const int a = m.link[L.parent].accum_slot;
         c.S(a)+=Ar.xx; c.S(a+1)+=Ar.xy; c.S(a+2)+=Ar.xz; c.S(a+3)+=Ar.yy; c.S(a+4)+=Ar.yz; c.S(a+5)+=Ar.zz;
@@ -579,7 +696,8 @@ struct Core {
         c.S(a+15)+=Cp.xx; c.S(a+16)+=Cp.xy; c.S(a+17)+=Cp.xz; c.S(a+18)+=Cp.yy; c.S(a+19)+=Cp.yz; c.S(a+20)+=Cp.zz;
         c.S(a+21)+=fp.x; c.S(a+22)+=fp.y; c.S(a+23)+=fp.z; c.S(a+24)+=np.x; c.S(a+25)+=np.y; c.S(a+26)+=np.z;
       }
-    }
+    };
+    links_bwd(m, body);
   }
 
   /* Runge-Kutta-Gill bookkeeping of one scalar state pair (x, x') with slope (kq, kv) ([EXT A-9]):
@@ -643,8 +761,8 @@ struct Core {
     double nxq[4] = {0,0,0,0};
     const bool pfF = stage >= ST_K2 && stage <= ST_K4, pfX = stage == ST_K2;
     const int NLc = Spec::nl(m), NQc = Spec::nq(m);
-#pragma unroll (Spec::UNROLL)
-    for(int i=0;i<NLc;i++){
+    auto body = [&](const int i, auto Ktag){
+      using Kt = decltype(Ktag);
       const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), qo = Spec::qofs(i,L);
       if( !Ctx::RIGID ) c.phase_sync(3);
       if( i == 0 && Spec::ndof(i,L) == 1 ){
@@ -657,23 +775,23 @@ struct Core {
         if( pfF ){ nxq[0] = c.gld(c.st.q[c.cur^1], jn); nxq[1] = c.gld(c.st.qd[c.cur^1], jn); }
         if( pfX ){ nxq[2] = c.gld(c.st.q[c.cur], jn); nxq[3] = c.gld(c.st.qd[c.cur], jn); }
       }
-      if( !Spec::serial(i,L) ){
-        if( Spec::parent(i,L) < 0 ){ al = v3(0,0,0); aa = v3(0,0,0); om = v3(0,0,0); }
+      if( !SER<Kt>(i,L) ){
+        if( ROOT<Kt>(i,L) ){ al = v3(0,0,0); aa = v3(0,0,0); om = v3(0,0,0); }
         else { const int b = m.link[L.parent].branch_slot; al = ld3(b); aa = ld3(b+3); om = ld3(b+6); }
       }
       V3 vJ, wJ;
-      const XF x = joint_xform(m, L, i, vJ, wJ);
+      const XF x = joint_xform<Kt>(m, L, i, vJ, wJ);
       const V3 omp = xf_tmul(x, om);
       const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
       const V3 za = cross(omp, wJ);
       const V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
-      switch(Spec::jtype(i,L)){
+      switch(JT<Kt>(i,L)){
       case J_REVOL: case J_PRISM: {
         const V3 Ul = ld3(sl), Ua = ld3(sl+3);
         double Dinv, uu; c.TL2(Spec::sc(i,L)+2, Dinv, uu);
         const double acc = Dinv*( uu - (dot(Ul,xl) + dot(Ua,xa)) );
         al = xl + zl; aa = xa + za;
-        if( Spec::jtype(i,L) == J_REVOL ) aa.z += acc; else al.z += acc;
+        if( JT<Kt>(i,L) == J_REVOL ) aa.z += acc; else al.z += acc;
         if( stage == ST_PROBE ){}
         else if( stage >= ST_REF ){ c.gst(c.st.qdd, qo, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; }
         else {
@@ -731,7 +849,8 @@ struct Core {
       om = omp + wJ;
       if( Spec::frame_slot(i,L) >= 0 ){ st3(L.frame_slot+18, al); st3(L.frame_slot+21, aa); }
       if( Spec::branch_slot(i,L) >= 0 ){ st3(L.branch_slot, al); st3(L.branch_slot+3, aa); st3(L.branch_slot+6, om); }
-    }
+    };
+    links_fwd(m, body);
   }
 
 
@@ -783,7 +902,7 @@ struct Core {
       default: break;
       }
       if( L.parent < 0 || L.jtype == J_FLOAT ) break;
-      V3 vJ, wJ; const XF x = joint_xform(m, L, i, vJ, wJ);
+      V3 vJ, wJ; const XF x = joint_xform<TagRT>(m, L, i, vJ, wJ);
       dpf = xf_mul(x, paf); dpn = xf_mul(x, pan) + cross(x.p, dpf);
       i = L.parent;
     }
@@ -791,7 +910,7 @@ struct Core {
       const LinkDev &L = m.link[i]; const int sl = L.slot;
       V3 al = v3(0,0,0), aa = v3(0,0,0);
       if( L.parent >= 0 ){ al = w3(da0+6*L.parent); aa = w3(da0+6*L.parent+3); }
-      V3 vJ, wJ; const XF x = joint_xform(m, L, i, vJ, wJ);
+      V3 vJ, wJ; const XF x = joint_xform<TagRT>(m, L, i, vJ, wJ);
       V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
       switch(L.jtype){
       case J_REVOL: case J_PRISM: {

@@ -108,7 +108,7 @@ template <class T> static T *dalloc(Shard &s, size_t n)
 
 /* kernel variants, one translation unit each (rkfd_kernel_variant.cu): BLOCK_GSCR_RIGID_SPEC_MINB */
 #define RKFD_VARIANT_LIST(X) \
-  X(256,0,0,3,2) X(512,0,0,3,1) X(128,0,0,3,4) X(128,0,0,3,3) X(128,0,0,4,4) X(128,0,0,1,1) X(256,0,0,1,1) X(128,0,0,2,1) \
+  X(128,0,0,5,4) X(256,0,0,5,2) X(512,0,0,5,1) X(256,0,0,6,2) X(256,0,0,3,2) X(512,0,0,3,1) X(128,0,0,3,4) X(128,0,0,3,3) X(128,0,0,4,4) X(128,0,0,1,1) X(256,0,0,1,1) X(128,0,0,2,1) \
   X(128,0,0,0,1) X(256,0,0,0,1) X(64,0,0,0,1) X(32,0,0,0,1) X(64,1,0,0,1) \
   X(128,0,1,0,1) X(256,0,1,0,1) X(64,0,1,0,1) X(32,0,1,0,1) X(64,1,1,0,1)
 #define RKFD_DECL(B,G,R,S,M) extern const KernelVariant rkfd_variant_##B##_##G##_##R##_##S##_##M;
@@ -116,8 +116,9 @@ RKFD_VARIANT_LIST(RKFD_DECL)
 #undef RKFD_DECL
 /* order = preference among variants that keep the same number of environments resident (measured on B200,
  * profiles/): model specialisations (spec > 0) come first and are taken whenever the model matches; among the
- * tensor-memory specialisations (16 resident warps per SM) two 256-thread CTAs beat one 512-thread CTA (barrier
- * stalls) and four 128-thread CTAs (four independent instruction streams through the instruction cache) */
+ * tensor-memory specialisations (16 resident warps per SM) the rolled link loops with four 128-thread CTAs per SM
+ * are fastest (3.2 k instructions stay in the instruction caches); the fully unrolled code (8.7 k instructions)
+ * prefers two 256-thread CTAs (two instruction streams instead of four), one 512-thread CTA loses to barrier stalls */
 #define RKFD_REF(B,G,R,S,M) &rkfd_variant_##B##_##G##_##R##_##S##_##M,
 static const KernelVariant *g_variants[] = { RKFD_VARIANT_LIST(RKFD_REF) };
 #undef RKFD_REF

@@ -63,6 +63,7 @@ struct DevCtx {
   __device__ __forceinline__ int lanes() const { return 32; }
   __device__ __forceinline__ int lane() const { return tid0 & 31; }
   __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+  __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
   __device__ __forceinline__ unsigned long long bcast(unsigned long long x, int src) const { return __shfl_sync(0xffffffffu, x, src); }
   __device__ __forceinline__ double allsum(double x) const {
 #pragma unroll

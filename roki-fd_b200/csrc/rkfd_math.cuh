@@ -72,7 +72,10 @@ RKFD_HD M3 mul_skew(const S3 &m, V3 p){
  * A revolute link frame is R = Ro * Rz(q).  When the constant part Ro is the identity or a quarter turn
  * about x (DH alpha in {0, +90, -90} deg: the usual case), products with R are a planar rotation plus a
  * signed permutation instead of dense 3x3 products.  Everything else uses the dense path. */
-enum RoClass : int { RO_GENERAL = 0, RO_IDENT = 1, RO_RXP = 2 /* Rx(+90): (x,y,z)->(x,-z,y) */, RO_RXM = 3 /* Rx(-90): (x,y,z)->(x,z,-y) */ };
+enum RoClass : int { RO_GENERAL = 0, RO_IDENT = 1, RO_RXP = 2 /* Rx(+90): (x,y,z)->(x,-z,y) */, RO_RXM = 3 /* Rx(-90): (x,y,z)->(x,z,-y) */,
+                     RO_RXS = 4 /* Rx(sg*90), sign sg = +-1 read from the link table at run time (rolled link loops) */ };
+/* sign of the quarter turn: a literal for RXP / RXM (multiplications by it fold away), the table value for RXS */
+RKFD_HD double ro_sign(int cls, double table_sg){ return cls == RO_RXP ? 1.0 : ( cls == RO_RXM ? -1.0 : table_sg ); }
 
 RKFD_HD V3 rz_mul(double c, double s, V3 v){ return v3(c*v.x - s*v.y, s*v.x + c*v.y, v.z); }
 RKFD_HD V3 rz_tmul(double c, double s, V3 v){ return v3(c*v.x + s*v.y, c*v.y - s*v.x, v.z); }
@@ -90,42 +93,40 @@ RKFD_HD M3 rz_gen(double c, double s, const M3 &B){
   r.yx = c*tyx - s*tyy; r.yy = s*tyx + c*tyy; r.yz = tyz;
   r.zx = c*B.zx - s*B.zy; r.zy = s*B.zx + c*B.zy; r.zz = B.zz; return r; }
 /* Ro v, Ro^T v, Ro A Ro^T, Ro B Ro^T, M Ro for the special classes (cls != RO_GENERAL) */
-RKFD_HD V3 ro_mul(int cls, V3 v){ return cls == RO_RXP ? v3(v.x, -v.z, v.y) : ( cls == RO_RXM ? v3(v.x, v.z, -v.y) : v ); }
-RKFD_HD V3 ro_tmul(int cls, V3 v){ return cls == RO_RXP ? v3(v.x, v.z, -v.y) : ( cls == RO_RXM ? v3(v.x, -v.z, v.y) : v ); }
-RKFD_HD S3 ro_sym(int cls, const S3 &A){
+RKFD_HD V3 ro_mul(int cls, double sg, V3 v){ return cls == RO_IDENT ? v : v3(v.x, -sg*v.z, sg*v.y); }
+RKFD_HD V3 ro_tmul(int cls, double sg, V3 v){ return cls == RO_IDENT ? v : v3(v.x, sg*v.z, -sg*v.y); }
+RKFD_HD S3 ro_sym(int cls, double sg, const S3 &A){
   if( cls == RO_IDENT ) return A;
-  const double sg = cls == RO_RXP ? 1.0 : -1.0;       /* rows: x<-x, y<- -sg z, z<- sg y */
-  S3 r; r.xx = A.xx; r.xy = -sg*A.xz; r.xz = sg*A.xy; r.yy = A.zz; r.yz = -A.yz; r.zz = A.yy; return r; }
-RKFD_HD M3 ro_gen(int cls, const M3 &B){
+  S3 r;                                                /* rows: x<-x, y<- -sg z, z<- sg y */ r.xx = A.xx; r.xy = -sg*A.xz; r.xz = sg*A.xy; r.yy = A.zz; r.yz = -A.yz; r.zz = A.yy; return r; }
+RKFD_HD M3 ro_gen(int cls, double sg, const M3 &B){
   if( cls == RO_IDENT ) return B;
-  const double sg = cls == RO_RXP ? 1.0 : -1.0;
   M3 r;
   r.xx = B.xx;     r.xy = -sg*B.xz; r.xz = sg*B.xy;
   r.yx = -sg*B.zx; r.yy = B.zz;     r.yz = -B.zy;
   r.zx = sg*B.yx;  r.zy = -B.yz;    r.zz = B.yy; return r; }
 /* M Ro: columns of the result are M applied to the columns of Ro */
-RKFD_HD M3 mul_ro(int cls, const M3 &M){
-  if( cls == RO_IDENT ) return M;
-  const double sg = cls == RO_RXP ? 1.0 : -1.0;       /* Ro columns: e_x, sg e_z, -sg e_y */
+RKFD_HD M3 mul_ro(int cls, double sg, const M3 &M){
+  if( cls == RO_IDENT ) return M;                     /* Ro columns: e_x, sg e_z, -sg e_y */
   return from_cols(col0(M), sg*col2(M), (-sg)*col1(M)); }
 
 /* link frame w.r.t. its parent */
 struct XF {
   int fast;        /* 1: R = Ro(cls) * Rz(c,s) handled structurally; 0: dense R */
   int cls;
+  double sg;       /* sign of the quarter turn (fast, cls != RO_IDENT) */
   double c, s;
   M3 R;            /* dense rotation (fast == 0) */
   V3 p;            /* origin of the link frame in parent coordinates */
   V3 ptl;          /* R^T p */
 };
-RKFD_HD V3 xf_tmul(const XF &x, V3 v){ return x.fast ? rz_tmul(x.c, x.s, ro_tmul(x.cls, v)) : tmul(x.R, v); }
-RKFD_HD V3 xf_mul(const XF &x, V3 v){ return x.fast ? ro_mul(x.cls, rz_mul(x.c, x.s, v)) : mul(x.R, v); }
-RKFD_HD S3 xf_sym(const XF &x, const S3 &A){ return x.fast ? ro_sym(x.cls, rz_sym(x.c, x.s, A)) : rot_sym(x.R, A); }
-RKFD_HD M3 xf_gen(const XF &x, const M3 &B){ return x.fast ? ro_gen(x.cls, rz_gen(x.c, x.s, B)) : rot_gen(x.R, B); }
+RKFD_HD V3 xf_tmul(const XF &x, V3 v){ return x.fast ? rz_tmul(x.c, x.s, ro_tmul(x.cls, x.sg, v)) : tmul(x.R, v); }
+RKFD_HD V3 xf_mul(const XF &x, V3 v){ return x.fast ? ro_mul(x.cls, x.sg, rz_mul(x.c, x.s, v)) : mul(x.R, v); }
+RKFD_HD S3 xf_sym(const XF &x, const S3 &A){ return x.fast ? ro_sym(x.cls, x.sg, rz_sym(x.c, x.s, A)) : rot_sym(x.R, A); }
+RKFD_HD M3 xf_gen(const XF &x, const M3 &B){ return x.fast ? ro_gen(x.cls, x.sg, rz_gen(x.c, x.s, B)) : rot_gen(x.R, B); }
 /* Rw R */
 RKFD_HD M3 xf_world(const XF &x, const M3 &Rw){
   if( !x.fast ) return mm(Rw, x.R);
-  const M3 T = mul_ro(x.cls, Rw); const V3 t0 = col0(T), t1 = col1(T);
+  const M3 T = mul_ro(x.cls, x.sg, Rw); const V3 t0 = col0(T), t1 = col1(T);
   return from_cols(x.c*t0 + x.s*t1, x.c*t1 - x.s*t0, col2(T)); }
 
 /* angle-axis vector -> rotation matrix (Rodrigues) */

@@ -72,6 +72,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
         const double *cand[3] = {RI, RP, RM}; d.rcls = RO_GENERAL;
         for(int cidx=0;cidx<3;cidx++){ bool ok = true; for(int k=0;k<9;k++) if( std::fabs(d.Ro[k]-cand[cidx][k]) > 1e-14 ) ok = false;
           if( ok ){ d.rcls = cidx+1; std::memcpy(d.Ro, cand[cidx], sizeof d.Ro); break; } }
+        d.rsg = d.rcls == RO_RXP ? 1.0 : ( d.rcls == RO_RXM ? -1.0 : 0.0 );
         for(int k=0;k<3;k++) d.pol[k] = d.Ro[k]*d.po[0] + d.Ro[3+k]*d.po[1] + d.Ro[6+k]*d.po[2];
       }
       { /* Io = Ic - m [c x]^2 = Ic + m (|c|^2 E - c c^T) */

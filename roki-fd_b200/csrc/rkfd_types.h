@@ -36,6 +36,7 @@ struct LinkDev {
   double po[3];        /* org frame position */
   double pol[3];       /* Ro^T po */
   int rcls;            /* RoClass of Ro (rkfd_math.cuh): 0 general, 1 identity, 2/3 quarter turn about x */
+  double rsg;          /* +1 for Rx(+90), -1 for Rx(-90), 0 otherwise (sign read at run time by the rolled specialisation) */
   double mass;
   double com[3];
   double mc[3];        /* mass * com */

@@ -31,6 +31,7 @@ struct HostCtx {
   int lanes() const { return 1; }
   int lane() const { return 0; }
   unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  bool any(bool p) const { return p; }
   template <class T> T bcast(T x, int) const { return x; }
   double allsum(double x) const { return x; }
   void select(int){}
@@ -98,7 +99,7 @@ const char *hostsim_error(HostSim *h){ return h->err.c_str(); }
 int hostsim_nq(HostSim *h){ return h->model.nq; }
 int hostsim_nl(HostSim *h){ return h->model.nl; }
 /* model specialisation the kernel would pick (0: generic); hostsim_use_spec makes hostsim_run use it */
-int hostsim_spec_match(HostSim *h, int tm){ return spec_match(h->model, tm); }
+int hostsim_spec_match(HostSim *h, int tm){ return tm == 2 ? spec_match_rolled(h->model) : spec_match(h->model, tm); }   /* 2: rolled */
 void hostsim_use_spec(HostSim *h, int id){ h->spec = ( id > 0 && (spec_match_mask(h->model) >> id & 1u) ) ? id : 0; }
 int hostsim_nslot(HostSim *h){ return h->model.nslot; }
 int hostsim_nscratch(HostSim *h){ return h->model.nscratch; }
@@ -140,6 +141,9 @@ void hostsim_run(HostSim *h, int mode, int nsteps)
     switch(h->spec){
 #define RKFD_SPEC_X(id, nl, cls, tmv) case id: { ctx.tm = tmv != 0; ctx.tsp.assign(spec_ntspace(id) + 1, std::nan("")); Core<HostCtx, SpecOf<id>::type> core(ctx); core.run(h->model, mode, nsteps); } break;
     RKFD_SPEC_TABLE(RKFD_SPEC_X)
+#undef RKFD_SPEC_X
+#define RKFD_SPEC_X(id, nl) case id: { ctx.tm = true; ctx.tsp.assign(spec_ntspace(id) + 1, std::nan("")); Core<HostCtx, SpecOf<id>::type> core(ctx); core.run(h->model, mode, nsteps); } break;
+    RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
     default: { Core<HostCtx> core(ctx); core.run(h->model, mode, nsteps); } break;
     }

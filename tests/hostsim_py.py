@@ -79,9 +79,9 @@ class HostSim:
         self.B, self.nq, self.nl, self.nslot = B, L.hostsim_nq(self.h), L.hostsim_nl(self.h), L.hostsim_nslot(self.h)
         self.nscratch = L.hostsim_nscratch(self.h)
         # model specialisations the kernel could pick (0: generic): scratch in shared memory / in tensor memory
-        self.spec, self.spec_tm = L.hostsim_spec_match(self.h, 0), L.hostsim_spec_match(self.h, 1)
-        if spec:                                   # "smem" | "tmem": run that specialisation's code path
-            sid = self.spec_tm if spec == "tmem" else self.spec
+        self.spec, self.spec_tm, self.spec_rolled = (L.hostsim_spec_match(self.h, k) for k in (0, 1, 2))
+        if spec:                                   # "smem" | "tmem" | "rolled": run that specialisation's code path
+            sid = {"smem": self.spec, "tmem": self.spec_tm, "rolled": self.spec_rolled}[spec]
             assert sid > 0, "model matches no compiled specialisation"
             L.hostsim_use_spec(self.h, sid)
 

@@ -226,6 +226,25 @@ def test_specialised_core_is_bit_identical(name):
                 assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("name", ["c2_arm7", "c3_arm7_penalty"])
+def test_rolled_specialisation_matches_generic(name):
+    """The rolled specialisation reads the sign of each quarter-turn frame from the link table at run time
+    (multiplications by +-1): same equations, products may be contracted differently -> agreement to rounding."""
+    w = SPEC_WORLDS[name][0]()
+    B, nsteps = 16, 30
+    q, qd, u = ch.sample_state(w, B, seed=13)
+    out = []
+    for spec in (None, "rolled"):
+        hs = HostSim(w, B, spec=spec)
+        assert hs.spec_rolled == 5
+        hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(nsteps)
+        out.append((hs.get_state(), hs.get_contact(), hs.get_pivot()))
+    (q0, qd0, a0), (c0), (p0) = out[0]
+    (q1, qd1, a1), (c1), (p1) = out[1]
+    assert relerr(q1, q0) < 1e-12 and relerr(qd1, qd0) < 1e-11 and relerr(a1, a0) < 1e-9
+    assert (c0[0] == c1[0]).all() and (p0[0] == p1[0]).all()
+
+
 def test_specialisation_not_picked_for_other_shapes():
     assert HostSim(ch.world_c5(base_z=0.1), 1).spec == 0                      # rigid pairs
     assert HostSim(ch.World(chains=[ch.box(), ch.floor_soft()]), 1).spec == 0  # float joint
