@@ -280,7 +280,7 @@ def main():
                              "algorithmic_flop_per_env_step": ALG_FLOP}}
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_envs, n_steps = 512 * cores, 20
+        n_envs, n_steps = 1024 * cores, 400       # ~10-20 s of CPU work on every host core (settling included)
         ow, cq, cqd, cu = cpu_settled_state(world, ch, n_envs)
         v, used, dt = cpu_baseline_run(ow, cq, cqd, cu, n_steps)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": "port",

@@ -344,3 +344,40 @@ def test_async_transfers_match_synchronous(capi):
     for a, b in zip(ref, (oq.numpy(), oqd.numpy(), oqdd.numpy())):
         assert np.array_equal(a, b)
     fd.destroy()
+
+
+# (RKFD_SPEC, RKFD_FORCE_BLOCK, RKFD_FORCE_MINB): every compiled specialisation that C2/C3 (the 7-DoF arm) can run on
+ARM7_VARIANTS = [(5, 128, 4), (5, 256, 2), (5, 512, 1), (3, 256, 2), (3, 512, 1), (3, 128, 4), (3, 128, 3),
+                 (1, 128, 1), (1, 256, 1), (0, 128, 1)]
+
+
+@pytest.mark.parametrize("variant", ARM7_VARIANTS, ids=lambda v: "spec%d_block%d_minb%d" % v)
+def test_kernel_variants_agree(capi, oracle, monkeypatch, variant):
+    """Every kernel variant of the serial-revolute specialisations (unrolled / rolled link loops, scratch in shared
+    or tensor memory, 8-16 resident warps per SM) against the oracle after a committing evaluation + 25 steps of C3
+    with contacts, and against the generic table-driven kernel (same arithmetic: agreement to rounding).  The
+    batch covers several CTAs per SM so that co-resident CTAs share the SM's tensor memory."""
+    spec, block, minb = variant
+    w = ch.world_c3(base_z=0.1)
+    B = 148 * 4 * 128 + 77
+    q, qd, u = ch.sample_state(w, B, seed=21)
+
+    def run(env):
+        for k in ("RKFD_SPEC", "RKFD_FORCE_BLOCK", "RKFD_FORCE_MINB"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, str(v))
+        fd = gpu_world(capi, w, q, qd, u)
+        fd.update_n(25)
+        out = fd.batch_get_state(), fd.batch_get_contact(), fd.batch_get_status()
+        fd.destroy()
+        return out
+
+    (gq, gqd, gqdd), (ga, gt, gr, gf), status = run({"RKFD_SPEC": spec, "RKFD_FORCE_BLOCK": block, "RKFD_FORCE_MINB": minb})
+    (rq, rqd, rqdd), (ra, rt, rr, rf), _ = run({"RKFD_SPEC": 0})
+    assert (status == 0).all()
+    assert relerr(gq, rq) < 1e-11 and relerr(gqd, rqd) < 1e-10 and relerr(gqdd, rqdd) < 1e-8
+    assert (ga == ra).mean() > 0.9999 and ga.sum() > 0
+    n = 48
+    oq, oqd, oqdd, _ = oracle.OracleWorld(w).batch_run(q[:n], qd[:n], u[:n], nsteps=25)
+    assert relerr(gq[:n], oq) < 1e-9 and relerr(gqd[:n], oqd) < 1e-8
