@@ -409,13 +409,13 @@ struct Core {
         const PairDev &pr = m.pair[pi]; const BoxDev &bx = m.box[pr.box];
         const M3 Rb = box_R(bx);
         const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
-        /* (A) detection */
+        /* (A) detection: vertex in the box frame = Rb^T (pw - pb) + (Rb^T Rw) vloc, the two factors once per pair */
+        const M3 Mb = tmm(Rb, Rw); const V3 ob = tmul(Rb, pw - pb);
         unsigned long long in = 0;
         for(int k=0;k<cl.nvert;k++){
           const int s = pr.sofs + k;
           const V3 vloc = v3(m.vert[3*(cl.vofs+k)], m.vert[3*(cl.vofs+k)+1], m.vert[3*(cl.vofs+k)+2]);
-          const V3 vw = pw + mul(Rw, vloc);
-          const V3 vb = tmul(Rb, vw - pb);
+          const V3 vb = ob + mul(Mb, vloc);
           const double dx = bx.half[0]-fabs(vb.x), dy = bx.half[1]-fabs(vb.y), dz = bx.half[2]-fabs(vb.z);
           const bool inside = (dx > -ZTOL) && (dy > -ZTOL) && (dz > -ZTOL);
           if( inside ) in |= 1ull << k;
@@ -471,7 +471,13 @@ struct Core {
   }
 
   /* ---- pass 1: outward kinematics + collision + penalty */
+  /* Worlds without rigid pairs: gravity enters as the acceleration (0,0,+g) of the root's parent instead of a force at
+   * every centre of mass (same q''; the true link accelerations, which only the rigid-contact solve needs, are
+   * not formed): no gravity direction to propagate outward, no gravity terms in the bias forces. */
+  static RKFD_HD bool grav_acc(const ModelDev &m){ return Spec::NL != 0 ? true : !m.has_rigid; }
+
   RKFD_HD void pass1(const ModelDev &m, bool ref){
+    const bool gacc = grav_acc(m);
     M3 Rw = ident3(); V3 pw = v3(0,0,0), vl = v3(0,0,0), om = v3(0,0,0), gd = v3(0,0,-GRAVITY);
     const int qs = rk0, qds = rk0 + Spec::nq(m);
     auto body = [&](const int i, auto Ktag){
@@ -513,14 +519,16 @@ struct Core {
       } break;
       default: x.R = org_R(L); x.p = org_p(L); break;
       }
-      const V3 om_n = xf_tmul(x, om) + wJ;
-      const V3 gd_n = xf_tmul(x, gd);
+      V3 om_n = xf_tmul(x, om);
+      if( JT<Kt>(i,L) == J_REVOL ) om_n.z += wJ.z; else om_n = om_n + wJ;      /* additions of literal zeros are not folded away */
       if( m.need_world ){
-        const V3 vl_n = xf_tmul(x, vl + cross(om, x.p)) + vJ;
+        V3 vl_n = xf_tmul(x, vl + cross(om, x.p));
+        if( JT<Kt>(i,L) != J_REVOL ) vl_n = vl_n + vJ;
         pw = pw + mul(Rw, x.p); Rw = xf_world(x, Rw); vl = vl_n;
       }
-      om = om_n; gd = gd_n;
-      st3(Spec::wslot(i,L), om); st3(Spec::wslot(i,L)+3, gd);
+      om = om_n;
+      st3(Spec::wslot(i,L), om);
+      if( !gacc ){ gd = xf_tmul(x, gd); st3(Spec::wslot(i,L)+3, gd); }
       const int wx = Spec::wext_slot(i,L), fs = Spec::frame_slot(i,L), bs = Spec::branch_slot(i,L);
       if( wx >= 0 ){
         const V6 w = contacts(m, L, Rw, pw, vl, om, ref);
@@ -545,7 +553,7 @@ struct Core {
       if( L.mtype == M_DC ){
         const double tin = L.m_tin*e, treg = L.m_reg*v;
         jm = L.m_jm; tdrive = tin - treg;
-        tf = jm; tf *= -v / m.dt; tf -= tin; tf += treg; tf += prev_in;
+        tf = jm; tf *= -v * m.inv_dt; tf -= tin; tf += treg; tf += prev_in;
         double fmax;
         if( !(piv & (1u<<j)) ) fmax = L.sfriction;
         else {
@@ -572,21 +580,23 @@ struct Core {
      * ahead, so that their HBM/L2 latency overlaps the articulated-inertia arithmetic of the current link */
     double nx_u = 0.0, nx_prev = 0.0;
     if( NLc > 0 && m.link[NLc-1].mtype != M_NONE ){ nx_u = c.gld(c.st.u, NLc-1); nx_prev = c.gld(c.st.piv_prev, Spec::qofs(NLc-1, m.link[NLc-1])); }
+    const bool gacc = grav_acc(m);
     auto body = [&](const int i, auto Ktag){
       using Kt = decltype(Ktag);
       const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L);
       if( !Ctx::RIGID ) c.phase_sync(3);
       const double pf_u = nx_u, pf_prev = nx_prev;
       if( i > 0 && m.link[i-1].mtype != M_NONE ){ nx_u = c.gld(c.st.u, i-1); nx_prev = c.gld(c.st.piv_prev, Spec::qofs(i-1, m.link[i-1])); }
-      const V3 om = ld3(Spec::wslot(i,L)), gd = ld3(Spec::wslot(i,L)+3);
+      const V3 om = ld3(Spec::wslot(i,L));
       const V3 mc = v3(L.mc[0],L.mc[1],L.mc[2]);
       S3 A, C; M3 B;
       A.xx = L.mass; A.xy = 0; A.xz = 0; A.yy = L.mass; A.yz = 0; A.zz = L.mass;
       B.xx = 0; B.xy = mc.z; B.xz = -mc.y; B.yx = -mc.z; B.yy = 0; B.yz = mc.x; B.zx = mc.y; B.zy = -mc.x; B.zz = 0;
       C.xx = L.Io[0]; C.xy = L.Io[1]; C.xz = L.Io[2]; C.yy = L.Io[3]; C.yz = L.Io[4]; C.zz = L.Io[5];
       /* bias ( w x (w x mc) ; w x (Io w) ) minus gravity (m gd ; mc x gd) minus external wrench */
-      V3 pf = cross(om, cross(om, mc)) - L.mass*gd;
-      V3 pn = cross(om, mul(C, om)) - cross(mc, gd);
+      V3 pf = cross(om, cross(om, mc));
+      V3 pn = cross(om, mul(C, om));
+      if( !gacc ){ const V3 gd = ld3(Spec::wslot(i,L)+3); pf = pf - L.mass*gd; pn = pn - cross(mc, gd); }
       if( Spec::wext_slot(i,L) >= 0 ){ pf = pf - ld3(Spec::wext_slot(i,L)); pn = pn - ld3(Spec::wext_slot(i,L)+3); }
       if( Spec::accum_slot(i,L) >= 0 ){
         const int a = L.accum_slot; const S3 aA = lds(a), aC = lds(a+15); const M3 aB = ldm(a+6);
@@ -605,11 +615,19 @@ struct Core {
       V3 vJ, wJ;
       const XF x = joint_xform<Kt>(m, L, i, vJ, wJ);
       /* velocity-product acceleration (link frame): parent angular velocity in link axes = om - wJ */
-      const V3 omp = om - wJ;
-      const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
-      const V3 za = cross(omp, wJ);
       /* p' = pA + IA zeta */
-      if( JT<Kt>(i,L) != J_FLOAT ){
+      if( JT<Kt>(i,L) == J_REVOL ){
+        /* revolute: vJ = 0, wJ = (0,0,q'), so zeta_a = (wp.y q', -wp.x q', 0); written out because products with the
+         * literal zeros are not folded by the compiler */
+        const V3 omp = v3(om.x, om.y, om.z - wJ.z);
+        const V3 zl = cross(omp, cross(omp, x.ptl));
+        const double zax = omp.y*wJ.z, zay = -omp.x*wJ.z;
+        pf = pf + mul(A, zl) + v3(B.xx*zax + B.xy*zay, B.yx*zax + B.yy*zay, B.zx*zax + B.zy*zay);
+        pn = pn + tmul(B, zl) + v3(C.xx*zax + C.xy*zay, C.xy*zax + C.yy*zay, C.xz*zax + C.yz*zay);
+      } else if( JT<Kt>(i,L) != J_FLOAT ){
+        const V3 omp = om - wJ;
+        const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
+        const V3 za = cross(omp, wJ);
         pf = pf + mul(A, zl) + mul(B, za);
         pn = pn + tmul(B, zl) + mul(C, za);
       }
@@ -776,22 +794,23 @@ struct Core {
         if( pfX ){ nxq[2] = c.gld(c.st.q[c.cur], jn); nxq[3] = c.gld(c.st.qd[c.cur], jn); }
       }
       if( !SER<Kt>(i,L) ){
-        if( ROOT<Kt>(i,L) ){ al = v3(0,0,0); aa = v3(0,0,0); om = v3(0,0,0); }
+        if( ROOT<Kt>(i,L) ){ al = v3(0,0, grav_acc(m) ? GRAVITY : 0.0); aa = v3(0,0,0); om = v3(0,0,0); }
         else { const int b = m.link[L.parent].branch_slot; al = ld3(b); aa = ld3(b+3); om = ld3(b+6); }
       }
       V3 vJ, wJ;
       const XF x = joint_xform<Kt>(m, L, i, vJ, wJ);
       const V3 omp = xf_tmul(x, om);
-      const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
-      const V3 za = cross(omp, wJ);
+      V3 zl, za;
+      if( JT<Kt>(i,L) == J_REVOL ){ zl = cross(omp, cross(omp, x.ptl)); za = v3(omp.y*wJ.z, -omp.x*wJ.z, 0.0); }
+      else { zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ); za = cross(omp, wJ); }
       const V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
       switch(JT<Kt>(i,L)){
       case J_REVOL: case J_PRISM: {
         const V3 Ul = ld3(sl), Ua = ld3(sl+3);
         double Dinv, uu; c.TL2(Spec::sc(i,L)+2, Dinv, uu);
         const double acc = Dinv*( uu - (dot(Ul,xl) + dot(Ua,xa)) );
-        al = xl + zl; aa = xa + za;
-        if( JT<Kt>(i,L) == J_REVOL ) aa.z += acc; else al.z += acc;
+        al = xl + zl;
+        if( JT<Kt>(i,L) == J_REVOL ){ aa = v3(xa.x + za.x, xa.y + za.y, xa.z + acc); } else { aa = xa + za; al.z += acc; }
         if( stage == ST_PROBE ){}
         else if( stage >= ST_REF ){ c.gst(c.st.qdd, qo, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; }
         else {
@@ -846,7 +865,7 @@ struct Core {
       } break;
       default: al = xl + zl; aa = xa + za; break;
       }
-      om = omp + wJ;
+      if( JT<Kt>(i,L) == J_REVOL ) om = v3(omp.x, omp.y, omp.z + wJ.z); else om = omp + wJ;
       if( Spec::frame_slot(i,L) >= 0 ){ st3(L.frame_slot+18, al); st3(L.frame_slot+21, aa); }
       if( Spec::branch_slot(i,L) >= 0 ){ st3(L.branch_slot, al); st3(L.branch_slot+3, aa); st3(L.branch_slot+6, om); }
     };

@@ -65,8 +65,12 @@ RKFD_HD M3 rot_gen(const M3 &R, const M3 &B){ return mm(mm(R,B), transpose(R)); 
 /* [p x] M  (rows of the result are cross products of p with the columns of M) */
 RKFD_HD M3 skew_mul(V3 p, const M3 &m){ return from_cols(cross(p,col0(m)), cross(p,col1(m)), cross(p,col2(m))); }
 /* M [p x] : column j = M (p x e_j) */
-RKFD_HD M3 mul_skew(const S3 &m, V3 p){
-  return from_cols(mul(m, v3(0, p.z, -p.y)), mul(m, v3(-p.z, 0, p.x)), mul(m, v3(p.y, -p.x, 0))); }
+RKFD_HD M3 mul_skew(const S3 &m, V3 p){     /* written out: products with the zero entries of [p x] are not folded by the compiler */
+  M3 r;
+  r.xx = m.xy*p.z - m.xz*p.y; r.yx = m.yy*p.z - m.yz*p.y; r.zx = m.yz*p.z - m.zz*p.y;
+  r.xy = m.xz*p.x - m.xx*p.z; r.yy = m.yz*p.x - m.xy*p.z; r.zy = m.zz*p.x - m.xz*p.z;
+  r.xz = m.xx*p.y - m.xy*p.x; r.yz = m.xy*p.y - m.yy*p.x; r.zz = m.xz*p.y - m.yz*p.x;
+  return r; }
 
 /* ---- structured link transforms ------------------------------------------------------------------
  * A revolute link frame is R = Ro * Rz(q).  When the constant part Ro is the identity or a quarter turn

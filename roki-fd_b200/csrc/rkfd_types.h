@@ -76,6 +76,7 @@ struct ModelDev {
   int slot_pair[MAX_SLOTS], slot_vert[MAX_SLOTS];
   int rk_slot;         /* first slot of the RKG stage state: QS[nq], QDS[nq], PQ[nq], PQD[nq] */
   double dt, friction_weight;
+  double inv_dt;       /* 1/dt */
   double sc_sin[MAX_PYRAMID], sc_cos[MAX_PYRAMID];
   LinkDev link[MAX_LINKS];
   CellDev cell[MAX_CELLS];
