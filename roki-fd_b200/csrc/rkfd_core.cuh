@@ -1299,15 +1299,20 @@ struct Core {
     if( !Ctx::RIGID ) c.phase_sync(2);
     c.tfence();
     if( Ctx::RIGID ){
-      /* rigid pairs in contact (reference rkfd_vert.c:385-386): any lane of the warp -> cooperative solve */
+      /* rigid pairs in contact (reference rkfd_vert.c:385-386): any lane of the warp -> cooperative solve.
+       * Round 0 = rkFDUpdateAccBias (rkfd_util.c:149-161): the inward/outward passes without contact forces, then the
+       * solve; round 1 = the evaluation proper.  One rolled loop so that the passes exist once in the kernel. */
       const unsigned act = c.ballot( RKFD_POPC64(cfl & m.rigid_mask) > 0 );
-      if( act ){
-        pass2(m, false); pass3(m, ST_PROBE);      /* rkFDUpdateAccBias (rkfd_util.c:149-161) */
-        rigid_solve(m, ref, act);
+#pragma unroll 1
+      for(int round = act ? 0 : 1; round < 2; round++){
+        pass2(m, round ? ref : false);
+        pass3(m, round ? stage : (int)ST_PROBE);
+        if( round == 0 ) rigid_solve(m, ref, act);
       }
+      return;
     }
     pass2(m, ref);
-    if( !Ctx::RIGID ) c.phase_sync(2);
+    c.phase_sync(2);
     c.tfence();
     pass3(m, stage);
   }
