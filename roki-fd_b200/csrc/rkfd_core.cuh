@@ -59,6 +59,9 @@ constexpr int ACCUM_SLOTS = 27;    /* A(6) B(9) C(6) pf(3) pn(3) */
 constexpr int WEXT_SLOTS = 6;
 constexpr int FRAME_SLOTS = 24;    /* rigid worlds, links with cells: Rw(9) pw(3) vl(3) w(3) a(6) */
 constexpr int GEO_DOUBLES = 27;    /* per rigid contact: vw n t1 t2 d vel prob rl (8 x 3), slot, link, pair */
+/* per-environment workspace of the single-link MLCP path: Lambda (6x6, column-major) then per contact
+ * g (3x6) h (3x6) b (3) diag (3) f (3) rho (3) prob (3) mu slot */
+constexpr int W1_CT = 36, W1_CTN = 53;
 
 enum StageMode : int { ST_K1 = 0, ST_K2 = 1, ST_K3 = 2, ST_K4 = 3, ST_REF = 4, ST_EVAL = 5, ST_EVAL_REF = 6,
                        ST_PROBE = 7 /* acceleration pass of rkFDUpdateAccBias: no integrator bookkeeping, no q'' output */ };
@@ -954,7 +957,210 @@ struct Core {
     }
   }
 
+  /* =====================================================================================================
+   * MLCP when every rigid contact of the environment sits on ONE link (an end effector on the floor, a free
+   * body on the floor): the Delassus matrix factors as A = H Lambda H^T with the 6x6 inverse operational-space
+   * inertia Lambda of that link and one 6-vector h = (axis, rho x axis) per contact row, so that
+   *   - 6 cached-ABA probes (unit wrench components at the link origin) replace the 3N per-contact probes,
+   *   - projected Gauss-Seidel runs on the 6-vector u = Lambda * (sum of contact wrenches): a row product is
+   *     h.u and a force update adds g = Lambda h times the change - no N x N matrix exists,
+   *   - the probes of up to 5 environments of the warp run at once (lanes over (environment, component)),
+   *     the sweeps run one environment per lane.
+   * Same equations as rkfd_mlcp.c:104-284 (including the row offsets of the friction sweep and the
+   * unconditional commit of the friction type); sums are formed in a different order, so results agree with the
+   * dense path to rounding.
+   * ===================================================================================================== */
+  RKFD_HD V3 w13(int o){ return v3(c.W1(o), c.W1(o+1), c.W1(o+2)); }
+  RKFD_HD void sw13(int o, V3 v){ c.W1(o)=v.x; c.W1(o+1)=v.y; c.W1(o+2)=v.z; }
+
+  /* acceleration response (link frame) of link Lc to the bias change (dpf, dpn) on itself ([EXT A-5]) */
+  RKFD_HD void probe_link(const ModelDev &m, int Lc, V3 dpf, V3 dpn, V3 &ral, V3 &raa){
+    double du[6*MAX_LINKS]; int pth[MAX_LINKS]; int np = 0;
+    for(int i=Lc;;){
+      const LinkDev &L = m.link[i]; const int sl = L.slot;
+      pth[np] = i;
+      V3 paf = dpf, pan = dpn;
+      switch(L.jtype){
+      case J_REVOL: case J_PRISM: {
+        const double d = L.jtype == J_REVOL ? -dpn.z : -dpf.z;
+        du[6*np] = d;
+        const double k = T(Spec::sc(i,L)+2)*d;
+        paf = dpf + k*ld3(sl); pan = dpn + k*ld3(sl+3);
+      } break;
+      case J_SPHER: {
+        const M3 E = tmm(ldm(sl+27), org_R(L));
+        const V3 d = -tmul(E, dpn);
+        du[6*np] = d.x; du[6*np+1] = d.y; du[6*np+2] = d.z;
+        const V3 k = mul(lds(sl+18), d);
+        paf = dpf + mul(ldm(sl), k); pan = dpn + mul(ldm(sl+9), k);
+      } break;
+      case J_FLOAT: du[6*np]=dpf.x; du[6*np+1]=dpf.y; du[6*np+2]=dpf.z; du[6*np+3]=dpn.x; du[6*np+4]=dpn.y; du[6*np+5]=dpn.z; break;
+      default: break;
+      }
+      np++;
+      if( L.parent < 0 || L.jtype == J_FLOAT ) break;
+      V3 vJ, wJ; const XF x = joint_xform<TagRT>(m, L, i, vJ, wJ);
+      dpf = xf_mul(x, paf); dpn = xf_mul(x, pan) + cross(x.p, dpf);
+      i = L.parent;
+    }
+    V3 al = v3(0,0,0), aa = v3(0,0,0);
+    for(int q=np-1;q>=0;q--){
+      const int i = pth[q]; const LinkDev &L = m.link[i]; const int sl = L.slot;
+      V3 vJ, wJ; const XF x = joint_xform<TagRT>(m, L, i, vJ, wJ);
+      V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
+      switch(L.jtype){
+      case J_REVOL: case J_PRISM: {
+        const double acc = T(Spec::sc(i,L)+2)*( du[6*q] - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
+        if( L.jtype == J_REVOL ) xa.z += acc; else xl.z += acc;
+      } break;
+      case J_SPHER: {
+        const V3 rhs = v3(du[6*q],du[6*q+1],du[6*q+2]) - (tmul(ldm(sl), xl) + tmul(ldm(sl+9), xa));
+        xa = xa + mul(tmm(ldm(sl+27), org_R(L)), mul(lds(sl+18), rhs));
+      } break;
+      case J_FLOAT: {   /* da = -IA^-1 dp */
+        double r[6] = {0,0,0,0,0,0}; int k = 0;
+        for(int a=0;a<6;a++) for(int b=a;b<6;b++){ const double iv = c.S(sl+18+k); r[a] -= iv*du[6*q+b]; if( b != a ) r[b] -= iv*du[6*q+a]; k++; }
+        xl = v3(r[0],r[1],r[2]); xa = v3(r[3],r[4],r[5]);
+      } break;
+      default: break;
+      }
+      al = xl; aa = xa;
+    }
+    ral = al; raa = aa;
+  }
+
+  RKFD_HD void rigid_mlcp_single(const ModelDev &m, bool ref, unsigned act){
+    const int nlanes = c.lanes(), lane = c.lane();
+    const int Lc = m.rigid_link; const LinkDev &LL = m.link[Lc];
+    /* ---- Lambda: lanes over (environment of the warp with contacts, wrench component) */
+    const int nact = RKFD_POPC64((unsigned long long)act);
+    for(int t=lane; t<6*nact; t+=nlanes){
+      const int j = t/6, comp = t - 6*j;
+      unsigned a = act; for(int q=0;q<j;q++) a &= a - 1;
+      c.select(RKFD_FFS32(a) - 1);
+      const M3 Rw = ldm(LL.frame_slot);
+      const int ax = comp < 3 ? comp : comp - 3;
+      const V3 el = ax == 0 ? v3(Rw.xx, Rw.xy, Rw.xz) : ( ax == 1 ? v3(Rw.yx, Rw.yy, Rw.yz) : v3(Rw.zx, Rw.zy, Rw.zz) );   /* Rw^T e_ax */
+      const V3 z = v3(0,0,0);
+      V3 ral, raa;
+      probe_link(m, Lc, comp < 3 ? -el : z, comp < 3 ? z : -el, ral, raa);
+      sw13(6*comp, mul(Rw, ral)); sw13(6*comp+3, mul(Rw, raa));
+      c.unselect();
+    }
+    c.gsync();
+    /* ---- one environment per lane from here on */
+    const unsigned long long fl = cfl;
+    const int N = RKFD_POPC64(fl & m.rigid_mask);
+    if( N == 0 ) return;
+    double lam[36];
+#pragma unroll
+    for(int i=0;i<36;i++) lam[i] = c.W1(i);            /* lam[6*col + row] */
+    const M3 Rw = ldm(LL.frame_slot); const V3 pw = ld3(LL.frame_slot+9), vl = ld3(LL.frame_slot+12), om = ld3(LL.frame_slot+15);
+    const V3 al = ld3(LL.frame_slot+18), aa = ld3(LL.frame_slot+21);
+    const V3 vlw = mul(Rw, vl), omw = mul(Rw, om);
+    /* contacts in (pair, vertex) order: geometry, rows h, responses g = Lambda h, bias b (rkfd_mlcp.c:104-188) */
+    { int k = 0;
+      for(int s=0;s<m.nslot;s++){
+        if( !( (fl & m.rigid_mask) >> (2*s) & 1ull ) ) continue;
+        const PairDev &pr = m.pair[m.slot_pair[s]]; const CellDev &cl = m.cell[pr.cell]; const BoxDev &bx = m.box[pr.box];
+        const int vi = cl.vofs + m.slot_vert[s];
+        const V3 rl = v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2]);
+        const M3 Rb = box_R(bx); const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
+        const V3 vw = pw + mul(Rw, rl), vb = tmul(Rb, vw - pb);
+        V3 ax[3], prob;
+        box_face(bx, Rb, vb, bx.half[0]-fabs(vb.x), bx.half[1]-fabs(vb.y), bx.half[2]-fabs(vb.z), ax[0], ax[1], ax[2], prob);
+        const V3 refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
+        const V3 d = vw - (pb + mul(Rb, refb));
+        const V3 rho = vw - pw;
+        const V3 vel = vlw + cross(omw, rho);
+        /* rkFDLinkPointWldAcc (rkfd_util.c:92-101): R ( a + alpha x r + w x (w x r) ) */
+        const V3 r = tmul(Rw, rho);
+        const V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r)));
+        const double mu = ( (fl >> (2*s+1)) & 1ull ) ? pr.KF : pr.SF;
+        const int o = W1_CT + W1_CTN*k;
+        for(int i=0;i<3;i++){
+          const V3 hl = ax[i], ha = cross(rho, ax[i]);
+          const double h[6] = {hl.x, hl.y, hl.z, ha.x, ha.y, ha.z};
+          double g[6], dg = 0;
+#pragma unroll
+          for(int rr=0;rr<6;rr++){ double sum = 0;
+#pragma unroll
+            for(int cc=0;cc<6;cc++) sum += lam[6*cc+rr]*h[cc];
+            g[rr] = sum; }
+#pragma unroll
+          for(int rr=0;rr<6;rr++){ dg += h[rr]*g[rr]; c.W1(o+6*i+rr) = g[rr]; c.W1(o+18+6*i+rr) = h[rr]; }
+          /* velocity level + compensation (rkfd_mlcp.c:146-188); relaxation on the diagonal */
+          const double comp = pr.K * ( i == 0 ? 1.0 : mu ) * dot(d, ax[i]);
+          c.W1(o+36+i) = dot(ax[i], accp)*m.dt + dot(vel, ax[i]) + comp;
+          c.W1(o+39+i) = dg + pr.L;
+          c.W1(o+42+i) = 0.0;
+        }
+        sw13(o+45, rho); sw13(o+48, prob); c.W1(o+51) = mu; c.W1(o+52) = (double)s;
+        k++;
+      } }
+    /* ---- projected Gauss-Seidel on u = Lambda * (sum of contact wrenches) (rkfd_mlcp.c:190-249) */
+    double u[6] = {0,0,0,0,0,0};
+    for(int cnt=0;cnt<m.max_iter;cnt++){
+      for(int k=0;k<N;k++){
+        const int o = W1_CT + W1_CTN*k; const double L = m.pair[m.slot_pair[(int)c.W1(o+52)]].L;
+        double sum = 0;
+#pragma unroll
+        for(int rr=0;rr<6;rr++) sum += c.W1(o+18+rr)*u[rr];
+        const double fo = c.W1(o+42), aoo = c.W1(o+39);
+        sum += L*fo;
+        double ff = -( c.W1(o+36) + sum - aoo*fo ) / aoo;
+        ff = ff < ZTOL ? 0.0 : ff;
+        const double dlt = ff - fo;
+        c.W1(o+42) = ff;
+#pragma unroll
+        for(int rr=0;rr<6;rr++) u[rr] += c.W1(o+rr)*dlt;
+      }
+      for(int k=0;k<N;k++){
+        const int o = W1_CT + W1_CTN*k; const double L = m.pair[m.slot_pair[(int)c.W1(o+52)]].L;
+        double ff[2];
+        for(int i=0;i<2;i++){           /* rows offset+0 / offset+1, as the reference reads them (:219-225) */
+          const double aii = c.W1(o+39+i), fi = c.W1(o+42+i);
+          double sum = 0;
+#pragma unroll
+          for(int rr=0;rr<6;rr++) sum += c.W1(o+18+6*i+rr)*u[rr];
+          sum += L*fi;
+          ff[i] = fabs(aii) < ZTOL ? 0.0 : -( c.W1(o+36+i) + sum - aii*fi ) / aii;
+        }
+        const double mu = c.W1(o+51), fn = c.W1(o+42);
+        const double fnorm = ff[0]*ff[0] + ff[1]*ff[1];
+        double fs = (mu*fn)*(mu*fn), f1, f2;
+        if( fnorm < ZTOL || fs < ZTOL ){ f1 = 0.0; f2 = 0.0; }
+        else if( fnorm > fs ){ fs /= fnorm; f1 = ff[0]*fs; f2 = ff[1]*fs; }
+        else { f1 = ff[0]; f2 = ff[1]; }
+        const double d1 = f1 - c.W1(o+43), d2 = f2 - c.W1(o+44);
+        c.W1(o+43) = f1; c.W1(o+44) = f2;
+#pragma unroll
+        for(int rr=0;rr<6;rr++) u[rr] += c.W1(o+6+rr)*d1 + c.W1(o+12+rr)*d2;
+      }
+    }
+    /* ---- f /= dt; forces, wrench on the link, friction state (rkfd_mlcp.c:252-284: committed regardless of
+     * doUpRef, world components of f as "normal"/"tangential" - mirrored) */
+    unsigned long long nfl = fl;
+    V3 wl = v3(0,0,0), wa = v3(0,0,0);
+    for(int k=0;k<N;k++){
+      const int o = W1_CT + W1_CTN*k; const int s = (int)c.W1(o+52);
+      const V3 fw = (c.W1(o+42)/m.dt)*w13(o+18) + (c.W1(o+43)/m.dt)*w13(o+24) + (c.W1(o+44)/m.dt)*w13(o+30);
+      const double mu = c.W1(o+51);
+      const bool kin = sqrt(fw.y*fw.y + fw.z*fw.z) > mu*fw.x - ZTOL;
+      if( kin ){ nfl |= 2ull << (2*s); const V3 prob = w13(o+48); c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
+      else nfl &= ~(2ull << (2*s));
+      /* rkFDContactForcePushWrench (rkfd_util.c:268-282) */
+      const V3 pos = tmul(Rw, w13(o+45)), fll = tmul(Rw, fw);
+      wl = wl + fll; wa = wa + cross(pos, fll);
+      if( ref ){ c.gst(c.st.cf,3*s,fw.x); c.gst(c.st.cf,3*s+1,fw.y); c.gst(c.st.cf,3*s+2,fw.z); }
+    }
+    c.S(LL.wext_slot) += wl.x; c.S(LL.wext_slot+1) += wl.y; c.S(LL.wext_slot+2) += wl.z;
+    c.S(LL.wext_slot+3) += wa.x; c.S(LL.wext_slot+4) += wa.y; c.S(LL.wext_slot+5) += wa.z;
+    cfl = nfl;
+  }
+
   RKFD_HD void rigid_solve(const ModelDev &m, bool ref, unsigned act){
+    if( m.rigid_link >= 0 ){ rigid_mlcp_single(m, ref, act); return; }
     const int nlanes = c.lanes(), lane = c.lane();
     while( act ){
       const int src = RKFD_FFS32(act) - 1; act &= act - 1;

@@ -156,6 +156,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     st.cf = dalloc<double>(*s, (size_t)3*ns*s->ld);
     st.status = dalloc<int>(*s, s->ld);
     st.ws = model.ws_doubles > 0 ? dalloc<double>(*s, (size_t)(s->ld/32)*model.ws_doubles) : nullptr;
+    st.ws1 = model.ws1_doubles > 0 ? dalloc<double>(*s, (size_t)model.ws1_doubles*s->ld) : nullptr;
     int nmax = nq; if( nl > nmax ) nmax = nl; if( 3*ns > nmax ) nmax = 3*ns;
     s->nstage = (size_t)nmax*s->B; s->dstage = dalloc<double>(*s, s->nstage);
     /* launch configuration: the block size that keeps most environments resident per SM; scratch in HBM

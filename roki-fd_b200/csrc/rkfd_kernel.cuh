@@ -78,6 +78,7 @@ struct DevCtx {
   /* level 1: once per evaluation, 2: per pass, 3: per link iteration */
   __device__ __forceinline__ void phase_sync(int level) const { if( level <= RKFD_SYNC_LEVEL ) __syncthreads(); }
   __device__ __forceinline__ double &W(int i){ return st.ws[(size_t)(e0 >> 5)*wsd + i]; }
+  __device__ __forceinline__ double &W1(int i){ return st.ws1[(size_t)i*st.ld + e]; }     /* element i of the selected environment */
   /* per-env state in HBM: element k of the selected environment (global address space asserted: LDG/STG, not generic) */
   __device__ __forceinline__ double gld(const double *p, int k) const { const double *a = p + ((size_t)k*st.ld + e); __builtin_assume(__isGlobal(a)); return *a; }
   __device__ __forceinline__ void gst(double *p, int k, double v){ double *a = p + ((size_t)k*st.ld + e); __builtin_assume(__isGlobal(a)); *a = v; }

@@ -154,6 +154,13 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
     if( m.pair[p].type == C_RIGID ){ m.rigid_mask |= 1ull << (2*sidx); nrs++; }
   }
   m.nmax = 3*nrs; m.ws_doubles = 0;
+  /* single-link MLCP path (Core::rigid_mlcp_single): every rigid slot on one link */
+  m.rigid_link = -1; m.ws1_doubles = 0;
+  if( m.has_rigid ){
+    int lk = -2;
+    for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID ){ const int l = m.cell[m.pair[p].cell].link; lk = ( lk == -2 || lk == l ) ? l : -1; }
+    if( lk >= 0 && m.solver == S_MLCP ){ m.rigid_link = lk; m.ws1_doubles = W1_CT + W1_CTN*nrs; }
+  }
   if( m.has_rigid ){
     const int n = m.nmax, mc = m.pyramid*nrs, nm = n + mc; int o = 0;
     m.ws_geo = o; o += GEO_DOUBLES*nrs;

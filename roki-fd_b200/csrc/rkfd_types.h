@@ -72,6 +72,8 @@ struct ModelDev {
   int ws_doubles;      /* per-warp workspace (doubles) of the rigid-contact solve, 0 when no rigid pair */
   int ws_geo, ws_b, ws_f, ws_A, ws_du, ws_da, ws_qp;   /* offsets inside the workspace */
   int nmax;            /* 3 * (rigid contact slots) */
+  int rigid_link;      /* link that carries EVERY rigid contact slot, -1 when they sit on several links */
+  int ws1_doubles;     /* per-ENVIRONMENT workspace (doubles) of the single-link MLCP path, 0 when unused */
   unsigned long long rigid_mask;   /* bit 2s set when slot s belongs to a rigid pair */
   int slot_pair[MAX_SLOTS], slot_vert[MAX_SLOTS];
   int rk_slot;         /* first slot of the RKG stage state: QS[nq], QDS[nq], PQ[nq], PQD[nq] */
@@ -101,6 +103,7 @@ struct StateDev {
   double *cf;             /* [nslot*3][ld] contact force (world) of the last reference evaluation */
   double *scratch;        /* optional global scratch [nscratch][ld] when shared memory is too small */
   double *ws;             /* rigid-contact workspace, ws_doubles per warp (ld/32 warps) */
+  double *ws1;            /* [ws1_doubles][ld] per-environment workspace of the single-link MLCP path */
   int *status;            /* [ld] per-env status word (bit0: non-finite acceleration) */
 };
 

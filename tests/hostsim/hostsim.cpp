@@ -39,6 +39,7 @@ struct HostCtx {
   void gsync(){}
   void phase_sync(int){}
   double &W(int i){ return wsp[i]; }
+  double &W1(int i){ return st.ws1[(size_t)i*st.ld + e]; }
   double gld(const double *p, int k) const { return p[(size_t)k*st.ld + e]; }
   void gst(double *p, int k, double v){ p[(size_t)k*st.ld + e] = v; }
 };
@@ -92,6 +93,7 @@ int hostsim_finalize(HostSim *h, int B)
   for(int k=0;k<2;k++){ st.q[k] = halloc<double>(h, (size_t)nq*B); st.qd[k] = halloc<double>(h, (size_t)nq*B); }
   st.qdd = halloc<double>(h, (size_t)nq*B); st.u = halloc<double>(h, (size_t)nl*B); st.piv_prev = halloc<double>(h, (size_t)nq*B);
   st.piv_type = halloc<unsigned int>(h, B); st.cflags = halloc<unsigned long long>(h, B);
+  st.ws1 = halloc<double>(h, (size_t)(m.ws1_doubles > 0 ? m.ws1_doubles : 1)*B);
   st.cref = halloc<double>(h, (size_t)3*ns*B); st.cf = halloc<double>(h, (size_t)3*ns*B); st.status = halloc<int>(h, B);
   return 0;
 }
