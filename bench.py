@@ -154,7 +154,7 @@ def main():
 
     import torch
     import rokifd_b200  # noqa: F401
-    from rokifd_b200 import capi, chains as ch
+    from rokifd_b200 import capi, chains as ch, multi
 
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
@@ -167,7 +167,7 @@ def main():
 
     world = ch.world_c3()
     B = args.envs
-    q, qd, u = ch.sample_state(world, B, seed=20260418 + rank)
+    q, qd, u = multi.rank_problem(world, ch, B, rank)     # weak scaling: every rank its own synthetic states
     fd, _ = capi.create_world(world, B=B, devices=[local_rank])
     fd.batch_set_state(q, qd)
     fd.batch_set_motor_input(u)
@@ -204,11 +204,8 @@ def main():
     per_launch_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
     if os.environ.get("RKFD_BENCH_DEBUG"):
         print("rank %d: total %.3f ms, per-launch min/median/max %.3f/%.3f/%.3f ms" % (rank, total_ms, min(per_launch_ms), float(np.median(per_launch_ms)), max(per_launch_ms)), file=sys.stderr)
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = B * world_size * args.steps / (total_ms * 1e-3)
+    total_ms = multi.max_over_ranks(dist, total_ms, device="cuda")      # the job's time is the slowest rank's
+    value = multi.job_throughput(B, world_size, args.steps, total_ms)
     assert (fd.batch_get_status() == 0).all(), "non-finite accelerations in the timed run"
     ca, _, _, _ = fd.batch_get_contact()
     contact_frac, mean_active = float((ca.sum(1) > 0).mean()), float(ca.sum(1).mean())
@@ -244,10 +241,7 @@ def main():
     fd.batch_sync()
     barrier()
     assert np.isfinite(oq.numpy()).all()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B * world_size * e2e_steps / (float(t.item()) * 1e-3)
+    e2e_value = multi.job_throughput(B, world_size, e2e_steps, multi.max_over_ranks(dist, e0.elapsed_time(e1), device="cuda"))
     h2d = B * (2 * nq + nl) * 8
     d2h = B * 3 * nq * 8
 
