@@ -525,9 +525,9 @@ struct Core {
       V3 om_n = xf_tmul(x, om);
       if( JT<Kt>(i,L) == J_REVOL ) om_n.z += wJ.z; else om_n = om_n + wJ;      /* additions of literal zeros are not folded away */
       if( m.need_world ){
-        V3 vl_n = xf_tmul(x, vl + cross(om, x.p));
+        V3 vl_n = xf_tmul(x, cadd(vl, om, x.p));
         if( JT<Kt>(i,L) != J_REVOL ) vl_n = vl_n + vJ;
-        pw = pw + mul(Rw, x.p); Rw = xf_world(x, Rw); vl = vl_n;
+        pw = madd(pw, Rw, x.p); Rw = xf_world(x, Rw); vl = vl_n;
       }
       om = om_n;
       st3(Spec::wslot(i,L), om);
@@ -625,14 +625,16 @@ struct Core {
         const V3 omp = v3(om.x, om.y, om.z - wJ.z);
         const V3 zl = cross(omp, cross(omp, x.ptl));
         const double zax = omp.y*wJ.z, zay = -omp.x*wJ.z;
-        pf = pf + mul(A, zl) + v3(B.xx*zax + B.xy*zay, B.yx*zax + B.yy*zay, B.zx*zax + B.zy*zay);
-        pn = pn + tmul(B, zl) + v3(C.xx*zax + C.xy*zay, C.xy*zax + C.yy*zay, C.xz*zax + C.yz*zay);
+        pf = madd(pf, A, zl);
+        pf = v3(fma(B.xy,zay,fma(B.xx,zax,pf.x)), fma(B.yy,zay,fma(B.yx,zax,pf.y)), fma(B.zy,zay,fma(B.zx,zax,pf.z)));
+        pn = maddt(pn, B, zl);
+        pn = v3(fma(C.xy,zay,fma(C.xx,zax,pn.x)), fma(C.yy,zay,fma(C.xy,zax,pn.y)), fma(C.yz,zay,fma(C.xz,zax,pn.z)));
       } else if( JT<Kt>(i,L) != J_FLOAT ){
         const V3 omp = om - wJ;
         const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
         const V3 za = cross(omp, wJ);
-        pf = pf + mul(A, zl) + mul(B, za);
-        pn = pn + tmul(B, zl) + mul(C, za);
+        pf = madd(madd(pf, A, zl), B, za);
+        pn = madd(maddt(pn, B, zl), C, za);
       }
       switch(JT<Kt>(i,L)){
       case J_REVOL: {
@@ -644,7 +646,7 @@ struct Core {
         A.xx-=Wl.x*Ul.x; A.xy-=Wl.x*Ul.y; A.xz-=Wl.x*Ul.z; A.yy-=Wl.y*Ul.y; A.yz-=Wl.y*Ul.z; A.zz-=Wl.z*Ul.z;
         C.xx-=Wa.x*Ua.x; C.xy-=Wa.x*Ua.y; C.xz-=Wa.x*Ua.z; C.yy-=Wa.y*Ua.y; C.yz-=Wa.y*Ua.z; C.zz-=Wa.z*Ua.z;
         B.xx-=Wl.x*Ua.x; B.xy-=Wl.x*Ua.y; B.xz-=Wl.x*Ua.z; B.yx-=Wl.y*Ua.x; B.yy-=Wl.y*Ua.y; B.yz-=Wl.y*Ua.z; B.zx-=Wl.z*Ua.x; B.zy-=Wl.z*Ua.y; B.zz-=Wl.z*Ua.z;
-        pf = pf + u*Wl; pn = pn + u*Wa;
+        pf = vfma(u, Wl, pf); pn = vfma(u, Wa, pn);
       } break;
       case J_PRISM: {
         double jm; const double tau = joint_torque(m, L, i, ref, jm, pf_u, pf_prev);
@@ -655,7 +657,7 @@ struct Core {
         A.xx-=Wl.x*Ul.x; A.xy-=Wl.x*Ul.y; A.xz-=Wl.x*Ul.z; A.yy-=Wl.y*Ul.y; A.yz-=Wl.y*Ul.z; A.zz-=Wl.z*Ul.z;
         C.xx-=Wa.x*Ua.x; C.xy-=Wa.x*Ua.y; C.xz-=Wa.x*Ua.z; C.yy-=Wa.y*Ua.y; C.yz-=Wa.y*Ua.z; C.zz-=Wa.z*Ua.z;
         B.xx-=Wl.x*Ua.x; B.xy-=Wl.x*Ua.y; B.xz-=Wl.x*Ua.z; B.yx-=Wl.y*Ua.x; B.yy-=Wl.y*Ua.y; B.yz-=Wl.y*Ua.z; B.zx-=Wl.z*Ua.x; B.zy-=Wl.z*Ua.y; B.zz-=Wl.z*Ua.z;
-        pf = pf + u*Wl; pn = pn + u*Wa;
+        pf = vfma(u, Wl, pf); pn = vfma(u, Wa, pn);
       } break;
       case J_SPHER: {
         /* S = [0; E], E = R^T Ro (= RJ^T); U = [B E; C E]; D = E^T C E; tau = 0 */
@@ -702,13 +704,9 @@ struct Core {
       /* X^T Ia X and X^T pa into the parent frame */
       const V3 p = x.p;
       const S3 Ar = xf_sym(x, A), Cr = xf_sym(x, C); const M3 Br = xf_gen(x, B);
-      const M3 T = mul_skew(Ar, p);                       /* A' [p x] */
-      M3 Bp; Bp.xx=Br.xx-T.xx; Bp.xy=Br.xy-T.xy; Bp.xz=Br.xz-T.xz; Bp.yx=Br.yx-T.yx; Bp.yy=Br.yy-T.yy; Bp.yz=Br.yz-T.yz; Bp.zx=Br.zx-T.zx; Bp.zy=Br.zy-T.zy; Bp.zz=Br.zz-T.zz;
-      const M3 Z1 = skew_mul(p, Bp), Z2 = skew_mul(p, Br);  /* C_p = C' + [p x] B_p + ([p x] B')^T */
-      S3 Cp;
-      Cp.xx = Cr.xx + Z1.xx + Z2.xx; Cp.xy = Cr.xy + Z1.xy + Z2.yx; Cp.xz = Cr.xz + Z1.xz + Z2.zx;
-      Cp.yy = Cr.yy + Z1.yy + Z2.yy; Cp.yz = Cr.yz + Z1.yz + Z2.zy; Cp.zz = Cr.zz + Z1.zz + Z2.zz;
-      const V3 fp = xf_mul(x, pf); const V3 np = xf_mul(x, pn) + cross(p, fp);
+      const M3 Bp = shift_B(Br, Ar, p);                   /* B_p = B' - A' [p x] */
+      const S3 Cp = shift_C(Cr, Bp, Br, p);               /* C_p = C' + [p x] B_p + ([p x] B')^T */
+      const V3 fp = xf_mul(x, pf); const V3 np = cadd(xf_mul(x, pn), p, fp);
       if( SER<Kt>(i,L) ){ kA = Ar; kB = Bp; kC = Cp; kf = fp; kn = np; }
       else {
         const int a = m.link[L.parent].accum_slot;
@@ -806,14 +804,16 @@ struct Core {
       V3 zl, za;
       if( JT<Kt>(i,L) == J_REVOL ){ zl = cross(omp, cross(omp, x.ptl)); za = v3(omp.y*wJ.z, -omp.x*wJ.z, 0.0); }
       else { zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ); za = cross(omp, wJ); }
-      const V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
+      const V3 xl = xf_tmul(x, cadd(al, aa, x.p)), xa = xf_tmul(x, aa);
       switch(JT<Kt>(i,L)){
       case J_REVOL: case J_PRISM: {
         const V3 Ul = ld3(sl), Ua = ld3(sl+3);
         double Dinv, uu; c.TL2(Spec::sc(i,L)+2, Dinv, uu);
-        const double acc = Dinv*( uu - (dot(Ul,xl) + dot(Ua,xa)) );
-        al = xl + zl;
-        if( JT<Kt>(i,L) == J_REVOL ){ aa = v3(xa.x + za.x, xa.y + za.y, xa.z + acc); } else { aa = xa + za; al.z += acc; }
+        const double acc = Dinv*fma(-Ua.z,xa.z,fma(-Ua.y,xa.y,fma(-Ua.x,xa.x,fma(-Ul.z,xl.z,fma(-Ul.y,xl.y,fma(-Ul.x,xl.x,uu))))));
+        if( JT<Kt>(i,L) == J_REVOL ){
+          al = cadd(xl, omp, cross(omp, x.ptl));
+          aa = v3(fma(omp.y, wJ.z, xa.x), fma(-omp.x, wJ.z, xa.y), xa.z + acc);
+        } else { al = xl + zl; aa = xa + za; al.z += acc; }
         if( stage == ST_PROBE ){}
         else if( stage >= ST_REF ){ c.gst(c.st.qdd, qo, acc); if( !(fabs(acc) < 1.0e300) ) bad = 1; }
         else {

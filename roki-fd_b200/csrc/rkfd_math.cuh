@@ -72,6 +72,31 @@ RKFD_HD M3 mul_skew(const S3 &m, V3 p){     /* written out: products with the ze
   r.xz = m.xx*p.y - m.xy*p.x; r.yz = m.xy*p.y - m.yy*p.x; r.zz = m.xz*p.y - m.yz*p.x;
   return r; }
 
+/* ---- accumulate forms: acc + M v, acc + a x b, ... as explicit fused multiply-add chains.  `acc + mul(M, v)` costs
+ * four instructions per component (the compiler may not re-associate the sum), these cost three (two for a cross
+ * product component): about one fp64 instruction in eight of the dynamics passes. */
+RKFD_HD V3 madd(V3 a, const M3 &m, V3 v){ return v3(fma(m.xz,v.z,fma(m.xy,v.y,fma(m.xx,v.x,a.x))), fma(m.yz,v.z,fma(m.yy,v.y,fma(m.yx,v.x,a.y))), fma(m.zz,v.z,fma(m.zy,v.y,fma(m.zx,v.x,a.z)))); }
+RKFD_HD V3 maddt(V3 a, const M3 &m, V3 v){ return v3(fma(m.zx,v.z,fma(m.yx,v.y,fma(m.xx,v.x,a.x))), fma(m.zy,v.z,fma(m.yy,v.y,fma(m.xy,v.x,a.y))), fma(m.zz,v.z,fma(m.yz,v.y,fma(m.xz,v.x,a.z)))); }
+RKFD_HD V3 madd(V3 a, const S3 &m, V3 v){ return v3(fma(m.xz,v.z,fma(m.xy,v.y,fma(m.xx,v.x,a.x))), fma(m.yz,v.z,fma(m.yy,v.y,fma(m.xy,v.x,a.y))), fma(m.zz,v.z,fma(m.yz,v.y,fma(m.xz,v.x,a.z)))); }
+RKFD_HD V3 cadd(V3 a, V3 b, V3 c){ return v3(fma(b.y,c.z,fma(-b.z,c.y,a.x)), fma(b.z,c.x,fma(-b.x,c.z,a.y)), fma(b.x,c.y,fma(-b.y,c.x,a.z))); }   /* a + b x c */
+RKFD_HD V3 vfma(double k, V3 b, V3 a){ return v3(fma(k,b.x,a.x), fma(k,b.y,a.y), fma(k,b.z,a.z)); }                                        /* a + k b */
+/* Br - Ar [p x]   and   Cr + [p x] Bp + ([p x] Br)^T  (shift of an articulated inertia by p, blocks of the congruence) */
+RKFD_HD M3 shift_B(const M3 &Br, const S3 &A, V3 p){
+  M3 r;
+  r.xx = fma(A.xz,p.y,fma(-A.xy,p.z,Br.xx)); r.yx = fma(A.yz,p.y,fma(-A.yy,p.z,Br.yx)); r.zx = fma(A.zz,p.y,fma(-A.yz,p.z,Br.zx));
+  r.xy = fma(A.xx,p.z,fma(-A.xz,p.x,Br.xy)); r.yy = fma(A.xy,p.z,fma(-A.yz,p.x,Br.yy)); r.zy = fma(A.xz,p.z,fma(-A.zz,p.x,Br.zy));
+  r.xz = fma(A.xy,p.x,fma(-A.xx,p.y,Br.xz)); r.yz = fma(A.yy,p.x,fma(-A.xy,p.y,Br.yz)); r.zz = fma(A.yz,p.x,fma(-A.xz,p.y,Br.zz));
+  return r; }
+RKFD_HD S3 shift_C(const S3 &Cr, const M3 &Bp, const M3 &Br, V3 p){
+  S3 r;       /* ([p x] M)_ij = (p x col_j(M))_i */
+  r.xx = fma(p.y,Br.zx,fma(-p.z,Br.yx,fma(p.y,Bp.zx,fma(-p.z,Bp.yx,Cr.xx))));
+  r.xy = fma(p.z,Br.xx,fma(-p.x,Br.zx,fma(p.y,Bp.zy,fma(-p.z,Bp.yy,Cr.xy))));
+  r.xz = fma(p.x,Br.yx,fma(-p.y,Br.xx,fma(p.y,Bp.zz,fma(-p.z,Bp.yz,Cr.xz))));
+  r.yy = fma(p.z,Br.xy,fma(-p.x,Br.zy,fma(p.z,Bp.xy,fma(-p.x,Bp.zy,Cr.yy))));
+  r.yz = fma(p.x,Br.yy,fma(-p.y,Br.xy,fma(p.z,Bp.xz,fma(-p.x,Bp.zz,Cr.yz))));
+  r.zz = fma(p.x,Br.yz,fma(-p.y,Br.xz,fma(p.x,Bp.yz,fma(-p.y,Bp.xz,Cr.zz))));
+  return r; }
+
 /* ---- structured link transforms ------------------------------------------------------------------
  * A revolute link frame is R = Ro * Rz(q).  When the constant part Ro is the identity or a quarter turn
  * about x (DH alpha in {0, +90, -90} deg: the usual case), products with R are a planar rotation plus a

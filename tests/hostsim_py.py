@@ -22,7 +22,7 @@ def lib():
         deps = [os.path.join(_SRC, "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in
                                                      ("rkfd_core.cuh", "rkfd_math.cuh", "rkfd_types.h", "rkfd_model.cpp", "rkfd_model.h")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + _CSRC,
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-mfma", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-I" + _CSRC,
                                    os.path.join(_SRC, "hostsim.cpp"), os.path.join(_CSRC, "rkfd_model.cpp"), "-o", so])
         L = C.CDLL(so)
         L.hostsim_new.restype = C.c_void_p

@@ -152,7 +152,7 @@ STATISTICAL = {"c5_arm7_vert": 0.5, "box_vert": 0.95}
 def test_rigid_eval_matches_oracle(oracle, name):
     """One committing evaluation with rigid contacts: q'', contact forces and friction flags."""
     w = RIGID_WORLDS[name]()
-    B = 48
+    B = 400 if name == "c5_arm7_vert" else 48      # the statistical case needs a sample (8 % of the envs touch the floor)
     q, qd, u = ch.sample_state(w, B, seed=5)
     if "box" in name:
         q[:, 2] = np.linspace(-0.01, 0.08, B)
