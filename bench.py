@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=B_PER_GPU, help="environments per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-upload-state", action="store_true", help="e2e leg: also re-send (q, q') host->device every step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -221,9 +222,14 @@ def main():
 
     def e2e_step():
         # every step: this step's inputs host->device from pinned memory, the step, its result device->host.
+        # A step's inputs are what the reference's callers set between two rkFDUpdate calls - the motor inputs
+        # (rkJointMotorSetInput, example/chain/arm_box_test.c:21); the simulator owns the state, as the reference's
+        # rkFD does.  Its result is the state the caller reads back: q, q', q''.  --e2e-upload-state also re-sends
+        # (q, q') every step (rkFDChainSetDis/SetVel before every update).
         # The calls are asynchronous (copy streams + staging ring), so the transfers of neighbouring steps overlap
         # the step kernel; rkFDBatchJoin + the closing event make the timed region cover all of them.
-        fd.batch_set_state_async(hq.data_ptr(), hqd.data_ptr())
+        if args.e2e_upload_state:
+            fd.batch_set_state_async(hq.data_ptr(), hqd.data_ptr())
         fd.batch_set_motor_input_async(hu.data_ptr())
         fd.update()
         fd.batch_get_state_async(oq.data_ptr(), oqd.data_ptr(), oqdd.data_ptr())
@@ -242,7 +248,7 @@ def main():
     barrier()
     assert np.isfinite(oq.numpy()).all()
     e2e_value = multi.job_throughput(B, world_size, e2e_steps, multi.max_over_ranks(dist, e0.elapsed_time(e1), device="cuda"))
-    h2d = B * (2 * nq + nl) * 8
+    h2d = B * ((2 * nq if args.e2e_upload_state else 0) + nl) * 8
     d2h = B * 3 * nq * 8
 
     # ---- roofline of the dominant kernel (rkfd_step_kernel: the only kernel of a step) ------------------
@@ -263,7 +269,9 @@ def main():
            "config": {"workload": WORKLOAD, "envs_per_gpu": B, "dt": world.dt, "integrator": "RKG", "solver": world.solver,
                       "settle_steps": SETTLE_STEPS, "envs_in_contact": contact_frac, "mean_active_vertices": mean_active,
                       "l2": "per-GPU state (%.0f MB) is larger than the 126 MB L2" % (B * 8 * 140 / 1e6)},
-           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                   "io": "per step: motor inputs u[B][%d] host->device%s, rkFDUpdate, (q, q', q'')[B][%d] device->host; pinned host buffers, "
+                         "asynchronous copies on their own streams" % (nl, " + state (q, q')" if args.e2e_upload_state else "", nq)},
            "gpu_launches": int(launches),
            "clocks": clocks,
            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,

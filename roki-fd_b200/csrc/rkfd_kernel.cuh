@@ -48,9 +48,6 @@ struct DevCtx {
   }
   __device__ __forceinline__ void tfence(){
     if( TM ){
-#ifdef RKFD_TM_SYNCWARP
-      __syncwarp();
-#endif
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
   }
@@ -114,18 +111,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) rkfd_step_kernel(StateDev st, int
     ctx.tbase = tmem_addr + (((warp & 3u)*32u) << 16) + (warp >> 2)*TMEM_COLS_PER_WARPGROUP;
   }
   Core<DevCtx<BLOCK,GSCR,RIGID,TM>, Spec> core(ctx);
-#ifdef RKFD_TM_ZERO
-  if( TM ){ for(int k=0;k<64;k++) ctx.TS(k, 0.0); ctx.tfence(); }
-#endif
-#ifdef RKFD_TM_DEBUG
-  if( TM ){   /* write/read-back self test of the thread's T space before the real work */
-    for(int k=0;k<Spec::NTSPACE;k++) ctx.TS(k, 1000.0*e + k);
-    ctx.tfence();
-    int nbad = 0; for(int k=0;k<Spec::NTSPACE;k++) if( ctx.TL(k) != 1000.0*e + k ) nbad++;
-    unsigned smid, wid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-    if( (threadIdx.x & 31) == 0 && blockIdx.x < 4 ) printf("[tm] block %d warp %d smid %u warpid %u tmem_addr %x tbase %x selftest bad %d\n", blockIdx.x, threadIdx.x>>5, smid, wid, tmem_addr, ctx.tbase, nbad);
-  }
-#endif
   core.run(c_model, mode, nsteps);
   if( TM ){
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
