@@ -1378,23 +1378,54 @@ struct Core {
         c.W(oV+e) = (t == u) ? 1.0 : 0.0;
       }
       c.gsync();
-      /* l = S^+ rhs: cyclic Jacobi eigen-decomposition of the symmetric S (ma x ma) */
-      for(int sweep=0; sweep<40 && ma>1; sweep++){
-        double part = 0;
-        for(int e=lane;e<ma*ma;e+=nlanes){ const int t = e/ma, u = e - t*ma; if( u > t ) part += c.W(oS+e)*c.W(oS+e); }
-        const double off = c.allsum(part);
-        if( off < 1.0e-300 ) break;
-        for(int p=0;p<ma-1;p++) for(int q=p+1;q<ma;q++){
-          const double apq = c.W(oS+p*ma+q);
-          if( fabs(apq) < 1.0e-300 ) continue;
-          const double th = (c.W(oS+q*ma+q) - c.W(oS+p*ma+p))/(2.0*apq);
-          const double tt = (th >= 0 ? 1.0 : -1.0)/(fabs(th) + sqrt(th*th + 1.0)), cs = 1.0/sqrt(tt*tt + 1.0), sn = tt*cs;
-          c.gsync();
-          for(int k=lane;k<ma;k+=nlanes){ const double akp = c.W(oS+k*ma+p), akq = c.W(oS+k*ma+q); c.W(oS+k*ma+p) = cs*akp - sn*akq; c.W(oS+k*ma+q) = sn*akp + cs*akq; }
-          c.gsync();
-          for(int k=lane;k<ma;k+=nlanes){ const double apk = c.W(oS+p*ma+k), aqk = c.W(oS+q*ma+k); c.W(oS+p*ma+k) = cs*apk - sn*aqk; c.W(oS+q*ma+k) = sn*apk + cs*aqk;
-                                           const double vkp = c.W(oV+k*ma+p), vkq = c.W(oV+k*ma+q); c.W(oV+k*ma+p) = cs*vkp - sn*vkq; c.W(oV+k*ma+q) = sn*vkp + cs*vkq; }
-          c.gsync();
+      /* l = S^+ rhs: Jacobi eigen-decomposition of the symmetric S (ma x ma) in the PARALLEL (round-robin) ordering:
+       * a sweep is me-1 rounds of me/2 rotations on disjoint index pairs (me = ma rounded up to even); the lanes
+       * first compute the rotations of the round, then apply all of them to the columns of S and V, then to the
+       * rows of S - three warp barriers per round instead of three per rotation (ma = 24: 69 instead of 828 per
+       * sweep), and every lane has work.  (cs, sn) of the round live behind the anti-cycling history. */
+      { const int me = (ma + 1) & ~1, np = me/2, ocs = ohist + QP_HIST*(mx+1);
+        for(int sweep=0; sweep<40 && ma>1; sweep++){
+          double part = 0;
+          for(int e=lane;e<ma*ma;e+=nlanes){ const int t = e/ma, u = e - t*ma; if( u > t ) part += c.W(oS+e)*c.W(oS+e); }
+          const double off = c.allsum(part);
+          if( off < 1.0e-300 ) break;
+          for(int rnd=0; rnd<me-1; rnd++){
+            /* pair i of the round: (me-1, rnd) for i = 0, ((rnd+i) mod (me-1), (rnd+me-1-i) mod (me-1)) otherwise */
+            for(int i=lane;i<np;i+=nlanes){
+              int p = i == 0 ? me-1 : (rnd + i) % (me-1), q = i == 0 ? rnd : (rnd + me-1 - i) % (me-1);
+              if( p > q ){ const int t = p; p = q; q = t; }
+              double cs = 1.0, sn = 0.0;
+              if( q < ma ){
+                const double apq = c.W(oS+p*ma+q);
+                if( !(fabs(apq) < 1.0e-300) ){
+                  const double th = (c.W(oS+q*ma+q) - c.W(oS+p*ma+p))/(2.0*apq);
+                  const double tt = (th >= 0 ? 1.0 : -1.0)/(fabs(th) + sqrt(th*th + 1.0));
+                  cs = 1.0/sqrt(tt*tt + 1.0); sn = tt*cs;
+                }
+              }
+              c.W(ocs+2*i) = cs; c.W(ocs+2*i+1) = sn;
+            }
+            c.gsync();
+            for(int e=lane;e<np*ma;e+=nlanes){          /* columns p, q of S and V */
+              const int i = e/ma, k = e - i*ma;
+              int p = i == 0 ? me-1 : (rnd + i) % (me-1), q = i == 0 ? rnd : (rnd + me-1 - i) % (me-1);
+              if( p > q ){ const int t = p; p = q; q = t; }
+              if( q >= ma ) continue;
+              const double cs = c.W(ocs+2*i), sn = c.W(ocs+2*i+1);
+              const double akp = c.W(oS+k*ma+p), akq = c.W(oS+k*ma+q); c.W(oS+k*ma+p) = cs*akp - sn*akq; c.W(oS+k*ma+q) = sn*akp + cs*akq;
+              const double vkp = c.W(oV+k*ma+p), vkq = c.W(oV+k*ma+q); c.W(oV+k*ma+p) = cs*vkp - sn*vkq; c.W(oV+k*ma+q) = sn*vkp + cs*vkq;
+            }
+            c.gsync();
+            for(int e=lane;e<np*ma;e+=nlanes){          /* rows p, q of S */
+              const int i = e/ma, k = e - i*ma;
+              int p = i == 0 ? me-1 : (rnd + i) % (me-1), q = i == 0 ? rnd : (rnd + me-1 - i) % (me-1);
+              if( p > q ){ const int t = p; p = q; q = t; }
+              if( q >= ma ) continue;
+              const double cs = c.W(ocs+2*i), sn = c.W(ocs+2*i+1);
+              const double apk = c.W(oS+p*ma+k), aqk = c.W(oS+q*ma+k); c.W(oS+p*ma+k) = cs*apk - sn*aqk; c.W(oS+q*ma+k) = sn*apk + cs*aqk;
+            }
+            c.gsync();
+          }
         }
       }
       double lmax = 0;

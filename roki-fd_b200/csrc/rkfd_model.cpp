@@ -171,7 +171,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
     m.ws_da = o; o += n*6*nl;         /* per probe column: link acceleration increments */
     m.ws_qp = o;
     (void)nm;
-    if( m.solver == S_VERT ) o += 2*n*n + 4*n + 3*mc + mc + n*mc + 2*mc*mc + 3*mc + 32*(mc+1) + 64;   /* layout in Core::qp_vert */
+    if( m.solver == S_VERT ) o += 2*n*n + 4*n + 3*mc + mc + n*mc + 2*mc*mc + 3*mc + 32*(mc+1) + (mc+2) + 64;   /* layout in Core::qp_vert */
     m.ws_doubles = (o + 31) & ~31;
   }
   return true;
