@@ -350,6 +350,7 @@ struct Core {
   RKFD_HD XF joint_xform(const ModelDev &m, const LinkDev &L, int i, V3 &vJ, V3 &wJ){
     const int sl = Spec::slot(i,L), qs = rk0 + Spec::qofs(i,L), qds = rk0 + Spec::nq(m) + Spec::qofs(i,L);
     XF x; x.fast = 0; x.cls = CLS<Kt>(i,L); x.sg = ro_sign(x.cls, L.rsg); x.c = 1.0; x.s = 0.0;
+    x.pz = ( JT<Kt>(i,L) == J_REVOL || JT<Kt>(i,L) == J_FIXED ) && L.po[0] == 0.0 && L.po[1] == 0.0;
     vJ = v3(0,0,0); wJ = v3(0,0,0);
     switch(JT<Kt>(i,L)){
     case J_REVOL: {
@@ -457,8 +458,7 @@ struct Core {
             const double vs = norm(v);
             f = fn*n;
             if( !(fabs(vs) < ZTOL) ){
-              v = v3(v.x/vs, v.y/vs, v.z/vs);
-              f = f + (-(1.0 - exp(-1.0*m.friction_weight*vs))*pr.KF*fn)*v;
+              f = f + ((-(1.0 - exp(-1.0*m.friction_weight*vs))*pr.KF*fn)/vs)*v;
             }
             if( ref ){ cfl |= kbit; c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
           } else if( ref ) cfl &= ~kbit;
@@ -479,7 +479,9 @@ struct Core {
    * not formed): no gravity direction to propagate outward, no gravity terms in the bias forces. */
   static RKFD_HD bool grav_acc(const ModelDev &m){ return Spec::NL != 0 ? true : !m.has_rigid; }
 
-  RKFD_HD void pass1(const ModelDev &m, bool ref){
+  /* `fresh`: sin/cos of the revolute joints are computed from the stage angle (first stage of a step, single
+   * evaluations); otherwise pass 3 of the previous stage has already rotated them to the new stage angle */
+  RKFD_HD void pass1(const ModelDev &m, bool ref, bool fresh){
     const bool gacc = grav_acc(m);
     M3 Rw = ident3(); V3 pw = v3(0,0,0), vl = v3(0,0,0), om = v3(0,0,0), gd = v3(0,0,-GRAVITY);
     const int qs = rk0, qds = rk0 + Spec::nq(m);
@@ -496,11 +498,13 @@ struct Core {
         }
       }
       XF x; x.fast = 0; x.cls = CLS<Kt>(i,L); x.sg = ro_sign(x.cls, L.rsg); x.c = 1.0; x.s = 0.0;
+      x.pz = ( JT<Kt>(i,L) == J_REVOL || JT<Kt>(i,L) == J_FIXED ) && L.po[0] == 0.0 && L.po[1] == 0.0;
       V3 vJ = v3(0,0,0), wJ = v3(0,0,0);
       switch(JT<Kt>(i,L)){
       case J_REVOL: {
-        double sn, co; sincos(T(qs+qo), &sn, &co);
-        Tw(Spec::sc(i,L), sn); Tw(Spec::sc(i,L)+1, co);
+        double sn, co;
+        if( fresh ){ sincos(T(qs+qo), &sn, &co); Tw(Spec::sc(i,L), sn); Tw(Spec::sc(i,L)+1, co); }
+        else c.TL2(Spec::sc(i,L), sn, co);
         x.s = sn; x.c = co; x.p = org_p(L);
         if( CLS<Kt>(i,L) != RO_GENERAL ) x.fast = 1;
         else { const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
@@ -525,9 +529,9 @@ struct Core {
       V3 om_n = xf_tmul(x, om);
       if( JT<Kt>(i,L) == J_REVOL ) om_n.z += wJ.z; else om_n = om_n + wJ;      /* additions of literal zeros are not folded away */
       if( m.need_world ){
-        V3 vl_n = xf_tmul(x, cadd(vl, om, x.p));
+        V3 vl_n = xf_tmul(x, cadd_p(vl, om, x.p, x.pz));
         if( JT<Kt>(i,L) != J_REVOL ) vl_n = vl_n + vJ;
-        pw = madd(pw, Rw, x.p); Rw = xf_world(x, Rw); vl = vl_n;
+        pw = madd_p(pw, Rw, x.p, x.pz); Rw = xf_world(x, Rw); vl = vl_n;
       }
       om = om_n;
       st3(Spec::wslot(i,L), om);
@@ -704,9 +708,9 @@ struct Core {
       /* X^T Ia X and X^T pa into the parent frame */
       const V3 p = x.p;
       const S3 Ar = xf_sym(x, A), Cr = xf_sym(x, C); const M3 Br = xf_gen(x, B);
-      const M3 Bp = shift_B(Br, Ar, p);                   /* B_p = B' - A' [p x] */
-      const S3 Cp = shift_C(Cr, Bp, Br, p);               /* C_p = C' + [p x] B_p + ([p x] B')^T */
-      const V3 fp = xf_mul(x, pf); const V3 np = cadd(xf_mul(x, pn), p, fp);
+      const M3 Bp = shift_B_p(Br, Ar, p, x.pz);           /* B_p = B' - A' [p x] */
+      const S3 Cp = shift_C_p(Cr, Bp, Br, p, x.pz);       /* C_p = C' + [p x] B_p + ([p x] B')^T */
+      const V3 fp = xf_mul(x, pf); const V3 np = padd_c(xf_mul(x, pn), p, fp, x.pz);
       if( SER<Kt>(i,L) ){ kA = Ar; kB = Bp; kC = Cp; kf = fp; kn = np; }
       else {
         const int a = m.link[L.parent].accum_slot;
@@ -735,14 +739,27 @@ struct Core {
     rk_lin_pf(k, stage, slotS, slotP, gout, j, slope, F, x0);
   }
   /* F = running combination and x0 = committed value, fetched by the caller (possibly one link ahead) */
-  RKFD_HD void rk_lin_pf(const RK &k, int stage, int slotS, int slotP, double *gout, int j, double slope, double F, double x0g){
+  RKFD_HD double rk_lin_pf(const RK &k, int stage, int slotS, int slotP, double *gout, int j, double slope, double F, double x0g){
+    double xn = 0.0;       /* the next stage value */
     switch(stage){
-    case ST_K1: { const double x0 = T(slotS); c.gst(gout, j, x0 + k.b1*slope); Tw(slotP, x0 + k.c31*slope); Tw(slotS, x0 + k.c21*slope); } break;
-    case ST_K2: { c.gst(gout, j, F + k.b2*slope); Tw(slotS, T(slotP) + k.c32*slope); Tw(slotP, x0g + k.c42*slope); } break;
-    case ST_K3: { c.gst(gout, j, F + k.b3*slope); Tw(slotS, T(slotP) + k.c43*slope); } break;
-    case ST_K4: { const double x = F + k.b4*slope; c.gst(gout, j, x); Tw(slotS, x); } break;
+    case ST_K1: { const double x0 = T(slotS); c.gst(gout, j, x0 + k.b1*slope); Tw(slotP, x0 + k.c31*slope); xn = x0 + k.c21*slope; Tw(slotS, xn); } break;
+    case ST_K2: { c.gst(gout, j, F + k.b2*slope); xn = T(slotP) + k.c32*slope; Tw(slotS, xn); Tw(slotP, x0g + k.c42*slope); } break;
+    case ST_K3: { c.gst(gout, j, F + k.b3*slope); xn = T(slotP) + k.c43*slope; Tw(slotS, xn); } break;
+    case ST_K4: { xn = F + k.b4*slope; c.gst(gout, j, xn); Tw(slotS, xn); } break;
     default: break;
     }
+    return xn;
+  }
+  /* sin/cos of a revolute joint carried from the stage angle qold to qnew = qold + d: angle addition with the
+   * Taylor series of (sin d, cos d) (|d| <= 1/16: truncation below 1e-18), a full sincos otherwise.  A step
+   * computes sincos once per joint (first stage) instead of five times; four chained rotations add a few ulp. */
+  RKFD_HD void rot_sincos(int sc, double s0, double c0, double qold, double qnew){
+    const double d = qnew - qold, d2 = d*d;
+    const double sd = d*fma(d2, fma(d2, fma(d2, fma(d2, 1.0/362880.0, -1.0/5040.0), 1.0/120.0), -1.0/6.0), 1.0);
+    const double cd = fma(d2, fma(d2, fma(d2, fma(d2, 1.0/40320.0, -1.0/720.0), 1.0/24.0), -0.5), 1.0);
+    double sn = fma(s0, cd, c0*sd), co = fma(c0, cd, -(s0*sd));
+    if( !(fabs(d) <= 0.0625) ) sincos(qnew, &sn, &co);
+    Tw(sc, sn); Tw(sc+1, co);
   }
   /* rotation (angle-axis) component triple starting at j: increments compose on SO(3) */
   RKFD_HD void rk_rot(const ModelDev &m, const RK &k, int stage, int slotS, int slotP, double *gin, double *gout, int j, V3 w){
@@ -804,7 +821,7 @@ struct Core {
       V3 zl, za;
       if( JT<Kt>(i,L) == J_REVOL ){ zl = cross(omp, cross(omp, x.ptl)); za = v3(omp.y*wJ.z, -omp.x*wJ.z, 0.0); }
       else { zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ); za = cross(omp, wJ); }
-      const V3 xl = xf_tmul(x, cadd(al, aa, x.p)), xa = xf_tmul(x, aa);
+      const V3 xl = xf_tmul(x, cadd_p(al, aa, x.p, x.pz)), xa = xf_tmul(x, aa);
       switch(JT<Kt>(i,L)){
       case J_REVOL: case J_PRISM: {
         const V3 Ul = ld3(sl), Ua = ld3(sl+3);
@@ -819,7 +836,11 @@ struct Core {
         else {
           const int j = qo, qs = rk0 + j, qds = qs + NQc, pq = qs + 2*NQc, pqd = qs + 3*NQc;
           const double vel = T(qds);
-          rk_lin_pf(k, stage, qs,  pq,  c.st.q[c.cur^1],  j, vel, pfq[0], pfq[2]);
+          if( JT<Kt>(i,L) == J_REVOL ){
+            const double qold = T(qs);
+            const double qnew = rk_lin_pf(k, stage, qs,  pq,  c.st.q[c.cur^1],  j, vel, pfq[0], pfq[2]);
+            rot_sincos(Spec::sc(i,L), x.s, x.c, qold, qnew);
+          } else rk_lin_pf(k, stage, qs,  pq,  c.st.q[c.cur^1],  j, vel, pfq[0], pfq[2]);
           rk_lin_pf(k, stage, qds, pqd, c.st.qd[c.cur^1], j, acc, pfq[1], pfq[3]);
         }
       } break;
@@ -1532,7 +1553,7 @@ struct Core {
      * the union of all passes (the kernel is far larger than the instruction cache) */
     c.phase_sync(1);
     c.tfence();               /* T-space stores of the previous pass are complete before this pass loads them */
-    pass1(m, ref);
+    pass1(m, ref, stage == ST_K1 || stage >= ST_EVAL);
     if( !Ctx::RIGID ) c.phase_sync(2);
     c.tfence();
     if( Ctx::RIGID ){

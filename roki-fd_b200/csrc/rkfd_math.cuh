@@ -97,6 +97,29 @@ RKFD_HD S3 shift_C(const S3 &Cr, const M3 &Bp, const M3 &Br, V3 p){
   r.zz = fma(p.x,Br.yz,fma(-p.y,Br.xz,fma(p.x,Bp.yz,fma(-p.y,Bp.xz,Cr.zz))));
   return r; }
 
+/* the same with the frame offset p of a link, short forms when p = (0,0,p.z) (x.pz) */
+struct XF;
+RKFD_HD V3 cadd_p(V3 a, V3 b, V3 p, int pz){ return pz ? v3(fma(b.y,p.z,a.x), fma(-b.x,p.z,a.y), a.z) : cadd(a, b, p); }          /* a + b x p */
+RKFD_HD V3 padd_c(V3 a, V3 p, V3 c, int pz){ return pz ? v3(fma(-p.z,c.y,a.x), fma(p.z,c.x,a.y), a.z) : cadd(a, p, c); }           /* a + p x c */
+RKFD_HD V3 madd_p(V3 a, const M3 &m, V3 p, int pz){ return pz ? v3(fma(m.xz,p.z,a.x), fma(m.yz,p.z,a.y), fma(m.zz,p.z,a.z)) : madd(a, m, p); }
+RKFD_HD M3 shift_B_p(const M3 &Br, const S3 &A, V3 p, int pz){
+  if( !pz ) return shift_B(Br, A, p);
+  M3 r;
+  r.xx = fma(-A.xy,p.z,Br.xx); r.yx = fma(-A.yy,p.z,Br.yx); r.zx = fma(-A.yz,p.z,Br.zx);
+  r.xy = fma(A.xx,p.z,Br.xy);  r.yy = fma(A.xy,p.z,Br.yy);  r.zy = fma(A.xz,p.z,Br.zy);
+  r.xz = Br.xz; r.yz = Br.yz; r.zz = Br.zz;
+  return r; }
+RKFD_HD S3 shift_C_p(const S3 &Cr, const M3 &Bp, const M3 &Br, V3 p, int pz){
+  if( !pz ) return shift_C(Cr, Bp, Br, p);
+  S3 r;
+  r.xx = fma(-p.z,Br.yx,fma(-p.z,Bp.yx,Cr.xx));
+  r.xy = fma(p.z,Br.xx,fma(-p.z,Bp.yy,Cr.xy));
+  r.xz = fma(-p.z,Bp.yz,Cr.xz);
+  r.yy = fma(p.z,Br.xy,fma(p.z,Bp.xy,Cr.yy));
+  r.yz = fma(p.z,Bp.xz,Cr.yz);
+  r.zz = Cr.zz;
+  return r; }
+
 /* ---- structured link transforms ------------------------------------------------------------------
  * A revolute link frame is R = Ro * Rz(q).  When the constant part Ro is the identity or a quarter turn
  * about x (DH alpha in {0, +90, -90} deg: the usual case), products with R are a planar rotation plus a
@@ -146,6 +169,8 @@ struct XF {
   double c, s;
   M3 R;            /* dense rotation (fast == 0) */
   V3 p;            /* origin of the link frame in parent coordinates */
+  int pz;          /* p = (0, 0, p.z): the link origin sits on the parent's z axis (warp-uniform, from the table) - the
+                      products with [p x] then lose two thirds of their terms */
   V3 ptl;          /* R^T p */
 };
 RKFD_HD V3 xf_tmul(const XF &x, V3 v){ return x.fast ? rz_tmul(x.c, x.s, ro_tmul(x.cls, x.sg, v)) : tmul(x.R, v); }
