@@ -151,7 +151,7 @@ struct SpecGeneric {
   static RKFD_HD int nq(const ModelDev &m){ return m.nq; }
   /* 1-DoF joints: slots of (sin, cos, 1/D, u) in the "T space" (Ctx::TL/TS) - the scratch column itself here */
   static RKFD_HD int sc(int, const LinkDev &L){ return L.slot + 6; }
-  static constexpr int TM = 0, NTSPACE = 0;
+  static constexpr int TM = 0, NTSPACE = 0, SCS = 0;
 };
 /* link 0 = fixed root, links 1..NL-1 revolute and serial; CLS: 2 bits per revolute link (RoClass 1..3) */
 /* TM_ = 1: the integrator stage state and (sin, cos, 1/D, u) of every joint live in TENSOR MEMORY (tcgen05.st/ld,
@@ -161,7 +161,7 @@ struct SpecGeneric {
  * in warp-uniform code. */
 template <int ID_, int NL_, unsigned CLS_, int TM_>
 struct SpecSerialRev {
-  static constexpr int ID = ID_, NL = NL_, UNROLL = NL_, TM = TM_, ROLL = 0;
+  static constexpr int ID = ID_, NL = NL_, UNROLL = NL_, TM = TM_, ROLL = 0, SCS = 0;
   static constexpr int WEXT = TM_ ? 6*NL_ : 6 + 10*(NL_-1);
   static constexpr int RK = TM_ ? 4*(NL_-1) : WEXT + 6;                 /* T space when TM_ */
   static constexpr int NSCRATCH = TM_ ? WEXT + 6 : RK + 4*(NL_-1);     /* shared-memory doubles per environment */
@@ -190,29 +190,37 @@ struct SpecSerialRev {
  * by every warp (ncu: no_instruction is its second largest stall); the rolled bodies are ~7 KB per pass and stay
  * cached.  Costs: table entries are fetched through uniform registers instead of immediate constant operands, and a
  * handful of multiplications by the sign.  Scratch layout = the tensor-memory layout of SpecSerialRev<.,.,.,1>. */
-template <int ID_, int NL_>
+/* RG_ = 1: worlds with rigid pairs, all of them on the last link, MLCP solver (Core::rigid_mlcp_single).  Pass 2 runs
+ * twice per evaluation there, so the angular velocity keeps its own 3 slots next to U, and the last
+ * link publishes its world frame / velocity / acceleration (24 slots) for the contact solve. */
+template <int ID_, int NL_, int RG_ = 0>
 struct SpecSerialRevRolled {
-  static constexpr int ID = ID_, NL = NL_, UNROLL = 1, TM = 1, ROLL = 1;
-  static constexpr int WEXT = 6*NL_, RK = 4*(NL_-1), NSCRATCH = WEXT + 6, NTSPACE = 8*(NL_-1);
+  static constexpr int ID = ID_, NL = NL_, UNROLL = 1, TM = 1, ROLL = 1, RG = RG_;
+  /* RG: (sin, cos, 1/D, u) stay in the shared-memory column (SCS): the contact solve reads them for OTHER lanes'
+   * environments (lane-parallel probes) and in divergent code, which tensor memory allows neither */
+  static constexpr int SCS = RG_;
+  static constexpr int PER = RG_ ? 13 : 6, FRAME = PER*NL_, WEXT = FRAME + (RG_ ? 24 : 0);
+  static constexpr int RK = RG_ ? 0 : 4*(NL_-1), NSCRATCH = WEXT + 6, NTSPACE = (RG_ ? 4 : 8)*(NL_-1);
   static RKFD_HD int nl(const ModelDev &){ return NL_; }
   static RKFD_HD int jtype(int i, const LinkDev &){ return i == 0 ? J_FIXED : J_REVOL; }
   static RKFD_HD int parent(int i, const LinkDev &){ return i - 1; }
   static RKFD_HD int serial(int i, const LinkDev &){ return i > 0 ? 1 : 0; }
-  static RKFD_HD int slot(int i, const LinkDev &){ return 6*i; }
-  static RKFD_HD int wslot(int i, const LinkDev &){ return 6*i; }
+  static RKFD_HD int slot(int i, const LinkDev &){ return PER*i; }
+  static RKFD_HD int wslot(int i, const LinkDev &){ return PER*i + (RG_ ? 6 : 0); }
   static RKFD_HD int rcls(int i, const LinkDev &){ return i == 0 ? RO_GENERAL : RO_RXS; }
   static RKFD_HD int qofs(int i, const LinkDev &){ return i > 0 ? i - 1 : 0; }
   static RKFD_HD int ndof(int i, const LinkDev &){ return i > 0 ? 1 : 0; }
   static RKFD_HD int branch_slot(int, const LinkDev &){ return -1; }
   static RKFD_HD int accum_slot(int, const LinkDev &){ return -1; }
   static RKFD_HD int wext_slot(int i, const LinkDev &L){ return ( i == NL_-1 && L.cell_end > L.cell_begin ) ? WEXT : -1; }
-  static RKFD_HD int frame_slot(int, const LinkDev &){ return -1; }
+  static RKFD_HD int frame_slot(int i, const LinkDev &L){ return ( RG_ && i == NL_-1 && L.cell_end > L.cell_begin ) ? FRAME : -1; }
   static RKFD_HD int rk_slot(const ModelDev &){ return RK; }
   static RKFD_HD int nq(const ModelDev &){ return NL_ - 1; }
-  static RKFD_HD int sc(int i, const LinkDev &){ return 4*(i-1); }
+  static RKFD_HD int sc(int i, const LinkDev &){ return RG_ ? PER*i + 9 : 4*(i-1); }
 };
-inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL){
-  if( m.has_rigid || m.nl != NL || NL < 2 ) return false;
+inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0){
+  if( RG ? !( m.has_rigid && m.rigid_link == NL-1 ) : m.has_rigid ) return false;
+  if( m.nl != NL || NL < 2 ) return false;
   for(int i=0;i<NL;i++){
     const LinkDev &L = m.link[i];
     if( i == 0 ){ if( L.parent >= 0 || L.jtype != J_FIXED || L.cell_end > L.cell_begin ) return false; continue; }
@@ -240,12 +248,12 @@ inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
  * revolute links, frames alternating Rx(-90)/Rx(+90)); 2: fixed base + 2 parallel revolute links (arm_2DoF.ztk) */
 #define RKFD_SPEC_TABLE(X) X(3, 8, 0x3BBBu, 1) X(4, 3, 0x5u, 1) X(1, 8, 0x3BBBu, 0) X(2, 3, 0x5u, 0)
 /* rolled specialisations: (id, links); 5: fixed base + 7 revolute links, 6: + 6 revolute links */
-#define RKFD_SPEC_ROLLED_TABLE(X) X(5, 8) X(6, 7)
+#define RKFD_SPEC_ROLLED_TABLE(X) X(5, 8, 0) X(6, 7, 0) X(7, 8, 1)
 template <int ID> struct SpecOf { using type = SpecGeneric; };
 #define RKFD_SPEC_X(id, nl, cls, tm) template <> struct SpecOf<id> { using type = SpecSerialRev<id, nl, cls, tm>; };
 RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-#define RKFD_SPEC_X(id, nl) template <> struct SpecOf<id> { using type = SpecSerialRevRolled<id, nl>; };
+#define RKFD_SPEC_X(id, nl, rg) template <> struct SpecOf<id> { using type = SpecSerialRevRolled<id, nl, rg>; };
 RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
 /* specialisation ids the model is eligible for (bit id set; 0: generic kernel only), and their scratch sizes */
@@ -254,13 +262,13 @@ inline unsigned spec_match_mask(const ModelDev &m){
 #define RKFD_SPEC_X(id, nl, cls, tm) if( spec_serial_rev_match(m, nl, cls) ) mask |= 1u << id;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-#define RKFD_SPEC_X(id, nl) if( spec_serial_rev_rolled_match(m, nl) ) mask |= 1u << id;
+#define RKFD_SPEC_X(id, nl, rg) if( spec_serial_rev_rolled_match(m, nl, rg) ) mask |= 1u << id;
   RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return mask;
 }
 inline int spec_match_rolled(const ModelDev &m){
-#define RKFD_SPEC_X(id, nl) if( spec_serial_rev_rolled_match(m, nl) ) return id;
+#define RKFD_SPEC_X(id, nl, rg) if( spec_serial_rev_rolled_match(m, nl, rg) ) return id;
   RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return 0;
@@ -275,7 +283,7 @@ inline int spec_nscratch(int id){
 #define RKFD_SPEC_X(sid, nl, cls, tm) if( id == sid ) return SpecSerialRev<sid, nl, cls, tm>::NSCRATCH;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-#define RKFD_SPEC_X(sid, nl) if( id == sid ) return SpecSerialRevRolled<sid, nl>::NSCRATCH;
+#define RKFD_SPEC_X(sid, nl, rg) if( id == sid ) return SpecSerialRevRolled<sid, nl, rg>::NSCRATCH;
   RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return 0;
@@ -284,7 +292,7 @@ inline int spec_ntspace(int id){
 #define RKFD_SPEC_X(sid, nl, cls, tm) if( id == sid ) return SpecSerialRev<sid, nl, cls, tm>::NTSPACE;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-#define RKFD_SPEC_X(sid, nl) if( id == sid ) return SpecSerialRevRolled<sid, nl>::NTSPACE;
+#define RKFD_SPEC_X(sid, nl, rg) if( id == sid ) return SpecSerialRevRolled<sid, nl, rg>::NTSPACE;
   RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return 0;
@@ -333,6 +341,10 @@ struct Core {
    * the scratch column otherwise */
   RKFD_HD double T(int k){ return c.TL(k); }
   RKFD_HD void Tw(int k, double v){ c.TS(k, v); }
+  /* per-joint (sin, cos, 1/D, u): T space, or the scratch column when the specialisation says so (Spec::SCS) */
+  RKFD_HD double Q(int k){ return Spec::SCS ? c.S(k) : c.TL(k); }
+  RKFD_HD void Qw(int k, double v){ if( Spec::SCS ) c.S(k) = v; else c.TS(k, v); }
+  RKFD_HD void Q2(int k, double &a, double &b){ if( Spec::SCS ){ a = c.S(k); b = c.S(k+1); } else c.TL2(k, a, b); }
   RKFD_HD V3 t3(int k){ double x, y, z; c.TL2(k, x, y); z = c.TL(k+2); return v3(x, y, z); }
   RKFD_HD void tw3(int k, V3 v){ c.TS(k, v.x); c.TS(k+1, v.y); c.TS(k+2, v.z); }
   RKFD_HD V3 ld3(int k){ return v3(c.S(k), c.S(k+1), c.S(k+2)); }
@@ -346,7 +358,8 @@ struct Core {
 
   /* link frame w.r.t. parent and joint velocity (vJ,wJ, link frame) from the stage state and the joint data
    * cached by pass 1 ([EXT A-3]) */
-  template <class Kt>
+  /* VEL = false: the transform only (the contact-solve probes: no T-space access, which must be warp-uniform) */
+  template <class Kt, bool VEL = true>
   RKFD_HD XF joint_xform(const ModelDev &m, const LinkDev &L, int i, V3 &vJ, V3 &wJ){
     const int sl = Spec::slot(i,L), qs = rk0 + Spec::qofs(i,L), qds = rk0 + Spec::nq(m) + Spec::qofs(i,L);
     XF x; x.fast = 0; x.cls = CLS<Kt>(i,L); x.sg = ro_sign(x.cls, L.rsg); x.c = 1.0; x.s = 0.0;
@@ -354,25 +367,25 @@ struct Core {
     vJ = v3(0,0,0); wJ = v3(0,0,0);
     switch(JT<Kt>(i,L)){
     case J_REVOL: {
-      c.TL2(Spec::sc(i,L), x.s, x.c); x.p = org_p(L);
+      Q2(Spec::sc(i,L), x.s, x.c); x.p = org_p(L);
       if( CLS<Kt>(i,L) != RO_GENERAL ){ x.fast = 1; x.ptl = rz_tmul(x.c, x.s, v3(L.pol[0],L.pol[1],L.pol[2])); }
       else {
         const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
         x.R = from_cols(x.c*o0 + x.s*o1, x.c*o1 - x.s*o0, col2(Ro)); x.ptl = tmul(x.R, x.p);
       }
-      wJ.z = T(qds);
+      if( VEL ) wJ.z = T(qds);
     } break;
     case J_PRISM: {
-      x.R = org_R(L); x.p = org_p(L) + T(qs)*col2(x.R); x.ptl = tmul(x.R, x.p); vJ.z = T(qds);
+      x.R = org_R(L); x.p = org_p(L) + T(qs)*col2(x.R); x.ptl = tmul(x.R, x.p); if( VEL ) vJ.z = T(qds);
     } break;
     case J_SPHER: {
       x.R = ldm(sl+27); x.p = org_p(L); x.ptl = tmul(x.R, x.p);
-      wJ = tmul(x.R, mul(org_R(L), t3(qds)));
+      if( VEL ) wJ = tmul(x.R, mul(org_R(L), t3(qds)));
     } break;
     case J_FLOAT: {
       x.R = ldm(sl+6); x.p = ld3(sl+15); x.ptl = tmul(x.R, x.p);
       const M3 Ro = org_R(L);
-      vJ = tmul(x.R, mul(Ro, t3(qds))); wJ = tmul(x.R, mul(Ro, t3(qds+3)));
+      if( VEL ){ vJ = tmul(x.R, mul(Ro, t3(qds))); wJ = tmul(x.R, mul(Ro, t3(qds+3))); }
     } break;
     default: x.R = org_R(L); x.p = org_p(L); x.ptl = v3(L.pol[0],L.pol[1],L.pol[2]); break;
     }
@@ -503,8 +516,8 @@ struct Core {
       switch(JT<Kt>(i,L)){
       case J_REVOL: {
         double sn, co;
-        if( fresh ){ sincos(T(qs+qo), &sn, &co); Tw(Spec::sc(i,L), sn); Tw(Spec::sc(i,L)+1, co); }
-        else c.TL2(Spec::sc(i,L), sn, co);
+        if( fresh ){ sincos(T(qs+qo), &sn, &co); Qw(Spec::sc(i,L), sn); Qw(Spec::sc(i,L)+1, co); }
+        else Q2(Spec::sc(i,L), sn, co);
         x.s = sn; x.c = co; x.p = org_p(L);
         if( CLS<Kt>(i,L) != RO_GENERAL ) x.fast = 1;
         else { const M3 Ro = org_R(L); const V3 o0 = col0(Ro), o1 = col1(Ro);
@@ -645,7 +658,7 @@ struct Core {
         double jm; const double tau = joint_torque(m, L, i, ref, jm, pf_u, pf_prev);
         const V3 Ul = col2(B), Ua = v3(C.xz, C.yz, C.zz);
         const double Dinv = 1.0/(C.zz + jm), u = tau - pn.z;
-        st3(sl, Ul); st3(sl+3, Ua); Tw(Spec::sc(i,L)+2, Dinv); Tw(Spec::sc(i,L)+3, u);
+        st3(sl, Ul); st3(sl+3, Ua); Qw(Spec::sc(i,L)+2, Dinv); Qw(Spec::sc(i,L)+3, u);
         const V3 Wl = Dinv*Ul, Wa = Dinv*Ua;
         A.xx-=Wl.x*Ul.x; A.xy-=Wl.x*Ul.y; A.xz-=Wl.x*Ul.z; A.yy-=Wl.y*Ul.y; A.yz-=Wl.y*Ul.z; A.zz-=Wl.z*Ul.z;
         C.xx-=Wa.x*Ua.x; C.xy-=Wa.x*Ua.y; C.xz-=Wa.x*Ua.z; C.yy-=Wa.y*Ua.y; C.yz-=Wa.y*Ua.z; C.zz-=Wa.z*Ua.z;
@@ -656,7 +669,7 @@ struct Core {
         double jm; const double tau = joint_torque(m, L, i, ref, jm, pf_u, pf_prev);
         const V3 Ul = v3(A.xz, A.yz, A.zz), Ua = v3(B.zx, B.zy, B.zz);
         const double Dinv = 1.0/(A.zz + jm), u = tau - pf.z;
-        st3(sl, Ul); st3(sl+3, Ua); Tw(Spec::sc(i,L)+2, Dinv); Tw(Spec::sc(i,L)+3, u);
+        st3(sl, Ul); st3(sl+3, Ua); Qw(Spec::sc(i,L)+2, Dinv); Qw(Spec::sc(i,L)+3, u);
         const V3 Wl = Dinv*Ul, Wa = Dinv*Ua;
         A.xx-=Wl.x*Ul.x; A.xy-=Wl.x*Ul.y; A.xz-=Wl.x*Ul.z; A.yy-=Wl.y*Ul.y; A.yz-=Wl.y*Ul.z; A.zz-=Wl.z*Ul.z;
         C.xx-=Wa.x*Ua.x; C.xy-=Wa.x*Ua.y; C.xz-=Wa.x*Ua.z; C.yy-=Wa.y*Ua.y; C.yz-=Wa.y*Ua.z; C.zz-=Wa.z*Ua.z;
@@ -759,7 +772,7 @@ struct Core {
     const double cd = fma(d2, fma(d2, fma(d2, fma(d2, 1.0/40320.0, -1.0/720.0), 1.0/24.0), -0.5), 1.0);
     double sn = fma(s0, cd, c0*sd), co = fma(c0, cd, -(s0*sd));
     if( !(fabs(d) <= 0.0625) ) sincos(qnew, &sn, &co);
-    Tw(sc, sn); Tw(sc+1, co);
+    Qw(sc, sn); Qw(sc+1, co);
   }
   /* rotation (angle-axis) component triple starting at j: increments compose on SO(3) */
   RKFD_HD void rk_rot(const ModelDev &m, const RK &k, int stage, int slotS, int slotP, double *gin, double *gout, int j, V3 w){
@@ -825,7 +838,7 @@ struct Core {
       switch(JT<Kt>(i,L)){
       case J_REVOL: case J_PRISM: {
         const V3 Ul = ld3(sl), Ua = ld3(sl+3);
-        double Dinv, uu; c.TL2(Spec::sc(i,L)+2, Dinv, uu);
+        double Dinv, uu; Q2(Spec::sc(i,L)+2, Dinv, uu);
         const double acc = Dinv*fma(-Ua.z,xa.z,fma(-Ua.y,xa.y,fma(-Ua.x,xa.x,fma(-Ul.z,xl.z,fma(-Ul.y,xl.y,fma(-Ul.x,xl.x,uu))))));
         if( JT<Kt>(i,L) == J_REVOL ){
           al = cadd(xl, omp, cross(omp, x.ptl));
@@ -890,7 +903,7 @@ struct Core {
       default: al = xl + zl; aa = xa + za; break;
       }
       if( JT<Kt>(i,L) == J_REVOL ) om = v3(omp.x, omp.y, omp.z + wJ.z); else om = omp + wJ;
-      if( Spec::frame_slot(i,L) >= 0 ){ st3(L.frame_slot+18, al); st3(L.frame_slot+21, aa); }
+      if( Spec::frame_slot(i,L) >= 0 ){ st3(Spec::frame_slot(i,L)+18, al); st3(Spec::frame_slot(i,L)+21, aa); }
       if( Spec::branch_slot(i,L) >= 0 ){ st3(L.branch_slot, al); st3(L.branch_slot+3, aa); st3(L.branch_slot+6, om); }
     };
     links_fwd(m, body);
@@ -931,7 +944,7 @@ struct Core {
       case J_REVOL: case J_PRISM: {
         const double du = L.jtype == J_REVOL ? -dpn.z : -dpf.z;
         c.W(du0+6*i) = du;
-        const double k = T(Spec::sc(i,L)+2)*du;
+        const double k = Q(Spec::sc(i,L)+2)*du;
         paf = dpf + k*ld3(sl); pan = dpn + k*ld3(sl+3);
       } break;
       case J_SPHER: {
@@ -945,7 +958,7 @@ struct Core {
       default: break;
       }
       if( L.parent < 0 || L.jtype == J_FLOAT ) break;
-      V3 vJ, wJ; const XF x = joint_xform<TagRT>(m, L, i, vJ, wJ);
+      V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
       dpf = xf_mul(x, paf); dpn = xf_mul(x, pan) + cross(x.p, dpf);
       i = L.parent;
     }
@@ -953,11 +966,11 @@ struct Core {
       const LinkDev &L = m.link[i]; const int sl = L.slot;
       V3 al = v3(0,0,0), aa = v3(0,0,0);
       if( L.parent >= 0 ){ al = w3(da0+6*L.parent); aa = w3(da0+6*L.parent+3); }
-      V3 vJ, wJ; const XF x = joint_xform<TagRT>(m, L, i, vJ, wJ);
+      V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
       V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
       switch(L.jtype){
       case J_REVOL: case J_PRISM: {
-        const double acc = T(Spec::sc(i,L)+2)*( c.W(du0+6*i) - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
+        const double acc = Q(Spec::sc(i,L)+2)*( c.W(du0+6*i) - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
         if( L.jtype == J_REVOL ) xa.z += acc; else xl.z += acc;
       } break;
       case J_SPHER: {
@@ -998,14 +1011,14 @@ struct Core {
   RKFD_HD void probe_link(const ModelDev &m, int Lc, V3 dpf, V3 dpn, V3 &ral, V3 &raa){
     double du[6*MAX_LINKS]; int pth[MAX_LINKS]; int np = 0;
     for(int i=Lc;;){
-      const LinkDev &L = m.link[i]; const int sl = L.slot;
+      const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = Spec::jtype(i,L);
       pth[np] = i;
       V3 paf = dpf, pan = dpn;
-      switch(L.jtype){
+      switch(jt){
       case J_REVOL: case J_PRISM: {
-        const double d = L.jtype == J_REVOL ? -dpn.z : -dpf.z;
+        const double d = jt == J_REVOL ? -dpn.z : -dpf.z;
         du[6*np] = d;
-        const double k = T(Spec::sc(i,L)+2)*d;
+        const double k = Q(Spec::sc(i,L)+2)*d;
         paf = dpf + k*ld3(sl); pan = dpn + k*ld3(sl+3);
       } break;
       case J_SPHER: {
@@ -1019,20 +1032,20 @@ struct Core {
       default: break;
       }
       np++;
-      if( L.parent < 0 || L.jtype == J_FLOAT ) break;
-      V3 vJ, wJ; const XF x = joint_xform<TagRT>(m, L, i, vJ, wJ);
+      if( Spec::parent(i,L) < 0 || jt == J_FLOAT ) break;
+      V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
       dpf = xf_mul(x, paf); dpn = xf_mul(x, pan) + cross(x.p, dpf);
-      i = L.parent;
+      i = Spec::parent(i,L);
     }
     V3 al = v3(0,0,0), aa = v3(0,0,0);
     for(int q=np-1;q>=0;q--){
-      const int i = pth[q]; const LinkDev &L = m.link[i]; const int sl = L.slot;
-      V3 vJ, wJ; const XF x = joint_xform<TagRT>(m, L, i, vJ, wJ);
+      const int i = pth[q]; const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = Spec::jtype(i,L);
+      V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
       V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
-      switch(L.jtype){
+      switch(jt){
       case J_REVOL: case J_PRISM: {
-        const double acc = T(Spec::sc(i,L)+2)*( du[6*q] - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
-        if( L.jtype == J_REVOL ) xa.z += acc; else xl.z += acc;
+        const double acc = Q(Spec::sc(i,L)+2)*( du[6*q] - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
+        if( jt == J_REVOL ) xa.z += acc; else xl.z += acc;
       } break;
       case J_SPHER: {
         const V3 rhs = v3(du[6*q],du[6*q+1],du[6*q+2]) - (tmul(ldm(sl), xl) + tmul(ldm(sl+9), xa));
@@ -1053,13 +1066,14 @@ struct Core {
   RKFD_HD void rigid_mlcp_single(const ModelDev &m, bool ref, unsigned act){
     const int nlanes = c.lanes(), lane = c.lane();
     const int Lc = m.rigid_link; const LinkDev &LL = m.link[Lc];
+    const int fsl = Spec::frame_slot(Lc, LL), wsl = Spec::wext_slot(Lc, LL);
     /* ---- Lambda: lanes over (environment of the warp with contacts, wrench component) */
     const int nact = RKFD_POPC64((unsigned long long)act);
     for(int t=lane; t<6*nact; t+=nlanes){
       const int j = t/6, comp = t - 6*j;
       unsigned a = act; for(int q=0;q<j;q++) a &= a - 1;
       c.select(RKFD_FFS32(a) - 1);
-      const M3 Rw = ldm(LL.frame_slot);
+      const M3 Rw = ldm(fsl);
       const int ax = comp < 3 ? comp : comp - 3;
       const V3 el = ax == 0 ? v3(Rw.xx, Rw.xy, Rw.xz) : ( ax == 1 ? v3(Rw.yx, Rw.yy, Rw.yz) : v3(Rw.zx, Rw.zy, Rw.zz) );   /* Rw^T e_ax */
       const V3 z = v3(0,0,0);
@@ -1076,8 +1090,8 @@ struct Core {
     double lam[36];
 #pragma unroll
     for(int i=0;i<36;i++) lam[i] = c.W1(i);            /* lam[6*col + row] */
-    const M3 Rw = ldm(LL.frame_slot); const V3 pw = ld3(LL.frame_slot+9), vl = ld3(LL.frame_slot+12), om = ld3(LL.frame_slot+15);
-    const V3 al = ld3(LL.frame_slot+18), aa = ld3(LL.frame_slot+21);
+    const M3 Rw = ldm(fsl); const V3 pw = ld3(fsl+9), vl = ld3(fsl+12), om = ld3(fsl+15);
+    const V3 al = ld3(fsl+18), aa = ld3(fsl+21);
     const V3 vlw = mul(Rw, vl), omw = mul(Rw, om);
     /* contacts in (pair, vertex) order: geometry, rows h, responses g = Lambda h, bias b (rkfd_mlcp.c:104-188) */
     { int k = 0;
@@ -1096,7 +1110,8 @@ struct Core {
         const V3 vel = vlw + cross(omw, rho);
         /* rkFDLinkPointWldAcc (rkfd_util.c:92-101): R ( a + alpha x r + w x (w x r) ) */
         const V3 r = tmul(Rw, rho);
-        const V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r)));
+        V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r)));
+        if( grav_acc(m) ) accp.z -= GRAVITY;       /* link accelerations carry the fictitious base acceleration there */
         const double mu = ( (fl >> (2*s+1)) & 1ull ) ? pr.KF : pr.SF;
         const int o = W1_CT + W1_CTN*k;
         for(int i=0;i<3;i++){
@@ -1175,8 +1190,8 @@ struct Core {
       wl = wl + fll; wa = wa + cross(pos, fll);
       if( ref ){ c.gst(c.st.cf,3*s,fw.x); c.gst(c.st.cf,3*s+1,fw.y); c.gst(c.st.cf,3*s+2,fw.z); }
     }
-    c.S(LL.wext_slot) += wl.x; c.S(LL.wext_slot+1) += wl.y; c.S(LL.wext_slot+2) += wl.z;
-    c.S(LL.wext_slot+3) += wa.x; c.S(LL.wext_slot+4) += wa.y; c.S(LL.wext_slot+5) += wa.z;
+    c.S(wsl) += wl.x; c.S(wsl+1) += wl.y; c.S(wsl+2) += wl.z;
+    c.S(wsl+3) += wa.x; c.S(wsl+4) += wa.y; c.S(wsl+5) += wa.z;
     cfl = nfl;
   }
 
@@ -1564,8 +1579,9 @@ struct Core {
 #pragma unroll 1
       for(int round = act ? 0 : 1; round < 2; round++){
         pass2(m, round ? ref : false);
+        c.tfence();
         pass3(m, round ? stage : (int)ST_PROBE);
-        if( round == 0 ) rigid_solve(m, ref, act);
+        if( round == 0 ){ rigid_solve(m, ref, act); c.gsync(); }     /* lanes leave the solve at different points: reconverge */
       }
       return;
     }

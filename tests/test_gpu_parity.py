@@ -381,3 +381,40 @@ def test_kernel_variants_agree(capi, oracle, monkeypatch, variant):
     n = 48
     oq, oqd, oqdd, _ = oracle.OracleWorld(w).batch_run(q[:n], qd[:n], u[:n], nsteps=25)
     assert relerr(gq[:n], oq) < 1e-9 and relerr(gqd[:n], oqd) < 1e-8
+
+
+@pytest.mark.parametrize("variant", [(7, 128, 2), (7, 64, 4), (0, 128, 1)], ids=lambda v: "spec%d_block%d_minb%d" % v)
+def test_rigid_mlcp_kernel_variants_agree(capi, oracle, monkeypatch, variant):
+    """C5 with the MLCP solver (single-link wrench-space path): the rolled rigid specialisation and the generic
+    kernel against each other and against the oracle, over a batch that fills several CTAs per SM."""
+    spec, block, minb = variant
+    w = ch.world_c5(base_z=0.1, solver="MLCP")
+    B = 148 * 2 * 128 + 33
+    q, qd, u = ch.sample_state(w, B, seed=23)
+
+    def run(env, nsteps):
+        for k in ("RKFD_SPEC", "RKFD_FORCE_BLOCK", "RKFD_FORCE_MINB"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, str(v))
+        fd = gpu_world(capi, w, q, qd, u)
+        first = fd.batch_get_state()[2].copy(), fd.batch_get_contact()
+        fd.update_n(nsteps)
+        out = first, fd.batch_get_state()
+        fd.destroy()
+        return out
+
+    (a1, c1), (q1, qd1, _) = run({"RKFD_SPEC": spec, "RKFD_FORCE_BLOCK": block, "RKFD_FORCE_MINB": minb}, 8)
+    (a0, c0), (q0, qd0, _) = run({"RKFD_SPEC": 0}, 8)
+    assert c0[0].sum() > 1000 and (c0[0] == c1[0]).all()
+    assert relerr(a1, a0) < 1e-9
+    fin = np.isfinite(q0).all(1) & (np.abs(q0).max(1) < 1e3)      # envs that start deep inside the floor blow up
+    assert fin.mean() > 0.9
+    d = np.abs(q1[fin] - q0[fin]).max(1)
+    assert (d < 1e-8).mean() > 0.999
+    n = 32
+    ow = oracle.OracleWorld(w)
+    for b in range(n):
+        e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
+        ref = e.eval(True)
+        assert relerr(a1[b], ref) < 1e-8, b

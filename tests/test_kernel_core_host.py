@@ -245,8 +245,36 @@ def test_rolled_specialisation_matches_generic(name):
     assert (c0[0] == c1[0]).all() and (p0[0] == p1[0]).all()
 
 
+def test_rolled_rigid_specialisation_matches_generic(oracle):
+    """C5 with the MLCP solver: the rolled specialisation with the rigid scratch layout (gravity as base
+    acceleration, corrected in the contact-point accelerations) against the generic kernel and the oracle."""
+    w = ch.world_c5(base_z=0.1, solver="MLCP")
+    B, nsteps = 64, 12
+    q, qd, u = ch.sample_state(w, B, seed=5)
+    out = []
+    for spec in (None, "rolled"):
+        hs = HostSim(w, B, spec=spec)
+        assert hs.spec_rolled == 7
+        hs.set_state(q, qd, u); hs.eval(ref=True)
+        first = hs.get_state()[2].copy(), hs.get_contact()
+        hs.step(nsteps)
+        out.append((first, hs.get_state()))
+    (a0, c0), (q0, qd0, _) = out[0]
+    (a1, c1), (q1, qd1, _) = out[1]
+    assert c0[0].sum() > 10 and (c0[0] == c1[0]).all() and (c0[1] == c1[1]).all()
+    assert relerr(a1, a0) < 1e-9 and np.allclose(c1[3], c0[3], rtol=1e-9, atol=1e-9)
+    # random initial states that start with the whole cube below the floor blow up (in the oracle too): skip them
+    fin = np.isfinite(q0).all(1) & (np.abs(q0).max(1) < 1e3)
+    assert fin.sum() >= B - 4 and (np.isfinite(q1).all(1) == np.isfinite(q0).all(1)).all()
+    assert relerr(q1[fin], q0[fin]) < 1e-10 and relerr(qd1[fin], qd0[fin]) < 1e-8
+    ref = oracle_run(oracle, w, q, qd, u, nsteps)
+    ok = sum(relerr(q1[b, :w.nq], ref[b][0][0]) < 1e-7 for b in np.where(fin)[0])
+    assert ok >= fin.sum() - 1, ok
+
+
 def test_specialisation_not_picked_for_other_shapes():
-    assert HostSim(ch.world_c5(base_z=0.1), 1).spec == 0                      # rigid pairs
+    hs = HostSim(ch.world_c5(base_z=0.1, solver="Vert"), 1)                   # rigid pairs, Vert solver
+    assert hs.spec == 0 and hs.spec_tm == 0 and hs.spec_rolled == 0
     assert HostSim(ch.World(chains=[ch.box(), ch.floor_soft()]), 1).spec == 0  # float joint
     rng = np.random.default_rng(0)
     assert HostSim(ch.World(chains=[ch.random_chain(rng, 8, jtypes=("revolute",))]), 1).spec == 0   # general frames
