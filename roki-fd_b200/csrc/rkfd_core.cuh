@@ -1063,11 +1063,12 @@ struct Core {
     ral = al; raa = aa;
   }
 
-  RKFD_HD void rigid_mlcp_single(const ModelDev &m, bool ref, unsigned act){
+  /* Lambda (6x6, column-major in W1[0..35]) of the contact link of every environment in `act`: lanes over
+   * (environment of the warp with contacts, wrench component) */
+  RKFD_HD void lambda_probes(const ModelDev &m, unsigned act){
     const int nlanes = c.lanes(), lane = c.lane();
     const int Lc = m.rigid_link; const LinkDev &LL = m.link[Lc];
-    const int fsl = Spec::frame_slot(Lc, LL), wsl = Spec::wext_slot(Lc, LL);
-    /* ---- Lambda: lanes over (environment of the warp with contacts, wrench component) */
+    const int fsl = Spec::frame_slot(Lc, LL);
     const int nact = RKFD_POPC64((unsigned long long)act);
     for(int t=lane; t<6*nact; t+=nlanes){
       const int j = t/6, comp = t - 6*j;
@@ -1083,6 +1084,12 @@ struct Core {
       c.unselect();
     }
     c.gsync();
+  }
+
+  RKFD_HD void rigid_mlcp_single(const ModelDev &m, bool ref, unsigned act){
+    const int Lc = m.rigid_link; const LinkDev &LL = m.link[Lc];
+    const int fsl = Spec::frame_slot(Lc, LL), wsl = Spec::wext_slot(Lc, LL);
+    lambda_probes(m, act);
     /* ---- one environment per lane from here on */
     const unsigned long long fl = cfl;
     const int N = RKFD_POPC64(fl & m.rigid_mask);
@@ -1195,8 +1202,249 @@ struct Core {
     cfl = nfl;
   }
 
+  /* =====================================================================================================
+   * Vert (friction pyramid + least-squares QP by the active-set method, rkfd_vert.c:73-324, rkfd_opt_qp.c:43-181)
+   * when every rigid contact sits on ONE link, one environment per lane, no N x N matrix:
+   *   A = H Lambda H^T  (rows h = (axis, rho x axis), Lambda 6x6)  =>  Q = A^T A + diag(L) = diag(L) + H M H^T,
+   *   M = Lambda^T (H^T H) Lambda,  c = A^T c0 = H w,  w = Lambda^T H^T c0.
+   * The pyramid rows of a vertex only touch that vertex's 3 unknowns, so the equality-constrained problem of an
+   * active-set iteration is solved exactly in closed form: with Pi_k the 3x3 projector onto the null space of the
+   * active rows of vertex k and P = sum_k (1/L_k) H_k^T Pi_k H_k (6x6),
+   *   (I + P M) v = -P w,   u = M v + w,   x*_k = -(1/L_k) Pi_k H_k u,
+   * and the multipliers are the minimum-norm solutions of N_k^T l_k = (I - Pi_k) H_k u per vertex (1x1 / 2x2 / 3x3
+   * systems) - the same x* and the same minimum-norm multipliers the reference takes from the pseudo-inverse of
+   * the singular KKT matrix ([EXT A-14]), without a pseudo-inverse.  The active-set logic (identical-point test,
+   * release of the most negative multipliers, step to the first blocking row, anti-cycling history) is the
+   * reference's.
+   * ===================================================================================================== */
+  RKFD_HD bool solve6(double (&a)[36], double (&b)[6]){      /* a x = b by Gaussian elimination with partial pivoting; x -> b */
+    for(int k=0;k<6;k++){
+      int p = k; double big = fabs(a[6*k+k]);
+      for(int i=k+1;i<6;i++) if( fabs(a[6*i+k]) > big ){ big = fabs(a[6*i+k]); p = i; }
+      if( !(big > 0.0) ) return false;
+      if( p != k ){ for(int j=0;j<6;j++){ const double t = a[6*k+j]; a[6*k+j] = a[6*p+j]; a[6*p+j] = t; } const double t = b[k]; b[k] = b[p]; b[p] = t; }
+      const double inv = 1.0/a[6*k+k];
+      for(int i=k+1;i<6;i++){ const double f = a[6*i+k]*inv; if( f != 0.0 ){ for(int j=k;j<6;j++) a[6*i+j] -= f*a[6*k+j]; b[i] -= f*b[k]; } }
+    }
+    for(int k=5;k>=0;k--){ double sum = b[k]; for(int j=k+1;j<6;j++) sum -= a[6*k+j]*b[j]; b[k] = sum/a[6*k+k]; }
+    return true;
+  }
+  /* projector onto the null space of the active pyramid rows (mask am) of a vertex with friction coefficient fric */
+  RKFD_HD void pyramid_projector(const ModelDev &m, unsigned am, double fric, double (&pi)[9]){
+    const int na = RKFD_POPC64((unsigned long long)am);
+    for(int i=0;i<9;i++) pi[i] = 0.0;
+    if( na == 0 ){ pi[0] = pi[4] = pi[8] = 1.0; return; }
+    if( na >= 3 ) return;
+    const int i0 = RKFD_FFS32(am) - 1; const V3 a0 = v3(fric, m.sc_sin[i0], m.sc_cos[i0]);
+    if( na == 1 ){
+      const double inv = 1.0/dot(a0,a0);
+      pi[0] = 1.0 - a0.x*a0.x*inv; pi[1] = -a0.x*a0.y*inv; pi[2] = -a0.x*a0.z*inv;
+      pi[3] = pi[1]; pi[4] = 1.0 - a0.y*a0.y*inv; pi[5] = -a0.y*a0.z*inv;
+      pi[6] = pi[2]; pi[7] = pi[5]; pi[8] = 1.0 - a0.z*a0.z*inv;
+      return;
+    }
+    const int i1 = RKFD_FFS32(am & (am - 1)) - 1; const V3 a1 = v3(fric, m.sc_sin[i1], m.sc_cos[i1]);
+    const V3 nn = cross(a0, a1); const double inv = 1.0/dot(nn,nn);
+    pi[0] = nn.x*nn.x*inv; pi[1] = nn.x*nn.y*inv; pi[2] = nn.x*nn.z*inv;
+    pi[3] = pi[1]; pi[4] = nn.y*nn.y*inv; pi[5] = nn.y*nn.z*inv;
+    pi[6] = pi[2]; pi[7] = pi[5]; pi[8] = nn.z*nn.z*inv;
+  }
+
+  RKFD_HD void rigid_vert_single(const ModelDev &m, bool ref, unsigned act){
+    const int Lc = m.rigid_link; const LinkDev &LL = m.link[Lc];
+    const int fsl = Spec::frame_slot(Lc, LL), wsl = Spec::wext_slot(Lc, LL);
+    lambda_probes(m, act);
+    const unsigned long long fl = cfl;
+    const int N = RKFD_POPC64(fl & m.rigid_mask);
+    if( N == 0 ) return;
+    const int pyr = m.pyramid, QP_HIST = 32, QP_MAXIT = 256;
+    const int nrs = m.nmax/3, ohist = W1_CT + W1_CTN*nrs;
+    double lam[36];
+    for(int i=0;i<36;i++) lam[i] = c.W1(i);            /* lam[6*col + row] */
+    const M3 Rw = ldm(fsl); const V3 pw = ld3(fsl+9), vl = ld3(fsl+12), om = ld3(fsl+15);
+    const V3 al = ld3(fsl+18), aa = ld3(fsl+21);
+    const V3 vlw = mul(Rw, vl), omw = mul(Rw, om);
+    /* contacts in (pair, vertex) order: rows h, compensated velocity-level bias c0 (rkfd_vert.c:107-123, 189-232);
+     * per contact in W1: x (0..2) x* (3..5) h (18..35) c0 (36..38) fric (39) L (40) rho (45..47) prob (48..50) mu slot */
+    double G[36], hc[6];
+    for(int i=0;i<36;i++) G[i] = 0.0;
+    for(int i=0;i<6;i++) hc[i] = 0.0;
+    { int k = 0;
+      for(int s=0;s<m.nslot;s++){
+        if( !( (fl & m.rigid_mask) >> (2*s) & 1ull ) ) continue;
+        const PairDev &pr = m.pair[m.slot_pair[s]]; const CellDev &cl = m.cell[pr.cell]; const BoxDev &bx = m.box[pr.box];
+        const int vi = cl.vofs + m.slot_vert[s];
+        const V3 rl = v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2]);
+        const M3 Rb = box_R(bx); const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
+        const V3 vw = pw + mul(Rw, rl), vb = tmul(Rb, vw - pb);
+        V3 ax[3], prob;
+        box_face(bx, Rb, vb, bx.half[0]-fabs(vb.x), bx.half[1]-fabs(vb.y), bx.half[2]-fabs(vb.z), ax[0], ax[1], ax[2], prob);
+        const V3 refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
+        const V3 d = vw - (pb + mul(Rb, refb));
+        const V3 rho = vw - pw;
+        const V3 vel = vlw + cross(omw, rho);
+        const V3 r = tmul(Rw, rho);
+        V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r)));
+        if( grav_acc(m) ) accp.z -= GRAVITY;
+        const double mu = ( (fl >> (2*s+1)) & 1ull ) ? pr.KF : pr.SF;
+        const int o = W1_CT + W1_CTN*k;
+        for(int i=0;i<3;i++){
+          const V3 hl = ax[i], ha = cross(rho, ax[i]);
+          const double h[6] = {hl.x, hl.y, hl.z, ha.x, ha.y, ha.z};
+          const double c0 = dot(ax[i], accp)*m.dt + dot(vel, ax[i]) + pr.K * ( i == 0 ? 1.0 : mu ) * dot(d, ax[i]);
+          for(int rr=0;rr<6;rr++){ c.W1(o+18+6*i+rr) = h[rr]; hc[rr] += h[rr]*c0; for(int cc=0;cc<6;cc++) G[6*rr+cc] += h[rr]*h[cc]; }
+          c.W1(o+36+i) = c0;
+          c.W1(o+i) = i == 0 ? 1.0 : 0.0;            /* initial point f_n = 1 per vertex (rkfd_vert.c:234-244) */
+        }
+        c.W1(o+39) = mu*m.sc_cos[0]; c.W1(o+40) = pr.L;
+        sw13(o+45, rho); sw13(o+48, prob); c.W1(o+51) = mu; c.W1(o+52) = (double)s;
+        k++;
+      } }
+    /* M = Lambda^T G Lambda, w = Lambda^T hc   (Lambda[r][c] = lam[6c + r]) */
+    double M[36], w[6];
+    { double T[36];
+      for(int r=0;r<6;r++) for(int cc=0;cc<6;cc++){ double sum = 0; for(int j=0;j<6;j++) sum += G[6*r+j]*lam[6*cc+j]; T[6*r+cc] = sum; }      /* G Lambda */
+      for(int r=0;r<6;r++) for(int cc=0;cc<6;cc++){ double sum = 0; for(int j=0;j<6;j++) sum += lam[6*r+j]*T[6*j+cc]; M[6*r+cc] = sum; }       /* Lambda^T (G Lambda) */
+      for(int r=0;r<6;r++){ double sum = 0; for(int j=0;j<6;j++) sum += lam[6*r+j]*hc[j]; w[r] = sum; } }
+    /* initial active set (rkfd_opt_qp.c:27-40) */
+    unsigned am[MAX_SLOTS];
+    for(int k=0;k<N;k++){
+      const int o = W1_CT + W1_CTN*k; const double fric = c.W1(o+39); unsigned a = 0;
+      for(int i=0;i<pyr;i++){ const double cond = fric*c.W1(o) + m.sc_sin[i]*c.W1(o+1) + m.sc_cos[i]*c.W1(o+2); if( fabs(cond) < ZTOL ) a |= 1u << i; }
+      am[k] = a;
+    }
+    int nhist = 0;
+    for(int iter=0; iter<QP_MAXIT; iter++){
+      /* ---- x* of the equality-constrained problem */
+      double P[36];
+      for(int i=0;i<36;i++) P[i] = 0.0;
+      for(int k=0;k<N;k++){
+        const int o = W1_CT + W1_CTN*k; double pi[9];
+        pyramid_projector(m, am[k], c.W1(o+39), pi);
+        const double il = 1.0/c.W1(o+40);
+        for(int a=0;a<3;a++) for(int b=0;b<3;b++){
+          const double pab = pi[3*a+b]*il; if( pab == 0.0 ) continue;
+          for(int rr=0;rr<6;rr++){ const double ha = c.W1(o+18+6*a+rr)*pab; for(int cc=0;cc<6;cc++) P[6*rr+cc] += ha*c.W1(o+18+6*b+cc); }
+        }
+      }
+      double K6[36], v[6], u[6];
+      for(int r=0;r<6;r++){ double sum = 0; for(int cc=0;cc<6;cc++){ double pm = 0; for(int j=0;j<6;j++) pm += P[6*r+j]*M[6*j+cc]; K6[6*r+cc] = pm + (r == cc ? 1.0 : 0.0); sum += P[6*r+cc]*w[cc]; } v[r] = -sum; }
+      if( !solve6(K6, v) ){ bad |= 2; break; }
+      for(int r=0;r<6;r++){ double sum = w[r]; for(int j=0;j<6;j++) sum += M[6*r+j]*v[j]; u[r] = sum; }
+      bool same = true, neg = false; double lmin = 0; bool first = true;
+      for(int k=0;k<N;k++){
+        const int o = W1_CT + W1_CTN*k; double pi[9];
+        pyramid_projector(m, am[k], c.W1(o+39), pi);
+        const double il = 1.0/c.W1(o+40);
+        double hu[3];
+        for(int a=0;a<3;a++){ double sum = 0; for(int rr=0;rr<6;rr++) sum += c.W1(o+18+6*a+rr)*u[rr]; hu[a] = sum; }
+        for(int a=0;a<3;a++){
+          const double xs = -il*(pi[3*a]*hu[0] + pi[3*a+1]*hu[1] + pi[3*a+2]*hu[2]);
+          c.W1(o+3+a) = xs;
+          if( !(fabs(xs - c.W1(o+a)) < ZTOL) ) same = false;
+        }
+      }
+      if( same ){
+        /* multipliers: minimum-norm solution of N_k^T l_k = L_k x*_k + H_k u per vertex */
+        for(int k=0;k<N;k++){
+          const int o = W1_CT + W1_CTN*k; const unsigned a = am[k]; const int na = RKFD_POPC64((unsigned long long)a);
+          c.W1(o) = c.W1(o+3); c.W1(o+1) = c.W1(o+4); c.W1(o+2) = c.W1(o+5);
+          if( na == 0 ) continue;
+          const double fric = c.W1(o+39), Lk = c.W1(o+40);
+          V3 r;
+          { double hu[3]; for(int ax=0;ax<3;ax++){ double sum = 0; for(int rr=0;rr<6;rr++) sum += c.W1(o+18+6*ax+rr)*u[rr]; hu[ax] = sum; }
+            r = v3(Lk*c.W1(o+3) + hu[0], Lk*c.W1(o+4) + hu[1], Lk*c.W1(o+5) + hu[2]); }
+          if( na == 1 ){
+            const int i0 = RKFD_FFS32(a) - 1; const V3 a0 = v3(fric, m.sc_sin[i0], m.sc_cos[i0]);
+            const double l = dot(a0, r)/dot(a0, a0);
+            c.W1(o+6+0) = l;       /* multipliers of this vertex in slots 6.. (up to pyr <= 12 of them: 6..17) */
+          } else if( na == 2 ){
+            const int i0 = RKFD_FFS32(a) - 1, i1 = RKFD_FFS32(a & (a - 1)) - 1;
+            const V3 a0 = v3(fric, m.sc_sin[i0], m.sc_cos[i0]), a1 = v3(fric, m.sc_sin[i1], m.sc_cos[i1]);
+            const double g00 = dot(a0,a0), g01 = dot(a0,a1), g11 = dot(a1,a1), r0 = dot(a0,r), r1 = dot(a1,r);
+            const double det = g00*g11 - g01*g01;
+            c.W1(o+6+0) = (g11*r0 - g01*r1)/det; c.W1(o+6+1) = (g00*r1 - g01*r0)/det;
+          } else {
+            S3 sg; sg.xx=sg.xy=sg.xz=sg.yy=sg.yz=sg.zz=0;
+            for(int i=0;i<pyr;i++) if( a >> i & 1u ){ const V3 ai = v3(fric, m.sc_sin[i], m.sc_cos[i]);
+              sg.xx += ai.x*ai.x; sg.xy += ai.x*ai.y; sg.xz += ai.x*ai.z; sg.yy += ai.y*ai.y; sg.yz += ai.y*ai.z; sg.zz += ai.z*ai.z; }
+            const V3 z = mul(sym3_inverse(sg), r);
+            int t = 0;
+            for(int i=0;i<pyr;i++) if( a >> i & 1u ){ c.W1(o+6+t) = fric*z.x + m.sc_sin[i]*z.y + m.sc_cos[i]*z.z; t++; }
+          }
+          for(int t=0;t<na;t++){ const double l = c.W1(o+6+t); if( l < 0 ) neg = true; if( first || l < lmin ){ lmin = l; first = false; } }
+        }
+        if( !neg ) break;                                  /* optimal */
+        for(int k=0;k<N;k++){                               /* release every row within 1e-8 of the most negative multiplier (rkfd_opt_qp.c:117-131) */
+          const int o = W1_CT + W1_CTN*k; unsigned a = am[k]; int t = 0;
+          for(int i=0;i<pyr;i++) if( am[k] >> i & 1u ){ if( fabs(c.W1(o+6+t) - lmin) < 1.0e-8 ) a &= ~(1u << i); t++; }
+          am[k] = a;
+        }
+        continue;
+      }
+      /* ---- step to the first blocking row, newly active rows (rkfd_opt_qp.c:133-151) */
+      double alpha = 1.0;
+      for(int k=0;k<N;k++){
+        const int o = W1_CT + W1_CTN*k; const double fric = c.W1(o+39);
+        const V3 x = w13(o), dx = w13(o+3) - x;
+        for(int i=0;i<pyr;i++){
+          if( am[k] >> i & 1u ) continue;
+          const double ad = fric*dx.x + m.sc_sin[i]*dx.y + m.sc_cos[i]*dx.z;
+          if( ad < 0 ){ const double cond = fric*x.x + m.sc_sin[i]*x.y + m.sc_cos[i]*x.z; const double t2 = (0.0 - cond)/ad; if( t2 < alpha ) alpha = t2; }
+        }
+      }
+      double vv[6] = {0,0,0,0,0,0}, lx2 = 0;
+      for(int k=0;k<N;k++){
+        const int o = W1_CT + W1_CTN*k; const double fric = c.W1(o+39);
+        V3 x = w13(o); const V3 xs = w13(o+3);
+        x = v3(x.x + alpha*(xs.x - x.x), x.y + alpha*(xs.y - x.y), x.z + alpha*(xs.z - x.z));
+        sw13(o, x);
+        for(int i=0;i<pyr;i++){
+          if( am[k] >> i & 1u ) continue;
+          const double cond = fric*x.x + m.sc_sin[i]*x.y + m.sc_cos[i]*x.z;
+          if( fabs(cond) < ZTOL ) am[k] |= 1u << i;
+        }
+        lx2 += c.W1(o+40)*dot(x,x);
+        for(int rr=0;rr<6;rr++) vv[rr] += c.W1(o+18+rr)*x.x + c.W1(o+24+rr)*x.y + c.W1(o+30+rr)*x.z;
+      }
+      /* anti-cycling: same active set with the same objective value -> stop (rkfd_opt_qp.c:152-171) */
+      double objv = 0.5*lx2;
+      for(int r=0;r<6;r++){ double sum = 0; for(int j=0;j<6;j++) sum += M[6*r+j]*vv[j]; objv += 0.5*vv[r]*sum + w[r]*vv[r]; }
+      bool endflag = false;
+      for(int h=0;h<nhist && !endflag;h++){
+        bool eq = true;
+        for(int k=0;k<N;k++) if( (double)am[k] != c.W1(ohist+h*(nrs+1)+k) ){ eq = false; break; }
+        if( eq && !(fabs(c.W1(ohist+h*(nrs+1)+nrs)/objv - 1.0) > 1.0e-8) ) endflag = true;
+      }
+      if( endflag ) break;
+      if( nhist < QP_HIST ){
+        for(int k=0;k<N;k++) c.W1(ohist+nhist*(nrs+1)+k) = (double)am[k];
+        c.W1(ohist+nhist*(nrs+1)+nrs) = objv;
+        nhist++;
+      } else { bad |= 2; break; }
+    }
+    /* f = x / dt ; forces, wrench, friction state from the final active set (rkfd_vert.c:282, 286-324) */
+    unsigned long long nfl = fl;
+    V3 wl = v3(0,0,0), wa = v3(0,0,0);
+    for(int k=0;k<N;k++){
+      const int o = W1_CT + W1_CTN*k; const int s = (int)c.W1(o+52);
+      const V3 fw = (c.W1(o)/m.dt)*w13(o+18) + (c.W1(o+1)/m.dt)*w13(o+24) + (c.W1(o+2)/m.dt)*w13(o+30);
+      const bool flag = am[k] != 0;
+      if( ref ){
+        if( flag ){ nfl |= 2ull << (2*s); const V3 prob = w13(o+48); c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
+        else nfl &= ~(2ull << (2*s));
+        c.gst(c.st.cf,3*s,fw.x); c.gst(c.st.cf,3*s+1,fw.y); c.gst(c.st.cf,3*s+2,fw.z);
+      }
+      const V3 pos = tmul(Rw, w13(o+45)), fll = tmul(Rw, fw);
+      wl = wl + fll; wa = wa + cross(pos, fll);
+    }
+    c.S(wsl) += wl.x; c.S(wsl+1) += wl.y; c.S(wsl+2) += wl.z;
+    c.S(wsl+3) += wa.x; c.S(wsl+4) += wa.y; c.S(wsl+5) += wa.z;
+    cfl = nfl;
+  }
+
   RKFD_HD void rigid_solve(const ModelDev &m, bool ref, unsigned act){
-    if( m.rigid_link >= 0 ){ rigid_mlcp_single(m, ref, act); return; }
+    if( m.rigid_link >= 0 ){ if( m.solver == S_MLCP ) rigid_mlcp_single(m, ref, act); else rigid_vert_single(m, ref, act); return; }
     const int nlanes = c.lanes(), lane = c.lane();
     while( act ){
       const int src = RKFD_FFS32(act) - 1; act &= act - 1;

@@ -159,7 +159,10 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   if( m.has_rigid ){
     int lk = -2;
     for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID ){ const int l = m.cell[m.pair[p].cell].link; lk = ( lk == -2 || lk == l ) ? l : -1; }
+    bool lpos = true;           /* the Vert path divides by the relaxation of every rigid pair */
+    for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID && !(m.pair[p].L > 0.0) ) lpos = false;
     if( lk >= 0 && m.solver == S_MLCP ){ m.rigid_link = lk; m.ws1_doubles = W1_CT + W1_CTN*nrs; }
+    if( lk >= 0 && m.solver == S_VERT && lpos && m.pyramid <= 12 ){ m.rigid_link = lk; m.ws1_doubles = W1_CT + W1_CTN*nrs + 32*(nrs+1); }
   }
   if( m.has_rigid ){
     const int n = m.nmax, mc = m.pyramid*nrs, nm = n + mc; int o = 0;

@@ -273,8 +273,8 @@ def test_rolled_rigid_specialisation_matches_generic(oracle):
 
 
 def test_specialisation_not_picked_for_other_shapes():
-    hs = HostSim(ch.world_c5(base_z=0.1, solver="Vert"), 1)                   # rigid pairs, Vert solver
-    assert hs.spec == 0 and hs.spec_tm == 0 and hs.spec_rolled == 0
+    hs = HostSim(ch.world_c5(base_z=0.1, solver="Vert"), 1)                   # rigid pairs: only the rolled rigid layout
+    assert hs.spec == 0 and hs.spec_tm == 0 and hs.spec_rolled == 7
     assert HostSim(ch.World(chains=[ch.box(), ch.floor_soft()]), 1).spec == 0  # float joint
     rng = np.random.default_rng(0)
     assert HostSim(ch.World(chains=[ch.random_chain(rng, 8, jtypes=("revolute",))]), 1).spec == 0   # general frames
