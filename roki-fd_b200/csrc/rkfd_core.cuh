@@ -38,7 +38,14 @@
 #define RKFD_FFS64(x) __builtin_ffsll((long long)(x))
 #endif
 
+/* unroll factor of the rolled link loops (1: one body per pass) */
+#ifndef RKFD_ROLL_UNROLL
+#define RKFD_ROLL_UNROLL 1
+#endif
+
 namespace rkfd {
+
+constexpr int ROLL_UNROLL = RKFD_ROLL_UNROLL;
 
 /* scratch slots per link by joint type */
 RKFD_HD int link_slot_count(int jtype, int has_rigid){
@@ -317,7 +324,7 @@ struct Core {
   template <class F> RKFD_HD void links_fwd(const ModelDev &m, F &&f){
     if constexpr ( Spec::ROLL != 0 ){
       f(0, LinkTag<J_FIXED, RO_GENERAL, 1>{});
-#pragma unroll 1
+#pragma unroll (ROLL_UNROLL)
       for(int i=1;i<Spec::NL;i++) f(i, LinkTag<J_REVOL, RO_RXS, 0>{});
     } else {
       const int NLc = Spec::nl(m);
@@ -327,7 +334,7 @@ struct Core {
   }
   template <class F> RKFD_HD void links_bwd(const ModelDev &m, F &&f){
     if constexpr ( Spec::ROLL != 0 ){
-#pragma unroll 1
+#pragma unroll (ROLL_UNROLL)
       for(int i=Spec::NL-1;i>=1;i--) f(i, LinkTag<J_REVOL, RO_RXS, 0>{});
       f(0, LinkTag<J_FIXED, RO_GENERAL, 1>{});
     } else {
