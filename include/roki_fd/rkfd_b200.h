@@ -309,6 +309,7 @@ __ROKI_FD_EXPORT rkChain *rkChainB200Alloc(void);
 __ROKI_FD_EXPORT void rkChainB200Free(rkChain *chain);
 __ROKI_FD_EXPORT void rkFDB200PrpSet(rkFD *fd, double dt, int pyramid, double friction_weight, int max_iter);
 __ROKI_FD_EXPORT int rkFDB200SetSolver(rkFD *fd, int solver);                /* 0 Vert, 1 MLCP, 2 Volume */
+__ROKI_FD_EXPORT int rkFDB200SetIntegrator(rkFD *fd, int integrator);        /* RKFD_ODE_RKG / RK4 / Euler / Heun: rkFDODE2AssignRegular */
 __ROKI_FD_EXPORT double rkFDB200Time(rkFD *fd);
 __ROKI_FD_EXPORT int rkFDB200Size(rkFD *fd);
 __ROKI_FD_EXPORT rkChain *rkFDB200CellChain(rkFDCell *cell);

@@ -125,6 +125,8 @@ class OracleWorld:
             _, ph = _d(b.half)
             L.ork_world_add_box(self.h, pR, pp, ph, world.stuff_id(b.stuff))
         L.ork_world_set_prp(self.h, world.dt, world.pyramid, world.friction_weight, world.max_iter)
+        L.ork_world_set_integrator.argtypes = [C.c_void_p, C.c_int]
+        L.ork_world_set_integrator(self.h, {"RKG": 0, "RK4": 1, "Euler": 2, "Heun": 3}[getattr(world, "integrator", "RKG")])
         L.ork_world_set_solver(self.h, SOLVER[world.solver])
         for ci in world.contact_info:
             L.ork_world_add_contact_info(self.h, world.stuff_id(ci.stuff_a), world.stuff_id(ci.stuff_b),

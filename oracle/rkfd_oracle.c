@@ -115,7 +115,7 @@ struct ork_world {
   int nbox; ork_box *box;
   int nci; ork_cinfo_ent *ci; ork_cinfo cidef;
   int npair, nslot; ork_pair *pair;
-  double dt, friction_weight; int pyramid, max_iter, solver;
+  double dt, friction_weight; int pyramid, max_iter, solver, integrator;
   double sc_table[2][64];   /* sin/cos pyramid table (rkfd_util.c:199-214) */
 };
 
@@ -226,6 +226,9 @@ void ork_world_add_contact_info(ork_world *w, int sa, int sb, int type,
   e = &w->ci[w->nci++];
   e->sa=sa; e->sb=sb; e->ci.type=type; e->ci.K=K; e->ci.L=L; e->ci.E=E; e->ci.V=V; e->ci.SF=SF; e->ci.KF=KF;
 }
+/* [EXT] zODE2AssignRegular( ode, RKG | RK4 | Euler | Heun ) (reference rkfd_sim.h:86): 0 Runge-Kutta-Gill (the
+ * default, rkfd_sim.c:46-47), 1 classical Runge-Kutta, 2 Euler, 3 Heun */
+void ork_world_set_integrator(ork_world *w, int integrator){ w->integrator = integrator; }
 void ork_world_set_prp(ork_world *w, double dt, int pyramid, double fw, int max_iter)
 {
   int i; double th, dth, off;
@@ -906,37 +909,34 @@ static void cat_dis(const ork_world *w, double *q, double k, const double *v)
     default: for(j=0;j<l->ndof;j++) qi[j] += k*vi[j]; break; } }
 }
 
-/* rkFDUpdate (rkfd_sim.c:560-566): zODE2Update with Runge-Kutta-Gill on the regularised system
- * x = (dis, vel) ([EXT A-9]), t += dt, then the committing reference evaluation */
+/* rkFDUpdate (rkfd_sim.c:560-566): zODE2Update with the assigned explicit Runge-Kutta scheme (default
+ * Runge-Kutta-Gill) on the regularised system x = (dis, vel) ([EXT A-9]), t += dt, then the committing
+ * reference evaluation.  Stage states are built from the committed state by successive manifold increments in
+ * the order k1, k2, ...; zero tableau entries are skipped. */
 void ork_env_update(ork_env *e)
 {
-  const ork_world *w = e->w; int nq = w->nq, i; double dt = w->dt;
+  const ork_world *w = e->w; int nq = w->nq, i, s, j, ns; double dt = w->dt;
   const double r2 = sqrt(2.0);
-  const double c21 = 0.5, c31 = (r2-1.0)/2.0, c32 = 1.0-1.0/r2, c42 = -1.0/r2, c43 = 1.0+1.0/r2;
-  const double b1 = 1.0/6.0, b2 = (2.0-r2)/6.0, b3 = (2.0+r2)/6.0, b4 = 1.0/6.0;
+  double a[4][4] = {{0}}, b[4] = {0};
   double *xq = e->xs[0], *xv = e->xs[1];
-  /* k1 */
-  memcpy(e->k[0][0],e->qd,nq*8); eval_dynamics(e,e->q,e->qd,e->k[0][1],0);
-  /* k2 */
-  memcpy(xq,e->q,nq*8); memcpy(xv,e->qd,nq*8);
-  cat_dis(w,xq,c21*dt,e->k[0][0]); for(i=0;i<nq;i++) xv[i] += c21*dt*e->k[0][1][i];
-  memcpy(e->k[1][0],xv,nq*8); eval_dynamics(e,xq,xv,e->k[1][1],0);
-  /* k3 */
-  memcpy(xq,e->q,nq*8); memcpy(xv,e->qd,nq*8);
-  cat_dis(w,xq,c31*dt,e->k[0][0]); cat_dis(w,xq,c32*dt,e->k[1][0]);
-  for(i=0;i<nq;i++){ xv[i] += c31*dt*e->k[0][1][i]; xv[i] += c32*dt*e->k[1][1][i]; }
-  memcpy(e->k[2][0],xv,nq*8); eval_dynamics(e,xq,xv,e->k[2][1],0);
-  /* k4 */
-  memcpy(xq,e->q,nq*8); memcpy(xv,e->qd,nq*8);
-  cat_dis(w,xq,c42*dt,e->k[1][0]); cat_dis(w,xq,c43*dt,e->k[2][0]);
-  for(i=0;i<nq;i++){ xv[i] += c42*dt*e->k[1][1][i]; xv[i] += c43*dt*e->k[2][1][i]; }
-  memcpy(e->k[3][0],xv,nq*8); eval_dynamics(e,xq,xv,e->k[3][1],0);
+  switch(w->integrator){
+  case 1: ns = 4; a[1][0] = 0.5; a[2][1] = 0.5; a[3][2] = 1.0; b[0] = 1.0/6.0; b[1] = 2.0/6.0; b[2] = 2.0/6.0; b[3] = 1.0/6.0; break;
+  case 2: ns = 1; b[0] = 1.0; break;
+  case 3: ns = 2; a[1][0] = 1.0; b[0] = 0.5; b[1] = 0.5; break;
+  default: ns = 4; a[1][0] = 0.5; a[2][0] = (r2-1.0)/2.0; a[2][1] = 1.0-1.0/r2; a[3][1] = -1.0/r2; a[3][2] = 1.0+1.0/r2;
+    b[0] = 1.0/6.0; b[1] = (2.0-r2)/6.0; b[2] = (2.0+r2)/6.0; b[3] = 1.0/6.0; break;
+  }
+  for(s=0;s<ns;s++){
+    if( s == 0 ){ memcpy(e->k[0][0],e->qd,nq*8); eval_dynamics(e,e->q,e->qd,e->k[0][1],0); continue; }
+    memcpy(xq,e->q,nq*8); memcpy(xv,e->qd,nq*8);
+    for(j=0;j<s;j++) if( a[s][j] != 0.0 ){
+      cat_dis(w,xq,a[s][j]*dt,e->k[j][0]);
+      for(i=0;i<nq;i++) xv[i] += a[s][j]*dt*e->k[j][1][i]; }
+    memcpy(e->k[s][0],xv,nq*8); eval_dynamics(e,xq,xv,e->k[s][1],0);
+  }
   /* combination */
-  cat_dis(w,e->q,b1*dt,e->k[0][0]); cat_dis(w,e->q,b2*dt,e->k[1][0]);
-  cat_dis(w,e->q,b3*dt,e->k[2][0]); cat_dis(w,e->q,b4*dt,e->k[3][0]);
-  for(i=0;i<nq;i++){
-    e->qd[i] += b1*dt*e->k[0][1][i]; e->qd[i] += b2*dt*e->k[1][1][i];
-    e->qd[i] += b3*dt*e->k[2][1][i]; e->qd[i] += b4*dt*e->k[3][1][i]; }
+  for(s=0;s<ns;s++) cat_dis(w,e->q,b[s]*dt,e->k[s][0]);
+  for(i=0;i<nq;i++) for(s=0;s<ns;s++) e->qd[i] += b[s]*dt*e->k[s][1][i];
   e->t += dt;
   eval_dynamics(e,e->q,e->qd,e->qdd,1);               /* _rkFDUpdateRef */
 }

@@ -59,6 +59,7 @@ void ork_world_add_contact_info(ork_world *w, int stuff_a, int stuff_b, int type
 /* properties (reference rkfd_property.c:10-18) and solver choice (rkfd_sim.h:89-93);
  * choosing the solver also installs its default contact info (rkfd_vert.c:340-348 ...) */
 void ork_world_set_prp(ork_world *w, double dt, int pyramid, double friction_weight, int max_iter);
+void ork_world_set_integrator(ork_world *w, int integrator);    /* 0 RKG (default), 1 RK4, 2 Euler, 3 Heun */
 void ork_world_set_solver(ork_world *w, int solver);
 /* finish: builds (cell x box) pairs in registration order and associates contact info */
 void ork_world_finalize(ork_world *w);

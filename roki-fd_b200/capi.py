@@ -66,7 +66,7 @@ def lib():
         "rkFDContactInfoAdd": (C.c_bool, [vp, C.c_char_p, C.c_char_p, ci, cd, cd, cd, cd, cd, cd]),
         "rkFDUpdateInit": (None, [vp]), "rkFDUpdate": (vp, [vp]), "rkFDUpdateN": (vp, [vp, ci]),
         "rkFDUpdateDestroy": (None, [vp]), "rkFDSolve": (vp, [vp]),
-        "rkFDB200PrpSet": (None, [vp, cd, ci, cd, ci]), "rkFDB200SetSolver": (ci, [vp, ci]), "rkFDB200Time": (cd, [vp]),
+        "rkFDB200PrpSet": (None, [vp, cd, ci, cd, ci]), "rkFDB200SetSolver": (ci, [vp, ci]), "rkFDB200SetIntegrator": (ci, [vp, ci]), "rkFDB200Time": (cd, [vp]),
         "rkFDB200Size": (ci, [vp]), "rkFDB200CellChain": (vp, [vp]),
         "rkFDB200Dis": (_dp, [vp]), "rkFDB200Vel": (_dp, [vp]), "rkFDB200Acc": (_dp, [vp]),
         "zVecAlloc": (vp, [ci]), "zVecFree": (None, [vp]),
@@ -232,6 +232,11 @@ class RkFD:
 
     def prp_set(self, dt=0.001, pyramid=8, friction_weight=100.0, max_iter=10):
         lib().rkFDB200PrpSet(self.h, dt, pyramid, friction_weight, max_iter)
+
+    def set_integrator(self, name):
+        """rkFDODE2AssignRegular(fd, RKG | RK4 | Euler | Heun)."""
+        if lib().rkFDB200SetIntegrator(self.h, {"RKG": 0, "RK4": 1, "Euler": 2, "Heun": 3}[name]) != 0:
+            raise ValueError("integrator %r" % name)
 
     def set_solver(self, name):
         if lib().rkFDB200SetSolver(self.h, SOLVER[name]) != 0:
@@ -404,6 +409,7 @@ def create_world(world: World, B=None, devices=None):
     cells = [fd.chain_reg(ch) for ch in world.chains]
     fd.prp_set(world.dt, world.pyramid, world.friction_weight, world.max_iter)
     fd.set_solver(world.solver)
+    fd.set_integrator(getattr(world, "integrator", "RKG"))
     if B is not None:
         fd.batch_set_env_num(B)
     if devices is not None:

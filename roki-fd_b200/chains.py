@@ -116,6 +116,7 @@ class World:
     friction_weight: float = 100.0
     max_iter: int = 10
     solver: str = "Vert"
+    integrator: str = "RKG"        # zODE2AssignRegular: "RKG" (reference default) | "RK4" | "Euler" | "Heun"
 
     def __post_init__(self):
         self._stuff = {}

@@ -342,7 +342,9 @@ extern "C" void rkFDUpdateInit(rkFD *fd)
     w.cidef.SF = fd->cidef.sf; w.cidef.KF = fd->cidef.kf;
     w.dt = fd->prp.dt; w.friction_weight = fd->prp.friction_weight; w.pyramid = fd->prp.pyramid; w.max_iter = fd->prp.max_iter;
     w.solver = fd->solver.com == &g_solver_mlcp ? S_MLCP : ( fd->solver.com == &g_solver_volume ? S_VOLUME : S_VERT );
-    if( fd->ode.form != RKFD_ODE2_Regular || fd->ode.integrator != RKFD_ODE_RKG ) throw std::runtime_error("only the Regular/RKG integrator is implemented");
+    if( fd->ode.form != RKFD_ODE2_Regular || fd->ode.integrator < RKFD_ODE_RKG || fd->ode.integrator > RKFD_ODE_Heun )
+      throw std::runtime_error("integrators: Regular form with RKG, RK4, Euler or Heun");
+    w.integrator = fd->ode.integrator;
     std::string err;
     if( !build_model(w, fi->model, err) ) throw std::runtime_error(err);
     if( fi->model.has_rigid && w.solver == S_VOLUME ) throw std::runtime_error("rigid contact pairs with the Volume solver are not implemented on the device yet");
@@ -469,6 +471,11 @@ extern "C" rkChain *rkChainB200Alloc(void){ return (rkChain*)std::calloc(1, size
 extern "C" void rkChainB200Free(rkChain *c){ std::free(c); }
 extern "C" void rkFDB200PrpSet(rkFD *fd, double dt, int pyramid, double fw, int max_iter)
 { rkFDPrpSetDT(fd, dt); rkFDPrpSetPyramid(fd, pyramid); rkFDPrpSetFrictionWeight(fd, fw); rkFDPrpSetMaxIter(fd, max_iter); }
+extern "C" int rkFDB200SetIntegrator(rkFD *fd, int integrator)      /* function form of rkFDODE2AssignRegular for FFI callers */
+{
+  if( integrator < RKFD_ODE_RKG || integrator > RKFD_ODE_Heun ) return 1;
+  fd->ode.form = RKFD_ODE2_Regular; fd->ode.integrator = integrator; return 0;
+}
 extern "C" int rkFDB200SetSolver(rkFD *fd, int solver)
 {
   if( !FI(fd) ) return 1;

@@ -746,13 +746,21 @@ struct Core {
   /* Runge-Kutta-Gill bookkeeping of one scalar state pair (x, x') with slope (kq, kv) ([EXT A-9]):
    * stage states are built from the committed state by successive increments, the combination is
    * accumulated in the output buffer */
-  struct RK { double c21, c31, c32, c42, c43, b1, b2, b3, b4; };
-  RKFD_HD RK rk_coef(double dt){
+  /* The other explicit schemes of [EXT] zODE2AssignRegular use the same bookkeeping: classical Runge-Kutta is the
+   * same four stages with c31 = c42 = 0; Heun runs stages K1 and K4 (c21 = dt, b1 = b4 = dt/2); Euler runs K1 alone,
+   * whose running combination is already the new state (ns = 1). */
+  struct RK { double c21, c31, c32, c42, c43, b1, b2, b3, b4; int ns; };
+  RKFD_HD RK rk_coef(double dt, int integrator){
     const double r2 = sqrt(2.0); RK k;
     k.c21 = 0.5*dt; k.c31 = ((r2-1.0)/2.0)*dt; k.c32 = (1.0-1.0/r2)*dt; k.c42 = (-1.0/r2)*dt; k.c43 = (1.0+1.0/r2)*dt;
-    k.b1 = (1.0/6.0)*dt; k.b2 = ((2.0-r2)/6.0)*dt; k.b3 = ((2.0+r2)/6.0)*dt; k.b4 = (1.0/6.0)*dt;
+    k.b1 = (1.0/6.0)*dt; k.b2 = ((2.0-r2)/6.0)*dt; k.b3 = ((2.0+r2)/6.0)*dt; k.b4 = (1.0/6.0)*dt; k.ns = 4;
+    if( integrator == 1 ){ k.c31 = 0.0; k.c32 = 0.5*dt; k.c42 = 0.0; k.c43 = dt; k.b2 = (2.0/6.0)*dt; k.b3 = (2.0/6.0)*dt; }
+    else if( integrator == 2 ){ k.ns = 1; k.b1 = dt; }
+    else if( integrator == 3 ){ k.ns = 2; k.c21 = dt; k.b1 = 0.5*dt; k.b4 = 0.5*dt; }
     return k;
   }
+  static RKFD_HD int rk_stages(int integrator){ return integrator == 2 ? 1 : ( integrator == 3 ? 2 : 4 ); }
+  static RKFD_HD int rk_next_stage(int stage, int ns){ return stage == ST_K1 ? ( ns == 4 ? ST_K2 : ( ns == 2 ? ST_K4 : ST_REF ) ) : stage + 1; }
   /* velocity-like (vector-space) component j */
   RKFD_HD void rk_lin(const ModelDev &m, const RK &k, int stage, int slotS, int slotP, double *gin, double *gout, int j, double slope){
     const double F = ( stage >= ST_K2 && stage <= ST_K4 ) ? c.gld(gout, j) : 0.0, x0 = stage == ST_K2 ? c.gld(gin, j) : 0.0;
@@ -762,7 +770,7 @@ struct Core {
   RKFD_HD double rk_lin_pf(const RK &k, int stage, int slotS, int slotP, double *gout, int j, double slope, double F, double x0g){
     double xn = 0.0;       /* the next stage value */
     switch(stage){
-    case ST_K1: { const double x0 = T(slotS); c.gst(gout, j, x0 + k.b1*slope); Tw(slotP, x0 + k.c31*slope); xn = x0 + k.c21*slope; Tw(slotS, xn); } break;
+    case ST_K1: { const double x0 = T(slotS); const double F = x0 + k.b1*slope; c.gst(gout, j, F); Tw(slotP, x0 + k.c31*slope); xn = k.ns == 1 ? F : x0 + k.c21*slope; Tw(slotS, xn); } break;
     case ST_K2: { c.gst(gout, j, F + k.b2*slope); xn = T(slotP) + k.c32*slope; Tw(slotS, xn); Tw(slotP, x0g + k.c42*slope); } break;
     case ST_K3: { c.gst(gout, j, F + k.b3*slope); xn = T(slotP) + k.c43*slope; Tw(slotS, xn); } break;
     case ST_K4: { xn = F + k.b4*slope; c.gst(gout, j, xn); Tw(slotS, xn); } break;
@@ -786,11 +794,11 @@ struct Core {
     switch(stage){
     case ST_K1: { const V3 x0 = t3(slotS); const V3 F = aa_cascade(x0, k.b1*w);
       c.gst(gout,j,F.x); c.gst(gout,j+1,F.y); c.gst(gout,j+2,F.z);
-      tw3(slotP, aa_cascade(x0, k.c31*w)); tw3(slotS, aa_cascade(x0, k.c21*w)); } break;
+      tw3(slotP, k.c31 == 0.0 ? x0 : aa_cascade(x0, k.c31*w)); tw3(slotS, k.ns == 1 ? F : aa_cascade(x0, k.c21*w)); } break;
     case ST_K2: { const V3 x0 = v3(c.gld(gin,j), c.gld(gin,j+1), c.gld(gin,j+2));
       const V3 F = aa_cascade(v3(c.gld(gout,j), c.gld(gout,j+1), c.gld(gout,j+2)), k.b2*w);
       c.gst(gout,j,F.x); c.gst(gout,j+1,F.y); c.gst(gout,j+2,F.z);
-      tw3(slotS, aa_cascade(t3(slotP), k.c32*w)); tw3(slotP, aa_cascade(x0, k.c42*w)); } break;
+      tw3(slotS, aa_cascade(t3(slotP), k.c32*w)); tw3(slotP, k.c42 == 0.0 ? x0 : aa_cascade(x0, k.c42*w)); } break;
     case ST_K3: { const V3 F = aa_cascade(v3(c.gld(gout,j), c.gld(gout,j+1), c.gld(gout,j+2)), k.b3*w);
       c.gst(gout,j,F.x); c.gst(gout,j+1,F.y); c.gst(gout,j+2,F.z);
       tw3(slotS, aa_cascade(t3(slotP), k.c43*w)); } break;
@@ -811,7 +819,7 @@ struct Core {
 
   /* ---- pass 3: outward acceleration pass + integrator bookkeeping */
   RKFD_HD void pass3(const ModelDev &m, int stage){
-    const RK k = rk_coef(m.dt);
+    const RK k = rk_coef(m.dt, m.integrator);
     V3 al = v3(0,0,0), aa = v3(0,0,0), om = v3(0,0,0);
     /* running combination (and, at stage 2, the committed state) of the next 1-DoF joint are requested one link ahead */
     double nxq[4] = {0,0,0,0};
@@ -1857,10 +1865,13 @@ struct Core {
 #pragma unroll 1
     for(int s=0;s<nsteps;s++){
       load_stage_state(m);
+      const int ns = rk_stages(m.integrator);
 #pragma unroll 1
-      for(int stage=first; stage<=last; stage++){
+      for(int stage=first;;){
         if( stage == ST_REF ) c.cur ^= 1;   /* the output buffer now holds the committed state */
         evaluate(m, stage);
+        if( stage == last ) break;
+        stage = rk_next_stage(stage, ns);
       }
     }
     store_flags();

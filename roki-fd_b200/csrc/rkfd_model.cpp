@@ -22,7 +22,7 @@ static void mat3_mulv(const double *a, const double *x, double *y){
 bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
 {
   std::memset(&m, 0, sizeof m);
-  m.dt = w.dt; m.inv_dt = 1.0/w.dt; m.friction_weight = w.friction_weight; m.pyramid = w.pyramid; m.max_iter = w.max_iter; m.solver = w.solver;
+  m.dt = w.dt; m.inv_dt = 1.0/w.dt; m.friction_weight = w.friction_weight; m.pyramid = w.pyramid; m.max_iter = w.max_iter; m.solver = w.solver; m.integrator = w.integrator;
   if( w.pyramid > MAX_PYRAMID || w.pyramid < 1 ){ err = "pyramid order out of range"; return false; }
   { /* rkFDCrateSinCosTable (reference rkfd_util.c:199-214) with the Vert offset -pi/pyramid (rkfd_vert.c:369) */
     const double off = -M_PI / w.pyramid, dth = 2.0*M_PI / w.pyramid; double th = 0.0;

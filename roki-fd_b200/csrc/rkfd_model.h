@@ -58,7 +58,7 @@ struct WorldHost {
   std::vector<ContactInfoHost> ci;
   ContactInfoHost cidef;
   double dt = 0.001, friction_weight = 100.0;
-  int pyramid = 8, max_iter = 10, solver = S_VERT;
+  int pyramid = 8, max_iter = 10, solver = S_VERT, integrator = 0;
 };
 
 /* Flattens the world into `out`.  Returns false and fills `err` when a limit of the fused kernel is

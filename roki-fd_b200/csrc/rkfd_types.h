@@ -68,6 +68,7 @@ struct ModelDev {
   int need_world;      /* any collision cell: world frames must be propagated */
   int has_rigid, has_elastic;
   int solver, pyramid, max_iter;
+  int integrator;      /* 0 Runge-Kutta-Gill, 1 classical Runge-Kutta, 2 Euler, 3 Heun ([EXT] zODE2AssignRegular) */
   int nscratch;        /* scratch slots (doubles) per env */
   int ws_doubles;      /* per-warp workspace (doubles) of the rigid-contact solve, 0 when no rigid pair */
   int ws_geo, ws_b, ws_f, ws_A, ws_du, ws_da, ws_qp;   /* offsets inside the workspace */

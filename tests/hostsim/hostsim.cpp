@@ -82,6 +82,7 @@ void hostsim_add_contact_info(HostSim *h, int sa, int sb, int type, double K, do
 { ContactInfoHost c; c.a = "s"+std::to_string(sa); c.b = "s"+std::to_string(sb); c.type = type; c.K=K; c.L=L; c.E=E; c.V=V; c.SF=SF; c.KF=KF; h->world.ci.push_back(c); }
 void hostsim_set_prp(HostSim *h, double dt, int pyramid, double fw, int max_iter, int solver)
 { h->world.dt = dt; h->world.pyramid = pyramid; h->world.friction_weight = fw; h->world.max_iter = max_iter; h->world.solver = solver; }
+void hostsim_set_integrator(HostSim *h, int integrator){ h->world.integrator = integrator; }
 
 /* returns 0 on success */
 int hostsim_finalize(HostSim *h, int B)

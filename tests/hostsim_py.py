@@ -74,6 +74,8 @@ class HostSim:
             L.hostsim_add_contact_info(self.h, world.stuff_id(ci.stuff_a), world.stuff_id(ci.stuff_b),
                                        CONTACT[ci.type], ci.K, ci.L, ci.E, ci.V, ci.SF, ci.KF)
         L.hostsim_set_prp(self.h, world.dt, world.pyramid, world.friction_weight, world.max_iter, SOLVER[world.solver])
+        L.hostsim_set_integrator.argtypes = [C.c_void_p, C.c_int]
+        L.hostsim_set_integrator(self.h, {"RKG": 0, "RK4": 1, "Euler": 2, "Heun": 3}[getattr(world, "integrator", "RKG")])
         if L.hostsim_finalize(self.h, B) != 0:
             raise RuntimeError(L.hostsim_error(self.h).decode())
         self.B, self.nq, self.nl, self.nslot = B, L.hostsim_nq(self.h), L.hostsim_nl(self.h), L.hostsim_nslot(self.h)

@@ -418,3 +418,18 @@ def test_rigid_mlcp_kernel_variants_agree(capi, oracle, monkeypatch, variant):
         e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
         ref = e.eval(True)
         assert relerr(a1[b], ref) < 1e-8, b
+
+
+@pytest.mark.parametrize("integ", ["RK4", "Euler", "Heun"])
+def test_integrator_menu(capi, oracle, integ):
+    """rkFDODE2AssignRegular(fd, RK4 | Euler | Heun) through the C-ABI against the oracle (C3, 20 steps)."""
+    w = ch.world_c3(base_z=0.1)
+    w.integrator = integ
+    B = 96
+    q, qd, u = ch.sample_state(w, B, seed=41)
+    fd = gpu_world(capi, w, q, qd, u)
+    fd.update_n(20)
+    gq, gqd, gqdd = fd.batch_get_state()
+    fd.destroy()
+    oq, oqd, oqdd, _ = oracle.OracleWorld(w).batch_run(q, qd, u, nsteps=20)
+    assert relerr(gq, oq) < 1e-9 and relerr(gqd, oqd) < 1e-8

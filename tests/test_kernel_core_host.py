@@ -278,3 +278,25 @@ def test_specialisation_not_picked_for_other_shapes():
     assert HostSim(ch.World(chains=[ch.box(), ch.floor_soft()]), 1).spec == 0  # float joint
     rng = np.random.default_rng(0)
     assert HostSim(ch.World(chains=[ch.random_chain(rng, 8, jtypes=("revolute",))]), 1).spec == 0   # general frames
+
+
+@pytest.mark.parametrize("integ", ["RK4", "Euler", "Heun"])
+@pytest.mark.parametrize("name", ["c3_arm7_penalty", "c1_box_hardsoft"])
+def test_integrator_menu_matches_oracle(oracle, name, integ):
+    """rkFDODE2AssignRegular(fd, RK4 | Euler | Heun): the stage bookkeeping of the kernel against the oracle's
+    tableau loop (revolute joints and a floating body with the exponential-map `cat`)."""
+    w = WORLDS[name]()
+    w.integrator = integ
+    B, nsteps = 8, 15
+    q, qd, u = ch.sample_state(w, B, seed=31)
+    if name == "c1_box_hardsoft":
+        q[:, 2] = np.linspace(0.0, 0.12, B)
+    specs = (None, "rolled") if name == "c3_arm7_penalty" else (None,)
+    ref = oracle_run(oracle, w, q, qd, u, nsteps)
+    for spec in specs:
+        hs = HostSim(w, B, spec=spec)
+        hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(nsteps)
+        hq, hqd, hqdd = hs.get_state()
+        for b in range(B):
+            (oq, oqd, oqdd), _, _ = ref[b]
+            assert relerr(hq[b, :w.nq], oq) < 1e-9 and relerr(hqd[b, :w.nq], oqd) < 1e-8, (name, integ, spec, b)

@@ -270,3 +270,28 @@ def test_delassus_matrix_is_J_Minv_JT(oracle):
         assert np.allclose(A, Aref, rtol=1e-5, atol=1e-6 * np.abs(Aref).max())
         return
     pytest.skip("no contact sampled")
+
+
+def test_integrator_orders():
+    """The four explicit schemes of zODE2AssignRegular converge with their orders on a frictionless double pendulum
+    (Euler 1, Heun 2, RK4 and RKG 4): halving dt divides the end-state error by 2 / 4 / 16."""
+    import copy
+    from oracle import oracle as orc
+    w0 = ch.World(chains=[ch.arm_2dof(motors=False)])
+    for l in w0.chains[0].links:
+        l.viscosity = l.coulomb = l.sfriction = 0.0
+    q0, qd0 = np.array([0.4, -0.7]), np.array([0.3, 0.5])
+
+    def end_state(integ, dt, T=0.08):
+        w = copy.deepcopy(w0); w.integrator = integ; w.dt = dt
+        e = orc.OracleWorld(w).env()
+        e.set_state(q0, qd0); e.update_init()
+        for _ in range(int(round(T / dt))):
+            e.update()
+        return np.concatenate(e.get_state()[:2])
+
+    exact = end_state("RK4", 0.08 / 512)
+    for integ, order in (("Euler", 1), ("Heun", 2), ("RK4", 4), ("RKG", 4)):
+        e1 = np.abs(end_state(integ, 0.08 / 8) - exact).max()
+        e2 = np.abs(end_state(integ, 0.08 / 16) - exact).max()
+        assert 0.8 * 2 ** order < e1 / e2 < 1.25 * 2 ** order, (integ, e1, e2)
