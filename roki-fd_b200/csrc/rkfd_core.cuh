@@ -305,6 +305,17 @@ inline int spec_ntspace(int id){
   return 0;
 }
 
+/* explicit Runge-Kutta coefficients times dt ([EXT A-9]; zODE2AssignRegular menu) */
+inline ModelDev::RK rk_coef(double dt, int integrator){
+  const double r2 = sqrt(2.0); ModelDev::RK k;
+  k.c21 = 0.5*dt; k.c31 = ((r2-1.0)/2.0)*dt; k.c32 = (1.0-1.0/r2)*dt; k.c42 = (-1.0/r2)*dt; k.c43 = (1.0+1.0/r2)*dt;
+  k.b1 = (1.0/6.0)*dt; k.b2 = ((2.0-r2)/6.0)*dt; k.b3 = ((2.0+r2)/6.0)*dt; k.b4 = (1.0/6.0)*dt; k.ns = 4;
+  if( integrator == 1 ){ k.c31 = 0.0; k.c32 = 0.5*dt; k.c42 = 0.0; k.c43 = dt; k.b2 = (2.0/6.0)*dt; k.b3 = (2.0/6.0)*dt; }
+  else if( integrator == 2 ){ k.ns = 1; k.b1 = dt; }
+  else if( integrator == 3 ){ k.ns = 2; k.c21 = dt; k.b1 = 0.5*dt; k.b4 = 0.5*dt; }
+  return k;
+}
+
 template <class Ctx, class Spec = SpecGeneric>
 struct Core {
   Ctx &c;
@@ -749,16 +760,7 @@ struct Core {
   /* The other explicit schemes of [EXT] zODE2AssignRegular use the same bookkeeping: classical Runge-Kutta is the
    * same four stages with c31 = c42 = 0; Heun runs stages K1 and K4 (c21 = dt, b1 = b4 = dt/2); Euler runs K1 alone,
    * whose running combination is already the new state (ns = 1). */
-  struct RK { double c21, c31, c32, c42, c43, b1, b2, b3, b4; int ns; };
-  RKFD_HD RK rk_coef(double dt, int integrator){
-    const double r2 = sqrt(2.0); RK k;
-    k.c21 = 0.5*dt; k.c31 = ((r2-1.0)/2.0)*dt; k.c32 = (1.0-1.0/r2)*dt; k.c42 = (-1.0/r2)*dt; k.c43 = (1.0+1.0/r2)*dt;
-    k.b1 = (1.0/6.0)*dt; k.b2 = ((2.0-r2)/6.0)*dt; k.b3 = ((2.0+r2)/6.0)*dt; k.b4 = (1.0/6.0)*dt; k.ns = 4;
-    if( integrator == 1 ){ k.c31 = 0.0; k.c32 = 0.5*dt; k.c42 = 0.0; k.c43 = dt; k.b2 = (2.0/6.0)*dt; k.b3 = (2.0/6.0)*dt; }
-    else if( integrator == 2 ){ k.ns = 1; k.b1 = dt; }
-    else if( integrator == 3 ){ k.ns = 2; k.c21 = dt; k.b1 = 0.5*dt; k.b4 = 0.5*dt; }
-    return k;
-  }
+  using RK = ModelDev::RK;
   static RKFD_HD int rk_stages(int integrator){ return integrator == 2 ? 1 : ( integrator == 3 ? 2 : 4 ); }
   static RKFD_HD int rk_next_stage(int stage, int ns){ return stage == ST_K1 ? ( ns == 4 ? ST_K2 : ( ns == 2 ? ST_K4 : ST_REF ) ) : stage + 1; }
   /* velocity-like (vector-space) component j */
@@ -819,7 +821,7 @@ struct Core {
 
   /* ---- pass 3: outward acceleration pass + integrator bookkeeping */
   RKFD_HD void pass3(const ModelDev &m, int stage){
-    const RK k = rk_coef(m.dt, m.integrator);
+    const RK &k = m.rk;
     V3 al = v3(0,0,0), aa = v3(0,0,0), om = v3(0,0,0);
     /* running combination (and, at stage 2, the committed state) of the next 1-DoF joint are requested one link ahead */
     double nxq[4] = {0,0,0,0};
@@ -1865,7 +1867,7 @@ struct Core {
 #pragma unroll 1
     for(int s=0;s<nsteps;s++){
       load_stage_state(m);
-      const int ns = rk_stages(m.integrator);
+      const int ns = m.rk.ns;
 #pragma unroll 1
       for(int stage=first;;){
         if( stage == ST_REF ) c.cur ^= 1;   /* the output buffer now holds the committed state */

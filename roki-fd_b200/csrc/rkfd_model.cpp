@@ -23,6 +23,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
 {
   std::memset(&m, 0, sizeof m);
   m.dt = w.dt; m.inv_dt = 1.0/w.dt; m.friction_weight = w.friction_weight; m.pyramid = w.pyramid; m.max_iter = w.max_iter; m.solver = w.solver; m.integrator = w.integrator;
+  m.rk = rk_coef(w.dt, w.integrator);
   if( w.pyramid > MAX_PYRAMID || w.pyramid < 1 ){ err = "pyramid order out of range"; return false; }
   { /* rkFDCrateSinCosTable (reference rkfd_util.c:199-214) with the Vert offset -pi/pyramid (rkfd_vert.c:369) */
     const double off = -M_PI / w.pyramid, dth = 2.0*M_PI / w.pyramid; double th = 0.0;

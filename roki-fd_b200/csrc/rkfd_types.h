@@ -69,6 +69,8 @@ struct ModelDev {
   int has_rigid, has_elastic;
   int solver, pyramid, max_iter;
   int integrator;      /* 0 Runge-Kutta-Gill, 1 classical Runge-Kutta, 2 Euler, 3 Heun ([EXT] zODE2AssignRegular) */
+  /* stage coefficients of the integrator times dt, folded on the host (constant-bank operands in the kernel) */
+  struct RK { double c21, c31, c32, c42, c43, b1, b2, b3, b4; int ns; } rk;
   int nscratch;        /* scratch slots (doubles) per env */
   int ws_doubles;      /* per-warp workspace (doubles) of the rigid-contact solve, 0 when no rigid pair */
   int ws_geo, ws_b, ws_f, ws_A, ws_du, ws_da, ws_qp;   /* offsets inside the workspace */
