@@ -200,9 +200,11 @@ struct SpecSerialRev {
 /* RG_ = 1: worlds with rigid pairs, all of them on the last link, MLCP solver (Core::rigid_mlcp_single).  Pass 2 runs
  * twice per evaluation there, so the angular velocity keeps its own 3 slots next to U, and the last
  * link publishes its world frame / velocity / acceleration (24 slots) for the contact solve. */
-template <int ID_, int NL_, int RG_ = 0>
+/* GEN_ = 1: the constant frame rotations of the revolute links are arbitrary (dense 3x3 products instead of the
+ * quarter-turn forms): every fixed-base serial revolute arm gets the rolled kernel, whatever its DH twists. */
+template <int ID_, int NL_, int RG_ = 0, int GEN_ = 0>
 struct SpecSerialRevRolled {
-  static constexpr int ID = ID_, NL = NL_, UNROLL = 1, TM = 1, ROLL = 1, RG = RG_;
+  static constexpr int ID = ID_, NL = NL_, UNROLL = 1, TM = 1, ROLL = 1, RG = RG_, RCLS = GEN_ ? RO_GENERAL : RO_RXS;
   /* RG: (sin, cos, 1/D, u) stay in the shared-memory column (SCS): the contact solve reads them for OTHER lanes'
    * environments (lane-parallel probes) and in divergent code, which tensor memory allows neither */
   static constexpr int SCS = RG_;
@@ -214,7 +216,7 @@ struct SpecSerialRevRolled {
   static RKFD_HD int serial(int i, const LinkDev &){ return i > 0 ? 1 : 0; }
   static RKFD_HD int slot(int i, const LinkDev &){ return PER*i; }
   static RKFD_HD int wslot(int i, const LinkDev &){ return PER*i + (RG_ ? 6 : 0); }
-  static RKFD_HD int rcls(int i, const LinkDev &){ return i == 0 ? RO_GENERAL : RO_RXS; }
+  static RKFD_HD int rcls(int i, const LinkDev &){ return i == 0 ? RO_GENERAL : RCLS; }
   static RKFD_HD int qofs(int i, const LinkDev &){ return i > 0 ? i - 1 : 0; }
   static RKFD_HD int ndof(int i, const LinkDev &){ return i > 0 ? 1 : 0; }
   static RKFD_HD int branch_slot(int, const LinkDev &){ return -1; }
@@ -225,14 +227,14 @@ struct SpecSerialRevRolled {
   static RKFD_HD int nq(const ModelDev &){ return NL_ - 1; }
   static RKFD_HD int sc(int i, const LinkDev &){ return RG_ ? PER*i + 9 : 4*(i-1); }
 };
-inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0){
+inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0, int GEN = 0){
   if( RG ? !( m.has_rigid && m.rigid_link == NL-1 ) : m.has_rigid ) return false;
   if( m.nl != NL || NL < 2 ) return false;
   for(int i=0;i<NL;i++){
     const LinkDev &L = m.link[i];
     if( i == 0 ){ if( L.parent >= 0 || L.jtype != J_FIXED || L.cell_end > L.cell_begin ) return false; continue; }
     if( L.jtype != J_REVOL || L.parent != i-1 || !L.serial || L.qofs != i-1 ) return false;
-    if( L.rcls != RO_RXP && L.rcls != RO_RXM ) return false;
+    if( !GEN && L.rcls != RO_RXP && L.rcls != RO_RXM ) return false;
     if( i != NL-1 && L.cell_end > L.cell_begin ) return false;
   }
   return true;
@@ -254,13 +256,14 @@ inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
 /* compiled specialisations: (id, links, rotation classes).  1: the 7-DoF arm of BASELINE.json (fixed base + 7
  * revolute links, frames alternating Rx(-90)/Rx(+90)); 2: fixed base + 2 parallel revolute links (arm_2DoF.ztk) */
 #define RKFD_SPEC_TABLE(X) X(3, 8, 0x3BBBu, 1) X(4, 3, 0x5u, 1) X(1, 8, 0x3BBBu, 0) X(2, 3, 0x5u, 0)
-/* rolled specialisations: (id, links); 5: fixed base + 7 revolute links, 6: + 6 revolute links */
-#define RKFD_SPEC_ROLLED_TABLE(X) X(5, 8, 0) X(6, 7, 0) X(7, 8, 1)
+/* rolled specialisations: (id, links, rigid layout, general frames); 5/6: fixed base + 7/6 revolute links with
+ * quarter-turn frames, 7: the same with rigid pairs on the last link, 8-10: general frames, 2/6/7 revolute links */
+#define RKFD_SPEC_ROLLED_TABLE(X) X(5, 8, 0, 0) X(6, 7, 0, 0) X(7, 8, 1, 0) X(8, 3, 0, 1) X(9, 7, 0, 1) X(10, 8, 0, 1)
 template <int ID> struct SpecOf { using type = SpecGeneric; };
 #define RKFD_SPEC_X(id, nl, cls, tm) template <> struct SpecOf<id> { using type = SpecSerialRev<id, nl, cls, tm>; };
 RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-#define RKFD_SPEC_X(id, nl, rg) template <> struct SpecOf<id> { using type = SpecSerialRevRolled<id, nl, rg>; };
+#define RKFD_SPEC_X(id, nl, rg, gen) template <> struct SpecOf<id> { using type = SpecSerialRevRolled<id, nl, rg, gen>; };
 RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
 /* specialisation ids the model is eligible for (bit id set; 0: generic kernel only), and their scratch sizes */
@@ -269,13 +272,13 @@ inline unsigned spec_match_mask(const ModelDev &m){
 #define RKFD_SPEC_X(id, nl, cls, tm) if( spec_serial_rev_match(m, nl, cls) ) mask |= 1u << id;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-#define RKFD_SPEC_X(id, nl, rg) if( spec_serial_rev_rolled_match(m, nl, rg) ) mask |= 1u << id;
+#define RKFD_SPEC_X(id, nl, rg, gen) if( spec_serial_rev_rolled_match(m, nl, rg, gen) ) mask |= 1u << id;
   RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return mask;
 }
 inline int spec_match_rolled(const ModelDev &m){
-#define RKFD_SPEC_X(id, nl, rg) if( spec_serial_rev_rolled_match(m, nl, rg) ) return id;
+#define RKFD_SPEC_X(id, nl, rg, gen) if( spec_serial_rev_rolled_match(m, nl, rg, gen) ) return id;
   RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return 0;
@@ -290,7 +293,7 @@ inline int spec_nscratch(int id){
 #define RKFD_SPEC_X(sid, nl, cls, tm) if( id == sid ) return SpecSerialRev<sid, nl, cls, tm>::NSCRATCH;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-#define RKFD_SPEC_X(sid, nl, rg) if( id == sid ) return SpecSerialRevRolled<sid, nl, rg>::NSCRATCH;
+#define RKFD_SPEC_X(sid, nl, rg, gen) if( id == sid ) return SpecSerialRevRolled<sid, nl, rg, gen>::NSCRATCH;
   RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return 0;
@@ -299,7 +302,7 @@ inline int spec_ntspace(int id){
 #define RKFD_SPEC_X(sid, nl, cls, tm) if( id == sid ) return SpecSerialRev<sid, nl, cls, tm>::NTSPACE;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-#define RKFD_SPEC_X(sid, nl, rg) if( id == sid ) return SpecSerialRevRolled<sid, nl, rg>::NTSPACE;
+#define RKFD_SPEC_X(sid, nl, rg, gen) if( id == sid ) return SpecSerialRevRolled<sid, nl, rg, gen>::NTSPACE;
   RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
   return 0;
@@ -336,7 +339,7 @@ struct Core {
     if constexpr ( Spec::ROLL != 0 ){
       f(0, LinkTag<J_FIXED, RO_GENERAL, 1>{});
 #pragma unroll (ROLL_UNROLL)
-      for(int i=1;i<Spec::NL;i++) f(i, LinkTag<J_REVOL, RO_RXS, 0>{});
+      for(int i=1;i<Spec::NL;i++) f(i, LinkTag<J_REVOL, Spec::RCLS, 0>{});
     } else {
       const int NLc = Spec::nl(m);
 #pragma unroll (Spec::UNROLL)
@@ -346,7 +349,7 @@ struct Core {
   template <class F> RKFD_HD void links_bwd(const ModelDev &m, F &&f){
     if constexpr ( Spec::ROLL != 0 ){
 #pragma unroll (ROLL_UNROLL)
-      for(int i=Spec::NL-1;i>=1;i--) f(i, LinkTag<J_REVOL, RO_RXS, 0>{});
+      for(int i=Spec::NL-1;i>=1;i--) f(i, LinkTag<J_REVOL, Spec::RCLS, 0>{});
       f(0, LinkTag<J_FIXED, RO_GENERAL, 1>{});
     } else {
       const int NLc = Spec::nl(m);

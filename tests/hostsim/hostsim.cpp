@@ -145,7 +145,7 @@ void hostsim_run(HostSim *h, int mode, int nsteps)
 #define RKFD_SPEC_X(id, nl, cls, tmv) case id: { ctx.tm = tmv != 0; ctx.tsp.assign(spec_ntspace(id) + 1, std::nan("")); Core<HostCtx, SpecOf<id>::type> core(ctx); core.run(h->model, mode, nsteps); } break;
     RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
-#define RKFD_SPEC_X(id, nl, rg) case id: { ctx.tm = true; ctx.tsp.assign(spec_ntspace(id) + 1, std::nan("")); Core<HostCtx, SpecOf<id>::type> core(ctx); core.run(h->model, mode, nsteps); } break;
+#define RKFD_SPEC_X(id, nl, rg, gen) case id: { ctx.tm = true; ctx.tsp.assign(spec_ntspace(id) + 1, std::nan("")); Core<HostCtx, SpecOf<id>::type> core(ctx); core.run(h->model, mode, nsteps); } break;
     RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
     default: { Core<HostCtx> core(ctx); core.run(h->model, mode, nsteps); } break;

@@ -300,3 +300,23 @@ def test_integrator_menu_matches_oracle(oracle, name, integ):
         for b in range(B):
             (oq, oqd, oqdd), _, _ = ref[b]
             assert relerr(hq[b, :w.nq], oq) < 1e-9 and relerr(hqd[b, :w.nq], oqd) < 1e-8, (name, integ, spec, b)
+
+
+def test_rolled_general_frame_specialisation(oracle):
+    """Fixed-base serial revolute arms with arbitrary constant frames (arm_2DoF.ztk; a random 7-joint arm) run the
+    rolled specialisation with dense frame rotations: against the generic kernel (same arithmetic) and the oracle."""
+    rng = np.random.default_rng(3)
+    worlds = [(ch.world_c1_serial(), 8), (ch.World(chains=[ch.random_chain(rng, 8, jtypes=("revolute",), motors=True)]), 10)]
+    for w, sid in worlds:
+        B, nsteps = 6, 12
+        q = rng.uniform(-1.5, 1.5, (B, w.nq)); qd = rng.uniform(-2, 2, (B, w.nq)); u = rng.uniform(-6, 6, (B, w.nl))
+        out = []
+        for spec in (None, "rolled"):
+            hs = HostSim(w, B, spec=spec)
+            assert hs.spec_rolled == sid
+            hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(nsteps)
+            out.append(hs.get_state())
+        assert relerr(out[1][0], out[0][0]) < 1e-12 and relerr(out[1][1], out[0][1]) < 1e-11
+        ref = oracle_run(oracle, w, q, qd, u, nsteps)
+        for b in range(B):
+            assert relerr(out[1][0][b, :w.nq], ref[b][0][0]) < 1e-9
