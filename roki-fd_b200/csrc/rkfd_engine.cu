@@ -155,7 +155,8 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     st.cref = dalloc<double>(*s, (size_t)3*ns*s->ld);
     st.cf = dalloc<double>(*s, (size_t)3*ns*s->ld);
     st.status = dalloc<int>(*s, s->ld);
-    st.ws = model.ws_doubles > 0 ? dalloc<double>(*s, (size_t)(s->ld/32)*model.ws_doubles) : nullptr;
+    /* per-warp workspace of the dense warp-cooperative contact solve; the single-link paths use ws1 only */
+    st.ws = ( model.ws_doubles > 0 && model.rigid_link < 0 ) ? dalloc<double>(*s, (size_t)(s->ld/32)*model.ws_doubles) : nullptr;
     st.ws1 = model.ws1_doubles > 0 ? dalloc<double>(*s, (size_t)model.ws1_doubles*s->ld) : nullptr;
     int nmax = nq; if( nl > nmax ) nmax = nl; if( 3*ns > nmax ) nmax = 3*ns;
     s->nstage = (size_t)nmax*s->B; s->dstage = dalloc<double>(*s, s->nstage);
