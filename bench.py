@@ -106,7 +106,7 @@ def cpu_baseline_run(ow, q, qd, u, n_steps, threads=0):
     return q.shape[0] * (n_steps + 0.2) / dt, used, dt
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be
     compiled (its dependencies are absent), so this times the oracle port with every host thread."""
     rank = int(os.environ.get("RANK", "0"))
@@ -135,10 +135,49 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
                             "note": "CPU restatement of RoKi-FD's algorithm; reference un-buildable (ZEDA/ZM/Zeo/RoKi absent)"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+def _json_only_stdout():
+    """Everything but the result line goes to stderr: native libraries (NCCL prints its version banner) write to file
+    descriptor 1 directly, and the contract is ONE JSON line on stdout.  Returns the function that prints it."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real, (json.dumps(obj) + "\n").encode())
+    return emit
+
+
+def bind_to_gpu_numa_node(torch, device_index):
+    """Pins this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers of the
+    end-to-end leg are allocated next to it (8 ranks on a two-socket box otherwise push half of their PCIe traffic
+    across the socket interconnect).  Best effort: returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def main():
+    emit = _json_only_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -149,7 +188,7 @@ def main():
     ap.add_argument("--e2e-upload-state", action="store_true", help="e2e leg: also re-send (q, q') host->device every step")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -161,6 +200,7 @@ def main():
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)     # before any pinned allocation: host buffers next to the GPU
     dist = None
     if world_size > 1:
         import torch.distributed as dist
@@ -268,7 +308,7 @@ def main():
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": WORKLOAD, "envs_per_gpu": B, "dt": world.dt, "integrator": "RKG", "solver": world.solver,
                       "settle_steps": SETTLE_STEPS, "envs_in_contact": contact_frac, "mean_active_vertices": mean_active,
-                      "l2": "per-GPU state (%.0f MB) is larger than the 126 MB L2" % (B * 8 * 140 / 1e6)},
+                      "numa_node": numa, "l2": "per-GPU state (%.0f MB) is larger than the 126 MB L2" % (B * 8 * 140 / 1e6)},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                    "io": "per step: motor inputs u[B][%d] host->device%s, rkFDUpdate, (q, q', q'')[B][%d] device->host; pinned host buffers, "
                          "asynchronous copies on their own streams" % (nl, " + state (q, q')" if args.e2e_upload_state else "", nq)},
@@ -290,7 +330,7 @@ def main():
                                "note": "CPU restatement of RoKi-FD's algorithm; reference un-buildable (ZEDA/ZM/Zeo/RoKi absent)"}
     fd.destroy()
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
