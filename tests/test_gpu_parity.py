@@ -433,3 +433,30 @@ def test_integrator_menu(capi, oracle, integ):
     fd.destroy()
     oq, oqd, oqdd, _ = oracle.OracleWorld(w).batch_run(q, qd, u, nsteps=20)
     assert relerr(gq, oq) < 1e-9 and relerr(gqd, oqd) < 1e-8
+
+
+def test_divergent_slow_paths_keep_tensor_memory_accesses_converged(capi, monkeypatch):
+    """Lanes of one warp take different branches around the warp-collective tensor-memory accesses of the
+    specialised kernels: huge joint angles (the slow argument reduction of sincos) and joint velocities so large
+    that the stage-to-stage angle addition falls back to sincos.  The kernels must neither hang nor disagree with
+    the generic kernel."""
+    w = ch.world_c3(base_z=0.45)
+    B = 512
+    q, qd, u = ch.sample_state(w, B, seed=77)
+    rng = np.random.default_rng(5)
+    big = rng.random(B) < 0.3
+    q[big] += rng.uniform(-3e6, 3e6, (big.sum(), w.nq))
+    fast = rng.random(B) < 0.3
+    qd[fast] = rng.uniform(-400, 400, (fast.sum(), w.nq))
+    out = []
+    for spec in (0, 5, 3):
+        monkeypatch.setenv("RKFD_SPEC", str(spec))
+        fd = gpu_world(capi, w, q, qd, u)
+        fd.update_n(3)
+        out.append(fd.batch_get_state())
+        fd.destroy()
+    fin = np.isfinite(out[0][0]).all(1)
+    assert fin.mean() > 0.95
+    for o in out[1:]:
+        assert (np.isfinite(o[0]).all(1) == fin).all()
+        assert relerr(o[1][fin], out[0][1][fin]) < 1e-9
