@@ -294,6 +294,34 @@ def world_c1_serial():
     return World(chains=[arm_2dof()])
 
 
+def biped(stuff="body"):
+    """A small legged tree for the C4-shaped workload (multi-limb legged model): floating
+    trunk + two legs of three revolute joints (hip, knee, ankle: pitch axes) with DC motors and an 8-vertex sole
+    under each ankle link.  12 DoF, 7 links, 16 contact vertices.  (The reference's humanoid mighty.ztk has 26 DoF
+    and needs the Volume solver, which is not built.)"""
+    links = [Link(name="trunk", jtype="float", mass=8.0, stuff=stuff, com=np.array([0, 0, 0.1]),
+                  inertia=np.diag([0.12, 0.10, 0.06]))]
+    for side, y in (("L", 0.09), ("R", -0.09)):
+        base = len(links)
+        specs = [("hip", 0, np.array([0.0, y, -0.05]), 1.5, 0.18), ("knee", base, np.array([0.0, -0.2, 0.0]), 1.0, 0.18),
+                 ("ankle", base + 1, np.array([0.0, -0.2, 0.0]), 0.4, 0.03)]
+        for k, (nm, parent, p, m, ln) in enumerate(specs):
+            l = Link(name=nm + side, parent=parent, jtype="revolute", mass=m, stuff=stuff,
+                     com=np.array([0.0, -ln / 2, 0.0]), inertia=np.diag([m * 0.004, m * 0.001, m * 0.004]),
+                     org_p=p, org_R=rot_x(np.pi / 2) if k == 0 else np.eye(3))
+            l.motor = motor_arm2dof()
+            l.viscosity, l.coulomb, l.sfriction = 2.2, 4.32, 4.92
+            links.append(l)
+        links[-1].shapes = [box_verts(0.16, 0.03, 0.08, center=(0.03, -0.045, 0.0))]
+    return ChainModel("biped", links)
+
+
+def world_c4_penalty():
+    """C4-shaped workload with what is built: the legged tree on the soft floor (vertex penalty contact)."""
+    return World(chains=[biped(), floor_soft()],
+                 contact_info=[ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0, SF=0.5, KF=0.3)])
+
+
 def sample_state(world, B, seed=20260418):
     """Synthetic randomised states of SURVEY.md section 8d: q ~ U(-pi/2, pi/2), qd ~ U(-1, 1),
     motor voltage ~ U(-6, 6); float joints get position z lifted by +0.3."""

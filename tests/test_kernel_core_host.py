@@ -36,6 +36,7 @@ WORLDS = {
                                         contact_info=[c for c in ch.contact_info_table() if c.type == "elastic"]
                                         + [ch.ContactInfo("ground", "body", "elastic", E=500.0, V=5.0)]),
     "c1_serial_arm2dof": lambda: ch.world_c1_serial(),
+    "c4_biped_penalty": lambda: ch.world_c4_penalty(),
 }
 
 
