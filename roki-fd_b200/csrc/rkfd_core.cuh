@@ -157,9 +157,14 @@ struct SpecGeneric {
   static RKFD_HD int rk_slot(const ModelDev &m){ return m.rk_slot; }
   static RKFD_HD int nq(const ModelDev &m){ return m.nq; }
   /* 1-DoF joints: slots of (sin, cos, 1/D, u) in the "T space" (Ctx::TL/TS) - the scratch column itself here */
-  static RKFD_HD int sc(int, const LinkDev &L){ return L.slot + 6; }
-  static constexpr int TM = 0, NTSPACE = 0, SCS = 0;
+  static RKFD_HD int sc(int, const LinkDev &L){ return L.sc; }
+  static constexpr int TM = 0, NTSPACE = 0, SCS = 0, TCOLS = 128;
 };
+/* The generic table-driven kernel with the T space in tensor memory (worlds without rigid pairs; the table carries
+ * the tensor-memory layout, model_layout(m, true)): trees, floating bases, any joint mix.  256 TMEM columns per
+ * warpgroup = 128 doubles per thread, two 128-thread CTAs per SM. */
+struct SpecGenericTM : SpecGeneric { static constexpr int ID = 11, TM = 1, TCOLS = 256; };
+constexpr int SPEC_GENERIC_TM = 11, SPEC_GENERIC_TM_MAX_T = 128;
 /* link 0 = fixed root, links 1..NL-1 revolute and serial; CLS: 2 bits per revolute link (RoClass 1..3) */
 /* TM_ = 1: the integrator stage state and (sin, cos, 1/D, u) of every joint live in TENSOR MEMORY (tcgen05.st/ld,
  * one TMEM lane per thread, 8 bytes per element) instead of the shared-memory column, which then holds 6 doubles per
@@ -168,7 +173,7 @@ struct SpecGeneric {
  * in warp-uniform code. */
 template <int ID_, int NL_, unsigned CLS_, int TM_>
 struct SpecSerialRev {
-  static constexpr int ID = ID_, NL = NL_, UNROLL = NL_, TM = TM_, ROLL = 0, SCS = 0;
+  static constexpr int ID = ID_, NL = NL_, UNROLL = NL_, TM = TM_, ROLL = 0, SCS = 0, TCOLS = 128;
   static constexpr int WEXT = TM_ ? 6*NL_ : 6 + 10*(NL_-1);
   static constexpr int RK = TM_ ? 4*(NL_-1) : WEXT + 6;                 /* T space when TM_ */
   static constexpr int NSCRATCH = TM_ ? WEXT + 6 : RK + 4*(NL_-1);     /* shared-memory doubles per environment */
@@ -207,7 +212,7 @@ struct SpecSerialRevRolled {
   static constexpr int ID = ID_, NL = NL_, UNROLL = 1, TM = 1, ROLL = 1, RG = RG_, RCLS = GEN_ ? RO_GENERAL : RO_RXS;
   /* RG: (sin, cos, 1/D, u) stay in the shared-memory column (SCS): the contact solve reads them for OTHER lanes'
    * environments (lane-parallel probes) and in divergent code, which tensor memory allows neither */
-  static constexpr int SCS = RG_;
+  static constexpr int SCS = RG_, TCOLS = 128;
   static constexpr int PER = RG_ ? 13 : 6, FRAME = PER*NL_, WEXT = FRAME + (RG_ ? 24 : 0);
   static constexpr int RK = RG_ ? 0 : 4*(NL_-1), NSCRATCH = WEXT + 6, NTSPACE = (RG_ ? 4 : 8)*(NL_-1);
   static RKFD_HD int nl(const ModelDev &){ return NL_; }
@@ -260,6 +265,7 @@ inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
  * quarter-turn frames, 7: the same with rigid pairs on the last link, 8-10: general frames, 2/6/7 revolute links */
 #define RKFD_SPEC_ROLLED_TABLE(X) X(5, 8, 0, 0) X(6, 7, 0, 0) X(7, 8, 1, 0) X(8, 3, 0, 1) X(9, 7, 0, 1) X(10, 8, 0, 1)
 template <int ID> struct SpecOf { using type = SpecGeneric; };
+template <> struct SpecOf<11> { using type = SpecGenericTM; };
 #define RKFD_SPEC_X(id, nl, cls, tm) template <> struct SpecOf<id> { using type = SpecSerialRev<id, nl, cls, tm>; };
 RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
@@ -299,6 +305,7 @@ inline int spec_nscratch(int id){
   return 0;
 }
 inline int spec_ntspace(int id){
+  if( id == SPEC_GENERIC_TM ) return SPEC_GENERIC_TM_MAX_T;
 #define RKFD_SPEC_X(sid, nl, cls, tm) if( id == sid ) return SpecSerialRev<sid, nl, cls, tm>::NTSPACE;
   RKFD_SPEC_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
@@ -366,7 +373,7 @@ struct Core {
   RKFD_HD double Q(int k){ return Spec::SCS ? c.S(k) : c.TL(k); }
   RKFD_HD void Qw(int k, double v){ if( Spec::SCS ) c.S(k) = v; else c.TS(k, v); }
   RKFD_HD void Q2(int k, double &a, double &b){ if( Spec::SCS ){ a = c.S(k); b = c.S(k+1); } else c.TL2(k, a, b); }
-  RKFD_HD V3 t3(int k){ double x, y, z; c.TL2(k, x, y); z = c.TL(k+2); return v3(x, y, z); }
+  RKFD_HD V3 t3(int k){ const double x = c.TL(k), y = c.TL(k+1), z = c.TL(k+2); return v3(x, y, z); }   /* k is arbitrary: no paired (x4) load */
   RKFD_HD void tw3(int k, V3 v){ c.TS(k, v.x); c.TS(k+1, v.y); c.TS(k+2, v.z); }
   RKFD_HD V3 ld3(int k){ return v3(c.S(k), c.S(k+1), c.S(k+2)); }
   RKFD_HD void st3(int k, V3 v){ c.S(k)=v.x; c.S(k+1)=v.y; c.S(k+2)=v.z; }

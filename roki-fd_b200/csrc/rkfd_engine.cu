@@ -17,6 +17,7 @@
 #include <stdexcept>
 
 #include "rkfd_kernel.cuh"
+#include "rkfd_model.h"
 
 namespace rkfd {
 
@@ -108,7 +109,7 @@ template <class T> static T *dalloc(Shard &s, size_t n)
 
 /* kernel variants, one translation unit each (rkfd_kernel_variant.cu): BLOCK_GSCR_RIGID_SPEC_MINB */
 #define RKFD_VARIANT_LIST(X) \
-  X(128,0,1,7,2) X(64,0,1,7,4) X(128,0,0,5,4) X(128,0,0,8,4) X(128,0,0,9,4) X(128,0,0,10,4) X(256,0,0,5,2) X(512,0,0,5,1) X(256,0,0,6,2) X(256,0,0,3,2) X(512,0,0,3,1) X(128,0,0,3,4) X(128,0,0,3,3) X(128,0,0,4,4) X(128,0,0,1,1) X(256,0,0,1,1) X(128,0,0,2,1) \
+  X(128,0,1,7,2) X(64,0,1,7,4) X(128,0,0,5,4) X(128,0,0,8,4) X(128,0,0,9,4) X(128,0,0,10,4) X(128,0,0,11,2) X(256,0,0,5,2) X(512,0,0,5,1) X(256,0,0,6,2) X(256,0,0,3,2) X(512,0,0,3,1) X(128,0,0,3,4) X(128,0,0,3,3) X(128,0,0,4,4) X(128,0,0,1,1) X(256,0,0,1,1) X(128,0,0,2,1) \
   X(128,0,0,0,1) X(256,0,0,0,1) X(64,0,0,0,1) X(32,0,0,0,1) X(64,1,0,0,1) \
   X(128,0,1,0,1) X(256,0,1,0,1) X(64,0,1,0,1) X(32,0,1,0,1) X(64,1,1,0,1)
 #define RKFD_DECL(B,G,R,S,M) extern const KernelVariant rkfd_variant_##B##_##G##_##R##_##S##_##M;
@@ -127,8 +128,10 @@ static int g_model_owner[64][NVARIANTS] = {{0}};   /* [device][variant]: engine 
 
 static int variant_index(const KernelVariant *kv){ for(int i=0;i<NVARIANTS;i++) if( g_variants[i] == kv ) return i; return 0; }
 
-Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : model_(model), B_(B), id_(g_next_engine_id++)
+Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : model_(model), model_tm_(model), B_(B), id_(g_next_engine_id++)
 {
+  /* the same table with the tensor-memory scratch map, for the generic kernel variant that keeps its T space in TMEM */
+  if( !model.has_rigid ) model_layout(model_tm_, true);
   if( B <= 0 ) throw std::runtime_error("rokifd_b200: environment count must be positive");
   if( device_count() <= 0 ) throw std::runtime_error("rokifd_b200: no CUDA device (there is no CPU fallback)");
   std::vector<int> devs = devices;
@@ -165,6 +168,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     int best = 0; const bool rigid = model.has_rigid && model.solver != S_VOLUME;
     /* model specialisation (RKFD_SPEC=0 forces the generic kernel: tuning / comparison aid) */
     unsigned specs = spec_match_mask(model);
+    if( !model.has_rigid && model_tm_.ntspace > 0 && model_tm_.ntspace <= SPEC_GENERIC_TM_MAX_T ) specs |= 1u << SPEC_GENERIC_TM;
     if( const char *fs = std::getenv("RKFD_SPEC") ) specs &= 1u << std::atoi(fs);    /* 0: generic kernel only */
     for(int pass=0; pass<3 && best==0; pass++)
       for(const KernelVariant *kv : g_variants){
@@ -173,7 +177,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
         if( pass == 0 ? !( kv->spec > 0 && (specs >> kv->spec & 1u) ) : kv->spec != 0 ) continue;
         if( const char *fb = std::getenv("RKFD_FORCE_BLOCK") ) if( std::atoi(fb) != kv->block ) continue;   /* tuning aids */
         if( const char *fm = std::getenv("RKFD_FORCE_MINB") ) if( std::atoi(fm) != kv->minb ) continue;
-        const int nscr = kv->spec ? spec_nscratch(kv->spec) : model.nscratch;
+        const int nscr = kv->spec == SPEC_GENERIC_TM ? model_tm_.nscratch : ( kv->spec ? spec_nscratch(kv->spec) : model.nscratch );
         size_t smem = kv->gscr ? 0 : (size_t)nscr*kv->block*sizeof(double);
         if( const char *pad = std::getenv("RKFD_SMEM_PAD") ) smem += (size_t)std::atoi(pad);   /* tuning aid: lowers occupancy */
         if( smem > 227*1024 ) continue;
@@ -215,7 +219,7 @@ void Engine::upload_model(Shard &s)
   if( owner == id_ ) return;
   /* another engine's kernels may still read the constant table on this device */
   if( owner != 0 ) CK(cudaDeviceSynchronize());
-  CK(s.kv->upload(&model_, s.stream));
+  CK(s.kv->upload(s.kv->spec == SPEC_GENERIC_TM ? &model_tm_ : &model_, s.stream));
   owner = id_;
 }
 

@@ -54,7 +54,7 @@ class Engine {
  private:
   void upload_model(Shard &s);
   void launch(Shard &s, int mode, int nsteps);
-  ModelDev model_;
+  ModelDev model_, model_tm_;     /* model_tm_: the same table with the tensor-memory scratch map (generic TM kernel) */
   int B_;
   std::vector<Shard*> shards_;
   long long launches_ = 0;

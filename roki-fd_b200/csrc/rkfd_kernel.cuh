@@ -19,10 +19,11 @@ extern __shared__ double rkfd_smem[];
 /* tensor memory as per-thread scratch: one TMEM lane per thread (warp w of the CTA owns lanes 32*(w%4)..+31),
  * element k of the thread = 32-bit columns 2k, 2k+1.  tcgen05.ld/st are warp-collective (.sync.aligned): every
  * T-space access sits in warp-uniform code. */
-constexpr int TMEM_COLS_PER_WARPGROUP = 128;     /* 64 doubles per thread */
+/* columns per warpgroup: Spec::TCOLS (128 = 64 doubles per thread for the arm specialisations, 256 for the generic kernel) */
 
 template <int BLOCK, bool GSCR, bool RIGID_, bool TM>
 struct DevCtx {
+  /* (the tensor-memory columns per warpgroup only enter the kernel prologue: tbase) */
   static constexpr bool RIGID = RIGID_;
   StateDev st; int e, cur, tid;     /* e / tid: the SELECTED environment / scratch column (own, except in cooperative sections) */
   int e0, tid0, wsd;
@@ -95,11 +96,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) rkfd_step_kernel(StateDev st, int
    * and the tensor-memory allocation below rely on; the padding environments hold a valid zero state */
   DevCtx<BLOCK,GSCR,RIGID,TM> ctx; ctx.st = st; ctx.e = ctx.e0 = e; ctx.cur = cur; ctx.tid = ctx.tid0 = threadIdx.x; ctx.wsd = c_model.ws_doubles;
   ctx.tbase = 0;
-  constexpr unsigned TCOLS = TMEM_COLS_PER_WARPGROUP*((BLOCK + 127)/128);
+  constexpr unsigned TCOLS = Spec::TCOLS*((BLOCK + 127)/128);
   __shared__ unsigned tmem_addr;
   if( TM ){
     static_assert(!TM || ((TCOLS & (TCOLS-1)) == 0 && TCOLS >= 32 && TCOLS <= 512), "tensor-memory columns: power of two in [32, 512]");
-    static_assert(!TM || 2*Spec::NTSPACE <= TMEM_COLS_PER_WARPGROUP, "T space does not fit the tensor-memory lane");
+    static_assert(!TM || 2*Spec::NTSPACE <= Spec::TCOLS, "T space does not fit the tensor-memory lane");
     if( threadIdx.x < 32 ){
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(&tmem_addr)), "r"(TCOLS) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) rkfd_step_kernel(StateDev st, int
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned warp = threadIdx.x >> 5;
-    ctx.tbase = tmem_addr + (((warp & 3u)*32u) << 16) + (warp >> 2)*TMEM_COLS_PER_WARPGROUP;
+    ctx.tbase = tmem_addr + (((warp & 3u)*32u) << 16) + (warp >> 2)*Spec::TCOLS;
   }
   Core<DevCtx<BLOCK,GSCR,RIGID,TM>, Spec> core(ctx);
   core.run(c_model, mode, nsteps);

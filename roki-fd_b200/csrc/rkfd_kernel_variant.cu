@@ -33,7 +33,7 @@ static int blocks_per_sm(size_t smem)
     const int regs_warp = ((a.numRegs*32 + 255)/256)*256, warps = RKFD_BLOCK/32;
     int n = regs_sm/(regs_warp*warps);
     const int by_smem = (int)((size_t)smem_sm/(smem + a.sharedSizeBytes + (size_t)resv));
-    const int by_tmem = 512/(TMEM_COLS_PER_WARPGROUP*((RKFD_BLOCK + 127)/128)), by_thr = 2048/RKFD_BLOCK;
+    const int by_tmem = 512/(SpecOf<RKFD_SPEC>::type::TCOLS*((RKFD_BLOCK + 127)/128)), by_thr = 2048/RKFD_BLOCK;
     if( by_smem < n ) n = by_smem; if( by_tmem < n ) n = by_tmem; if( by_thr < n ) n = by_thr;
     if( n > nb ) nb = n;
   }

@@ -19,6 +19,32 @@ static void mat3_mulv(const double *a, const double *x, double *y){
   std::memcpy(y, t, sizeof t);
 }
 
+void model_layout(ModelDev &m, bool tm)
+{
+  const int nl = m.nl, nq = m.nq;
+  int slot = 0, t = 0;
+  for(int i=0;i<nl;i++){
+    LinkDev &d = m.link[i];
+    d.branch_slot = d.accum_slot = d.wext_slot = d.frame_slot = -1;
+    d.slot = slot; d.wslot = slot + link_w_offset(d.jtype, m.has_rigid);
+    const bool one = d.jtype == J_REVOL || d.jtype == J_PRISM;
+    if( tm && one ){ d.sc = t; t += 4; slot += link_slot_count(d.jtype, m.has_rigid) - 4; d.wslot = d.slot + ( m.has_rigid ? 6 : 0 ); }
+    else { d.sc = slot + 6; slot += link_slot_count(d.jtype, m.has_rigid); }
+  }
+  for(int i=0;i<nl;i++){
+    LinkDev &d = m.link[i];
+    if( d.parent >= 0 && !d.serial ){
+      LinkDev &p = m.link[d.parent];
+      if( p.branch_slot < 0 ){ p.branch_slot = slot; slot += BRANCH_SLOTS; p.accum_slot = slot; slot += ACCUM_SLOTS; }
+    }
+    if( d.cell_end > d.cell_begin ){ d.wext_slot = slot; slot += WEXT_SLOTS;
+      if( m.has_rigid ){ d.frame_slot = slot; slot += FRAME_SLOTS; } }
+  }
+  if( tm ){ m.rk_slot = t; t += 4*nq; m.ntspace = t; }
+  else { m.rk_slot = slot; slot += 4*nq; m.ntspace = 0; }
+  m.nscratch = slot;
+}
+
 bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
 {
   std::memset(&m, 0, sizeof m);
@@ -135,19 +161,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   for(int i=0;i<nl;i++) if( m.link[i].parent >= 0 ) m.link[m.link[i].parent].nchild++;
   for(int i=0;i<nl;i++){ LinkDev &d = m.link[i]; d.serial = ( d.parent >= 0 && d.parent == i-1 && m.link[d.parent].nchild == 1 ) ? 1 : 0;
     d.branch_slot = d.accum_slot = d.wext_slot = d.frame_slot = -1; }
-  int slot = 0;
-  for(int i=0;i<nl;i++){ m.link[i].slot = slot; m.link[i].wslot = slot + link_w_offset(m.link[i].jtype, m.has_rigid); slot += link_slot_count(m.link[i].jtype, m.has_rigid); }
-  for(int i=0;i<nl;i++){
-    LinkDev &d = m.link[i];
-    if( d.parent >= 0 && !d.serial ){
-      LinkDev &p = m.link[d.parent];
-      if( p.branch_slot < 0 ){ p.branch_slot = slot; slot += BRANCH_SLOTS; p.accum_slot = slot; slot += ACCUM_SLOTS; }
-    }
-    if( d.cell_end > d.cell_begin ){ d.wext_slot = slot; slot += WEXT_SLOTS;
-      if( m.has_rigid ){ d.frame_slot = slot; slot += FRAME_SLOTS; } }
-  }
-  m.rk_slot = slot; slot += 4*nq;
-  m.nscratch = slot;
+  model_layout(m, false);
   /* ---- rigid-contact tables: slot -> (pair, vertex), workspace layout per warp */
   m.rigid_mask = 0; int nrs = 0;
   for(int p=0;p<m.npair;p++) for(int k=0;k<m.cell[m.pair[p].cell].nvert;k++){

@@ -65,5 +65,10 @@ struct WorldHost {
  * exceeded or the topology is not supported. */
 bool build_model(const WorldHost &w, ModelDev &out, std::string &err);
 
+/* Scratch map of the generic kernel.  tm = false: everything in the shared-memory column.  tm = true (worlds without
+ * rigid pairs): (sin, cos, 1/D, u) of the 1-DoF joints and the integrator stage state move to the T space (tensor
+ * memory), the column keeps the rest.  Rewrites slot/sc/wslot/branch/accum/wext/frame slots, rk_slot, nscratch, ntspace. */
+void model_layout(ModelDev &m, bool tm);
+
 }  // namespace rkfd
 #endif

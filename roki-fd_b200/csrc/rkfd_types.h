@@ -48,6 +48,8 @@ struct LinkDev {
   double m_min, m_max;
   int parent, jtype, mtype, ndof, qofs;
   int slot;            /* first scratch slot of this link */
+  int sc;              /* 1-DoF joints: index of (sin, cos, 1/D, u) - slot + 6 in the scratch column, or a T-space index in the
+                          tensor-memory layout of the generic kernel (model_layout_tm) */
   int wslot;           /* slots of (w, gravity direction) written by pass 1: aliased with U (= slot) unless the world has
                           rigid pairs, where pass 2 runs twice per evaluation and they must survive */
   int serial;          /* 1: parent == index-1 and the parent has no other child (carry in registers) */
@@ -72,6 +74,7 @@ struct ModelDev {
   /* stage coefficients of the integrator times dt, folded on the host (constant-bank operands in the kernel) */
   struct RK { double c21, c31, c32, c42, c43, b1, b2, b3, b4; int ns; } rk;
   int nscratch;        /* scratch slots (doubles) per env */
+  int ntspace;         /* tensor-memory layout: T-space doubles per env (per-joint scalars + integrator state), else 0 */
   int ws_doubles;      /* per-warp workspace (doubles) of the rigid-contact solve, 0 when no rigid pair */
   int ws_geo, ws_b, ws_f, ws_A, ws_du, ws_da, ws_qp;   /* offsets inside the workspace */
   int nmax;            /* 3 * (rigid contact slots) */

@@ -103,7 +103,9 @@ int hostsim_nq(HostSim *h){ return h->model.nq; }
 int hostsim_nl(HostSim *h){ return h->model.nl; }
 /* model specialisation the kernel would pick (0: generic); hostsim_use_spec makes hostsim_run use it */
 int hostsim_spec_match(HostSim *h, int tm){ return tm == 2 ? spec_match_rolled(h->model) : spec_match(h->model, tm); }   /* 2: rolled */
-void hostsim_use_spec(HostSim *h, int id){ h->spec = ( id > 0 && (spec_match_mask(h->model) >> id & 1u) ) ? id : 0; }
+void hostsim_use_spec(HostSim *h, int id){
+  if( id == SPEC_GENERIC_TM ){ h->spec = h->model.has_rigid ? 0 : id; return; }
+  h->spec = ( id > 0 && (spec_match_mask(h->model) >> id & 1u) ) ? id : 0; }
 int hostsim_nslot(HostSim *h){ return h->model.nslot; }
 int hostsim_nscratch(HostSim *h){ return h->model.nscratch; }
 void hostsim_free(HostSim *h){ for(void *p : h->allocs) std::free(p); for(auto *c : h->chains) delete c; delete h; }
@@ -148,6 +150,10 @@ void hostsim_run(HostSim *h, int mode, int nsteps)
 #define RKFD_SPEC_X(id, nl, rg, gen) case id: { ctx.tm = true; ctx.tsp.assign(spec_ntspace(id) + 1, std::nan("")); Core<HostCtx, SpecOf<id>::type> core(ctx); core.run(h->model, mode, nsteps); } break;
     RKFD_SPEC_ROLLED_TABLE(RKFD_SPEC_X)
 #undef RKFD_SPEC_X
+    case SPEC_GENERIC_TM: {     /* the generic core on the tensor-memory scratch map */
+      ModelDev mt = h->model; model_layout(mt, true);
+      ctx.tm = true; ctx.tsp.assign(mt.ntspace + 1, std::nan("")); ctx.scr.assign(mt.nscratch + 1, std::nan(""));
+      Core<HostCtx, SpecGenericTM> core(ctx); core.run(mt, mode, nsteps); } break;
     default: { Core<HostCtx> core(ctx); core.run(h->model, mode, nsteps); } break;
     }
     h->last_ws = ctx.wsp;

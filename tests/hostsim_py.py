@@ -83,7 +83,7 @@ class HostSim:
         # model specialisations the kernel could pick (0: generic): scratch in shared memory / in tensor memory
         self.spec, self.spec_tm, self.spec_rolled = (L.hostsim_spec_match(self.h, k) for k in (0, 1, 2))
         if spec:                                   # "smem" | "tmem" | "rolled": run that specialisation's code path
-            sid = {"smem": self.spec, "tmem": self.spec_tm, "rolled": self.spec_rolled}[spec]
+            sid = {"smem": self.spec, "tmem": self.spec_tm, "rolled": self.spec_rolled, "generic_tm": 11}[spec]
             assert sid > 0, "model matches no compiled specialisation"
             L.hostsim_use_spec(self.h, sid)
 

@@ -461,3 +461,23 @@ def test_divergent_slow_paths_keep_tensor_memory_accesses_converged(capi, monkey
     for o in out[1:]:
         assert (np.isfinite(o[0]).all(1) == fin).all()
         assert relerr(o[1][fin], out[0][1][fin]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["c4_biped_penalty", "c1_box_hardsoft", "arm_and_box"])
+def test_generic_kernel_with_tensor_memory_scratch(capi, monkeypatch, name):
+    """The generic table-driven kernel with its T space in tensor memory (RKFD_SPEC=11: trees, floating bases, any joint
+    mix without rigid pairs) against the shared-memory generic kernel: same arithmetic, agreement to rounding."""
+    w = WORLDS[name]()
+    B = 148 * 2 * 128 + 5
+    q, qd, u = ch.sample_state(w, B, seed=29)
+    out = []
+    for spec in (0, 11):
+        monkeypatch.setenv("RKFD_SPEC", str(spec))
+        fd = gpu_world(capi, w, q, qd, u)
+        fd.update_n(12)
+        out.append(fd.batch_get_state())
+        fd.destroy()
+    fin = np.isfinite(out[0][0]).all(1)
+    assert fin.mean() > 0.95
+    for x, y in zip(out[0][:2], out[1][:2]):      # two instantiations: the compiler contracts a few products differently
+        assert relerr(y[fin], x[fin]) < 1e-11

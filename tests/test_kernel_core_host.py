@@ -321,3 +321,21 @@ def test_rolled_general_frame_specialisation(oracle):
         ref = oracle_run(oracle, w, q, qd, u, nsteps)
         for b in range(B):
             assert relerr(out[1][0][b, :w.nq], ref[b][0][0]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["c4_biped_penalty", "c1_box_hardsoft", "arm_and_box"])
+def test_generic_core_on_tensor_memory_layout(name):
+    """The generic table-driven core on the tensor-memory scratch map (model_layout(m, true): per-joint scalars and the
+    integrator state in the T space) is the same arithmetic: bit-identical to the shared-memory layout."""
+    w = WORLDS[name]() if name in WORLDS else ch.World(chains=[ch.arm_2dof(), ch.box(), ch.floor_soft()],
+                                                       contact_info=[ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0)])
+    B, nsteps = 6, 15
+    q, qd, u = ch.sample_state(w, B, seed=19)
+    out = []
+    for spec in (None, "generic_tm"):
+        hs = HostSim(w, B, spec=spec)
+        hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(nsteps)
+        out.append((hs.get_state(), hs.get_contact()))
+    for a, b in zip(out[0], out[1]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
