@@ -226,8 +226,22 @@ def test_multi_device_sharding(capi, oracle):
     fd.destroy()
 
 
+def biped_pose(name, q):
+    """The random trunk pose made a standing one (both soles near the floor)."""
+    if "biped" in name:
+        q[:, 2] = 0.44; q[:, 3:6] *= 0.1; q[:, 6:] *= 0.3
+    return q
+
+
+def biped_rigid(solver):
+    """Contacts on TWO links of one tree (both soles on the rigid floor): the dense warp-cooperative contact solve."""
+    return ch.World(chains=[ch.biped(), ch.floor()],
+                    contact_info=[ch.ContactInfo("ground", "body", "rigid", K=1000.0, L=0.001, SF=0.5, KF=0.3)], solver=solver)
+
+
 RIGID_WORLDS = {
     "c5_arm7_mlcp": lambda: ch.world_c5(base_z=0.1, solver="MLCP"),
+    "biped_two_feet_mlcp": lambda: biped_rigid("MLCP"),
     "box_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="MLCP"),
     "box_hardsoft_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor_hardsoft()], contact_info=ch.contact_info_table(), solver="MLCP"),
     "box_vert_default_ci": lambda: ch.World(chains=[ch.box(), ch.floor()], solver="Vert"),
@@ -281,6 +295,7 @@ def test_rigid_evaluation_matches_oracle(capi, oracle, name):
     w = RIGID_WORLDS[name]()
     B = 256
     q, qd, u = ch.sample_state(w, B, seed=5)
+    q = biped_pose(name, q)
     if "box" in name:
         q[:, 2] = np.linspace(-0.01, 0.08, B)
         q[:, 1] = np.linspace(-0.3, 0.3, B)
@@ -307,6 +322,7 @@ def test_rigid_short_trajectory(capi, oracle, name):
     w = RIGID_WORLDS[name]()
     B, nsteps = 128, 20
     q, qd, u = ch.sample_state(w, B, seed=9)
+    q = biped_pose(name, q)
     if "box" in name:
         q[:, 2] = np.linspace(0.02, 0.08, B)
     fd = gpu_world(capi, w, q, qd, u)

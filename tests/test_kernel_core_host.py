@@ -132,8 +132,22 @@ def test_two_chains_in_one_world(oracle):
         assert relerr(hq[b], ref[b][0][0]) < 1e-9
 
 
+def biped_pose(name, q):
+    """The random trunk pose made a standing one (both soles near the floor)."""
+    if "biped" in name:
+        q[:, 2] = 0.44; q[:, 3:6] *= 0.1; q[:, 6:] *= 0.3
+    return q
+
+
+def biped_rigid(solver):
+    """Contacts on TWO links of one tree (both soles on the rigid floor): the dense warp-cooperative contact solve."""
+    return ch.World(chains=[ch.biped(), ch.floor()],
+                    contact_info=[ch.ContactInfo("ground", "body", "rigid", K=1000.0, L=0.001, SF=0.5, KF=0.3)], solver=solver)
+
+
 RIGID_WORLDS = {
     "c5_arm7_mlcp": lambda: ch.world_c5(base_z=0.1, solver="MLCP"),
+    "biped_two_feet_mlcp": lambda: biped_rigid("MLCP"),
     "box_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="MLCP"),
     "box_hardsoft_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor_hardsoft()], contact_info=ch.contact_info_table(), solver="MLCP"),
     "c5_arm7_vert": lambda: ch.world_c5(base_z=0.1, solver="Vert"),
@@ -155,6 +169,7 @@ def test_rigid_eval_matches_oracle(oracle, name):
     w = RIGID_WORLDS[name]()
     B = 400 if name == "c5_arm7_vert" else 48      # the statistical case needs a sample (8 % of the envs touch the floor)
     q, qd, u = ch.sample_state(w, B, seed=5)
+    q = biped_pose(name, q)
     if "box" in name:
         q[:, 2] = np.linspace(-0.01, 0.08, B)
         q[:, 1] = np.linspace(-0.3, 0.3, B)
@@ -188,6 +203,7 @@ def test_rigid_steps_match_oracle(oracle, name):
     w = RIGID_WORLDS[name]()
     B, nsteps = 8, 10
     q, qd, u = ch.sample_state(w, B, seed=9)
+    q = biped_pose(name, q)
     if "box" in name:
         q[:, 2] = np.linspace(0.02, 0.08, B)
     hs = HostSim(w, B)
