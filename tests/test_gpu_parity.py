@@ -497,3 +497,24 @@ def test_generic_kernel_with_tensor_memory_scratch(capi, monkeypatch, name):
     assert fin.mean() > 0.95
     for x, y in zip(out[0][:2], out[1][:2]):      # two instantiations: the compiler contracts a few products differently
         assert relerr(y[fin], x[fin]) < 1e-11
+
+
+@pytest.mark.parametrize("nlinks,spec", [(3, 8), (7, 9), (8, 10)])
+def test_general_frame_arm_specialisations(capi, oracle, monkeypatch, nlinks, spec):
+    """Random fixed-base serial revolute arms with arbitrary constant frames (2 / 6 / 7 joints, DC motors + joint
+    friction): the rolled general-frame specialisation against the generic kernel and the oracle."""
+    rng = np.random.default_rng(100 + nlinks)
+    w = ch.World(chains=[ch.random_chain(rng, nlinks, jtypes=("revolute",), motors=True)])
+    B = 4096 + 17
+    q = rng.uniform(-1.5, 1.5, (B, w.nq)); qd = rng.uniform(-2, 2, (B, w.nq)); u = rng.uniform(-6, 6, (B, w.nl))
+    out = []
+    for sid in (0, spec):
+        monkeypatch.setenv("RKFD_SPEC", str(sid))
+        fd = gpu_world(capi, w, q, qd, u)
+        fd.update_n(15)
+        out.append(fd.batch_get_state())
+        fd.destroy()
+    assert relerr(out[1][0], out[0][0]) < 1e-11 and relerr(out[1][1], out[0][1]) < 1e-10
+    n = 24
+    oq, oqd, _, _ = oracle.OracleWorld(w).batch_run(q[:n], qd[:n], u[:n], nsteps=15)
+    assert relerr(out[1][0][:n], oq) < 1e-9 and relerr(out[1][1][:n], oqd) < 1e-8
