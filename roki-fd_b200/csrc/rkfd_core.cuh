@@ -66,9 +66,10 @@ constexpr int ACCUM_SLOTS = 27;    /* A(6) B(9) C(6) pf(3) pn(3) */
 constexpr int WEXT_SLOTS = 6;
 constexpr int FRAME_SLOTS = 24;    /* rigid worlds, links with cells: Rw(9) pw(3) vl(3) w(3) a(6) */
 constexpr int GEO_DOUBLES = 27;    /* per rigid contact: vw n t1 t2 d vel prob rl (8 x 3), slot, link, pair */
-/* per-environment workspace of the single-link MLCP path: Lambda (6x6, column-major) then per contact
+/* per-environment workspace of the wrench-coordinate contact paths: Lambda (6x6, column-major) per group, then per contact
  * g (3x6) h (3x6) b (3) diag (3) f (3) rho (3) prob (3) mu slot */
-constexpr int W1_CT = 36, W1_CTN = 53;
+constexpr int MAX_RG = 4;                      /* contact groups (links in different chains) of the wrench-coordinate paths */
+constexpr int W1_CT = 36*MAX_RG, W1_CTN = 53;
 
 enum StageMode : int { ST_K1 = 0, ST_K2 = 1, ST_K3 = 2, ST_K4 = 3, ST_REF = 4, ST_EVAL = 5, ST_EVAL_REF = 6,
                        ST_PROBE = 7 /* acceleration pass of rkFDUpdateAccBias: no integrator bookkeeping, no q'' output */ };
@@ -233,7 +234,7 @@ struct SpecSerialRevRolled {
   static RKFD_HD int sc(int i, const LinkDev &){ return RG_ ? PER*i + 9 : 4*(i-1); }
 };
 inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0, int GEN = 0){
-  if( RG ? !( m.has_rigid && m.rigid_link == NL-1 ) : m.has_rigid ) return false;
+  if( RG ? !( m.has_rigid && m.nrg == 1 && m.rigid_link == NL-1 ) : m.has_rigid ) return false;
   if( m.nl != NL || NL < 2 ) return false;
   for(int i=0;i<NL;i++){
     const LinkDev &L = m.link[i];
@@ -1090,15 +1091,15 @@ struct Core {
     ral = al; raa = aa;
   }
 
-  /* Lambda (6x6, column-major in W1[0..35]) of the contact link of every environment in `act`: lanes over
-   * (environment of the warp with contacts, wrench component) */
+  /* Lambda (6x6, column-major in W1[36 g ..]) of every contact-group link of every environment in `act`: lanes over
+   * (environment of the warp with contacts, group, wrench component) */
   RKFD_HD void lambda_probes(const ModelDev &m, unsigned act){
     const int nlanes = c.lanes(), lane = c.lane();
-    const int Lc = m.rigid_link; const LinkDev &LL = m.link[Lc];
-    const int fsl = Spec::frame_slot(Lc, LL);
-    const int nact = RKFD_POPC64((unsigned long long)act);
-    for(int t=lane; t<6*nact; t+=nlanes){
-      const int j = t/6, comp = t - 6*j;
+    const int nact = RKFD_POPC64((unsigned long long)act), per = 6*m.nrg;
+    for(int t=lane; t<per*nact; t+=nlanes){
+      const int j = t/per, rem = t - per*j, g = rem/6, comp = rem - 6*g;
+      const int Lc = m.rg_link[g]; const LinkDev &LL = m.link[Lc];
+      const int fsl = Spec::frame_slot(Lc, LL);
       unsigned a = act; for(int q=0;q<j;q++) a &= a - 1;
       c.select(RKFD_FFS32(a) - 1);
       const M3 Rw = ldm(fsl);
@@ -1107,31 +1108,37 @@ struct Core {
       const V3 z = v3(0,0,0);
       V3 ral, raa;
       probe_link(m, Lc, comp < 3 ? -el : z, comp < 3 ? z : -el, ral, raa);
-      sw13(6*comp, mul(Rw, ral)); sw13(6*comp+3, mul(Rw, raa));
+      sw13(36*g + 6*comp, mul(Rw, ral)); sw13(36*g + 6*comp+3, mul(Rw, raa));
       c.unselect();
     }
     c.gsync();
   }
 
   RKFD_HD void rigid_mlcp_single(const ModelDev &m, bool ref, unsigned act){
-    const int Lc = m.rigid_link; const LinkDev &LL = m.link[Lc];
-    const int fsl = Spec::frame_slot(Lc, LL), wsl = Spec::wext_slot(Lc, LL);
     lambda_probes(m, act);
-    /* ---- one environment per lane from here on */
+    /* ---- one environment per lane from here on; the groups do not couple: projected Gauss-Seidel per group */
+    if( RKFD_POPC64(cfl & m.rigid_mask) == 0 ) return;
+    unsigned long long nfl = cfl;
+    for(int g=0;g<m.nrg;g++) rigid_mlcp_group(m, ref, g, nfl);
+    cfl = nfl;
+  }
+  RKFD_HD void rigid_mlcp_group(const ModelDev &m, bool ref, int g, unsigned long long &nfl){
+    const int Lc = m.rg_link[g]; const LinkDev &LL = m.link[Lc];
+    const int fsl = Spec::frame_slot(Lc, LL), wsl = Spec::wext_slot(Lc, LL);
     const unsigned long long fl = cfl;
-    const int N = RKFD_POPC64(fl & m.rigid_mask);
-    if( N == 0 ) return;
     double lam[36];
 #pragma unroll
-    for(int i=0;i<36;i++) lam[i] = c.W1(i);            /* lam[6*col + row] */
+    for(int i=0;i<36;i++) lam[i] = c.W1(36*g + i);     /* lam[6*col + row] */
     const M3 Rw = ldm(fsl); const V3 pw = ld3(fsl+9), vl = ld3(fsl+12), om = ld3(fsl+15);
     const V3 al = ld3(fsl+18), aa = ld3(fsl+21);
     const V3 vlw = mul(Rw, vl), omw = mul(Rw, om);
     /* contacts in (pair, vertex) order: geometry, rows h, responses g = Lambda h, bias b (rkfd_mlcp.c:104-188) */
+    int N = 0;
     { int k = 0;
       for(int s=0;s<m.nslot;s++){
         if( !( (fl & m.rigid_mask) >> (2*s) & 1ull ) ) continue;
         const PairDev &pr = m.pair[m.slot_pair[s]]; const CellDev &cl = m.cell[pr.cell]; const BoxDev &bx = m.box[pr.box];
+        if( cl.link != Lc ) continue;
         const int vi = cl.vofs + m.slot_vert[s];
         const V3 rl = v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2]);
         const M3 Rb = box_R(bx); const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
@@ -1167,7 +1174,9 @@ struct Core {
         }
         sw13(o+45, rho); sw13(o+48, prob); c.W1(o+51) = mu; c.W1(o+52) = (double)s;
         k++;
-      } }
+      }
+      N = k; }
+    if( N == 0 ) return;
     /* ---- projected Gauss-Seidel on u = Lambda * (sum of contact wrenches) (rkfd_mlcp.c:190-249) */
     double u[6] = {0,0,0,0,0,0};
     for(int cnt=0;cnt<m.max_iter;cnt++){
@@ -1210,7 +1219,6 @@ struct Core {
     }
     /* ---- f /= dt; forces, wrench on the link, friction state (rkfd_mlcp.c:252-284: committed regardless of
      * doUpRef, world components of f as "normal"/"tangential" - mirrored) */
-    unsigned long long nfl = fl;
     V3 wl = v3(0,0,0), wa = v3(0,0,0);
     for(int k=0;k<N;k++){
       const int o = W1_CT + W1_CTN*k; const int s = (int)c.W1(o+52);
@@ -1226,7 +1234,6 @@ struct Core {
     }
     c.S(wsl) += wl.x; c.S(wsl+1) += wl.y; c.S(wsl+2) += wl.z;
     c.S(wsl+3) += wa.x; c.S(wsl+4) += wa.y; c.S(wsl+5) += wa.z;
-    cfl = nfl;
   }
 
   /* =====================================================================================================
@@ -1278,28 +1285,26 @@ struct Core {
   }
 
   RKFD_HD void rigid_vert_single(const ModelDev &m, bool ref, unsigned act){
-    const int Lc = m.rigid_link; const LinkDev &LL = m.link[Lc];
-    const int fsl = Spec::frame_slot(Lc, LL), wsl = Spec::wext_slot(Lc, LL);
+    /* contact groups (links in different chains) share ONE active-set iteration, as the reference's single QP does:
+     * identical-point test, most negative multiplier, step length and history are global; the KKT solves decouple */
     lambda_probes(m, act);
     const unsigned long long fl = cfl;
     const int N = RKFD_POPC64(fl & m.rigid_mask);
     if( N == 0 ) return;
     const int pyr = m.pyramid, QP_HIST = 32, QP_MAXIT = 256;
     const int nrs = m.nmax/3, ohist = W1_CT + W1_CTN*nrs;
-    double lam[36];
-    for(int i=0;i<36;i++) lam[i] = c.W1(i);            /* lam[6*col + row] */
-    const M3 Rw = ldm(fsl); const V3 pw = ld3(fsl+9), vl = ld3(fsl+12), om = ld3(fsl+15);
-    const V3 al = ld3(fsl+18), aa = ld3(fsl+21);
-    const V3 vlw = mul(Rw, vl), omw = mul(Rw, om);
+    const int ng = m.nrg;
     /* contacts in (pair, vertex) order: rows h, compensated velocity-level bias c0 (rkfd_vert.c:107-123, 189-232);
      * per contact in W1: x (0..2) x* (3..5) h (18..35) c0 (36..38) fric (39) L (40) rho (45..47) prob (48..50) mu slot */
-    double G[36], hc[6];
-    for(int i=0;i<36;i++) G[i] = 0.0;
-    for(int i=0;i<6;i++) hc[i] = 0.0;
     { int k = 0;
       for(int s=0;s<m.nslot;s++){
         if( !( (fl & m.rigid_mask) >> (2*s) & 1ull ) ) continue;
         const PairDev &pr = m.pair[m.slot_pair[s]]; const CellDev &cl = m.cell[pr.cell]; const BoxDev &bx = m.box[pr.box];
+        int g = 0; while( g < ng-1 && m.rg_link[g] != cl.link ) g++;
+        const int fsl = Spec::frame_slot(cl.link, m.link[cl.link]);
+        const M3 Rw = ldm(fsl); const V3 pw = ld3(fsl+9), vl = ld3(fsl+12), om = ld3(fsl+15);
+        const V3 al = ld3(fsl+18), aa = ld3(fsl+21);
+        const V3 vlw = mul(Rw, vl), omw = mul(Rw, om);
         const int vi = cl.vofs + m.slot_vert[s];
         const V3 rl = v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2]);
         const M3 Rb = box_R(bx); const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
@@ -1319,20 +1324,29 @@ struct Core {
           const V3 hl = ax[i], ha = cross(rho, ax[i]);
           const double h[6] = {hl.x, hl.y, hl.z, ha.x, ha.y, ha.z};
           const double c0 = dot(ax[i], accp)*m.dt + dot(vel, ax[i]) + pr.K * ( i == 0 ? 1.0 : mu ) * dot(d, ax[i]);
-          for(int rr=0;rr<6;rr++){ c.W1(o+18+6*i+rr) = h[rr]; hc[rr] += h[rr]*c0; for(int cc=0;cc<6;cc++) G[6*rr+cc] += h[rr]*h[cc]; }
+          for(int rr=0;rr<6;rr++) c.W1(o+18+6*i+rr) = h[rr];
           c.W1(o+36+i) = c0;
           c.W1(o+i) = i == 0 ? 1.0 : 0.0;            /* initial point f_n = 1 per vertex (rkfd_vert.c:234-244) */
         }
-        c.W1(o+39) = mu*m.sc_cos[0]; c.W1(o+40) = pr.L;
+        c.W1(o+39) = mu*m.sc_cos[0]; c.W1(o+40) = pr.L; c.W1(o+41) = (double)g;
         sw13(o+45, rho); sw13(o+48, prob); c.W1(o+51) = mu; c.W1(o+52) = (double)s;
         k++;
       } }
-    /* M = Lambda^T G Lambda, w = Lambda^T hc   (Lambda[r][c] = lam[6c + r]) */
-    double M[36], w[6];
-    { double T[36];
+    /* per group: M = Lambda^T G Lambda (row-major, written over Lambda in W1), w = Lambda^T hc   (Lambda[r][c] = lam[6c + r]) */
+    double w[MAX_RG][6], u[MAX_RG][6];
+    for(int g=0;g<ng;g++){
+      double lam[36], G[36], hc[6], T[36];
+      for(int i=0;i<36;i++){ lam[i] = c.W1(36*g + i); G[i] = 0.0; }
+      for(int i=0;i<6;i++) hc[i] = 0.0;
+      for(int k=0;k<N;k++){
+        const int o = W1_CT + W1_CTN*k; if( (int)c.W1(o+41) != g ) continue;
+        for(int i=0;i<3;i++){ const double c0 = c.W1(o+36+i);
+          for(int rr=0;rr<6;rr++){ const double hr = c.W1(o+18+6*i+rr); hc[rr] += hr*c0; for(int cc=0;cc<6;cc++) G[6*rr+cc] += hr*c.W1(o+18+6*i+cc); } }
+      }
       for(int r=0;r<6;r++) for(int cc=0;cc<6;cc++){ double sum = 0; for(int j=0;j<6;j++) sum += G[6*r+j]*lam[6*cc+j]; T[6*r+cc] = sum; }      /* G Lambda */
-      for(int r=0;r<6;r++) for(int cc=0;cc<6;cc++){ double sum = 0; for(int j=0;j<6;j++) sum += lam[6*r+j]*T[6*j+cc]; M[6*r+cc] = sum; }       /* Lambda^T (G Lambda) */
-      for(int r=0;r<6;r++){ double sum = 0; for(int j=0;j<6;j++) sum += lam[6*r+j]*hc[j]; w[r] = sum; } }
+      for(int r=0;r<6;r++) for(int cc=0;cc<6;cc++){ double sum = 0; for(int j=0;j<6;j++) sum += lam[6*r+j]*T[6*j+cc]; c.W1(36*g + 6*r+cc) = sum; }   /* Lambda^T (G Lambda) */
+      for(int r=0;r<6;r++){ double sum = 0; for(int j=0;j<6;j++) sum += lam[6*r+j]*hc[j]; w[g][r] = sum; }
+    }
     /* initial active set (rkfd_opt_qp.c:27-40) */
     unsigned am[MAX_SLOTS];
     for(int k=0;k<N;k++){
@@ -1342,11 +1356,14 @@ struct Core {
     }
     int nhist = 0;
     for(int iter=0; iter<QP_MAXIT; iter++){
-      /* ---- x* of the equality-constrained problem */
-      double P[36];
-      for(int i=0;i<36;i++) P[i] = 0.0;
+      /* ---- x* of the equality-constrained problem, group by group */
+      bool singular = false;
+      for(int g=0;g<ng;g++){
+      double P[36], M[36];
+      for(int i=0;i<36;i++){ P[i] = 0.0; M[i] = c.W1(36*g + i); }
       for(int k=0;k<N;k++){
         const int o = W1_CT + W1_CTN*k; double pi[9];
+        if( (int)c.W1(o+41) != g ) continue;
         pyramid_projector(m, am[k], c.W1(o+39), pi);
         const double il = 1.0/c.W1(o+40);
         for(int a=0;a<3;a++) for(int b=0;b<3;b++){
@@ -1354,17 +1371,19 @@ struct Core {
           for(int rr=0;rr<6;rr++){ const double ha = c.W1(o+18+6*a+rr)*pab; for(int cc=0;cc<6;cc++) P[6*rr+cc] += ha*c.W1(o+18+6*b+cc); }
         }
       }
-      double K6[36], v[6], u[6];
-      for(int r=0;r<6;r++){ double sum = 0; for(int cc=0;cc<6;cc++){ double pm = 0; for(int j=0;j<6;j++) pm += P[6*r+j]*M[6*j+cc]; K6[6*r+cc] = pm + (r == cc ? 1.0 : 0.0); sum += P[6*r+cc]*w[cc]; } v[r] = -sum; }
-      if( !solve6(K6, v) ){ bad |= 2; break; }
-      for(int r=0;r<6;r++){ double sum = w[r]; for(int j=0;j<6;j++) sum += M[6*r+j]*v[j]; u[r] = sum; }
+      double K6[36], v[6];
+      for(int r=0;r<6;r++){ double sum = 0; for(int cc=0;cc<6;cc++){ double pm = 0; for(int j=0;j<6;j++) pm += P[6*r+j]*M[6*j+cc]; K6[6*r+cc] = pm + (r == cc ? 1.0 : 0.0); sum += P[6*r+cc]*w[g][cc]; } v[r] = -sum; }
+      if( !solve6(K6, v) ){ singular = true; break; }
+      for(int r=0;r<6;r++){ double sum = w[g][r]; for(int j=0;j<6;j++) sum += M[6*r+j]*v[j]; u[g][r] = sum; }
+      }
+      if( singular ){ bad |= 2; break; }
       bool same = true, neg = false; double lmin = 0; bool first = true;
       for(int k=0;k<N;k++){
-        const int o = W1_CT + W1_CTN*k; double pi[9];
+        const int o = W1_CT + W1_CTN*k; double pi[9]; const int gk = (int)c.W1(o+41);
         pyramid_projector(m, am[k], c.W1(o+39), pi);
         const double il = 1.0/c.W1(o+40);
         double hu[3];
-        for(int a=0;a<3;a++){ double sum = 0; for(int rr=0;rr<6;rr++) sum += c.W1(o+18+6*a+rr)*u[rr]; hu[a] = sum; }
+        for(int a=0;a<3;a++){ double sum = 0; for(int rr=0;rr<6;rr++) sum += c.W1(o+18+6*a+rr)*u[gk][rr]; hu[a] = sum; }
         for(int a=0;a<3;a++){
           const double xs = -il*(pi[3*a]*hu[0] + pi[3*a+1]*hu[1] + pi[3*a+2]*hu[2]);
           c.W1(o+3+a) = xs;
@@ -1379,7 +1398,8 @@ struct Core {
           if( na == 0 ) continue;
           const double fric = c.W1(o+39), Lk = c.W1(o+40);
           V3 r;
-          { double hu[3]; for(int ax=0;ax<3;ax++){ double sum = 0; for(int rr=0;rr<6;rr++) sum += c.W1(o+18+6*ax+rr)*u[rr]; hu[ax] = sum; }
+          { const int gk = (int)c.W1(o+41);
+            double hu[3]; for(int ax=0;ax<3;ax++){ double sum = 0; for(int rr=0;rr<6;rr++) sum += c.W1(o+18+6*ax+rr)*u[gk][rr]; hu[ax] = sum; }
             r = v3(Lk*c.W1(o+3) + hu[0], Lk*c.W1(o+4) + hu[1], Lk*c.W1(o+5) + hu[2]); }
           if( na == 1 ){
             const int i0 = RKFD_FFS32(a) - 1; const V3 a0 = v3(fric, m.sc_sin[i0], m.sc_cos[i0]);
@@ -1420,9 +1440,10 @@ struct Core {
           if( ad < 0 ){ const double cond = fric*x.x + m.sc_sin[i]*x.y + m.sc_cos[i]*x.z; const double t2 = (0.0 - cond)/ad; if( t2 < alpha ) alpha = t2; }
         }
       }
-      double vv[6] = {0,0,0,0,0,0}, lx2 = 0;
+      double vv[MAX_RG][6], lx2 = 0;
+      for(int g=0;g<ng;g++) for(int r=0;r<6;r++) vv[g][r] = 0.0;
       for(int k=0;k<N;k++){
-        const int o = W1_CT + W1_CTN*k; const double fric = c.W1(o+39);
+        const int o = W1_CT + W1_CTN*k; const double fric = c.W1(o+39); const int gk = (int)c.W1(o+41);
         V3 x = w13(o); const V3 xs = w13(o+3);
         x = v3(x.x + alpha*(xs.x - x.x), x.y + alpha*(xs.y - x.y), x.z + alpha*(xs.z - x.z));
         sw13(o, x);
@@ -1432,11 +1453,11 @@ struct Core {
           if( fabs(cond) < ZTOL ) am[k] |= 1u << i;
         }
         lx2 += c.W1(o+40)*dot(x,x);
-        for(int rr=0;rr<6;rr++) vv[rr] += c.W1(o+18+rr)*x.x + c.W1(o+24+rr)*x.y + c.W1(o+30+rr)*x.z;
+        for(int rr=0;rr<6;rr++) vv[gk][rr] += c.W1(o+18+rr)*x.x + c.W1(o+24+rr)*x.y + c.W1(o+30+rr)*x.z;
       }
       /* anti-cycling: same active set with the same objective value -> stop (rkfd_opt_qp.c:152-171) */
       double objv = 0.5*lx2;
-      for(int r=0;r<6;r++){ double sum = 0; for(int j=0;j<6;j++) sum += M[6*r+j]*vv[j]; objv += 0.5*vv[r]*sum + w[r]*vv[r]; }
+      for(int g=0;g<ng;g++) for(int r=0;r<6;r++){ double sum = 0; for(int j=0;j<6;j++) sum += c.W1(36*g + 6*r+j)*vv[g][j]; objv += 0.5*vv[g][r]*sum + w[g][r]*vv[g][r]; }
       bool endflag = false;
       for(int h=0;h<nhist && !endflag;h++){
         bool eq = true;
@@ -1452,9 +1473,14 @@ struct Core {
     }
     /* f = x / dt ; forces, wrench, friction state from the final active set (rkfd_vert.c:282, 286-324) */
     unsigned long long nfl = fl;
+    for(int g=0;g<ng;g++){
+    const int Lc = m.rg_link[g]; const LinkDev &LL = m.link[Lc];
+    const int fsl = Spec::frame_slot(Lc, LL), wsl = Spec::wext_slot(Lc, LL);
+    const M3 Rw = ldm(fsl);
     V3 wl = v3(0,0,0), wa = v3(0,0,0);
     for(int k=0;k<N;k++){
       const int o = W1_CT + W1_CTN*k; const int s = (int)c.W1(o+52);
+      if( (int)c.W1(o+41) != g ) continue;
       const V3 fw = (c.W1(o)/m.dt)*w13(o+18) + (c.W1(o+1)/m.dt)*w13(o+24) + (c.W1(o+2)/m.dt)*w13(o+30);
       const bool flag = am[k] != 0;
       if( ref ){
@@ -1467,6 +1493,7 @@ struct Core {
     }
     c.S(wsl) += wl.x; c.S(wsl+1) += wl.y; c.S(wsl+2) += wl.z;
     c.S(wsl+3) += wa.x; c.S(wsl+4) += wa.y; c.S(wsl+5) += wa.z;
+    }
     cfl = nfl;
   }
 

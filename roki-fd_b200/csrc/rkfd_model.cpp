@@ -171,13 +171,26 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   m.nmax = 3*nrs; m.ws_doubles = 0;
   /* single-link MLCP path (Core::rigid_mlcp_single): every rigid slot on one link */
   m.rigid_link = -1; m.ws1_doubles = 0;
+  m.nrg = 0;
   if( m.has_rigid ){
-    int lk = -2;
-    for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID ){ const int l = m.cell[m.pair[p].cell].link; lk = ( lk == -2 || lk == l ) ? l : -1; }
+    /* contact groups: links with rigid cells, at most MAX_RG of them, pairwise in different chains */
+    int lk = -2; bool ok = true;
+    for(int p=0;p<m.npair && ok;p++) if( m.pair[p].type == C_RIGID ){
+      const int l = m.cell[m.pair[p].cell].link; bool seen = false;
+      for(int g=0;g<m.nrg;g++) if( m.rg_link[g] == l ) seen = true;
+      if( seen ) continue;
+      if( m.nrg >= MAX_RG ){ ok = false; break; }
+      int root = l; while( m.link[root].parent >= 0 ) root = m.link[root].parent;
+      for(int g=0;g<m.nrg;g++){ int r2 = m.rg_link[g]; while( m.link[r2].parent >= 0 ) r2 = m.link[r2].parent; if( r2 == root ) ok = false; }
+      m.rg_link[m.nrg++] = l;
+    }
+    lk = ( ok && m.nrg > 0 ) ? m.rg_link[0] : -1;
+    if( !ok ) m.nrg = 0;
     bool lpos = true;           /* the Vert path divides by the relaxation of every rigid pair */
     for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID && !(m.pair[p].L > 0.0) ) lpos = false;
     if( lk >= 0 && m.solver == S_MLCP ){ m.rigid_link = lk; m.ws1_doubles = W1_CT + W1_CTN*nrs; }
     if( lk >= 0 && m.solver == S_VERT && lpos && m.pyramid <= 12 ){ m.rigid_link = lk; m.ws1_doubles = W1_CT + W1_CTN*nrs + 32*(nrs+1); }
+    if( m.rigid_link < 0 ) m.nrg = 0;
   }
   if( m.has_rigid ){
     const int n = m.nmax, mc = m.pyramid*nrs, nm = n + mc; int o = 0;

@@ -78,7 +78,9 @@ struct ModelDev {
   int ws_doubles;      /* per-warp workspace (doubles) of the rigid-contact solve, 0 when no rigid pair */
   int ws_geo, ws_b, ws_f, ws_A, ws_du, ws_da, ws_qp;   /* offsets inside the workspace */
   int nmax;            /* 3 * (rigid contact slots) */
-  int rigid_link;      /* link that carries EVERY rigid contact slot, -1 when they sit on several links */
+  int rigid_link;      /* >= 0: the wrench-coordinate contact paths apply (= rg_link[0]); -1: the dense path */
+  int nrg, rg_link[4]; /* contact groups of those paths: the links that carry rigid cells, each in a different chain (no dynamic
+                          coupling between groups: the reference zeroes those blocks of A, rkfd_vert.c:133-137) */
   int ws1_doubles;     /* per-ENVIRONMENT workspace (doubles) of the single-link MLCP path, 0 when unused */
   unsigned long long rigid_mask;   /* bit 2s set when slot s belongs to a rigid pair */
   int slot_pair[MAX_SLOTS], slot_vert[MAX_SLOTS];

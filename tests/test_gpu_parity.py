@@ -246,6 +246,9 @@ RIGID_WORLDS = {
     "box_hardsoft_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor_hardsoft()], contact_info=ch.contact_info_table(), solver="MLCP"),
     "box_vert_default_ci": lambda: ch.World(chains=[ch.box(), ch.floor()], solver="Vert"),
     "arm7_vert_default_ci": lambda: ch.World(chains=[ch.arm7(base_z=0.1, contact_cube=True), ch.floor()], solver="Vert"),
+    # two free bodies on the floor: contact links in different chains -> two groups of the wrench-coordinate paths
+    "two_box_mlcp": lambda: ch.World(chains=[ch.box("a"), ch.box("b"), ch.floor()], contact_info=ch.contact_info_table(), solver="MLCP"),
+    "two_box_vert_default_ci": lambda: ch.World(chains=[ch.box("a"), ch.box("b"), ch.floor()], solver="Vert"),
 }
 
 # Vert with relaxation L = 1e-4 (contactinfo.ztk): QP Hessian cond ~ 1e5 and 1e-12 decision thresholds in the
@@ -299,6 +302,8 @@ def test_rigid_evaluation_matches_oracle(capi, oracle, name):
     if "box" in name:
         q[:, 2] = np.linspace(-0.01, 0.08, B)
         q[:, 1] = np.linspace(-0.3, 0.3, B)
+    if "two_box" in name:
+        q[:, 8] = np.linspace(0.07, -0.01, B); q[:, 6] += 2.0
     fd = gpu_world(capi, w, q, qd, u)
     _, _, gqdd = fd.batch_get_state()
     a, t, r, f = fd.batch_get_contact()
@@ -325,6 +330,8 @@ def test_rigid_short_trajectory(capi, oracle, name):
     q = biped_pose(name, q)
     if "box" in name:
         q[:, 2] = np.linspace(0.02, 0.08, B)
+    if "two_box" in name:
+        q[:, 8] = np.linspace(0.07, 0.03, B); q[:, 6] += 2.0
     fd = gpu_world(capi, w, q, qd, u)
     fd.update_n(nsteps)
     gq, gqd, _ = fd.batch_get_state()

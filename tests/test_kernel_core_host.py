@@ -153,6 +153,9 @@ RIGID_WORLDS = {
     "c5_arm7_vert": lambda: ch.world_c5(base_z=0.1, solver="Vert"),
     "box_vert": lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="Vert"),
     "box_vert_default_ci": lambda: ch.World(chains=[ch.box(), ch.floor()], solver="Vert"),
+    # two free bodies on the floor: contact links in different chains -> two groups of the wrench-coordinate paths
+    "two_box_mlcp": lambda: ch.World(chains=[ch.box("a"), ch.box("b"), ch.floor()], contact_info=ch.contact_info_table(), solver="MLCP"),
+    "two_box_vert_default_ci": lambda: ch.World(chains=[ch.box("a"), ch.box("b"), ch.floor()], solver="Vert"),
 }
 
 
@@ -173,6 +176,8 @@ def test_rigid_eval_matches_oracle(oracle, name):
     if "box" in name:
         q[:, 2] = np.linspace(-0.01, 0.08, B)
         q[:, 1] = np.linspace(-0.3, 0.3, B)
+    if "two_box" in name:
+        q[:, 8] = np.linspace(0.07, -0.01, B); q[:, 6] += 2.0
     hs = HostSim(w, B)
     hs.set_state(q, qd, u)
     hs.eval(ref=True)
@@ -206,6 +211,8 @@ def test_rigid_steps_match_oracle(oracle, name):
     q = biped_pose(name, q)
     if "box" in name:
         q[:, 2] = np.linspace(0.02, 0.08, B)
+    if "two_box" in name:
+        q[:, 8] = np.linspace(0.07, 0.03, B); q[:, 6] += 2.0
     hs = HostSim(w, B)
     hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(nsteps)
     hq, hqd, _ = hs.get_state()
