@@ -70,6 +70,9 @@ def lib():
         L.ork_batch_run.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp]
         L.ork_qp_solve_asm.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip]
         L.ork_le_solve_mp_sym.argtypes = [C.c_int, _dp, _dp, _dp]
+        L.ork_env_get_volume.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
+        L.ork_world_npair.argtypes = [C.c_void_p]
+        L.ork_lp_solve.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         _LIB = L
     return _LIB
 
@@ -246,6 +249,28 @@ class OracleEnv:
         n = lib().ork_env_get_rigid_system(self.h, A.ctypes.data_as(_dp), b.ctypes.data_as(_dp),
                                            f.ctypes.data_as(_dp), cap)
         return A.reshape(-1)[:n * n].reshape(n, n), b[:n], f[:n]
+
+    def volume(self):
+        """Volume solver results of the last evaluation per pair: (np, type, wrench[6], center[3]); np = -1: no contact volume."""
+        n = max(lib().ork_world_npair(self.w.h), 1)
+        npl, ty = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        wr, ce = np.zeros((n, 6)), np.zeros((n, 3))
+        lib().ork_env_get_volume(self.h, npl.ctypes.data_as(_ip), ty.ctypes.data_as(_ip), wr.ctypes.data_as(_dp), ce.ctypes.data_as(_dp))
+        return npl, ty, wr, ce
+
+
+def lp_solve(A, b, c=None):
+    """min c^T x s.t. A x = b, x >= 0 (c None: feasibility).  Returns (ok, x)."""
+    b, pb = _d(b)
+    m = b.shape[0]
+    A, pA = _d(np.asarray(A, float).reshape(m, -1))
+    n = A.shape[1]
+    pc = None
+    if c is not None:
+        c, pc = _d(c)
+    x = np.zeros(n)
+    ok = lib().ork_lp_solve(m, n, pA, pb, pc, x.ctypes.data_as(_dp))
+    return bool(ok), x
 
 
 def qp_solve_asm(Q, c, A, b, init=None):

@@ -148,6 +148,8 @@ struct ork_env {
   ork_lw *lw;
   /* rigid system of the last evaluation */
   int rn; double *rA, *rb, *rf;
+  /* Volume solver, per pair: friction type (rkCDPairDat.type), planes of the last evaluation (-1: no volume), wrench, center */
+  int *v_type, *v_np; double *v_wrench, *v_center;
   /* RKG workspace */
   double *k[4][2], *xs[2];
 };
@@ -244,7 +246,7 @@ void ork_world_set_solver(ork_world *w, int solver)
   w->solver = solver;
   /* default contact info: rkfd_vert.c:340-348, rkfd_mlcp.c:301-310, rkfd_volume.c:961-969 */
   w->cidef.type = ORK_CONTACT_RIGID;
-  w->cidef.K = 1000.0; w->cidef.L = 1.0; w->cidef.SF = 0.5; w->cidef.KF = 0.3;
+  w->cidef.K = 1000.0; w->cidef.L = solver == ORK_SOLVER_VOLUME ? 0.001 : 1.0; w->cidef.SF = 0.5; w->cidef.KF = 0.3;
   w->cidef.E = 0.0; w->cidef.V = 0.0;
 }
 void ork_world_finalize(ork_world *w)
@@ -284,6 +286,8 @@ ork_env *ork_env_new(const ork_world *w)
   e->c_refw=(double*)calloc(3*ns,8); e->c_vel=(double*)calloc(3*ns,8);
   e->lw=(ork_lw*)calloc(w->nl,sizeof(ork_lw));
   e->rn=0; e->rA=(double*)calloc(9*ns*ns,8); e->rb=(double*)calloc(3*ns,8); e->rf=(double*)calloc(3*ns,8);
+  { int np = w->npair>0?w->npair:1; e->v_type=(int*)calloc(np,sizeof(int)); e->v_np=(int*)calloc(np,sizeof(int));
+    e->v_wrench=(double*)calloc(6*np,8); e->v_center=(double*)calloc(3*np,8); }
   for(i=0;i<4;i++) for(j=0;j<2;j++) e->k[i][j]=(double*)calloc(nq,8);
   e->xs[0]=(double*)calloc(nq,8); e->xs[1]=(double*)calloc(nq,8);
   return e;
@@ -296,6 +300,7 @@ void ork_env_free(ork_env *e)
   free(e->c_active); free(e->c_type); free(e->c_ref); free(e->c_f); free(e->c_pro);
   free(e->c_norm); free(e->c_axis); free(e->c_vert); free(e->c_refw); free(e->c_vel);
   free(e->lw); free(e->rA); free(e->rb); free(e->rf);
+  free(e->v_type); free(e->v_np); free(e->v_wrench); free(e->v_center);
   for(i=0;i<4;i++) for(j=0;j<2;j++) free(e->k[i][j]);
   free(e->xs[0]); free(e->xs[1]); free(e);
 }
@@ -872,6 +877,456 @@ static void solver_rigid(ork_env *e, int do_up_ref)
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Volume solver (rkfd_volume.c).  [EXT A-15] rkCDColVolBREPVert (RoKi, absent) is restricted to
+ * (moving cell with the 8 corners of a parallelepiped, vertex k = sign bits x:k&1 y:k&2 z:k&4) x
+ * (ONE face half-space of a static box, the face of the first vertex found inside):
+ *   colvol = cell polyhedron clipped by that half-space (triangulated: every clipped triangle as a fan,
+ *            the cut polygon as a fan over its angularly sorted corners),
+ *   norm   = outward normal of that face, axis[] = the face frame of the vertex test (A-10),
+ *   center = barycentre of colvol.
+ * Every integral of rkfd_volume.c:397-491 is a midpoint rule on polynomials of degree <= 2, i.e.
+ * independent of how the faces are triangulated. */
+#define VOL_MAXTRI 96
+#define VOL_MAXPL 48
+typedef struct { double v[3], norm[3], r[2], s[2]; } ork_vplane;
+typedef struct {
+  int pair, link; const ork_cinfo *ci;
+  double center[3], norm[3], axis[9];
+  int ntri; double tri[VOL_MAXTRI][9], tn[VOL_MAXTRI][3];
+  int npl; ork_vplane pl[VOL_MAXPL];      /* in zListForEach order (tail first) */
+  double wrench[6];
+} ork_vpair;
+
+static const int ork_box_quads[6][4] = { {1,3,7,5}, {0,4,6,2}, {2,6,7,3}, {0,1,5,4}, {4,5,7,6}, {0,2,3,1} };
+
+static void vol_emit(ork_vpair *vp, const double *a, const double *b, const double *c, const double *n)
+{
+  double e1[3], e2[3], cr[3]; double *t;
+  if( vp->ntri >= VOL_MAXTRI ) return;
+  t = vp->tri[vp->ntri];
+  v3_sub(b,a,e1); v3_sub(c,a,e2); v3_cross(e1,e2,cr);
+  v3_copy(a,t);
+  if( v3_dot(cr,n) >= 0 ){ v3_copy(b,t+3); v3_copy(c,t+6); } else { v3_copy(c,t+3); v3_copy(b,t+6); }
+  v3_copy(n,vp->tn[vp->ntri]);
+  vp->ntri++;
+}
+
+/* colvol, center of one colliding pair; returns 0 when the clipped volume is empty */
+static int vol_build(ork_env *e, int pi, ork_vpair *vp)
+{
+  const ork_world *w = e->w; const ork_pair *p = &w->pair[pi]; const ork_cell *cl = &w->cell[p->cell];
+  const ork_box *bx = &w->box[p->box]; const ork_lw *x = &e->lw[cl->link];
+  double vw[8][3], cen[3] = {0,0,0}, p0[3], d[8], cut[64][3], vol = 0, bc[3] = {0,0,0}; int ncut = 0, k, s0 = -1, f, i, j;
+  if( cl->nvert != 8 ) return 0;
+  for(k=0;k<8;k++) if( e->c_active[p->sofs+k] ){ s0 = p->sofs+k; break; }
+  if( s0 < 0 ) return 0;
+  vp->pair = pi; vp->link = cl->link; vp->ci = &p->ci; vp->ntri = 0; vp->npl = 0;
+  v3_copy(e->c_norm+3*s0,vp->norm); memcpy(vp->axis,e->c_axis+9*s0,9*sizeof(double));
+  m3_mulv(bx->R,e->c_pro+3*s0,p0); v3_add(p0,bx->p,p0);          /* a point of the face plane */
+  for(k=0;k<8;k++){ m3_mulv(x->Rw,w->vert+3*(cl->vofs+k),vw[k]); v3_add(vw[k],x->pw,vw[k]); v3_cat(cen,0.125,vw[k]);
+    { double t[3]; v3_sub(vw[k],p0,t); d[k] = v3_dot(vp->norm,t); if( fabs(d[k]) <= ORK_TOL ) d[k] = 0.0; } }
+  for(f=0;f<6;f++){
+    const int *qd = ork_box_quads[f]; double e1[3], e2[3], fn[3], t[3], nn; int tr;
+    v3_sub(vw[qd[1]],vw[qd[0]],e1); v3_sub(vw[qd[3]],vw[qd[0]],e2); v3_cross(e1,e2,fn);
+    nn = v3_norm(fn); if( nn == 0 ) continue;
+    fn[0]/=nn; fn[1]/=nn; fn[2]/=nn;
+    v3_sub(vw[qd[0]],cen,t); if( v3_dot(fn,t) < 0 ){ fn[0]=-fn[0]; fn[1]=-fn[1]; fn[2]=-fn[2]; }
+    for(tr=0;tr<2;tr++){
+      int id[3] = { qd[0], qd[1+tr], qd[2+tr] }; double poly[4][3]; int np = 0;
+      /* Sutherland-Hodgman against d <= 0 */
+      for(i=0;i<3;i++){
+        int a = id[i], b = id[(i+1)%3];
+        if( d[a] <= 0 ){ v3_copy(vw[a],poly[np++]); if( d[a] == 0 && ncut < 64 ) v3_copy(vw[a],cut[ncut++]); }
+        if( (d[a] < 0 && d[b] > 0) || (d[a] > 0 && d[b] < 0) ){
+          double tt = d[a]/(d[a]-d[b]);
+          for(j=0;j<3;j++) poly[np][j] = vw[a][j] + tt*(vw[b][j]-vw[a][j]);
+          if( ncut < 64 ) v3_copy(poly[np],cut[ncut++]);
+          np++;
+        }
+      }
+      for(i=1;i+1<np;i++) vol_emit(vp,poly[0],poly[i],poly[i+1],fn);
+    }
+  }
+  /* the cut polygon: distinct cut points sorted by angle about their mean in the face frame */
+  { double u[64][3]; double ang[64], m[3] = {0,0,0}; int nu = 0;
+    for(i=0;i<ncut;i++){ int dup = 0;
+      for(j=0;j<nu;j++){ double t[3]; v3_sub(cut[i],u[j],t); if( v3_norm(t) < 1.0e-10 ){ dup = 1; break; } }
+      if( !dup ) v3_copy(cut[i],u[nu++]); }
+    if( nu >= 3 ){
+      for(i=0;i<nu;i++) v3_cat(m,1.0/nu,u[i]);
+      for(i=0;i<nu;i++){ double t[3]; v3_sub(u[i],m,t); ang[i] = atan2(v3_dot(t,vp->axis+6),v3_dot(t,vp->axis+3)); }
+      for(i=1;i<nu;i++){ double a = ang[i], t[3]; v3_copy(u[i],t);
+        for(j=i-1;j>=0 && ang[j] > a;j--){ ang[j+1] = ang[j]; v3_copy(u[j],u[j+1]); }
+        ang[j+1] = a; v3_copy(t,u[j+1]); }
+      for(i=1;i+1<nu;i++) vol_emit(vp,u[0],u[i],u[i+1],vp->norm);
+    } }
+  /* barycentre (signed tetrahedra about the cell centre; triangles are outward oriented) */
+  for(i=0;i<vp->ntri;i++){ double a[3], b[3], c[3], cr[3], v6;
+    v3_sub(vp->tri[i],cen,a); v3_sub(vp->tri[i]+3,cen,b); v3_sub(vp->tri[i]+6,cen,c);
+    v3_cross(b,c,cr); v6 = v3_dot(a,cr)/6.0; vol += v6;
+    for(j=0;j<3;j++) bc[j] += v6*0.25*(a[j]+b[j]+c[j]); }
+  if( !(vol > 1.0e-18) ) return 0;
+  for(j=0;j<3;j++) vp->center[j] = cen[j] + bc[j]/vol;
+  return 1;
+}
+
+/* _rkFDSolverSetContactPlane (rkfd_volume.c:350-374) */
+static void vol_set_plane(ork_vpair *vp, const double *p, const double *fnorm)
+{
+  double tmpv[3], nn, cand_n[3], t[3]; int i;
+  v3_copy(fnorm,tmpv); v3_cat(tmpv,-v3_dot(fnorm,vp->norm),vp->norm);
+  if( fabs(tmpv[0]) < ORK_TOL && fabs(tmpv[1]) < ORK_TOL && fabs(tmpv[2]) < ORK_TOL ) return;   /* zVec3DIsTiny */
+  nn = -v3_norm(tmpv); cand_n[0]=tmpv[0]/nn; cand_n[1]=tmpv[1]/nn; cand_n[2]=tmpv[2]/nn;
+  for(i=0;i<vp->npl;i++){ ork_vplane *q = &vp->pl[i];
+    v3_sub(cand_n,q->norm,t);
+    if( fabs(t[0]) < 1e-8 && fabs(t[1]) < 1e-8 && fabs(t[2]) < 1e-8 ){
+      v3_sub(q->v,p,t);
+      if( fabs(v3_dot(cand_n,t)) < 1e-8 ){
+        double cr[3]; v3_cross(cand_n,t,cr);
+        if( v3_dot(vp->norm,cr) > 0.0 ) v3_copy(p,q->v);
+        return; } } }
+  if( vp->npl >= VOL_MAXPL ) return;
+  v3_copy(p,vp->pl[vp->npl].v); v3_copy(cand_n,vp->pl[vp->npl].norm); vp->npl++;   /* zListInsertHead: last in zListForEach order */
+}
+
+static void vol_cc(const double *pm_in, const double *h, double K, double s, const double *norm, double *cc)
+{ /* _rkFDSolverConstraintMidDepth + _rkFDSolverConstraintDepth (rkfd_volume.c:232-241, 296-310) */
+  double k = K*s/6.0, hm[3], hc, t[3], pmh[3]; int i, j;
+  hm[0] = k*(h[0]+h[1]); hm[1] = k*(h[1]+h[2]); hm[2] = k*(h[0]+h[2]); hc = k*(h[0]+h[1]+h[2])*2;
+  for(j=0;j<3;j++){ cc[j] = -hc*norm[j]; cc[3+j] = 0; }
+  for(i=0;i<3;i++){ for(j=0;j<3;j++) pmh[j] = pm_in[3*i+j]*hm[i]; v3_cross(norm,pmh,t); v3_add(cc+3,t,cc+3); }
+}
+static double vol_area(const double *p)
+{ double e1[3], e2[3], cr[3]; v3_sub(p+3,p,e1); v3_sub(p+6,p,e2); v3_cross(e1,e2,cr); return 0.5*v3_norm(cr); }
+static void vol_mid(const double *p, double *pm)
+{ int j; for(j=0;j<3;j++){ pm[j] = 0.5*(p[j]+p[3+j]); pm[3+j] = 0.5*(p[3+j]+p[6+j]); pm[6+j] = 0.5*(p[6+j]+p[j]); } }
+/* _rkFDSolverConstraintInnerPoint (rkfd_volume.c:331-348) */
+static void vol_inner(const double *p1, const double *p2, double h1, double h2, double *pp)
+{ int j;
+  if( fabs(h1) < ORK_TOL ){ v3_copy(p1,pp); return; }
+  if( fabs(h2) < ORK_TOL ){ v3_copy(p2,pp); return; }
+  if( fabs(h2-h1) < ORK_TOL ){ for(j=0;j<3;j++) pp[j] = 0.5*(p1[j]+p2[j]); return; }
+  for(j=0;j<3;j++) pp[j] = p1[j]*(h2/(h2-h1)) + (h1/(h1-h2))*p2[j];
+}
+/* _rkFDSolverConstraint (rkfd_volume.c:397-491): q (6x6 row-major, element (i,j) = _zMat6DElem), c */
+static void vol_constraint(ork_vpair *vp, double *q, double *c)
+{
+  int i, j, a, b;
+  memset(q,0,36*8); memset(c,0,6*8);
+  for(i=0;i<vp->ntri;i++){
+    double pf[9], p[9], pm[9], pp[6], h[3], s, cc[6], pc[3], S[9]; int st = 0, stp[3] = {0,0,0};
+    for(j=0;j<3;j++){ v3_sub(vp->tri[i]+3*j,vp->center,pf+3*j); h[j] = v3_dot(vp->norm,pf+3*j);
+      v3_copy(pf+3*j,p+3*j); v3_cat(p+3*j,-h[j],vp->norm); }
+    vol_mid(p,pm); s = vol_area(p);
+    /* _rkFDSolverConstraintAddQ (:279-294) */
+    for(j=0;j<3;j++) pc[j] = (s/3.0)*(p[j]+p[3+j]+p[6+j]);
+    for(j=0;j<3;j++) q[6*j+j] += s;
+    m3_skew(pc,S);                      /* [pc x] */
+    for(a=0;a<3;a++) for(b=0;b<3;b++){ q[6*(3+a)+b] += S[3*a+b]; q[6*a+3+b] -= S[3*a+b]; }
+    for(j=0;j<3;j++){ double M[9], M2[9]; m3_skew(pm+3*j,M); m3_mul(M,M,M2);     /* [pm x][pm x] */
+      for(a=0;a<3;a++) for(b=0;b<3;b++) q[6*(3+a)+3+b] -= (s/3.0)*M2[3*a+b]; }
+    vol_cc(pm,h,vp->ci->K,s,vp->norm,cc);
+    /* _rkFDSolverConstraintSignDepth (:312-329) */
+    for(j=0;j<3;j++){
+      if( h[j] > ORK_TOL ){ st += 1<<(j*2); stp[1] = j; }
+      else if( h[j] < -ORK_TOL ){ st += 1<<(j*2+1); stp[2] = j; }
+      else stp[0] = j; }
+    switch( st ){
+    case 0x01: case 0x04: case 0x10: case 0x05: case 0x11: case 0x14:
+      vol_set_plane(vp,pf+3*stp[0],vp->tn[i]);  /* fall through */
+    case 0x15:
+      for(j=0;j<6;j++) c[j] += cc[j];
+      continue;
+    case 0x02: case 0x08: case 0x20: case 0x0a: case 0x22: case 0x28:
+      vol_set_plane(vp,pf+3*stp[0],vp->tn[i]);  /* fall through */
+    case 0x2a:
+      for(j=0;j<6;j++) c[j] -= cc[j];
+      continue;
+    case 0x24: case 0x12: case 0x09:
+      for(j=0;j<6;j++) c[j] += cc[j];
+      vol_inner(pf+3*stp[1],pf+3*stp[2],h[stp[1]],h[stp[2]],p+3*stp[1]);
+      h[stp[1]] = 0.0;
+      v3_copy(p+3*stp[0],pp); v3_copy(p+3*stp[1],pp+3);
+      break;
+    case 0x06: case 0x21: case 0x18:
+      for(j=0;j<6;j++) c[j] += cc[j];
+      vol_inner(pf+3*stp[1],pf+3*stp[2],h[stp[1]],h[stp[2]],p+3*stp[2]);
+      h[stp[2]] = 0.0;
+      v3_copy(p+3*stp[2],pp); v3_copy(p+3*stp[0],pp+3);
+      break;
+    case 0x16: case 0x19: case 0x25:
+      stp[0] = (stp[2]+1)%3; stp[1] = (stp[0]+1)%3;
+      for(j=0;j<6;j++) c[j] += cc[j];
+      vol_inner(pf+3*stp[2],pf+3*stp[0],h[stp[2]],h[stp[0]],p+3*stp[0]);
+      vol_inner(pf+3*stp[2],pf+3*stp[1],h[stp[2]],h[stp[1]],p+3*stp[1]);
+      h[stp[0]] = h[stp[1]] = 0.0;
+      v3_copy(p+3*stp[0],pp); v3_copy(p+3*stp[1],pp+3);
+      break;
+    case 0x1a: case 0x26: case 0x29:
+      stp[0] = (stp[1]+1)%3; stp[2] = (stp[0]+1)%3;
+      for(j=0;j<6;j++) c[j] -= cc[j];
+      vol_inner(pf+3*stp[1],pf+3*stp[0],h[stp[1]],h[stp[0]],p+3*stp[0]);
+      vol_inner(pf+3*stp[1],pf+3*stp[2],h[stp[1]],h[stp[2]],p+3*stp[2]);
+      h[stp[0]] = h[stp[2]] = 0.0;
+      v3_copy(p+3*stp[2],pp); v3_copy(p+3*stp[0],pp+3);
+      break;
+    default:
+      continue;
+    }
+    s = vol_area(p); vol_mid(p,pm);
+    vol_cc(pm,h,vp->ci->K,s,vp->norm,cc);
+    switch( st ){
+    case 0x1a: case 0x26: case 0x29: for(j=0;j<6;j++) c[j] += 2.0*cc[j]; break;
+    default: for(j=0;j<6;j++) c[j] -= 2.0*cc[j];
+    }
+    vol_set_plane(vp,pp,vp->tn[i]);
+  }
+  /* rkCDPlaneListQuickSort with __rk_fd_plane_cmp (:376-395): ascending angle key along zListForEach
+   * order ([EXT] sort direction assumed); insertion sort, ties (|dth| tiny) keep their order */
+  { double th[VOL_MAXPL]; const double *n = vp->axis, *a1 = vp->axis+3;
+    for(i=0;i<vp->npl;i++){ double t[3]; v3_cross(a1,vp->pl[i].norm,t);
+      th[i] = v3_dot(t,n) > 0 ? atan2(-v3_norm(t),v3_dot(a1,vp->pl[i].norm)) : atan2(v3_norm(t),v3_dot(a1,vp->pl[i].norm)); }
+    for(i=1;i<vp->npl;i++){ ork_vplane t = vp->pl[i]; double a = th[i];
+      for(j=i-1;j>=0 && !(fabs(th[j]-a) < ORK_TOL) && th[j] > a;j--){ vp->pl[j+1] = vp->pl[j]; th[j+1] = th[j]; }
+      vp->pl[j+1] = t; th[j+1] = a; } }
+}
+
+/* [EXT A-16] zLPSolveSimplex / zLPFeasibleBase (ZM, absent): min c^T x  s.t.  A x = b, x >= 0 by the two-phase
+ * tableau simplex with Bland's rule.  c == NULL: feasibility only.  Returns 1 on success. */
+static int vol_lp(int m, int n, const double *A, const double *b, const double *c, double *x)
+{
+  int nt = n + m, i, j, r, it, ok = 1, phase; int *basis = (int*)malloc(m*sizeof(int));
+  double *T = (double*)malloc((size_t)m*(nt+1)*8), *cost = (double*)malloc(nt*8), bmax = 0, eps;
+  for(i=0;i<m;i++){ double sg = b[i] < 0 ? -1.0 : 1.0;
+    for(j=0;j<n;j++) T[(nt+1)*i+j] = sg*A[n*i+j];
+    for(j=0;j<m;j++) T[(nt+1)*i+n+j] = i==j ? 1.0 : 0.0;
+    T[(nt+1)*i+nt] = sg*b[i]; basis[i] = n+i; if( fabs(b[i]) > bmax ) bmax = fabs(b[i]); }
+  eps = 1.0e-10*(1.0+bmax);
+  for(phase=1;phase<=2 && ok;phase++){
+    int ncol = phase==1 ? nt : n;
+    if( phase == 2 && !c ) break;
+    for(j=0;j<nt;j++) cost[j] = phase==1 ? ( j>=n ? 1.0 : 0.0 ) : ( j<n ? c[j] : 0.0 );
+    for(it=0;it<20000;it++){
+      int enter = -1, leave = -1; double best = 0;
+      for(j=0;j<ncol && enter<0;j++){ double rc = cost[j]; int bas = 0;
+        for(i=0;i<m;i++){ if( basis[i]==j ) bas = 1; rc -= cost[basis[i]]*T[(nt+1)*i+j]; }
+        if( !bas && rc < -1.0e-11 ) enter = j; }
+      if( enter < 0 ) break;
+      for(i=0;i<m;i++){ double a = T[(nt+1)*i+enter];
+        if( a > 1.0e-11 ){ double ratio = T[(nt+1)*i+nt]/a;
+          if( leave < 0 || ratio < best - 1.0e-13 || ( fabs(ratio-best) <= 1.0e-13 && basis[i] < basis[leave] ) ){ leave = i; best = ratio; } } }
+      if( leave < 0 ){ ok = 0; break; }          /* unbounded */
+      { double pv = T[(nt+1)*leave+enter];
+        for(j=0;j<=nt;j++) T[(nt+1)*leave+j] /= pv;
+        for(r=0;r<m;r++) if( r != leave ){ double fct = T[(nt+1)*r+enter]; if( fct != 0 ) for(j=0;j<=nt;j++) T[(nt+1)*r+j] -= fct*T[(nt+1)*leave+j]; }
+        basis[leave] = enter; }
+    }
+    if( phase == 1 ){ double art = 0;
+      for(i=0;i<m;i++) if( basis[i] >= n ) art += T[(nt+1)*i+nt];
+      if( art > eps ) ok = 0;
+      else for(i=0;i<m;i++) if( basis[i] >= n ){   /* drive a degenerate artificial out of the basis if possible */
+        for(j=0;j<n;j++) if( fabs(T[(nt+1)*i+j]) > 1.0e-9 ) break;
+        if( j < n ){ double pv = T[(nt+1)*i+j]; int jj;
+          for(jj=0;jj<=nt;jj++) T[(nt+1)*i+jj] /= pv;
+          for(r=0;r<m;r++) if( r != i ){ double fct = T[(nt+1)*r+j]; if( fct != 0 ) for(jj=0;jj<=nt;jj++) T[(nt+1)*r+jj] -= fct*T[(nt+1)*i+jj]; }
+          basis[i] = j; } } }
+  }
+  if( ok && x ){ for(j=0;j<n;j++) x[j] = 0; for(i=0;i<m;i++) if( basis[i] < n ) x[basis[i]] = T[(nt+1)*i+nt]; }
+  free(T); free(cost); free(basis);
+  return ok;
+}
+
+/* cached-ABA probe with a 6-D wrench (f, t world axes) at world point pos of `link` (rkfd_volume.c:176-211) */
+static void aba_probe6(ork_env *e, int link, const double *pos_w, const double *f6)
+{
+  const ork_world *w = e->w; int i, j, k, r; ork_lw *x = &e->lw[link]; double pos[3], fl[3], tl[3], n[3];
+  for(i=0;i<w->nl;i++){ memset(e->lw[i].du,0,sizeof e->lw[i].du); memset(e->lw[i].dp,0,sizeof e->lw[i].dp); }
+  v3_sub(pos_w,x->pw,pos); m3_tmulv(x->Rw,pos,pos); m3_tmulv(x->Rw,f6,fl); m3_tmulv(x->Rw,f6+3,tl); v3_cross(pos,fl,n);
+  for(r=0;r<3;r++){ x->dp[r] = -fl[r]; x->dp[3+r] = -(tl[r]+n[r]); }
+  for(i=link;i>=0;i=w->link[i].parent){
+    const ork_link *l = &w->link[i]; ork_lw *y = &e->lw[i]; int nd = l->ndof; double pa[6], t6[6];
+    memcpy(pa,y->dp,sizeof pa);
+    for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += y->S[6*k+j]*y->dp[k]; y->du[j] = -s; }
+    for(j=0;j<nd;j++){ t6[j]=0; for(k=0;k<nd;k++) t6[j] += y->Dinv[6*j+k]*y->du[k]; }
+    for(r=0;r<6;r++) for(j=0;j<nd;j++) pa[r] += y->U[6*r+j]*t6[j];
+    if( l->parent < 0 ) break;
+    m6_tmulv(y->X,pa,t6); for(r=0;r<6;r++) e->lw[l->parent].dp[r] += t6[r];
+  }
+  aba_forward(e,NULL,1);
+}
+int ork_lp_solve(int m, int n, const double *A, const double *b, const double *c, double *x){ return vol_lp(m,n,A,b,c,x); }
+static int link_root(const ork_world *w, int l){ while( w->link[l].parent >= 0 ) l = w->link[l].parent; return l; }
+
+static void solver_volume(ork_env *e, int do_up_ref)
+{
+  const ork_world *w = e->w; int pi, P = 0, n, m, i, j, k, col, off, colnum = 0, pyr = w->pyramid;
+  ork_vpair *vp = (ork_vpair*)malloc(sizeof(ork_vpair)*(w->npair>0?w->npair:1));
+  double dt = w->dt, *A, *b, *Q, *c, *nf, *dz, *init, *f, sn[64], cs[64]; int *idx;
+  for(pi=0;pi<w->npair;pi++) e->v_np[pi] = -1;
+  for(pi=0;pi<w->npair;pi++){
+    if( w->pair[pi].ci.type != ORK_CONTACT_RIGID ) continue;
+    if( vol_build(e,pi,&vp[P]) ) P++;
+  }
+  if( P == 0 ){ free(vp); return; }
+  n = 6*P;
+  A = (double*)calloc(n*n,8); b = (double*)calloc(n,8); Q = (double*)calloc(n*n,8); c = (double*)calloc(n,8);
+  init = (double*)calloc(n,8); f = (double*)calloc(n,8);
+  for(i=0;i<pyr && i<64;i++){ sn[i] = sin(2.0*M_PI/pyr*i); cs[i] = cos(2.0*M_PI/pyr*i); }   /* offset 0 (rkfd_volume.c:1000) */
+  /* _rkFDSolverRelationAccForce (rkfd_volume.c:176-211) */
+  aba_backward(e); aba_forward(e,NULL,0);
+  for(i=0;i<w->nl;i++) memcpy(e->lw[i].a0,e->lw[i].a,sizeof e->lw[i].a);
+  for(k=0;k<P;k++){ const ork_lw *x = &e->lw[vp[k].link];
+    link_point_wld_acc(x,vp[k].center,b+6*k); m3_mulv(x->Rw,x->a+3,b+6*k+3); }
+  for(k=0;k<P;k++) for(i=0;i<6;i++){
+    double f6[6] = {0,0,0,0,0,0}; f6[i] = 1.0; col = 6*k+i;
+    aba_probe6(e,vp[k].link,vp[k].center,f6);
+    for(j=0;j<P;j++){
+      if( link_root(w,vp[j].link) != link_root(w,vp[k].link) ){ int r; for(r=0;r<6;r++) A[n*(6*j+r)+col] = 0; }
+      else { const ork_lw *x = &e->lw[vp[j].link]; double av[6]; int r;
+        link_point_wld_acc(x,vp[j].center,av); m3_mulv(x->Rw,x->a+3,av+3);
+        for(r=0;r<6;r++) A[n*(6*j+r)+col] = av[r] - b[6*j+r]; } }
+  }
+  for(i=0;i<w->nl;i++) memcpy(e->lw[i].a,e->lw[i].a0,sizeof e->lw[i].a);
+  /* _rkFDSolverBiasVel (:214-226) */
+  for(i=0;i<n;i++) b[i] *= dt;
+  for(k=0;k<P;k++){ const ork_lw *x = &e->lw[vp[k].link]; double v6[6];
+    link_point_wld_vel(x,vp[k].center,v6); m3_mulv(x->Rw,x->v+3,v6+3);
+    for(i=0;i<6;i++) b[6*k+i] += v6[i]; }
+  /* _rkFDSolverQPCreate (:496-528) */
+  for(k=0;k<P;k++){ double qv[36], cv[6], t6[6]; int r, s;
+    vol_constraint(&vp[k],qv,cv);
+    for(i=0;i<6;i++) for(j=0;j<6;j++){ double qe = qv[6*i+j];
+      for(r=0;r<n;r++) for(s=0;s<n;s++) Q[n*r+s] += qe*A[n*(6*k+i)+r]*A[n*(6*k+j)+s]; }
+    m6_mulv(qv,b+6*k,t6);
+    for(i=0;i<6;i++){ cv[i] += t6[i]; for(r=0;r<n;r++) c[r] += cv[i]*A[n*(6*k+i)+r]; }
+  }
+  for(k=0;k<P;k++) for(i=0;i<6;i++) Q[n*(6*k+i)+6*k+i] += vp[k].ci->L;
+  /* _rkFDSolverCountContacts, _rkFDSolverFrictionConstraint (:21-29, 121-138) */
+  for(k=0;k<P;k++) colnum += vp[k].npl;
+  m = P + colnum;
+  nf = (double*)calloc((size_t)m*n,8); dz = (double*)calloc(m,8); idx = (int*)calloc(m,sizeof(int));
+  { int io = 0, jo = 0;
+    for(k=0;k<P;k++){ ork_vpair *v = &vp[k];
+      for(j=0;j<3;j++) nf[n*io+jo+j] = v->norm[j];
+      io++;
+      for(i=0;i<v->npl;i++){ ork_vplane *pl = &v->pl[i]; double a = -v3_dot(pl->norm,pl->v), b1 = v3_dot(pl->norm,v->axis+6), b2 = -v3_dot(pl->norm,v->axis+3);
+        for(j=0;j<3;j++){ nf[n*io+jo+j] = a*v->norm[j]; nf[n*io+jo+3+j] = b1*v->axis[3+j] + b2*v->axis[6+j]; }
+        io++; }
+      jo += 6; } }
+  /* _rkFDSolverQP (:530-548) */
+  for(k=0;k<P;k++) for(j=0;j<3;j++) init[6*k+j] = vp[k].norm[j];
+  ork_qp_solve_asm(n,m,Q,c,nf,dz,init,f,idx);
+  for(i=0;i<n;i++) f[i] /= dt;
+  /* _rkFDSolverSetForce (:552-568); the offset is NOT advanced for a pair without planes - mirrored */
+  off = 0;
+  for(k=0;k<P;k++){ ork_vpair *v = &vp[k];
+    if( v->npl == 0 ){ memset(v->wrench,0,sizeof v->wrench); continue; }
+    memcpy(v->wrench,f+off,6*8);
+    if( ( fabs(v->wrench[0]) < ORK_TOL && fabs(v->wrench[1]) < ORK_TOL && fabs(v->wrench[2]) < ORK_TOL ) || v3_dot(v->wrench,v->norm) < ORK_TOL )
+      memset(v->wrench,0,sizeof v->wrench);
+    off += 6; }
+  /* _rkFDSolverModifyNormalForceCenter (:580-631) */
+  for(k=0;k<P;k++){ ork_vpair *v = &vp[k]; double fn = v3_dot(v->norm,v->wrench), r0[3], r[3], dir[3], tmp[3], d, s; int flag = 0, np = v->npl, i0, i1, i2, i3, it;
+    if( fn < ORK_TOL || np < 3 ) continue;
+    for(j=0;j<3;j++) r0[j] = v->axis[3+j]*( -v3_dot(v->axis+6,v->wrench+3)/fn ) + v->axis[6+j]*( v3_dot(v->axis+3,v->wrench+3)/fn );
+    i2 = np-1; i1 = np-2; i0 = np-3;
+    for(it=0,i3=0;it<np;it++,i0=i1,i1=i2,i2=i3,i3=i3+1){
+      int mod = 0;
+      v3_sub(v->pl[i2].v,v->pl[i1].v,dir); d = v3_dot(dir,dir);
+      if( fabs(d) < ORK_TOL ) continue;
+      v3_sub(r0,v->pl[i1].v,tmp);
+      if( v3_dot(tmp,v->pl[i1].norm) > ORK_TOL ) continue;
+      s = v3_dot(dir,tmp)/d;
+      if( s < ORK_TOL ){
+        if( flag ) break;
+        v3_sub(v->pl[i0].v,v->pl[i1].v,tmp); v3_add(tmp,dir,tmp);
+        v3_copy(v->pl[i1].v,r); v3_cat(r,ORK_TOL/v3_norm(tmp),tmp); mod = 1;
+      } else if( s < 1.0-ORK_TOL ){
+        v3_copy(v->pl[i1].v,r); v3_cat(r,s,dir); v3_cat(r,ORK_TOL,v->pl[i1].norm); mod = 1;
+      } else {
+        const double *v3p = v->pl[i3 < np ? i3 : 0].v;      /* zListCellNext of the head is the root cell: index 0 assumed */
+        v3_sub(v3p,v->pl[i2].v,tmp); v3_sub(tmp,dir,tmp);
+        v3_copy(v->pl[i2].v,r); v3_cat(r,ORK_TOL/v3_norm(tmp),tmp); mod = 2;
+      }
+      { /* _rkFDSolverModifyNormForceCenterTrq (:572-578) */
+        double na = v3_dot(v->norm,v->wrench+3), k1 = fn*v3_dot(v->axis+6,r), k2 = -fn*v3_dot(v->axis+3,r);
+        for(j=0;j<3;j++) v->wrench[3+j] = na*v->norm[j] + k1*v->axis[3+j] + k2*v->axis[6+j]; }
+      if( mod == 1 ) break;
+      flag = 1;
+    } }
+  /* _rkFDSolverModifyWrench (:869-916) */
+  for(k=0;k<P;k++){ ork_vpair *v = &vp[k]; double wv[6], fn, fs, tl = 0; int np = v->npl, kinetic = 0, setforce = 0;
+    if( np == 0 ) continue;
+    if( fabs(v3_dot(v->wrench,v->axis)) < ORK_TOL ) continue;
+    for(i=0;i<3;i++){ wv[i] = v3_dot(v->wrench,v->axis+3*i); wv[i+3] = v3_dot(v->wrench+3,v->axis+3*i); }
+    fn = wv[0]; fs = sqrt(wv[1]*wv[1]+wv[2]*wv[2]);
+    for(i=0;i<np;i++){ ork_vplane *pl = &v->pl[i]; double rl;      /* _rkFDSolverPlaneVertPos (:700-713) */
+      pl->r[0] = v3_dot(pl->v,v->axis+3); pl->r[1] = v3_dot(pl->v,v->axis+6);
+      rl = sqrt(pl->r[0]*pl->r[0]+pl->r[1]*pl->r[1]); if( tl < rl ) tl = rl; }
+    if( fabs(tl) < ORK_TOL ){
+      wv[3] = wv[4] = wv[5] = 0;
+      if( !(fabs(fs) < ORK_TOL) && fs > v->ci->SF*fn ){   /* _rkFDSolverModifyWrenchKineticCenter (:715-731) */
+        double vel[3], nv; link_point_wld_vel(&e->lw[v->link],v->center,vel);
+        v3_cat(vel,-v3_dot(v->norm,vel),v->norm); nv = v3_norm(vel);
+        if( fabs(nv) < ORK_TOL ){ wv[1] = 0; wv[2] = 0; }
+        else { double t = kinetic_friction_weight(w->friction_weight,nv)*v->ci->KF*wv[0]/nv;
+          wv[1] = -t*v3_dot(vel,v->axis+3); wv[2] = -t*v3_dot(vel,v->axis+6); }
+        kinetic = 1;
+      }
+      setforce = 1;
+    } else if( ( !(fabs(fs) < ORK_TOL) && fs > v->ci->SF*fn ) || fabs(wv[3]) > tl*wv[0] ){
+      kinetic = 2;
+    } else {
+      /* _rkFDSolverModifyWrenchStatic (:643-688): feasibility of the wrench inside the friction pyramids at the polygon corners */
+      int fnum = pyr*np; double *ma = (double*)malloc(6*fnum*8), mb[6];
+      for(j=0;j<np;j++) for(i=0;i<pyr;i++){ int cc = pyr*j+i; ork_vplane *pl = &v->pl[j];
+        ma[0*fnum+cc] = 1.0; ma[1*fnum+cc] = pl->r[1]; ma[2*fnum+cc] = -pl->r[0];
+        ma[3*fnum+cc] = v->ci->SF*cs[i]; ma[4*fnum+cc] = v->ci->SF*sn[i];
+        ma[5*fnum+cc] = -( ma[2*fnum+cc]*ma[4*fnum+cc] + ma[1*fnum+cc]*ma[3*fnum+cc] ); }
+      mb[0] = wv[0]; mb[1] = wv[4]; mb[2] = wv[5]; mb[3] = wv[1]; mb[4] = wv[2]; mb[5] = wv[3];
+      if( !vol_lp(6,fnum,ma,mb,NULL,NULL) ) kinetic = 2;
+      free(ma);
+    }
+    if( kinetic == 2 ){
+      /* _rkFDSolverModifyWrenchKinetic (:733-843) */
+      double *ma = (double*)malloc(3*np*8), mb[3], *mc = (double*)malloc(np*8), *mf = (double*)calloc(np,8), wn[3];
+      for(j=0;j<np;j++){ ma[j] = 1.0; ma[np+j] = v->pl[j].r[1]; ma[2*np+j] = -v->pl[j].r[0]; }
+      mb[0] = wv[0]; mb[1] = wv[4]; mb[2] = wv[5];
+      for(i=0;i<3;i++) wn[i] = fabs(wv[i+1]) < ORK_TOL ? 0.0 : 1.0/wv[i+1];
+      for(j=0;j<np;j++){ ork_vplane *pl = &v->pl[j]; double p[3], vel[3], nv;     /* _rkFDSolverPlaneVertSlideDir (:759-776) */
+        v3_add(v->center,pl->v,p); link_point_wld_vel(&e->lw[v->link],p,vel);
+        v3_cat(vel,-v3_dot(v->norm,vel),v->norm); nv = v3_norm(vel);
+        if( fabs(nv) < ORK_TOL ){ pl->s[0] = pl->s[1] = 0; }
+        else { double ww = kinetic_friction_weight(w->friction_weight,nv)*v->ci->KF/nv;
+          pl->s[0] = -ww*v3_dot(vel,v->axis+3); pl->s[1] = -ww*v3_dot(vel,v->axis+6); }
+        mc[j] = -wn[0]*pl->s[0] - wn[1]*pl->s[1] - wn[2]*( pl->r[0]*pl->s[1] - pl->r[1]*pl->s[0] ); }
+      if( !vol_lp(3,np,ma,mb,mc,mf) ){
+        /* _rkFDSolverModifyWrenchKineticEvalFuncSafety (:795-812): one row, costs accumulated */
+        double wn2[2]; for(i=0;i<2;i++) wn2[i] = fabs(wv[i+3]) < ORK_TOL ? 0.0 : 1.0/wv[i+3];
+        for(j=0;j<np;j++) mc[j] += wn2[0]*v->pl[j].r[0] - wn2[1]*v->pl[j].r[1];
+        for(j=0;j<np;j++) mf[j] = 0;
+        vol_lp(1,np,ma,mb,mc,mf);
+      }
+      wv[1] = wv[2] = wv[3] = 0;                          /* _rkFDSolverModifyWrenchKineticTotalWrench (:814-828) */
+      for(j=0;j<np;j++){ double fx = v->pl[j].s[0]*mf[j], fy = v->pl[j].s[1]*mf[j];
+        wv[1] += fx; wv[2] += fy; wv[3] += v->pl[j].r[0]*fy - v->pl[j].r[1]*fx; }
+      free(ma); free(mc); free(mf);
+      setforce = 1;
+    }
+    if( do_up_ref ) e->v_type[v->pair] = kinetic ? ORK_KF : ORK_SF;
+    if( setforce ){ memset(v->wrench,0,sizeof v->wrench);     /* _rkFDSolverModifyWrenchSetForce (:858-867) */
+      for(i=0;i<3;i++){ v3_cat(v->wrench,wv[i],v->axis+3*i); v3_cat(v->wrench+3,wv[i+3],v->axis+3*i); } }
+  }
+  /* _rkFDSolverPushWrench (:919-936) */
+  for(k=0;k<P;k++){ ork_vpair *v = &vp[k]; ork_lw *x = &e->lw[v->link]; double pos[3], fl[3], tl[3], nn[3];
+    v3_sub(v->center,x->pw,pos); m3_tmulv(x->Rw,pos,pos);
+    m3_tmulv(x->Rw,v->wrench,fl); m3_tmulv(x->Rw,v->wrench+3,tl); v3_cross(pos,fl,nn);
+    v3_add(x->wext,fl,x->wext); v3_add(x->wext+3,tl,x->wext+3); v3_add(x->wext+3,nn,x->wext+3);
+    e->v_np[v->pair] = v->npl; memcpy(e->v_wrench+6*v->pair,v->wrench,6*8); memcpy(e->v_center+3*v->pair,v->center,3*8); }
+  free(A); free(b); free(Q); free(c); free(nf); free(dz); free(init); free(f); free(idx); free(vp);
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* one dynamics evaluation: _rkFDUpdate body / _rkFDUpdateRef (rkfd_sim.c:525-549) */
 static void eval_dynamics(ork_env *e, const double *q, const double *qd, double *qdd, int do_up_ref)
 {
@@ -887,7 +1342,7 @@ static void eval_dynamics(ork_env *e, const double *q, const double *qd, double 
   joint_friction(e,q,qd,do_up_ref);
   if( has_elastic ) solver_penalty(e,do_up_ref);
   e->rn = 0;
-  if( has_rigid && w->solver != ORK_SOLVER_VOLUME ) solver_rigid(e,do_up_ref);
+  if( has_rigid ){ if( w->solver == ORK_SOLVER_VOLUME ) solver_volume(e,do_up_ref); else solver_rigid(e,do_up_ref); }
   /* _rkFDUpdateAcc (:502-523) */
   aba_backward(e); aba_forward(e,qdd,0);
   if( do_up_ref ) update_prev_driving_trq(e);         /* solver->_update_ref (:548) */
@@ -963,6 +1418,14 @@ double ork_env_energy(const ork_env *e)
     (void)j; }
   return E;
 }
+/* Volume solver results of the last evaluation per pair: np (-1: no contact volume), type, wrench (world, at center), center */
+void ork_env_get_volume(const ork_env *e, int *np, int *type, double *wrench, double *center)
+{
+  int n = e->w->npair;
+  if(np) memcpy(np,e->v_np,n*sizeof(int)); if(type) memcpy(type,e->v_type,n*sizeof(int));
+  if(wrench) memcpy(wrench,e->v_wrench,6*n*8); if(center) memcpy(center,e->v_center,3*n*8);
+}
+int ork_world_npair(const ork_world *w){ return w->npair; }
 int ork_env_get_rigid_system(const ork_env *e, double *A, double *b, double *f, int cap)
 {
   int n = e->rn; if( n > cap ) return -n;

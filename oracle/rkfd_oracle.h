@@ -98,6 +98,13 @@ double ork_env_energy(const ork_env *e);
 /* last rigid-contact system (Delassus matrix A (n x n, row-major), bias b, solution f); returns n */
 int ork_env_get_rigid_system(const ork_env *e, double *A, double *b, double *f, int cap);
 
+/* Volume solver (rkfd_volume.c) results of the last evaluation, per pair: np = contact-polygon planes (-1: no contact
+ * volume), type = pair friction type, wrench (6, world axes, at center), center (3) */
+void ork_env_get_volume(const ork_env *e, int *np, int *type, double *wrench, double *center);
+int ork_world_npair(const ork_world *w);
+/* [EXT A-16] LP by the two-phase simplex (Bland): min c^T x s.t. A x = b (m x n, row-major), x >= 0; c NULL: feasibility */
+int ork_lp_solve(int m, int n, const double *A, const double *b, const double *c, double *x);
+
 /* ---- batch driver (CPU baseline): B independent envs, OpenMP over envs ---------- */
 /* q, qd, u: env-major (B x nq / B x nl); steps every env `nsteps` times; returns threads used */
 int ork_batch_run(const ork_world *w, int B, double *q, double *qd, const double *u,

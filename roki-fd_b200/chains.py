@@ -298,7 +298,7 @@ def biped(stuff="body"):
     """A small legged tree for the C4-shaped workload (multi-limb legged model): floating
     trunk + two legs of three revolute joints (hip, knee, ankle: pitch axes) with DC motors and an 8-vertex sole
     under each ankle link.  12 DoF, 7 links, 16 contact vertices.  (The reference's humanoid mighty.ztk has 26 DoF
-    and needs the Volume solver, which is not built.)"""
+    and polyhedral soles; this tree keeps box soles, the shape the Volume solver here covers.)"""
     links = [Link(name="trunk", jtype="float", mass=8.0, stuff=stuff, com=np.array([0, 0, 0.1]),
                   inertia=np.diag([0.12, 0.10, 0.06]))]
     for side, y in (("L", 0.09), ("R", -0.09)):
@@ -320,6 +320,12 @@ def world_c4_penalty():
     """C4-shaped workload with what is built: the legged tree on the soft floor (vertex penalty contact)."""
     return World(chains=[biped(), floor_soft()],
                  contact_info=[ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0, SF=0.5, KF=0.3)])
+
+
+def world_c4_volume():
+    """C4 (BASELINE.json configs[3]): the legged tree on the rigid floor with volume-based contact (rkfd_volume),
+    the solver's default contact info (rkfd_volume.c:961-969)."""
+    return World(chains=[biped(), floor()], solver="Volume")
 
 
 def sample_state(world, B, seed=20260418):

@@ -184,7 +184,8 @@ static void solver_update_ref(rkFDSolver *s){ (void)s; }
 static void solver_destroy(rkFDSolver *s){ (void)s; }
 static rkFDSolverCom g_solver_vert   = { solver_defci, solver_init, solver_colchk, solver_update, solver_update_ref, solver_destroy };
 static rkFDSolverCom g_solver_mlcp   = { solver_defci, solver_init, solver_colchk, solver_update, solver_update_ref, solver_destroy };
-static rkFDSolverCom g_solver_volume = { solver_defci, solver_init, solver_colchk, solver_update, solver_update_ref, solver_destroy };
+static void solver_defci_volume(rkFDSolver *s, rkContactInfo *ci){ solver_defci(s, ci); rkContactInfoSetL(ci, 0.001); }   /* rkfd_volume.c:961-969 */
+static rkFDSolverCom g_solver_volume = { solver_defci_volume, solver_init, solver_colchk, solver_update, solver_update_ref, solver_destroy };
 static rkFDSolver *solver_create(rkFDSolver *s, rkFDSolverCom *com){ if( !(s->prp = std::calloc(1, 64)) ) return NULL; s->com = com; return s; }
 extern "C" rkFDSolver *rkFDSolverCreate_Vert(rkFDSolver *s){ return solver_create(s, &g_solver_vert); }
 extern "C" rkFDSolver *rkFDSolverCreate_MLCP(rkFDSolver *s){ return solver_create(s, &g_solver_mlcp); }
@@ -347,7 +348,6 @@ extern "C" void rkFDUpdateInit(rkFD *fd)
     w.integrator = fd->ode.integrator;
     std::string err;
     if( !build_model(w, fi->model, err) ) throw std::runtime_error(err);
-    if( fi->model.has_rigid && w.solver == S_VOLUME ) throw std::runtime_error("rigid contact pairs with the Volume solver are not implemented on the device yet");
     fi->engine = new Engine(fi->model, fi->B, fi->devices);
     const int n = fd->size, nl = fi->model.nl, B = fi->B;
     /* initial state: the batched arrays when given, else the scalar state replicated over the envs */

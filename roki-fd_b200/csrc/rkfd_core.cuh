@@ -1497,7 +1497,10 @@ struct Core {
     cfl = nfl;
   }
 
+#include "rkfd_volume.cuh"
+
   RKFD_HD void rigid_solve(const ModelDev &m, bool ref, unsigned act){
+    if constexpr ( Spec::NL == 0 ){ if( m.solver == S_VOLUME ){ rigid_volume(m, ref); return; } }
     if( m.rigid_link >= 0 ){ if( m.solver == S_MLCP ) rigid_mlcp_single(m, ref, act); else rigid_vert_single(m, ref, act); return; }
     const int nlanes = c.lanes(), lane = c.lane();
     while( act ){

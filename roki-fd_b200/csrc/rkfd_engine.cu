@@ -165,7 +165,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     s->nstage = (size_t)nmax*s->B; s->dstage = dalloc<double>(*s, s->nstage);
     /* launch configuration: the block size that keeps most environments resident per SM; scratch in HBM
      * (gscr) only when no shared-memory variant fits */
-    int best = 0; const bool rigid = model.has_rigid && model.solver != S_VOLUME;
+    int best = 0; const bool rigid = model.has_rigid;
     /* model specialisation (RKFD_SPEC=0 forces the generic kernel: tuning / comparison aid) */
     unsigned specs = spec_match_mask(model);
     if( !model.has_rigid && model_tm_.ntspace > 0 && model_tm_.ntspace <= SPEC_GENERIC_TM_MAX_T ) specs |= 1u << SPEC_GENERIC_TM;

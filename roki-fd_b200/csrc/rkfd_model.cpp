@@ -192,6 +192,12 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
     if( lk >= 0 && m.solver == S_VERT && lpos && m.pyramid <= 12 ){ m.rigid_link = lk; m.ws1_doubles = W1_CT + W1_CTN*nrs + 32*(nrs+1); }
     if( m.rigid_link < 0 ) m.nrg = 0;
   }
+  if( m.has_rigid && m.solver == S_VOLUME ){
+    /* the Volume solver (rkfd_volume.cuh) works on thread-local data: no workspace; cells must be parallelepipeds */
+    for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID && m.cell[m.pair[p].cell].nvert != 8 ){ err = "Volume solver: rigid cells must have the 8 corners of a box (sign-bit order)"; return false; }
+    m.ws_doubles = 0; m.ws_geo = m.ws_b = m.ws_f = m.ws_A = m.ws_du = m.ws_da = m.ws_qp = 0;
+    return true;
+  }
   if( m.has_rigid ){
     const int n = m.nmax, mc = m.pyramid*nrs, nm = n + mc; int o = 0;
     m.ws_geo = o; o += GEO_DOUBLES*nrs;

@@ -1,0 +1,640 @@
+/* rkfd_volume.cuh - Volume contact solver (reference src/rkfd_volume.c), member functions of Core (included inside
+ * the struct body of rkfd_core.cuh).
+ *
+ * One environment per lane: every lane whose environment has a rigid pair in contact runs the whole solve on its
+ * own scratch column and on thread-local workspaces (the matrices are at most 12 x 12 / 18 x 12):
+ *   contact volume   [EXT A-15] cell parallelepiped (8 corners, sign-bit order) clipped by the half-space of ONE
+ *                    face of the static box; two streaming passes over the 12 cell triangles - (0) volume and
+ *                    barycentre (tetrahedra about a point of the clipping plane, so the cut polygon contributes
+ *                    nothing), (1) the surface integrals and the contact-polygon planes; the cut polygon is
+ *                    integrated as a fan of its boundary segments.  No triangle list is stored.
+ *   A, b             6 cached-ABA probes per pair (unit force / torque at the volume centre), responses read at the
+ *                    centres of all pairs of the same tree                         rkfd_volume.c:141-226
+ *   Q6, c6, planes   per triangle: midpoint-rule integrals, sign cases             rkfd_volume.c:232-491
+ *   QP               Q = sum A_p^T Q6 A_p + L, rows: normal force >= 0 and one centre-of-pressure row per polygon
+ *                    edge; dense active-set method (rkfd_opt_qp.c:43-181) with the KKT solve through the Schur
+ *                    complement of the Cholesky-factored Q (pseudo-inverse by Jacobi only when the active rows are
+ *                    dependent)                                                    rkfd_volume.c:496-548
+ *   post-processing  non-pushing wrenches zeroed, centre of pressure projected into the polygon, static-friction
+ *                    feasibility LP / kinetic-friction redistribution LP ([EXT A-16] two-phase simplex with Bland's
+ *                    rule), wrench on the link                                     rkfd_volume.c:552-936
+ * Limits: VOL_P pairs in contact per environment, VOL_PL polygon planes per pair, pyramid * planes <= VOL_LPN
+ * (status bit 2 is raised otherwise and the surplus is ignored). */
+
+#ifdef __CUDACC__
+#define RKFD_VOL_NI __host__ __device__ __noinline__
+#else
+#define RKFD_VOL_NI inline
+#endif
+  static constexpr int VOL_P = 2, VOL_PL = 8, VOL_N = 6*VOL_P, VOL_M = VOL_P*(1+VOL_PL), VOL_LPN = 64, VOL_LPS = VOL_LPN + 7;
+  struct VolPair {
+    int pair, link, fsl, wsl, npl, sofs;
+    V3 center, norm, a1, a2;
+    double K, L, SF, KF;
+    V3 plv[VOL_PL], pln[VOL_PL]; double r[VOL_PL][2], s[VOL_PL][2];
+    double q6[36], c6[6], w[6];
+  };
+  static RKFD_HD bool vtiny(double x){ return fabs(x) < ZTOL; }
+
+  /* _rkFDSolverSetContactPlane (rkfd_volume.c:350-374) */
+  RKFD_HD void vol_set_plane(VolPair &vp, V3 p, V3 fnorm){
+    const V3 t = fnorm - dot(fnorm, vp.norm)*vp.norm;
+    if( vtiny(t.x) && vtiny(t.y) && vtiny(t.z) ) return;
+    const V3 cn = (-1.0/norm(t))*t;
+    for(int i=0;i<vp.npl;i++){
+      const V3 dn = cn - vp.pln[i];
+      if( fabs(dn.x) < 1e-8 && fabs(dn.y) < 1e-8 && fabs(dn.z) < 1e-8 ){
+        const V3 dv = vp.plv[i] - p;
+        if( fabs(dot(cn, dv)) < 1e-8 ){
+          if( dot(vp.norm, cross(cn, dv)) > 0.0 ) vp.plv[i] = p;
+          return;
+        }
+      }
+    }
+    if( vp.npl >= VOL_PL ){ bad |= 4; return; }
+    vp.plv[vp.npl] = p; vp.pln[vp.npl] = cn; vp.npl++;
+  }
+  /* _rkFDSolverConstraintMidDepth + _rkFDSolverConstraintDepth (rkfd_volume.c:232-241, 296-310) */
+  static RKFD_HD void vol_cc(const V3 (&p)[3], const double (&h)[3], double K, V3 nrm, double (&cc)[6]){
+    const double s = 0.5*norm(cross(p[1]-p[0], p[2]-p[0])), k = K*s/6.0;
+    const double hm0 = k*(h[0]+h[1]), hm1 = k*(h[1]+h[2]), hm2 = k*(h[0]+h[2]), hc = k*(h[0]+h[1]+h[2])*2;
+    const V3 m0 = 0.5*(p[0]+p[1]), m1 = 0.5*(p[1]+p[2]), m2 = 0.5*(p[2]+p[0]);
+    const V3 a = cross(nrm, hm0*m0) + cross(nrm, hm1*m1) + cross(nrm, hm2*m2);
+    cc[0] = -hc*nrm.x; cc[1] = -hc*nrm.y; cc[2] = -hc*nrm.z; cc[3] = a.x; cc[4] = a.y; cc[5] = a.z;
+  }
+  /* _rkFDSolverConstraintInnerPoint (rkfd_volume.c:331-348) */
+  static RKFD_HD V3 vol_inner(V3 p1, V3 p2, double h1, double h2){
+    if( vtiny(h1) ) return p1;
+    if( vtiny(h2) ) return p2;
+    if( vtiny(h2-h1) ) return 0.5*(p1+p2);
+    return (h2/(h2-h1))*p1 + (h1/(h1-h2))*p2;
+  }
+  /* one triangle of the contact volume (outward face normal fn): body of the loop of _rkFDSolverConstraint
+   * (rkfd_volume.c:397-491) */
+  RKFD_VOL_NI void vol_tri(VolPair &vp, V3 ta, V3 tb, V3 tc, V3 fn){
+    if( dot(cross(tb-ta, tc-ta), fn) < 0 ){ const V3 t = tb; tb = tc; tc = t; }
+    V3 pf[3] = { ta - vp.center, tb - vp.center, tc - vp.center }, p[3], pp0;
+    double h[3], cc[6];
+    for(int j=0;j<3;j++){ h[j] = dot(vp.norm, pf[j]); p[j] = pf[j] - h[j]*vp.norm; }
+    { /* _rkFDSolverConstraintAddQ (:279-294) */
+      const double s = 0.5*norm(cross(p[1]-p[0], p[2]-p[0]));
+      const V3 pc = (s/3.0)*(p[0]+p[1]+p[2]);
+      double *q = vp.q6;
+      q[0] += s; q[7] += s; q[14] += s;
+      /* [pc x] into the lower-left block, its negative into the upper-right one */
+      q[6*3+1] += -pc.z; q[6*3+2] +=  pc.y; q[6*4+0] +=  pc.z; q[6*4+2] += -pc.x; q[6*5+0] += -pc.y; q[6*5+1] +=  pc.x;
+      q[6*0+4] -= -pc.z; q[6*0+5] -=  pc.y; q[6*1+3] -=  pc.z; q[6*1+5] -= -pc.x; q[6*2+3] -= -pc.y; q[6*2+4] -=  pc.x;
+      const V3 pm[3] = { 0.5*(p[0]+p[1]), 0.5*(p[1]+p[2]), 0.5*(p[2]+p[0]) };
+      for(int j=0;j<3;j++){   /* [m x][m x] = m m^T - |m|^2 I */
+        const V3 m_ = pm[j]; const double mm_ = dot(m_, m_), k = s/3.0;
+        q[6*3+3] -= k*(m_.x*m_.x - mm_); q[6*3+4] -= k*m_.x*m_.y; q[6*3+5] -= k*m_.x*m_.z;
+        q[6*4+3] -= k*m_.y*m_.x; q[6*4+4] -= k*(m_.y*m_.y - mm_); q[6*4+5] -= k*m_.y*m_.z;
+        q[6*5+3] -= k*m_.z*m_.x; q[6*5+4] -= k*m_.z*m_.y; q[6*5+5] -= k*(m_.z*m_.z - mm_);
+      }
+    }
+    vol_cc(p, h, vp.K, vp.norm, cc);
+    int st = 0, stp[3] = {0,0,0};
+    for(int j=0;j<3;j++){
+      if( h[j] > ZTOL ){ st += 1<<(j*2); stp[1] = j; }
+      else if( h[j] < -ZTOL ){ st += 1<<(j*2+1); stp[2] = j; }
+      else stp[0] = j;
+    }
+    double sgn2 = -2.0;
+    switch( st ){
+    case 0x01: case 0x04: case 0x10: case 0x05: case 0x11: case 0x14:
+      vol_set_plane(vp, pf[stp[0]], fn);
+    case 0x15:
+      for(int j=0;j<6;j++) vp.c6[j] += cc[j];
+      return;
+    case 0x02: case 0x08: case 0x20: case 0x0a: case 0x22: case 0x28:
+      vol_set_plane(vp, pf[stp[0]], fn);
+    case 0x2a:
+      for(int j=0;j<6;j++) vp.c6[j] -= cc[j];
+      return;
+    case 0x24: case 0x12: case 0x09:
+      for(int j=0;j<6;j++) vp.c6[j] += cc[j];
+      p[stp[1]] = vol_inner(pf[stp[1]], pf[stp[2]], h[stp[1]], h[stp[2]]);
+      h[stp[1]] = 0.0;
+      pp0 = p[stp[0]];
+      break;
+    case 0x06: case 0x21: case 0x18:
+      for(int j=0;j<6;j++) vp.c6[j] += cc[j];
+      p[stp[2]] = vol_inner(pf[stp[1]], pf[stp[2]], h[stp[1]], h[stp[2]]);
+      h[stp[2]] = 0.0;
+      pp0 = p[stp[2]];
+      break;
+    case 0x16: case 0x19: case 0x25:
+      stp[0] = (stp[2]+1)%3; stp[1] = (stp[0]+1)%3;
+      for(int j=0;j<6;j++) vp.c6[j] += cc[j];
+      p[stp[0]] = vol_inner(pf[stp[2]], pf[stp[0]], h[stp[2]], h[stp[0]]);
+      p[stp[1]] = vol_inner(pf[stp[2]], pf[stp[1]], h[stp[2]], h[stp[1]]);
+      h[stp[0]] = h[stp[1]] = 0.0;
+      pp0 = p[stp[0]];
+      break;
+    case 0x1a: case 0x26: case 0x29:
+      stp[0] = (stp[1]+1)%3; stp[2] = (stp[0]+1)%3;
+      for(int j=0;j<6;j++) vp.c6[j] -= cc[j];
+      p[stp[0]] = vol_inner(pf[stp[1]], pf[stp[0]], h[stp[1]], h[stp[0]]);
+      p[stp[2]] = vol_inner(pf[stp[1]], pf[stp[2]], h[stp[1]], h[stp[2]]);
+      h[stp[0]] = h[stp[2]] = 0.0;
+      pp0 = p[stp[2]];
+      sgn2 = 2.0;
+      break;
+    default:
+      return;
+    }
+    vol_cc(p, h, vp.K, vp.norm, cc);
+    for(int j=0;j<6;j++) vp.c6[j] += sgn2*cc[j];
+    vol_set_plane(vp, pp0, fn);
+  }
+
+  /* the 12 triangles of the cell clipped by {x : nn.(x - p0) <= 0}.  pass 0: volume and barycentre; pass 1:
+   * integration (vol_tri) incl. the cut polygon.  Returns false when the volume is empty. */
+  RKFD_VOL_NI bool vol_clip(VolPair &vp, const V3 (&vw)[8], const double (&d)[8], V3 cen, V3 p0, int pass){
+    const int quads[6][4] = { {1,3,7,5}, {0,4,6,2}, {2,6,7,3}, {0,1,5,4}, {4,5,7,6}, {0,2,3,1} };
+    double vol = 0; V3 bc = v3(0,0,0), o = v3(0,0,0); bool have_o = false;
+    for(int f=0;f<6;f++){
+      const int *qd = quads[f];
+      V3 fn = cross(vw[qd[1]]-vw[qd[0]], vw[qd[3]]-vw[qd[0]]);
+      const double nn = norm(fn); if( nn == 0 ) continue;
+      fn = (1.0/nn)*fn;
+      if( dot(fn, vw[qd[0]]-cen) < 0 ) fn = -fn;
+      for(int tr=0;tr<2;tr++){
+        const int id[3] = { qd[0], qd[1+tr], qd[2+tr] };
+        V3 poly[4]; bool onp[4]; int np = 0;
+        for(int i=0;i<3;i++){
+          const int a = id[i], b = id[(i+1)%3];
+          if( d[a] <= 0 ){ poly[np] = vw[a]; onp[np] = d[a] == 0; np++; }
+          if( (d[a] < 0 && d[b] > 0) || (d[a] > 0 && d[b] < 0) ){
+            const double tt = d[a]/(d[a]-d[b]);
+            poly[np] = vw[a] + tt*(vw[b]-vw[a]); onp[np] = true; np++;
+          }
+        }
+        if( np < 3 ) continue;
+        /* pass 1: the boundary segment of the cut polygon carried by this clipped triangle closes the loop below as
+         * one more triangle (o, segment) of the cut polygon, o = the first cut point found */
+        int n_on = 0, i0 = 0, i1 = 0;
+        for(int i=0;i<np;i++) if( onp[i] ){ if( n_on == 0 ) i0 = i; else i1 = i; n_on++; }
+        const bool seg = pass == 1 && n_on == 2;
+        if( seg && !have_o ){ o = poly[i0]; have_o = true; }
+        const V3 sa = poly[i0], sb = poly[i1];
+        for(int i=1;i+1<np+(seg?1:0);i++){
+          V3 a = i+1 < np ? poly[0] : o, b = i+1 < np ? poly[i] : sa, c2 = i+1 < np ? poly[i+1] : sb;
+          if( pass == 0 ){
+            if( dot(cross(b-a, c2-a), fn) < 0 ){ const V3 t = b; b = c2; c2 = t; }
+            const V3 ra = a-p0, rb = b-p0, rc = c2-p0;
+            const double v6 = dot(ra, cross(rb, rc))/6.0;
+            vol += v6; bc = bc + (0.25*v6)*(ra+rb+rc);
+          } else vol_tri(vp, a, b, c2, i+1 < np ? fn : vp.norm);
+        }
+      }
+    }
+    if( pass == 0 ){
+      if( !(vol > 1.0e-18) ) return false;
+      vp.center = p0 + (1.0/vol)*bc;
+    }
+    return true;
+  }
+
+  /* acceleration response (frame of link Lt) of link Lt to the bias change (dpf, dpn) on link Lc of the same tree
+   * ([EXT A-5]; probe_link with a separate target) */
+  RKFD_VOL_NI void vol_probe(const ModelDev &m, int Lc, V3 dpf, V3 dpn, int Lt, V3 &ral, V3 &raa){
+    if( Lt == Lc ){ probe_link(m, Lc, dpf, dpn, ral, raa); return; }
+    double du[6*MAX_LINKS]; int pth[MAX_LINKS]; int np = 0;
+    for(int i=Lc;;){
+      const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = Spec::jtype(i,L);
+      pth[np] = i;
+      V3 paf = dpf, pan = dpn;
+      for(int k=0;k<6;k++) du[6*np+k] = 0.0;
+      switch(jt){
+      case J_REVOL: case J_PRISM: {
+        const double d = jt == J_REVOL ? -dpn.z : -dpf.z;
+        du[6*np] = d;
+        const double k = Q(Spec::sc(i,L)+2)*d;
+        paf = dpf + k*ld3(sl); pan = dpn + k*ld3(sl+3);
+      } break;
+      case J_SPHER: {
+        const M3 E = tmm(ldm(sl+27), org_R(L));
+        const V3 d = -tmul(E, dpn);
+        du[6*np] = d.x; du[6*np+1] = d.y; du[6*np+2] = d.z;
+        const V3 k = mul(lds(sl+18), d);
+        paf = dpf + mul(ldm(sl), k); pan = dpn + mul(ldm(sl+9), k);
+      } break;
+      case J_FLOAT: du[6*np]=dpf.x; du[6*np+1]=dpf.y; du[6*np+2]=dpf.z; du[6*np+3]=dpn.x; du[6*np+4]=dpn.y; du[6*np+5]=dpn.z; break;
+      default: break;
+      }
+      np++;
+      if( Spec::parent(i,L) < 0 || jt == J_FLOAT ) break;
+      V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
+      dpf = xf_mul(x, paf); dpn = xf_mul(x, pan) + cross(x.p, dpf);
+      i = Spec::parent(i,L);
+    }
+    int pt[MAX_LINKS]; int nt = 0;
+    for(int i=Lt;;){ const LinkDev &L = m.link[i]; pt[nt++] = i; if( Spec::parent(i,L) < 0 || Spec::jtype(i,L) == J_FLOAT ) break; i = Spec::parent(i,L); }
+    V3 al = v3(0,0,0), aa = v3(0,0,0);
+    for(int q=nt-1;q>=0;q--){
+      const int i = pt[q]; const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = Spec::jtype(i,L);
+      double d[6] = {0,0,0,0,0,0};
+      for(int k=0;k<np;k++) if( pth[k] == i ) for(int r=0;r<6;r++) d[r] = du[6*k+r];
+      V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
+      V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
+      switch(jt){
+      case J_REVOL: case J_PRISM: {
+        const double acc = Q(Spec::sc(i,L)+2)*( d[0] - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
+        if( jt == J_REVOL ) xa.z += acc; else xl.z += acc;
+      } break;
+      case J_SPHER: {
+        const V3 rhs = v3(d[0],d[1],d[2]) - (tmul(ldm(sl), xl) + tmul(ldm(sl+9), xa));
+        xa = xa + mul(tmm(ldm(sl+27), org_R(L)), mul(lds(sl+18), rhs));
+      } break;
+      case J_FLOAT: {   /* da = -IA^-1 dp */
+        double r[6] = {0,0,0,0,0,0}; int k = 0;
+        for(int a=0;a<6;a++) for(int b=a;b<6;b++){ const double iv = c.S(sl+18+k); r[a] -= iv*d[b]; if( b != a ) r[b] -= iv*d[a]; k++; }
+        xl = v3(r[0],r[1],r[2]); xa = v3(r[3],r[4],r[5]);
+      } break;
+      default: break;
+      }
+      al = xl; aa = xa;
+    }
+    ral = al; raa = aa;
+  }
+
+  /* x = pinv(S) rhs for a symmetric ma x ma matrix (stride VOL_M) by cyclic Jacobi; eigenvalue cut-off as the oracle's */
+  static RKFD_VOL_NI void vol_pinv_solve(int ma, double *S, const double *rhs, double *x){
+    double V[VOL_M*VOL_M];
+    for(int i=0;i<ma;i++) for(int j=0;j<ma;j++) V[VOL_M*i+j] = i == j ? 1.0 : 0.0;
+    for(int sweep=0;sweep<60;sweep++){
+      double off = 0; for(int i=0;i<ma;i++) for(int j=i+1;j<ma;j++) off += S[VOL_M*i+j]*S[VOL_M*i+j];
+      if( off < 1e-300 ) break;
+      for(int i=0;i<ma;i++) for(int j=i+1;j<ma;j++){
+        const double apq = S[VOL_M*i+j];
+        if( fabs(apq) < 1e-300 ) continue;
+        const double th = (S[VOL_M*j+j]-S[VOL_M*i+i])/(2.0*apq);
+        const double t = (th >= 0 ? 1.0 : -1.0)/(fabs(th)+sqrt(th*th+1.0)), cs = 1.0/sqrt(t*t+1.0), sn = t*cs;
+        for(int k=0;k<ma;k++){ const double akp = S[VOL_M*k+i], akq = S[VOL_M*k+j]; S[VOL_M*k+i] = cs*akp-sn*akq; S[VOL_M*k+j] = sn*akp+cs*akq; }
+        for(int k=0;k<ma;k++){ const double apk = S[VOL_M*i+k], aqk = S[VOL_M*j+k]; S[VOL_M*i+k] = cs*apk-sn*aqk; S[VOL_M*j+k] = sn*apk+cs*aqk; }
+        for(int k=0;k<ma;k++){ const double vkp = V[VOL_M*k+i], vkq = V[VOL_M*k+j]; V[VOL_M*k+i] = cs*vkp-sn*vkq; V[VOL_M*k+j] = sn*vkp+cs*vkq; }
+      }
+    }
+    double lmax = 0; for(int i=0;i<ma;i++) if( fabs(S[VOL_M*i+i]) > lmax ) lmax = fabs(S[VOL_M*i+i]);
+    for(int i=0;i<ma;i++) x[i] = 0;
+    for(int k=0;k<ma;k++){
+      const double lam = S[VOL_M*k+k]; if( fabs(lam) <= 1.0e-11*lmax ) continue;
+      double s = 0; for(int i=0;i<ma;i++) s += V[VOL_M*i+k]*rhs[i];
+      s /= lam;
+      for(int i=0;i<ma;i++) x[i] += s*V[VOL_M*i+k];
+    }
+  }
+
+  /* rkFDQPSolveASM (rkfd_opt_qp.c:43-181) on dense data: min 1/2 x^T Q x + c^T x  s.t.  A x >= 0 (m rows, stride
+   * VOL_N).  Q is positive definite (relaxation L > 0 on its diagonal): Qi = Q^-1 once; per iteration
+   * S lambda = Aw Qi c, x* = Qi (Aw^T lambda - c).  x holds the initial point on entry.  idx: active flags. */
+  RKFD_VOL_NI void vol_asm(int n, int mrows, const double *Qm, const double *cv, const double *A, double *x, unsigned &idx_out){
+    const int QP_HIST = 32, QP_MAXIT = 256;
+    double Qi[VOL_N*VOL_N], qc[VOL_N];
+    { /* Cholesky Q = G G^T, Qi = G^-T G^-1 */
+      double G[VOL_N*VOL_N];
+      for(int i=0;i<n;i++) for(int j=0;j<=i;j++){
+        double s = Qm[VOL_N*i+j]; for(int k=0;k<j;k++) s -= G[VOL_N*i+k]*G[VOL_N*j+k];
+        if( i == j ){ if( !(s > 0) ){ bad |= 2; s = 1.0; } G[VOL_N*i+i] = sqrt(s); } else G[VOL_N*i+j] = s/G[VOL_N*j+j];
+      }
+      for(int col=0;col<n;col++){
+        double y[VOL_N];
+        for(int i=0;i<n;i++){ double s = i == col ? 1.0 : 0.0; for(int k=0;k<i;k++) s -= G[VOL_N*i+k]*y[k]; y[i] = s/G[VOL_N*i+i]; }
+        for(int i=n-1;i>=0;i--){ double s = y[i]; for(int k=i+1;k<n;k++) s -= G[VOL_N*k+i]*y[k]; y[i] = s/G[VOL_N*i+i]; }
+        for(int i=0;i<n;i++) Qi[VOL_N*i+col] = y[i];
+      }
+    }
+    for(int i=0;i<n;i++){ double s = 0; for(int j=0;j<n;j++) s += Qi[VOL_N*i+j]*cv[j]; qc[i] = s; }
+    unsigned idx = 0;
+    for(int i=0;i<mrows;i++){ double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*i+j]*x[j]; if( fabs(s) < ZTOL ) idx |= 1u << i; }
+    unsigned hist_idx[QP_HIST]; double hist_obj[QP_HIST]; int nhist = 0;
+    for(int iter=0; iter<QP_MAXIT; iter++){
+      int act[VOL_M]; int ma = 0;
+      for(int i=0;i<mrows;i++) if( idx >> i & 1u ) act[ma++] = i;
+      double xs[VOL_N], lam[VOL_M];
+      if( ma > 0 ){
+        double Y[VOL_N*VOL_M], S[VOL_M*VOL_M], rhs[VOL_M];     /* Y = Qi Aw^T (n x ma) */
+        for(int i=0;i<n;i++) for(int k=0;k<ma;k++){ double s = 0; for(int j=0;j<n;j++) s += Qi[VOL_N*i+j]*A[VOL_N*act[k]+j]; Y[VOL_M*i+k] = s; }
+        for(int a=0;a<ma;a++){
+          for(int b=0;b<ma;b++){ double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*act[a]+j]*Y[VOL_M*j+b]; S[VOL_M*a+b] = s; }
+          double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*act[a]+j]*qc[j]; rhs[a] = s;
+        }
+        /* Cholesky of S; dependent active rows -> pseudo-inverse */
+        bool spd = true; double G[VOL_M*VOL_M]; double smax = 0;
+        for(int a=0;a<ma;a++) if( S[VOL_M*a+a] > smax ) smax = S[VOL_M*a+a];
+        for(int i=0;i<ma && spd;i++) for(int j=0;j<=i;j++){
+          double s = S[VOL_M*i+j]; for(int k=0;k<j;k++) s -= G[VOL_M*i+k]*G[VOL_M*j+k];
+          if( i == j ){ if( !(s > 1.0e-10*smax) ){ spd = false; break; } G[VOL_M*i+i] = sqrt(s); } else G[VOL_M*i+j] = s/G[VOL_M*j+j];
+        }
+        if( spd ){
+          for(int i=0;i<ma;i++){ double s = rhs[i]; for(int k=0;k<i;k++) s -= G[VOL_M*i+k]*lam[k]; lam[i] = s/G[VOL_M*i+i]; }
+          for(int i=ma-1;i>=0;i--){ double s = lam[i]; for(int k=i+1;k<ma;k++) s -= G[VOL_M*k+i]*lam[k]; lam[i] = s/G[VOL_M*i+i]; }
+        } else vol_pinv_solve(ma, S, rhs, lam);
+        for(int i=0;i<n;i++){ double s = -qc[i]; for(int k=0;k<ma;k++) s += Y[VOL_M*i+k]*lam[k]; xs[i] = s; }
+      } else for(int i=0;i<n;i++) xs[i] = -qc[i];
+      bool stepped = false;
+      for(int i=0;i<n;i++) if( !(fabs(xs[i]-x[i]) < ZTOL) ){ stepped = true; break; }
+      if( !stepped ){
+        for(int i=0;i<n;i++) x[i] = xs[i];
+        bool neg = false; for(int k=0;k<ma;k++) if( lam[k] < 0 ){ neg = true; break; }
+        if( !neg ) break;
+        double lmin = lam[0]; for(int k=1;k<ma;k++) if( lam[k] < lmin ) lmin = lam[k];
+        for(int k=0;k<ma;k++) if( fabs(lam[k]-lmin) < 1.0e-8 ) idx &= ~(1u << act[k]);
+        continue;
+      }
+      double alpha = 1.0;
+      for(int i=0;i<mrows;i++){
+        if( idx >> i & 1u ) continue;
+        double ad = 0, ax = 0; for(int j=0;j<n;j++){ ad += A[VOL_N*i+j]*(xs[j]-x[j]); ax += A[VOL_N*i+j]*x[j]; }
+        if( ad < 0 ){ const double t = (0.0 - ax)/ad; if( t < alpha ) alpha = t; }
+      }
+      for(int i=0;i<n;i++) x[i] += alpha*(xs[i]-x[i]);
+      for(int i=0;i<mrows;i++){
+        if( idx >> i & 1u ) continue;
+        double ax = 0; for(int j=0;j<n;j++) ax += A[VOL_N*i+j]*x[j];
+        if( fabs(ax) < ZTOL ) idx |= 1u << i;
+      }
+      double objv = 0;
+      for(int i=0;i<n;i++){ double s = 0; for(int j=0;j<n;j++) s += Qm[VOL_N*i+j]*x[j]; objv += 0.5*x[i]*s + cv[i]*x[i]; }
+      bool endflag = false;
+      for(int h=0;h<nhist && !endflag;h++) if( hist_idx[h] == idx && !(fabs(hist_obj[h]/objv - 1.0) > 1.0e-8) ) endflag = true;
+      if( endflag ) break;
+      if( nhist < QP_HIST ){ hist_idx[nhist] = idx; hist_obj[nhist] = objv; nhist++; }
+      if( iter == QP_MAXIT-1 ) bad |= 2;
+    }
+    idx_out = idx;
+  }
+
+  /* [EXT A-16] min cost^T x  s.t.  A x = b, x >= 0: two-phase tableau simplex, Bland's rule (cost == nullptr:
+   * feasibility only).  A: mr x nc with stride VOL_LPN.  Same pivoting rules and tolerances as the oracle's vol_lp. */
+  static RKFD_VOL_NI bool vol_lp(int mr, int nc, const double *A, const double *b, const double *cost_in, double *x){
+    const int nt = nc + mr; double T[6*VOL_LPS]; int basis[6]; double bmax = 0;
+    for(int i=0;i<mr;i++){ const double sg = b[i] < 0 ? -1.0 : 1.0;
+      for(int j=0;j<nc;j++) T[VOL_LPS*i+j] = sg*A[VOL_LPN*i+j];
+      for(int j=0;j<mr;j++) T[VOL_LPS*i+nc+j] = i == j ? 1.0 : 0.0;
+      T[VOL_LPS*i+nt] = sg*b[i]; basis[i] = nc+i; if( fabs(b[i]) > bmax ) bmax = fabs(b[i]); }
+    const double eps = 1.0e-10*(1.0+bmax);
+    bool ok = true;
+    for(int phase=1;phase<=2 && ok;phase++){
+      const int ncol = phase == 1 ? nt : nc;
+      if( phase == 2 && !cost_in ) break;
+      for(int it=0;it<20000;it++){
+        int enter = -1, leave = -1; double best = 0;
+        for(int j=0;j<ncol && enter<0;j++){
+          double rc = phase == 1 ? ( j >= nc ? 1.0 : 0.0 ) : cost_in[j]; bool bas = false;
+          for(int i=0;i<mr;i++){ if( basis[i] == j ) bas = true;
+            const double cb = phase == 1 ? ( basis[i] >= nc ? 1.0 : 0.0 ) : ( basis[i] < nc ? cost_in[basis[i]] : 0.0 );
+            rc -= cb*T[VOL_LPS*i+j]; }
+          if( !bas && rc < -1.0e-11 ) enter = j;
+        }
+        if( enter < 0 ) break;
+        for(int i=0;i<mr;i++){ const double a = T[VOL_LPS*i+enter];
+          if( a > 1.0e-11 ){ const double ratio = T[VOL_LPS*i+nt]/a;
+            if( leave < 0 || ratio < best - 1.0e-13 || ( fabs(ratio-best) <= 1.0e-13 && basis[i] < basis[leave] ) ){ leave = i; best = ratio; } } }
+        if( leave < 0 ){ ok = false; break; }
+        const double pv = T[VOL_LPS*leave+enter];
+        for(int j=0;j<=nt;j++) T[VOL_LPS*leave+j] /= pv;
+        for(int r=0;r<mr;r++) if( r != leave ){ const double fct = T[VOL_LPS*r+enter]; if( fct != 0 ) for(int j=0;j<=nt;j++) T[VOL_LPS*r+j] -= fct*T[VOL_LPS*leave+j]; }
+        basis[leave] = enter;
+      }
+      if( phase == 1 ){
+        double art = 0;
+        for(int i=0;i<mr;i++) if( basis[i] >= nc ) art += T[VOL_LPS*i+nt];
+        if( art > eps ) ok = false;
+        else for(int i=0;i<mr;i++) if( basis[i] >= nc ){
+          int j = 0; for(;j<nc;j++) if( fabs(T[VOL_LPS*i+j]) > 1.0e-9 ) break;
+          if( j < nc ){ const double pv = T[VOL_LPS*i+j];
+            for(int jj=0;jj<=nt;jj++) T[VOL_LPS*i+jj] /= pv;
+            for(int r=0;r<mr;r++) if( r != i ){ const double fct = T[VOL_LPS*r+j]; if( fct != 0 ) for(int jj=0;jj<=nt;jj++) T[VOL_LPS*r+jj] -= fct*T[VOL_LPS*i+jj]; }
+            basis[i] = j; }
+        }
+      }
+    }
+    if( ok && x ){ for(int j=0;j<nc;j++) x[j] = 0; for(int i=0;i<mr;i++) if( basis[i] < nc ) x[basis[i]] = T[VOL_LPS*i+nt]; }
+    return ok;
+  }
+
+  RKFD_HD V3 vol_point_vel(const VolPair &vp, V3 p){     /* rkFDLinkPointWldVel (rkfd_util.c:14-24), static partner */
+    const M3 Rw = ldm(vp.fsl); const V3 pw = ld3(vp.fsl+9), vl = ld3(vp.fsl+12), om = ld3(vp.fsl+15);
+    return mul(Rw, vl) + cross(mul(Rw, om), p - pw);
+  }
+
+  /* _rkFDSolverVolume (rkfd_volume.c:939-957) for this lane's environment */
+  RKFD_VOL_NI void rigid_volume(const ModelDev &m, bool ref){
+    const unsigned long long fl = cfl;
+    if( RKFD_POPC64(fl & m.rigid_mask) == 0 ) return;
+    VolPair vp[VOL_P]; int P = 0;
+    /* ---- contact volumes (rkFDSolverColChk_Volume, [EXT A-15]) */
+    for(int pi=0;pi<m.npair;pi++){
+      const PairDev &pr = m.pair[pi]; if( pr.type != C_RIGID ) continue;
+      const CellDev &cl = m.cell[pr.cell]; if( cl.nvert != 8 ) continue;
+      int k0 = -1; for(int k=0;k<8;k++) if( fl >> (2*(pr.sofs+k)) & 1ull ){ k0 = k; break; }
+      if( k0 < 0 ) continue;
+      if( P >= VOL_P ){ bad |= 4; break; }
+      VolPair &v = vp[P];
+      const LinkDev &L = m.link[cl.link]; const BoxDev &bx = m.box[pr.box];
+      v.pair = pi; v.link = cl.link; v.fsl = Spec::frame_slot(cl.link, L); v.wsl = Spec::wext_slot(cl.link, L); v.npl = 0; v.sofs = pr.sofs;
+      v.K = pr.K; v.L = pr.L; v.SF = pr.SF; v.KF = pr.KF;
+      const M3 Rw = ldm(v.fsl); const V3 pw = ld3(v.fsl+9);
+      const M3 Rb = box_R(bx); const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
+      V3 vw[8], cen = v3(0,0,0); double d[8];
+      for(int k=0;k<8;k++){ const int vi = cl.vofs + k; vw[k] = pw + mul(Rw, v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2])); cen = cen + 0.125*vw[k]; }
+      V3 prob;
+      { const V3 vb = tmul(Rb, vw[k0] - pb);
+        box_face(bx, Rb, vb, bx.half[0]-fabs(vb.x), bx.half[1]-fabs(vb.y), bx.half[2]-fabs(vb.z), v.norm, v.a1, v.a2, prob); }
+      const V3 p0 = pb + mul(Rb, prob);
+      for(int k=0;k<8;k++){ d[k] = dot(v.norm, vw[k] - p0); if( fabs(d[k]) <= ZTOL ) d[k] = 0.0; }
+      for(int i=0;i<36;i++) v.q6[i] = 0.0;
+      for(int i=0;i<6;i++){ v.c6[i] = 0.0; v.w[i] = 0.0; }
+      bool empty = false;
+#pragma unroll 1
+      for(int pass=0; pass<2 && !empty; pass++) empty = !vol_clip(v, vw, d, cen, p0, pass);
+      if( empty ) continue;
+      /* rkCDPlaneListQuickSort with __rk_fd_plane_cmp (:376-395): ascending angle key, ties keep their order */
+      { double th[VOL_PL];
+        for(int i=0;i<v.npl;i++){ const V3 t = cross(v.a1, v.pln[i]); th[i] = dot(t, v.norm) > 0 ? atan2(-norm(t), dot(v.a1, v.pln[i])) : atan2(norm(t), dot(v.a1, v.pln[i])); }
+        for(int i=1;i<v.npl;i++){ const V3 tv = v.plv[i], tn = v.pln[i]; const double a = th[i]; int j = i-1;
+          for(;j>=0 && !(fabs(th[j]-a) < ZTOL) && th[j] > a;j--){ v.plv[j+1] = v.plv[j]; v.pln[j+1] = v.pln[j]; th[j+1] = th[j]; }
+          v.plv[j+1] = tv; v.pln[j+1] = tn; th[j+1] = a; } }
+      P++;
+    }
+    if( P == 0 ) return;
+    const int n = 6*P;
+    /* ---- A (6P x 6P), b: probes at the volume centres (rkfd_volume.c:141-226) */
+    double A[VOL_N*VOL_N], b[VOL_N];
+    for(int k=0;k<P;k++){
+      const VolPair &v = vp[k];
+      const M3 Rw = ldm(v.fsl); const V3 pw = ld3(v.fsl+9), vl = ld3(v.fsl+12), om = ld3(v.fsl+15), al = ld3(v.fsl+18), aa = ld3(v.fsl+21);
+      const V3 r = tmul(Rw, v.center - pw);
+      const V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r))), acca = mul(Rw, aa);
+      const V3 velp = mul(Rw, vl) + cross(mul(Rw, om), v.center - pw), vela = mul(Rw, om);
+      b[6*k] = accp.x*m.dt + velp.x; b[6*k+1] = accp.y*m.dt + velp.y; b[6*k+2] = accp.z*m.dt + velp.z;
+      b[6*k+3] = acca.x*m.dt + vela.x; b[6*k+4] = acca.y*m.dt + vela.y; b[6*k+5] = acca.z*m.dt + vela.z;
+    }
+    for(int k=0;k<P;k++){
+      const VolPair &v = vp[k];
+      const M3 Rw = ldm(v.fsl); const V3 pos = tmul(Rw, v.center - ld3(v.fsl+9));
+      int rootk = v.link; while( Spec::parent(rootk, m.link[rootk]) >= 0 ) rootk = Spec::parent(rootk, m.link[rootk]);
+      for(int i=0;i<6;i++){
+        const V3 e = v3(i%3 == 0 ? 1.0 : 0.0, i%3 == 1 ? 1.0 : 0.0, i%3 == 2 ? 1.0 : 0.0);
+        const V3 el = tmul(Rw, e);
+        const V3 dpf = i < 3 ? -el : v3(0,0,0), dpn = i < 3 ? -cross(pos, el) : -el;
+        for(int j=0;j<P;j++){
+          const VolPair &u = vp[j];
+          int rootj = u.link; while( Spec::parent(rootj, m.link[rootj]) >= 0 ) rootj = Spec::parent(rootj, m.link[rootj]);
+          V3 rl = v3(0,0,0), ra = v3(0,0,0);
+          if( rootj == rootk ){
+            V3 ral, raa; vol_probe(m, v.link, dpf, dpn, u.link, ral, raa);
+            const M3 Ru = ldm(u.fsl); const V3 ru = tmul(Ru, u.center - ld3(u.fsl+9));
+            rl = mul(Ru, ral + cross(raa, ru)); ra = mul(Ru, raa);
+          }
+          A[VOL_N*(6*j)+6*k+i] = rl.x; A[VOL_N*(6*j+1)+6*k+i] = rl.y; A[VOL_N*(6*j+2)+6*k+i] = rl.z;
+          A[VOL_N*(6*j+3)+6*k+i] = ra.x; A[VOL_N*(6*j+4)+6*k+i] = ra.y; A[VOL_N*(6*j+5)+6*k+i] = ra.z;
+        }
+      }
+    }
+    /* ---- QP (rkfd_volume.c:496-548) */
+    double Qm[VOL_N*VOL_N], cv[VOL_N], nf[VOL_M*VOL_N], x[VOL_N];
+    for(int i=0;i<n;i++){ cv[i] = 0.0; x[i] = 0.0; for(int j=0;j<n;j++) Qm[VOL_N*i+j] = 0.0; }
+    for(int k=0;k<P;k++){
+      const VolPair &v = vp[k];
+      double T[6*VOL_N];       /* T = Q6 A_k (6 x n) */
+      for(int i=0;i<6;i++) for(int s=0;s<n;s++){ double t = 0; for(int j=0;j<6;j++) t += v.q6[6*i+j]*A[VOL_N*(6*k+j)+s]; T[VOL_N*i+s] = t; }
+      for(int r=0;r<n;r++) for(int s=0;s<n;s++){ double t = 0; for(int i=0;i<6;i++) t += A[VOL_N*(6*k+i)+r]*T[VOL_N*i+s]; Qm[VOL_N*r+s] += t; }
+      for(int i=0;i<6;i++){ double t = v.c6[i]; for(int j=0;j<6;j++) t += v.q6[6*i+j]*b[6*k+j];
+        for(int r=0;r<n;r++) cv[r] += t*A[VOL_N*(6*k+i)+r]; }
+    }
+    for(int k=0;k<P;k++) for(int i=0;i<6;i++) Qm[VOL_N*(6*k+i)+6*k+i] += vp[k].L;
+    int mrows = 0;
+    for(int k=0;k<P;k++){
+      const VolPair &v = vp[k];
+      for(int j=0;j<n;j++) nf[VOL_N*mrows+j] = 0.0;
+      nf[VOL_N*mrows+6*k] = v.norm.x; nf[VOL_N*mrows+6*k+1] = v.norm.y; nf[VOL_N*mrows+6*k+2] = v.norm.z;
+      mrows++;
+      for(int i=0;i<v.npl;i++){
+        const double a = -dot(v.pln[i], v.plv[i]), b1 = dot(v.pln[i], v.a2), b2 = -dot(v.pln[i], v.a1);
+        for(int j=0;j<n;j++) nf[VOL_N*mrows+j] = 0.0;
+        const V3 f = a*v.norm, t = b1*v.a1 + b2*v.a2;
+        nf[VOL_N*mrows+6*k] = f.x; nf[VOL_N*mrows+6*k+1] = f.y; nf[VOL_N*mrows+6*k+2] = f.z;
+        nf[VOL_N*mrows+6*k+3] = t.x; nf[VOL_N*mrows+6*k+4] = t.y; nf[VOL_N*mrows+6*k+5] = t.z;
+        mrows++;
+      }
+      x[6*k] = v.norm.x; x[6*k+1] = v.norm.y; x[6*k+2] = v.norm.z;
+    }
+    unsigned idx = 0;
+    vol_asm(n, mrows, Qm, cv, nf, x, idx);
+    /* ---- f /= dt, _rkFDSolverSetForce (:552-568; the offset is not advanced for a pair without planes - mirrored) */
+    { int off = 0;
+      for(int k=0;k<P;k++){ VolPair &v = vp[k];
+        if( v.npl == 0 ){ for(int i=0;i<6;i++) v.w[i] = 0.0; continue; }
+        for(int i=0;i<6;i++) v.w[i] = x[off+i]/m.dt;
+        const V3 f = v3(v.w[0],v.w[1],v.w[2]);
+        if( ( vtiny(f.x) && vtiny(f.y) && vtiny(f.z) ) || dot(f, v.norm) < ZTOL ) for(int i=0;i<6;i++) v.w[i] = 0.0;
+        off += 6; } }
+    unsigned long long nfl = fl;
+    for(int k=0;k<P;k++){
+      VolPair &v = vp[k]; const int np = v.npl;
+      V3 wf = v3(v.w[0],v.w[1],v.w[2]), wt = v3(v.w[3],v.w[4],v.w[5]);
+      /* ---- _rkFDSolverModifyNormalForceCenter (:580-631) */
+      { const double fn = dot(v.norm, wf);
+        if( !(fn < ZTOL) && np >= 3 ){
+          const V3 r0 = (-dot(v.a2, wt)/fn)*v.a1 + (dot(v.a1, wt)/fn)*v.a2;
+          bool flag = false; int i0 = np-3, i1 = np-2, i2 = np-1, i3 = 0;
+          for(int it=0; it<np; it++, i0=i1, i1=i2, i2=i3, i3=i3+1){
+            const V3 dir = v.plv[i2] - v.plv[i1]; const double d = dot(dir, dir);
+            if( vtiny(d) ) continue;
+            const V3 tmp = r0 - v.plv[i1];
+            if( dot(tmp, v.pln[i1]) > ZTOL ) continue;
+            const double s = dot(dir, tmp)/d;
+            V3 r; int mod;
+            if( s < ZTOL ){
+              if( flag ) break;
+              const V3 t2 = (v.plv[i0] - v.plv[i1]) + dir;
+              r = v.plv[i1] + (ZTOL/norm(t2))*t2; mod = 1;
+            } else if( s < 1.0-ZTOL ){
+              r = v.plv[i1] + s*dir + ZTOL*v.pln[i1]; mod = 1;
+            } else {
+              const V3 t2 = (v.plv[i3 < np ? i3 : 0] - v.plv[i2]) - dir;
+              r = v.plv[i2] + (ZTOL/norm(t2))*t2; mod = 2;
+            }
+            wt = dot(v.norm, wt)*v.norm + (fn*dot(v.a2, r))*v.a1 + (-fn*dot(v.a1, r))*v.a2;
+            if( mod == 1 ) break;
+            flag = true;
+          }
+        } }
+      /* ---- _rkFDSolverModifyWrench (:869-916) */
+      if( np > 0 && !vtiny(dot(wf, v.norm)) ){
+        double wv[6] = { dot(wf, v.norm), dot(wf, v.a1), dot(wf, v.a2), dot(wt, v.norm), dot(wt, v.a1), dot(wt, v.a2) };
+        const double fn = wv[0], fs = sqrt(wv[1]*wv[1] + wv[2]*wv[2]);
+        double tl = 0;
+        for(int i=0;i<np;i++){ v.r[i][0] = dot(v.plv[i], v.a1); v.r[i][1] = dot(v.plv[i], v.a2);
+          const double rl = sqrt(v.r[i][0]*v.r[i][0] + v.r[i][1]*v.r[i][1]); if( tl < rl ) tl = rl; }
+        int kinetic = 0; bool setforce = false;
+        if( vtiny(tl) ){
+          wv[3] = wv[4] = wv[5] = 0;
+          if( !vtiny(fs) && fs > v.SF*fn ){
+            V3 vel = vol_point_vel(v, v.center); vel = vel - dot(v.norm, vel)*v.norm;
+            const double nv = norm(vel);
+            if( vtiny(nv) ){ wv[1] = 0; wv[2] = 0; }
+            else { const double t = (1.0 - exp(-1.0*m.friction_weight*nv))*v.KF*wv[0]/nv; wv[1] = -t*dot(vel, v.a1); wv[2] = -t*dot(vel, v.a2); }
+            kinetic = 1;
+          }
+          setforce = true;
+        } else if( ( !vtiny(fs) && fs > v.SF*fn ) || fabs(wv[3]) > tl*wv[0] ){
+          kinetic = 2;
+        } else {
+          /* static friction: the wrench inside the friction pyramids at the polygon corners? (:643-688) */
+          const int pyr = m.pyramid, fnum = pyr*np;
+          if( fnum > VOL_LPN ){ bad |= 4; }
+          else {
+            double ma[6*VOL_LPN], mb[6];
+            for(int j=0;j<np;j++) for(int i=0;i<pyr;i++){ const int cc = pyr*j+i;
+              const double sn = sin(6.283185307179586/pyr*i), cs = cos(6.283185307179586/pyr*i);
+              ma[cc] = 1.0; ma[VOL_LPN+cc] = v.r[j][1]; ma[2*VOL_LPN+cc] = -v.r[j][0];
+              ma[3*VOL_LPN+cc] = v.SF*cs; ma[4*VOL_LPN+cc] = v.SF*sn;
+              ma[5*VOL_LPN+cc] = -( ma[2*VOL_LPN+cc]*ma[4*VOL_LPN+cc] + ma[VOL_LPN+cc]*ma[3*VOL_LPN+cc] ); }
+            mb[0] = wv[0]; mb[1] = wv[4]; mb[2] = wv[5]; mb[3] = wv[1]; mb[4] = wv[2]; mb[5] = wv[3];
+            if( !vol_lp(6, fnum, ma, mb, nullptr, nullptr) ) kinetic = 2;
+          }
+        }
+        if( kinetic == 2 ){
+          /* kinetic friction: normal force redistributed over the polygon corners by an LP (:733-843) */
+          double ma[3*VOL_LPN], mb[3], mc[VOL_PL], mf[VOL_PL], wn[3];
+          for(int j=0;j<np;j++){ ma[j] = 1.0; ma[VOL_LPN+j] = v.r[j][1]; ma[2*VOL_LPN+j] = -v.r[j][0]; mf[j] = 0.0; }
+          mb[0] = wv[0]; mb[1] = wv[4]; mb[2] = wv[5];
+          for(int i=0;i<3;i++) wn[i] = vtiny(wv[i+1]) ? 0.0 : 1.0/wv[i+1];
+          for(int j=0;j<np;j++){
+            V3 vel = vol_point_vel(v, v.center + v.plv[j]); vel = vel - dot(v.norm, vel)*v.norm;
+            const double nv = norm(vel);
+            if( vtiny(nv) ){ v.s[j][0] = 0; v.s[j][1] = 0; }
+            else { const double ww = (1.0 - exp(-1.0*m.friction_weight*nv))*v.KF/nv; v.s[j][0] = -ww*dot(vel, v.a1); v.s[j][1] = -ww*dot(vel, v.a2); }
+            mc[j] = -wn[0]*v.s[j][0] - wn[1]*v.s[j][1] - wn[2]*( v.r[j][0]*v.s[j][1] - v.r[j][1]*v.s[j][0] );
+          }
+          if( !vol_lp(3, np, ma, mb, mc, mf) ){
+            double wn2[2]; for(int i=0;i<2;i++) wn2[i] = vtiny(wv[i+3]) ? 0.0 : 1.0/wv[i+3];
+            for(int j=0;j<np;j++){ mc[j] += wn2[0]*v.r[j][0] - wn2[1]*v.r[j][1]; mf[j] = 0.0; }
+            vol_lp(1, np, ma, mb, mc, mf);
+          }
+          wv[1] = wv[2] = wv[3] = 0;
+          for(int j=0;j<np;j++){ const double fx = v.s[j][0]*mf[j], fy = v.s[j][1]*mf[j];
+            wv[1] += fx; wv[2] += fy; wv[3] += v.r[j][0]*fy - v.r[j][1]*fx; }
+          setforce = true;
+        }
+        if( ref ){ if( kinetic ) nfl |= 2ull << (2*v.sofs); else nfl &= ~(2ull << (2*v.sofs)); }
+        if( setforce ){ wf = wv[0]*v.norm + wv[1]*v.a1 + wv[2]*v.a2; wt = wv[3]*v.norm + wv[4]*v.a1 + wv[5]*v.a2; }
+      }
+      /* ---- _rkFDSolverPushWrench (:919-936) */
+      { const M3 Rw = ldm(v.fsl); const V3 pos = tmul(Rw, v.center - ld3(v.fsl+9));
+        const V3 fl_ = tmul(Rw, wf), tl_ = tmul(Rw, wt) + cross(pos, fl_);
+        c.S(v.wsl) += fl_.x; c.S(v.wsl+1) += fl_.y; c.S(v.wsl+2) += fl_.z;
+        c.S(v.wsl+3) += tl_.x; c.S(v.wsl+4) += tl_.y; c.S(v.wsl+5) += tl_.z;
+        if( ref ){   /* results of the pair in its first three contact slots: force, torque, centre */
+          const int s = v.sofs;
+          c.gst(c.st.cf,3*s,wf.x); c.gst(c.st.cf,3*s+1,wf.y); c.gst(c.st.cf,3*s+2,wf.z);
+          c.gst(c.st.cf,3*s+3,wt.x); c.gst(c.st.cf,3*s+4,wt.y); c.gst(c.st.cf,3*s+5,wt.z);
+          c.gst(c.st.cf,3*s+6,v.center.x); c.gst(c.st.cf,3*s+7,v.center.y); c.gst(c.st.cf,3*s+8,v.center.z);
+        } }
+    }
+    cfl = nfl;
+  }

@@ -81,7 +81,8 @@ void hostsim_add_box(HostSim *h, int chain, int link, const double *center, doub
 void hostsim_add_contact_info(HostSim *h, int sa, int sb, int type, double K, double L, double E, double V, double SF, double KF)
 { ContactInfoHost c; c.a = "s"+std::to_string(sa); c.b = "s"+std::to_string(sb); c.type = type; c.K=K; c.L=L; c.E=E; c.V=V; c.SF=SF; c.KF=KF; h->world.ci.push_back(c); }
 void hostsim_set_prp(HostSim *h, double dt, int pyramid, double fw, int max_iter, int solver)
-{ h->world.dt = dt; h->world.pyramid = pyramid; h->world.friction_weight = fw; h->world.max_iter = max_iter; h->world.solver = solver; }
+{ h->world.dt = dt; h->world.pyramid = pyramid; h->world.friction_weight = fw; h->world.max_iter = max_iter; h->world.solver = solver;
+  if( solver == S_VOLUME ) h->world.cidef.L = 0.001; }
 void hostsim_set_integrator(HostSim *h, int integrator){ h->world.integrator = integrator; }
 
 /* returns 0 on success */
@@ -137,6 +138,7 @@ void hostsim_get_pivot(HostSim *h, int *type, double *prev)
   const int nq = h->model.nq, B = h->B;
   for(int e=0;e<B;e++) for(int j=0;j<nq;j++){ type[(size_t)e*nq+j] = (h->st.piv_type[e] >> j) & 1u; prev[(size_t)e*nq+j] = h->st.piv_prev[(size_t)j*B+e]; }
 }
+void hostsim_get_status(HostSim *h, int *status){ for(int e=0;e<h->B;e++) status[e] = h->st.status[e]; }
 /* mode 0: nsteps steps; 1: eval; 2: committing eval */
 void hostsim_run(HostSim *h, int mode, int nsteps)
 {

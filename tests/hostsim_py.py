@@ -20,7 +20,7 @@ def lib():
     if _LIB is None:
         so = os.path.join(_SRC, "libhostsim.so")
         deps = [os.path.join(_SRC, "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in
-                                                     ("rkfd_core.cuh", "rkfd_math.cuh", "rkfd_types.h", "rkfd_model.cpp", "rkfd_model.h")]
+                                                     ("rkfd_core.cuh", "rkfd_volume.cuh", "rkfd_math.cuh", "rkfd_types.h", "rkfd_model.cpp", "rkfd_model.h")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-mfma", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-I" + _CSRC,
                                    os.path.join(_SRC, "hostsim.cpp"), os.path.join(_CSRC, "rkfd_model.cpp"), "-o", so])
@@ -42,6 +42,7 @@ def lib():
         L.hostsim_get_state.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.hostsim_get_contact.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
         L.hostsim_get_pivot.argtypes = [C.c_void_p, _ip, _dp]
+        L.hostsim_get_status.argtypes = [C.c_void_p, _ip]
         L.hostsim_run.argtypes = [C.c_void_p, C.c_int, C.c_int]
         _LIB = L
     return _LIB
@@ -112,6 +113,11 @@ class HostSim:
         r, f = np.zeros((self.B, n, 3)), np.zeros((self.B, n, 3))
         lib().hostsim_get_contact(self.h, a.ctypes.data_as(_ip), t.ctypes.data_as(_ip), r.ctypes.data_as(_dp), f.ctypes.data_as(_dp))
         return a, t, r, f
+
+    def get_status(self):
+        st = np.zeros(self.B, np.int32)
+        lib().hostsim_get_status(self.h, st.ctypes.data_as(_ip))
+        return st
 
     def get_pivot(self):
         n = max(self.nq, 1)

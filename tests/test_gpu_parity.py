@@ -525,3 +525,72 @@ def test_general_frame_arm_specialisations(capi, oracle, monkeypatch, nlinks, sp
     n = 24
     oq, oqd, _, _ = oracle.OracleWorld(w).batch_run(q[:n], qd[:n], u[:n], nsteps=15)
     assert relerr(out[1][0][:n], oq) < 1e-9 and relerr(out[1][1][:n], oqd) < 1e-8
+
+
+# ---- Volume solver (rkfd_volume.c, BASELINE config C4): contact volume of a box cell against one face of the static box
+VOLUME_WORLDS = {
+    "box_volume": lambda: ch.World(chains=[ch.box(), ch.floor()], solver="Volume"),
+    "box_volume_ci": lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="Volume"),
+    "c4_biped_volume": lambda: ch.world_c4_volume(),                      # two pairs on one tree: coupled 12 x 12 QP
+    "arm7_volume": lambda: ch.World(chains=[ch.arm7(base_z=0.1, contact_cube=True), ch.floor()], solver="Volume"),
+    "two_box_volume": lambda: ch.World(chains=[ch.box("a"), ch.box("b"), ch.floor()], solver="Volume"),
+}
+
+
+def volume_pose(name, q):
+    B = q.shape[0]
+    if "biped" in name:
+        q[:, 2] = 0.44; q[:, 3:6] *= 0.1; q[:, 6:] *= 0.3
+    if "box" in name:
+        q[:, 2] = np.linspace(0.0, 0.08, B); q[:, 3:6] *= 0.3
+    if "two_box" in name:
+        q[:, 8] = np.linspace(0.07, 0.01, B); q[:, 6] += 2.0
+    return q
+
+
+@pytest.mark.parametrize("name", list(VOLUME_WORLDS))
+def test_volume_evaluation_matches_oracle(capi, oracle, name):
+    """One committing evaluation with the Volume solver on the device: q'' within 1e-9, pair wrenches and volume
+    centres (read back through the contact-force slots of the pair) against the oracle."""
+    w = VOLUME_WORLDS[name]()
+    B = 256
+    q, qd, u = ch.sample_state(w, B, seed=5)
+    q = volume_pose(name, q)
+    fd = gpu_world(capi, w, q, qd, u)
+    _, _, gqdd = fd.batch_get_state()
+    a, t, r, f = fd.batch_get_contact()
+    assert (fd.batch_get_status() == 0).all()
+    ow = oracle.OracleWorld(w)
+    nvol, worst = 0, 0.0
+    for b in range(B):
+        e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
+        ref = e.eval(True)
+        npl, ty, wr, ce = e.volume()
+        worst = max(worst, relerr(gqdd[b], ref))
+        for p in range(len(npl)):
+            if npl[p] <= 0 or not a[b][8 * p:8 * p + 8].any():
+                continue
+            nvol += 1
+            got = f[b][8 * p:8 * p + 3].reshape(-1)
+            assert np.allclose(got[:6], wr[p], rtol=1e-8, atol=1e-8 * max(1.0, np.abs(wr[p]).max())), (name, b, p)
+            assert np.allclose(got[6:9], ce[p], atol=1e-10)
+    print("volume %s: %d contact volumes, max rel err of q'' %.2e" % (name, nvol, worst))
+    assert nvol > 0 and worst < 1e-9
+    fd.destroy()
+
+
+@pytest.mark.parametrize("name", list(VOLUME_WORLDS))
+def test_volume_short_trajectory(capi, oracle, name):
+    w = VOLUME_WORLDS[name]()
+    B, nsteps = 128, 20
+    q, qd, u = ch.sample_state(w, B, seed=9)
+    q = volume_pose(name, q)
+    fd = gpu_world(capi, w, q, qd, u)
+    fd.update_n(nsteps)
+    gq, gqd, _ = fd.batch_get_state()
+    assert (fd.batch_get_status() == 0).all()
+    oq, oqd, _, _ = oracle.OracleWorld(w).batch_run(q, qd, u, nsteps=nsteps)
+    err = np.array([relerr(gq[b], oq[b]) for b in range(B)])
+    print("volume trajectory %s: %d/%d envs within 1e-6 (max %.2e)" % (name, (err < 1e-6).sum(), B, err.max()))
+    assert (err < 1e-6).mean() >= 0.97
+    fd.destroy()

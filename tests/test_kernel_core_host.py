@@ -362,3 +362,68 @@ def test_generic_core_on_tensor_memory_layout(name):
     for a, b in zip(out[0], out[1]):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+# ---- Volume solver (rkfd_volume.c): contact volume of a box cell against one face of the static box
+VOLUME_WORLDS = {
+    "box_volume": lambda: ch.World(chains=[ch.box(), ch.floor()], solver="Volume"),
+    "box_volume_ci": lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="Volume"),
+    "biped_volume": lambda: ch.world_c4_volume(),                         # two pairs on one tree: coupled 12 x 12 QP
+    "arm7_volume": lambda: ch.World(chains=[ch.arm7(base_z=0.1, contact_cube=True), ch.floor()], solver="Volume"),
+    "two_box_volume": lambda: ch.World(chains=[ch.box("a"), ch.box("b"), ch.floor()], solver="Volume"),   # uncoupled pairs
+}
+
+
+def volume_pose(name, q):
+    B = q.shape[0]
+    if "biped" in name:
+        q[:, 2] = 0.44; q[:, 3:6] *= 0.1; q[:, 6:] *= 0.3
+    if "box" in name:
+        q[:, 2] = np.linspace(0.0, 0.08, B); q[:, 3:6] *= 0.3
+    if "two_box" in name:
+        q[:, 8] = np.linspace(0.07, 0.01, B); q[:, 6] += 2.0
+    return q
+
+
+@pytest.mark.parametrize("name", list(VOLUME_WORLDS))
+def test_volume_eval_matches_oracle(oracle, name):
+    """One committing evaluation with the Volume solver: q'', pair wrenches and volume centres."""
+    w = VOLUME_WORLDS[name]()
+    B = 32
+    q, qd, u = ch.sample_state(w, B, seed=5)
+    q = volume_pose(name, q)
+    hs = HostSim(w, B)
+    hs.set_state(q, qd, u); hs.eval(ref=True)
+    _, _, qdd = hs.get_state()
+    a, t, r, f = hs.get_contact()
+    assert (hs.get_status() == 0).all()
+    ow = oracle.OracleWorld(w)
+    sofs = np.cumsum([0] + [8] * 64)
+    nvol = 0
+    for b in range(B):
+        e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
+        ref = e.eval(True)
+        npl, ty, wr, ce = e.volume()
+        assert relerr(qdd[b, :w.nq], ref) < 1e-9, (name, b)
+        for p in range(len(npl)):
+            if npl[p] <= 0 or not a[b][sofs[p]:sofs[p] + 8].any():
+                continue
+            nvol += 1
+            got = f[b][sofs[p]:sofs[p] + 3].reshape(-1)
+            assert np.allclose(got[:6], wr[p], rtol=1e-8, atol=1e-8 * max(1.0, np.abs(wr[p]).max())), (name, b, p)
+            assert np.allclose(got[6:9], ce[p], atol=1e-10)
+    assert nvol > 0
+
+
+@pytest.mark.parametrize("name", list(VOLUME_WORLDS))
+def test_volume_steps_match_oracle(oracle, name):
+    w = VOLUME_WORLDS[name]()
+    B, nsteps = 8, 20
+    q, qd, u = ch.sample_state(w, B, seed=9)
+    q = volume_pose(name, q)
+    hs = HostSim(w, B)
+    hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(nsteps)
+    hq, hqd, _ = hs.get_state()
+    ref = oracle_run(oracle, w, q, qd, u, nsteps)
+    for b in range(B):
+        assert relerr(hq[b, :w.nq], ref[b][0][0]) < 1e-7, (name, b)
