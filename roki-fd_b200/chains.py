@@ -328,6 +328,18 @@ def world_c4_volume():
     return World(chains=[biped(), floor()], solver="Volume")
 
 
+def sample_c4_standing(world, B, seed=20260418):
+    """C4 workload states: the legged tree standing on both soles (trunk 0.512 m +- 2 mm above the floor, joint angles
+    +- 0.05 rad, velocities +- 0.05, motors off: joint friction holds the pose), i.e. both contact volumes live in
+    every environment and every step."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros((B, world.nq)); qd = rng.uniform(-0.05, 0.05, (B, world.nq)); u = np.zeros((B, world.nl))
+    q[:, 2] = 0.512 + rng.uniform(-0.002, 0.002, B)
+    q[:, 3:6] = rng.uniform(-0.02, 0.02, (B, 3))
+    q[:, 6:] = rng.uniform(-0.05, 0.05, (B, world.nq - 6))
+    return q, qd, u
+
+
 def sample_state(world, B, seed=20260418):
     """Synthetic randomised states of SURVEY.md section 8d: q ~ U(-pi/2, pi/2), qd ~ U(-1, 1),
     motor voltage ~ U(-6, 6); float joints get position z lifted by +0.3."""

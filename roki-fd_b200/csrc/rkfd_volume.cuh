@@ -21,12 +21,17 @@
  * Limits: VOL_P pairs in contact per environment, VOL_PL polygon planes per pair, pyramid * planes <= VOL_LPN
  * (status bit 2 is raised otherwise and the surplus is ignored). */
 
+#ifdef RKFD_VOL_STATS      /* host harness only: work counters */
+#define VOL_STAT(i, n) (rkfd_vol_stats[i] += (n))
+#else
+#define VOL_STAT(i, n)
+#endif
 #ifdef __CUDACC__
 #define RKFD_VOL_NI __host__ __device__ __noinline__
 #else
 #define RKFD_VOL_NI inline
 #endif
-  static constexpr int VOL_P = 2, VOL_PL = 8, VOL_N = 6*VOL_P, VOL_M = VOL_P*(1+VOL_PL), VOL_LPN = 64, VOL_LPS = VOL_LPN + 7;
+  static constexpr int VOL_P = 2, VOL_PL = 8, VOL_N = 6*VOL_P, VOL_M = VOL_P*(1+VOL_PL), VOL_MA = VOL_M, VOL_LPN = VOL_PL, VOL_LPS = VOL_LPN + 4;
   struct VolPair {
     int pair, link, fsl, wsl, npl, sofs;
     V3 center, norm, a1, a2;
@@ -259,30 +264,33 @@
     ral = al; raa = aa;
   }
 
-  /* x = pinv(S) rhs for a symmetric ma x ma matrix (stride VOL_M) by cyclic Jacobi; eigenvalue cut-off as the oracle's */
+  /* x = pinv(S) rhs for a symmetric ma x ma matrix (stride VOL_MA) by cyclic Jacobi; eigenvalue cut-off as the oracle's */
   static RKFD_VOL_NI void vol_pinv_solve(int ma, double *S, const double *rhs, double *x){
-    double V[VOL_M*VOL_M];
-    for(int i=0;i<ma;i++) for(int j=0;j<ma;j++) V[VOL_M*i+j] = i == j ? 1.0 : 0.0;
+    double V[VOL_MA*VOL_MA];
+    for(int i=0;i<ma;i++) for(int j=0;j<ma;j++) V[VOL_MA*i+j] = i == j ? 1.0 : 0.0;
     for(int sweep=0;sweep<60;sweep++){
-      double off = 0; for(int i=0;i<ma;i++) for(int j=i+1;j<ma;j++) off += S[VOL_M*i+j]*S[VOL_M*i+j];
-      if( off < 1e-300 ) break;
+      /* converged when the off-diagonal part is below rounding relative to the diagonal (the oracle keeps sweeping
+       * until it is exactly zero: rotations by angles below 1e-16 that do not change the result) */
+      double off = 0, dg = 0; for(int i=0;i<ma;i++){ dg += S[VOL_MA*i+i]*S[VOL_MA*i+i]; for(int j=i+1;j<ma;j++) off += S[VOL_MA*i+j]*S[VOL_MA*i+j]; }
+      if( off <= 1e-32*dg ) break;
+      VOL_STAT(2, 1);
       for(int i=0;i<ma;i++) for(int j=i+1;j<ma;j++){
-        const double apq = S[VOL_M*i+j];
+        const double apq = S[VOL_MA*i+j];
         if( fabs(apq) < 1e-300 ) continue;
-        const double th = (S[VOL_M*j+j]-S[VOL_M*i+i])/(2.0*apq);
+        const double th = (S[VOL_MA*j+j]-S[VOL_MA*i+i])/(2.0*apq);
         const double t = (th >= 0 ? 1.0 : -1.0)/(fabs(th)+sqrt(th*th+1.0)), cs = 1.0/sqrt(t*t+1.0), sn = t*cs;
-        for(int k=0;k<ma;k++){ const double akp = S[VOL_M*k+i], akq = S[VOL_M*k+j]; S[VOL_M*k+i] = cs*akp-sn*akq; S[VOL_M*k+j] = sn*akp+cs*akq; }
-        for(int k=0;k<ma;k++){ const double apk = S[VOL_M*i+k], aqk = S[VOL_M*j+k]; S[VOL_M*i+k] = cs*apk-sn*aqk; S[VOL_M*j+k] = sn*apk+cs*aqk; }
-        for(int k=0;k<ma;k++){ const double vkp = V[VOL_M*k+i], vkq = V[VOL_M*k+j]; V[VOL_M*k+i] = cs*vkp-sn*vkq; V[VOL_M*k+j] = sn*vkp+cs*vkq; }
+        for(int k=0;k<ma;k++){ const double akp = S[VOL_MA*k+i], akq = S[VOL_MA*k+j]; S[VOL_MA*k+i] = cs*akp-sn*akq; S[VOL_MA*k+j] = sn*akp+cs*akq; }
+        for(int k=0;k<ma;k++){ const double apk = S[VOL_MA*i+k], aqk = S[VOL_MA*j+k]; S[VOL_MA*i+k] = cs*apk-sn*aqk; S[VOL_MA*j+k] = sn*apk+cs*aqk; }
+        for(int k=0;k<ma;k++){ const double vkp = V[VOL_MA*k+i], vkq = V[VOL_MA*k+j]; V[VOL_MA*k+i] = cs*vkp-sn*vkq; V[VOL_MA*k+j] = sn*vkp+cs*vkq; }
       }
     }
-    double lmax = 0; for(int i=0;i<ma;i++) if( fabs(S[VOL_M*i+i]) > lmax ) lmax = fabs(S[VOL_M*i+i]);
+    double lmax = 0; for(int i=0;i<ma;i++) if( fabs(S[VOL_MA*i+i]) > lmax ) lmax = fabs(S[VOL_MA*i+i]);
     for(int i=0;i<ma;i++) x[i] = 0;
     for(int k=0;k<ma;k++){
-      const double lam = S[VOL_M*k+k]; if( fabs(lam) <= 1.0e-11*lmax ) continue;
-      double s = 0; for(int i=0;i<ma;i++) s += V[VOL_M*i+k]*rhs[i];
+      const double lam = S[VOL_MA*k+k]; if( fabs(lam) <= 1.0e-11*lmax ) continue;
+      double s = 0; for(int i=0;i<ma;i++) s += V[VOL_MA*i+k]*rhs[i];
       s /= lam;
-      for(int i=0;i<ma;i++) x[i] += s*V[VOL_M*i+k];
+      for(int i=0;i<ma;i++) x[i] += s*V[VOL_MA*i+k];
     }
   }
 
@@ -310,28 +318,29 @@
     for(int i=0;i<mrows;i++){ double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*i+j]*x[j]; if( fabs(s) < ZTOL ) idx |= 1u << i; }
     unsigned hist_idx[QP_HIST]; double hist_obj[QP_HIST]; int nhist = 0;
     for(int iter=0; iter<QP_MAXIT; iter++){
-      int act[VOL_M]; int ma = 0;
+      int act[VOL_M]; int ma = 0; VOL_STAT(0, 1);
       for(int i=0;i<mrows;i++) if( idx >> i & 1u ) act[ma++] = i;
-      double xs[VOL_N], lam[VOL_M];
+      if( ma > VOL_MA ){ bad |= 2; ma = VOL_MA; }      /* more active rows than unknowns: dependent rows, surplus ignored */
+      double xs[VOL_N], lam[VOL_MA];
       if( ma > 0 ){
-        double Y[VOL_N*VOL_M], S[VOL_M*VOL_M], rhs[VOL_M];     /* Y = Qi Aw^T (n x ma) */
-        for(int i=0;i<n;i++) for(int k=0;k<ma;k++){ double s = 0; for(int j=0;j<n;j++) s += Qi[VOL_N*i+j]*A[VOL_N*act[k]+j]; Y[VOL_M*i+k] = s; }
+        double Y[VOL_N*VOL_MA], S[VOL_MA*VOL_MA], rhs[VOL_MA];     /* Y = Qi Aw^T (n x ma) */
+        for(int i=0;i<n;i++) for(int k=0;k<ma;k++){ double s = 0; for(int j=0;j<n;j++) s += Qi[VOL_N*i+j]*A[VOL_N*act[k]+j]; Y[VOL_MA*i+k] = s; }
         for(int a=0;a<ma;a++){
-          for(int b=0;b<ma;b++){ double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*act[a]+j]*Y[VOL_M*j+b]; S[VOL_M*a+b] = s; }
+          for(int b=0;b<ma;b++){ double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*act[a]+j]*Y[VOL_MA*j+b]; S[VOL_MA*a+b] = s; }
           double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*act[a]+j]*qc[j]; rhs[a] = s;
         }
         /* Cholesky of S; dependent active rows -> pseudo-inverse */
-        bool spd = true; double G[VOL_M*VOL_M]; double smax = 0;
-        for(int a=0;a<ma;a++) if( S[VOL_M*a+a] > smax ) smax = S[VOL_M*a+a];
+        bool spd = true; double G[VOL_MA*VOL_MA]; double smax = 0;
+        for(int a=0;a<ma;a++) if( S[VOL_MA*a+a] > smax ) smax = S[VOL_MA*a+a];
         for(int i=0;i<ma && spd;i++) for(int j=0;j<=i;j++){
-          double s = S[VOL_M*i+j]; for(int k=0;k<j;k++) s -= G[VOL_M*i+k]*G[VOL_M*j+k];
-          if( i == j ){ if( !(s > 1.0e-10*smax) ){ spd = false; break; } G[VOL_M*i+i] = sqrt(s); } else G[VOL_M*i+j] = s/G[VOL_M*j+j];
+          double s = S[VOL_MA*i+j]; for(int k=0;k<j;k++) s -= G[VOL_MA*i+k]*G[VOL_MA*j+k];
+          if( i == j ){ if( !(s > 1.0e-10*smax) ){ spd = false; break; } G[VOL_MA*i+i] = sqrt(s); } else G[VOL_MA*i+j] = s/G[VOL_MA*j+j];
         }
         if( spd ){
-          for(int i=0;i<ma;i++){ double s = rhs[i]; for(int k=0;k<i;k++) s -= G[VOL_M*i+k]*lam[k]; lam[i] = s/G[VOL_M*i+i]; }
-          for(int i=ma-1;i>=0;i--){ double s = lam[i]; for(int k=i+1;k<ma;k++) s -= G[VOL_M*k+i]*lam[k]; lam[i] = s/G[VOL_M*i+i]; }
-        } else vol_pinv_solve(ma, S, rhs, lam);
-        for(int i=0;i<n;i++){ double s = -qc[i]; for(int k=0;k<ma;k++) s += Y[VOL_M*i+k]*lam[k]; xs[i] = s; }
+          for(int i=0;i<ma;i++){ double s = rhs[i]; for(int k=0;k<i;k++) s -= G[VOL_MA*i+k]*lam[k]; lam[i] = s/G[VOL_MA*i+i]; }
+          for(int i=ma-1;i>=0;i--){ double s = lam[i]; for(int k=i+1;k<ma;k++) s -= G[VOL_MA*k+i]*lam[k]; lam[i] = s/G[VOL_MA*i+i]; }
+        } else { VOL_STAT(1, 1); vol_pinv_solve(ma, S, rhs, lam); }
+        for(int i=0;i<n;i++){ double s = -qc[i]; for(int k=0;k<ma;k++) s += Y[VOL_MA*i+k]*lam[k]; xs[i] = s; }
       } else for(int i=0;i<n;i++) xs[i] = -qc[i];
       bool stepped = false;
       for(int i=0;i<n;i++) if( !(fabs(xs[i]-x[i]) < ZTOL) ){ stepped = true; break; }
@@ -362,14 +371,17 @@
       if( endflag ) break;
       if( nhist < QP_HIST ){ hist_idx[nhist] = idx; hist_obj[nhist] = objv; nhist++; }
       if( iter == QP_MAXIT-1 ) bad |= 2;
+#ifdef RKFD_VOL_STATS
+      if( iter+1 > rkfd_vol_stats[7] ) rkfd_vol_stats[7] = iter+1;
+#endif
     }
     idx_out = idx;
   }
 
   /* [EXT A-16] min cost^T x  s.t.  A x = b, x >= 0: two-phase tableau simplex, Bland's rule (cost == nullptr:
-   * feasibility only).  A: mr x nc with stride VOL_LPN.  Same pivoting rules and tolerances as the oracle's vol_lp. */
+   * feasibility only).  A: mr x nc (mr <= 3: the kinetic-friction LPs) with stride VOL_LPN.  Same pivoting rules and tolerances as the oracle's vol_lp. */
   static RKFD_VOL_NI bool vol_lp(int mr, int nc, const double *A, const double *b, const double *cost_in, double *x){
-    const int nt = nc + mr; double T[6*VOL_LPS]; int basis[6]; double bmax = 0;
+    const int nt = nc + mr; double T[3*VOL_LPS]; int basis[3]; double bmax = 0;      /* mr <= 3, nc <= VOL_LPN */
     for(int i=0;i<mr;i++){ const double sg = b[i] < 0 ? -1.0 : 1.0;
       for(int j=0;j<nc;j++) T[VOL_LPS*i+j] = sg*A[VOL_LPN*i+j];
       for(int j=0;j<mr;j++) T[VOL_LPS*i+nc+j] = i == j ? 1.0 : 0.0;
@@ -380,7 +392,7 @@
       const int ncol = phase == 1 ? nt : nc;
       if( phase == 2 && !cost_in ) break;
       for(int it=0;it<20000;it++){
-        int enter = -1, leave = -1; double best = 0;
+        int enter = -1, leave = -1; double best = 0; VOL_STAT(5, 1);
         for(int j=0;j<ncol && enter<0;j++){
           double rc = phase == 1 ? ( j >= nc ? 1.0 : 0.0 ) : cost_in[j]; bool bas = false;
           for(int i=0;i<mr;i++){ if( basis[i] == j ) bas = true;
@@ -413,6 +425,78 @@
     }
     if( ok && x ){ for(int j=0;j<nc;j++) x[j] = 0; for(int i=0;i<mr;i++) if( basis[i] < nc ) x[basis[i]] = T[VOL_LPS*i+nt]; }
     return ok;
+  }
+
+  /* static friction (rkfd_volume.c:643-688): is b = (fn, t1, t2, f1, f2, tn) a non-negative combination of the columns
+   * g_j = (1, r2, -r1, SF cos_i, SF sin_i, r1 SF sin_i - r2 SF cos_i), j = pyramid * corner + i, i.e. can pyramid forces
+   * at the polygon corners carry the wrench?  Phase 1 of the simplex with Bland's rule exactly as vol_lp (same entering
+   * and leaving choices), in revised form: the 6 x 6 basis inverse instead of the 6 x (columns + 7) tableau, columns
+   * generated on the fly - the whole state stays in registers. */
+  RKFD_VOL_NI bool vol_static_feasible(const ModelDev &m, const VolPair &v, int np, const double (&b)[6]){
+    const int pyr = m.pyramid, nc = pyr*np, nt = nc + 6;
+    double Bi[36], xb[6], sg[6]; int basis[6]; double bmax = 0;
+#pragma unroll
+    for(int i=0;i<6;i++){ sg[i] = b[i] < 0 ? -1.0 : 1.0; xb[i] = sg[i]*b[i]; basis[i] = nc+i; if( fabs(b[i]) > bmax ) bmax = fabs(b[i]);
+#pragma unroll
+      for(int j=0;j<6;j++) Bi[6*i+j] = i == j ? 1.0 : 0.0; }
+    const double eps = 1.0e-10*(1.0+bmax);
+    VOL_STAT(3, 1);
+    for(int it=0; it<20000; it++){
+      double y[6], col[6]; VOL_STAT(4, 1);
+#pragma unroll
+      for(int j=0;j<6;j++){ double s = 0;
+#pragma unroll
+        for(int i=0;i<6;i++) s += basis[i] >= nc ? Bi[6*i+j] : 0.0; y[j] = s; }
+      int enter = -1;
+      for(int j=0;j<nt && enter<0;j++){
+        bool bas = false;
+#pragma unroll
+        for(int i=0;i<6;i++) bas = bas || basis[i] == j;
+        if( bas ) continue;
+        if( j < nc ){
+          const int k = j/pyr, i = j - pyr*k; const double r1 = v.r[k][0], r2 = v.r[k][1], fc = v.SF*m.sc_cos[i], fs = v.SF*m.sc_sin[i];
+          col[0] = sg[0]; col[1] = sg[1]*r2; col[2] = -sg[2]*r1; col[3] = sg[3]*fc; col[4] = sg[4]*fs; col[5] = -sg[5]*( (-r1)*fs + r2*fc );
+        } else {
+#pragma unroll
+          for(int i=0;i<6;i++) col[i] = i == j-nc ? 1.0 : 0.0;
+        }
+        double rc = j >= nc ? 1.0 : 0.0;
+#pragma unroll
+        for(int i=0;i<6;i++) rc -= y[i]*col[i];
+        if( rc < -1.0e-11 ) enter = j;
+      }
+      if( enter < 0 ) break;
+      double d[6]; int leave = -1; double best = 0;
+#pragma unroll
+      for(int i=0;i<6;i++){ double s = 0;
+#pragma unroll
+        for(int j=0;j<6;j++) s += Bi[6*i+j]*col[j]; d[i] = s; }
+#pragma unroll
+      for(int i=0;i<6;i++) if( d[i] > 1.0e-11 ){ const double ratio = xb[i]/d[i];
+        if( leave < 0 || ratio < best - 1.0e-13 || ( fabs(ratio-best) <= 1.0e-13 && basis[i] < basis[leave < 0 ? 0 : leave] ) ){ leave = i; best = ratio; } }
+      if( leave < 0 ) return false;
+      double prow[6], pv = 0, px = 0;
+#pragma unroll
+      for(int i=0;i<6;i++) if( i == leave ){ pv = d[i]; px = xb[i];
+#pragma unroll
+        for(int j=0;j<6;j++) prow[j] = Bi[6*i+j]; }
+      px /= pv;
+#pragma unroll
+      for(int j=0;j<6;j++) prow[j] /= pv;
+#pragma unroll
+      for(int i=0;i<6;i++){
+        if( i == leave ){ xb[i] = px; basis[i] = enter;
+#pragma unroll
+          for(int j=0;j<6;j++) Bi[6*i+j] = prow[j]; }
+        else { xb[i] -= d[i]*px;
+#pragma unroll
+          for(int j=0;j<6;j++) Bi[6*i+j] -= d[i]*prow[j]; }
+      }
+    }
+    double art = 0;
+#pragma unroll
+    for(int i=0;i<6;i++) if( basis[i] >= nc ) art += xb[i];
+    return !(art > eps);
   }
 
   RKFD_HD V3 vol_point_vel(const VolPair &vp, V3 p){     /* rkFDLinkPointWldVel (rkfd_util.c:14-24), static partner */
@@ -522,7 +606,7 @@
       }
       x[6*k] = v.norm.x; x[6*k+1] = v.norm.y; x[6*k+2] = v.norm.z;
     }
-    unsigned idx = 0;
+    unsigned idx = 0; VOL_STAT(6, 1);
     vol_asm(n, mrows, Qm, cv, nf, x, idx);
     /* ---- f /= dt, _rkFDSolverSetForce (:552-568; the offset is not advanced for a pair without planes - mirrored) */
     { int off = 0;
@@ -585,18 +669,8 @@
           kinetic = 2;
         } else {
           /* static friction: the wrench inside the friction pyramids at the polygon corners? (:643-688) */
-          const int pyr = m.pyramid, fnum = pyr*np;
-          if( fnum > VOL_LPN ){ bad |= 4; }
-          else {
-            double ma[6*VOL_LPN], mb[6];
-            for(int j=0;j<np;j++) for(int i=0;i<pyr;i++){ const int cc = pyr*j+i;
-              const double sn = sin(6.283185307179586/pyr*i), cs = cos(6.283185307179586/pyr*i);
-              ma[cc] = 1.0; ma[VOL_LPN+cc] = v.r[j][1]; ma[2*VOL_LPN+cc] = -v.r[j][0];
-              ma[3*VOL_LPN+cc] = v.SF*cs; ma[4*VOL_LPN+cc] = v.SF*sn;
-              ma[5*VOL_LPN+cc] = -( ma[2*VOL_LPN+cc]*ma[4*VOL_LPN+cc] + ma[VOL_LPN+cc]*ma[3*VOL_LPN+cc] ); }
-            mb[0] = wv[0]; mb[1] = wv[4]; mb[2] = wv[5]; mb[3] = wv[1]; mb[4] = wv[2]; mb[5] = wv[3];
-            if( !vol_lp(6, fnum, ma, mb, nullptr, nullptr) ) kinetic = 2;
-          }
+          const double mb[6] = { wv[0], wv[4], wv[5], wv[1], wv[2], wv[3] };
+          if( !vol_static_feasible(m, v, np, mb) ) kinetic = 2;
         }
         if( kinetic == 2 ){
           /* kinetic friction: normal force redistributed over the polygon corners by an LP (:733-843) */

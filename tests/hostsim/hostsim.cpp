@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#define RKFD_VOL_STATS
+static long long rkfd_vol_stats[8];
 #include "rkfd_core.cuh"
 #include "rkfd_model.h"
 
@@ -138,6 +140,7 @@ void hostsim_get_pivot(HostSim *h, int *type, double *prev)
   const int nq = h->model.nq, B = h->B;
   for(int e=0;e<B;e++) for(int j=0;j<nq;j++){ type[(size_t)e*nq+j] = (h->st.piv_type[e] >> j) & 1u; prev[(size_t)e*nq+j] = h->st.piv_prev[(size_t)j*B+e]; }
 }
+void hostsim_vol_stats(long long *out, int reset){ for(int i=0;i<8;i++){ out[i] = rkfd_vol_stats[i]; if( reset ) rkfd_vol_stats[i] = 0; } }
 void hostsim_get_status(HostSim *h, int *status){ for(int e=0;e<h->B;e++) status[e] = h->st.status[e]; }
 /* mode 0: nsteps steps; 1: eval; 2: committing eval */
 void hostsim_run(HostSim *h, int mode, int nsteps)

@@ -4,10 +4,10 @@ import numpy as np, torch, rokifd_b200
 from rokifd_b200 import capi, chains as ch
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
 w = ch.world_c4_volume()
-q, qd, u = ch.sample_state(w, B, seed=3); q[:, 2] = 0.44; q[:, 3:6] *= 0.1; q[:, 6:] *= 0.3
+q, qd, u = ch.sample_c4_standing(w, B, seed=3)
 fd, _ = capi.create_world(w, B=B); fd.batch_set_state(q, qd); fd.batch_set_motor_input(u); fd.update_init()
 st = torch.cuda.current_stream(); fd.batch_set_stream(st.cuda_stream)
-for n in (3, 10, 20):
+for n in [int(x) for x in os.environ.get('STEPS', '3,10,20').split(',')]:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for _ in range(n): fd.update()
