@@ -111,7 +111,7 @@ template <class T> static T *dalloc(Shard &s, size_t n)
 #define RKFD_VARIANT_LIST(X) \
   X(128,0,1,7,2) X(64,0,1,7,4) X(128,0,0,5,4) X(128,0,0,8,4) X(128,0,0,9,4) X(128,0,0,10,4) X(128,0,0,11,2) X(256,0,0,5,2) X(512,0,0,5,1) X(256,0,0,6,2) X(256,0,0,3,2) X(512,0,0,3,1) X(128,0,0,3,4) X(128,0,0,3,3) X(128,0,0,4,4) X(128,0,0,1,1) X(256,0,0,1,1) X(128,0,0,2,1) \
   X(128,0,0,0,1) X(256,0,0,0,1) X(64,0,0,0,1) X(32,0,0,0,1) X(64,1,0,0,1) \
-  X(128,0,1,0,1) X(256,0,1,0,1) X(64,0,1,0,1) X(32,0,1,0,1) X(64,1,1,0,1)
+  X(128,0,1,0,1) X(256,0,1,0,1) X(64,0,1,0,1) X(32,0,1,0,1) X(64,1,1,0,1) X(128,1,1,0,4)
 #define RKFD_DECL(B,G,R,S,M) extern const KernelVariant rkfd_variant_##B##_##G##_##R##_##S##_##M;
 RKFD_VARIANT_LIST(RKFD_DECL)
 #undef RKFD_DECL
@@ -170,7 +170,11 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     unsigned specs = spec_match_mask(model);
     if( !model.has_rigid && model_tm_.ntspace > 0 && model_tm_.ntspace <= SPEC_GENERIC_TM_MAX_T ) specs |= 1u << SPEC_GENERIC_TM;
     if( const char *fs = std::getenv("RKFD_SPEC") ) specs &= 1u << std::atoi(fs);    /* 0: generic kernel only */
-    for(int pass=0; pass<3 && best==0; pass++)
+    /* scratch in HBM even when shared memory would fit: tuning aid, and the default of the Volume solver - its lanes live in
+     * thread-local memory anyway and the 291-double column of a legged tree leaves room for 2 warps per SM only (C4,
+     * 131,072 envs: 130 -> 103 ms per step) */
+    const int pass0 = ( std::getenv("RKFD_FORCE_GSCR") || ( model.has_rigid && model.solver == S_VOLUME && !std::getenv("RKFD_FORCE_SMEM") ) ) ? 2 : 0;
+    for(int pass=pass0; pass<3 && best==0; pass++)
       for(const KernelVariant *kv : g_variants){
         /* pass 0: a matching specialisation; 1: generic, shared-memory scratch; 2: generic, scratch in HBM */
         if( kv->rigid != rigid || kv->gscr != (pass == 2) ) continue;

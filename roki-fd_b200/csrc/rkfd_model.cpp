@@ -195,7 +195,15 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   }
   if( m.has_rigid && m.solver == S_VOLUME ){
     /* the Volume solver (rkfd_volume.cuh) works on thread-local data: no workspace; cells must be parallelepipeds */
-    for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID && m.cell[m.pair[p].cell].nvert != 8 ){ err = "Volume solver: rigid cells must have the 8 corners of a box (sign-bit order)"; return false; }
+    for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID ){
+      const CellDev &c = m.cell[m.pair[p].cell]; bool ok = c.nvert == 8;
+      for(int k=0;k<8 && ok;k++) for(int a=0;a<3;a++){      /* v[k] = v[0] + sum over the set bits b of k of (v[1<<b] - v[0]) */
+        const double *v = m.vert + 3*c.vofs; double x = v[a], scale = 1e-300;
+        for(int b=0;b<3;b++){ if( k >> b & 1 ) x += v[3*(1<<b)+a] - v[a]; scale += std::fabs(v[3*(1<<b)+a] - v[a]); }
+        if( std::fabs(x - v[3*k+a]) > 1e-9*(1.0 + scale) ) ok = false;
+      }
+      if( !ok ){ err = "Volume solver: rigid cells must have the 8 corners of a box (vertex k = sign bits x: k&1, y: k&2, z: k&4)"; return false; }
+    }
     m.ws_doubles = 0; m.ws_geo = m.ws_b = m.ws_f = m.ws_A = m.ws_du = m.ws_da = m.ws_qp = 0;
     return true;
   }

@@ -427,3 +427,12 @@ def test_volume_steps_match_oracle(oracle, name):
     ref = oracle_run(oracle, w, q, qd, u, nsteps)
     for b in range(B):
         assert relerr(hq[b, :w.nq], ref[b][0][0]) < 1e-7, (name, b)
+
+
+def test_volume_refuses_cells_that_are_not_boxes():
+    rng = np.random.default_rng(0)
+    body = ch.ChainModel("blob", [ch.Link(name="l", jtype="float", mass=1.0, stuff="body", inertia=np.eye(3) * 1e-2,
+                                          shapes=[rng.normal(size=(8, 3)) * 0.1])])
+    with pytest.raises(Exception, match="Volume solver"):
+        HostSim(ch.World(chains=[body, ch.floor()], solver="Volume"), 1)
+    HostSim(ch.World(chains=[body, ch.floor()], solver="Vert"), 1)          # fine for the vertex solvers

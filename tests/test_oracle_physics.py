@@ -295,3 +295,76 @@ def test_integrator_orders():
         e1 = np.abs(end_state(integ, 0.08 / 8) - exact).max()
         e2 = np.abs(end_state(integ, 0.08 / 16) - exact).max()
         assert 0.8 * 2 ** order < e1 / e2 < 1.25 * 2 ** order, (integ, e1, e2)
+
+
+# ---- Volume solver (rkfd_volume.c): pins of the oracle's restatement
+def test_lp_matches_scipy(oracle):
+    """[EXT A-16] two-phase simplex: optimum value and feasibility verdict against scipy's HiGHS."""
+    from scipy.optimize import linprog
+    rng = np.random.default_rng(11)
+    nfeas = ninf = 0
+    for trial in range(60):
+        m, n = int(rng.integers(1, 7)), int(rng.integers(3, 30))
+        A = rng.normal(size=(m, n))
+        if trial % 3:
+            b = A @ rng.uniform(0, 1, n)            # feasible by construction
+        elif trial % 2:
+            b = rng.normal(size=m)
+        else:
+            A = np.abs(A); b = -np.abs(rng.normal(size=m)) - 0.1     # infeasible: A x >= 0 > b
+        c = rng.uniform(0.1, 1.0, n)                # bounded below on x >= 0
+        ok, x = oracle.lp_solve(A, b, c)
+        ref = linprog(c, A_eq=A, b_eq=b, bounds=[(0, None)] * n, method="highs")
+        assert ok == (ref.status == 0), trial
+        okf, _ = oracle.lp_solve(A, b)
+        assert okf == ok
+        if ok:
+            nfeas += 1
+            assert (x >= -1e-9).all() and np.allclose(A @ x, b, atol=1e-8)
+            assert abs(c @ x - ref.fun) < 1e-8 * max(1.0, abs(ref.fun))
+        else:
+            ninf += 1
+    assert nfeas > 10 and ninf > 3
+
+
+def test_volume_box_rests_in_equilibrium(oracle):
+    """A tilted box dropped on the rigid floor with the Volume solver ends flat and at rest; the contact wrench is
+    then the weight, applied under the centre of mass, with static friction."""
+    w = ch.World(chains=[ch.box(), ch.floor()], solver="Volume")
+    e = oracle.OracleWorld(w).env()
+    q = np.zeros(6); q[2] = 0.049; q[3] = 0.05; q[4] = 0.02
+    qd = np.zeros(6); qd[0] = 0.3
+    e.set_state(q, qd); e.set_motor_input(np.zeros(w.nl)); e.update_init()
+    for _ in range(1500):
+        e.update()
+    qq, qqd, qdd = e.get_state()
+    npl, ty, wr, ce = e.volume()
+    assert np.abs(qqd).max() < 1e-8 and np.abs(qdd).max() < 1e-6
+    assert abs(qq[2] - 0.05) < 1e-3                       # flat on the floor (0.1 m cube)
+    assert npl[0] == 4 and ty[0] == 0                     # square contact polygon, static friction
+    assert np.allclose(wr[0][:3], [0, 0, 0.5 * 9.80665], atol=1e-6)
+    # torque about the volume centre balances the offset of the centre of mass: tau = (com - centre) x f
+    tau = np.cross(qq[:3] - ce[0], wr[0][:3])
+    assert np.allclose(wr[0][3:], -tau, atol=1e-6)
+
+
+def test_volume_sliding_box_kinetic_friction_ratio(oracle):
+    """A box sliding on the rigid floor (it chatters: the friction torque tips it): whenever the pair pushes, it is
+    kinetic and the tangential force is KF * (1 - exp(-w v)) * fn against the motion (rkfd_volume.c:715-843,
+    rkfd_util.c:193-196: the per-corner friction directions coincide for a translating body)."""
+    w = ch.World(chains=[ch.box(), ch.floor()], solver="Volume")
+    e = oracle.OracleWorld(w).env()
+    q = np.zeros(6); q[2] = 0.0499
+    qd = np.zeros(6); qd[0] = 1.0
+    e.set_state(q, qd); e.set_motor_input(np.zeros(w.nl)); e.update_init()
+    npush = 0
+    for _ in range(120):
+        e.update()
+        qq, qqd, qdd = e.get_state()
+        npl, ty, wr, ce = e.volume()
+        if npl[0] > 0 and wr[0][2] > 0.1:
+            npush += 1
+            assert ty[0] == 1
+            assert abs(wr[0][0] / wr[0][2] + 0.3 * (1 - np.exp(-100.0 * qqd[0]))) < 5e-3
+            assert abs(wr[0][1]) < 1e-6 * wr[0][2]
+    assert npush > 20 and 0.5 < qqd[0] < 0.8          # about 0.3 g of deceleration over 0.12 s
