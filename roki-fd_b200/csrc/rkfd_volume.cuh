@@ -13,8 +13,8 @@
  *   Q6, c6, planes   per triangle: midpoint-rule integrals, sign cases             rkfd_volume.c:232-491
  *   QP               Q = sum A_p^T Q6 A_p + L, rows: normal force >= 0 and one centre-of-pressure row per polygon
  *                    edge; dense active-set method (rkfd_opt_qp.c:43-181) with the KKT solve through the Schur
- *                    complement of the Cholesky-factored Q (pseudo-inverse by Jacobi only when the active rows are
- *                    dependent)                                                    rkfd_volume.c:496-548
+ *                    complement of the Cholesky-factored Q (minimum-norm multipliers by iterated Tikhonov
+ *                    regularisation when the active rows are dependent)            rkfd_volume.c:496-548
  *   post-processing  non-pushing wrenches zeroed, centre of pressure projected into the polygon, static-friction
  *                    feasibility LP / kinetic-friction redistribution LP ([EXT A-16] two-phase simplex with Bland's
  *                    rule), wrench on the link                                     rkfd_volume.c:552-936
@@ -264,84 +264,55 @@
     ral = al; raa = aa;
   }
 
-  /* x = pinv(S) rhs for a symmetric ma x ma matrix (stride VOL_MA) by cyclic Jacobi; eigenvalue cut-off as the oracle's */
-  static RKFD_VOL_NI void vol_pinv_solve(int ma, double *S, const double *rhs, double *x){
-    double V[VOL_MA*VOL_MA];
-    for(int i=0;i<ma;i++) for(int j=0;j<ma;j++) V[VOL_MA*i+j] = i == j ? 1.0 : 0.0;
-    for(int sweep=0;sweep<60;sweep++){
-      /* converged when the off-diagonal part is below rounding relative to the diagonal (the oracle keeps sweeping
-       * until it is exactly zero: rotations by angles below 1e-16 that do not change the result) */
-      double off = 0, dg = 0; for(int i=0;i<ma;i++){ dg += S[VOL_MA*i+i]*S[VOL_MA*i+i]; for(int j=i+1;j<ma;j++) off += S[VOL_MA*i+j]*S[VOL_MA*i+j]; }
-      if( off <= 1e-32*dg ) break;
-      VOL_STAT(2, 1);
-      for(int i=0;i<ma;i++) for(int j=i+1;j<ma;j++){
-        const double apq = S[VOL_MA*i+j];
-        if( fabs(apq) < 1e-300 ) continue;
-        const double th = (S[VOL_MA*j+j]-S[VOL_MA*i+i])/(2.0*apq);
-        const double t = (th >= 0 ? 1.0 : -1.0)/(fabs(th)+sqrt(th*th+1.0)), cs = 1.0/sqrt(t*t+1.0), sn = t*cs;
-        for(int k=0;k<ma;k++){ const double akp = S[VOL_MA*k+i], akq = S[VOL_MA*k+j]; S[VOL_MA*k+i] = cs*akp-sn*akq; S[VOL_MA*k+j] = sn*akp+cs*akq; }
-        for(int k=0;k<ma;k++){ const double apk = S[VOL_MA*i+k], aqk = S[VOL_MA*j+k]; S[VOL_MA*i+k] = cs*apk-sn*aqk; S[VOL_MA*j+k] = sn*apk+cs*aqk; }
-        for(int k=0;k<ma;k++){ const double vkp = V[VOL_MA*k+i], vkq = V[VOL_MA*k+j]; V[VOL_MA*k+i] = cs*vkp-sn*vkq; V[VOL_MA*k+j] = sn*vkp+cs*vkq; }
-      }
-    }
-    double lmax = 0; for(int i=0;i<ma;i++) if( fabs(S[VOL_MA*i+i]) > lmax ) lmax = fabs(S[VOL_MA*i+i]);
-    for(int i=0;i<ma;i++) x[i] = 0;
-    for(int k=0;k<ma;k++){
-      const double lam = S[VOL_MA*k+k]; if( fabs(lam) <= 1.0e-11*lmax ) continue;
-      double s = 0; for(int i=0;i<ma;i++) s += V[VOL_MA*i+k]*rhs[i];
-      s /= lam;
-      for(int i=0;i<ma;i++) x[i] += s*V[VOL_MA*i+k];
-    }
-  }
-
   /* rkFDQPSolveASM (rkfd_opt_qp.c:43-181) on dense data: min 1/2 x^T Q x + c^T x  s.t.  A x >= 0 (m rows, stride
-   * VOL_N).  Q is positive definite (relaxation L > 0 on its diagonal): Qi = Q^-1 once; per iteration
-   * S lambda = Aw Qi c, x* = Qi (Aw^T lambda - c).  x holds the initial point on entry.  idx: active flags. */
+   * VOL_N).  Q is positive definite (relaxation L > 0 on its diagonal): Q = G G^T once, z = G^-1 c and the rows
+   * B_i = G^-1 a_i of all constraints once (forward substitutions); an iteration then needs, with the active rows W,
+   *   S = B_W B_W^T,  S lambda = B_W z,  x* = G^-T ( B_W^T lambda - z )
+   * which is the KKT system [[-Q, A_W^T],[A_W, 0]] [x; lambda] = [c; 0] of the reference (rkfd_opt_qp.c:82-106).  The
+   * reference solves it with zLESolveMP: when active rows are dependent (an unloaded sole has ALL its rows active) the
+   * multipliers are the minimum-norm ones.  Here: lambda = S^+ (B_W z) by iterated Tikhonov regularisation -
+   * lambda += (S + eps I)^-1 (B_W z - S lambda), one Cholesky factorisation and four refinements - which converges to the
+   * minimum-norm solution of the (always consistent) system and is the plain solve when S is regular: one code path, no
+   * eigen-decomposition.  x holds the initial point on entry.  idx: active flags. */
   RKFD_VOL_NI void vol_asm(int n, int mrows, const double *Qm, const double *cv, const double *A, double *x, unsigned &idx_out){
     const int QP_HIST = 32, QP_MAXIT = 256;
-    double Qi[VOL_N*VOL_N], qc[VOL_N];
-    { /* Cholesky Q = G G^T, Qi = G^-T G^-1 */
-      double G[VOL_N*VOL_N];
-      for(int i=0;i<n;i++) for(int j=0;j<=i;j++){
-        double s = Qm[VOL_N*i+j]; for(int k=0;k<j;k++) s -= G[VOL_N*i+k]*G[VOL_N*j+k];
-        if( i == j ){ if( !(s > 0) ){ bad |= 2; s = 1.0; } G[VOL_N*i+i] = sqrt(s); } else G[VOL_N*i+j] = s/G[VOL_N*j+j];
-      }
-      for(int col=0;col<n;col++){
-        double y[VOL_N];
-        for(int i=0;i<n;i++){ double s = i == col ? 1.0 : 0.0; for(int k=0;k<i;k++) s -= G[VOL_N*i+k]*y[k]; y[i] = s/G[VOL_N*i+i]; }
-        for(int i=n-1;i>=0;i--){ double s = y[i]; for(int k=i+1;k<n;k++) s -= G[VOL_N*k+i]*y[k]; y[i] = s/G[VOL_N*i+i]; }
-        for(int i=0;i<n;i++) Qi[VOL_N*i+col] = y[i];
-      }
+    double G[VOL_N*VOL_N], z[VOL_N], Bm[VOL_M*VOL_N];
+    for(int i=0;i<n;i++) for(int j=0;j<=i;j++){
+      double s = Qm[VOL_N*i+j]; for(int k=0;k<j;k++) s -= G[VOL_N*i+k]*G[VOL_N*j+k];
+      if( i == j ){ if( !(s > 0) ){ bad |= 2; s = 1.0; } G[VOL_N*i+i] = sqrt(s); } else G[VOL_N*i+j] = s/G[VOL_N*j+j];
     }
-    for(int i=0;i<n;i++){ double s = 0; for(int j=0;j<n;j++) s += Qi[VOL_N*i+j]*cv[j]; qc[i] = s; }
+    for(int i=0;i<n;i++){ double s = cv[i]; for(int k=0;k<i;k++) s -= G[VOL_N*i+k]*z[k]; z[i] = s/G[VOL_N*i+i]; }
+    for(int r=0;r<mrows;r++) for(int i=0;i<n;i++){ double s = A[VOL_N*r+i]; for(int k=0;k<i;k++) s -= G[VOL_N*i+k]*Bm[VOL_N*r+k]; Bm[VOL_N*r+i] = s/G[VOL_N*i+i]; }
     unsigned idx = 0;
     for(int i=0;i<mrows;i++){ double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*i+j]*x[j]; if( fabs(s) < ZTOL ) idx |= 1u << i; }
     unsigned hist_idx[QP_HIST]; double hist_obj[QP_HIST]; int nhist = 0;
     for(int iter=0; iter<QP_MAXIT; iter++){
       int act[VOL_M]; int ma = 0; VOL_STAT(0, 1);
       for(int i=0;i<mrows;i++) if( idx >> i & 1u ) act[ma++] = i;
-      if( ma > VOL_MA ){ bad |= 2; ma = VOL_MA; }      /* more active rows than unknowns: dependent rows, surplus ignored */
-      double xs[VOL_N], lam[VOL_MA];
+      double xs[VOL_N], lam[VOL_MA], wv[VOL_N];
+      for(int i=0;i<n;i++) wv[i] = -z[i];
       if( ma > 0 ){
-        double Y[VOL_N*VOL_MA], S[VOL_MA*VOL_MA], rhs[VOL_MA];     /* Y = Qi Aw^T (n x ma) */
-        for(int i=0;i<n;i++) for(int k=0;k<ma;k++){ double s = 0; for(int j=0;j<n;j++) s += Qi[VOL_N*i+j]*A[VOL_N*act[k]+j]; Y[VOL_MA*i+k] = s; }
+        double S[VOL_MA*VOL_MA], C[VOL_MA*VOL_MA], rhs[VOL_MA], res[VOL_MA];
+        double smax = 0;
         for(int a=0;a<ma;a++){
-          for(int b=0;b<ma;b++){ double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*act[a]+j]*Y[VOL_MA*j+b]; S[VOL_MA*a+b] = s; }
-          double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*act[a]+j]*qc[j]; rhs[a] = s;
+          for(int b=0;b<=a;b++){ double s = 0; for(int j=0;j<n;j++) s += Bm[VOL_N*act[a]+j]*Bm[VOL_N*act[b]+j]; S[VOL_MA*a+b] = s; S[VOL_MA*b+a] = s; }
+          double s = 0; for(int j=0;j<n;j++) s += Bm[VOL_N*act[a]+j]*z[j]; rhs[a] = s; lam[a] = 0.0;
+          if( S[VOL_MA*a+a] > smax ) smax = S[VOL_MA*a+a];
         }
-        /* Cholesky of S; dependent active rows -> pseudo-inverse */
-        bool spd = true; double G[VOL_MA*VOL_MA]; double smax = 0;
-        for(int a=0;a<ma;a++) if( S[VOL_MA*a+a] > smax ) smax = S[VOL_MA*a+a];
-        for(int i=0;i<ma && spd;i++) for(int j=0;j<=i;j++){
-          double s = S[VOL_MA*i+j]; for(int k=0;k<j;k++) s -= G[VOL_MA*i+k]*G[VOL_MA*j+k];
-          if( i == j ){ if( !(s > 1.0e-10*smax) ){ spd = false; break; } G[VOL_MA*i+i] = sqrt(s); } else G[VOL_MA*i+j] = s/G[VOL_MA*j+j];
+        const double eps = 1.0e-9*smax + 1.0e-300;
+        for(int i=0;i<ma;i++) for(int j=0;j<=i;j++){
+          double s = S[VOL_MA*i+j] + ( i == j ? eps : 0.0 ); for(int k=0;k<j;k++) s -= C[VOL_MA*i+k]*C[VOL_MA*j+k];
+          if( i == j ) C[VOL_MA*i+i] = sqrt(s > 0 ? s : eps); else C[VOL_MA*i+j] = s/C[VOL_MA*j+j];
         }
-        if( spd ){
-          for(int i=0;i<ma;i++){ double s = rhs[i]; for(int k=0;k<i;k++) s -= G[VOL_MA*i+k]*lam[k]; lam[i] = s/G[VOL_MA*i+i]; }
-          for(int i=ma-1;i>=0;i--){ double s = lam[i]; for(int k=i+1;k<ma;k++) s -= G[VOL_MA*k+i]*lam[k]; lam[i] = s/G[VOL_MA*i+i]; }
-        } else { VOL_STAT(1, 1); vol_pinv_solve(ma, S, rhs, lam); }
-        for(int i=0;i<n;i++){ double s = -qc[i]; for(int k=0;k<ma;k++) s += Y[VOL_MA*i+k]*lam[k]; xs[i] = s; }
-      } else for(int i=0;i<n;i++) xs[i] = -qc[i];
+        for(int ref=0; ref<5; ref++){
+          for(int i=0;i<ma;i++){ double s = rhs[i]; for(int k=0;k<ma;k++) s -= S[VOL_MA*i+k]*lam[k]; res[i] = s; }
+          for(int i=0;i<ma;i++){ double s = res[i]; for(int k=0;k<i;k++) s -= C[VOL_MA*i+k]*res[k]; res[i] = s/C[VOL_MA*i+i]; }
+          for(int i=ma-1;i>=0;i--){ double s = res[i]; for(int k=i+1;k<ma;k++) s -= C[VOL_MA*k+i]*res[k]; res[i] = s/C[VOL_MA*i+i]; }
+          for(int i=0;i<ma;i++) lam[i] += res[i];
+        }
+        for(int k=0;k<ma;k++) for(int i=0;i<n;i++) wv[i] += lam[k]*Bm[VOL_N*act[k]+i];
+      }
+      for(int i=n-1;i>=0;i--){ double s = wv[i]; for(int k=i+1;k<n;k++) s -= G[VOL_N*k+i]*xs[k]; xs[i] = s/G[VOL_N*i+i]; }
       bool stepped = false;
       for(int i=0;i<n;i++) if( !(fabs(xs[i]-x[i]) < ZTOL) ){ stepped = true; break; }
       if( !stepped ){
@@ -371,9 +342,6 @@
       if( endflag ) break;
       if( nhist < QP_HIST ){ hist_idx[nhist] = idx; hist_obj[nhist] = objv; nhist++; }
       if( iter == QP_MAXIT-1 ) bad |= 2;
-#ifdef RKFD_VOL_STATS
-      if( iter+1 > rkfd_vol_stats[7] ) rkfd_vol_stats[7] = iter+1;
-#endif
     }
     idx_out = idx;
   }
