@@ -45,12 +45,27 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled while the device runs the benchmark load (settle + warm-up + timed steps)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t0, self.t1, self.note = None, None, None
+
+    def mark_begin(self):      # the device is under the benchmark's load from here ...
+        self.t0 = time.time()
+
+    def mark_end(self):        # ... to here: only samples in between are reported
+        self.t1 = time.time()
+
+    def _loaded(self):
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        return [r for (t, r) in self.rows if t0 + 0.15 <= t <= t1]      # +0.15 s: a sample reports the preceding interval
+
+    def loaded_samples(self):
+        return len(self._loaded())
 
     def start(self):
         try:
@@ -64,7 +79,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -75,7 +90,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in self._loaded():
             try:
                 sm.append(float(r[1])); mx = float(r[2])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -83,8 +98,11 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if self.note:
+            out["note"] = self.note
+        return out
 
 
 def cpu_settled_state(world, ch, n_envs, seed=20260418, settle=SETTLE_STEPS):
@@ -206,6 +224,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    sampler = ClockSampler(local_rank)      # started early: the first nvidia-smi of a fresh box can take seconds to report
+    sampler.start()
     world = ch.world_c3()
     B = args.envs
     q, qd, u = multi.rank_problem(world, ch, B, rank)     # weak scaling: every rank its own synthetic states
@@ -223,9 +243,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") --------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     # settle (untimed, ~1 s of GPU load: also lets nvidia-smi deliver samples of the loaded device), then warm-up
+    sampler.mark_begin()
     fd.update_n(SETTLE_STEPS // 2)
     torch.cuda.synchronize()
     fd.update_n(SETTLE_STEPS - SETTLE_STEPS // 2)
@@ -240,6 +259,14 @@ def main():
         ev[s + 1].record(stream)
     barrier()
     launches = fd.launch_count - l0
+    sampler.mark_end()
+    if sampler.loaded_samples() == 0:
+        # nvidia-smi delivered nothing inside the timed region (slow start): keep the same load on the device until it does
+        t_wait = time.time()
+        while sampler.loaded_samples() == 0 and time.time() - t_wait < 5.0:
+            fd.update_n(100); torch.cuda.synchronize()
+        sampler.mark_end()
+        sampler.note = "no nvidia-smi sample fell inside the loaded region (settle + warm-up + timed steps); sampled under the same load right after it"
     clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]

@@ -21,7 +21,7 @@
  * The reference headers pull ZEDA/ZM/Zeo/RoKi types in by value (zVec, rkChain, rkCD ...).  Those
  * libraries are not part of the reference tree, so this header carries minimal source-compatible
  * stand-ins for exactly the pieces the reference's example programs touch
- * (example/chain/*.c): zVec, rkChain/rkJoint accessors, rkCDPairChainUnreg.  Programs written
+ * (the .c files of example/chain): zVec, rkChain/rkJoint accessors, rkCDPairChainUnreg.  Programs written
  * against roki_fd.h recompile against this header unchanged (source compatibility; the by-value
  * `rkFD` layout is necessarily different).
  *
