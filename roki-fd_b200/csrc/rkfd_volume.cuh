@@ -274,29 +274,74 @@
    * lambda += (S + eps I)^-1 (B_W z - S lambda), one Cholesky factorisation and four refinements - which converges to the
    * minimum-norm solution of the (always consistent) system and is the plain solve when S is regular: one code path, no
    * eigen-decomposition.  x holds the initial point on entry.  idx: active flags. */
-  RKFD_VOL_NI void vol_asm(int n, int mrows, const double *Qm, const double *cv, const double *A, double *x, unsigned &idx_out){
+  RKFD_VOL_NI void vol_asm(int mrows, const double *Qm, const double *cv, const double *A, double *x, unsigned &idx_out){
+    /* The problem always has VOL_N unknowns (a single pair is padded with an identity block by the caller): every loop
+     * over the unknowns has a compile-time trip count and is fully unrolled, so that the thread-local loads of a dot
+     * product or a substitution are issued together instead of one per dependent multiply-add (the lanes wait on
+     * local-memory latency, not on arithmetic). */
+    constexpr int N = VOL_N;
     const int QP_HIST = 32, QP_MAXIT = 256;
-    double G[VOL_N*VOL_N], z[VOL_N], Bm[VOL_M*VOL_N];
-    for(int i=0;i<n;i++) for(int j=0;j<=i;j++){
-      double s = Qm[VOL_N*i+j]; for(int k=0;k<j;k++) s -= G[VOL_N*i+k]*G[VOL_N*j+k];
-      if( i == j ){ if( !(s > 0) ){ bad |= 2; s = 1.0; } G[VOL_N*i+i] = sqrt(s); } else G[VOL_N*i+j] = s/G[VOL_N*j+j];
+    double G[N*N], z[N], Bm[VOL_M*N];
+#pragma unroll
+    for(int i=0;i<N;i++){
+#pragma unroll
+      for(int j=0;j<=i;j++){
+        double s = Qm[N*i+j];
+#pragma unroll
+        for(int k=0;k<j;k++) s -= G[N*i+k]*G[N*j+k];
+        if( i == j ){ if( !(s > 0) ){ bad |= 2; s = 1.0; } G[N*i+i] = sqrt(s); } else G[N*i+j] = s/G[N*j+j];
+      }
     }
-    for(int i=0;i<n;i++){ double s = cv[i]; for(int k=0;k<i;k++) s -= G[VOL_N*i+k]*z[k]; z[i] = s/G[VOL_N*i+i]; }
-    for(int r=0;r<mrows;r++) for(int i=0;i<n;i++){ double s = A[VOL_N*r+i]; for(int k=0;k<i;k++) s -= G[VOL_N*i+k]*Bm[VOL_N*r+k]; Bm[VOL_N*r+i] = s/G[VOL_N*i+i]; }
+    double gi[N];                        /* reciprocals of the diagonal */
+#pragma unroll
+    for(int i=0;i<N;i++) gi[i] = 1.0/G[N*i+i];
+#pragma unroll
+    for(int i=0;i<N;i++){ double s = cv[i];
+#pragma unroll
+      for(int k=0;k<i;k++) s -= G[N*i+k]*z[k];
+      z[i] = s*gi[i]; }
+#pragma unroll 1
+    for(int r=0;r<mrows;r++){
+      double br[N];
+#pragma unroll
+      for(int i=0;i<N;i++){ double s = A[N*r+i];
+#pragma unroll
+        for(int k=0;k<i;k++) s -= G[N*i+k]*br[k];
+        br[i] = s*gi[i]; }
+#pragma unroll
+      for(int i=0;i<N;i++) Bm[N*r+i] = br[i];
+    }
     unsigned idx = 0;
-    for(int i=0;i<mrows;i++){ double s = 0; for(int j=0;j<n;j++) s += A[VOL_N*i+j]*x[j]; if( fabs(s) < ZTOL ) idx |= 1u << i; }
+#pragma unroll 1
+    for(int i=0;i<mrows;i++){ double s = 0;
+#pragma unroll
+      for(int j=0;j<N;j++) s += A[N*i+j]*x[j];
+      if( fabs(s) < ZTOL ) idx |= 1u << i; }
     unsigned hist_idx[QP_HIST]; double hist_obj[QP_HIST]; int nhist = 0;
+#pragma unroll 1
     for(int iter=0; iter<QP_MAXIT; iter++){
       int act[VOL_M]; int ma = 0; VOL_STAT(0, 1);
       for(int i=0;i<mrows;i++) if( idx >> i & 1u ) act[ma++] = i;
-      double xs[VOL_N], lam[VOL_MA], wv[VOL_N];
-      for(int i=0;i<n;i++) wv[i] = -z[i];
+      double xs[N], lam[VOL_MA], wv[N];
+#pragma unroll
+      for(int i=0;i<N;i++) wv[i] = -z[i];
       if( ma > 0 ){
         double S[VOL_MA*VOL_MA], C[VOL_MA*VOL_MA], rhs[VOL_MA], res[VOL_MA];
         double smax = 0;
+#pragma unroll 1
         for(int a=0;a<ma;a++){
-          for(int b=0;b<=a;b++){ double s = 0; for(int j=0;j<n;j++) s += Bm[VOL_N*act[a]+j]*Bm[VOL_N*act[b]+j]; S[VOL_MA*a+b] = s; S[VOL_MA*b+a] = s; }
-          double s = 0; for(int j=0;j<n;j++) s += Bm[VOL_N*act[a]+j]*z[j]; rhs[a] = s; lam[a] = 0.0;
+          double ba[N];
+#pragma unroll
+          for(int j=0;j<N;j++) ba[j] = Bm[N*act[a]+j];
+#pragma unroll 1
+          for(int b=0;b<=a;b++){ double s = 0;
+#pragma unroll
+            for(int j=0;j<N;j++) s += ba[j]*Bm[N*act[b]+j];
+            S[VOL_MA*a+b] = s; S[VOL_MA*b+a] = s; }
+          double s = 0;
+#pragma unroll
+          for(int j=0;j<N;j++) s += ba[j]*z[j];
+          rhs[a] = s; lam[a] = 0.0;
           if( S[VOL_MA*a+a] > smax ) smax = S[VOL_MA*a+a];
         }
         const double eps = 1.0e-9*smax + 1.0e-300;
@@ -310,33 +355,55 @@
           for(int i=ma-1;i>=0;i--){ double s = res[i]; for(int k=i+1;k<ma;k++) s -= C[VOL_MA*k+i]*res[k]; res[i] = s/C[VOL_MA*i+i]; }
           for(int i=0;i<ma;i++) lam[i] += res[i];
         }
-        for(int k=0;k<ma;k++) for(int i=0;i<n;i++) wv[i] += lam[k]*Bm[VOL_N*act[k]+i];
+#pragma unroll 1
+        for(int k=0;k<ma;k++){ const double lk = lam[k];
+#pragma unroll
+          for(int i=0;i<N;i++) wv[i] += lk*Bm[N*act[k]+i]; }
       }
-      for(int i=n-1;i>=0;i--){ double s = wv[i]; for(int k=i+1;k<n;k++) s -= G[VOL_N*k+i]*xs[k]; xs[i] = s/G[VOL_N*i+i]; }
+#pragma unroll
+      for(int i=N-1;i>=0;i--){ double s = wv[i];
+#pragma unroll
+        for(int k=i+1;k<N;k++) s -= G[N*k+i]*xs[k];
+        xs[i] = s*gi[i]; }
       bool stepped = false;
-      for(int i=0;i<n;i++) if( !(fabs(xs[i]-x[i]) < ZTOL) ){ stepped = true; break; }
+#pragma unroll
+      for(int i=0;i<N;i++) stepped = stepped || !(fabs(xs[i]-x[i]) < ZTOL);
       if( !stepped ){
-        for(int i=0;i<n;i++) x[i] = xs[i];
+#pragma unroll
+        for(int i=0;i<N;i++) x[i] = xs[i];
         bool neg = false; for(int k=0;k<ma;k++) if( lam[k] < 0 ){ neg = true; break; }
         if( !neg ) break;
         double lmin = lam[0]; for(int k=1;k<ma;k++) if( lam[k] < lmin ) lmin = lam[k];
         for(int k=0;k<ma;k++) if( fabs(lam[k]-lmin) < 1.0e-8 ) idx &= ~(1u << act[k]);
         continue;
       }
-      double alpha = 1.0;
+      double dx[N], alpha = 1.0;
+#pragma unroll
+      for(int j=0;j<N;j++) dx[j] = xs[j]-x[j];
+#pragma unroll 1
       for(int i=0;i<mrows;i++){
         if( idx >> i & 1u ) continue;
-        double ad = 0, ax = 0; for(int j=0;j<n;j++){ ad += A[VOL_N*i+j]*(xs[j]-x[j]); ax += A[VOL_N*i+j]*x[j]; }
+        double ad = 0, ax = 0;
+#pragma unroll
+        for(int j=0;j<N;j++){ const double aij = A[N*i+j]; ad += aij*dx[j]; ax += aij*x[j]; }
         if( ad < 0 ){ const double t = (0.0 - ax)/ad; if( t < alpha ) alpha = t; }
       }
-      for(int i=0;i<n;i++) x[i] += alpha*(xs[i]-x[i]);
+#pragma unroll
+      for(int i=0;i<N;i++) x[i] += alpha*dx[i];
+#pragma unroll 1
       for(int i=0;i<mrows;i++){
         if( idx >> i & 1u ) continue;
-        double ax = 0; for(int j=0;j<n;j++) ax += A[VOL_N*i+j]*x[j];
+        double ax = 0;
+#pragma unroll
+        for(int j=0;j<N;j++) ax += A[N*i+j]*x[j];
         if( fabs(ax) < ZTOL ) idx |= 1u << i;
       }
       double objv = 0;
-      for(int i=0;i<n;i++){ double s = 0; for(int j=0;j<n;j++) s += Qm[VOL_N*i+j]*x[j]; objv += 0.5*x[i]*s + cv[i]*x[i]; }
+#pragma unroll
+      for(int i=0;i<N;i++){ double s = 0;
+#pragma unroll
+        for(int j=0;j<N;j++) s += Qm[N*i+j]*x[j];
+        objv += 0.5*x[i]*s + cv[i]*x[i]; }
       bool endflag = false;
       for(int h=0;h<nhist && !endflag;h++) if( hist_idx[h] == idx && !(fabs(hist_obj[h]/objv - 1.0) > 1.0e-8) ) endflag = true;
       if( endflag ) break;
@@ -397,9 +464,17 @@
 
   /* static friction (rkfd_volume.c:643-688): is b = (fn, t1, t2, f1, f2, tn) a non-negative combination of the columns
    * g_j = (1, r2, -r1, SF cos_i, SF sin_i, r1 SF sin_i - r2 SF cos_i), j = pyramid * corner + i, i.e. can pyramid forces
-   * at the polygon corners carry the wrench?  Phase 1 of the simplex with Bland's rule exactly as vol_lp (same entering
-   * and leaving choices), in revised form: the 6 x 6 basis inverse instead of the 6 x (columns + 7) tableau, columns
+   * at the polygon corners carry the wrench?  Phase 1 of the simplex in revised form: the 6 x 6 basis inverse instead of the 6 x (columns + 7) tableau, columns
    * generated on the fly - the whole state stays in registers. */
+  static RKFD_HD void vol_static_col(const ModelDev &m, const VolPair &v, int pyr, int nc, const double (&sg)[6], int j, double (&col)[6]){
+    if( j < nc ){
+      const int k = j/pyr, i = j - pyr*k; const double r1 = v.r[k][0], r2 = v.r[k][1], fc = v.SF*m.sc_cos[i], fs = v.SF*m.sc_sin[i];
+      col[0] = sg[0]; col[1] = sg[1]*r2; col[2] = -sg[2]*r1; col[3] = sg[3]*fc; col[4] = sg[4]*fs; col[5] = -sg[5]*( (-r1)*fs + r2*fc );
+    } else {
+#pragma unroll
+      for(int i=0;i<6;i++) col[i] = i == j-nc ? 1.0 : 0.0;
+    }
+  }
   RKFD_VOL_NI bool vol_static_feasible(const ModelDev &m, const VolPair &v, int np, const double (&b)[6]){
     const int pyr = m.pyramid, nc = pyr*np, nt = nc + 6;
     double Bi[36], xb[6], sg[6]; int basis[6]; double bmax = 0;
@@ -415,33 +490,32 @@
       for(int j=0;j<6;j++){ double s = 0;
 #pragma unroll
         for(int i=0;i<6;i++) s += basis[i] >= nc ? Bi[6*i+j] : 0.0; y[j] = s; }
-      int enter = -1;
-      for(int j=0;j<nt && enter<0;j++){
+      /* entering column: the most negative reduced cost (Dantzig; every lane scans all columns: no divergence, a third of
+       * Bland's pivots); Bland's first negative column after 48 pivots (anti-cycling: the start is degenerate whenever
+       * a friction component of b is zero).  The verdict does not depend on the rule. */
+      int enter = -1; double rcmin = -1.0e-11;
+      for(int j=0;j<nt;j++){
         bool bas = false;
 #pragma unroll
         for(int i=0;i<6;i++) bas = bas || basis[i] == j;
         if( bas ) continue;
-        if( j < nc ){
-          const int k = j/pyr, i = j - pyr*k; const double r1 = v.r[k][0], r2 = v.r[k][1], fc = v.SF*m.sc_cos[i], fs = v.SF*m.sc_sin[i];
-          col[0] = sg[0]; col[1] = sg[1]*r2; col[2] = -sg[2]*r1; col[3] = sg[3]*fc; col[4] = sg[4]*fs; col[5] = -sg[5]*( (-r1)*fs + r2*fc );
-        } else {
-#pragma unroll
-          for(int i=0;i<6;i++) col[i] = i == j-nc ? 1.0 : 0.0;
-        }
+        double cj[6];
+        vol_static_col(m, v, pyr, nc, sg, j, cj);
         double rc = j >= nc ? 1.0 : 0.0;
 #pragma unroll
-        for(int i=0;i<6;i++) rc -= y[i]*col[i];
-        if( rc < -1.0e-11 ) enter = j;
+        for(int i=0;i<6;i++) rc -= y[i]*cj[i];
+        if( rc < rcmin ){ rcmin = rc; enter = j; if( it >= 48 ) break; }
       }
+      if( enter >= 0 ) vol_static_col(m, v, pyr, nc, sg, enter, col);
       if( enter < 0 ) break;
-      double d[6]; int leave = -1; double best = 0;
+      double d[6]; int leave = -1, lbas = 0; double best = 0;
 #pragma unroll
       for(int i=0;i<6;i++){ double s = 0;
 #pragma unroll
         for(int j=0;j<6;j++) s += Bi[6*i+j]*col[j]; d[i] = s; }
 #pragma unroll
       for(int i=0;i<6;i++) if( d[i] > 1.0e-11 ){ const double ratio = xb[i]/d[i];
-        if( leave < 0 || ratio < best - 1.0e-13 || ( fabs(ratio-best) <= 1.0e-13 && basis[i] < basis[leave < 0 ? 0 : leave] ) ){ leave = i; best = ratio; } }
+        if( leave < 0 || ratio < best - 1.0e-13 || ( fabs(ratio-best) <= 1.0e-13 && basis[i] < lbas ) ){ leave = i; lbas = basis[i]; best = ratio; } }
       if( leave < 0 ) return false;
       double prow[6], pv = 0, px = 0;
 #pragma unroll
@@ -574,8 +648,12 @@
       }
       x[6*k] = v.norm.x; x[6*k+1] = v.norm.y; x[6*k+2] = v.norm.z;
     }
+    /* a single pair: identity block for the unused unknowns (they stay zero) */
+    for(int i=n;i<VOL_N;i++){ cv[i] = 0.0; x[i] = 0.0;
+      for(int j=0;j<VOL_N;j++){ Qm[VOL_N*i+j] = i == j ? 1.0 : 0.0; Qm[VOL_N*j+i] = i == j ? 1.0 : 0.0; }
+      for(int r=0;r<mrows;r++) nf[VOL_N*r+i] = 0.0; }
     unsigned idx = 0; VOL_STAT(6, 1);
-    vol_asm(n, mrows, Qm, cv, nf, x, idx);
+    vol_asm(mrows, Qm, cv, nf, x, idx);
     /* ---- f /= dt, _rkFDSolverSetForce (:552-568; the offset is not advanced for a pair without planes - mirrored) */
     { int off = 0;
       for(int k=0;k<P;k++){ VolPair &v = vp[k];
