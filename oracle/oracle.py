@@ -68,6 +68,7 @@ def lib():
         L.ork_env_energy.argtypes = [C.c_void_p]
         L.ork_env_get_rigid_system.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int]
         L.ork_batch_run.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp]
+        L.ork_batch_run_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp, _ip, _ip, _dp, _ip]
         L.ork_qp_solve_asm.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip]
         L.ork_le_solve_mp_sym.argtypes = [C.c_int, _dp, _dp, _dp]
         L.ork_env_get_volume.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
@@ -158,6 +159,22 @@ class OracleWorld:
             u, pu = _d(u)
         used = lib().ork_batch_run(self.h, B, pq, pqd, pu, nsteps, nthreads, qdd.ctypes.data_as(_dp))
         return q, qd, qdd, used
+
+    def batch_run_state(self, q, qd, u=None, nsteps=1, nthreads=0):
+        """batch_run plus the final contact / pivot state: (q, qd, qdd, active, type, contact force, pivot type)."""
+        q, pq = _d(np.array(q, dtype=np.float64, copy=True))
+        qd, pqd = _d(np.array(qd, dtype=np.float64, copy=True))
+        B, ns, nq = q.shape[0], max(self.nslot, 1), max(self.nq, 1)
+        qdd = np.zeros_like(q)
+        pu = None
+        if u is not None:
+            u, pu = _d(u)
+        act, typ, piv = np.zeros((B, ns), np.int32), np.zeros((B, ns), np.int32), np.zeros((B, nq), np.int32)
+        cf = np.zeros((B, ns, 3))
+        lib().ork_batch_run_state(self.h, B, pq, pqd, pu, nsteps, nthreads, qdd.ctypes.data_as(_dp), act.ctypes.data_as(_ip),
+                                  typ.ctypes.data_as(_ip), cf.ctypes.data_as(_dp), piv.ctypes.data_as(_ip))
+        n = self.nslot
+        return q, qd, qdd, act[:, :n], typ[:, :n], cf[:, :n], piv[:, :self.nq]
 
 
 class OracleEnv:

@@ -1436,6 +1436,39 @@ int ork_env_get_rigid_system(const ork_env *e, double *A, double *b, double *f, 
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* as ork_batch_run, plus the final contact / pivot state of every env (any pointer may be NULL):
+ * act, type [B][nslot], cf [B][nslot][3] contact forces of the last committing evaluation, piv [B][nq] */
+int ork_batch_run_state(const ork_world *w, int B, double *q, double *qd, const double *u,
+                        int nsteps, int nthreads, double *qdd_out, int *act, int *type, double *cf, int *piv)
+{
+  int used = 1, nq = w->nq, nl = w->nl, ns = w->nslot;
+#ifdef _OPENMP
+  if( nthreads > 0 ) omp_set_num_threads(nthreads);
+  used = omp_get_max_threads();
+#endif
+#pragma omp parallel
+  {
+    ork_env *e = ork_env_new(w); int b, s;
+#pragma omp for schedule(dynamic,16)
+    for(b=0;b<B;b++){
+      int i;
+      e->t = 0;
+      for(i=0;i<nq;i++){ e->piv_type[i] = ORK_SF; e->piv_prev[i] = 0; e->tf[i] = 0; }
+      for(i=0;i<ns;i++) e->c_active[i] = 0;
+      ork_env_set_state(e,q+(size_t)nq*b,qd+(size_t)nq*b);
+      if( u ) ork_env_set_motor_input(e,u+(size_t)nl*b); else memset(e->min,0,nl*8);
+      ork_env_update_init(e);
+      for(s=0;s<nsteps;s++) ork_env_update(e);
+      ork_env_get_state(e,q+(size_t)nq*b,qd+(size_t)nq*b,qdd_out?qdd_out+(size_t)nq*b:NULL);
+      if( act ) memcpy(act+(size_t)ns*b,e->c_active,ns*sizeof(int));
+      if( type ) memcpy(type+(size_t)ns*b,e->c_type,ns*sizeof(int));
+      if( cf ) memcpy(cf+(size_t)3*ns*b,e->c_f,3*ns*8);
+      if( piv ) memcpy(piv+(size_t)nq*b,e->piv_type,nq*sizeof(int));
+    }
+    ork_env_free(e);
+  }
+  return used;
+}
 int ork_batch_run(const ork_world *w, int B, double *q, double *qd, const double *u,
                   int nsteps, int nthreads, double *qdd_out)
 {

@@ -110,6 +110,9 @@ int ork_lp_solve(int m, int n, const double *A, const double *b, const double *c
 int ork_batch_run(const ork_world *w, int B, double *q, double *qd, const double *u,
                   int nsteps, int nthreads, double *qdd_out);
 
+int ork_batch_run_state(const ork_world *w, int B, double *q, double *qd, const double *u,
+                        int nsteps, int nthreads, double *qdd_out, int *act, int *type, double *cf, int *piv);
+
 /* ---- standalone pieces exported for unit tests ---------------------------------- */
 /* rkFDQPSolveASM restatement (reference rkfd_opt_qp.c:43-181) with the default cond
  * (row . x).  q: n x n, c: n, a: m x n, b: m, ans: n (out), idx: m (out).  Returns iterations. */

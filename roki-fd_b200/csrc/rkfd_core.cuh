@@ -1880,7 +1880,9 @@ struct Core {
       /* rigid pairs in contact (reference rkfd_vert.c:385-386): any lane of the warp -> cooperative solve.
        * Round 0 = rkFDUpdateAccBias (rkfd_util.c:149-161): the inward/outward passes without contact forces, then the
        * solve; round 1 = the evaluation proper.  One rolled loop so that the passes exist once in the kernel. */
-      const unsigned act = c.ballot( RKFD_POPC64(cfl & m.rigid_mask) > 0 );
+      unsigned act = c.ballot( RKFD_POPC64(cfl & m.rigid_mask) > 0 );
+      /* Volume solver: the decision is taken per BLOCK, its solve has block barriers between its phases (rkfd_volume.cuh) */
+      if constexpr ( Spec::NL == 0 ){ if( m.solver == S_VOLUME ) act = c.block_or(act != 0) ? 1u : 0u; }
 #pragma unroll 1
       for(int round = act ? 0 : 1; round < 2; round++){
         pass2(m, round ? ref : false);

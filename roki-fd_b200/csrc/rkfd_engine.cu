@@ -111,7 +111,7 @@ template <class T> static T *dalloc(Shard &s, size_t n)
 #define RKFD_VARIANT_LIST(X) \
   X(128,0,1,7,2) X(64,0,1,7,4) X(128,0,0,5,4) X(128,0,0,8,4) X(128,0,0,9,4) X(128,0,0,10,4) X(128,0,0,11,2) X(256,0,0,5,2) X(512,0,0,5,1) X(256,0,0,6,2) X(256,0,0,3,2) X(512,0,0,3,1) X(128,0,0,3,4) X(128,0,0,3,3) X(128,0,0,4,4) X(128,0,0,1,1) X(256,0,0,1,1) X(128,0,0,2,1) \
   X(128,0,0,0,1) X(256,0,0,0,1) X(64,0,0,0,1) X(32,0,0,0,1) X(64,1,0,0,1) \
-  X(128,0,1,0,1) X(256,0,1,0,1) X(64,0,1,0,1) X(32,0,1,0,1) X(64,1,1,0,1) X(128,1,1,0,4)
+  X(128,0,1,0,1) X(256,0,1,0,1) X(64,0,1,0,1) X(32,0,1,0,1) X(64,1,1,0,1) X(128,1,1,0,4) X(256,1,1,0,1)
 #define RKFD_DECL(B,G,R,S,M) extern const KernelVariant rkfd_variant_##B##_##G##_##R##_##S##_##M;
 RKFD_VARIANT_LIST(RKFD_DECL)
 #undef RKFD_DECL
@@ -174,8 +174,13 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
      * thread-local memory anyway and the 291-double column of a legged tree leaves room for 2 warps per SM only (C4,
      * 131,072 envs: 130 -> 103 ms per step) */
     const int pass0 = ( std::getenv("RKFD_FORCE_GSCR") || ( model.has_rigid && model.solver == S_VOLUME && !std::getenv("RKFD_FORCE_SMEM") ) ) ? 2 : 0;
+    /* Volume solver: one 256-thread block per SM - its phases are separated by block barriers, so that the eight warps of
+     * an SM stay inside the same piece of code (C4, 131,072 envs: 68 ms per step with 64-thread blocks, 55 ms with 256) */
+    const bool volume = model.has_rigid && model.solver == S_VOLUME;
+    for(int attempt = volume ? 0 : 1; attempt < 2 && best == 0; attempt++)
     for(int pass=pass0; pass<3 && best==0; pass++)
       for(const KernelVariant *kv : g_variants){
+        if( attempt == 0 && !std::getenv("RKFD_FORCE_BLOCK") && kv->block != 256 ) continue;
         /* pass 0: a matching specialisation; 1: generic, shared-memory scratch; 2: generic, scratch in HBM */
         if( kv->rigid != rigid || kv->gscr != (pass == 2) ) continue;
         if( pass == 0 ? !( kv->spec > 0 && (specs >> kv->spec & 1u) ) : kv->spec != 0 ) continue;

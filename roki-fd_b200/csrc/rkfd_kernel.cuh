@@ -70,6 +70,7 @@ struct DevCtx {
   __device__ __forceinline__ void select(int src){ tid = (tid0 & ~31) | src; e = (e0 & ~31) | src; }
   __device__ __forceinline__ void unselect(){ tid = tid0; e = e0; }
   __device__ __forceinline__ void gsync() const { __syncwarp(); }
+  __device__ __forceinline__ bool block_or(bool p) const { return __syncthreads_or(p) != 0; }     /* block-uniform call sites only */
 #ifndef RKFD_SYNC_LEVEL
 #define RKFD_SYNC_LEVEL 2
 #endif

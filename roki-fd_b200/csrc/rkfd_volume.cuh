@@ -26,6 +26,14 @@
 #else
 #define VOL_STAT(i, n)
 #endif
+/* loops over the unknowns of the QP: rolled.  The solver is instruction-fetch bound (ncu: 11 no_instruction stall cycles per
+ * issued instruction with 8 divergent warps per SM walking through 350 KB of solver code): unrolling them (RKFD_VOL_UNROLL)
+ * batches the thread-local loads but costs 58 KB more code and measured 76 against 68 ms per step (C4, 131,072 envs). */
+#ifdef RKFD_VOL_UNROLL
+#define RKFD_VOL_U _Pragma("unroll")
+#else
+#define RKFD_VOL_U _Pragma("unroll 1")
+#endif
 #ifdef __CUDACC__
 #define RKFD_VOL_NI __host__ __device__ __noinline__
 #else
@@ -42,7 +50,7 @@
   static RKFD_HD bool vtiny(double x){ return fabs(x) < ZTOL; }
 
   /* _rkFDSolverSetContactPlane (rkfd_volume.c:350-374) */
-  RKFD_HD void vol_set_plane(VolPair &vp, V3 p, V3 fnorm){
+  RKFD_VOL_NI void vol_set_plane(VolPair &vp, V3 p, V3 fnorm){
     const V3 t = fnorm - dot(fnorm, vp.norm)*vp.norm;
     if( vtiny(t.x) && vtiny(t.y) && vtiny(t.z) ) return;
     const V3 cn = (-1.0/norm(t))*t;
@@ -60,7 +68,7 @@
     vp.plv[vp.npl] = p; vp.pln[vp.npl] = cn; vp.npl++;
   }
   /* _rkFDSolverConstraintMidDepth + _rkFDSolverConstraintDepth (rkfd_volume.c:232-241, 296-310) */
-  static RKFD_HD void vol_cc(const V3 (&p)[3], const double (&h)[3], double K, V3 nrm, double (&cc)[6]){
+  static RKFD_VOL_NI void vol_cc(const V3 (&p)[3], const double (&h)[3], double K, V3 nrm, double (&cc)[6]){
     const double s = 0.5*norm(cross(p[1]-p[0], p[2]-p[0])), k = K*s/6.0;
     const double hm0 = k*(h[0]+h[1]), hm1 = k*(h[1]+h[2]), hm2 = k*(h[0]+h[2]), hc = k*(h[0]+h[1]+h[2])*2;
     const V3 m0 = 0.5*(p[0]+p[1]), m1 = 0.5*(p[1]+p[2]), m2 = 0.5*(p[2]+p[0]);
@@ -68,7 +76,7 @@
     cc[0] = -hc*nrm.x; cc[1] = -hc*nrm.y; cc[2] = -hc*nrm.z; cc[3] = a.x; cc[4] = a.y; cc[5] = a.z;
   }
   /* _rkFDSolverConstraintInnerPoint (rkfd_volume.c:331-348) */
-  static RKFD_HD V3 vol_inner(V3 p1, V3 p2, double h1, double h2){
+  static RKFD_VOL_NI V3 vol_inner(V3 p1, V3 p2, double h1, double h2){
     if( vtiny(h1) ) return p1;
     if( vtiny(h2) ) return p2;
     if( vtiny(h2-h1) ) return 0.5*(p1+p2);
@@ -204,7 +212,6 @@
   /* acceleration response (frame of link Lt) of link Lt to the bias change (dpf, dpn) on link Lc of the same tree
    * ([EXT A-5]; probe_link with a separate target) */
   RKFD_VOL_NI void vol_probe(const ModelDev &m, int Lc, V3 dpf, V3 dpn, int Lt, V3 &ral, V3 &raa){
-    if( Lt == Lc ){ probe_link(m, Lc, dpf, dpn, ral, raa); return; }
     double du[6*MAX_LINKS]; int pth[MAX_LINKS]; int np = 0;
     for(int i=Lc;;){
       const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = Spec::jtype(i,L);
@@ -276,45 +283,43 @@
    * eigen-decomposition.  x holds the initial point on entry.  idx: active flags. */
   RKFD_VOL_NI void vol_asm(int mrows, const double *Qm, const double *cv, const double *A, double *x, unsigned &idx_out){
     /* The problem always has VOL_N unknowns (a single pair is padded with an identity block by the caller): every loop
-     * over the unknowns has a compile-time trip count and is fully unrolled, so that the thread-local loads of a dot
-     * product or a substitution are issued together instead of one per dependent multiply-add (the lanes wait on
-     * local-memory latency, not on arithmetic). */
+     * over the unknowns has a compile-time trip count (RKFD_VOL_U above decides whether it is unrolled). */
     constexpr int N = VOL_N;
     const int QP_HIST = 32, QP_MAXIT = 256;
     double G[N*N], z[N], Bm[VOL_M*N];
-#pragma unroll
+RKFD_VOL_U
     for(int i=0;i<N;i++){
-#pragma unroll
+RKFD_VOL_U
       for(int j=0;j<=i;j++){
         double s = Qm[N*i+j];
-#pragma unroll
+RKFD_VOL_U
         for(int k=0;k<j;k++) s -= G[N*i+k]*G[N*j+k];
         if( i == j ){ if( !(s > 0) ){ bad |= 2; s = 1.0; } G[N*i+i] = sqrt(s); } else G[N*i+j] = s/G[N*j+j];
       }
     }
     double gi[N];                        /* reciprocals of the diagonal */
-#pragma unroll
+RKFD_VOL_U
     for(int i=0;i<N;i++) gi[i] = 1.0/G[N*i+i];
-#pragma unroll
+RKFD_VOL_U
     for(int i=0;i<N;i++){ double s = cv[i];
-#pragma unroll
+RKFD_VOL_U
       for(int k=0;k<i;k++) s -= G[N*i+k]*z[k];
       z[i] = s*gi[i]; }
 #pragma unroll 1
     for(int r=0;r<mrows;r++){
       double br[N];
-#pragma unroll
+RKFD_VOL_U
       for(int i=0;i<N;i++){ double s = A[N*r+i];
-#pragma unroll
+RKFD_VOL_U
         for(int k=0;k<i;k++) s -= G[N*i+k]*br[k];
         br[i] = s*gi[i]; }
-#pragma unroll
+RKFD_VOL_U
       for(int i=0;i<N;i++) Bm[N*r+i] = br[i];
     }
     unsigned idx = 0;
 #pragma unroll 1
     for(int i=0;i<mrows;i++){ double s = 0;
-#pragma unroll
+RKFD_VOL_U
       for(int j=0;j<N;j++) s += A[N*i+j]*x[j];
       if( fabs(s) < ZTOL ) idx |= 1u << i; }
     unsigned hist_idx[QP_HIST]; double hist_obj[QP_HIST]; int nhist = 0;
@@ -323,7 +328,7 @@
       int act[VOL_M]; int ma = 0; VOL_STAT(0, 1);
       for(int i=0;i<mrows;i++) if( idx >> i & 1u ) act[ma++] = i;
       double xs[N], lam[VOL_MA], wv[N];
-#pragma unroll
+RKFD_VOL_U
       for(int i=0;i<N;i++) wv[i] = -z[i];
       if( ma > 0 ){
         double S[VOL_MA*VOL_MA], C[VOL_MA*VOL_MA], rhs[VOL_MA], res[VOL_MA];
@@ -331,15 +336,15 @@
 #pragma unroll 1
         for(int a=0;a<ma;a++){
           double ba[N];
-#pragma unroll
+RKFD_VOL_U
           for(int j=0;j<N;j++) ba[j] = Bm[N*act[a]+j];
 #pragma unroll 1
           for(int b=0;b<=a;b++){ double s = 0;
-#pragma unroll
+RKFD_VOL_U
             for(int j=0;j<N;j++) s += ba[j]*Bm[N*act[b]+j];
             S[VOL_MA*a+b] = s; S[VOL_MA*b+a] = s; }
           double s = 0;
-#pragma unroll
+RKFD_VOL_U
           for(int j=0;j<N;j++) s += ba[j]*z[j];
           rhs[a] = s; lam[a] = 0.0;
           if( S[VOL_MA*a+a] > smax ) smax = S[VOL_MA*a+a];
@@ -357,19 +362,19 @@
         }
 #pragma unroll 1
         for(int k=0;k<ma;k++){ const double lk = lam[k];
-#pragma unroll
+RKFD_VOL_U
           for(int i=0;i<N;i++) wv[i] += lk*Bm[N*act[k]+i]; }
       }
-#pragma unroll
+RKFD_VOL_U
       for(int i=N-1;i>=0;i--){ double s = wv[i];
-#pragma unroll
+RKFD_VOL_U
         for(int k=i+1;k<N;k++) s -= G[N*k+i]*xs[k];
         xs[i] = s*gi[i]; }
       bool stepped = false;
-#pragma unroll
+RKFD_VOL_U
       for(int i=0;i<N;i++) stepped = stepped || !(fabs(xs[i]-x[i]) < ZTOL);
       if( !stepped ){
-#pragma unroll
+RKFD_VOL_U
         for(int i=0;i<N;i++) x[i] = xs[i];
         bool neg = false; for(int k=0;k<ma;k++) if( lam[k] < 0 ){ neg = true; break; }
         if( !neg ) break;
@@ -378,30 +383,30 @@
         continue;
       }
       double dx[N], alpha = 1.0;
-#pragma unroll
+RKFD_VOL_U
       for(int j=0;j<N;j++) dx[j] = xs[j]-x[j];
 #pragma unroll 1
       for(int i=0;i<mrows;i++){
         if( idx >> i & 1u ) continue;
         double ad = 0, ax = 0;
-#pragma unroll
+RKFD_VOL_U
         for(int j=0;j<N;j++){ const double aij = A[N*i+j]; ad += aij*dx[j]; ax += aij*x[j]; }
         if( ad < 0 ){ const double t = (0.0 - ax)/ad; if( t < alpha ) alpha = t; }
       }
-#pragma unroll
+RKFD_VOL_U
       for(int i=0;i<N;i++) x[i] += alpha*dx[i];
 #pragma unroll 1
       for(int i=0;i<mrows;i++){
         if( idx >> i & 1u ) continue;
         double ax = 0;
-#pragma unroll
+RKFD_VOL_U
         for(int j=0;j<N;j++) ax += A[N*i+j]*x[j];
         if( fabs(ax) < ZTOL ) idx |= 1u << i;
       }
       double objv = 0;
-#pragma unroll
+RKFD_VOL_U
       for(int i=0;i<N;i++){ double s = 0;
-#pragma unroll
+RKFD_VOL_U
         for(int j=0;j<N;j++) s += Qm[N*i+j]*x[j];
         objv += 0.5*x[i]*s + cv[i]*x[i]; }
       bool endflag = false;
@@ -541,6 +546,12 @@
     return !(art > eps);
   }
 
+  /* rkFDKineticFrictionWeight (rkfd_util.c:193-196) times KF / |v|, tangential slip velocity of the point in `vel` */
+  RKFD_VOL_NI double vol_slip(const ModelDev &m, const VolPair &v, V3 p, V3 &vel){
+    vel = vol_point_vel(v, p); vel = vel - dot(v.norm, vel)*v.norm;
+    const double nv = norm(vel);
+    return vtiny(nv) ? 0.0 : (1.0 - exp(-1.0*m.friction_weight*nv))*v.KF/nv;
+  }
   RKFD_HD V3 vol_point_vel(const VolPair &vp, V3 p){     /* rkFDLinkPointWldVel (rkfd_util.c:14-24), static partner */
     const M3 Rw = ldm(vp.fsl); const V3 pw = ld3(vp.fsl+9), vl = ld3(vp.fsl+12), om = ld3(vp.fsl+15);
     return mul(Rw, vl) + cross(mul(Rw, om), p - pw);
@@ -548,8 +559,10 @@
 
   /* _rkFDSolverVolume (rkfd_volume.c:939-957) for this lane's environment */
   RKFD_VOL_NI void rigid_volume(const ModelDev &m, bool ref){
+    /* Every thread of the block walks through the phases below (lanes and warps without a contact volume with P = 0, i.e.
+     * empty loops), with a block barrier between phases: the warps of an SM then execute the same few KB of code at any
+     * time instead of eight different parts of the 350 KB solver (instruction-fetch stalls dominated the profile). */
     const unsigned long long fl = cfl;
-    if( RKFD_POPC64(fl & m.rigid_mask) == 0 ) return;
     VolPair vp[VOL_P]; int P = 0;
     /* ---- contact volumes (rkFDSolverColChk_Volume, [EXT A-15]) */
     for(int pi=0;pi<m.npair;pi++){
@@ -579,13 +592,13 @@
       if( empty ) continue;
       /* rkCDPlaneListQuickSort with __rk_fd_plane_cmp (:376-395): ascending angle key, ties keep their order */
       { double th[VOL_PL];
-        for(int i=0;i<v.npl;i++){ const V3 t = cross(v.a1, v.pln[i]); th[i] = dot(t, v.norm) > 0 ? atan2(-norm(t), dot(v.a1, v.pln[i])) : atan2(norm(t), dot(v.a1, v.pln[i])); }
+        for(int i=0;i<v.npl;i++){ const V3 t = cross(v.a1, v.pln[i]); const double y = norm(t); th[i] = atan2(dot(t, v.norm) > 0 ? -y : y, dot(v.a1, v.pln[i])); }
         for(int i=1;i<v.npl;i++){ const V3 tv = v.plv[i], tn = v.pln[i]; const double a = th[i]; int j = i-1;
           for(;j>=0 && !(fabs(th[j]-a) < ZTOL) && th[j] > a;j--){ v.plv[j+1] = v.plv[j]; v.pln[j+1] = v.pln[j]; th[j+1] = th[j]; }
           v.plv[j+1] = tv; v.pln[j+1] = tn; th[j+1] = a; } }
       P++;
     }
-    if( P == 0 ) return;
+    c.phase_sync(1);
     const int n = 6*P;
     /* ---- A (6P x 6P), b: probes at the volume centres (rkfd_volume.c:141-226) */
     double A[VOL_N*VOL_N], b[VOL_N];
@@ -620,6 +633,7 @@
         }
       }
     }
+    c.phase_sync(1);
     /* ---- QP (rkfd_volume.c:496-548) */
     double Qm[VOL_N*VOL_N], cv[VOL_N], nf[VOL_M*VOL_N], x[VOL_N];
     for(int i=0;i<n;i++){ cv[i] = 0.0; x[i] = 0.0; for(int j=0;j<n;j++) Qm[VOL_N*i+j] = 0.0; }
@@ -653,7 +667,9 @@
       for(int j=0;j<VOL_N;j++){ Qm[VOL_N*i+j] = i == j ? 1.0 : 0.0; Qm[VOL_N*j+i] = i == j ? 1.0 : 0.0; }
       for(int r=0;r<mrows;r++) nf[VOL_N*r+i] = 0.0; }
     unsigned idx = 0; VOL_STAT(6, 1);
-    vol_asm(mrows, Qm, cv, nf, x, idx);
+    c.phase_sync(1);
+    if( P > 0 ) vol_asm(mrows, Qm, cv, nf, x, idx);
+    c.phase_sync(1);
     /* ---- f /= dt, _rkFDSolverSetForce (:552-568; the offset is not advanced for a pair without planes - mirrored) */
     { int off = 0;
       for(int k=0;k<P;k++){ VolPair &v = vp[k];
@@ -704,10 +720,8 @@
         if( vtiny(tl) ){
           wv[3] = wv[4] = wv[5] = 0;
           if( !vtiny(fs) && fs > v.SF*fn ){
-            V3 vel = vol_point_vel(v, v.center); vel = vel - dot(v.norm, vel)*v.norm;
-            const double nv = norm(vel);
-            if( vtiny(nv) ){ wv[1] = 0; wv[2] = 0; }
-            else { const double t = (1.0 - exp(-1.0*m.friction_weight*nv))*v.KF*wv[0]/nv; wv[1] = -t*dot(vel, v.a1); wv[2] = -t*dot(vel, v.a2); }
+            V3 vel; const double t = vol_slip(m, v, v.center, vel)*wv[0];
+            wv[1] = -t*dot(vel, v.a1); wv[2] = -t*dot(vel, v.a2);
             kinetic = 1;
           }
           setforce = true;
@@ -725,10 +739,8 @@
           mb[0] = wv[0]; mb[1] = wv[4]; mb[2] = wv[5];
           for(int i=0;i<3;i++) wn[i] = vtiny(wv[i+1]) ? 0.0 : 1.0/wv[i+1];
           for(int j=0;j<np;j++){
-            V3 vel = vol_point_vel(v, v.center + v.plv[j]); vel = vel - dot(v.norm, vel)*v.norm;
-            const double nv = norm(vel);
-            if( vtiny(nv) ){ v.s[j][0] = 0; v.s[j][1] = 0; }
-            else { const double ww = (1.0 - exp(-1.0*m.friction_weight*nv))*v.KF/nv; v.s[j][0] = -ww*dot(vel, v.a1); v.s[j][1] = -ww*dot(vel, v.a2); }
+            V3 vel; const double ww = vol_slip(m, v, v.center + v.plv[j], vel);
+            v.s[j][0] = -ww*dot(vel, v.a1); v.s[j][1] = -ww*dot(vel, v.a2);
             mc[j] = -wn[0]*v.s[j][0] - wn[1]*v.s[j][1] - wn[2]*( v.r[j][0]*v.s[j][1] - v.r[j][1]*v.s[j][0] );
           }
           if( !vol_lp(3, np, ma, mb, mc, mf) ){
@@ -757,4 +769,5 @@
         } }
     }
     cfl = nfl;
+    c.phase_sync(1);
   }

@@ -39,6 +39,7 @@ struct HostCtx {
   void select(int){}
   void unselect(){}
   void gsync(){}
+  bool block_or(bool p) const { return p; }
   void phase_sync(int){}
   double &W(int i){ return wsp[i]; }
   double &W1(int i){ return st.ws1[(size_t)i*st.ld + e]; }
