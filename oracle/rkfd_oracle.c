@@ -960,13 +960,14 @@ static int vol_build(ork_env *e, int pi, ork_vpair *vp)
         ang[j+1] = a; v3_copy(t,u[j+1]); }
       for(i=1;i+1<nu;i++) vol_emit(vp,u[0],u[i],u[i+1],vp->norm);
     } }
-  /* barycentre (signed tetrahedra about the cell centre; triangles are outward oriented) */
+  /* barycentre (signed tetrahedra about a point of the clipping plane: a thin volume is then a sum of thin tetrahedra
+   * instead of the small difference of large ones; triangles are outward oriented) */
   for(i=0;i<vp->ntri;i++){ double a[3], b[3], c[3], cr[3], v6;
-    v3_sub(vp->tri[i],cen,a); v3_sub(vp->tri[i]+3,cen,b); v3_sub(vp->tri[i]+6,cen,c);
+    v3_sub(vp->tri[i],p0,a); v3_sub(vp->tri[i]+3,p0,b); v3_sub(vp->tri[i]+6,p0,c);
     v3_cross(b,c,cr); v6 = v3_dot(a,cr)/6.0; vol += v6;
     for(j=0;j<3;j++) bc[j] += v6*0.25*(a[j]+b[j]+c[j]); }
   if( !(vol > 1.0e-18) ) return 0;
-  for(j=0;j<3;j++) vp->center[j] = cen[j] + bc[j]/vol;
+  for(j=0;j<3;j++) vp->center[j] = p0[j] + bc[j]/vol;
   return 1;
 }
 

@@ -278,7 +278,7 @@
    * which is the KKT system [[-Q, A_W^T],[A_W, 0]] [x; lambda] = [c; 0] of the reference (rkfd_opt_qp.c:82-106).  The
    * reference solves it with zLESolveMP: when active rows are dependent (an unloaded sole has ALL its rows active) the
    * multipliers are the minimum-norm ones.  Here: lambda = S^+ (B_W z) by iterated Tikhonov regularisation -
-   * lambda += (S + eps I)^-1 (B_W z - S lambda), one Cholesky factorisation and four refinements - which converges to the
+   * lambda += (S + eps I)^-1 (B_W z - S lambda), one Cholesky factorisation and refinements to rounding - which converges to the
    * minimum-norm solution of the (always consistent) system and is the plain solve when S is regular: one code path, no
    * eigen-decomposition.  x holds the initial point on entry.  idx: active flags. */
   RKFD_VOL_NI void vol_asm(int mrows, const double *Qm, const double *cv, const double *A, double *x, unsigned &idx_out){
@@ -354,11 +354,15 @@ RKFD_VOL_U
           double s = S[VOL_MA*i+j] + ( i == j ? eps : 0.0 ); for(int k=0;k<j;k++) s -= C[VOL_MA*i+k]*C[VOL_MA*j+k];
           if( i == j ) C[VOL_MA*i+i] = sqrt(s > 0 ? s : eps); else C[VOL_MA*i+j] = s/C[VOL_MA*j+j];
         }
-        for(int ref=0; ref<5; ref++){
+        /* at most six refinements, fewer when the update is below rounding (2 when S is regular and well conditioned; a
+         * singular value s of S converges with the factor eps / (s + eps) per step) */
+        for(int ref=0; ref<6; ref++){
           for(int i=0;i<ma;i++){ double s = rhs[i]; for(int k=0;k<ma;k++) s -= S[VOL_MA*i+k]*lam[k]; res[i] = s; }
           for(int i=0;i<ma;i++){ double s = res[i]; for(int k=0;k<i;k++) s -= C[VOL_MA*i+k]*res[k]; res[i] = s/C[VOL_MA*i+i]; }
           for(int i=ma-1;i>=0;i--){ double s = res[i]; for(int k=i+1;k<ma;k++) s -= C[VOL_MA*k+i]*res[k]; res[i] = s/C[VOL_MA*i+i]; }
-          for(int i=0;i<ma;i++) lam[i] += res[i];
+          double dmax = 0, lmax = 0;
+          for(int i=0;i<ma;i++){ lam[i] += res[i]; if( fabs(res[i]) > dmax ) dmax = fabs(res[i]); if( fabs(lam[i]) > lmax ) lmax = fabs(lam[i]); }
+          if( dmax <= 1.0e-14*lmax ) break;
         }
 #pragma unroll 1
         for(int k=0;k<ma;k++){ const double lk = lam[k];
