@@ -1874,21 +1874,32 @@ struct Core {
     c.phase_sync(1);
     c.tfence();               /* T-space stores of the previous pass are complete before this pass loads them */
     pass1(m, ref, stage == ST_K1 || stage >= ST_EVAL);
-    if( !Ctx::RIGID ) c.phase_sync(2);
+    c.phase_sync(2);
     c.tfence();
     if( Ctx::RIGID ){
       /* rigid pairs in contact (reference rkfd_vert.c:385-386): any lane of the warp -> cooperative solve.
        * Round 0 = rkFDUpdateAccBias (rkfd_util.c:149-161): the inward/outward passes without contact forces, then the
-       * solve; round 1 = the evaluation proper.  One rolled loop so that the passes exist once in the kernel. */
-      unsigned act = c.ballot( RKFD_POPC64(cfl & m.rigid_mask) > 0 );
-      /* Volume solver: the decision is taken per BLOCK, its solve has block barriers between its phases (rkfd_volume.cuh) */
-      if constexpr ( Spec::NL == 0 ){ if( m.solver == S_VOLUME ) act = c.block_or(act != 0) ? 1u : 0u; }
+       * solve; round 1 = the evaluation proper.  One rolled loop so that the passes exist once in the kernel.
+       * Whether round 0 exists is decided per BLOCK and its pieces are separated by block barriers: a warp without
+       * contacts skips the work, not the barriers, so that the warps of an SM sit in the same piece of this very large
+       * kernel (ncu: 10 instruction-fetch stall cycles per issued instruction when every warp goes its own way).  The
+       * Volume solver has barriers inside its solve as well (rkfd_volume.cuh): every warp enters it. */
+      const unsigned act = c.ballot( RKFD_POPC64(cfl & m.rigid_mask) > 0 );
+      const bool volume = Spec::NL == 0 && m.solver == S_VOLUME;
+      const bool blk = c.block_or(act != 0);
 #pragma unroll 1
-      for(int round = act ? 0 : 1; round < 2; round++){
-        pass2(m, round ? ref : false);
+      for(int round = blk ? 0 : 1; round < 2; round++){
+        const bool work = round == 1 || act != 0 || volume;
+        if( work ) pass2(m, round ? ref : false);
+        c.phase_sync(2);
         c.tfence();
-        pass3(m, round ? stage : (int)ST_PROBE);
-        if( round == 0 ){ rigid_solve(m, ref, act); c.gsync(); }     /* lanes leave the solve at different points: reconverge */
+        if( work ) pass3(m, round ? stage : (int)ST_PROBE);
+        c.phase_sync(2);
+        if( round == 0 ){
+          if( work ) rigid_solve(m, ref, act);
+          c.gsync();                                   /* lanes leave the solve at different points: reconverge */
+          c.phase_sync(2);
+        }
       }
       return;
     }
