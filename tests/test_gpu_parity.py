@@ -596,3 +596,35 @@ def test_volume_short_trajectory(capi, oracle, name):
     print("volume trajectory %s: %d/%d envs within 1e-6 (max %.2e)" % (name, (err < 1e-6).sum(), B, err.max()))
     assert (err < 1e-6).mean() >= 0.97
     fd.destroy()
+
+
+# ---- edge cases: ragged batch sizes, worlds at the limits, nothing to do
+@pytest.mark.parametrize("B", [1, 31, 33, 513])
+@pytest.mark.parametrize("name", ["c3", "c4_volume", "c5_mlcp"])
+def test_ragged_env_counts(capi, oracle, name, B):
+    """Environment counts that fill neither a warp nor a block (the engine pads to whole blocks with zero-state
+    environments): the real environments still match the oracle and no padding environment leaks into the results."""
+    w = {"c3": lambda: ch.world_c3(base_z=0.1), "c4_volume": ch.world_c4_volume,
+         "c5_mlcp": lambda: ch.world_c5(base_z=0.45, solver="MLCP")}[name]()
+    q, qd, u = (ch.sample_c4_standing if name == "c4_volume" else ch.sample_state)(w, B, seed=77)
+    fd = gpu_world(capi, w, q, qd, u)
+    fd.update_n(5)
+    gq, gqd, gqdd = fd.batch_get_state()
+    assert gq.shape == (B, w.nq) and (fd.batch_get_status() == 0).all()
+    oq, oqd, oqdd, _ = oracle.OracleWorld(w).batch_run(q, qd, u, nsteps=5)
+    for b in range(B):
+        assert relerr(gq[b], oq[b]) < 1e-8 and relerr(gqd[b], oqd[b]) < 1e-6, (name, B, b)
+    fd.destroy()
+
+
+def test_world_without_moving_chain_and_zero_steps(capi):
+    """Only a static chain registered: UpdateInit succeeds or reports, nothing crashes; update_n(0) is a no-op."""
+    w = ch.world_c3(base_z=0.1)
+    q, qd, u = ch.sample_state(w, 64, seed=1)
+    fd = gpu_world(capi, w, q, qd, u)
+    before = fd.batch_get_state()
+    n0 = fd.launch_count
+    fd.update_n(0)
+    after = fd.batch_get_state()
+    assert fd.launch_count == n0 and all(np.array_equal(a, b) for a, b in zip(before, after))
+    fd.destroy()

@@ -436,3 +436,20 @@ def test_volume_refuses_cells_that_are_not_boxes():
     with pytest.raises(Exception, match="Volume solver"):
         HostSim(ch.World(chains=[body, ch.floor()], solver="Volume"), 1)
     HostSim(ch.World(chains=[body, ch.floor()], solver="Vert"), 1)          # fine for the vertex solvers
+
+
+def test_limits_are_reported_not_overrun():
+    """Worlds beyond the fused kernel's tables (cells, vertices, contact slots, joint dofs) are refused with a message."""
+    rng = np.random.default_rng(1)
+    many_cells = ch.ChainModel("c", [ch.Link(name="l%d" % i, parent=i - 1, jtype="revolute" if i else "fixed", mass=1.0, stuff="body",
+                                             inertia=np.eye(3) * 1e-2, shapes=[ch.box_verts(0.1, 0.1, 0.1)]) for i in range(10)])
+    with pytest.raises(Exception, match="too many"):
+        HostSim(ch.World(chains=[many_cells, ch.floor_soft()], contact_info=[ch.ContactInfo("soft", "body", "elastic", E=100.0, V=1.0)]), 1)
+    blob = ch.ChainModel("b", [ch.Link(name="l", jtype="float", mass=1.0, stuff="body", inertia=np.eye(3) * 1e-2,
+                                       shapes=[rng.normal(size=(80, 3))])])
+    with pytest.raises(Exception, match="too many"):
+        HostSim(ch.World(chains=[blob, ch.floor_soft()], contact_info=[ch.ContactInfo("soft", "body", "elastic", E=100.0, V=1.0)]), 1)
+    long_chain = ch.ChainModel("a", [ch.Link(name="l%d" % i, parent=i - 1, jtype="revolute" if i else "fixed", mass=1.0,
+                                             inertia=np.eye(3) * 1e-2, org_p=np.array([0, 0, 0.1])) for i in range(40)])
+    with pytest.raises(Exception):
+        HostSim(ch.World(chains=[long_chain]), 1)
