@@ -26,13 +26,14 @@
 #else
 #define VOL_STAT(i, n)
 #endif
-/* loops over the unknowns of the QP: rolled.  The solver is instruction-fetch bound (ncu: 11 no_instruction stall cycles per
- * issued instruction with 8 divergent warps per SM walking through 350 KB of solver code): unrolling them (RKFD_VOL_UNROLL)
- * batches the thread-local loads but costs 58 KB more code and measured 76 against 68 ms per step (C4, 131,072 envs). */
-#ifdef RKFD_VOL_UNROLL
-#define RKFD_VOL_U _Pragma("unroll")
-#else
+/* loops over the unknowns of the QP: fully unrolled (compile-time trip counts), so that the thread-local loads of a dot
+ * product or a substitution are issued together instead of one per dependent multiply-add.  Measured on C4 (131,072 envs, ms
+ * per step): rolled 68, unrolled 76 while the warps of an SM still went their own ways (58 KB more code: instruction
+ * fetch was the limit then); with the block barriers between the phases rolled 58, unrolled 39.  RKFD_VOL_ROLL rolls them. */
+#ifdef RKFD_VOL_ROLL
 #define RKFD_VOL_U _Pragma("unroll 1")
+#else
+#define RKFD_VOL_U _Pragma("unroll")
 #endif
 #ifdef __CUDACC__
 #define RKFD_VOL_NI __host__ __device__ __noinline__
@@ -644,9 +645,17 @@ RKFD_VOL_U
     for(int k=0;k<P;k++){
       const VolPair &v = vp[k];
       double T[6*VOL_N];       /* T = Q6 A_k (6 x n) */
-      for(int i=0;i<6;i++) for(int s=0;s<n;s++){ double t = 0; for(int j=0;j<6;j++) t += v.q6[6*i+j]*A[VOL_N*(6*k+j)+s]; T[VOL_N*i+s] = t; }
-      for(int r=0;r<n;r++) for(int s=0;s<n;s++){ double t = 0; for(int i=0;i<6;i++) t += A[VOL_N*(6*k+i)+r]*T[VOL_N*i+s]; Qm[VOL_N*r+s] += t; }
-      for(int i=0;i<6;i++){ double t = v.c6[i]; for(int j=0;j<6;j++) t += v.q6[6*i+j]*b[6*k+j];
+      for(int i=0;i<6;i++) for(int s=0;s<n;s++){ double t = 0;
+RKFD_VOL_U
+        for(int j=0;j<6;j++) t += v.q6[6*i+j]*A[VOL_N*(6*k+j)+s];
+        T[VOL_N*i+s] = t; }
+      for(int r=0;r<n;r++) for(int s=0;s<n;s++){ double t = 0;
+RKFD_VOL_U
+        for(int i=0;i<6;i++) t += A[VOL_N*(6*k+i)+r]*T[VOL_N*i+s];
+        Qm[VOL_N*r+s] += t; }
+      for(int i=0;i<6;i++){ double t = v.c6[i];
+RKFD_VOL_U
+        for(int j=0;j<6;j++) t += v.q6[6*i+j]*b[6*k+j];
         for(int r=0;r<n;r++) cv[r] += t*A[VOL_N*(6*k+i)+r]; }
     }
     for(int k=0;k<P;k++) for(int i=0;i<6;i++) Qm[VOL_N*(6*k+i)+6*k+i] += vp[k].L;
