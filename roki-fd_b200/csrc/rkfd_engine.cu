@@ -109,7 +109,7 @@ template <class T> static T *dalloc(Shard &s, size_t n)
 
 /* kernel variants, one translation unit each (rkfd_kernel_variant.cu): BLOCK_GSCR_RIGID_SPEC_MINB */
 #define RKFD_VARIANT_LIST(X) \
-  X(128,0,1,7,2) X(64,0,1,7,4) X(128,0,0,5,4) X(128,0,0,8,4) X(128,0,0,9,4) X(128,0,0,10,4) X(128,0,0,11,2) X(256,0,0,5,2) X(512,0,0,5,1) X(256,0,0,6,2) X(256,0,0,3,2) X(512,0,0,3,1) X(128,0,0,3,4) X(128,0,0,3,3) X(128,0,0,4,4) X(128,0,0,1,1) X(256,0,0,1,1) X(128,0,0,2,1) \
+  X(128,1,1,7,2) X(128,0,1,7,2) X(64,0,1,7,4) X(128,0,0,5,4) X(128,0,0,8,4) X(128,0,0,9,4) X(128,0,0,10,4) X(128,0,0,11,2) X(256,0,0,5,2) X(512,0,0,5,1) X(256,0,0,6,2) X(256,0,0,3,2) X(512,0,0,3,1) X(128,0,0,3,4) X(128,0,0,3,3) X(128,0,0,4,4) X(128,0,0,1,1) X(256,0,0,1,1) X(128,0,0,2,1) \
   X(128,0,0,0,1) X(256,0,0,0,1) X(64,0,0,0,1) X(32,0,0,0,1) X(64,1,0,0,1) \
   X(128,0,1,0,1) X(256,0,1,0,1) X(64,0,1,0,1) X(32,0,1,0,1) X(64,1,1,0,1) X(128,1,1,0,4) X(256,1,1,0,1)
 #define RKFD_DECL(B,G,R,S,M) extern const KernelVariant rkfd_variant_##B##_##G##_##R##_##S##_##M;
@@ -182,7 +182,11 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
       for(const KernelVariant *kv : g_variants){
         if( attempt == 0 && !std::getenv("RKFD_FORCE_BLOCK") && kv->block != 256 ) continue;
         /* pass 0: a matching specialisation; 1: generic, shared-memory scratch; 2: generic, scratch in HBM */
-        if( kv->rigid != rigid || kv->gscr != (pass == 2) ) continue;
+        /* a specialisation may keep its scratch column in HBM: the rigid layout of the 7-joint arm (134 doubles) leaves room
+         * for ONE 128-thread block per SM in shared memory, i.e. one warp per scheduler; through L1/L2 two blocks are resident
+         * and C5 steps in 1.51 instead of 1.95 ms (MLCP) / 4.85 instead of 5.96 ms (Vert).  RKFD_FORCE_SMEM: shared memory only */
+        if( kv->rigid != rigid ) continue;
+        if( pass == 0 ? ( kv->gscr && std::getenv("RKFD_FORCE_SMEM") ) : kv->gscr != (pass == 2) ) continue;
         if( pass == 0 ? !( kv->spec > 0 && (specs >> kv->spec & 1u) ) : kv->spec != 0 ) continue;
         if( const char *fb = std::getenv("RKFD_FORCE_BLOCK") ) if( std::atoi(fb) != kv->block ) continue;   /* tuning aids */
         if( const char *fm = std::getenv("RKFD_FORCE_MINB") ) if( std::atoi(fm) != kv->minb ) continue;

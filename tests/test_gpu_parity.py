@@ -407,17 +407,19 @@ def test_kernel_variants_agree(capi, oracle, monkeypatch, variant):
     assert relerr(gq[:n], oq) < 1e-9 and relerr(gqd[:n], oqd) < 1e-8
 
 
-@pytest.mark.parametrize("variant", [(7, 128, 2), (7, 64, 4), (0, 128, 1)], ids=lambda v: "spec%d_block%d_minb%d" % v)
+@pytest.mark.parametrize("variant", [(7, 128, 2, 0), (7, 128, 2, 1), (7, 64, 4, 1), (0, 128, 1, 0)],
+                         ids=lambda v: "spec%d_block%d_minb%d_%s" % (v[0], v[1], v[2], "smem" if v[3] else "default"))
 def test_rigid_mlcp_kernel_variants_agree(capi, oracle, monkeypatch, variant):
-    """C5 with the MLCP solver (single-link wrench-space path): the rolled rigid specialisation and the generic
-    kernel against each other and against the oracle, over a batch that fills several CTAs per SM."""
-    spec, block, minb = variant
+    """C5 with the MLCP solver (single-link wrench-space path): the rolled rigid specialisation (scratch column in HBM -
+    the default - and in shared memory) and the generic kernel against each other and against the oracle, over a batch
+    that fills several CTAs per SM."""
+    spec, block, minb, smem = variant
     w = ch.world_c5(base_z=0.1, solver="MLCP")
     B = 148 * 2 * 128 + 33
     q, qd, u = ch.sample_state(w, B, seed=23)
 
     def run(env, nsteps):
-        for k in ("RKFD_SPEC", "RKFD_FORCE_BLOCK", "RKFD_FORCE_MINB"):
+        for k in ("RKFD_SPEC", "RKFD_FORCE_BLOCK", "RKFD_FORCE_MINB", "RKFD_FORCE_SMEM"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, str(v))
@@ -428,7 +430,10 @@ def test_rigid_mlcp_kernel_variants_agree(capi, oracle, monkeypatch, variant):
         fd.destroy()
         return out
 
-    (a1, c1), (q1, qd1, _) = run({"RKFD_SPEC": spec, "RKFD_FORCE_BLOCK": block, "RKFD_FORCE_MINB": minb}, 8)
+    env = {"RKFD_SPEC": spec, "RKFD_FORCE_BLOCK": block, "RKFD_FORCE_MINB": minb}
+    if smem:
+        env["RKFD_FORCE_SMEM"] = 1
+    (a1, c1), (q1, qd1, _) = run(env, 8)
     (a0, c0), (q0, qd0, _) = run({"RKFD_SPEC": 0}, 8)
     assert c0[0].sum() > 1000 and (c0[0] == c1[0]).all()
     assert relerr(a1, a0) < 1e-9
