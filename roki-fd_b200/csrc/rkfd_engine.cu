@@ -201,6 +201,15 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
         if( rigid && best > 0 ) continue;
         if( nb*kv->block > best ){ best = nb*kv->block; s->kv = kv; s->smem = smem; }
       }
+    /* generic rigid kernel with a large scratch column (trees: 291 doubles for the biped): shared memory leaves room for one
+     * 64-thread block per SM; with the column in HBM four are resident (both soles of the biped on the rigid floor, dense
+     * MLCP path: 26.5 -> 14.5 ms per step of 16,384 envs) */
+    if( rigid && s->kv && s->kv->spec == 0 && !s->kv->gscr && best < 256 && !std::getenv("RKFD_FORCE_SMEM") && !std::getenv("RKFD_FORCE_BLOCK") )
+      for(const KernelVariant *kv : g_variants){
+        if( !kv->rigid || !kv->gscr || kv->spec != 0 || kv->block != 64 ) continue;
+        const int nb = kv->blocks_per_sm(0);
+        if( nb*kv->block >= 2*best ){ best = nb*kv->block; s->kv = kv; s->smem = 0; break; }
+      }
     if( s->kv && s->kv->gscr ) st.scratch = dalloc<double>(*s, (size_t)model.nscratch*s->ld);
     if( best == 0 ) throw std::runtime_error("rokifd_b200: no launch configuration fits this model");
     /* the zero-fills above ran on the legacy default stream, which this non-blocking stream does not wait for */
