@@ -249,11 +249,33 @@ void ork_world_set_solver(ork_world *w, int solver)
   w->cidef.K = 1000.0; w->cidef.L = solver == ORK_SOLVER_VOLUME ? 0.001 : 1.0; w->cidef.SF = 0.5; w->cidef.KF = 0.3;
   w->cidef.E = 0.0; w->cidef.V = 0.0;
 }
+/* [EXT A-15] the Volume solver takes cells with the 8 corners of a parallelepiped; their vertices are put into sign-bit
+ * order (vertex k = v0 + (k&1) ea + (k>>1&1) eb + (k>>2&1) ec, v0 = the first vertex, (a,b,c) the first index triple in
+ * lexicographic order that spans the cell) so that a polyhedron-described box (mighty.ztk's soles: bottom ring, top ring)
+ * is accepted.  Returns 0 when the 8 points are not a parallelepiped (order left as it is). */
+static int box_sign_bit_order(double *v)
+{
+  int a, b, c, k, j, i; double scale = 0, out[24];
+  for(k=1;k<8;k++) for(i=0;i<3;i++) if( fabs(v[3*k+i]-v[i]) > scale ) scale = fabs(v[3*k+i]-v[i]);
+  for(a=1;a<8;a++) for(b=a+1;b<8;b++) for(c=b+1;c<8;c++){
+    int used = 0, ok = 1;
+    for(k=0;k<8 && ok;k++){
+      double p[3]; int found = -1;
+      for(i=0;i<3;i++) p[i] = v[i] + ((k&1)?v[3*a+i]-v[i]:0.0) + ((k&2)?v[3*b+i]-v[i]:0.0) + ((k&4)?v[3*c+i]-v[i]:0.0);
+      for(j=0;j<8;j++) if( !(used>>j & 1) && fabs(v[3*j]-p[0]) <= 1e-9*(1+scale) && fabs(v[3*j+1]-p[1]) <= 1e-9*(1+scale) && fabs(v[3*j+2]-p[2]) <= 1e-9*(1+scale) ){ found = j; break; }
+      if( found < 0 ){ ok = 0; break; }
+      used |= 1<<found; memcpy(out+3*k,v+3*found,24);
+    }
+    if( ok ){ memcpy(v,out,sizeof out); return 1; }
+  }
+  return 0;
+}
 void ork_world_finalize(ork_world *w)
 {
   /* pairs in registration order: (moving cell) x (static box); contact info by stuff pair with
    * fallback to the solver default (rkfd_sim.c:200-207, :266-271) */
   int c,b,k,sofs=0;
+  if( w->solver == ORK_SOLVER_VOLUME ) for(c=0;c<w->ncell;c++) if( w->cell[c].nvert == 8 ) box_sign_bit_order(w->vert+3*w->cell[c].vofs);
   free(w->pair); w->npair = w->ncell*w->nbox;
   w->pair = (ork_pair*)calloc(w->npair>0?w->npair:1,sizeof(ork_pair));
   k = 0;

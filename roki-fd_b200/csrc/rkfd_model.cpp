@@ -1,6 +1,7 @@
 /* rkfd_model.cpp - flattening of registered chains into the device tables (host only). */
 #include "rkfd_model.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -43,6 +44,28 @@ void model_layout(ModelDev &m, bool tm)
   if( tm ){ m.rk_slot = t; t += 4*nq; m.ntspace = t; }
   else { m.rk_slot = slot; slot += 4*nq; m.ntspace = 0; }
   m.nscratch = slot;
+}
+
+/* [EXT A-15] vertices of an 8-corner cell into sign-bit order: vertex k = v0 + (k&1) ea + (k>>1&1) eb + (k>>2&1) ec with v0 the
+ * first vertex and (a,b,c) the first index triple in lexicographic order that spans the cell, so that polyhedron-described
+ * boxes (mighty.ztk's soles: bottom ring, top ring) are accepted; false when the points are not a parallelepiped. */
+static bool box_sign_bit_order(double *v)
+{
+  double scale = 0, out[24];
+  for(int k=1;k<8;k++) for(int i=0;i<3;i++) scale = std::max(scale, std::fabs(v[3*k+i]-v[i]));
+  const double tol = 1e-9*(1+scale);
+  for(int a=1;a<8;a++) for(int b=a+1;b<8;b++) for(int c=b+1;c<8;c++){
+    unsigned used = 0; bool ok = true;
+    for(int k=0;k<8 && ok;k++){
+      double p[3]; int found = -1;
+      for(int i=0;i<3;i++) p[i] = v[i] + ((k&1)?v[3*a+i]-v[i]:0.0) + ((k&2)?v[3*b+i]-v[i]:0.0) + ((k&4)?v[3*c+i]-v[i]:0.0);
+      for(int j=0;j<8;j++) if( !(used>>j & 1u) && std::fabs(v[3*j]-p[0]) <= tol && std::fabs(v[3*j+1]-p[1]) <= tol && std::fabs(v[3*j+2]-p[2]) <= tol ){ found = j; break; }
+      if( found < 0 ){ ok = false; break; }
+      used |= 1u<<found; std::memcpy(out+3*k, v+3*found, 24);
+    }
+    if( ok ){ std::memcpy(v, out, sizeof out); return true; }
+  }
+  return false;
 }
 
 bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
@@ -196,13 +219,8 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   if( m.has_rigid && m.solver == S_VOLUME ){
     /* the Volume solver (rkfd_volume.cuh) works on thread-local data: no workspace; cells must be parallelepipeds */
     for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID ){
-      const CellDev &c = m.cell[m.pair[p].cell]; bool ok = c.nvert == 8;
-      for(int k=0;k<8 && ok;k++) for(int a=0;a<3;a++){      /* v[k] = v[0] + sum over the set bits b of k of (v[1<<b] - v[0]) */
-        const double *v = m.vert + 3*c.vofs; double x = v[a], scale = 1e-300;
-        for(int b=0;b<3;b++){ if( k >> b & 1 ) x += v[3*(1<<b)+a] - v[a]; scale += std::fabs(v[3*(1<<b)+a] - v[a]); }
-        if( std::fabs(x - v[3*k+a]) > 1e-9*(1.0 + scale) ) ok = false;
-      }
-      if( !ok ){ err = "Volume solver: rigid cells must have the 8 corners of a box (vertex k = sign bits x: k&1, y: k&2, z: k&4)"; return false; }
+      const CellDev &c = m.cell[m.pair[p].cell];
+      if( c.nvert != 8 || !box_sign_bit_order(m.vert + 3*c.vofs) ){ err = "Volume solver: rigid cells must have the 8 corners of a box (parallelepiped)"; return false; }
     }
     m.ws_doubles = 0; m.ws_geo = m.ws_b = m.ws_f = m.ws_A = m.ws_du = m.ws_da = m.ws_qp = 0;
     return true;

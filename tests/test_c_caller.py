@@ -32,11 +32,13 @@ def test_c_caller_compiles_and_links_without_cuda_headers(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("solver,contacts,z0", [("Volume", "-", 0.049), ("Vert", "-", 0.049), ("MLCP", "contacts.ztk", 0.049)])
-def test_c_caller_matches_oracle(tmp_path, oracle, solver, contacts, z0):
+@pytest.mark.parametrize("solver,contacts,z0,cube", [("Volume", "-", 0.049, "cube.ztk"), ("Vert", "-", 0.049, "cube.ztk"),
+                                                     ("MLCP", "contacts.ztk", 0.049, "cube.ztk"),
+                                                     ("Volume", "-", 0.049, "cube_poly.ztk")])     # polyhedron-described box
+def test_c_caller_matches_oracle(tmp_path, oracle, solver, contacts, z0, cube):
     exe = build(tmp_path)
     nsteps = 60
-    args = [exe, os.path.join(GOLD, "cube.ztk"), os.path.join(GOLD, "rigidfloor.ztk"),
+    args = [exe, os.path.join(GOLD, cube), os.path.join(GOLD, "rigidfloor.ztk"),
             "-" if contacts == "-" else os.path.join(GOLD, contacts), solver, str(nsteps), repr(z0)]
     out = subprocess.check_output(args, text=True)
     final = [l for l in out.splitlines() if l.startswith("final:")][0].split()

@@ -453,3 +453,26 @@ def test_limits_are_reported_not_overrun():
                                              inertia=np.eye(3) * 1e-2, org_p=np.array([0, 0, 0.1])) for i in range(40)])
     with pytest.raises(Exception):
         HostSim(ch.World(chains=[long_chain]), 1)
+
+
+def test_volume_accepts_polyhedron_described_boxes(oracle):
+    """A box cell given in another vertex order (bottom ring then top ring, as the soles of the reference's mighty.ztk:
+    example/model/mighty.ztk:1691-1740) is put into sign-bit order by both sides and gives the results of the plain box."""
+    ring = [0, 1, 3, 2, 4, 5, 7, 6]                    # sign-bit index of ring vertex k
+    bv = ch.box_verts(0.1, 0.1, 0.1)
+    def world(verts):
+        body = ch.ChainModel("box", [ch.Link(name="link#00", jtype="float", mass=0.5, stuff="body", inertia=np.eye(3) * 8.33e-4,
+                                             shapes=[verts])])
+        return ch.World(chains=[body, ch.floor()], solver="Volume")
+    B = 24
+    w0, w1 = world(bv), world(bv[ring])
+    q, qd, u = ch.sample_state(w0, B, seed=5)
+    q[:, 2] = np.linspace(0.0, 0.08, B); q[:, 3:6] *= 0.3
+    out = []
+    for w in (w0, w1):
+        hs = HostSim(w, B); hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(10)
+        out.append(hs.get_state())
+        ref = oracle_run(oracle, w, q, qd, u, 10)
+        for b in range(B):
+            assert relerr(out[-1][0][b, :w.nq], ref[b][0][0]) < 1e-7
+    assert relerr(out[1][0], out[0][0]) < 1e-9
