@@ -476,3 +476,17 @@ def test_volume_accepts_polyhedron_described_boxes(oracle):
         for b in range(B):
             assert relerr(out[-1][0][b, :w.nq], ref[b][0][0]) < 1e-7
     assert relerr(out[1][0], out[0][0]) < 1e-9
+
+
+def test_volume_pair_limit_is_flagged():
+    """More contact volumes per environment than the solver's tables hold (2): the surplus is ignored and the status word
+    of the environment says so (no silent wrong answer)."""
+    w = ch.World(chains=[ch.box("a"), ch.box("b"), ch.box("c"), ch.floor()], solver="Volume")
+    q = np.zeros((2, 18)); qd = np.zeros((2, 18)); u = np.zeros((2, w.nl))
+    for k in range(3):
+        q[:, 6 * k] = 1.0 * k
+        q[:, 6 * k + 2] = 0.049
+    q[1, 14] = 0.2                                   # env 1: the third box is in the air -> two volumes only
+    hs = HostSim(w, 2); hs.set_state(q, qd, u); hs.eval(ref=True)
+    st = hs.get_status()
+    assert st[0] != 0 and st[1] == 0
