@@ -279,6 +279,9 @@ __ROKI_FD_EXPORT int rkFDBatchSetState(rkFD *fd, const double *q, const double *
 __ROKI_FD_EXPORT int rkFDBatchGetState(rkFD *fd, double *q, double *qd, double *qdd);
 __ROKI_FD_EXPORT int rkFDBatchSetMotorInput(rkFD *fd, const double *u);
 __ROKI_FD_EXPORT int rkFDBatchGetContactForce(rkFD *fd, double *f);
+/* Volume solver (reference rkfd_volume.c: one 6-D wrench per rigid pair instead of vertex forces): the first three slots of a
+ * pair hold the pair wrench of the last committing evaluation - force, torque about the volume centre (world axes) - and the
+ * volume centre */
 __ROKI_FD_EXPORT int rkFDBatchGetContactState(rkFD *fd, int *active, int *type, double *ref);
 __ROKI_FD_EXPORT int rkFDBatchSetContactState(rkFD *fd, const int *active, const int *type, const double *ref);
 __ROKI_FD_EXPORT int rkFDBatchGetPivot(rkFD *fd, int *type, double *prev_trq);
