@@ -73,6 +73,7 @@ def lib():
         L.ork_le_solve_mp_sym.argtypes = [C.c_int, _dp, _dp, _dp]
         L.ork_env_get_volume.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
         L.ork_world_npair.argtypes = [C.c_void_p]
+        L.ork_env_get_volume_constraint.argtypes = [C.c_void_p, _dp]
         L.ork_lp_solve.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         _LIB = L
     return _LIB
@@ -274,6 +275,13 @@ class OracleEnv:
         wr, ce = np.zeros((n, 6)), np.zeros((n, 3))
         lib().ork_env_get_volume(self.h, npl.ctypes.data_as(_ip), ty.ctypes.data_as(_ip), wr.ctypes.data_as(_dp), ce.ctypes.data_as(_dp))
         return npl, ty, wr, ce
+
+    def volume_constraint(self):
+        """Per pair (Q6 [6,6], c6 [6], norm [3]) of the last Volume evaluation."""
+        n = max(lib().ork_world_npair(self.w.h), 1)
+        qc = np.zeros((n, 45))
+        lib().ork_env_get_volume_constraint(self.h, qc.ctypes.data_as(_dp))
+        return qc[:, :36].reshape(n, 6, 6), qc[:, 36:42], qc[:, 42:45]
 
 
 def lp_solve(A, b, c=None):

@@ -150,6 +150,7 @@ struct ork_env {
   int rn; double *rA, *rb, *rf;
   /* Volume solver, per pair: friction type (rkCDPairDat.type), planes of the last evaluation (-1: no volume), wrench, center */
   int *v_type, *v_np; double *v_wrench, *v_center;
+  double *v_qc;      /* per pair: Q6 (36, row-major), c6 (6), norm (3) of the last evaluation (test hook) */
   /* RKG workspace */
   double *k[4][2], *xs[2];
 };
@@ -309,7 +310,7 @@ ork_env *ork_env_new(const ork_world *w)
   e->lw=(ork_lw*)calloc(w->nl,sizeof(ork_lw));
   e->rn=0; e->rA=(double*)calloc(9*ns*ns,8); e->rb=(double*)calloc(3*ns,8); e->rf=(double*)calloc(3*ns,8);
   { int np = w->npair>0?w->npair:1; e->v_type=(int*)calloc(np,sizeof(int)); e->v_np=(int*)calloc(np,sizeof(int));
-    e->v_wrench=(double*)calloc(6*np,8); e->v_center=(double*)calloc(3*np,8); }
+    e->v_wrench=(double*)calloc(6*np,8); e->v_center=(double*)calloc(3*np,8); e->v_qc=(double*)calloc(45*np,8); }
   for(i=0;i<4;i++) for(j=0;j<2;j++) e->k[i][j]=(double*)calloc(nq,8);
   e->xs[0]=(double*)calloc(nq,8); e->xs[1]=(double*)calloc(nq,8);
   return e;
@@ -322,7 +323,7 @@ void ork_env_free(ork_env *e)
   free(e->c_active); free(e->c_type); free(e->c_ref); free(e->c_f); free(e->c_pro);
   free(e->c_norm); free(e->c_axis); free(e->c_vert); free(e->c_refw); free(e->c_vel);
   free(e->lw); free(e->rA); free(e->rb); free(e->rf);
-  free(e->v_type); free(e->v_np); free(e->v_wrench); free(e->v_center);
+  free(e->v_type); free(e->v_np); free(e->v_wrench); free(e->v_center); free(e->v_qc);
   for(i=0;i<4;i++) for(j=0;j<2;j++) free(e->k[i][j]);
   free(e->xs[0]); free(e->xs[1]); free(e);
 }
@@ -1218,6 +1219,7 @@ static void solver_volume(ork_env *e, int do_up_ref)
   /* _rkFDSolverQPCreate (:496-528) */
   for(k=0;k<P;k++){ double qv[36], cv[6], t6[6]; int r, s;
     vol_constraint(&vp[k],qv,cv);
+    memcpy(e->v_qc+45*vp[k].pair,qv,36*8); memcpy(e->v_qc+45*vp[k].pair+36,cv,6*8); memcpy(e->v_qc+45*vp[k].pair+42,vp[k].norm,3*8);
     for(i=0;i<6;i++) for(j=0;j<6;j++){ double qe = qv[6*i+j];
       for(r=0;r<n;r++) for(s=0;s<n;s++) Q[n*r+s] += qe*A[n*(6*k+i)+r]*A[n*(6*k+j)+s]; }
     m6_mulv(qv,b+6*k,t6);
@@ -1449,6 +1451,8 @@ void ork_env_get_volume(const ork_env *e, int *np, int *type, double *wrench, do
   if(wrench) memcpy(wrench,e->v_wrench,6*n*8); if(center) memcpy(center,e->v_center,3*n*8);
 }
 int ork_world_npair(const ork_world *w){ return w->npair; }
+/* test hook: Q6 (36, row-major), c6 (6), norm (3) per pair of the last Volume evaluation (rkfd_volume.c:397-491) */
+void ork_env_get_volume_constraint(const ork_env *e, double *qc){ memcpy(qc,e->v_qc,45*(e->w->npair>0?e->w->npair:1)*8); }
 int ork_env_get_rigid_system(const ork_env *e, double *A, double *b, double *f, int cap)
 {
   int n = e->rn; if( n > cap ) return -n;

@@ -102,6 +102,8 @@ int ork_env_get_rigid_system(const ork_env *e, double *A, double *b, double *f, 
  * volume), type = pair friction type, wrench (6, world axes, at center), center (3) */
 void ork_env_get_volume(const ork_env *e, int *np, int *type, double *wrench, double *center);
 int ork_world_npair(const ork_world *w);
+/* test hook: per pair Q6 (36, row-major), c6 (6), norm (3) of the last Volume evaluation (rkfd_volume.c:397-491) */
+void ork_env_get_volume_constraint(const ork_env *e, double *qc);
 /* [EXT A-16] LP by the two-phase simplex (Bland): min c^T x s.t. A x = b (m x n, row-major), x >= 0; c NULL: feasibility */
 int ork_lp_solve(int m, int n, const double *A, const double *b, const double *c, double *x);
 

@@ -368,3 +368,60 @@ def test_volume_sliding_box_kinetic_friction_ratio(oracle):
             assert abs(wr[0][0] / wr[0][2] + 0.3 * (1 - np.exp(-100.0 * qqd[0]))) < 5e-3
             assert abs(wr[0][1]) < 1e-6 * wr[0][2]
     assert npush > 20 and 0.5 < qqd[0] < 0.8          # about 0.3 g of deceleration over 0.12 s
+
+
+def test_volume_surface_integrals_against_the_divergence_theorem(oracle):
+    """Independent pins of the contact-volume construction and of the signed surface integrals of rkfd_volume.c:397-491
+    for random box poses: with V the volume of (box intersected with the floor half-space) from scipy's convex hull, K the
+    compensation and n the contact normal, the centre must be the hull's centroid, Q6 symmetric positive semi-definite with
+    linear block (sum of projected face areas) * I, and the depth term c6 = (-K W n, torque) with W the integral of |height|
+    over the UNSIGNED projected faces: W = V exactly for a box lying flat (every vertical line crosses the surface once above
+    and once below the centre plane: the signed integral of the height over a closed surface is its volume, and its first
+    moment about the barycentre vanishes, so the torque part is zero), W >= V for tilted boxes."""
+    from scipy.spatial import ConvexHull
+    w = ch.World(chains=[ch.box(), ch.floor()], solver="Volume")
+    ow = oracle.OracleWorld(w)
+    rng = np.random.default_rng(4)
+    bv = ch.box_verts(0.1, 0.1, 0.1)
+    edges = [(a, b) for a in range(8) for b in range(a + 1, 8) if bin(a ^ b).count("1") == 1]
+    nchecked = 0
+    for trial in range(40):
+        flat = trial % 2 == 0
+        q = np.zeros(6); q[:2] = rng.uniform(-0.5, 0.5, 2); q[2] = rng.uniform(0.0, 0.07); q[3:] = rng.uniform(-0.6, 0.6, 3)
+        if flat:
+            q[2] = rng.uniform(0.0, 0.049); q[3:5] = 0.0
+        e = ow.env(); e.set_state(q, np.zeros(6)); e.set_motor_input(np.zeros(w.nl)); e.eval(True)
+        npl, ty, wr, ce = e.volume()
+        if npl[0] < 3:
+            continue
+        R, p = e.link_frames()
+        vw = bv @ R[0].T + p[0]
+        pts = [v for v in vw if v[2] <= 0]
+        for a, b in edges:
+            if (vw[a][2] < 0) != (vw[b][2] < 0):
+                t = vw[a][2] / (vw[a][2] - vw[b][2]); pts.append(vw[a] + t * (vw[b] - vw[a]))
+        hull = ConvexHull(np.array(pts))
+        if hull.volume < 1e-9:
+            continue
+        # centroid of the hull from its triangles (signed tetrahedra about an interior point)
+        c0 = np.mean(np.array(pts), 0); vol = 0.0; cen = np.zeros(3)
+        for tri in hull.simplices:
+            a, b, c = (hull.points[i] - c0 for i in tri)
+            v6 = abs(np.dot(a, np.cross(b, c))) / 6.0
+            vol += v6; cen += v6 * (a + b + c) / 4.0
+        cen = c0 + cen / vol
+        Q6, c6, nrm = e.volume_constraint()
+        K = 1000.0
+        assert abs(vol - hull.volume) < 1e-12
+        assert np.allclose(ce[0], cen, atol=1e-9)
+        assert np.allclose(nrm[0], [0, 0, 1])
+        if flat:
+            assert np.allclose(c6[0][:3], -K * hull.volume * nrm[0], rtol=1e-9, atol=1e-12)
+            assert np.allclose(c6[0][3:], 0.0, atol=1e-9 * K * hull.volume)
+        else:
+            assert np.allclose(c6[0][:2], 0.0, atol=1e-15) and -c6[0][2] >= K * hull.volume * (1 - 1e-9)
+        assert np.allclose(Q6[0], Q6[0].T, atol=1e-15)
+        assert np.allclose(Q6[0][:3, :3], Q6[0][0, 0] * np.eye(3), atol=1e-15) and Q6[0][0, 0] > 0
+        assert np.all(np.linalg.eigvalsh(Q6[0]) > -1e-12)
+        nchecked += 1
+    assert nchecked >= 15
