@@ -418,6 +418,12 @@ def test_volume_surface_integrals_against_the_divergence_theorem(oracle):
         if flat:
             assert np.allclose(c6[0][:3], -K * hull.volume * nrm[0], rtol=1e-9, atol=1e-12)
             assert np.allclose(c6[0][3:], 0.0, atol=1e-9 * K * hull.volume)
+            # flat 0.1 m cube: cap and bottom face project to the 0.1 x 0.1 square (the side faces to nothing), centred on the
+            # barycentre: Q6 = 2 * [[A I, 0], [0, -int [p x]^2 dA]] with int x^2 dA = int y^2 dA = 0.1^4 / 12
+            m2 = 0.1 ** 4 / 12
+            assert np.allclose(Q6[0][:3, :3], 0.02 * np.eye(3), atol=1e-12)
+            assert np.allclose(Q6[0][:3, 3:], 0.0, atol=1e-12) and np.allclose(Q6[0][3:, :3], 0.0, atol=1e-12)
+            assert np.allclose(Q6[0][3:, 3:], 2 * np.diag([m2, m2, 2 * m2]), atol=1e-12)
         else:
             assert np.allclose(c6[0][:2], 0.0, atol=1e-15) and -c6[0][2] >= K * hull.volume * (1 - 1e-9)
         assert np.allclose(Q6[0], Q6[0].T, atol=1e-15)
