@@ -115,3 +115,16 @@ def test_ztk_reader_on_reference_models():
     fd = capi.RkFD()
     assert fd.contact_info_scan_file(os.path.join(d, "contactinfo.ztk"))
     fd.destroy()
+
+
+def test_world_errors_are_reported_before_the_device_is_needed():
+    """rkFDUpdateInit checks the world (limits, cell shapes under the Volume solver) before it looks for a device: the
+    message reaches the caller on any machine."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    blob = ch.ChainModel("blob", [ch.Link(name="l", jtype="float", mass=1.0, stuff="body", inertia=np.eye(3) * 1e-2,
+                                          shapes=[rng.normal(size=(8, 3)) * 0.1])])
+    fd, _ = capi.create_world(ch.World(chains=[blob, ch.floor()], solver="Volume"), B=4)
+    with pytest.raises(RuntimeError, match="Volume solver"):
+        fd.update_init()
+    fd.destroy()
