@@ -1,4 +1,4 @@
-"""Parity protocol of SURVEY.md section 8(d) on the GPU: per-evaluation and free-running comparison of the device path
+"""TEST INFRASTRUCTURE (it loads the oracle, hence it lives under tests/): parity protocol of SURVEY.md section 8(d) on the GPU: per-evaluation and free-running comparison of the device path
 (through the C-ABI) with the CPU oracle on the same synthetic states.  Prints a markdown table (profiles/r01_parity_report.md).
 
 per-evaluation: one committing evaluation (rkFDUpdateInit) on B random envs: rel. error of q'' per env
