@@ -431,3 +431,31 @@ def test_volume_surface_integrals_against_the_divergence_theorem(oracle):
         assert np.all(np.linalg.eigvalsh(Q6[0]) > -1e-12)
         nchecked += 1
     assert nchecked >= 15
+
+
+def test_volume_wrench_respects_unilaterality_and_the_friction_cone(oracle):
+    """Random box states on the rigid floor (Volume solver): the pair pushes (fn >= 0); a static pair keeps its tangential force
+    inside the Coulomb cone SF * fn; a kinetic one has at most KF * fn (rkfd_volume.c:552-568, 869-916)."""
+    w = ch.World(chains=[ch.box(), ch.floor()], solver="Volume")
+    ow = oracle.OracleWorld(w)
+    rng = np.random.default_rng(8)
+    nstat = nkin = 0
+    for trial in range(200):
+        q = np.zeros(6); q[2] = rng.uniform(0.0, 0.06); q[3:] = rng.uniform(-0.4, 0.4, 3)
+        qd = rng.uniform(-1, 1, 6) * (0.0 if trial % 3 == 0 else 1.0)
+        e = ow.env(); e.set_state(q, qd); e.set_motor_input(np.zeros(w.nl)); e.eval(True)
+        npl, ty, wr, ce = e.volume()
+        if npl[0] <= 0:
+            continue
+        fn, ft = wr[0][2], np.hypot(wr[0][0], wr[0][1])
+        assert fn >= 0.0
+        if fn == 0.0:
+            assert np.allclose(wr[0], 0.0)
+            continue
+        if ty[0] == 0:
+            nstat += 1
+            assert ft <= 0.5 * fn * (1 + 1e-9) + 1e-12
+        else:
+            nkin += 1
+            assert ft <= 0.3 * fn * (1 + 1e-9) + 1e-12
+    assert nstat > 5 and nkin > 5
