@@ -70,6 +70,7 @@ def lib():
         L.ork_batch_run.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp]
         L.ork_batch_run_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp, _ip, _ip, _dp, _ip]
         L.ork_qp_solve_asm.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip]
+        L.ork_env_get_qp.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _ip, _ip, C.c_int, C.c_int]
         L.ork_le_solve_mp_sym.argtypes = [C.c_int, _dp, _dp, _dp]
         L.ork_env_get_volume.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
         L.ork_world_npair.argtypes = [C.c_void_p]
@@ -267,6 +268,19 @@ class OracleEnv:
         n = lib().ork_env_get_rigid_system(self.h, A.ctypes.data_as(_dp), b.ctypes.data_as(_dp),
                                            f.ctypes.data_as(_dp), cap)
         return A.reshape(-1)[:n * n].reshape(n, n), b[:n], f[:n]
+
+    def qp(self):
+        """Test hook: the Vert QP of the last evaluation: (Q, c, nf, x, idx, iterations, term); term 0 optimal,
+        1 anti-cycling exit (rkfd_opt_qp.c:152-171), 2 iteration cap."""
+        info = np.zeros(4, np.int32)
+        lib().ork_env_get_qp(self.h, None, None, None, None, None, info.ctypes.data_as(_ip), 0, 0)
+        n, m = int(info[0]), int(info[1])
+        if n == 0:
+            return None
+        Q, c, nf, x, idx = np.zeros((n, n)), np.zeros(n), np.zeros((m, n)), np.zeros(n), np.zeros(m, np.int32)
+        lib().ork_env_get_qp(self.h, Q.ctypes.data_as(_dp), c.ctypes.data_as(_dp), nf.ctypes.data_as(_dp), x.ctypes.data_as(_dp),
+                             idx.ctypes.data_as(_ip), info.ctypes.data_as(_ip), n, m)
+        return Q, c, nf, x, idx, int(info[2]), int(info[3])
 
     def volume(self):
         """Volume solver results of the last evaluation per pair: (np, type, wrench[6], center[3]); np = -1: no contact volume."""

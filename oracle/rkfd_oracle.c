@@ -148,6 +148,8 @@ struct ork_env {
   ork_lw *lw;
   /* rigid system of the last evaluation */
   int rn; double *rA, *rb, *rf;
+  /* test hook: the last Vert QP (ork_env_get_qp) */
+  int qp_n, qp_m, qp_iter, qp_term; double *qp_Q, *qp_c, *qp_nf, *qp_x; int *qp_idx;
   /* Volume solver, per pair: friction type (rkCDPairDat.type), planes of the last evaluation (-1: no volume), wrench, center */
   int *v_type, *v_np; double *v_wrench, *v_center;
   double *v_qc;      /* per pair: Q6 (36, row-major), c6 (6), norm (3) of the last evaluation (test hook) */
@@ -323,6 +325,7 @@ void ork_env_free(ork_env *e)
   free(e->c_active); free(e->c_type); free(e->c_ref); free(e->c_f); free(e->c_pro);
   free(e->c_norm); free(e->c_axis); free(e->c_vert); free(e->c_refw); free(e->c_vel);
   free(e->lw); free(e->rA); free(e->rb); free(e->rf);
+  free(e->qp_Q); free(e->qp_c); free(e->qp_nf); free(e->qp_x); free(e->qp_idx);
   free(e->v_type); free(e->v_np); free(e->v_wrench); free(e->v_center); free(e->v_qc);
   for(i=0;i<4;i++) for(j=0;j<2;j++) free(e->k[i][j]);
   free(e->xs[0]); free(e->xs[1]); free(e);
@@ -713,13 +716,27 @@ void ork_le_solve_mp_sym(int n, const double *a, const double *b, double *x)
   }
   for(i=0;i<n;i++) if( fabs(A[n*i+i]) > lmax ) lmax = fabs(A[n*i+i]);
   for(i=0;i<n;i++) x[i] = 0;
-  for(k=0;k<n;k++){
-    double lam = A[n*k+k], s = 0;
-    if( fabs(lam) <= 1.0e-11*lmax ) continue;
-    for(i=0;i<n;i++) s += V[n*i+k]*b[i];
-    s /= lam;
-    for(i=0;i<n;i++) x[i] += s*V[n*i+k];
-  }
+  /* x = pinv(a) b, then iterative refinement x += pinv(a) (b - a x) with the residual accumulated in long double: the
+   * active-set loop of rkfd_opt_qp.c decides with ABSOLUTE 1e-12 thresholds on x (:108-110), while one pseudo-inverse
+   * application in double carries an error of eps * cond(a) * |x| (1e-16 * 1e7 * 1e2 on the KKT matrices of contactinfo.ztk's
+   * relaxation 1e-4).  [EXT A-14] specifies zLESolveMP as THE minimum-norm least-squares solution; refinement makes this
+   * implementation deliver it to rounding, so that the loop's decisions are those of exact arithmetic
+   * (tests/test_oracle_physics.py pins it against a 60-digit evaluation).  Two solves whose exact solutions coincide (an
+   * active row released from a redundant set) then return the same doubles up to an ulp. */
+  { int round; double *r = (double*)malloc(n*8); long double *xl = (long double*)calloc(n,sizeof(long double));
+    for(round=0;round<5;round++){
+      for(i=0;i<n;i++){ long double acc = b[i]; for(j=0;j<n;j++) acc -= (long double)a[n*i+j]*xl[j]; r[i] = (double)acc; }
+      for(k=0;k<n;k++){
+        double lam = A[n*k+k], s = 0;
+        if( fabs(lam) <= 1.0e-11*lmax ) continue;
+        for(i=0;i<n;i++) s += V[n*i+k]*r[i];
+        s /= lam;
+        for(i=0;i<n;i++) xl[i] += (long double)(s*V[n*i+k]);
+      }
+    }
+    for(i=0;i<n;i++) x[i] = (double)xl[i];      /* the iterate is kept in long double and rounded once */
+    free(xl);
+    free(r); }
   free(A); free(V);
 }
 
@@ -730,8 +747,14 @@ static double qp_cond(int n, const double *a, const double *x, int i)
 { double s = 0; int j; for(j=0;j<n;j++) s += a[n*i+j]*x[j]; return s; }
 #define ORK_QP_ASM_TOL 1.0e-8
 #define ORK_QP_MAX_ITER 10000
+/* term (may be NULL): how the loop ended - 0 optimal (rkfd_opt_qp.c:113), 1 anti-cycling exit (:165), 2 iteration cap (not in the reference) */
+int ork_qp_solve_asm_ex(int n, int m, const double *q, const double *c, const double *a,
+                        const double *b, const double *init, double *ans, int *idx, int *term);
 int ork_qp_solve_asm(int n, int m, const double *q, const double *c, const double *a,
                      const double *b, const double *init, double *ans, int *idx)
+{ return ork_qp_solve_asm_ex(n,m,q,c,a,b,init,ans,idx,NULL); }
+int ork_qp_solve_asm_ex(int n, int m, const double *q, const double *c, const double *a,
+                        const double *b, const double *init, double *ans, int *idx, int *term)
 {
   int nmax = n+m, i, j, k, ma, nm, iter = 0, nhist = 0, caph = 16;
   double *qa = (double*)malloc(nmax*nmax*8), *xy = (double*)malloc(nmax*8), *cb = (double*)malloc(nmax*8);
@@ -742,7 +765,7 @@ int ork_qp_solve_asm(int n, int m, const double *q, const double *c, const doubl
   for(ma=0,i=0;i<m;i++){ idx[i] = fabs(qp_cond(n,a,ans,i)-b[i]) < ORK_TOL; ma += idx[i]; }
   for(;;){
     int stepped = 0;
-    if( ++iter > ORK_QP_MAX_ITER ) break;    /* safety net; the reference loop is unbounded */
+    if( ++iter > ORK_QP_MAX_ITER ){ if(term) *term = 2; break; }    /* safety net; the reference loop is unbounded */
     nm = n + ma;
     for(i=0;i<n;i++) for(j=0;j<n;j++) qa[nm*i+j] = -q[n*i+j];
     for(k=0,j=n;j<nm;j++){ while( k<m && !idx[k] ) k++; for(i=0;i<n;i++){ qa[nm*i+j] = a[n*k+i]; qa[nm*j+i] = a[n*k+i]; } k++; }
@@ -755,7 +778,7 @@ int ork_qp_solve_asm(int n, int m, const double *q, const double *c, const doubl
       int neg = 0;
       for(i=0;i<n;i++) ans[i] = xy[i];
       for(i=0;i<ma;i++) if( xy[n+i] < 0 ){ neg = 1; break; }
-      if( !neg ) break;                        /* optimal */
+      if( !neg ){ if(term) *term = 0; break; }                        /* optimal */
       tempd = xy[n]; for(i=1;i<ma;i++) if( xy[n+i] < tempd ) tempd = xy[n+i];
       for(k=0,i=0;i<m;i++) if( idx[i] ){
         if( fabs(xy[k+n]-tempd) < ORK_QP_ASM_TOL ){ idx[i] = 0; }
@@ -779,7 +802,7 @@ int ork_qp_solve_asm(int n, int m, const double *q, const double *c, const doubl
         if( !same ) continue;
         if( fabs(hmin[k]/objv - 1.0) > ORK_QP_ASM_TOL ) continue;
         end = 1; break; }
-      if( end ) break; }
+      if( end ){ if(term) *term = 1; break; } }
     if( nhist == caph ){ caph *= 2; hist = (int*)realloc(hist,caph*(m>0?m:1)*sizeof(int)); hmin = (double*)realloc(hmin,caph*8); }
     for(i=0;i<m;i++) hist[m*nhist+i] = idx[i];
     hmin[nhist++] = objv;
@@ -884,7 +907,11 @@ static void solver_rigid(ork_env *e, int do_up_ref)
     for(i=0;i<n;i++){ double s=0; for(j=0;j<n;j++) s += A[n*j+i]*c[j]; c2[i]=s; }
     for(k=0;k<N;k++) for(i=0;i<3;i++) Q[n*(3*k+i)+3*k+i] += pci[k]->L;
     for(k=0;k<N;k++) init[3*k] = 1.0;          /* _rkFDSolverQPASMInit (rkfd_vert.c:234-244) */
-    ork_qp_solve_asm(n,m,Q,c2,nf,dz,init,f,idx);
+    { int term = 0, it = ork_qp_solve_asm_ex(n,m,Q,c2,nf,dz,init,f,idx,&term);
+      e->qp_n = n; e->qp_m = m; e->qp_iter = it; e->qp_term = term;
+      e->qp_Q = (double*)realloc(e->qp_Q,n*n*8); e->qp_c = (double*)realloc(e->qp_c,n*8); e->qp_nf = (double*)realloc(e->qp_nf,m*n*8);
+      e->qp_x = (double*)realloc(e->qp_x,n*8); e->qp_idx = (int*)realloc(e->qp_idx,m*sizeof(int));
+      memcpy(e->qp_Q,Q,n*n*8); memcpy(e->qp_c,c2,n*8); memcpy(e->qp_nf,nf,m*n*8); memcpy(e->qp_x,f,n*8); memcpy(e->qp_idx,idx,m*sizeof(int)); }
     for(i=0;i<n;i++) f[i] /= dt;
     /* _rkFDSolverSetForce (rkfd_vert.c:286-324) */
     for(k=0;k<N;k++){ int s = slot[k], flag = 0; double *fw = e->c_f+3*s;
@@ -1453,6 +1480,21 @@ void ork_env_get_volume(const ork_env *e, int *np, int *type, double *wrench, do
 int ork_world_npair(const ork_world *w){ return w->npair; }
 /* test hook: Q6 (36, row-major), c6 (6), norm (3) per pair of the last Volume evaluation (rkfd_volume.c:397-491) */
 void ork_env_get_volume_constraint(const ork_env *e, double *qc){ memcpy(qc,e->v_qc,45*(e->w->npair>0?e->w->npair:1)*8); }
+/* test hook: the Vert QP of the last evaluation (min 1/2 x^T Q x + c^T x, nf x >= 0), its answer x (= f dt), the final
+ * active set and how the active-set loop ended: info = {n, m, iterations, term (0 optimal, 1 anti-cycling exit, 2 cap)} */
+int ork_env_get_qp(const ork_env *e, double *Q, double *c, double *nf, double *x, int *idx, int *info, int capn, int capm)
+{
+  int n = e->qp_n, m = e->qp_m;
+  if( info ){ info[0] = n; info[1] = m; info[2] = e->qp_iter; info[3] = e->qp_term; }
+  if( n > capn || m > capm || !e->qp_Q ) return 0;
+  if(Q) memcpy(Q,e->qp_Q,n*n*8);
+  if(c) memcpy(c,e->qp_c,n*8);
+  if(nf) memcpy(nf,e->qp_nf,m*n*8);
+  if(x) memcpy(x,e->qp_x,n*8);
+  if(idx) memcpy(idx,e->qp_idx,m*sizeof(int));
+  return n;
+}
+
 int ork_env_get_rigid_system(const ork_env *e, double *A, double *b, double *f, int cap)
 {
   int n = e->rn; if( n > cap ) return -n;

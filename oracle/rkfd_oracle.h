@@ -98,6 +98,11 @@ double ork_env_energy(const ork_env *e);
 /* last rigid-contact system (Delassus matrix A (n x n, row-major), bias b, solution f); returns n */
 int ork_env_get_rigid_system(const ork_env *e, double *A, double *b, double *f, int cap);
 
+/* test hook: the Vert QP of the last evaluation and how its active-set loop ended (see rkfd_oracle.c) */
+int ork_env_get_qp(const ork_env *e, double *Q, double *c, double *nf, double *x, int *idx, int *info, int capn, int capm);
+int ork_qp_solve_asm_ex(int n, int m, const double *q, const double *c, const double *a,
+                        const double *b, const double *init, double *ans, int *idx, int *term);
+
 /* Volume solver (rkfd_volume.c) results of the last evaluation, per pair: np = contact-polygon planes (-1: no contact
  * volume), type = pair friction type, wrench (6, world axes, at center), center (3) */
 void ork_env_get_volume(const ork_env *e, int *np, int *type, double *wrench, double *center);

@@ -70,6 +70,10 @@ constexpr int GEO_DOUBLES = 27;    /* per rigid contact: vw n t1 t2 d vel prob r
  * g (3x6) h (3x6) b (3) diag (3) f (3) rho (3) prob (3) mu slot */
 constexpr int MAX_RG = 4;                      /* contact groups (links in different chains) of the wrench-coordinate paths */
 constexpr int W1_CT = 36*MAX_RG, W1_CTN = 53;
+/* anti-cycling history of the Vert active-set loop (rkfd_opt_qp.c:152-171 keeps an unbounded list): QP_HIST entries of
+ * (active sets of 3 vertices packed into one double - 16 bits each, exact - ..., objective value) */
+constexpr int QP_HIST = 128;
+RKFD_HD int qp_hist_stride(int nrs){ return (nrs + 2)/3 + 1; }
 
 enum StageMode : int { ST_K1 = 0, ST_K2 = 1, ST_K3 = 2, ST_K4 = 3, ST_REF = 4, ST_EVAL = 5, ST_EVAL_REF = 6,
                        ST_PROBE = 7 /* acceleration pass of rkFDUpdateAccBias: no integrator bookkeeping, no q'' output */ };
@@ -1291,8 +1295,8 @@ struct Core {
     const unsigned long long fl = cfl;
     const int N = RKFD_POPC64(fl & m.rigid_mask);
     if( N == 0 ) return;
-    const int pyr = m.pyramid, QP_HIST = 32, QP_MAXIT = 256;
-    const int nrs = m.nmax/3, ohist = W1_CT + W1_CTN*nrs;
+    const int pyr = m.pyramid, QP_MAXIT = 256;
+    const int nrs = m.nmax/3, ohist = W1_CT + W1_CTN*nrs, hstr = qp_hist_stride(nrs), hw = (N + 2)/3;
     const int ng = m.nrg;
     /* contacts in (pair, vertex) order: rows h, compensated velocity-level bias c0 (rkfd_vert.c:107-123, 189-232);
      * per contact in W1: x (0..2) x* (3..5) h (18..35) c0 (36..38) fric (39) L (40) rho (45..47) prob (48..50) mu slot */
@@ -1458,16 +1462,20 @@ struct Core {
       /* anti-cycling: same active set with the same objective value -> stop (rkfd_opt_qp.c:152-171) */
       double objv = 0.5*lx2;
       for(int g=0;g<ng;g++) for(int r=0;r<6;r++){ double sum = 0; for(int j=0;j<6;j++) sum += c.W1(36*g + 6*r+j)*vv[g][j]; objv += 0.5*vv[g][r]*sum + w[g][r]*vv[g][r]; }
+      double pk[(MAX_SLOTS + 2)/3];
+      for(int k3=0;k3<hw;k3++){ double v = 0.0;
+        for(int j=2;j>=0;j--){ const int k = 3*k3 + j; v = v*65536.0 + ( k < N ? (double)am[k] : 0.0 ); }
+        pk[k3] = v; }
       bool endflag = false;
       for(int h=0;h<nhist && !endflag;h++){
         bool eq = true;
-        for(int k=0;k<N;k++) if( (double)am[k] != c.W1(ohist+h*(nrs+1)+k) ){ eq = false; break; }
-        if( eq && !(fabs(c.W1(ohist+h*(nrs+1)+nrs)/objv - 1.0) > 1.0e-8) ) endflag = true;
+        for(int k3=0;k3<hw;k3++) if( pk[k3] != c.W1(ohist+h*hstr+k3) ){ eq = false; break; }
+        if( eq && !(fabs(c.W1(ohist+h*hstr+hstr-1)/objv - 1.0) > 1.0e-8) ) endflag = true;
       }
       if( endflag ) break;
       if( nhist < QP_HIST ){
-        for(int k=0;k<N;k++) c.W1(ohist+nhist*(nrs+1)+k) = (double)am[k];
-        c.W1(ohist+nhist*(nrs+1)+nrs) = objv;
+        for(int k3=0;k3<hw;k3++) c.W1(ohist+nhist*hstr+k3) = pk[k3];
+        c.W1(ohist+nhist*hstr+hstr-1) = objv;
         nhist++;
       } else { bad |= 2; break; }
     }

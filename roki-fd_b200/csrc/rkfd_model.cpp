@@ -213,7 +213,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
     bool lpos = true;           /* the Vert path divides by the relaxation of every rigid pair */
     for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID && !(m.pair[p].L > 0.0) ) lpos = false;
     if( lk >= 0 && m.solver == S_MLCP ){ m.rigid_link = lk; m.ws1_doubles = W1_CT + W1_CTN*nrs; }
-    if( lk >= 0 && m.solver == S_VERT && lpos && m.pyramid <= 12 ){ m.rigid_link = lk; m.ws1_doubles = W1_CT + W1_CTN*nrs + 32*(nrs+1); }
+    if( lk >= 0 && m.solver == S_VERT && lpos && m.pyramid <= 12 ){ m.rigid_link = lk; m.ws1_doubles = W1_CT + W1_CTN*nrs + QP_HIST*qp_hist_stride(nrs); }
     if( m.rigid_link < 0 ) m.nrg = 0;
   }
   if( m.has_rigid && m.solver == S_VOLUME ){

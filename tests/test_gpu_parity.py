@@ -251,20 +251,25 @@ RIGID_WORLDS = {
     "two_box_vert_default_ci": lambda: ch.World(chains=[ch.box("a"), ch.box("b"), ch.floor()], solver="Vert"),
 }
 
-# Vert with relaxation L = 1e-4 (contactinfo.ztk): QP Hessian cond ~ 1e5 and 1e-12 decision thresholds in the
-# active-set iteration (rkfd_opt_qp.c:33,110,148) make the iteration path rounding dependent: statistical parity.
+# Vert with relaxation L = 1e-4 (contactinfo.ztk): KKT matrices of condition ~1e7 against the absolute 1e-12 decision
+# thresholds of the active-set loop (rkfd_opt_qp.c:33,110,148).  Round 1 agreed on 69 % of the contact environments of C5:
+# the ORACLE's pseudo-inverse noise made x* of consecutive iterations differ by more than 1e-12 and the loop left through
+# its anti-cycling exit short of the minimiser (the device path was at the minimiser every time: KKT residual 1e-10).
+# With the oracle's zLESolveMP refined to rounding (pinned against 50-digit arithmetic, tests/test_oracle_physics.py)
+# both sides follow the exact-arithmetic path.  (name, base height, environments, required share of contact environments
+# within 1e-9).  "deep" pushes the cube up to 20 cm into the floor: |f dt| ~ 2e3, where 1e-12 is 4 ulp.
 STAT_WORLDS = {
-    "box_vert": (lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="Vert"), 0.95),
-    "c5_arm7_vert": (lambda: ch.world_c5(base_z=0.1, solver="Vert"), 0.5),
+    "c5_arm7_vert": (lambda: ch.world_c5(base_z=0.3, solver="Vert"), 4096, 0.999),
+    "box_vert": (lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="Vert"), 512, 0.999),
+    "c5_arm7_vert_deep": (lambda: ch.world_c5(base_z=0.1, solver="Vert"), 512, 0.95),
 }
 
 
 @pytest.mark.parametrize("name", list(STAT_WORLDS))
-def test_vert_qp_ill_conditioned_statistical(capi, oracle, name):
-    mk, frac = STAT_WORLDS[name]
+def test_vert_qp_relaxation_1e_4(capi, oracle, name):
+    mk, B, frac = STAT_WORLDS[name]
     w = mk()
-    B = 512
-    q, qd, u = ch.sample_state(w, B, seed=5)
+    q, qd, u = ch.sample_state(w, B, seed=20260418 if B == 4096 else 5)
     if "box" in name:
         q[:, 2] = np.linspace(-0.01, 0.08, B)
         q[:, 1] = np.linspace(-0.3, 0.3, B)
@@ -272,20 +277,16 @@ def test_vert_qp_ill_conditioned_statistical(capi, oracle, name):
     _, _, gqdd = fd.batch_get_state()
     a, t, r, f = fd.batch_get_contact()
     assert np.isfinite(gqdd).all()
-    ow = oracle.OracleWorld(w)
-    good = nenv = 0
-    for b in range(B):
-        e = ow.env(); e.set_state(q[b], qd[b]); e.set_motor_input(u[b])
-        ref = e.eval(True)
-        oa, ot, orr, of = e.get_contact()
-        assert (a[b] == oa).all()
-        if oa.sum() == 0:
-            assert relerr(gqdd[b], ref) < 1e-9
-            continue
-        nenv += 1
-        good += relerr(gqdd[b], ref) < 1e-8
-    print("Vert QP %s: %d/%d contact envs within 1e-8 of the oracle" % (name, good, nenv))
-    assert good >= frac * nenv
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=0)
+    oqdd, oa, ot, of = o[2], o[3], o[4], o[5]
+    assert (a == oa).all()
+    err = np.abs(gqdd - oqdd).max(1) / np.maximum(np.abs(oqdd).max(1), 1e-12)
+    ferr = np.abs(f - of).reshape(B, -1).max(1) / np.maximum(np.abs(of).reshape(B, -1).max(1), 1e-12)
+    cont = oa.sum(1) > 0
+    assert (err[~cont] < 1e-9).all()
+    good = (err[cont] < 1e-9) & (ferr[cont] < 1e-9) & ((t == ot) | (oa == 0)).all(1)[cont]
+    print("Vert QP %s: %d/%d contact envs within 1e-9 of the oracle (q'' and forces), worst q'' %.2e" % (name, good.sum(), cont.sum(), err[cont].max()))
+    assert cont.sum() > 20 and good.sum() >= frac * cont.sum()
     fd.destroy()
 
 

@@ -151,6 +151,7 @@ RIGID_WORLDS = {
     "box_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="MLCP"),
     "box_hardsoft_mlcp": lambda: ch.World(chains=[ch.box(), ch.floor_hardsoft()], contact_info=ch.contact_info_table(), solver="MLCP"),
     "c5_arm7_vert": lambda: ch.world_c5(base_z=0.1, solver="Vert"),
+    "c5_arm7_vert_baseline": lambda: ch.world_c5(base_z=0.3, solver="Vert"),
     "box_vert": lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="Vert"),
     "box_vert_default_ci": lambda: ch.World(chains=[ch.box(), ch.floor()], solver="Vert"),
     # two free bodies on the floor: contact links in different chains -> two groups of the wrench-coordinate paths
@@ -159,18 +160,19 @@ RIGID_WORLDS = {
 }
 
 
-# Vert with a small relaxation (contactinfo.ztk: L = 1e-4) gives a QP whose Hessian has cond ~ 1e5 and whose
-# active-set iteration is decided by 1e-12 thresholds (rkfd_opt_qp.c:33,110,148): rounding-level differences
-# change the path and the early (anti-cycling) exit, so agreement is statistical there.  With the solver's own
-# default contact info (L = 1) agreement is exact.
-STATISTICAL = {"c5_arm7_vert": 0.5, "box_vert": 0.95}
+# Vert with a small relaxation (contactinfo.ztk: L = 1e-4) gives KKT matrices of condition ~1e7 while the active-set loop
+# decides with absolute 1e-12 thresholds (rkfd_opt_qp.c:33,110,148).  With the oracle's zLESolveMP refined to rounding both
+# sides follow the path of exact arithmetic (tests/ref_qp_mp.py) and agree on every environment of BASELINE's C5 state
+# distribution ("c5_arm7_vert_baseline").  "c5_arm7_vert" is a stress case: the cube is pushed up to 20 cm INTO the floor,
+# |f dt| reaches 2e3 and 1e-12 is then 4 ulp - one of its 32 contact environments is decided by the last bits.
+STATISTICAL = {"c5_arm7_vert": 0.95}
 
 
 @pytest.mark.parametrize("name", list(RIGID_WORLDS))
 def test_rigid_eval_matches_oracle(oracle, name):
     """One committing evaluation with rigid contacts: q'', contact forces and friction flags."""
     w = RIGID_WORLDS[name]()
-    B = 400 if name == "c5_arm7_vert" else 48      # the statistical case needs a sample (8 % of the envs touch the floor)
+    B = 1500 if name == "c5_arm7_vert_baseline" else 400 if name == "c5_arm7_vert" else 48      # the statistical case needs a sample (8 % of the envs touch the floor)
     q, qd, u = ch.sample_state(w, B, seed=5)
     q = biped_pose(name, q)
     if "box" in name:

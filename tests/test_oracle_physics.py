@@ -209,6 +209,52 @@ def test_qp_asm_matches_scipy(oracle):
         assert (A @ x - b > -1e-9).all()
 
 
+def _golden_vert_qps():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vert_qp_c5.npz"))
+
+
+def test_le_solve_mp_on_ill_conditioned_kkt_matches_50_digit_solution(oracle):
+    """[EXT A-14] zLESolveMP = THE minimum-norm solution: on a KKT matrix of BASELINE config C5 (relaxation 1e-4: condition
+    ~1e7, redundant active rows: singular) the oracle's solve agrees with the 50-digit pseudo-inverse to a few ulp of the
+    primal part, which is what the absolute 1e-12 decisions of rkfd_opt_qp.c:108-110 need."""
+    import mpmath as mp
+    import ref_qp_mp
+    g = _golden_vert_qps()
+    e = 2862
+    Q, c, nf = g["Q%d" % e], g["c%d" % e], g["nf%d" % e]
+    n = len(c)
+    for act in ([0, 1, 2, 3, 4, 5, 6, 7, 12], [3, 4, 5, 12], [3, 4, 12]):     # all 8 rows of a vertex (rank 3), 3 of them, 2
+        mp.mp.dps = 50
+        K = ref_qp_mp.kkt(Q.tolist(), nf.tolist(), act)
+        xm = ref_qp_mp.pinv_solve_sym(K, mp.matrix(list(c) + [0] * len(act)))
+        Kd = np.array([[float(K[i, j]) for j in range(K.cols)] for i in range(K.rows)])
+        xo = oracle.le_solve_mp_sym(Kd, np.concatenate([c, np.zeros(len(act))]))
+        xm = np.array([float(v) for v in xm])
+        assert np.abs(xo[:n] - xm[:n]).max() <= 4e-16 * np.abs(xm[:n]).max() + 1e-15, (act, np.abs(xo[:n] - xm[:n]).max())
+        assert np.abs(xo[n:] - xm[n:]).max() <= 1e-9 * max(1.0, np.abs(xm[n:]).max())
+
+
+def test_qp_asm_follows_the_exact_arithmetic_path_on_c5_golden_qps(oracle):
+    """Golden vectors (tests/golden/vert_qp_c5.npz, made by tests/golden/make_vert_qp_golden.py): rkFDQPSolveASM evaluated in
+    50-digit arithmetic on Vert QPs of BASELINE config C5.  In round 1 the oracle left the loop through the anti-cycling
+    exit (rkfd_opt_qp.c:152-171) short of the minimiser on every one of them (objective up to 20 % above the minimum),
+    because x* of two consecutive iterations differed by the rounding noise of its pseudo-inverse."""
+    g = _golden_vert_qps()
+    for e in g["envs"]:
+        Q, c, nf, xg, ig = g["Q%d" % e], g["c%d" % e], g["nf%d" % e], g["x%d" % e], g["idx%d" % e]
+        init = np.zeros(len(c)); init[0::3] = 1.0
+        x, idx, it = oracle.qp_solve_asm(Q, c, nf, np.zeros(nf.shape[0]), init)
+        assert np.abs(x - xg).max() <= 1e-11 * np.abs(xg).max(), (e, np.abs(x - xg).max())
+        assert (idx == ig).all(), e
+        assert abs(it - int(g["info%d" % e][0])) <= 1 and int(g["info%d" % e][1]) == 0
+        # the answer is the minimiser: KKT residual with non-negative multipliers on the active rows
+        from scipy.optimize import nnls
+        grad = Q @ x + c
+        _, rn = nnls(nf[idx == 1].T, grad)
+        assert rn <= 1e-9 * np.abs(grad).max() and (nf @ x).min() > -1e-11
+
+
 @pytest.mark.parametrize("solver", ["MLCP", "Vert"])
 def test_box_rests_on_rigid_ground(oracle, solver):
     w = ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver=solver)
