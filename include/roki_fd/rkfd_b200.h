@@ -287,6 +287,11 @@ __ROKI_FD_EXPORT int rkFDBatchSetContactState(rkFD *fd, const int *active, const
 __ROKI_FD_EXPORT int rkFDBatchGetPivot(rkFD *fd, int *type, double *prev_trq);
 __ROKI_FD_EXPORT int rkFDBatchSetPivot(rkFD *fd, const int *type, const double *prev_trq);
 __ROKI_FD_EXPORT int rkFDBatchGetStatus(rkFD *fd, int *status);                 /* per env, bit0: non-finite acceleration */
+/* end-of-run statistics of the batch, reduced on the device; sums: out[0] environments, [1] environments with an active
+ * contact, [2] active contact vertices, [3] environments with a non-zero status word; maxima: [4] |q''|, [5] |q'|;
+ * [6..7] reserved (0).  A one-process-per-GPU job all-reduces [0..3] with SUM and [4..5] with MAX (SURVEY.md section 8e:
+ * the only collective of the path, after the run). */
+__ROKI_FD_EXPORT int rkFDBatchStats(rkFD *fd, double out[8]);
 __ROKI_FD_EXPORT int rkFDBatchEval(rkFD *fd, int do_up_ref);                    /* one evaluation on the committed state */
 __ROKI_FD_EXPORT rkFD *rkFDUpdateN(rkFD *fd, int k);                            /* k steps in one launch, asynchronous */
 __ROKI_FD_EXPORT int rkFDBatchSync(rkFD *fd);

@@ -78,7 +78,7 @@ def lib():
         "rkFDBatchGetPivot": (ci, [vp, vp, vp]), "rkFDBatchSetPivot": (ci, [vp, vp, vp]),
         "rkFDBatchSetStateAsync": (ci, [vp, vp, vp]), "rkFDBatchSetMotorInputAsync": (ci, [vp, vp]),
         "rkFDBatchGetStateAsync": (ci, [vp, vp, vp, vp]), "rkFDBatchJoin": (ci, [vp]),
-        "rkFDBatchGetStatus": (ci, [vp, vp]), "rkFDBatchEval": (ci, [vp, ci]), "rkFDBatchSync": (ci, [vp]),
+        "rkFDBatchGetStatus": (ci, [vp, vp]), "rkFDBatchStats": (ci, [vp, C.POINTER(cd)]), "rkFDBatchEval": (ci, [vp, ci]), "rkFDBatchSync": (ci, [vp]),
         "rkFDBatchDevicePtr": (vp, [vp, ci, ci, _ip, _ip]), "rkFDBatchLaunchCount": (C.c_longlong, [vp]),
         "rkFDBatchLastError": (C.c_char_p, []), "rkFDBatchDeviceCount": (ci, []), "rkFDB200MeasureFp64": (ci, [_dp]),
     }
@@ -249,10 +249,12 @@ class RkFD:
         self._ck(lib().rkFDBatchSync(self.h))
 
     def update(self):
-        lib().rkFDUpdate(self.h)
+        if not lib().rkFDUpdate(self.h):          # NULL: no device engine (there is no CPU fallback)
+            raise RuntimeError(self.last_error())
 
     def update_n(self, k):
-        lib().rkFDUpdateN(self.h, k)
+        if not lib().rkFDUpdateN(self.h, k):
+            raise RuntimeError(self.last_error())
 
     def update_destroy(self):
         lib().rkFDUpdateDestroy(self.h)
@@ -388,6 +390,12 @@ class RkFD:
         s = np.zeros(self.env_num, np.int32)
         self._ck(lib().rkFDBatchGetStatus(self.h, _ptr(s)))
         return s
+
+    def batch_stats(self):
+        """[envs, envs in contact, active contact vertices, flagged envs (sums), max|q''|, max|q'| (maxima)] of this process's batch."""
+        out = (C.c_double * 8)()
+        self._ck(lib().rkFDBatchStats(self.h, out))
+        return [float(v) for v in out[:6]]
 
     def batch_eval(self, do_up_ref=False):
         self._ck(lib().rkFDBatchEval(self.h, int(do_up_ref)))

@@ -109,7 +109,7 @@ extern "C" void rkJointMotorSetInput(rkJoint *j, double *val)
   ChainImpl *ci = j->chain; ci->motor_in[j->link] = *val;
   FDImpl *fi = ci->owner;
   if( fi && fi->engine && ci->link_base >= 0 ){
-    try { for(int e=0;e<fi->B;e++) fi->engine->set_motor_input_one(e, ci->link_base + j->link, *val); }
+    try { fi->engine->fill_rows(2, ci->link_base + j->link, 1, val); }      /* the row u[link][0..B) in one fill */
     catch(const std::exception &ex){ complain("rkJointMotorSetInput", ex.what()); }
   }
 }
@@ -271,6 +271,9 @@ extern "C" rkFDCell *rkFDChainRegFile(rkFD *fd, char filename[])
 extern "C" bool rkFDChainUnreg(rkFD *fd, rkFDCell *cell)
 {
   FDImpl *fi = FI(fd); if( !fi ) return false;
+  /* the engine holds the flattened model: the reference sizes its solver and pair arrays in rkFDUpdateInit as well
+   * (rkfd_sim.c:479-490) - unregister between rkFDUpdateDestroy and the next rkFDUpdateInit */
+  if( fi->engine ){ complain("rkFDChainUnreg", "unregistration after rkFDUpdateInit is not supported (call rkFDUpdateDestroy first)"); return false; }
   for(size_t i=0;i<fi->cells.size();i++) if( fi->cells[i] == cell ){
     fi->cells.erase(fi->cells.begin()+i);
     rkChainDestroy(rkFDCellChain(cell)); std::free(cell);
@@ -279,17 +282,30 @@ extern "C" bool rkFDChainUnreg(rkFD *fd, rkFDCell *cell)
   }
   return false;
 }
+/* On a running simulator the cell windows of the reference alias fd->dis/vel (rkfd_sim.c:277-287): a SetDis/SetVel between
+ * two updates changes the state the next step integrates from.  Here that state lives on the device: the cell's slice is
+ * written to it for every environment (reset / teleport callers). */
+static void push_cell_state(rkFDCell *lc, int which)
+{
+  ChainImpl *ci = CI(rkFDCellChain(lc)); FDImpl *fi = ci ? ci->owner : nullptr;
+  if( !fi || !fi->engine || ci->is_static() ) return;
+  const int n = lc->data._dis.size; if( n <= 0 ) return;
+  try { fi->engine->fill_rows(which, ci->q_base, n, which == 0 ? lc->data._dis.buf : lc->data._vel.buf); }
+  catch(const std::exception &ex){ complain(which == 0 ? "rkFDChainSetDis" : "rkFDChainSetVel", ex.what()); }
+}
 extern "C" void rkFDChainSetDis(rkFDCell *lc, zVec dis)
 {
   if( !lc || !dis ) return;
   ChainImpl *ci = CI(rkFDCellChain(lc));
   for(int k=0;k<dis->size && k<lc->data._dis.size;k++){ lc->data._dis.buf[k] = dis->buf[k]; ci->dis[k] = dis->buf[k]; }
+  push_cell_state(lc, 0);
 }
 extern "C" void rkFDChainSetVel(rkFDCell *lc, zVec vel)
 {
   if( !lc || !vel ) return;
   ChainImpl *ci = CI(rkFDCellChain(lc));
   for(int k=0;k<vel->size && k<lc->data._vel.size;k++){ lc->data._vel.buf[k] = vel->buf[k]; ci->vel[k] = vel->buf[k]; }
+  push_cell_state(lc, 1);
 }
 
 static void ci_to_public(rkFD *fd)
@@ -348,6 +364,8 @@ extern "C" void rkFDUpdateInit(rkFD *fd)
     w.integrator = fd->ode.integrator;
     std::string err;
     if( !build_model(w, fi->model, err) ) throw std::runtime_error(err);
+    /* static chains carry no joint state, so the device rows are the host offsets of relayout() */
+    if( fi->model.nq != fd->size ) throw std::runtime_error("joint state layout mismatch between the host mirror and the device model");
     fi->engine = new Engine(fi->model, fi->B, fi->devices);
     const int n = fd->size, nl = fi->model.nl, B = fi->B;
     /* initial state: the batched arrays when given, else the scalar state replicated over the envs */
@@ -367,7 +385,9 @@ extern "C" void rkFDUpdateInit(rkFD *fd)
 extern "C" rkFD *rkFDUpdateN(rkFD *fd, int k)
 {
   FDImpl *fi = FI(fd); if( !fi ) return fd;
-  if( !fi->engine ){ if( !fi->warned ){ complain("rkFDUpdate", "no device engine (rkFDUpdateInit failed or was not called)"); fi->warned = true; } return fd; }
+  /* NULL and a message on EVERY call: `while( rkFDTime(&fd) < T ) rkFDUpdate(&fd);` would otherwise spin on a time that never
+   * advances; the time is pushed to +inf as well so that such loops end even when the return value is ignored */
+  if( !fi->engine ){ complain("rkFDUpdate", "no device engine (rkFDUpdateInit failed or was not called; there is no CPU fallback)"); fd->t = HUGE_VAL; return NULL; }
   try {
     fi->engine->step(k);
     fd->t += k*fd->prp.dt; fd->solver.t = fd->t;
@@ -452,6 +472,8 @@ extern "C" int rkFDBatchSetContactState(rkFD *fd, const int *a, const int *t, co
 extern "C" int rkFDBatchGetPivot(rkFD *fd, int *t, double *p){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->get_pivot(t, p)); }
 extern "C" int rkFDBatchSetPivot(rkFD *fd, const int *t, const double *p){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->set_pivot(t, p)); }
 extern "C" int rkFDBatchGetStatus(rkFD *fd, int *s){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->get_status(s)); }
+/* end-of-run statistics of the whole batch, reduced on the device (what a multi-process job all-reduces) */
+extern "C" int rkFDBatchStats(rkFD *fd, double out[8]){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->stats(out)); }
 extern "C" int rkFDBatchEval(rkFD *fd, int ref){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->eval(ref != 0)); }
 extern "C" int rkFDBatchSetStateAsync(rkFD *fd, const double *q, const double *qd){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->set_state_async(q, qd)); }
 extern "C" int rkFDBatchSetMotorInputAsync(rkFD *fd, const double *u){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->set_motor_input_async(u)); }

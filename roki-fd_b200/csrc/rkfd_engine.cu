@@ -34,18 +34,71 @@ void cuda_check(int err, const char *what)
 
 int device_count(){ int n = 0; if( cudaGetDeviceCount(&n) != cudaSuccess ) return 0; return n; }
 
-/* env-major host layout [B][n] <-> device SoA [n][ld] */
-__global__ void rkfd_scatter_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld)
+/* env-major host layout [B][n] <-> device SoA [n][ld]: transposes through a shared-memory tile of TE environments
+ * (TE*n contiguous doubles on the env-major side, n rows of TE contiguous doubles on the SoA side), so that both the
+ * global loads and the global stores of a warp are contiguous (round 1 moved one env-major row per thread: stride n*8 B,
+ * 64 us per array of 262,144 x 7; HBM-bound now: 2 x 14.7 MB per array).  The tile row stride is padded to an odd number
+ * of doubles so that the transposed shared-memory accesses spread over the banks. */
+constexpr int XP_THREADS = 256;
+/* environments per tile: 64 (512-byte rows on the SoA side) while the tile stays under the 48 KB default limit */
+static inline int xp_te(int n){ int te = 64; while( te > 4 && (size_t)te*(n | 1)*sizeof(double) > 40*1024 ) te >>= 1; return te; }
+__global__ void __launch_bounds__(XP_THREADS) rkfd_scatter_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE)
 {
-  const int e = blockIdx.x*blockDim.x + threadIdx.x;
-  if( e >= B ) return;
-  for(int k=0;k<n;k++) dst[(size_t)k*ld + e] = src[(size_t)e*n + k];
+  extern __shared__ double xp_tile[];
+  const int e0 = blockIdx.x*XP_TE, ne = min(XP_TE, B - e0), ns = n | 1;
+  const double *s0 = src + (size_t)e0*n;
+  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; xp_tile[e*ns + k] = s0[i]; }
+  __syncthreads();
+  for(int i=threadIdx.x; i<n*XP_TE; i+=XP_THREADS){ const int k = i/XP_TE, e = i - k*XP_TE; if( e < ne ) dst[(size_t)k*ld + e0 + e] = xp_tile[e*ns + k]; }
 }
-__global__ void rkfd_gather_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld)
+__global__ void __launch_bounds__(XP_THREADS) rkfd_gather_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE)
+{
+  extern __shared__ double xp_tile[];
+  const int e0 = blockIdx.x*XP_TE, ne = min(XP_TE, B - e0), ns = n | 1;
+  for(int i=threadIdx.x; i<n*XP_TE; i+=XP_THREADS){ const int k = i/XP_TE, e = i - k*XP_TE; if( e < ne ) xp_tile[e*ns + k] = src[(size_t)k*ld + e0 + e]; }
+  __syncthreads();
+  double *d0 = dst + (size_t)e0*n;
+  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; d0[i] = xp_tile[e*ns + k]; }
+}
+static inline int xp_grid(int B, int n){ const int te = xp_te(n); return (B + te - 1)/te; }
+static inline size_t xp_smem(int n){ return (size_t)xp_te(n)*(n | 1)*sizeof(double); }
+
+/* rows k0..k0+n-1 of an SoA array <- one value per row, every environment (rkFDChainSetDis/SetVel and
+ * rkJointMotorSetInput on a running simulator: the reference's cell windows alias fd->dis/vel, rkfd_sim.c:277-287) */
+__global__ void rkfd_fill_rows_kernel(double * __restrict__ dst, int ld, int B, int n, const double * __restrict__ vals)
 {
   const int e = blockIdx.x*blockDim.x + threadIdx.x;
   if( e >= B ) return;
-  for(int k=0;k<n;k++) dst[(size_t)e*n + k] = src[(size_t)k*ld + e];
+  for(int k=0;k<n;k++) dst[(size_t)k*ld + e] = vals[k];
+}
+
+/* end-of-run statistics of one shard, reduced on the device (rkFDBatchStats): out[0] environments, [1] environments with an
+ * active contact, [2] active contact vertices, [3] environments with a non-zero status word (sums); [4] max |q''|,
+ * [5] max |q'| (non-negative doubles order like their bit patterns: atomicMax on the 64-bit integer view) */
+__global__ void __launch_bounds__(256) rkfd_stats_kernel(StateDev st, int cur, int nq, unsigned long long active_mask, double *out)
+{
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  double cnt[4] = {0,0,0,0}, mx[2] = {0,0};
+  if( e < st.B ){
+    const int na = __popcll(st.cflags[e] & active_mask);
+    cnt[0] = 1.0; cnt[1] = na > 0 ? 1.0 : 0.0; cnt[2] = (double)na; cnt[3] = st.status[e] != 0 ? 1.0 : 0.0;
+    for(int k=0;k<nq;k++){
+      const double a = fabs(st.qdd[(size_t)k*st.ld + e]), v = fabs(st.qd[cur][(size_t)k*st.ld + e]);
+      if( a == a && a > mx[0] ) mx[0] = a;
+      if( v == v && v > mx[1] ) mx[1] = v;
+    }
+  }
+#pragma unroll
+  for(int o=16;o>0;o>>=1){
+#pragma unroll
+    for(int i=0;i<4;i++) cnt[i] += __shfl_xor_sync(0xffffffffu, cnt[i], o);
+#pragma unroll
+    for(int i=0;i<2;i++) mx[i] = fmax(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], o));
+  }
+  if( (threadIdx.x & 31) == 0 ){
+    for(int i=0;i<4;i++) if( cnt[i] != 0.0 ) atomicAdd(out + i, cnt[i]);
+    for(int i=0;i<2;i++) atomicMax((unsigned long long*)(out + 4 + i), (unsigned long long)__double_as_longlong(mx[i]));
+  }
 }
 
 /* register-resident DFMA loop on every SM: the measured fp64 roofline denominator (MEASURED_PEAKS.json
@@ -162,7 +215,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     st.ws = ( model.ws_doubles > 0 && model.rigid_link < 0 ) ? dalloc<double>(*s, (size_t)(s->ld/32)*model.ws_doubles) : nullptr;
     st.ws1 = model.ws1_doubles > 0 ? dalloc<double>(*s, (size_t)model.ws1_doubles*s->ld) : nullptr;
     int nmax = nq; if( nl > nmax ) nmax = nl; if( 3*ns > nmax ) nmax = 3*ns;
-    s->nstage = (size_t)nmax*s->B; s->dstage = dalloc<double>(*s, s->nstage);
+    s->nstage = (size_t)nmax*s->B; if( s->nstage < 256 ) s->nstage = 256; s->dstage = dalloc<double>(*s, s->nstage);
     /* launch configuration: the block size that keeps most environments resident per SM; scratch in HBM
      * (gscr) only when no shared-memory variant fits */
     int best = 0; const bool rigid = model.has_rigid;
@@ -297,13 +350,13 @@ static void h2d_scatter(Shard &s, const double *src, int n, double *dst)
 {
   if( n <= 0 ) return;
   CK(cudaMemcpyAsync(s.dstage, src + (size_t)s.e0*n, (size_t)s.B*n*sizeof(double), cudaMemcpyHostToDevice, s.stream));
-  rkfd_scatter_kernel<<<(s.B+255)/256, 256, 0, s.stream>>>(s.dstage, dst, s.B, n, s.ld);
+  rkfd_scatter_kernel<<<xp_grid(s.B, n), XP_THREADS, xp_smem(n), s.stream>>>(s.dstage, dst, s.B, n, s.ld, xp_te(n));
   CK(cudaGetLastError());
 }
 static void d2h_gather(Shard &s, const double *src, int n, double *dst)
 {
   if( n <= 0 ) return;
-  rkfd_gather_kernel<<<(s.B+255)/256, 256, 0, s.stream>>>(src, s.dstage, s.B, n, s.ld);
+  rkfd_gather_kernel<<<xp_grid(s.B, n), XP_THREADS, xp_smem(n), s.stream>>>(src, s.dstage, s.B, n, s.ld, xp_te(n));
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(dst + (size_t)s.e0*n, s.dstage, (size_t)s.B*n*sizeof(double), cudaMemcpyDeviceToHost, s.stream));
 }
@@ -333,7 +386,7 @@ static void h2d_scatter_async(Shard &s, const double *src, int n, double *dst)
   CK(cudaMemcpyAsync(s.ring[b], src + (size_t)s.e0*n, (size_t)s.B*n*sizeof(double), cudaMemcpyHostToDevice, s.h2d_stream));
   CK(cudaEventRecord(s.ring_ready[b], s.h2d_stream));
   CK(cudaStreamWaitEvent(s.stream, s.ring_ready[b], 0));
-  rkfd_scatter_kernel<<<(s.B+255)/256, 256, 0, s.stream>>>(s.ring[b], dst, s.B, n, s.ld);
+  rkfd_scatter_kernel<<<xp_grid(s.B, n), XP_THREADS, xp_smem(n), s.stream>>>(s.ring[b], dst, s.B, n, s.ld, xp_te(n));
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ring_done[b], s.stream));
 }
@@ -343,7 +396,7 @@ static void d2h_gather_async(Shard &s, const double *src, int n, double *dst)
   ring_setup(s);
   const int b = s.ring_next; s.ring_next = (b+1) % Shard::NRING;
   CK(cudaStreamWaitEvent(s.stream, s.ring_done[b], 0));
-  rkfd_gather_kernel<<<(s.B+255)/256, 256, 0, s.stream>>>(src, s.ring[b], s.B, n, s.ld);
+  rkfd_gather_kernel<<<xp_grid(s.B, n), XP_THREADS, xp_smem(n), s.stream>>>(src, s.ring[b], s.B, n, s.ld, xp_te(n));
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ring_ready[b], s.stream));
   CK(cudaStreamWaitEvent(s.d2h_stream, s.ring_ready[b], 0));
@@ -422,14 +475,37 @@ void Engine::set_motor_input(const double *u)
   for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream)); }
   CK(cudaSetDevice(prev));
 }
-void Engine::set_motor_input_one(int env, int link, double value)
+/* which: 0 q, 1 q', 2 motor input; rows k0..k0+n-1 <- vals for every environment */
+void Engine::fill_rows(int which, int k0, int n, const double *vals)
 {
+  if( n <= 0 ) return;
   int prev = 0; CK(cudaGetDevice(&prev));
   for(Shard *s : shards_){
-    if( env < s->e0 || env >= s->e0 + s->B ) continue;
     CK(cudaSetDevice(s->dev));
-    CK(cudaMemcpyAsync(s->st.u + (size_t)link*s->ld + (env - s->e0), &value, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    double *base = which == 0 ? s->st.q[s->cur] : ( which == 1 ? s->st.qd[s->cur] : s->st.u );
+    CK(cudaMemcpyAsync(s->dstage, vals, (size_t)n*sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    rkfd_fill_rows_kernel<<<(s->B+255)/256, 256, 0, s->stream>>>(base + (size_t)k0*s->ld, s->ld, s->B, n, s->dstage);
+    CK(cudaGetLastError());
+  }
+  for(Shard *s : shards_){ CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream)); }
+  CK(cudaSetDevice(prev));
+}
+
+void Engine::stats(double out[8])
+{
+  int prev = 0; CK(cudaGetDevice(&prev));
+  for(int i=0;i<8;i++) out[i] = 0.0;
+  unsigned long long amask = 0; for(int k=0;k<model_.nslot && k<32;k++) amask |= 1ull << (2*k);
+  for(Shard *s : shards_){
+    CK(cudaSetDevice(s->dev));
+    double h[8];
+    CK(cudaMemsetAsync(s->dstage, 0, 8*sizeof(double), s->stream));
+    rkfd_stats_kernel<<<(s->B+255)/256, 256, 0, s->stream>>>(s->st, s->cur, model_.nq, amask, s->dstage);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h, s->dstage, sizeof h, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    for(int i=0;i<4;i++) out[i] += h[i];
+    for(int i=4;i<6;i++) if( h[i] > out[i] ) out[i] = h[i];
   }
   CK(cudaSetDevice(prev));
 }

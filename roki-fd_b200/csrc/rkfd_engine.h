@@ -29,7 +29,10 @@ class Engine {
   void set_state(const double *q, const double *qd);
   void get_state(double *q, double *qd, double *qdd);
   void set_motor_input(const double *u);
-  void set_motor_input_one(int env, int link, double value);
+  /* rows k0..k0+n-1 of q (which 0), q' (1) or the motor input (2) <- vals, for every environment (scalar setters on a running simulator) */
+  void fill_rows(int which, int k0, int n, const double *vals);
+  /* end-of-run statistics reduced on the device: sums [0] envs [1] envs in contact [2] active contact vertices [3] flagged envs; maxima [4] |q''| [5] |q'| */
+  void stats(double out[8]);
   /* asynchronous variants (pinned host memory, valid until sync()); transfers overlap the step kernels */
   void set_state_async(const double *q, const double *qd);
   void set_motor_input_async(const double *u);

@@ -70,7 +70,12 @@ def test_no_cpu_fallback():
     fd, _ = capi.create_world(ch.world_c2(), B=4)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         fd.update_init()
-    fd.update()            # rkFDUpdate cannot fail (returns fd); it must not crash without an engine
+    # without an engine rkFDUpdate returns NULL, says so on every call and pushes the time to +inf, so that the reference
+    # idiom `while( rkFDTime(&fd) < T ) rkFDUpdate(&fd);` ends instead of spinning on a time that never advances
+    for _ in range(2):
+        with pytest.raises(RuntimeError, match="no device engine"):
+            fd.update()
+    assert fd.time == float("inf")
     with pytest.raises(RuntimeError):
         fd.batch_get_state()
     fd.destroy()
