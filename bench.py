@@ -311,6 +311,8 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: the configuration's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-upload-state", action="store_true", help="e2e leg: also re-send (q, q') host->device every step")
+    ap.add_argument("--e2e-outputs", default="q,qd", help="e2e leg: what the caller reads back every step, of q,qd,qdd (default q,qd: what the "
+                    "feedback loop of the reference's example/chain/arm_box_test.c:10-23 reads - rkJointGetDis/GetVel - before it sets the motor inputs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, emit)
@@ -402,6 +404,8 @@ def main():
     oq = torch.empty((B, nq), dtype=torch.float64).pin_memory(); oqd = torch.empty_like(oq).pin_memory()
     oqdd = torch.empty_like(oq).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
+    outs = [o for o in args.e2e_outputs.split(",") if o in ("q", "qd", "qdd")]
+    assert outs, "--e2e-outputs needs at least one of q,qd,qdd"
 
     def e2e_step():
         # every step: this step's inputs host->device from pinned memory, the step, its result device->host.
@@ -415,7 +419,8 @@ def main():
             fd.batch_set_state_async(hq.data_ptr(), hqd.data_ptr())
         fd.batch_set_motor_input_async(hu.data_ptr())
         fd.update()
-        fd.batch_get_state_async(oq.data_ptr(), oqd.data_ptr(), oqdd.data_ptr())
+        fd.batch_get_state_async(oq.data_ptr() if "q" in outs else None, oqd.data_ptr() if "qd" in outs else None,
+                                 oqdd.data_ptr() if "qdd" in outs else None)
 
     def e2e_time(closed_loop):
         for _ in range(3):
@@ -436,9 +441,9 @@ def main():
 
     e2e_value = e2e_time(False)
     e2e_closed = e2e_time(True)
-    assert np.isfinite(oq.numpy()).all() or nbad > 0
+    assert np.isfinite((oq if "q" in outs else oqd if "qd" in outs else oqdd).numpy()).all() or nbad > 0
     h2d = B * ((2 * nq if args.e2e_upload_state else 0) + nl) * 8
-    d2h = B * 3 * nq * 8
+    d2h = B * len(outs) * nq * 8
 
     # ---- end-of-run reductions over the job (the only collective, after the timed region) ----
     stats = fd.batch_stats()          # per rank: envs, envs in contact, active vertices, failed envs (sums); max|q''|, max|q'| (max)
@@ -487,10 +492,10 @@ def main():
                             "per-GPU state %.0f MB: fits the 126 MB L2 (the configuration's batch is what BASELINE.json names)" % (B * 8 * 140 / 1e6)},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                    "closed_loop_value": e2e_closed,
-                   "io": "per step: motor inputs u[B][%d] host->device%s, rkFDUpdate, (q, q', q'')[B][%d] device->host; pinned host buffers, "
+                   "io": "per step: motor inputs u[B][%d] host->device%s, rkFDUpdate, (%s)[B][%d] device->host; pinned host buffers, "
                          "asynchronous copies on their own streams.  value: pipelined caller (step k+1's inputs do not depend on step k's "
                          "outputs: transfers overlap the kernels); closed_loop_value: the caller waits for step k's state on the host before "
-                         "sending step k+1's inputs" % (nl, " + state (q, q')" if args.e2e_upload_state else "", nq)},
+                         "sending step k+1's inputs" % (nl, " + state (q, q')" if args.e2e_upload_state else "", ", ".join(outs), nq)},
            "gpu_launches": int(launches),
            "clocks": clocks,
            "job_stats": job_stats,

@@ -304,6 +304,9 @@ __ROKI_FD_EXPORT int rkFDBatchGetStateAsync(rkFD *fd, double *q, double *qd, dou
 __ROKI_FD_EXPORT int rkFDBatchJoin(rkFD *fd);
 __ROKI_FD_EXPORT void *rkFDBatchDevicePtr(rkFD *fd, int shard, int which, int *ld, int *B);  /* 0 q, 1 qd, 2 qdd, 3 u; SoA [k][ld] */
 __ROKI_FD_EXPORT long long rkFDBatchLaunchCount(rkFD *fd);
+/* the flattened model of the last rkFDUpdateInit as text (host side; also after an rkFDUpdateInit that found no device):
+ * returns the length needed */
+__ROKI_FD_EXPORT int rkFDB200DescribeModel(rkFD *fd, char *buf, int cap);
 __ROKI_FD_EXPORT const char *rkFDBatchLastError(void);
 __ROKI_FD_EXPORT int rkFDBatchDeviceCount(void);
 /* measured fp64 FMA roofline of the current device in TFLOP/s (register-resident DFMA loop on all SMs) */

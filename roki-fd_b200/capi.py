@@ -80,7 +80,7 @@ def lib():
         "rkFDBatchGetStateAsync": (ci, [vp, vp, vp, vp]), "rkFDBatchJoin": (ci, [vp]),
         "rkFDBatchGetStatus": (ci, [vp, vp]), "rkFDBatchStats": (ci, [vp, C.POINTER(cd)]), "rkFDBatchEval": (ci, [vp, ci]), "rkFDBatchSync": (ci, [vp]),
         "rkFDBatchDevicePtr": (vp, [vp, ci, ci, _ip, _ip]), "rkFDBatchLaunchCount": (C.c_longlong, [vp]),
-        "rkFDBatchLastError": (C.c_char_p, []), "rkFDBatchDeviceCount": (ci, []), "rkFDB200MeasureFp64": (ci, [_dp]),
+        "rkFDB200DescribeModel": (ci, [vp, C.c_char_p, ci]), "rkFDBatchLastError": (C.c_char_p, []), "rkFDBatchDeviceCount": (ci, []), "rkFDB200MeasureFp64": (ci, [_dp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -390,6 +390,17 @@ class RkFD:
         s = np.zeros(self.env_num, np.int32)
         self._ck(lib().rkFDBatchGetStatus(self.h, _ptr(s)))
         return s
+
+    def describe_model(self):
+        """The flattened device model of the last update_init as {name: [numbers]} (host side, no device needed)."""
+        n = lib().rkFDB200DescribeModel(self.h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().rkFDB200DescribeModel(self.h, buf, n + 1)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, _, v = line.partition(":")
+            out[k] = [float(x) for x in v.split()]
+        return out
 
     def batch_stats(self):
         """[envs, envs in contact, active contact vertices, flagged envs (sums), max|q''|, max|q'| (maxima)] of this process's batch."""

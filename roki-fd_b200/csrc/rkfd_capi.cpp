@@ -486,6 +486,32 @@ extern "C" const char *rkFDBatchLastError(void){ return g_err.c_str(); }
 extern "C" int rkFDBatchDeviceCount(void){ return device_count(); }
 extern "C" int rkFDB200MeasureFp64(double *tflops){ try { *tflops = measure_fp64_tflops(); } catch(const std::exception &ex){ return fail(ex.what()); } return 0; }
 
+/* The flattened device model of the last rkFDUpdateInit as text (one "name: numbers" line per table entry, %.17g): what
+ * the kernels will see of the registered chains.  Host-side only - it works without a device, because the world is
+ * flattened and checked before a device is looked for.  Returns the length needed (excluding the terminator). */
+extern "C" int rkFDB200DescribeModel(rkFD *fd, char *buf, int cap)
+{
+  FDImpl *fi = FI(fd); if( !fi ) return -1;
+  const ModelDev &m = fi->model; std::string s; char t[256];
+  auto num = [&](double v){ std::snprintf(t, sizeof t, " %.17g", v); s += t; };
+  auto arr = [&](const char *name, int idx, const double *v, int n){ std::snprintf(t, sizeof t, "%s[%d]:", name, idx); s += t; for(int i=0;i<n;i++) num(v[i]); s += "\n"; };
+  std::snprintf(t, sizeof t, "dims: %d %d %d %d %d %d %d\nprp: %d %d %d %d %.17g %.17g\n", m.nl, m.nq, m.ncell, m.nbox, m.npair, m.nslot, m.nvert,
+                m.solver, m.pyramid, m.max_iter, m.integrator, m.dt, m.friction_weight); s += t;
+  for(int i=0;i<m.nl;i++){
+    const LinkDev &L = m.link[i];
+    const double topo[7] = { (double)L.parent, (double)L.jtype, (double)L.mtype, (double)L.ndof, (double)L.qofs, (double)L.cell_begin, (double)L.cell_end };
+    arr("link.topo", i, topo, 7); arr("link.Ro", i, L.Ro, 9); arr("link.po", i, L.po, 3);
+    const double mp[10] = { L.mass, L.mc[0], L.mc[1], L.mc[2], L.Io[0], L.Io[1], L.Io[2], L.Io[3], L.Io[4], L.Io[5] }; arr("link.mass", i, mp, 10);
+    const double jf[9] = { L.stiffness, L.viscosity, L.coulomb, L.sfriction, L.m_tin, L.m_reg, L.m_jm, L.m_min, L.m_max }; arr("link.joint", i, jf, 9);
+  }
+  for(int i=0;i<m.ncell;i++){ const CellDev &c = m.cell[i]; const double v[5] = { (double)c.link, (double)c.vofs, (double)c.nvert, (double)c.pair_begin, (double)c.pair_end }; arr("cell", i, v, 5); }
+  for(int i=0;i<m.nbox;i++){ arr("box.R", i, m.box[i].R, 9); arr("box.p", i, m.box[i].p, 3); arr("box.half", i, m.box[i].half, 3); }
+  for(int i=0;i<m.npair;i++){ const PairDev &p = m.pair[i]; const double v[10] = { (double)p.cell, (double)p.box, (double)p.sofs, (double)p.type, p.K, p.L, p.E, p.V, p.SF, p.KF }; arr("pair", i, v, 10); }
+  for(int i=0;i<m.nvert;i++) arr("vert", i, m.vert + 3*i, 3);
+  if( buf && cap > 0 ){ std::snprintf(buf, cap, "%s", s.c_str()); }
+  return (int)s.size();
+}
+
 /* ---- function forms of the reference macros (FFI convenience) ------------------------------------------ */
 extern "C" rkFD *rkFDB200Alloc(void){ return (rkFD*)std::calloc(1, sizeof(rkFD)); }
 extern "C" void rkFDB200Free(rkFD *fd){ std::free(fd); }

