@@ -102,7 +102,7 @@ typedef struct {
   double M[36];   /* rigid-body 6x6 inertia at the link origin (A-4) */
 } ork_link;
 
-typedef struct { int link, nvert, vofs; } ork_cell;
+typedef struct { int link, nvert, vofs, volbox; } ork_cell;   /* volbox: the 8 corners of a parallelepiped in sign-bit order (Volume solver, A-15) */
 typedef struct { double R[9], p[3], half[3]; int stuff; } ork_box;
 typedef struct { int type; double K, L, E, V, SF, KF; } ork_cinfo;
 typedef struct { int sa, sb; ork_cinfo ci; } ork_cinfo_ent;
@@ -209,7 +209,7 @@ int ork_world_add_cell(ork_world *w, int link, int nvert, const double *verts)
 {
   w->cell = (ork_cell*)realloc(w->cell,(w->ncell+1)*sizeof(ork_cell));
   w->vert = (double*)realloc(w->vert,3*(w->nvert+nvert)*sizeof(double));
-  w->cell[w->ncell].link = link; w->cell[w->ncell].nvert = nvert; w->cell[w->ncell].vofs = w->nvert;
+  w->cell[w->ncell].link = link; w->cell[w->ncell].nvert = nvert; w->cell[w->ncell].vofs = w->nvert; w->cell[w->ncell].volbox = 0;
   memcpy(w->vert+3*w->nvert, verts, 3*nvert*sizeof(double));
   w->nvert += nvert;
   return w->ncell++;
@@ -278,7 +278,7 @@ void ork_world_finalize(ork_world *w)
   /* pairs in registration order: (moving cell) x (static box); contact info by stuff pair with
    * fallback to the solver default (rkfd_sim.c:200-207, :266-271) */
   int c,b,k,sofs=0;
-  if( w->solver == ORK_SOLVER_VOLUME ) for(c=0;c<w->ncell;c++) if( w->cell[c].nvert == 8 ) box_sign_bit_order(w->vert+3*w->cell[c].vofs);
+  if( w->solver == ORK_SOLVER_VOLUME ) for(c=0;c<w->ncell;c++) w->cell[c].volbox = w->cell[c].nvert == 8 && box_sign_bit_order(w->vert+3*w->cell[c].vofs);
   free(w->pair); w->npair = w->ncell*w->nbox;
   w->pair = (ork_pair*)calloc(w->npair>0?w->npair:1,sizeof(ork_pair));
   k = 0;
@@ -967,7 +967,7 @@ static int vol_build(ork_env *e, int pi, ork_vpair *vp)
   const ork_world *w = e->w; const ork_pair *p = &w->pair[pi]; const ork_cell *cl = &w->cell[p->cell];
   const ork_box *bx = &w->box[p->box]; const ork_lw *x = &e->lw[cl->link];
   double vw[8][3], cen[3] = {0,0,0}, p0[3], d[8], cut[64][3], vol = 0, bc[3] = {0,0,0}; int ncut = 0, k, s0 = -1, f, i, j;
-  if( cl->nvert != 8 ) return 0;
+  if( !cl->volbox ) return 0;      /* [EXT A-15]: contact volumes of box cells only; other rigid cells are watched, not solved */
   for(k=0;k<8;k++) if( e->c_active[p->sofs+k] ){ s0 = p->sofs+k; break; }
   if( s0 < 0 ) return 0;
   vp->pair = pi; vp->link = cl->link; vp->ci = &p->ci; vp->ntri = 0; vp->npl = 0;

@@ -173,6 +173,64 @@ class World:
         return nv * len(self.boxes)
 
 
+def world_from_flat(desc):
+    """A World equivalent to a flattened device model (`RkFD.describe_model()`: what `rkFDUpdateInit` made of the
+    registered chains - e.g. of the reference's own ZTK files read through `rkFDChainRegFile`).  Every moving link goes
+    into one forest chain, every static box into its own all-fixed chain; the contact parameters of each (cell, box) pair
+    come back through per-link / per-box `stuff` names.  Flattening the result again reproduces the description (the DC
+    motor constants are folded in the description: an equivalent motor with gear ratio 1 is returned)."""
+    jt = {0: "fixed", 1: "revolute", 2: "prismatic", 3: "spherical", 4: "float"}
+    nl, nq, ncell, nbox, npair, nslot, nvert = (int(v) for v in desc["dims"])
+    solver, pyramid, max_iter, integ = (int(v) for v in desc["prp"][:4])
+    dt, fw = desc["prp"][4], desc["prp"][5]
+    verts = np.array([desc["vert[%d]" % i] for i in range(nvert)], float).reshape(nvert, 3)
+    cells = [[int(v) for v in desc["cell[%d]" % i]] for i in range(ncell)]
+    links = []
+    for i in range(nl):
+        topo = [int(v) for v in desc["link.topo[%d]" % i]]
+        mp, jf = desc["link.mass[%d]" % i], desc["link.joint[%d]" % i]
+        m, com = mp[0], np.array(mp[10:13])
+        Io = np.array([[mp[4], mp[5], mp[6]], [mp[5], mp[7], mp[8]], [mp[6], mp[8], mp[9]]])
+        Ic = Io - m * (com @ com * np.eye(3) - np.outer(com, com))
+        l = Link(name="link#%02d" % i, parent=topo[0], jtype=jt[topo[1]], org_R=np.array(desc["link.Ro[%d]" % i]).reshape(3, 3),
+                 org_p=np.array(desc["link.po[%d]" % i]), mass=m, com=com, inertia=Ic, stuff="L%d" % i,
+                 stiffness=jf[0], viscosity=jf[1], coulomb=jf[2], sfriction=jf[3])
+        if topo[2] == 1:        # DC motor: m_tin = g k a, m_reg = (g k)^2 a, m_jm = g^2 (Jr + Jg)  ->  g = 1
+            k = jf[5] / jf[4] if jf[4] != 0.0 else 0.0
+            a = jf[4] * jf[4] / jf[5] if jf[5] != 0.0 else 0.0
+            l.motor = Motor(type="dc", k=k, admittance=a, gear=1.0, rotor_inertia=jf[6], gear_inertia=0.0, min=jf[7], max=jf[8])
+        elif topo[2] == 2:
+            l.motor = Motor(type="trq", min=jf[7], max=jf[8])
+        l.shapes = [verts[c[1]:c[1] + c[2]].copy() for c in cells[topo[5]:topo[6]]]
+        links.append(l)
+    chains = [ChainModel("flat", links)] if links else []
+    for b in range(nbox):
+        h = desc["box.half[%d]" % b]
+        chains.append(ChainModel("box%d" % b, [Link(name="box", jtype="fixed", stuff="B%d" % b, org_R=np.array(desc["box.R[%d]" % b]).reshape(3, 3),
+                                                     org_p=np.array(desc["box.p[%d]" % b]), boxes=[((0.0, 0.0, 0.0), 2 * h[0], 2 * h[1], 2 * h[2])])]))
+    ci, seen = [], set()
+    for p in range(npair):
+        v = desc["pair[%d]" % p]
+        key = ("L%d" % cells[int(v[0])][0], "B%d" % int(v[1]))
+        if key in seen:
+            continue
+        seen.add(key)
+        ci.append(ContactInfo(key[0], key[1], "rigid" if int(v[3]) == 0 else "elastic", K=v[4], L=v[5], E=v[6], V=v[7], SF=v[8], KF=v[9]))
+    return World(chains=chains, contact_info=ci, dt=dt, pyramid=pyramid, friction_weight=fw, max_iter=max_iter,
+                 solver={0: "Vert", 1: "MLCP", 2: "Volume"}[solver], integrator={0: "RKG", 1: "RK4", 2: "Euler", 3: "Heun"}[integ])
+
+
+def load_flat(path):
+    """A description saved as text (one `name: numbers` line per table entry) -> dict."""
+    out = {}
+    with open(path) as f:
+        for line in f:
+            k, _, v = line.partition(":")
+            if v.strip():
+                out[k] = [float(x) for x in v.split()]
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # models of the reference's example/model directory (values transcribed from the ZTK files)
 

@@ -501,13 +501,14 @@ extern "C" int rkFDB200DescribeModel(rkFD *fd, char *buf, int cap)
     const LinkDev &L = m.link[i];
     const double topo[7] = { (double)L.parent, (double)L.jtype, (double)L.mtype, (double)L.ndof, (double)L.qofs, (double)L.cell_begin, (double)L.cell_end };
     arr("link.topo", i, topo, 7); arr("link.Ro", i, L.Ro, 9); arr("link.po", i, L.po, 3);
-    const double mp[10] = { L.mass, L.mc[0], L.mc[1], L.mc[2], L.Io[0], L.Io[1], L.Io[2], L.Io[3], L.Io[4], L.Io[5] }; arr("link.mass", i, mp, 10);
+    const double mp[13] = { L.mass, L.mc[0], L.mc[1], L.mc[2], L.Io[0], L.Io[1], L.Io[2], L.Io[3], L.Io[4], L.Io[5], L.com[0], L.com[1], L.com[2] }; arr("link.mass", i, mp, 13);
     const double jf[9] = { L.stiffness, L.viscosity, L.coulomb, L.sfriction, L.m_tin, L.m_reg, L.m_jm, L.m_min, L.m_max }; arr("link.joint", i, jf, 9);
   }
   for(int i=0;i<m.ncell;i++){ const CellDev &c = m.cell[i]; const double v[5] = { (double)c.link, (double)c.vofs, (double)c.nvert, (double)c.pair_begin, (double)c.pair_end }; arr("cell", i, v, 5); }
   for(int i=0;i<m.nbox;i++){ arr("box.R", i, m.box[i].R, 9); arr("box.p", i, m.box[i].p, 3); arr("box.half", i, m.box[i].half, 3); }
   for(int i=0;i<m.npair;i++){ const PairDev &p = m.pair[i]; const double v[10] = { (double)p.cell, (double)p.box, (double)p.sofs, (double)p.type, p.K, p.L, p.E, p.V, p.SF, p.KF }; arr("pair", i, v, 10); }
   for(int i=0;i<m.nvert;i++) arr("vert", i, m.vert + 3*i, 3);
+  if( fd->dis && fd->size > 0 ) arr("init.q", 0, fd->dis->buf, fd->size);      /* the registered initial displacements ([roki::chain::init]) */
   if( buf && cap > 0 ){ std::snprintf(buf, cap, "%s", s.c_str()); }
   return (int)s.size();
 }

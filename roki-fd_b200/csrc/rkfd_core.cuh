@@ -238,6 +238,7 @@ struct SpecSerialRevRolled {
   static RKFD_HD int sc(int i, const LinkDev &){ return RG_ ? PER*i + 9 : 4*(i-1); }
 };
 inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0, int GEN = 0){
+  if( m.nfw > 1 ) return false;
   if( RG ? !( m.has_rigid && m.nrg == 1 && m.rigid_link == NL-1 ) : m.has_rigid ) return false;
   if( m.nl != NL || NL < 2 ) return false;
   for(int i=0;i<NL;i++){
@@ -252,7 +253,7 @@ inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0, 
 
 /* does the flattened model have the shape SpecSerialRev<.,NL,CLS> assumes? (host side) */
 inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
-  if( m.has_rigid || m.nl != NL || NL < 2 ) return false;
+  if( m.has_rigid || m.nl != NL || NL < 2 || m.nfw > 1 ) return false;
   for(int i=0;i<NL;i++){
     const LinkDev &L = m.link[i];
     if( i == 0 ){ if( L.parent >= 0 || L.jtype != J_FIXED || L.cell_end > L.cell_begin ) return false; continue; }
@@ -335,11 +336,18 @@ template <class Ctx, class Spec = SpecGeneric>
 struct Core {
   Ctx &c;
   unsigned int piv;             /* joint friction pivot: bit j = dof j kinetic */
-  unsigned long long cfl;       /* contact flags: bit 2s active, bit 2s+1 kinetic */
+  unsigned long long cfl;       /* contact flags, the word `cw` of them: bit 2f active, bit 2f+1 kinetic */
+  int cw;
   int bad;
   int rk0;                      /* first slot of the integrator stage state (QS, QDS, PQ, PQD) */
 
-  RKFD_HD explicit Core(Ctx &ctx) : c(ctx), piv(0), cfl(0), bad(0), rk0(0) {}
+  RKFD_HD explicit Core(Ctx &ctx) : c(ctx), piv(0), cfl(0), cw(0), bad(0), rk0(0) {}
+
+  /* the flag word the following code works on (warp-uniform: decided by the model) */
+  RKFD_HD void flag_select(int w){
+    if( Spec::NL != 0 ) return;      /* the arm specialisations only match single-word worlds (spec_*_match) */
+    if( w != cw ){ c.st.cflags[(size_t)cw*c.st.ld + c.e] = cfl; cfl = c.st.cflags[(size_t)w*c.st.ld + c.e]; cw = w; }
+  }
 
   /* link properties: the compile-time tag when it knows, the Spec accessor (table / unrolled index) otherwise */
   template <class Kt> static RKFD_HD int JT(int i, const LinkDev &L){ return Kt::jt >= 0 ? Kt::jt : Spec::jtype(i,L); }
@@ -461,23 +469,31 @@ struct Core {
         const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
         /* (A) detection: vertex in the box frame = Rb^T (pw - pb) + (Rb^T Rw) vloc, the two factors once per pair */
         const M3 Mb = tmm(Rb, Rw); const V3 ob = tmul(Rb, pw - pb);
-        unsigned long long in = 0;
-        for(int k=0;k<cl.nvert;k++){
-          const int s = pr.sofs + k;
-          const V3 vloc = v3(m.vert[3*(cl.vofs+k)], m.vert[3*(cl.vofs+k)+1], m.vert[3*(cl.vofs+k)+2]);
+        /* chunks of 32 vertices: one flag word each */
+        /* (the arm specialisations only match single-word worlds: one chunk, flag position = slot) */
+        const int c0end = Spec::NL != 0 ? 1 : cl.nvert;
+        for(int c0_=0; c0_<c0end; c0_+=32){
+        const int c0 = Spec::NL != 0 ? 0 : c0_;
+        const int nvc = Spec::NL != 0 ? cl.nvert : ( cl.nvert - c0 < 32 ? cl.nvert - c0 : 32 );
+        const int sh = Spec::NL != 0 ? pr.sofs : ( (pr.fofs + c0) & 31 );
+        flag_select((pr.fofs + c0) >> 5);
+        unsigned in = 0;
+        for(int k=0;k<nvc;k++){
+          const int s = pr.sofs + c0 + k, vi = cl.vofs + c0 + k;
+          const V3 vloc = v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2]);
           const V3 vb = ob + mul(Mb, vloc);
           const double dx = bx.half[0]-fabs(vb.x), dy = bx.half[1]-fabs(vb.y), dz = bx.half[2]-fabs(vb.z);
           const bool inside = (dx > -ZTOL) && (dy > -ZTOL) && (dz > -ZTOL);
-          if( inside ) in |= 1ull << k;
-          else { cfl &= ~(3ull << (2*s)); if( ref ){ c.gst(c.st.cf, 3*s, 0.0); c.gst(c.st.cf, 3*s+1, 0.0); c.gst(c.st.cf, 3*s+2, 0.0); } }
+          if( inside ) in |= 1u << k;
+          else { cfl &= ~(3ull << (2*(sh+k))); if( ref ){ c.gst(c.st.cf, 3*s, 0.0); c.gst(c.st.cf, 3*s+1, 0.0); c.gst(c.st.cf, 3*s+2, 0.0); } }
         }
         /* (B) the lane's own contacts */
         while( c.any(in != 0) ){
           if( in == 0 ) continue;
-          const int k = RKFD_FFS64(in) - 1; in &= in - 1;
-          const int s = pr.sofs + k;
-          const unsigned long long abit = 1ull << (2*s), kbit = 2ull << (2*s);
-          const V3 vloc = v3(m.vert[3*(cl.vofs+k)], m.vert[3*(cl.vofs+k)+1], m.vert[3*(cl.vofs+k)+2]);
+          const int k = RKFD_FFS32(in) - 1; in &= in - 1;
+          const int s = pr.sofs + c0 + k, vi = cl.vofs + c0 + k;
+          const unsigned long long abit = 1ull << (2*(sh+k)), kbit = 2ull << (2*(sh+k));
+          const V3 vloc = v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2]);
           const V3 vw = pw + mul(Rw, vloc);
           const V3 vb = tmul(Rb, vw - pb);
           const double dx = bx.half[0]-fabs(vb.x), dy = bx.half[1]-fabs(vb.y), dz = bx.half[2]-fabs(vb.z);
@@ -513,6 +529,7 @@ struct Core {
           const V3 fl = tmul(Rw, f);
           w.l = w.l + fl; w.a = w.a + cross(pos, fl);
           if( ref ){ c.gst(c.st.cf,3*s,f.x); c.gst(c.st.cf,3*s+1,f.y); c.gst(c.st.cf,3*s+2,f.z); }
+        }
         }
       }
     }
@@ -1352,7 +1369,7 @@ struct Core {
       for(int r=0;r<6;r++){ double sum = 0; for(int j=0;j<6;j++) sum += lam[6*r+j]*hc[j]; w[g][r] = sum; }
     }
     /* initial active set (rkfd_opt_qp.c:27-40) */
-    unsigned am[MAX_SLOTS];
+    unsigned am[RIGID_MAX_SLOTS];
     for(int k=0;k<N;k++){
       const int o = W1_CT + W1_CTN*k; const double fric = c.W1(o+39); unsigned a = 0;
       for(int i=0;i<pyr;i++){ const double cond = fric*c.W1(o) + m.sc_sin[i]*c.W1(o+1) + m.sc_cos[i]*c.W1(o+2); if( fabs(cond) < ZTOL ) a |= 1u << i; }
@@ -1462,7 +1479,7 @@ struct Core {
       /* anti-cycling: same active set with the same objective value -> stop (rkfd_opt_qp.c:152-171) */
       double objv = 0.5*lx2;
       for(int g=0;g<ng;g++) for(int r=0;r<6;r++){ double sum = 0; for(int j=0;j<6;j++) sum += c.W1(36*g + 6*r+j)*vv[g][j]; objv += 0.5*vv[g][r]*sum + w[g][r]*vv[g][r]; }
-      double pk[(MAX_SLOTS + 2)/3];
+      double pk[(RIGID_MAX_SLOTS + 2)/3];
       for(int k3=0;k3<hw;k3++){ double v = 0.0;
         for(int j=2;j>=0;j--){ const int k = 3*k3 + j; v = v*65536.0 + ( k < N ? (double)am[k] : 0.0 ); }
         pk[k3] = v; }
@@ -1867,8 +1884,8 @@ struct Core {
     return nfl;
   }
 
-  RKFD_HD void load_flags(){ piv = c.st.piv_type[c.e]; cfl = c.st.cflags[c.e]; }
-  RKFD_HD void store_flags(){ c.st.piv_type[c.e] = piv; c.st.cflags[c.e] = cfl; if( bad ) c.st.status[c.e] |= 1; }
+  RKFD_HD void load_flags(){ piv = c.st.piv_type[c.e]; cw = 0; cfl = c.st.cflags[c.e]; }
+  RKFD_HD void store_flags(){ c.st.piv_type[c.e] = piv; c.st.cflags[(size_t)(Spec::NL != 0 ? 0 : cw)*c.st.ld + c.e] = cfl; if( bad ) c.st.status[c.e] |= bad; }
   /* committed state (buffer `cur`) -> stage state */
   RKFD_HD void load_stage_state(const ModelDev &m){
     const int NQc = Spec::nq(m);

@@ -75,12 +75,13 @@ __global__ void rkfd_fill_rows_kernel(double * __restrict__ dst, int ld, int B, 
 /* end-of-run statistics of one shard, reduced on the device (rkFDBatchStats): out[0] environments, [1] environments with an
  * active contact, [2] active contact vertices, [3] environments with a non-zero status word (sums); [4] max |q''|,
  * [5] max |q'| (non-negative doubles order like their bit patterns: atomicMax on the 64-bit integer view) */
-__global__ void __launch_bounds__(256) rkfd_stats_kernel(StateDev st, int cur, int nq, unsigned long long active_mask, double *out)
+__global__ void __launch_bounds__(256) rkfd_stats_kernel(StateDev st, int cur, int nq, int nfw, double *out)
 {
   const int e = blockIdx.x*blockDim.x + threadIdx.x;
   double cnt[4] = {0,0,0,0}, mx[2] = {0,0};
   if( e < st.B ){
-    const int na = __popcll(st.cflags[e] & active_mask);
+    int na = 0;
+    for(int w=0;w<nfw;w++) na += __popcll(st.cflags[(size_t)w*st.ld + e] & 0x5555555555555555ull);     /* the active bits */
     cnt[0] = 1.0; cnt[1] = na > 0 ? 1.0 : 0.0; cnt[2] = (double)na; cnt[3] = st.status[e] != 0 ? 1.0 : 0.0;
     for(int k=0;k<nq;k++){
       const double a = fabs(st.qdd[(size_t)k*st.ld + e]), v = fabs(st.qd[cur][(size_t)k*st.ld + e]);
@@ -207,7 +208,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     st.u = dalloc<double>(*s, (size_t)nl*s->ld);
     st.piv_prev = dalloc<double>(*s, (size_t)nq*s->ld);
     st.piv_type = dalloc<unsigned int>(*s, s->ld);
-    st.cflags = dalloc<unsigned long long>(*s, s->ld);
+    st.cflags = dalloc<unsigned long long>(*s, (size_t)(model.nfw > 0 ? model.nfw : 1)*s->ld);
     st.cref = dalloc<double>(*s, (size_t)3*ns*s->ld);
     st.cf = dalloc<double>(*s, (size_t)3*ns*s->ld);
     st.status = dalloc<int>(*s, s->ld);
@@ -495,12 +496,11 @@ void Engine::stats(double out[8])
 {
   int prev = 0; CK(cudaGetDevice(&prev));
   for(int i=0;i<8;i++) out[i] = 0.0;
-  unsigned long long amask = 0; for(int k=0;k<model_.nslot && k<32;k++) amask |= 1ull << (2*k);
   for(Shard *s : shards_){
     CK(cudaSetDevice(s->dev));
     double h[8];
     CK(cudaMemsetAsync(s->dstage, 0, 8*sizeof(double), s->stream));
-    rkfd_stats_kernel<<<(s->B+255)/256, 256, 0, s->stream>>>(s->st, s->cur, model_.nq, amask, s->dstage);
+    rkfd_stats_kernel<<<(s->B+255)/256, 256, 0, s->stream>>>(s->st, s->cur, model_.nq, model_.nfw, s->dstage);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h, s->dstage, sizeof h, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -552,12 +552,15 @@ void Engine::get_contact(int *active, int *type, double *ref, double *f)
     if( f )   d2h_gather(*s, s->st.cf,   3*ns, f);
     CK(cudaStreamSynchronize(s->stream));
     if( active || type ){
-      std::vector<unsigned long long> bits(s->B);
-      CK(cudaMemcpy(bits.data(), s->st.cflags, s->B*sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-      for(int e=0;e<s->B;e++) for(int k=0;k<ns;k++){
-        if( active ) active[(size_t)(s->e0+e)*ns + k] = (int)((bits[e] >> (2*k)) & 1ull);
-        if( type )   type[(size_t)(s->e0+e)*ns + k]   = (int)((bits[e] >> (2*k+1)) & 1ull);
-      }
+      const int nfw = model_.nfw > 0 ? model_.nfw : 1;
+      std::vector<unsigned long long> bits((size_t)nfw*s->ld);
+      CK(cudaMemcpy(bits.data(), s->st.cflags, bits.size()*sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      /* slot (pair, vertex) -> flag position pair.fofs + vertex */
+      for(int p=0;p<model_.npair;p++){ const PairDev &pr = model_.pair[p]; const int nv = model_.cell[pr.cell].nvert;
+        for(int k=0;k<nv;k++){ const int f = pr.fofs + k, sl = pr.sofs + k;
+          for(int e=0;e<s->B;e++){ const unsigned long long wd = bits[(size_t)(f>>5)*s->ld + e];
+            if( active ) active[(size_t)(s->e0+e)*ns + sl] = (int)((wd >> (2*(f&31))) & 1ull);
+            if( type )   type[(size_t)(s->e0+e)*ns + sl]   = (int)((wd >> (2*(f&31)+1)) & 1ull); } } }
     }
   }
   CK(cudaSetDevice(prev));
@@ -571,12 +574,14 @@ void Engine::set_contact(const int *active, const int *type, const double *ref)
     if( ref ) h2d_scatter(*s, ref, 3*ns, s->st.cref);
     CK(cudaStreamSynchronize(s->stream));
     if( active && type ){
-      std::vector<unsigned long long> bits(s->B, 0ull);
-      for(int e=0;e<s->B;e++) for(int k=0;k<ns;k++){
-        if( active[(size_t)(s->e0+e)*ns + k] ) bits[e] |= 1ull << (2*k);
-        if( type[(size_t)(s->e0+e)*ns + k] )   bits[e] |= 2ull << (2*k);
-      }
-      CK(cudaMemcpy(s->st.cflags, bits.data(), s->B*sizeof(unsigned long long), cudaMemcpyHostToDevice));
+      const int nfw = model_.nfw > 0 ? model_.nfw : 1;
+      std::vector<unsigned long long> bits((size_t)nfw*s->ld, 0ull);
+      for(int p=0;p<model_.npair;p++){ const PairDev &pr = model_.pair[p]; const int nv = model_.cell[pr.cell].nvert;
+        for(int k=0;k<nv;k++){ const int f = pr.fofs + k, sl = pr.sofs + k;
+          for(int e=0;e<s->B;e++){ unsigned long long &wd = bits[(size_t)(f>>5)*s->ld + e];
+            if( active[(size_t)(s->e0+e)*ns + sl] ) wd |= 1ull << (2*(f&31));
+            if( type[(size_t)(s->e0+e)*ns + sl] )   wd |= 2ull << (2*(f&31)); } } }
+      CK(cudaMemcpy(s->st.cflags, bits.data(), bits.size()*sizeof(unsigned long long), cudaMemcpyHostToDevice));
     }
   }
   CK(cudaSetDevice(prev));

@@ -179,6 +179,11 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   }
   m.nslot = sofs;
   if( m.nslot > MAX_SLOTS ){ err = "too many contact slots (MAX_SLOTS)"; return false; }
+  /* flag positions: one word when everything fits 32 slots (position = slot), else whole words per pair */
+  if( m.nslot <= 32 ){ for(int p=0;p<m.npair;p++) m.pair[p].fofs = m.pair[p].sofs; m.nfw = 1; }
+  else { int fo = 0; for(int p=0;p<m.npair;p++){ m.pair[p].fofs = fo; fo += (m.cell[m.pair[p].cell].nvert + 31) & ~31; } m.nfw = fo/32; }
+  if( m.nfw > MAX_FWORDS ){ err = "too many contact flag words (MAX_FWORDS)"; return false; }
+  if( m.nfw < 1 ) m.nfw = 1;
   m.need_world = m.npair > 0;
 
   /* ---- topology flags and the scratch slot map */
@@ -188,9 +193,12 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   model_layout(m, false);
   /* ---- rigid-contact tables: slot -> (pair, vertex), workspace layout per warp */
   m.rigid_mask = 0; int nrs = 0;
+  if( m.has_rigid && m.solver != S_VOLUME && m.nslot > RIGID_MAX_SLOTS ){
+    err = "the rigid vertex solvers (MLCP, Vert) handle at most 32 contact slots per environment (cell vertices x static boxes)"; return false; }
   for(int p=0;p<m.npair;p++) for(int k=0;k<m.cell[m.pair[p].cell].nvert;k++){
-    const int sidx = m.pair[p].sofs + k; m.slot_pair[sidx] = p; m.slot_vert[sidx] = k;
-    if( m.pair[p].type == C_RIGID ){ m.rigid_mask |= 1ull << (2*sidx); nrs++; }
+    const int sidx = m.pair[p].sofs + k;
+    if( sidx < RIGID_MAX_SLOTS ){ m.slot_pair[sidx] = p; m.slot_vert[sidx] = k; }
+    if( m.pair[p].type == C_RIGID ){ if( sidx < 32 ) m.rigid_mask |= 1ull << (2*sidx); nrs++; }
   }
   m.nmax = 3*nrs; m.ws_doubles = 0;
   /* single-link MLCP path (Core::rigid_mlcp_single): every rigid slot on one link */
@@ -217,11 +225,15 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
     if( m.rigid_link < 0 ) m.nrg = 0;
   }
   if( m.has_rigid && m.solver == S_VOLUME ){
-    /* the Volume solver (rkfd_volume.cuh) works on thread-local data: no workspace; cells must be parallelepipeds */
+    /* the Volume solver (rkfd_volume.cuh) works on thread-local data: no workspace.  Contact volumes are formed for cells
+     * with the 8 corners of a box (parallelepiped; the soles of mighty.ztk); other rigid cells are watched only - an
+     * environment in which one of them touches is flagged (status bit 8).  At least one box cell must exist. */
+    int nvb = 0;
     for(int p=0;p<m.npair;p++) if( m.pair[p].type == C_RIGID ){
       const CellDev &c = m.cell[m.pair[p].cell];
-      if( c.nvert != 8 || !box_sign_bit_order(m.vert + 3*c.vofs) ){ err = "Volume solver: rigid cells must have the 8 corners of a box (parallelepiped)"; return false; }
+      m.pair[p].volbox = ( c.nvert == 8 && box_sign_bit_order(m.vert + 3*c.vofs) ) ? 1 : 0; nvb += m.pair[p].volbox;
     }
+    if( nvb == 0 ){ err = "Volume solver: no rigid cell has the 8 corners of a box (parallelepiped) - contact volumes are formed for box cells only"; return false; }
     m.ws_doubles = 0; m.ws_geo = m.ws_b = m.ws_f = m.ws_A = m.ws_du = m.ws_da = m.ws_qp = 0;
     return true;
   }

@@ -14,12 +14,19 @@
 
 namespace rkfd {
 
+/* sized for the reference's largest model (example/model/mighty.ztk: 25 links, 26 DoF, 19 shapes, 701 collision vertices)
+ * on a floor; the whole table is ~45 KB of the 64 KB constant bank */
 constexpr int MAX_LINKS = 32;
-constexpr int MAX_CELLS = 8;
-constexpr int MAX_VERTS = 64;
-constexpr int MAX_BOXES = 4;
-constexpr int MAX_PAIRS = 16;
-constexpr int MAX_SLOTS = 32;      /* contact slots per env handled by the fused kernel (2 flag bits each) */
+constexpr int MAX_CELLS = 32;
+constexpr int MAX_VERTS = 768;
+constexpr int MAX_BOXES = 8;
+constexpr int MAX_PAIRS = 64;
+constexpr int MAX_SLOTS = 1024;    /* contact slots per env = sum over (cell, box) pairs of the cell's vertices */
+/* Contact flags: 2 bits per slot (active, kinetic) in 64-bit words of 32 slots.  Worlds with at most 32 slots keep them in
+ * ONE word (flag position = slot); larger worlds give every pair its own word(s) (PairDev::fofs is a multiple of 32), and
+ * the kernel holds one word at a time in a register (Core::flag_select). */
+constexpr int MAX_FWORDS = 64;
+constexpr int RIGID_MAX_SLOTS = 32; /* the rigid VERTEX solvers (MLCP, Vert) address every rigid slot through one flag word */
 constexpr int MAX_PYRAMID = 16;
 
 enum JointType : int { J_FIXED = 0, J_REVOL = 1, J_PRISM = 2, J_SPHER = 3, J_FLOAT = 4 };
@@ -63,10 +70,11 @@ struct LinkDev {
 
 struct CellDev { int link, vofs, nvert, pair_begin, pair_end; };
 struct BoxDev { double R[9], p[3], half[3]; };
-struct PairDev { int cell, box, sofs, type; double K, L, E, V, SF, KF; };
+struct PairDev { int cell, box, sofs, type; double K, L, E, V, SF, KF; int fofs, volbox; };   /* fofs: flag position of vertex 0 (word fofs>>5, bit pair fofs&31); volbox: the cell has the 8 corners of a box in sign-bit order (Volume solver) */
 
 struct ModelDev {
   int nl, nq, ncell, nbox, npair, nslot, nvert;
+  int nfw;             /* contact flag words per environment */
   int need_world;      /* any collision cell: world frames must be propagated */
   int has_rigid, has_elastic;
   int solver, pyramid, max_iter;
@@ -83,7 +91,7 @@ struct ModelDev {
                           coupling between groups: the reference zeroes those blocks of A, rkfd_vert.c:133-137) */
   int ws1_doubles;     /* per-ENVIRONMENT workspace (doubles) of the single-link MLCP path, 0 when unused */
   unsigned long long rigid_mask;   /* bit 2s set when slot s belongs to a rigid pair */
-  int slot_pair[MAX_SLOTS], slot_vert[MAX_SLOTS];
+  int slot_pair[RIGID_MAX_SLOTS], slot_vert[RIGID_MAX_SLOTS];   /* single-word worlds (the rigid vertex solvers) */
   int rk_slot;         /* first slot of the RKG stage state: QS[nq], QDS[nq], PQ[nq], PQD[nq] */
   double dt, friction_weight;
   double inv_dt;       /* 1/dt */
@@ -106,7 +114,7 @@ struct StateDev {
   double *u;              /* [nl][ld] motor input per link */
   double *piv_prev;       /* [nq][ld] previous driving torque per dof */
   unsigned int *piv_type; /* [ld] bit j: dof j pivot is kinetic   (nq <= 32) */
-  unsigned long long *cflags; /* [ld] 2 bits per slot: bit 2s active, bit 2s+1 kinetic */
+  unsigned long long *cflags; /* [nfw][ld] 2 bits per flag position: bit 2f active, bit 2f+1 kinetic */
   double *cref;           /* [nslot*3][ld] anchor _ref in the box frame */
   double *cf;             /* [nslot*3][ld] contact force (world) of the last reference evaluation */
   double *scratch;        /* optional global scratch [nscratch][ld] when shared memory is too small */

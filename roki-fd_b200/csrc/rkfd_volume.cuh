@@ -42,7 +42,7 @@
 #endif
   static constexpr int VOL_P = 2, VOL_PL = 8, VOL_N = 6*VOL_P, VOL_M = VOL_P*(1+VOL_PL), VOL_MA = VOL_M, VOL_LPN = VOL_PL, VOL_LPS = VOL_LPN + 4;
   struct VolPair {
-    int pair, link, fsl, wsl, npl, sofs;
+    int pair, link, fsl, wsl, npl, sofs, fofs;
     V3 center, norm, a1, a2;
     double K, L, SF, KF;
     V3 plv[VOL_PL], pln[VOL_PL]; double r[VOL_PL][2], s[VOL_PL][2];
@@ -567,18 +567,26 @@ RKFD_VOL_U
     /* Every thread of the block walks through the phases below (lanes and warps without a contact volume with P = 0, i.e.
      * empty loops), with a block barrier between phases: the warps of an SM then execute the same few KB of code at any
      * time instead of eight different parts of the 350 KB solver (instruction-fetch stalls dominated the profile). */
-    const unsigned long long fl = cfl;
     VolPair vp[VOL_P]; int P = 0;
     /* ---- contact volumes (rkFDSolverColChk_Volume, [EXT A-15]) */
     for(int pi=0;pi<m.npair;pi++){
       const PairDev &pr = m.pair[pi]; if( pr.type != C_RIGID ) continue;
-      const CellDev &cl = m.cell[pr.cell]; if( cl.nvert != 8 ) continue;
-      int k0 = -1; for(int k=0;k<8;k++) if( fl >> (2*(pr.sofs+k)) & 1ull ){ k0 = k; break; }
+      const CellDev &cl = m.cell[pr.cell];
+      if( !pr.volbox ){
+        /* a rigid cell that is not a box (the non-sole shapes of a humanoid): its vertices are watched, a contact volume is
+         * not formed - [EXT A-15] covers box cells; the environment is flagged when such a cell touches */
+        for(int c0=0; c0<cl.nvert; c0+=32){ flag_select((pr.fofs + c0) >> 5);
+          const int sh = (pr.fofs + c0) & 31, nvc = cl.nvert - c0 < 32 ? cl.nvert - c0 : 32;
+          for(int k=0;k<nvc;k++) if( cfl >> (2*(sh+k)) & 1ull ) bad |= 8; }
+        continue;
+      }
+      flag_select(pr.fofs >> 5);
+      int k0 = -1; for(int k=0;k<8;k++) if( cfl >> (2*((pr.fofs & 31)+k)) & 1ull ){ k0 = k; break; }
       if( k0 < 0 ) continue;
       if( P >= VOL_P ){ bad |= 4; break; }
       VolPair &v = vp[P];
       const LinkDev &L = m.link[cl.link]; const BoxDev &bx = m.box[pr.box];
-      v.pair = pi; v.link = cl.link; v.fsl = Spec::frame_slot(cl.link, L); v.wsl = Spec::wext_slot(cl.link, L); v.npl = 0; v.sofs = pr.sofs;
+      v.pair = pi; v.link = cl.link; v.fsl = Spec::frame_slot(cl.link, L); v.wsl = Spec::wext_slot(cl.link, L); v.npl = 0; v.sofs = pr.sofs; v.fofs = pr.fofs;
       v.K = pr.K; v.L = pr.L; v.SF = pr.SF; v.KF = pr.KF;
       const M3 Rw = ldm(v.fsl); const V3 pw = ld3(v.fsl+9);
       const M3 Rb = box_R(bx); const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
@@ -691,7 +699,6 @@ RKFD_VOL_U
         const V3 f = v3(v.w[0],v.w[1],v.w[2]);
         if( ( vtiny(f.x) && vtiny(f.y) && vtiny(f.z) ) || dot(f, v.norm) < ZTOL ) for(int i=0;i<6;i++) v.w[i] = 0.0;
         off += 6; } }
-    unsigned long long nfl = fl;
     for(int k=0;k<P;k++){
       VolPair &v = vp[k]; const int np = v.npl;
       V3 wf = v3(v.w[0],v.w[1],v.w[2]), wt = v3(v.w[3],v.w[4],v.w[5]);
@@ -766,7 +773,7 @@ RKFD_VOL_U
             wv[1] += fx; wv[2] += fy; wv[3] += v.r[j][0]*fy - v.r[j][1]*fx; }
           setforce = true;
         }
-        if( ref ){ if( kinetic ) nfl |= 2ull << (2*v.sofs); else nfl &= ~(2ull << (2*v.sofs)); }
+        if( ref ){ flag_select(v.fofs >> 5); if( kinetic ) cfl |= 2ull << (2*(v.fofs & 31)); else cfl &= ~(2ull << (2*(v.fofs & 31))); }
         if( setforce ){ wf = wv[0]*v.norm + wv[1]*v.a1 + wv[2]*v.a2; wt = wv[3]*v.norm + wv[4]*v.a1 + wv[5]*v.a2; }
       }
       /* ---- _rkFDSolverPushWrench (:919-936) */
@@ -781,6 +788,5 @@ RKFD_VOL_U
           c.gst(c.st.cf,3*s+6,v.center.x); c.gst(c.st.cf,3*s+7,v.center.y); c.gst(c.st.cf,3*s+8,v.center.z);
         } }
     }
-    cfl = nfl;
     c.phase_sync(1);
   }

@@ -97,7 +97,7 @@ int hostsim_finalize(HostSim *h, int B)
   StateDev &st = h->st; std::memset(&st, 0, sizeof st); st.B = B; st.ld = B;
   for(int k=0;k<2;k++){ st.q[k] = halloc<double>(h, (size_t)nq*B); st.qd[k] = halloc<double>(h, (size_t)nq*B); }
   st.qdd = halloc<double>(h, (size_t)nq*B); st.u = halloc<double>(h, (size_t)nl*B); st.piv_prev = halloc<double>(h, (size_t)nq*B);
-  st.piv_type = halloc<unsigned int>(h, B); st.cflags = halloc<unsigned long long>(h, B);
+  st.piv_type = halloc<unsigned int>(h, B); st.cflags = halloc<unsigned long long>(h, (size_t)(m.nfw > 0 ? m.nfw : 1)*B);
   st.ws1 = halloc<double>(h, (size_t)(m.ws1_doubles > 0 ? m.ws1_doubles : 1)*B);
   st.cref = halloc<double>(h, (size_t)3*ns*B); st.cf = halloc<double>(h, (size_t)3*ns*B); st.status = halloc<int>(h, B);
   return 0;
@@ -131,10 +131,12 @@ void hostsim_get_state(HostSim *h, double *q, double *qd, double *qdd)
 }
 void hostsim_get_contact(HostSim *h, int *active, int *type, double *ref, double *f)
 {
-  const int ns = h->model.nslot, B = h->B;
-  for(int e=0;e<B;e++) for(int k=0;k<ns;k++){
-    active[(size_t)e*ns+k] = (int)((h->st.cflags[e] >> (2*k)) & 1ull); type[(size_t)e*ns+k] = (int)((h->st.cflags[e] >> (2*k+1)) & 1ull);
-    for(int a=0;a<3;a++){ ref[((size_t)e*ns+k)*3+a] = h->st.cref[(size_t)(3*k+a)*B+e]; f[((size_t)e*ns+k)*3+a] = h->st.cf[(size_t)(3*k+a)*B+e]; } }
+  const ModelDev &m = h->model; const int ns = m.nslot, B = h->B;
+  for(int p=0;p<m.npair;p++){ const PairDev &pr = m.pair[p]; const int nv = m.cell[pr.cell].nvert;
+    for(int kk=0;kk<nv;kk++){ const int fpos = pr.fofs + kk, k = pr.sofs + kk;
+      for(int e=0;e<B;e++){ const unsigned long long wd = h->st.cflags[(size_t)(fpos>>5)*B + e];
+        active[(size_t)e*ns+k] = (int)((wd >> (2*(fpos&31))) & 1ull); type[(size_t)e*ns+k] = (int)((wd >> (2*(fpos&31)+1)) & 1ull);
+        for(int a=0;a<3;a++){ ref[((size_t)e*ns+k)*3+a] = h->st.cref[(size_t)(3*k+a)*B+e]; f[((size_t)e*ns+k)*3+a] = h->st.cf[(size_t)(3*k+a)*B+e]; } } } }
 }
 void hostsim_get_pivot(HostSim *h, int *type, double *prev)
 {
