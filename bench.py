@@ -35,6 +35,14 @@ def _c4_states(world, ch, B, seed):
     return ch.sample_c4_standing(world, B, seed=seed)
 
 
+def _mighty_states(world, ch, B, seed):
+    """mighty.ztk near its registered standing pose ([roki::chain::init]: trunk at z = 0.3667, soles on the floor)."""
+    q0 = np.array(ch.load_flat(os.path.join(ROOT, "tests", "golden", "flat_mighty_on_floor.txt"))["init.q[0]"])
+    rng = np.random.default_rng(seed)
+    q = np.tile(q0, (B, 1)); q[:, 6:] += 0.002 * rng.uniform(-1, 1, (B, world.nq - 6))
+    return q, rng.uniform(-0.05, 0.05, (B, world.nq)), np.zeros((B, world.nl))
+
+
 def _default_states(world, ch, B, seed):
     return ch.sample_state(world, B, seed=seed)
 
@@ -53,6 +61,11 @@ CONFIGS = {
     "C4": dict(label="C4: legged tree (floating trunk + two 3-joint legs, 12 DoF, box soles) standing, volume-based contact (rkfd_volume)",
                world=lambda ch: ch.world_c4_volume(), envs=131072, settle=10, states=_c4_states,
                alg_bytes=66.0 * 12 + 74.0 * 16, alg_flop=None, cpu=(8, 40), ref=(4, 10), max_steps=10),
+    "C4-mighty": dict(label="C4 on the reference's own model: mighty.ztk (25 links, 26 DoF, 701 collision vertices; tests/golden/flat_mighty_on_floor.txt) "
+                            "standing on floor.ztk, volume-based contact (rkfd_volume) on the soles",
+                      world=lambda ch: ch.world_from_flat(ch.load_flat(os.path.join(ROOT, "tests", "golden", "flat_mighty_on_floor.txt"))),
+                      envs=32768, settle=10, states=lambda world, ch, B, seed: _mighty_states(world, ch, B, seed),
+                      alg_bytes=66.0 * 26 + 74.0 * 701, alg_flop=None, cpu=(8, 40), ref=(4, 10), max_steps=10),
     "C5-mlcp": dict(label="C5: arm7 + 8-vertex cube on the rigid floor (K=1000, L=1e-4), MLCP/PGS max_iter=10; 1M envs over 8 GPUs = 131,072 per GPU",
                     world=lambda ch: ch.world_c5(base_z=0.45, solver="MLCP"), envs=131072, settle=500, states=_default_states,
                     alg_bytes=1054.0, alg_flop=106191.0, cpu=(256, 400), ref=(128, 100)),

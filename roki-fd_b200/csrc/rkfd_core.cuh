@@ -1884,6 +1884,17 @@ struct Core {
     return nfl;
   }
 
+  /* does this environment have an active contact on a rigid pair?  (multi-word worlds: every pair owns whole words) */
+  RKFD_HD bool rigid_active(const ModelDev &m){
+    if( Spec::NL != 0 || m.nfw <= 1 ) return RKFD_POPC64(cfl & m.rigid_mask) > 0;
+    bool any = false;
+    for(int pi=0;pi<m.npair;pi++){
+      const PairDev &pr = m.pair[pi]; if( pr.type != C_RIGID ) continue;
+      const int nw = (m.cell[pr.cell].nvert + 31) >> 5;
+      for(int k=0;k<nw;k++){ flag_select((pr.fofs >> 5) + k); if( cfl & 0x5555555555555555ull ) any = true; }
+    }
+    return any;
+  }
   RKFD_HD void load_flags(){ piv = c.st.piv_type[c.e]; cw = 0; cfl = c.st.cflags[c.e]; }
   RKFD_HD void store_flags(){ c.st.piv_type[c.e] = piv; c.st.cflags[(size_t)(Spec::NL != 0 ? 0 : cw)*c.st.ld + c.e] = cfl; if( bad ) c.st.status[c.e] |= bad; }
   /* committed state (buffer `cur`) -> stage state */
@@ -1909,7 +1920,7 @@ struct Core {
        * contacts skips the work, not the barriers, so that the warps of an SM sit in the same piece of this very large
        * kernel (ncu: 10 instruction-fetch stall cycles per issued instruction when every warp goes its own way).  The
        * Volume solver has barriers inside its solve as well (rkfd_volume.cuh): every warp enters it. */
-      const unsigned act = c.ballot( RKFD_POPC64(cfl & m.rigid_mask) > 0 );
+      const unsigned act = c.ballot( rigid_active(m) );
       const bool volume = Spec::NL == 0 && m.solver == S_VOLUME;
       const bool blk = c.block_or(act != 0);
 #pragma unroll 1

@@ -582,6 +582,9 @@ RKFD_VOL_U
       }
       flag_select(pr.fofs >> 5);
       int k0 = -1; for(int k=0;k<8;k++) if( cfl >> (2*((pr.fofs & 31)+k)) & 1ull ){ k0 = k; break; }
+#ifdef RKFD_VOL_DEBUG
+      if( k0 >= 0 ) printf("VOLDBG pair %d k0 %d volbox %d P %d\n", pi, k0, pr.volbox, P);
+#endif
       if( k0 < 0 ) continue;
       if( P >= VOL_P ){ bad |= 4; break; }
       VolPair &v = vp[P];
@@ -602,6 +605,9 @@ RKFD_VOL_U
       bool empty = false;
 #pragma unroll 1
       for(int pass=0; pass<2 && !empty; pass++) empty = !vol_clip(v, vw, d, cen, p0, pass);
+#ifdef RKFD_VOL_DEBUG
+      printf("VOLDBG pair %d empty %d npl %d\n", pi, (int)empty, v.npl);
+#endif
       if( empty ) continue;
       /* rkCDPlaneListQuickSort with __rk_fd_plane_cmp (:376-395): ascending angle key, ties keep their order */
       { double th[VOL_PL];
@@ -690,6 +696,9 @@ RKFD_VOL_U
     unsigned idx = 0; VOL_STAT(6, 1);
     c.phase_sync(1);
     if( P > 0 ) vol_asm(mrows, Qm, cv, nf, x, idx);
+#ifdef RKFD_VOL_DEBUG
+    for(int k=0;k<P;k++){ printf("VOLDBG pair %d npl %d center %.6e %.6e %.6e x", vp[k].pair, vp[k].npl, vp[k].center.x, vp[k].center.y, vp[k].center.z); for(int i=0;i<6;i++) printf(" %.6e", x[6*k+i]); printf(" idx %x mrows %d bad %d c6", idx, mrows, bad); for(int i=0;i<6;i++) printf(" %.4e", vp[k].c6[i]); printf("\n"); }
+#endif
     c.phase_sync(1);
     /* ---- f /= dt, _rkFDSolverSetForce (:552-568; the offset is not advanced for a pair without planes - mirrored) */
     { int off = 0;

@@ -144,6 +144,8 @@ def _flattened(fd):
 
 
 def _same_model(ma, mb, keys=None):
+    ma = {k: v for k, v in ma.items() if not k.startswith("init.")}      # the registered initial state is not part of the model
+    mb = {k: v for k, v in mb.items() if not k.startswith("init.")}
     ks = set(ma) if keys is None else {k for k in ma if k.split("[")[0] in keys}
     assert (set(ma) == set(mb) or keys is not None) and len(ks) > 3
     for k in ks:

@@ -681,3 +681,35 @@ def test_batch_stats(capi):
     assert s[0] == B and s[1] == (a.sum(1) > 0).sum() and s[2] == a.sum() and s[3] == (fd.batch_get_status() != 0).sum()
     assert s[4] == np.abs(gqdd).max() and s[5] == np.abs(gqd).max()
     fd.destroy()
+
+
+@pytest.mark.parametrize("name,soft,solver", [("mighty_on_floor", True, None), ("arm_box_floor", True, None), ("mighty_on_floor", False, "Volume"),
+                                              ("boxdrop_hardsoft", False, "Vert")])
+def test_reference_model_files(capi, oracle, name, soft, solver):
+    """The reference's own models (tests/golden/flat_*.txt = what rkFDChainRegFile + rkFDUpdateInit make of example/model/*.ztk,
+    checked in tests/test_capi_host.py where the reference tree exists): mighty.ztk (25 links, 26 DoF, 701 collision vertices
+    in 22 flag words; BASELINE config C4's model) standing on floor.ztk under the Volume solver and with penalty contact,
+    arm_2DoF.ztk + box.ztk + floor.ztk (example/chain/arm_box_test.c) with penalty contact, box.ztk on floor_hardsoft.ztk
+    (example/chain/boxdrop_hardsoft_test.c): one committing evaluation (1e-9) and 50 free-running steps."""
+    from test_kernel_core_host import flat_world, flat_states
+    w, q0 = flat_world(name, solver=solver, soft=soft)
+    B = 256
+    if name == "boxdrop_hardsoft":
+        q, qd, u = ch.sample_state(w, B, seed=3); q[:, 2] = np.linspace(0.0, 0.12, B); q[:, 1] = np.linspace(-0.4, 0.4, B)
+    else:
+        q, qd, u = flat_states(name, w, q0, B)
+    fd = gpu_world(capi, w, q, qd, u)
+    _, _, gqdd = fd.batch_get_state()
+    a, t, r, f = fd.batch_get_contact()
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=0)
+    assert (a == o[3]).all() and o[3].sum() > 0 and (fd.batch_get_status() == 0).all()
+    err = np.abs(gqdd - o[2]).max(1) / np.maximum(np.abs(o[2]).max(1), 1e-12)
+    assert (err < 1e-9).mean() >= (0.99 if name == "boxdrop_hardsoft" else 1.0), (np.sort(err)[-5:])
+    fd.update_n(50)
+    gq, _, _ = fd.batch_get_state()
+    oq = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=50)[0]
+    errq = np.abs(gq - oq).max(1) / np.abs(oq).max(1)
+    print("reference model %s (%s): q'' max rel err %.2e; after 50 steps %d/%d envs within 1e-7 (max %.2e)" % (
+        name, w.solver if not soft else "penalty", err.max(), (errq < 1e-7).sum(), B, errq.max()))
+    assert (errq < 1e-7).mean() >= (1.0 if soft else 0.9)
+    fd.destroy()

@@ -1,6 +1,7 @@
 """The sm_100a kernel core (roki-fd_b200/csrc/rkfd_core.cuh) compiled for the host by the test-only
 harness tests/hostsim, against the oracle.  This checks the kernel ARITHMETIC where no GPU exists;
 the GPU parity tests proper are in test_gpu_parity.py (-m gpu) and go through the C-ABI."""
+import os
 import numpy as np
 import pytest
 
@@ -444,13 +445,18 @@ def test_limits_are_reported_not_overrun():
     """Worlds beyond the fused kernel's tables (cells, vertices, contact slots, joint dofs) are refused with a message."""
     rng = np.random.default_rng(1)
     many_cells = ch.ChainModel("c", [ch.Link(name="l%d" % i, parent=i - 1, jtype="revolute" if i else "fixed", mass=1.0, stuff="body",
-                                             inertia=np.eye(3) * 1e-2, shapes=[ch.box_verts(0.1, 0.1, 0.1)]) for i in range(10)])
+                                             inertia=np.eye(3) * 1e-2, shapes=[ch.box_verts(0.1, 0.1, 0.1)] * 2) for i in range(20)])
     with pytest.raises(Exception, match="too many"):
         HostSim(ch.World(chains=[many_cells, ch.floor_soft()], contact_info=[ch.ContactInfo("soft", "body", "elastic", E=100.0, V=1.0)]), 1)
     blob = ch.ChainModel("b", [ch.Link(name="l", jtype="float", mass=1.0, stuff="body", inertia=np.eye(3) * 1e-2,
-                                       shapes=[rng.normal(size=(80, 3))])])
+                                       shapes=[rng.normal(size=(800, 3))])])
     with pytest.raises(Exception, match="too many"):
         HostSim(ch.World(chains=[blob, ch.floor_soft()], contact_info=[ch.ContactInfo("soft", "body", "elastic", E=100.0, V=1.0)]), 1)
+    # the rigid VERTEX solvers address their contacts through one flag word: 32 slots
+    two_cubes = ch.ChainModel("b", [ch.Link(name="l", jtype="float", mass=1.0, stuff="body", inertia=np.eye(3) * 1e-2,
+                                            shapes=[ch.box_verts(0.1, 0.1, 0.1, center=(0.1 * k, 0, 0)) for k in range(5)])])
+    with pytest.raises(Exception, match="at most 32 contact slots"):
+        HostSim(ch.World(chains=[two_cubes, ch.floor()], solver="MLCP"), 1)
     long_chain = ch.ChainModel("a", [ch.Link(name="l%d" % i, parent=i - 1, jtype="revolute" if i else "fixed", mass=1.0,
                                              inertia=np.eye(3) * 1e-2, org_p=np.array([0, 0, 0.1])) for i in range(40)])
     with pytest.raises(Exception):
@@ -492,3 +498,50 @@ def test_volume_pair_limit_is_flagged():
     hs = HostSim(w, 2); hs.set_state(q, qd, u); hs.eval(ref=True)
     st = hs.get_status()
     assert st[0] != 0 and st[1] == 0
+
+
+# ---- the reference's own model files (tests/golden/flat_*.txt: what the C-ABI makes of example/model/*.ztk) -------------
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def flat_world(name, solver=None, soft=False):
+    desc = ch.load_flat(os.path.join(GOLD, "flat_%s.txt" % name))
+    w = ch.world_from_flat(desc)
+    if solver:
+        w.solver = solver
+    if soft:      # every pair elastic (contactinfo.ztk's soft/body record): the penalty path on the reference's geometry
+        for ci in w.contact_info:
+            ci.type, ci.E, ci.V = "elastic", 1000.0, 10.0
+    return w, np.array(desc["init.q[0]"])
+
+
+def flat_states(name, w, q0, B, seed=0):
+    rng = np.random.default_rng(seed)
+    q = np.tile(q0, (B, 1)); qd = rng.uniform(-0.05, 0.05, (B, w.nq)); u = np.zeros((B, w.nl))
+    if name.startswith("mighty"):          # the humanoid near its registered standing pose, soles on the floor
+        q[:, 6:] += 0.002 * rng.uniform(-1, 1, (B, w.nq - 6))
+    else:                                  # arm_box_test.c: arm swung down towards the floor, box dropped next to it
+        q[:, :2] = rng.uniform(-0.3, 0.3, (B, 2)) + np.array([np.pi / 2, 0.0]); qd[:, :2] = rng.uniform(-2, 2, (B, 2))
+        q[:, 2:5] = np.array([0.0, 0.6, 0.06]) + rng.uniform(-0.02, 0.02, (B, 3)); q[:, 5:8] = rng.uniform(-0.3, 0.3, (B, 3))
+    return q, qd, u
+
+
+@pytest.mark.parametrize("name,soft", [("mighty_on_floor", True), ("arm_box_floor", True), ("mighty_on_floor", False)])
+def test_reference_models_step_like_the_oracle(oracle, name, soft):
+    """mighty.ztk (25 links, 26 DoF, 701 collision vertices = 22 flag words) and arm_2DoF.ztk + box.ztk on floor.ztk:
+    one committing evaluation and 20 steps of the kernel core against the oracle - penalty contact on every pair, and the
+    Volume solver on mighty's soles (its other shapes are watched, not solved)."""
+    w, q0 = flat_world(name, soft=soft)
+    B = 12
+    q, qd, u = flat_states(name, w, q0, B)
+    hs = HostSim(w, B); hs.set_state(q, qd, u); hs.eval(ref=True)
+    _, _, hqdd = hs.get_state(); a, t, r, f = hs.get_contact()
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=0)
+    assert (a == o[3]).all() and o[3].sum() > 0 and (hs.get_status() == 0).all()
+    err = np.abs(hqdd - o[2]).max(1) / np.maximum(np.abs(o[2]).max(1), 1e-12)
+    assert (err < 1e-9).all(), err
+    hs.step(20)
+    hq, _, _ = hs.get_state()
+    oq = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=20)[0]
+    errq = np.abs(hq - oq).max(1) / np.abs(oq).max(1)
+    assert (errq < 1e-7).mean() >= (1.0 if soft else 0.9), errq      # Volume: a mode flip at a zTOL-sized margin may split a trajectory
