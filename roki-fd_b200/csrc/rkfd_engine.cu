@@ -39,29 +39,37 @@ int device_count(){ int n = 0; if( cudaGetDeviceCount(&n) != cudaSuccess ) retur
  * global loads and the global stores of a warp are contiguous (round 1 moved one env-major row per thread: stride n*8 B,
  * 64 us per array of 262,144 x 7; HBM-bound now: 2 x 14.7 MB per array).  The tile row stride is padded to an odd number
  * of doubles so that the transposed shared-memory accesses spread over the banks. */
-constexpr int XP_THREADS = 256;
+constexpr int XP_THREADS = 256, XP_MAXCOL = 128;
 /* environments per tile: 64 (512-byte rows on the SoA side) while the tile stays under the 48 KB default limit */
 static inline int xp_te(int n){ int te = 64; while( te > 4 && (size_t)te*(n | 1)*sizeof(double) > 40*1024 ) te >>= 1; return te; }
-__global__ void __launch_bounds__(XP_THREADS) rkfd_scatter_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE)
+/* columns c0..c0+n-1 of env-major rows of length nrow (wide arrays - the 2,103 contact columns of mighty.ztk - go through in
+ * column blocks of XP_MAXCOL) */
+__global__ void __launch_bounds__(XP_THREADS) rkfd_scatter_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE, int nrow, int c0)
 {
   extern __shared__ double xp_tile[];
   const int e0 = blockIdx.x*XP_TE, ne = min(XP_TE, B - e0), ns = n | 1;
-  const double *s0 = src + (size_t)e0*n;
-  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; xp_tile[e*ns + k] = s0[i]; }
+  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; xp_tile[e*ns + k] = src[(size_t)(e0 + e)*nrow + c0 + k]; }
   __syncthreads();
-  for(int i=threadIdx.x; i<n*XP_TE; i+=XP_THREADS){ const int k = i/XP_TE, e = i - k*XP_TE; if( e < ne ) dst[(size_t)k*ld + e0 + e] = xp_tile[e*ns + k]; }
+  for(int i=threadIdx.x; i<n*XP_TE; i+=XP_THREADS){ const int k = i/XP_TE, e = i - k*XP_TE; if( e < ne ) dst[(size_t)(c0 + k)*ld + e0 + e] = xp_tile[e*ns + k]; }
 }
-__global__ void __launch_bounds__(XP_THREADS) rkfd_gather_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE)
+__global__ void __launch_bounds__(XP_THREADS) rkfd_gather_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE, int nrow, int c0)
 {
   extern __shared__ double xp_tile[];
   const int e0 = blockIdx.x*XP_TE, ne = min(XP_TE, B - e0), ns = n | 1;
-  for(int i=threadIdx.x; i<n*XP_TE; i+=XP_THREADS){ const int k = i/XP_TE, e = i - k*XP_TE; if( e < ne ) xp_tile[e*ns + k] = src[(size_t)k*ld + e0 + e]; }
+  for(int i=threadIdx.x; i<n*XP_TE; i+=XP_THREADS){ const int k = i/XP_TE, e = i - k*XP_TE; if( e < ne ) xp_tile[e*ns + k] = src[(size_t)(c0 + k)*ld + e0 + e]; }
   __syncthreads();
-  double *d0 = dst + (size_t)e0*n;
-  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; d0[i] = xp_tile[e*ns + k]; }
+  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; dst[(size_t)(e0 + e)*nrow + c0 + k] = xp_tile[e*ns + k]; }
 }
-static inline int xp_grid(int B, int n){ const int te = xp_te(n); return (B + te - 1)/te; }
-static inline size_t xp_smem(int n){ return (size_t)xp_te(n)*(n | 1)*sizeof(double); }
+static void xp_scatter(const double *src, double *dst, int B, int n, int ld, cudaStream_t st)
+{
+  for(int c0=0; c0<n; c0+=XP_MAXCOL){ const int nc = n - c0 < XP_MAXCOL ? n - c0 : XP_MAXCOL, te = xp_te(nc);
+    rkfd_scatter_kernel<<<(B + te - 1)/te, XP_THREADS, (size_t)te*(nc | 1)*sizeof(double), st>>>(src, dst, B, nc, ld, te, n, c0); }
+}
+static void xp_gather(const double *src, double *dst, int B, int n, int ld, cudaStream_t st)
+{
+  for(int c0=0; c0<n; c0+=XP_MAXCOL){ const int nc = n - c0 < XP_MAXCOL ? n - c0 : XP_MAXCOL, te = xp_te(nc);
+    rkfd_gather_kernel<<<(B + te - 1)/te, XP_THREADS, (size_t)te*(nc | 1)*sizeof(double), st>>>(src, dst, B, nc, ld, te, n, c0); }
+}
 
 /* rows k0..k0+n-1 of an SoA array <- one value per row, every environment (rkFDChainSetDis/SetVel and
  * rkJointMotorSetInput on a running simulator: the reference's cell windows alias fd->dis/vel, rkfd_sim.c:277-287) */
@@ -351,13 +359,13 @@ static void h2d_scatter(Shard &s, const double *src, int n, double *dst)
 {
   if( n <= 0 ) return;
   CK(cudaMemcpyAsync(s.dstage, src + (size_t)s.e0*n, (size_t)s.B*n*sizeof(double), cudaMemcpyHostToDevice, s.stream));
-  rkfd_scatter_kernel<<<xp_grid(s.B, n), XP_THREADS, xp_smem(n), s.stream>>>(s.dstage, dst, s.B, n, s.ld, xp_te(n));
+  xp_scatter(s.dstage, dst, s.B, n, s.ld, s.stream);
   CK(cudaGetLastError());
 }
 static void d2h_gather(Shard &s, const double *src, int n, double *dst)
 {
   if( n <= 0 ) return;
-  rkfd_gather_kernel<<<xp_grid(s.B, n), XP_THREADS, xp_smem(n), s.stream>>>(src, s.dstage, s.B, n, s.ld, xp_te(n));
+  xp_gather(src, s.dstage, s.B, n, s.ld, s.stream);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(dst + (size_t)s.e0*n, s.dstage, (size_t)s.B*n*sizeof(double), cudaMemcpyDeviceToHost, s.stream));
 }
@@ -387,7 +395,7 @@ static void h2d_scatter_async(Shard &s, const double *src, int n, double *dst)
   CK(cudaMemcpyAsync(s.ring[b], src + (size_t)s.e0*n, (size_t)s.B*n*sizeof(double), cudaMemcpyHostToDevice, s.h2d_stream));
   CK(cudaEventRecord(s.ring_ready[b], s.h2d_stream));
   CK(cudaStreamWaitEvent(s.stream, s.ring_ready[b], 0));
-  rkfd_scatter_kernel<<<xp_grid(s.B, n), XP_THREADS, xp_smem(n), s.stream>>>(s.ring[b], dst, s.B, n, s.ld, xp_te(n));
+  xp_scatter(s.ring[b], dst, s.B, n, s.ld, s.stream);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ring_done[b], s.stream));
 }
@@ -397,7 +405,7 @@ static void d2h_gather_async(Shard &s, const double *src, int n, double *dst)
   ring_setup(s);
   const int b = s.ring_next; s.ring_next = (b+1) % Shard::NRING;
   CK(cudaStreamWaitEvent(s.stream, s.ring_done[b], 0));
-  rkfd_gather_kernel<<<xp_grid(s.B, n), XP_THREADS, xp_smem(n), s.stream>>>(src, s.ring[b], s.B, n, s.ld, xp_te(n));
+  xp_gather(src, s.ring[b], s.B, n, s.ld, s.stream);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ring_ready[b], s.stream));
   CK(cudaStreamWaitEvent(s.d2h_stream, s.ring_ready[b], 0));
