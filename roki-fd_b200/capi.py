@@ -14,7 +14,8 @@ import numpy as np
 from .chains import NDOF, ChainModel, World
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librokifd_b200.so")
+# ROKIFD_B200_LIB: a tuning aid (tools/build_exp.sh builds variants of the library); the default is the in-tree product library
+LIB_PATH = os.environ.get("ROKIFD_B200_LIB") or os.path.join(_HERE, "librokifd_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -100,7 +100,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
         std::memcpy(fr[i].data(), R, sizeof R); std::memcpy(fr[i].data()+9, p, sizeof p);
         for(const BoxShape &bs : l.boxes){
           StatBox sb; double c[3];
-          std::memcpy(sb.b.R, R, sizeof R); mat3_mulv(R, bs.center, c);
+          mat3_mul(R, bs.R, sb.b.R); mat3_mulv(R, bs.center, c);
           for(int k=0;k<3;k++) sb.b.p[k] = p[k] + c[k];
           sb.b.half[0] = 0.5*bs.depth; sb.b.half[1] = 0.5*bs.width; sb.b.half[2] = 0.5*bs.height;
           sb.stuff = l.stuff; boxes.push_back(sb);

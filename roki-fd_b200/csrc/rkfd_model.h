@@ -15,7 +15,8 @@ struct MotorHost {
   double k = 0, admittance = 0, gear = 1, rotor_inertia = 0, gear_inertia = 0, min = -1e300, max = 1e300;
 };
 
-struct BoxShape { double center[3]; double depth, width, height; };   /* zeo box: depth=x width=y height=z */
+/* zeo box: depth along ax, width along ay, height along az; R = [ax ay az] (columns, row-major storage), identity by default */
+struct BoxShape { double center[3]; double depth, width, height; double R[9] = {1,0,0, 0,1,0, 0,0,1}; };
 
 struct LinkHost {
   std::string name, stuff;

@@ -60,19 +60,104 @@ const Field *find(const Section &s, const char *key){ for(const Field &f : s.fie
 std::string word(const Section &s, const char *key){ const Field *f = find(s, key); return ( f && !f->val.empty() ) ? f->val[0] : std::string(); }
 const double DEG = M_PI/180.0;
 
-struct Shape { std::vector<double> verts; bool is_box = false; BoxShape box; };
+/* mass properties of a shape at unit density, about the origin of the frame the shape is written in ([EXT] Zeo computes
+ * them for `COM: auto` / `inertia: auto`): volume, volume * centroid, second-moment matrix int x x^T dV */
+struct MassProp {
+  double vol = 0, vc[3] = {0,0,0}, xx[9] = {0,0,0, 0,0,0, 0,0,0};
+  void add(const MassProp &o){ vol += o.vol; for(int i=0;i<3;i++) vc[i] += o.vc[i]; for(int i=0;i<9;i++) xx[i] += o.xx[i]; }
+};
+struct Shape { std::vector<double> verts; bool is_box = false; BoxShape box; MassProp mp; bool has_mp = false; };
 
-void ring(std::vector<double> &v, const double c[3], const double ax[3], double r, int div)
+/* closed triangle mesh: signed tetrahedra against the origin */
+MassProp mesh_massprop(const std::vector<double> &v, const std::vector<int> &tri)
 {
-  /* orthonormal basis perpendicular to ax */
-  double a[3] = {ax[0],ax[1],ax[2]}, n = std::sqrt(a[0]*a[0]+a[1]*a[1]+a[2]*a[2]); if( n == 0 ){ a[2] = 1; n = 1; }
+  MassProp m;
+  for(size_t t=0;t+2<tri.size();t+=3){
+    const double *a = &v[3*tri[t]], *b = &v[3*tri[t+1]], *c = &v[3*tri[t+2]];
+    const double vol = ( a[0]*(b[1]*c[2]-b[2]*c[1]) + a[1]*(b[2]*c[0]-b[0]*c[2]) + a[2]*(b[0]*c[1]-b[1]*c[0]) )/6.0;
+    m.vol += vol;
+    double S[3];
+    for(int i=0;i<3;i++){ S[i] = a[i]+b[i]+c[i]; m.vc[i] += vol*0.25*S[i]; }
+    for(int i=0;i<3;i++) for(int j=0;j<3;j++) m.xx[3*i+j] += vol/20.0*( a[i]*a[j] + b[i]*b[j] + c[i]*c[j] + S[i]*S[j] );
+  }
+  if( m.vol < 0 ){ m.vol = -m.vol; for(int i=0;i<3;i++) m.vc[i] = -m.vc[i]; for(int i=0;i<9;i++) m.xx[i] = -m.xx[i]; }   /* inward-oriented faces */
+  return m;
+}
+/* a solid of revolution-like primitive given in its own axes (e1, e2, ax unit, origin o): volume V, centroid at o + zc ax,
+ * second moments about the centroid diag(it, it, ia) in (e1, e2, ax) */
+MassProp axial_massprop(const double o[3], const double ax[3], double V, double zc, double it, double ia)
+{
+  MassProp m; m.vol = V; double c[3];
+  for(int i=0;i<3;i++){ c[i] = o[i] + zc*ax[i]; m.vc[i] = V*c[i]; }
+  /* second moments about the centroid: it * (I - ax ax^T) + ia * ax ax^T, then the parallel shift V c c^T */
+  for(int i=0;i<3;i++) for(int j=0;j<3;j++) m.xx[3*i+j] = it*((i==j?1.0:0.0) - ax[i]*ax[j]) + ia*ax[i]*ax[j] + V*c[i]*c[j];
+  return m;
+}
+
+void basis_perp(const double ax[3], double a[3], double e1[3], double e2[3])
+{
+  double n = std::sqrt(ax[0]*ax[0]+ax[1]*ax[1]+ax[2]*ax[2]); a[0] = ax[0]; a[1] = ax[1]; a[2] = ax[2]; if( n == 0 ){ a[0] = a[1] = 0; a[2] = 1; n = 1; }
   for(int k=0;k<3;k++) a[k] /= n;
   double t[3] = {1,0,0}; if( std::fabs(a[0]) > 0.9 ){ t[0] = 0; t[1] = 1; }
-  double d = t[0]*a[0]+t[1]*a[1]+t[2]*a[2]; double e1[3] = {t[0]-d*a[0], t[1]-d*a[1], t[2]-d*a[2]};
+  const double d = t[0]*a[0]+t[1]*a[1]+t[2]*a[2];
+  for(int k=0;k<3;k++) e1[k] = t[k]-d*a[k];
   n = std::sqrt(e1[0]*e1[0]+e1[1]*e1[1]+e1[2]*e1[2]); for(int k=0;k<3;k++) e1[k] /= n;
-  double e2[3] = {a[1]*e1[2]-a[2]*e1[1], a[2]*e1[0]-a[0]*e1[2], a[0]*e1[1]-a[1]*e1[0]};
+  e2[0] = a[1]*e1[2]-a[2]*e1[1]; e2[1] = a[2]*e1[0]-a[0]*e1[2]; e2[2] = a[0]*e1[1]-a[1]*e1[0];
+}
+void ring(std::vector<double> &v, const double c[3], const double ax[3], double r, int div)
+{
+  double a[3], e1[3], e2[3]; basis_perp(ax, a, e1, e2);
   for(int i=0;i<div;i++){ const double th = 2.0*M_PI*i/div, cs = std::cos(th), sn = std::sin(th);
     for(int k=0;k<3;k++) v.push_back(c[k] + r*(cs*e1[k] + sn*e2[k])); }
+}
+
+/* `loop: <axis> <coordinate>  x y | arc cw|ccw <radius> <div> ...` + `prism: dx dy dz` | `pyramid: x y z` ([EXT] Zeo's
+ * polyhedron sugar, puma.ztk:67-88): a planar polygon whose corners may be joined by circular arcs (radius r, the minor
+ * arc, `div` segments), extruded along a vector or joined to an apex.  Vertices: the loop, then the shifted loop / apex. */
+bool read_loop_sugar(const Section &s, Shape &sh, std::string &warn)
+{
+  const Field *fl = find(s, "loop"); if( !fl || fl->val.size() < 2 ) return false;
+  const char axc = fl->val[0].empty() ? 'z' : fl->val[0][0]; const double h0 = std::atof(fl->val[1].c_str());
+  std::vector<double> pts;      /* 2-D loop */
+  struct Arc { size_t after; bool cw; double r; int div; }; std::vector<Arc> arcs;
+  for(size_t i=2;i<fl->val.size();){
+    if( fl->val[i] == "arc" && i+3 < fl->val.size() ){ Arc a; a.after = pts.size()/2; a.cw = fl->val[i+1] == "cw"; a.r = std::atof(fl->val[i+2].c_str()); a.div = std::atoi(fl->val[i+3].c_str()); arcs.push_back(a); i += 4; }
+    else if( i+1 < fl->val.size() ){ pts.push_back(std::atof(fl->val[i].c_str())); pts.push_back(std::atof(fl->val[i+1].c_str())); i += 2; }
+    else break;
+  }
+  const size_t np = pts.size()/2; if( np < 3 ){ warn += "polyhedron loop with fewer than 3 corners; "; return false; }
+  std::vector<double> loop;
+  for(size_t k=0;k<np;k++){
+    loop.push_back(pts[2*k]); loop.push_back(pts[2*k+1]);
+    for(const Arc &a : arcs) if( a.after == k+1 ){       /* between corner k and corner k+1 (cyclic) */
+      const double *p0 = &pts[2*k], *p1 = &pts[2*((k+1)%np)];
+      const double dx = p1[0]-p0[0], dy = p1[1]-p0[1], ch = std::sqrt(dx*dx+dy*dy); if( ch == 0 || a.div < 2 ) continue;
+      const double r = a.r > 0.5*ch ? a.r : 0.5*ch, hh = std::sqrt(r*r - 0.25*ch*ch);
+      /* clockwise travel keeps the centre on the right of the direction of travel */
+      const double sg = a.cw ? 1.0 : -1.0, cx = 0.5*(p0[0]+p1[0]) + sg*hh*dy/ch, cy = 0.5*(p0[1]+p1[1]) - sg*hh*dx/ch;
+      double a0 = std::atan2(p0[1]-cy, p0[0]-cx), a1 = std::atan2(p1[1]-cy, p1[0]-cx), sw = a.cw ? a0 - a1 : a1 - a0;
+      while( sw <= 0 ) sw += 2.0*M_PI;
+      while( sw > 2.0*M_PI ) sw -= 2.0*M_PI;
+      for(int j=1;j<a.div;j++){ const double th = a0 + (a.cw ? -1.0 : 1.0)*sw*j/a.div; loop.push_back(cx + r*std::cos(th)); loop.push_back(cy + r*std::sin(th)); }
+    }
+  }
+  const size_t n = loop.size()/2;
+  auto to3 = [&](double u, double v, double out[3]){ if( axc == 'x' ){ out[0] = h0; out[1] = u; out[2] = v; } else if( axc == 'y' ){ out[0] = v; out[1] = h0; out[2] = u; } else { out[0] = u; out[1] = v; out[2] = h0; } };
+  std::vector<int> tri;
+  for(size_t k=0;k<n;k++){ double q[3]; to3(loop[2*k], loop[2*k+1], q); sh.verts.insert(sh.verts.end(), q, q+3); }
+  if( const Field *fp = find(s, "prism") ){
+    const double d[3] = { num(*fp,0), num(*fp,1), num(*fp,2) };
+    for(size_t k=0;k<n;k++) for(int i=0;i<3;i++) sh.verts.push_back(sh.verts[3*k+i] + d[i]);
+    for(size_t k=0;k<n;k++){ const int a = (int)k, b = (int)((k+1)%n), a2 = a+(int)n, b2 = b+(int)n;
+      tri.insert(tri.end(), {a, b, b2}); tri.insert(tri.end(), {a, b2, a2}); }           /* side quads */
+    for(size_t k=1;k+1<n;k++){ tri.insert(tri.end(), {0, (int)k+1, (int)k}); tri.insert(tri.end(), {(int)n, (int)(n+k), (int)(n+k+1)}); }   /* caps as signed fans */
+  } else if( const Field *fp = find(s, "pyramid") ){
+    for(int i=0;i<3;i++) sh.verts.push_back(num(*fp,i));
+    for(size_t k=0;k<n;k++) tri.insert(tri.end(), {(int)k, (int)((k+1)%n), (int)n});
+    for(size_t k=1;k+1<n;k++) tri.insert(tri.end(), {0, (int)k+1, (int)k});
+  } else { warn += "polyhedron loop without prism/pyramid; "; return true; }
+  sh.mp = mesh_massprop(sh.verts, tri); sh.has_mp = true;
+  return true;
 }
 
 bool read_shape(const Section &s, Shape &sh, std::string &warn)
@@ -84,14 +169,37 @@ bool read_shape(const Section &s, Shape &sh, std::string &warn)
     if( const Field *f = find(s, "depth") ) b.depth = num(*f, 0);
     if( const Field *f = find(s, "width") ) b.width = num(*f, 0);
     if( const Field *f = find(s, "height") ) b.height = num(*f, 0);
-    if( find(s, "ax") || find(s, "ay") || find(s, "az") ) warn += "box axes (ax/ay/az) ignored; ";
+    /* ax / ay / az: the box axes in the link frame (two given: the third is their cross product; one: completed) */
+    { double ax[3][3] = {{1,0,0},{0,1,0},{0,0,1}}; bool have[3] = {false,false,false}; const char *key[3] = {"ax","ay","az"};
+      for(int a=0;a<3;a++) if( const Field *f = find(s, key[a]) ){ double n = 0; for(int k=0;k<3;k++){ ax[a][k] = num(*f, k); n += ax[a][k]*ax[a][k]; }
+        n = std::sqrt(n); if( n > 0 ){ for(int k=0;k<3;k++) ax[a][k] /= n; have[a] = true; } }
+      auto cross3 = [](const double *u, const double *v, double *w){ w[0] = u[1]*v[2]-u[2]*v[1]; w[1] = u[2]*v[0]-u[0]*v[2]; w[2] = u[0]*v[1]-u[1]*v[0]; };
+      if( have[0] || have[1] || have[2] ){
+        if( have[0] && have[1] ) cross3(ax[0], ax[1], ax[2]);
+        else if( have[1] && have[2] ) cross3(ax[1], ax[2], ax[0]);
+        else if( have[2] && have[0] ) cross3(ax[2], ax[0], ax[1]);
+        else { const int g = have[0] ? 0 : ( have[1] ? 1 : 2 ); double a_[3], e1[3], e2[3]; basis_perp(ax[g], a_, e1, e2);
+          for(int k=0;k<3;k++){ ax[(g+1)%3][k] = e1[k]; ax[(g+2)%3][k] = e2[k]; } }
+        for(int r=0;r<3;r++) for(int c=0;c<3;c++) b.R[3*r+c] = ax[c][r];
+      } }
     sh.is_box = true; sh.box = b;
-    for(int k=0;k<8;k++){ sh.verts.push_back(b.center[0] + ((k&1)?0.5:-0.5)*b.depth); sh.verts.push_back(b.center[1] + ((k&2)?0.5:-0.5)*b.width); sh.verts.push_back(b.center[2] + ((k&4)?0.5:-0.5)*b.height); }
+    for(int k=0;k<8;k++){ const double l[3] = { ((k&1)?0.5:-0.5)*b.depth, ((k&2)?0.5:-0.5)*b.width, ((k&4)?0.5:-0.5)*b.height };
+      for(int r=0;r<3;r++) sh.verts.push_back(b.center[r] + b.R[3*r]*l[0] + b.R[3*r+1]*l[1] + b.R[3*r+2]*l[2]); }
+    { const double V = b.depth*b.width*b.height, d2[3] = { b.depth*b.depth/12.0, b.width*b.width/12.0, b.height*b.height/12.0 };
+      sh.mp.vol = V; for(int i=0;i<3;i++) sh.mp.vc[i] = V*b.center[i];
+      for(int i=0;i<3;i++) for(int j=0;j<3;j++){ double t = 0; for(int k=0;k<3;k++) t += b.R[3*i+k]*d2[k]*b.R[3*j+k]; sh.mp.xx[3*i+j] = V*( t + b.center[i]*b.center[j] ); }
+      sh.has_mp = true; }
     return true;
   }
   if( type == "polyhedron" ){
-    if( find(s, "loop") || find(s, "prism") || find(s, "pyramid") ){ warn += "polyhedron loop/prism sugar not supported, shape '" + word(s, "name") + "' has no collision vertices; "; return true; }
-    for(const Field &f : s.fields) if( f.key == "vert" && f.val.size() >= 4 ){ sh.verts.push_back(num(f,1)); sh.verts.push_back(num(f,2)); sh.verts.push_back(num(f,3)); }
+    if( find(s, "loop") ){ read_loop_sugar(s, sh, warn); return true; }
+    std::vector<int> tri;
+    for(const Field &f : s.fields){
+      if( f.key == "vert" && f.val.size() >= 4 ){ sh.verts.push_back(num(f,1)); sh.verts.push_back(num(f,2)); sh.verts.push_back(num(f,3)); }
+      if( f.key == "face" && f.val.size() >= 3 ) for(int k=0;k<3;k++) tri.push_back((int)num(f,k));
+    }
+    bool ok = !tri.empty(); for(int t : tri) if( t < 0 || 3*t+2 >= (int)sh.verts.size() ) ok = false;
+    if( ok ){ sh.mp = mesh_massprop(sh.verts, tri); sh.has_mp = true; }
     return true;
   }
   if( type == "cylinder" || type == "cone" ){
@@ -102,8 +210,29 @@ bool read_shape(const Section &s, Shape &sh, std::string &warn)
     }
     const Field *fr = find(s, "radius"); const double r = fr ? num(*fr, 0) : 0.0;
     const Field *fd = find(s, "div"); const int div = fd ? (int)num(*fd, 0) : 32;
-    if( type == "cylinder" ){ const double ax[3] = {c[1][0]-c[0][0], c[1][1]-c[0][1], c[1][2]-c[0][2]}; ring(sh.verts, c[0], ax, r, div); ring(sh.verts, c[1], ax, r, div); }
-    else { const double ax[3] = {vert[0]-c[0][0], vert[1]-c[0][1], vert[2]-c[0][2]}; if( hasv ){ sh.verts.push_back(vert[0]); sh.verts.push_back(vert[1]); sh.verts.push_back(vert[2]); } ring(sh.verts, c[0], ax, r, div); }
+    double a[3], e1[3], e2[3];
+    if( type == "cylinder" ){ const double ax[3] = {c[1][0]-c[0][0], c[1][1]-c[0][1], c[1][2]-c[0][2]}; ring(sh.verts, c[0], ax, r, div); ring(sh.verts, c[1], ax, r, div);
+      const double h = std::sqrt(ax[0]*ax[0]+ax[1]*ax[1]+ax[2]*ax[2]), V = M_PI*r*r*h; basis_perp(ax, a, e1, e2);
+      /* second moments about the centroid: transverse V r^2/4, axial V h^2/12 */
+      sh.mp = axial_massprop(c[0], a, V, 0.5*h, V*r*r/4.0, V*h*h/12.0); sh.has_mp = true; }
+    else { const double ax[3] = {vert[0]-c[0][0], vert[1]-c[0][1], vert[2]-c[0][2]}; if( hasv ){ sh.verts.push_back(vert[0]); sh.verts.push_back(vert[1]); sh.verts.push_back(vert[2]); } ring(sh.verts, c[0], ax, r, div);
+      const double h = std::sqrt(ax[0]*ax[0]+ax[1]*ax[1]+ax[2]*ax[2]), V = M_PI*r*r*h/3.0; basis_perp(ax, a, e1, e2);
+      /* cone: centroid h/4 above the base; second moments about it: transverse 3 V r^2/20, axial 3 V h^2/80 */
+      sh.mp = axial_massprop(c[0], a, V, 0.25*h, 3.0*V*r*r/20.0, 3.0*V*h*h/80.0); sh.has_mp = true; }
+    return true;
+  }
+  if( type == "sphere" ){
+    double c[3] = {0,0,0}; if( const Field *f = find(s, "center") ) for(int k=0;k<3;k++) c[k] = num(*f, k);
+    const Field *fr = find(s, "radius"); const double r = fr ? num(*fr, 0) : 0.0;
+    /* [EXT] Zeo tessellates a sphere for the vertex test; its default division is not visible in the tree: 8 latitude
+     * bands x 8 meridians here (58 vertices), `div` when the file gives one */
+    const Field *fd = find(s, "div"); const int div = fd ? (int)num(*fd, 0) : 8;
+    sh.verts.insert(sh.verts.end(), {c[0], c[1], c[2]+r});
+    for(int i=1;i<div;i++){ const double ph = M_PI*i/div; for(int j=0;j<div;j++){ const double th = 2.0*M_PI*j/div;
+      sh.verts.insert(sh.verts.end(), {c[0] + r*std::sin(ph)*std::cos(th), c[1] + r*std::sin(ph)*std::sin(th), c[2] + r*std::cos(ph)}); } }
+    sh.verts.insert(sh.verts.end(), {c[0], c[1], c[2]-r});
+    const double V = 4.0/3.0*M_PI*r*r*r; const double az[3] = {0,0,1};
+    sh.mp = axial_massprop(c, az, V, 0.0, V*r*r/5.0, V*r*r/5.0); sh.has_mp = true;
     return true;
   }
   warn += "shape type '" + type + "' not supported; ";
@@ -140,8 +269,10 @@ bool ztk_read_chain(const char *filename, ChainHost &chain, std::string &err)
       else if( jt == "spherical" ) l.jtype = J_SPHER; else if( jt == "float" ) l.jtype = J_FLOAT;
       else { err = "joint type '" + jt + "' of link '" + l.name + "' is not supported"; return false; }
       if( const Field *f = find(s, "mass") ) l.mass = num(*f, 0);
-      if( const Field *f = find(s, "COM") ){ if( !f->val.empty() && f->val[0] == "auto" ) warn += "COM: auto not supported; "; else for(int k=0;k<3;k++) l.com[k] = num(*f, k); }
-      if( const Field *f = find(s, "inertia") ){ if( !f->val.empty() && f->val[0] == "auto" ) warn += "inertia: auto not supported; "; else for(int k=0;k<9;k++) l.inertia[k] = num(*f, k); }
+      bool com_auto = false, inertia_auto = false; double density = 0.0;
+      if( const Field *f = find(s, "density") ) density = num(*f, 0);
+      if( const Field *f = find(s, "COM") ){ if( !f->val.empty() && f->val[0] == "auto" ) com_auto = true; else for(int k=0;k<3;k++) l.com[k] = num(*f, k); }
+      if( const Field *f = find(s, "inertia") ){ if( !f->val.empty() && f->val[0] == "auto" ) inertia_auto = true; else for(int k=0;k<9;k++) l.inertia[k] = num(*f, k); }
       if( const Field *f = find(s, "frame") ) for(int r=0;r<3;r++){ for(int c=0;c<3;c++) l.Ro[3*r+c] = num(*f, 4*r+c, r==c); l.po[r] = num(*f, 4*r+3); }
       if( const Field *f = find(s, "pos") ) for(int k=0;k<3;k++) l.po[k] = num(*f, k);
       if( const Field *f = find(s, "DH") ){
@@ -159,10 +290,24 @@ bool ztk_read_chain(const char *filename, ChainHost &chain, std::string &err)
       if( !mn.empty() ){ auto it = motors.find(mn); if( it == motors.end() ){ err = "unknown motor '" + mn + "'"; return false; } l.motor = it->second; }
       const std::string pn = word(s, "parent");
       if( !pn.empty() ){ auto it = link_index.find(pn); if( it == link_index.end() ){ err = "parent '" + pn + "' of link '" + l.name + "' must be defined before it"; return false; } l.parent = it->second; }
+      MassProp lmp;
       for(const Field &f : s.fields) if( f.key == "shape" && !f.val.empty() ){
         auto it = shapes.find(f.val[0]); if( it == shapes.end() ){ err = "unknown shape '" + f.val[0] + "'"; return false; }
         if( !it->second.verts.empty() ) l.shapes.push_back(it->second.verts);
         if( it->second.is_box ) l.boxes.push_back(it->second.box);
+        if( it->second.has_mp ) lmp.add(it->second.mp); else if( com_auto || inertia_auto ) warn += "shape '" + f.val[0] + "' has no mass properties for COM/inertia: auto; ";
+      }
+      /* `COM: auto` / `inertia: auto` / `density:`: uniform density over the link's shapes ([EXT] Zeo; arm.ztk:79-80) */
+      if( ( com_auto || inertia_auto || density > 0.0 ) && lmp.vol > 0.0 ){
+        if( density > 0.0 && !( l.mass > 0.0 ) ) l.mass = density*lmp.vol;
+        const double rho = l.mass/lmp.vol; double c[3]; for(int k=0;k<3;k++) c[k] = lmp.vc[k]/lmp.vol;
+        if( com_auto || find(s, "COM") == nullptr ) for(int k=0;k<3;k++) l.com[k] = c[k];
+        if( inertia_auto || find(s, "inertia") == nullptr ){
+          /* inertia about the COM from the second moments about the origin: I = tr(X) E - X with X = rho xx - m c c^T */
+          double X[9]; for(int i=0;i<3;i++) for(int j=0;j<3;j++) X[3*i+j] = rho*lmp.xx[3*i+j] - l.mass*l.com[i]*l.com[j];
+          const double tr = X[0]+X[4]+X[8];
+          for(int i=0;i<3;i++) for(int j=0;j<3;j++) l.inertia[3*i+j] = (i==j ? tr : 0.0) - X[3*i+j];
+        }
       }
       link_index[l.name] = (int)chain.links.size();
       chain.links.push_back(l);

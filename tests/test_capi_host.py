@@ -203,3 +203,76 @@ def test_reference_model_files_match_the_transcribed_worlds():
             if k.startswith("link.topo"):
                 m[k] = m[k][:5]            # parent, joint type, motor type, dofs, offset (not the cell range)
     _same_model(ma, mb, keys={"link.topo", "link.Ro", "link.po", "link.mass", "link.joint"})
+
+
+def test_ztk_shape_sugar_and_automatic_mass_properties():
+    """loop / arc / prism polyhedra (puma.ztk:67-88), box axes, spheres, `COM: auto` / `inertia: auto` / `density:`
+    (arm.ztk:79-80): vertices and mass properties of tests/golden/sugar.ztk against an independent evaluation (scipy's
+    convex hull for the prism, closed forms for the primitives)."""
+    from scipy.spatial import ConvexHull
+    fd = capi.RkFD()
+    assert fd.chain_reg_file(os.path.join(GOLD, "sugar.ztk")) is not None
+    m = _flattened(fd)
+    fd.destroy()
+    verts = np.array([m["vert[%d]" % i] for i in range(int(m["dims"][6]))])
+    cells = [[int(v) for v in m["cell[%d]" % i]] for i in range(int(m["dims"][2]))]
+
+    def link(i):
+        mp = m["link.mass[%d]" % i]
+        Io = np.array([[mp[4], mp[5], mp[6]], [mp[5], mp[7], mp[8]], [mp[6], mp[8], mp[9]]])
+        c = np.array(mp[10:13])
+        return mp[0], c, Io - mp[0] * (c @ c * np.eye(3) - np.outer(c, c))
+    # --- the prism: 6 corners + 11 arc points per ring, two rings; convex, so the hull is the solid
+    pv = verts[cells[0][1]:cells[0][1] + cells[0][2]]
+    assert pv.shape[0] == 2 * (6 + 11) and np.allclose(sorted(set(np.round(pv[:, 2], 12))), [0.01, 0.05])
+    arc = pv[1:12]
+    assert np.allclose(np.hypot(arc[:, 0] - (-0.05 + np.sqrt(0.08 ** 2 - 0.06 ** 2)), arc[:, 1]), 0.08) and (arc[:, 0] < -0.05).all()
+    hull = ConvexHull(pv)
+    vol, vc, xx = 0.0, np.zeros(3), np.zeros((3, 3))
+    o = pv.mean(0)
+    for s in hull.simplices:                      # tetrahedra (o, a, b, c), 4-point degree-2 rule
+        a, b, c = pv[s] - o
+        v = abs(np.dot(a, np.cross(b, c))) / 6.0
+        S = a + b + c
+        vol += v; vc += v * 0.25 * S
+        xx += v / 20.0 * (np.outer(a, a) + np.outer(b, b) + np.outer(c, c) + np.outer(S, S))
+    assert abs(vol - hull.volume) < 1e-12
+    com = o + vc / vol
+    X = 2.0 / vol * xx - 2.0 * np.outer(vc / vol, vc / vol)      # density * second moments about the centroid
+    mass, c, Ic = link(0)
+    assert mass == 2.0 and np.allclose(c, com, atol=1e-12) and np.allclose(Ic, np.trace(X) * np.eye(3) - X, atol=1e-12)
+    # --- the tilted box: corners on the rotated axes, inertia R diag R^T
+    bv = verts[cells[1][1]:cells[1][1] + 8]
+    R = np.array([[0.8, -0.6, 0], [0.6, 0.8, 0], [0, 0, 1.0]])
+    loc = (bv - np.array([0.1, 0, 0.05])) @ R
+    assert np.allclose(np.abs(loc), [0.1, 0.05, 0.03])
+    mass, c, Ic = link(1)
+    d = np.array([0.2, 0.1, 0.06])
+    assert np.allclose(c, [0.1, 0, 0.05]) and np.allclose(Ic, R @ np.diag(1.5 / 12 * (d @ d - d * d)) @ R.T, atol=1e-14)
+    # --- density: sphere + cone
+    Vs, Vc = 4 / 3 * np.pi * 0.03 ** 3, np.pi * 0.02 ** 2 * 0.08 / 3
+    mass, c, Ic = link(2)
+    assert abs(mass - 1000 * (Vs + Vc)) < 1e-12
+    cs, cc = np.array([0, 0.1, 0]), np.array([0, 0, 0.04])
+    assert np.allclose(c, (Vs * cs + Vc * cc) / (Vs + Vc), atol=1e-14)
+    Is = 1000 * Vs * 0.4 * 0.03 ** 2 * np.eye(3)
+    Icn = 1000 * Vc * np.diag([3 / 80 * (4 * 0.02 ** 2 + 0.08 ** 2)] * 2 + [0.3 * 0.02 ** 2])
+    tot = np.zeros((3, 3))
+    for mi, ci, Ii in ((1000 * Vs, cs, Is), (1000 * Vc, cc, Icn)):
+        r = ci - c
+        tot += Ii + mi * (r @ r * np.eye(3) - np.outer(r, r))
+    assert np.allclose(Ic, tot, atol=1e-14)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/example/model"), reason="reference tree not present")
+def test_ztk_reader_fills_the_gaps_of_the_reference_models():
+    """puma.ztk's loop/prism shapes give collision vertices, arm.ztk's `COM: auto` links get mass properties, no shape of
+    the reference's model directory is dropped."""
+    d = "/root/reference/example/model"
+    fd = capi.RkFD(); assert fd.chain_reg_file(os.path.join(d, "puma.ztk")) is not None
+    m = _flattened(fd); fd.destroy()
+    assert int(m["dims"][2]) == 7 and int(m["dims"][6]) > 300           # 7 cells: base, post, shoulder, upperarm, forearm, hand ...
+    fd = capi.RkFD(); assert fd.chain_reg_file(os.path.join(d, "arm.ztk")) is not None
+    m = _flattened(fd); fd.destroy()
+    Vs, Vc = 4 / 3 * np.pi * 0.02 ** 3, np.pi * 0.01 ** 2 * 0.11
+    assert abs(m["link.mass[1]"][12] - Vc * 0.075 / (Vs + Vc)) < 1e-12 and m["link.mass[4]"][4] == pytest.approx(0.6 * 0.4 * 0.02 ** 2)
