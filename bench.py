@@ -380,6 +380,7 @@ def main():
         fd.update()
     barrier()
     l0 = fd.launch_count
+    r0 = fd.resort_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record(stream)
     for s in range(args.steps):
@@ -387,6 +388,7 @@ def main():
         ev[s + 1].record(stream)
     barrier()
     launches = fd.launch_count - l0
+    resorts = fd.resort_count - r0
     sampler.mark_end()
     if sampler.loaded_samples() == 0:
         # nvidia-smi delivered nothing inside the timed region (slow start): keep the same load on the device until it does
@@ -501,6 +503,7 @@ def main():
            "config": {"workload": workload_string(cfg, B), "name": args.config, "envs_per_gpu": B, "dt": world.dt, "integrator": "RKG", "solver": world.solver,
                       "settle_steps": settle, "envs_in_contact": contact_frac, "mean_active_vertices": mean_active, "flagged_envs": nbad,
                       "numa_node": numa, "numa_how": numa_how,
+                      "env_resorts_in_timed_region": int(resorts),       # the engine re-orders its slots by contact count every 16 steps (rkFDBatchSetResortInterval)
                       "l2": "per-GPU state (%.0f MB) is larger than the 126 MB L2" % (B * 8 * 140 / 1e6) if B * 8 * 140 > 126e6 else
                             "per-GPU state %.0f MB: fits the 126 MB L2 (the configuration's batch is what BASELINE.json names)" % (B * 8 * 140 / 1e6)},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,

@@ -287,6 +287,15 @@ __ROKI_FD_EXPORT int rkFDBatchSetContactState(rkFD *fd, const int *active, const
 __ROKI_FD_EXPORT int rkFDBatchGetPivot(rkFD *fd, int *type, double *prev_trq);
 __ROKI_FD_EXPORT int rkFDBatchSetPivot(rkFD *fd, const int *type, const double *prev_trq);
 __ROKI_FD_EXPORT int rkFDBatchGetStatus(rkFD *fd, int *status);                 /* per env, bit0: non-finite acceleration */
+/* Environment re-sort.  The kernels address environments by slot (thread index) and environments never interact, so the
+ * engine re-orders the slots by the number of active contact vertices every `steps` steps (default 16 in worlds with
+ * contact pairs, RKFD_RESORT=<steps> overrides): warps then hold environments with the same amount of contact work.
+ * Results per environment do not depend on it and every host-side call maps through the order; only callers of
+ * rkFDBatchDevicePtr see slots: they read the order with rkFDBatchSlotMap (perm[slot] = environment of that shard, B
+ * entries) or switch the re-sort off (steps = 0: slot = environment). */
+__ROKI_FD_EXPORT int rkFDBatchSetResortInterval(rkFD *fd, int steps);
+__ROKI_FD_EXPORT int rkFDBatchSlotMap(rkFD *fd, int shard, int *perm);
+__ROKI_FD_EXPORT long long rkFDBatchResortCount(rkFD *fd);
 /* end-of-run statistics of the batch, reduced on the device; sums: out[0] environments, [1] environments with an active
  * contact, [2] active contact vertices, [3] environments with a non-zero status word; maxima: [4] |q''|, [5] |q'|;
  * [6..7] reserved (0).  A one-process-per-GPU job all-reduces [0..3] with SUM and [4..5] with MAX (SURVEY.md section 8e:

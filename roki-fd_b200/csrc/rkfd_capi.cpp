@@ -36,7 +36,7 @@ struct ChainImpl : ChainHost {
 struct FDImpl {
   std::vector<rkFDCell*> cells;          /* registration order */
   std::vector<ContactInfoHost> ci;
-  int B = 1; bool batch = false; std::vector<int> devices;
+  int B = 1; bool batch = false; std::vector<int> devices; int resort = -1;     /* -1: the engine's default */
   Engine *engine = nullptr;
   ModelDev model;
   std::vector<double> pend_q, pend_qd, pend_u;   /* batched initial state given before rkFDUpdateInit */
@@ -367,6 +367,7 @@ extern "C" void rkFDUpdateInit(rkFD *fd)
     /* static chains carry no joint state, so the device rows are the host offsets of relayout() */
     if( fi->model.nq != fd->size ) throw std::runtime_error("joint state layout mismatch between the host mirror and the device model");
     fi->engine = new Engine(fi->model, fi->B, fi->devices);
+    if( fi->resort >= 0 ) fi->engine->set_resort_interval(fi->resort);
     const int n = fd->size, nl = fi->model.nl, B = fi->B;
     /* initial state: the batched arrays when given, else the scalar state replicated over the envs */
     std::vector<double> q((size_t)B*n), qd((size_t)B*n), u((size_t)B*(nl > 0 ? nl : 1), 0.0);
@@ -472,6 +473,10 @@ extern "C" int rkFDBatchSetContactState(rkFD *fd, const int *a, const int *t, co
 extern "C" int rkFDBatchGetPivot(rkFD *fd, int *t, double *p){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->get_pivot(t, p)); }
 extern "C" int rkFDBatchSetPivot(rkFD *fd, const int *t, const double *p){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->set_pivot(t, p)); }
 extern "C" int rkFDBatchGetStatus(rkFD *fd, int *s){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->get_status(s)); }
+/* environment re-sort (rkfd_engine.cu): slots ordered by contact count every `steps` steps; 0 = never (slot = environment) */
+extern "C" int rkFDBatchSetResortInterval(rkFD *fd, int steps){ BATCH_GUARD(fd); if( steps < 0 ) return fail("steps must be >= 0"); fi->resort = steps; if( fi->engine ) fi->engine->set_resort_interval(steps); return 0; }
+extern "C" int rkFDBatchSlotMap(rkFD *fd, int shard, int *perm){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->slot_map(shard, perm)); }
+extern "C" long long rkFDBatchResortCount(rkFD *fd){ FDImpl *fi = FI(fd); return ( fi && fi->engine ) ? fi->engine->resorts() : 0; }
 /* end-of-run statistics of the whole batch, reduced on the device (what a multi-process job all-reduces) */
 extern "C" int rkFDBatchStats(rkFD *fd, double out[8]){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->stats(out)); }
 extern "C" int rkFDBatchEval(rkFD *fd, int ref){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->eval(ref != 0)); }

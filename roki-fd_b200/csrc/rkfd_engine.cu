@@ -44,31 +44,83 @@ constexpr int XP_THREADS = 256, XP_MAXCOL = 128;
 static inline int xp_te(int n){ int te = 64; while( te > 4 && (size_t)te*(n | 1)*sizeof(double) > 40*1024 ) te >>= 1; return te; }
 /* columns c0..c0+n-1 of env-major rows of length nrow (wide arrays - the 2,103 contact columns of mighty.ztk - go through in
  * column blocks of XP_MAXCOL) */
-__global__ void __launch_bounds__(XP_THREADS) rkfd_scatter_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE, int nrow, int c0)
+__global__ void __launch_bounds__(XP_THREADS) rkfd_scatter_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE, int nrow, int c0, const int * __restrict__ perm)
 {
   extern __shared__ double xp_tile[];
   const int e0 = blockIdx.x*XP_TE, ne = min(XP_TE, B - e0), ns = n | 1;
-  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; xp_tile[e*ns + k] = src[(size_t)(e0 + e)*nrow + c0 + k]; }
+  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; xp_tile[e*ns + k] = src[(size_t)(perm ? perm[e0 + e] : e0 + e)*nrow + c0 + k]; }
   __syncthreads();
   for(int i=threadIdx.x; i<n*XP_TE; i+=XP_THREADS){ const int k = i/XP_TE, e = i - k*XP_TE; if( e < ne ) dst[(size_t)(c0 + k)*ld + e0 + e] = xp_tile[e*ns + k]; }
 }
-__global__ void __launch_bounds__(XP_THREADS) rkfd_gather_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE, int nrow, int c0)
+__global__ void __launch_bounds__(XP_THREADS) rkfd_gather_kernel(const double * __restrict__ src, double * __restrict__ dst, int B, int n, int ld, int XP_TE, int nrow, int c0, const int * __restrict__ perm)
 {
   extern __shared__ double xp_tile[];
   const int e0 = blockIdx.x*XP_TE, ne = min(XP_TE, B - e0), ns = n | 1;
   for(int i=threadIdx.x; i<n*XP_TE; i+=XP_THREADS){ const int k = i/XP_TE, e = i - k*XP_TE; if( e < ne ) xp_tile[e*ns + k] = src[(size_t)(c0 + k)*ld + e0 + e]; }
   __syncthreads();
-  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; dst[(size_t)(e0 + e)*nrow + c0 + k] = xp_tile[e*ns + k]; }
+  for(int i=threadIdx.x; i<ne*n; i+=XP_THREADS){ const int e = i/n, k = i - e*n; dst[(size_t)(perm ? perm[e0 + e] : e0 + e)*nrow + c0 + k] = xp_tile[e*ns + k]; }
 }
-static void xp_scatter(const double *src, double *dst, int B, int n, int ld, cudaStream_t st)
+static void xp_scatter(const double *src, double *dst, int B, int n, int ld, cudaStream_t st, const int *perm)
 {
   for(int c0=0; c0<n; c0+=XP_MAXCOL){ const int nc = n - c0 < XP_MAXCOL ? n - c0 : XP_MAXCOL, te = xp_te(nc);
-    rkfd_scatter_kernel<<<(B + te - 1)/te, XP_THREADS, (size_t)te*(nc | 1)*sizeof(double), st>>>(src, dst, B, nc, ld, te, n, c0); }
+    rkfd_scatter_kernel<<<(B + te - 1)/te, XP_THREADS, (size_t)te*(nc | 1)*sizeof(double), st>>>(src, dst, B, nc, ld, te, n, c0, perm); }
 }
-static void xp_gather(const double *src, double *dst, int B, int n, int ld, cudaStream_t st)
+static void xp_gather(const double *src, double *dst, int B, int n, int ld, cudaStream_t st, const int *perm)
 {
   for(int c0=0; c0<n; c0+=XP_MAXCOL){ const int nc = n - c0 < XP_MAXCOL ? n - c0 : XP_MAXCOL, te = xp_te(nc);
-    rkfd_gather_kernel<<<(B + te - 1)/te, XP_THREADS, (size_t)te*(nc | 1)*sizeof(double), st>>>(src, dst, B, nc, ld, te, n, c0); }
+    rkfd_gather_kernel<<<(B + te - 1)/te, XP_THREADS, (size_t)te*(nc | 1)*sizeof(double), st>>>(src, dst, B, nc, ld, te, n, c0, perm); }
+}
+
+/* ---- environment re-sort ----------------------------------------------------------------------------------------
+ * Environments never interact and the kernels address them by SLOT (thread index), so the engine is free to choose which
+ * environment lives in which slot.  Every `resort interval` steps it orders the slots by the number of active contact
+ * vertices (descending): the 32 lanes of a warp then hold environments with the same amount of contact work - the penalty
+ * force code runs with full warps instead of 7 of 32 lanes, warps (and whole blocks) without contacts skip it and its
+ * barriers, and the rigid-contact solvers find their environments packed into few warps.  Results per environment do not
+ * depend on the slot (bit-identical).  perm[slot] = environment, inv[environment] = slot; the host-side API maps through
+ * them in the transposing copies. */
+constexpr int SORT_BINS = 64;
+__global__ void __launch_bounds__(256) rkfd_sort_key_kernel(const unsigned long long * __restrict__ cflags, int nfw, int ld, int B, unsigned char *key, int *bins)
+{
+  __shared__ int h[SORT_BINS];
+  if( threadIdx.x < SORT_BINS ) h[threadIdx.x] = 0;
+  __syncthreads();
+  const int sl = blockIdx.x*blockDim.x + threadIdx.x;
+  if( sl < B ){
+    int na = 0;
+    for(int w=0;w<nfw;w++) na += __popcll(cflags[(size_t)w*ld + sl] & 0x5555555555555555ull);
+    if( na > SORT_BINS-1 ) na = SORT_BINS-1;
+    key[sl] = (unsigned char)na; atomicAdd(&h[na], 1);
+  }
+  __syncthreads();
+  if( threadIdx.x < SORT_BINS && h[threadIdx.x] ) atomicAdd(&bins[threadIdx.x], h[threadIdx.x]);
+}
+/* first slot of every bin, most contacts first */
+__global__ void rkfd_sort_offsets_kernel(int *bins){ if( threadIdx.x == 0 ){ int run = 0; for(int k=SORT_BINS-1;k>=0;k--){ const int c = bins[k]; bins[k] = run; run += c; } } }
+__global__ void __launch_bounds__(256) rkfd_sort_assign_kernel(const unsigned char * __restrict__ key, int *cursor, int *newpos, int B)
+{
+  /* one atomic per (warp, bin): lanes with the same key take consecutive slots in lane order */
+  const int sl = blockIdx.x*blockDim.x + threadIdx.x; const unsigned lane = threadIdx.x & 31;
+  const int k = sl < B ? (int)key[sl] : -1;
+  const unsigned peers = __match_any_sync(0xffffffffu, k);
+  int base = 0;
+  if( k >= 0 && lane == (unsigned)(__ffs(peers) - 1) ) base = atomicAdd(&cursor[k], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+  if( k >= 0 ) newpos[sl] = base + __popc(peers & ((1u << lane) - 1u));
+}
+template <class T> __global__ void __launch_bounds__(256) rkfd_permute_rows_kernel(const T * __restrict__ src, T * __restrict__ dst, const int * __restrict__ newpos, int B, int nrows, int ld)
+{
+  const int sl = blockIdx.x*blockDim.x + threadIdx.x;
+  if( sl >= B ) return;
+  const int d = newpos[sl];
+  for(int r=0;r<nrows;r++) dst[(size_t)r*ld + d] = src[(size_t)r*ld + sl];
+}
+__global__ void __launch_bounds__(256) rkfd_perm_compose_kernel(const int * __restrict__ perm_old, const int * __restrict__ newpos, int *perm_new, int *inv_new, int B)
+{
+  const int sl = blockIdx.x*blockDim.x + threadIdx.x;
+  if( sl >= B ) return;
+  const int e = perm_old ? perm_old[sl] : sl, d = newpos[sl];
+  perm_new[d] = e; inv_new[e] = d;
 }
 
 /* rows k0..k0+n-1 of an SoA array <- one value per row, every environment (rkFDChainSetDis/SetVel and
@@ -156,6 +208,10 @@ struct Shard {
   double *ring[NRING] = {nullptr}; cudaEvent_t ring_done[NRING] = {nullptr}; cudaEvent_t ring_ready[NRING] = {nullptr};
   int ring_next = 0; bool ring_init = false;
   const KernelVariant *kv = nullptr; size_t smem = 0;
+  /* environment re-sort: perm[slot] = environment (nullptr: identity), host copies made on demand */
+  int *perm = nullptr, *inv = nullptr, *perm_buf[2] = {nullptr, nullptr}, *inv_buf = nullptr, *newpos = nullptr, *bins = nullptr; unsigned char *key = nullptr;
+  void *ptmp = nullptr; size_t ptmp_bytes = 0; int perm_cur = 0, steps_since_sort = 0; long long sorts = 0;
+  std::vector<int> h_perm; bool h_perm_valid = false;
   std::vector<void*> allocs;
 };
 
@@ -195,6 +251,11 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
   /* the same table with the tensor-memory scratch map, for the generic kernel variant that keeps its T space in TMEM */
   if( !model.has_rigid ) model_layout(model_tm_, true);
   if( B <= 0 ) throw std::runtime_error("rokifd_b200: environment count must be positive");
+  /* environment re-sort by contact count: every 16 steps when the world has contact pairs (RKFD_RESORT=<steps>, 0: never).
+   * Measured on one B200 over 256 settled steps, sorts included (tools/exp_resort.py): C3 0.538 ms per step without, 0.484 /
+   * 0.481 / 0.489 / 0.503 ms at 8 / 16 / 32 / 64; C5 MLCP 1.88 -> 1.42, C5 Vert 6.97 -> 5.09 at 16 */
+  resort_interval_ = model.npair > 0 ? 16 : 0;
+  if( const char *rs = std::getenv("RKFD_RESORT") ) resort_interval_ = std::atoi(rs);
   if( device_count() <= 0 ) throw std::runtime_error("rokifd_b200: no CUDA device (there is no CPU fallback)");
   std::vector<int> devs = devices;
   if( devs.empty() ){ int d = 0; CK(cudaGetDevice(&d)); devs.push_back(d); }
@@ -317,11 +378,61 @@ void Engine::launch(Shard &s, int mode, int nsteps)
   if( mode == 0 && (nsteps & 1) ) s.cur ^= 1;
 }
 
+static const std::vector<int> &host_perm(Shard &s)
+{
+  if( !s.h_perm_valid ){
+    s.h_perm.resize(s.B);
+    if( s.perm ){ CK(cudaStreamSynchronize(s.stream)); CK(cudaMemcpy(s.h_perm.data(), s.perm, (size_t)s.B*sizeof(int), cudaMemcpyDeviceToHost)); }
+    else for(int i=0;i<s.B;i++) s.h_perm[i] = i;
+    s.h_perm_valid = true;
+  }
+  return s.h_perm;
+}
+
+void Engine::resort(Shard &s)
+{
+  const int nq = model_.nq > 0 ? model_.nq : 1, nl = model_.nl > 0 ? model_.nl : 1, ns = model_.nslot > 0 ? model_.nslot : 1, nfw = model_.nfw > 0 ? model_.nfw : 1;
+  if( !s.newpos ){
+    s.newpos = dalloc<int>(s, s.ld); s.bins = dalloc<int>(s, SORT_BINS); s.key = dalloc<unsigned char>(s, s.ld);
+    s.perm_buf[0] = dalloc<int>(s, s.ld); s.perm_buf[1] = dalloc<int>(s, s.ld); s.inv_buf = dalloc<int>(s, s.ld);
+    size_t rows = (size_t)3*ns; if( (size_t)nq > rows ) rows = nq; if( (size_t)nl > rows ) rows = nl; if( (size_t)nfw > rows ) rows = nfw;
+    s.ptmp_bytes = rows*s.ld*sizeof(double); s.ptmp = dalloc<double>(s, rows*s.ld);
+    CK(cudaDeviceSynchronize());       /* dalloc's zero-fill runs on the legacy stream */
+  }
+  const int grid = (s.ld + 255)/256;
+  CK(cudaMemsetAsync(s.bins, 0, SORT_BINS*sizeof(int), s.stream));
+  rkfd_sort_key_kernel<<<grid, 256, 0, s.stream>>>(s.st.cflags, nfw, s.ld, s.B, s.key, s.bins);
+  rkfd_sort_offsets_kernel<<<1, 32, 0, s.stream>>>(s.bins);
+  rkfd_sort_assign_kernel<<<grid, 256, 0, s.stream>>>(s.key, s.bins, s.newpos, s.B);
+  CK(cudaGetLastError());
+  auto perm_rows = [&](void *base, size_t elem, int nrows){
+    if( !base || nrows <= 0 ) return;
+    const size_t bytes = (size_t)nrows*s.ld*elem;
+    /* the padding slots [B, ld) keep their (valid, zero-state) content */
+    CK(cudaMemcpyAsync(s.ptmp, base, bytes, cudaMemcpyDeviceToDevice, s.stream));
+    if( elem == 8 ) rkfd_permute_rows_kernel<unsigned long long><<<grid, 256, 0, s.stream>>>((const unsigned long long*)s.ptmp, (unsigned long long*)base, s.newpos, s.B, nrows, s.ld);
+    else rkfd_permute_rows_kernel<unsigned int><<<grid, 256, 0, s.stream>>>((const unsigned int*)s.ptmp, (unsigned int*)base, s.newpos, s.B, nrows, s.ld);
+    CK(cudaGetLastError());
+  };
+  StateDev &st = s.st;
+  perm_rows(st.q[s.cur], 8, nq); perm_rows(st.qd[s.cur], 8, nq); perm_rows(st.qdd, 8, nq); perm_rows(st.u, 8, nl);
+  perm_rows(st.piv_prev, 8, nq); perm_rows(st.piv_type, 4, 1); perm_rows(st.cflags, 8, nfw);
+  perm_rows(st.cref, 8, 3*ns); perm_rows(st.cf, 8, 3*ns); perm_rows(st.status, 4, 1);
+  int *pn = s.perm_buf[s.perm_cur ^ 1];
+  rkfd_perm_compose_kernel<<<grid, 256, 0, s.stream>>>(s.perm, s.newpos, pn, s.inv_buf, s.B);
+  CK(cudaGetLastError());
+  s.perm = pn; s.inv = s.inv_buf; s.perm_cur ^= 1; s.h_perm_valid = false; s.steps_since_sort = 0; s.sorts++;
+}
+
 void Engine::step(int nsteps)
 {
   if( nsteps <= 0 ) return;
   int prev = 0; CK(cudaGetDevice(&prev));
-  for(Shard *s : shards_) launch(*s, 0, nsteps);
+  for(Shard *s : shards_){
+    if( resort_interval_ > 0 && s->steps_since_sort >= resort_interval_ ){ CK(cudaSetDevice(s->dev)); resort(*s); }
+    s->steps_since_sort += nsteps;
+    launch(*s, 0, nsteps);
+  }
   CK(cudaSetDevice(prev));
 }
 void Engine::eval(bool ref)
@@ -346,6 +457,15 @@ void Engine::set_stream(void *stream)
   if( s->own_stream && s->stream ) CK(cudaStreamDestroy(s->stream));
   s->stream = (cudaStream_t)stream; s->own_stream = false;
 }
+void Engine::slot_map(int si, int *perm)
+{
+  if( si < 0 || si >= (int)shards_.size() ) return;
+  int prev = 0; CK(cudaGetDevice(&prev)); CK(cudaSetDevice(shards_[si]->dev));
+  const std::vector<int> &hp = host_perm(*shards_[si]);
+  for(int i=0;i<shards_[si]->B;i++) perm[i] = hp[i];
+  CK(cudaSetDevice(prev));
+}
+long long Engine::resorts() const { long long n = 0; for(const Shard *s : shards_) n += s->sorts; return n; }
 void *Engine::device_ptr(int si, int which, int *ld, int *B)
 {
   if( si < 0 || si >= (int)shards_.size() ) return nullptr;
@@ -359,13 +479,13 @@ static void h2d_scatter(Shard &s, const double *src, int n, double *dst)
 {
   if( n <= 0 ) return;
   CK(cudaMemcpyAsync(s.dstage, src + (size_t)s.e0*n, (size_t)s.B*n*sizeof(double), cudaMemcpyHostToDevice, s.stream));
-  xp_scatter(s.dstage, dst, s.B, n, s.ld, s.stream);
+  xp_scatter(s.dstage, dst, s.B, n, s.ld, s.stream, s.perm);
   CK(cudaGetLastError());
 }
 static void d2h_gather(Shard &s, const double *src, int n, double *dst)
 {
   if( n <= 0 ) return;
-  xp_gather(src, s.dstage, s.B, n, s.ld, s.stream);
+  xp_gather(src, s.dstage, s.B, n, s.ld, s.stream, s.perm);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(dst + (size_t)s.e0*n, s.dstage, (size_t)s.B*n*sizeof(double), cudaMemcpyDeviceToHost, s.stream));
 }
@@ -395,7 +515,7 @@ static void h2d_scatter_async(Shard &s, const double *src, int n, double *dst)
   CK(cudaMemcpyAsync(s.ring[b], src + (size_t)s.e0*n, (size_t)s.B*n*sizeof(double), cudaMemcpyHostToDevice, s.h2d_stream));
   CK(cudaEventRecord(s.ring_ready[b], s.h2d_stream));
   CK(cudaStreamWaitEvent(s.stream, s.ring_ready[b], 0));
-  xp_scatter(s.ring[b], dst, s.B, n, s.ld, s.stream);
+  xp_scatter(s.ring[b], dst, s.B, n, s.ld, s.stream, s.perm);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ring_done[b], s.stream));
 }
@@ -405,7 +525,7 @@ static void d2h_gather_async(Shard &s, const double *src, int n, double *dst)
   ring_setup(s);
   const int b = s.ring_next; s.ring_next = (b+1) % Shard::NRING;
   CK(cudaStreamWaitEvent(s.stream, s.ring_done[b], 0));
-  xp_gather(src, s.ring[b], s.B, n, s.ld, s.stream);
+  xp_gather(src, s.ring[b], s.B, n, s.ld, s.stream, s.perm);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ring_ready[b], s.stream));
   CK(cudaStreamWaitEvent(s.d2h_stream, s.ring_ready[b], 0));
@@ -529,7 +649,8 @@ void Engine::get_pivot(int *type, double *prev_trq)
     if( type ){
       std::vector<unsigned int> bits(s->B);
       CK(cudaMemcpy(bits.data(), s->st.piv_type, s->B*sizeof(unsigned int), cudaMemcpyDeviceToHost));
-      for(int e=0;e<s->B;e++) for(int j=0;j<nq;j++) type[(size_t)(s->e0+e)*nq + j] = (bits[e] >> j) & 1u;
+      const std::vector<int> &hp = host_perm(*s);
+      for(int sl=0;sl<s->B;sl++) for(int j=0;j<nq;j++) type[(size_t)(s->e0+hp[sl])*nq + j] = (bits[sl] >> j) & 1u;
     }
   }
   CK(cudaSetDevice(prev));
@@ -544,7 +665,8 @@ void Engine::set_pivot(const int *type, const double *prev_trq)
     CK(cudaStreamSynchronize(s->stream));
     if( type ){
       std::vector<unsigned int> bits(s->B, 0u);
-      for(int e=0;e<s->B;e++) for(int j=0;j<nq;j++) if( type[(size_t)(s->e0+e)*nq + j] ) bits[e] |= 1u << j;
+      const std::vector<int> &hp = host_perm(*s);
+      for(int sl=0;sl<s->B;sl++) for(int j=0;j<nq;j++) if( type[(size_t)(s->e0+hp[sl])*nq + j] ) bits[sl] |= 1u << j;
       CK(cudaMemcpy(s->st.piv_type, bits.data(), s->B*sizeof(unsigned int), cudaMemcpyHostToDevice));
     }
   }
@@ -563,10 +685,11 @@ void Engine::get_contact(int *active, int *type, double *ref, double *f)
       const int nfw = model_.nfw > 0 ? model_.nfw : 1;
       std::vector<unsigned long long> bits((size_t)nfw*s->ld);
       CK(cudaMemcpy(bits.data(), s->st.cflags, bits.size()*sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      const std::vector<int> &hp = host_perm(*s);
       /* slot (pair, vertex) -> flag position pair.fofs + vertex */
       for(int p=0;p<model_.npair;p++){ const PairDev &pr = model_.pair[p]; const int nv = model_.cell[pr.cell].nvert;
         for(int k=0;k<nv;k++){ const int f = pr.fofs + k, sl = pr.sofs + k;
-          for(int e=0;e<s->B;e++){ const unsigned long long wd = bits[(size_t)(f>>5)*s->ld + e];
+          for(int t=0;t<s->B;t++){ const unsigned long long wd = bits[(size_t)(f>>5)*s->ld + t]; const int e = hp[t];
             if( active ) active[(size_t)(s->e0+e)*ns + sl] = (int)((wd >> (2*(f&31))) & 1ull);
             if( type )   type[(size_t)(s->e0+e)*ns + sl]   = (int)((wd >> (2*(f&31)+1)) & 1ull); } } }
     }
@@ -584,9 +707,10 @@ void Engine::set_contact(const int *active, const int *type, const double *ref)
     if( active && type ){
       const int nfw = model_.nfw > 0 ? model_.nfw : 1;
       std::vector<unsigned long long> bits((size_t)nfw*s->ld, 0ull);
+      const std::vector<int> &hp = host_perm(*s);
       for(int p=0;p<model_.npair;p++){ const PairDev &pr = model_.pair[p]; const int nv = model_.cell[pr.cell].nvert;
         for(int k=0;k<nv;k++){ const int f = pr.fofs + k, sl = pr.sofs + k;
-          for(int e=0;e<s->B;e++){ unsigned long long &wd = bits[(size_t)(f>>5)*s->ld + e];
+          for(int t=0;t<s->B;t++){ unsigned long long &wd = bits[(size_t)(f>>5)*s->ld + t]; const int e = hp[t];
             if( active[(size_t)(s->e0+e)*ns + sl] ) wd |= 1ull << (2*(f&31));
             if( type[(size_t)(s->e0+e)*ns + sl] )   wd |= 2ull << (2*(f&31)); } } }
       CK(cudaMemcpy(s->st.cflags, bits.data(), bits.size()*sizeof(unsigned long long), cudaMemcpyHostToDevice));
@@ -599,7 +723,9 @@ void Engine::get_status(int *status)
   int prev = 0; CK(cudaGetDevice(&prev));
   for(Shard *s : shards_){
     CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->stream));
-    CK(cudaMemcpy(status + s->e0, s->st.status, s->B*sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> tmp(s->B); const std::vector<int> &hp = host_perm(*s);
+    CK(cudaMemcpy(tmp.data(), s->st.status, s->B*sizeof(int), cudaMemcpyDeviceToHost));
+    for(int sl=0;sl<s->B;sl++) status[s->e0 + hp[sl]] = tmp[sl];
   }
   CK(cudaSetDevice(prev));
 }

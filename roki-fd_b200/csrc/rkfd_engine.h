@@ -52,11 +52,19 @@ class Engine {
   void set_stream(void *cuda_stream);
   /* device pointers of shard `s` (SoA [k][ld], see StateDev): 0 q, 1 qd, 2 qdd, 3 u */
   void *device_ptr(int s, int which, int *ld, int *B);
+  /* environment re-sort (slots ordered by contact count every `steps` steps; 0: never - then slot = environment, which callers
+   * of device_ptr need).  slot_map: perm[slot] = environment of shard s (host copy, B entries) */
+  void set_resort_interval(int steps){ resort_interval_ = steps; }
+  int resort_interval() const { return resort_interval_; }
+  void slot_map(int s, int *perm);
+  long long resorts() const;
   long long launches() const { return launches_; }
 
  private:
   void upload_model(Shard &s);
   void launch(Shard &s, int mode, int nsteps);
+  void resort(Shard &s);
+  int resort_interval_ = 0;
   ModelDev model_, model_tm_;     /* model_tm_: the same table with the tensor-memory scratch map (generic TM kernel) */
   int B_;
   std::vector<Shard*> shards_;

@@ -713,3 +713,45 @@ def test_reference_model_files(capi, oracle, name, soft, solver):
         name, w.solver if not soft else "penalty", err.max(), (errq < 1e-7).sum(), B, errq.max()))
     assert (errq < 1e-7).mean() >= (1.0 if soft else 0.9)
     fd.destroy()
+
+
+@pytest.mark.parametrize("name", ["c3", "c5_mlcp", "arm_box_floor"])
+def test_environment_resort_is_invisible(capi, name):
+    """The engine re-orders its slots by contact count while stepping (rkFDBatchSetResortInterval): every host-side result -
+    state, accelerations, contact flags / anchors / forces, friction pivots, status - is bit-identical to a run without it,
+    also when state and motor inputs are written between the sorts."""
+    if name == "arm_box_floor":
+        from test_kernel_core_host import flat_world, flat_states
+        w, q0 = flat_world(name, soft=True)
+        B = 3000
+        q, qd, u = flat_states(name, w, q0, B)
+    else:
+        w = ch.world_c3(base_z=0.3) if name == "c3" else ch.world_c5(base_z=0.3, solver="MLCP")
+        B = 20000
+        q, qd, u = ch.sample_state(w, B, seed=11)
+    out = []
+    for interval in (0, 7):
+        fd, _ = capi.create_world(w, B=B)
+        fd.batch_set_resort_interval(interval)
+        fd.batch_set_state(q, qd); fd.batch_set_motor_input(u); fd.update_init()
+        for seg in range(6):
+            for _ in range(20):
+                fd.update()
+            if seg == 2:       # inputs written mid-run go to the right environments
+                u2 = u.copy(); u2[::3] *= -1.0
+                fd.batch_set_motor_input(u2)
+            if seg == 3:
+                gq, gqd, _ = fd.batch_get_state(); gq[::5] += 0.01
+                fd.batch_set_state(gq, gqd)
+        res = list(fd.batch_get_state()) + list(fd.batch_get_contact()) + list(fd.batch_get_pivot()) + [fd.batch_get_status()]
+        out.append((res, fd.resort_count))
+        fd.destroy()
+    assert out[0][1] == 0 and out[1][1] >= 10
+    a_act = out[0][0][3]
+    assert a_act.sum() > 0
+    for x, y in zip(out[0][0], out[1][0]):
+        if x.ndim == 3:            # anchors / forces: compared on active slots (inactive ones keep stale values)
+            m = (a_act == 1)[:, :, None]
+            assert np.array_equal(x * m, y * m)
+        else:
+            assert np.array_equal(x, y)
