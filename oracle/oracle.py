@@ -121,10 +121,20 @@ class OracleWorld:
         _, pi = _i(li)
         _, pd = _d(ld)
         self.h = L.ork_world_new(nl, pi, pd)
+        L.ork_world_add_link_box.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+        L.ork_world_unreg_self_collision.argtypes = [C.c_void_p, C.c_int]
         for k, l in enumerate(links):
-            for verts in l.shapes:
+            for verts in l.cells():
                 v, pv = _d(verts)
                 L.ork_world_add_cell(self.h, k, v.shape[0], pv)
+            for (ctr, d, w_, h_) in l.boxes:       # box primitives of a moving link: targets for other links' vertices
+                _, pR = _d(np.eye(3).reshape(9)); _, pp = _d(np.asarray(ctr, float)); _, ph = _d(np.array([d / 2, w_ / 2, h_ / 2]))
+                L.ork_world_add_link_box(self.h, k, pR, pp, ph)
+        base = 0
+        for chn in world.moving_chains():
+            if not chn.self_collide:
+                L.ork_world_unreg_self_collision(self.h, base)
+            base += len(chn.links)
         for b in world.boxes:
             _, pR = _d(np.asarray(b.R, float).reshape(9))
             _, pp = _d(b.p)

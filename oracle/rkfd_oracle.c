@@ -103,10 +103,11 @@ typedef struct {
 } ork_link;
 
 typedef struct { int link, nvert, vofs, volbox; } ork_cell;   /* volbox: the 8 corners of a parallelepiped in sign-bit order (Volume solver, A-15) */
-typedef struct { double R[9], p[3], half[3]; int stuff; } ork_box;
+/* link < 0: a static box, (R, p) its world frame; link >= 0: a box carried by that moving link, (R, p) its frame in the link */
+typedef struct { double R[9], p[3], half[3]; int stuff, link; } ork_box;
 typedef struct { int type; double K, L, E, V, SF, KF; } ork_cinfo;
 typedef struct { int sa, sb; ork_cinfo ci; } ork_cinfo_ent;
-typedef struct { int cell, box, sofs; ork_cinfo ci; } ork_pair;
+typedef struct { int cell, box, sofs; ork_cinfo ci; } ork_pair;    /* vertices of `cell` against `box` (static, or on another moving link) */
 
 struct ork_world {
   int nl, nq;
@@ -115,6 +116,7 @@ struct ork_world {
   int nbox; ork_box *box;
   int nci; ork_cinfo_ent *ci; ork_cinfo cidef;
   int npair, nslot; ork_pair *pair;
+  int *self_col;      /* per link: 1 when pairs between cells of ITS chain are registered (rkCDPairChainUnreg clears it) */
   double dt, friction_weight; int pyramid, max_iter, solver, integrator;
   double sc_table[2][64];   /* sin/cos pyramid table (rkfd_util.c:199-214) */
 };
@@ -184,6 +186,7 @@ ork_world *ork_world_new(int nl, const int *li, const double *ld)
 {
   ork_world *w = (ork_world*)calloc(1,sizeof *w); int i;
   w->nl = nl; w->link = (ork_link*)calloc(nl,sizeof(ork_link));
+  w->self_col = (int*)calloc(nl>0?nl:1,sizeof(int)); for(i=0;i<nl;i++) w->self_col[i] = 1;
   w->nq = 0;
   for(i=0;i<nl;i++){
     ork_link *l = &w->link[i]; const double *d = ld + ORK_LINK_ND*i;
@@ -203,7 +206,7 @@ ork_world *ork_world_new(int nl, const int *li, const double *ld)
 void ork_world_free(ork_world *w)
 {
   if(!w) return;
-  free(w->link); free(w->cell); free(w->vert); free(w->box); free(w->ci); free(w->pair); free(w);
+  free(w->link); free(w->cell); free(w->vert); free(w->box); free(w->ci); free(w->pair); free(w->self_col); free(w);
 }
 int ork_world_add_cell(ork_world *w, int link, int nvert, const double *verts)
 {
@@ -220,8 +223,24 @@ int ork_world_add_box(ork_world *w, const double *R, const double *p, const doub
   w->box = (ork_box*)realloc(w->box,(w->nbox+1)*sizeof(ork_box));
   b = &w->box[w->nbox];
   memcpy(b->R,R,9*sizeof(double)); memcpy(b->p,p,3*sizeof(double)); memcpy(b->half,half,3*sizeof(double));
-  b->stuff = stuff;
+  b->stuff = stuff; b->link = -1;
   return w->nbox++;
+}
+/* a box primitive on a moving link (frame in the link): a collision TARGET for the vertices of cells on other links; its own
+ * 8 corners are registered as a cell by the caller.  [EXT A-10] moving-vs-moving collision = vertex of one cell inside a box of
+ * another link (both directions when both carry boxes). */
+int ork_world_add_link_box(ork_world *w, int link, const double *R, const double *p, const double *half)
+{
+  int b = ork_world_add_box(w,R,p,half,w->link[link].stuff);
+  w->box[b].link = link;
+  return b;
+}
+/* [EXT] rkCDPairChainUnreg: drops the pairs between cells of the chain that `link` belongs to (registered by default) */
+void ork_world_unreg_self_collision(ork_world *w, int link)
+{
+  int i, r = link, ri;
+  while( w->link[r].parent >= 0 ) r = w->link[r].parent;
+  for(i=0;i<w->nl;i++){ ri = i; while( w->link[ri].parent >= 0 ) ri = w->link[ri].parent; if( ri == r ) w->self_col[i] = 0; }
 }
 void ork_world_add_contact_info(ork_world *w, int sa, int sb, int type,
                                 double K, double L, double E, double V, double SF, double KF)
@@ -279,16 +298,37 @@ void ork_world_finalize(ork_world *w)
    * fallback to the solver default (rkfd_sim.c:200-207, :266-271) */
   int c,b,k,sofs=0;
   if( w->solver == ORK_SOLVER_VOLUME ) for(c=0;c<w->ncell;c++) w->cell[c].volbox = w->cell[c].nvert == 8 && box_sign_bit_order(w->vert+3*w->cell[c].vofs);
-  free(w->pair); w->npair = w->ncell*w->nbox;
-  w->pair = (ork_pair*)calloc(w->npair>0?w->npair:1,sizeof(ork_pair));
-  k = 0;
-  for(c=0;c<w->ncell;c++) for(b=0;b<w->nbox;b++){
-    ork_pair *p = &w->pair[k++]; int i, sa = w->link[w->cell[c].link].stuff, sb = w->box[b].stuff;
-    p->cell=c; p->box=b; p->sofs=sofs; sofs += w->cell[c].nvert;
-    p->ci = w->cidef;
-    for(i=0;i<w->nci;i++)
-      if( (w->ci[i].sa==sa && w->ci[i].sb==sb) || (w->ci[i].sa==sb && w->ci[i].sb==sa) ){ p->ci = w->ci[i].ci; break; }
-  }
+  /* static pairs first (cell order x box order), then the pairs with boxes on moving links: cells of OTHER links - of other
+   * chains, and of the same chain while its self-collision pairs are registered ([EXT] rkCDPairChainUnreg) */
+  { int pass, n = 0;
+    free(w->pair); w->pair = NULL;
+    for(pass=0;pass<2;pass++){
+      k = 0;
+      for(c=0;c<w->ncell;c++) for(b=0;b<w->nbox;b++) if( w->box[b].link < 0 ){ if( pass ){ w->pair[k].cell = c; w->pair[k].box = b; } k++; }
+      for(c=0;c<w->ncell;c++) for(b=0;b<w->nbox;b++) if( w->box[b].link >= 0 ){
+        int la = w->cell[c].link, lb = w->box[b].link, ra = la, rb = lb;
+        if( la == lb ) continue;
+        while( w->link[ra].parent >= 0 ) ra = w->link[ra].parent;
+        while( w->link[rb].parent >= 0 ) rb = w->link[rb].parent;
+        if( ra == rb && !w->self_col[la] ) continue;
+        if( pass ){ w->pair[k].cell = c; w->pair[k].box = b; } k++; }
+      if( !pass ){ n = k; w->pair = (ork_pair*)calloc(n>0?n:1,sizeof(ork_pair)); }
+    }
+    w->npair = n; }
+  { int n = 0, dropped = 0;
+    for(k=0;k<w->npair;k++){
+      ork_pair p = w->pair[k]; int i, sa, sb;
+      c = p.cell; b = p.box; sa = w->link[w->cell[c].link].stuff; sb = w->box[b].stuff;
+      p.ci = w->cidef;
+      for(i=0;i<w->nci;i++)
+        if( (w->ci[i].sa==sa && w->ci[i].sb==sb) || (w->ci[i].sa==sb && w->ci[i].sb==sa) ){ p.ci = w->ci[i].ci; break; }
+      /* rigid contact between two MOVING links (A coupling two chains, rkfd_vert.c:125-151) is not restated: such pairs
+       * are not formed (the device side does the same and says so) */
+      if( w->box[b].link >= 0 && p.ci.type != ORK_CONTACT_ELASTIC ){ dropped++; continue; }
+      p.sofs = sofs; sofs += w->cell[c].nvert;
+      w->pair[n++] = p;
+    }
+    w->npair = n; (void)dropped; }
   w->nslot = sofs;
 }
 int ork_world_nq(const ork_world *w){ return w->nq; }
@@ -437,8 +477,13 @@ static void eval_collision(ork_env *e)
 {
   const ork_world *w = e->w; int pi, k, a;
   for(pi=0;pi<w->npair;pi++){
-    const ork_pair *p = &w->pair[pi]; const ork_cell *cl = &w->cell[p->cell]; const ork_box *bx = &w->box[p->box];
+    const ork_pair *p = &w->pair[pi]; const ork_cell *cl = &w->cell[p->cell]; const ork_box *bx0 = &w->box[p->box];
     const ork_lw *x = &e->lw[cl->link];
+    ork_box bw = *bx0; const ork_box *bx = &bw;
+    if( bx0->link >= 0 ){      /* a box on a moving link: its world frame of this evaluation */
+      const ork_lw *xb = &e->lw[bx0->link];
+      m3_mul(xb->Rw,bx0->R,bw.R); m3_mulv(xb->Rw,bx0->p,bw.p); v3_add(bw.p,xb->pw,bw.p);
+    }
     for(k=0;k<cl->nvert;k++){
       int s = p->sofs + k, amin = 0, inside = 1; double vw[3], vb[3], d[3], dep, depmin = 0, sg;
       double nb[3] = {0,0,0}, t1b[3] = {0,0,0}, t2b[3] = {0,0,0}, prob[3];
@@ -509,12 +554,15 @@ static void solver_penalty(ork_env *e, int do_up_ref)
       int s = p->sofs+k; double d[3], vr[3], *f = e->c_f+3*s;
       if( !e->c_active[s] ) continue;
       v3_sub(e->c_vert+3*s,e->c_refw+3*s,d);
-      link_point_wld_vel(&e->lw[cl->link],e->c_vert+3*s,vr);    /* rkFDChainPointRelativeVel, STAT partner = 0 */
+      link_point_wld_vel(&e->lw[cl->link],e->c_vert+3*s,vr);    /* rkFDChainPointRelativeVel (rkfd_util.c:42-60), STAT partner = 0 */
+      if( w->box[p->box].link >= 0 ){ double vb[3]; link_point_wld_vel(&e->lw[w->box[p->box].link],e->c_vert+3*s,vb); v3_sub(vr,vb,vr); }
       f[0] = -p->ci.E*d[0]; f[1] = -p->ci.E*d[1]; f[2] = -p->ci.E*d[2];
       v3_cat(f, -1.0*(p->ci.V + p->ci.E*w->dt), vr);
       if( v3_dot(f,e->c_axis+9*s) < 0.0 ) continue;
       modify_friction(e,&p->ci,s,vr,do_up_ref);
       push_wrench(e,cl->link,e->c_vert+3*s,f);
+      if( w->box[p->box].link >= 0 ){        /* the partner takes the opposite force at the same point (rkfd_util.c:276-278) */
+        double fr[3] = { -f[0], -f[1], -f[2] }; push_wrench(e,w->box[p->box].link,e->c_vert+3*s,fr); }
     }
   }
 }

@@ -61,6 +61,10 @@ void ork_world_add_contact_info(ork_world *w, int stuff_a, int stuff_b, int type
 void ork_world_set_prp(ork_world *w, double dt, int pyramid, double friction_weight, int max_iter);
 void ork_world_set_integrator(ork_world *w, int integrator);    /* 0 RKG (default), 1 RK4, 2 Euler, 3 Heun */
 void ork_world_set_solver(ork_world *w, int solver);
+/* a box carried by a moving link (frame in the link): a collision target for the vertices of cells on other links */
+int ork_world_add_link_box(ork_world *w, int link, const double *R, const double *p, const double *half);
+/* [EXT] rkCDPairChainUnreg: drops the pairs between cells of the chain `link` belongs to (registered by default) */
+void ork_world_unreg_self_collision(ork_world *w, int link);
 /* finish: builds (cell x box) pairs in registration order and associates contact info */
 void ork_world_finalize(ork_world *w);
 int ork_world_nq(const ork_world *w);       /* total joint size */

@@ -56,7 +56,7 @@ def lib():
         "rkFDCreate": (vp, [vp]), "rkFDDestroy": (None, [vp]),
         "rkChainInit": (vp, [vp]), "rkChainDestroy": (None, [vp]), "rkChainReadZTK": (vp, [vp, C.c_char_p]),
         "rkChainLinkNum": (ci, [vp]), "rkChainJointSize": (ci, [vp]), "rkChainLinkJoint": (vp, [vp, ci]),
-        "rkJointMotorSetInput": (None, [vp, _dp]), "rkJointGetDis": (None, [vp, _dp]), "rkJointGetVel": (None, [vp, _dp]),
+        "rkCDPairChainUnreg": (None, [vp, vp]), "rkJointMotorSetInput": (None, [vp, _dp]), "rkJointGetDis": (None, [vp, _dp]), "rkJointGetVel": (None, [vp, _dp]),
         "rkJointDOF": (ci, [vp]),
         "rkB200LinkDescInit": (None, [C.POINTER(LinkDesc)]), "rkChainB200SetName": (ci, [vp, C.c_char_p]),
         "rkChainB200AddLink": (ci, [vp, C.POINTER(LinkDesc)]), "rkChainB200LinkAddVerts": (ci, [vp, ci, ci, _dp]),
@@ -435,6 +435,9 @@ def create_world(world: World, B=None, devices=None):
     for ci in world.contact_info:
         fd.contact_info_add(ci)
     cells = [fd.chain_reg(ch) for ch in world.chains]
+    for chn, cell in zip(world.chains, cells):
+        if not getattr(chn, "self_collide", False):        # as every example program of the reference does
+            lib().rkCDPairChainUnreg(None, cell.chain_handle)
     fd.prp_set(world.dt, world.pyramid, world.friction_weight, world.max_iter)
     fd.set_solver(world.solver)
     fd.set_integrator(getattr(world, "integrator", "RKG"))

@@ -66,14 +66,22 @@ class Link:
     sfriction: float = 0.0
     motor: Optional[Motor] = None
     shapes: List[np.ndarray] = field(default_factory=list)   # vertex clouds (n x 3, link frame)
-    # static links only: boxes as (center(3), depth, width, height) in the link frame
+    # box primitives as (center(3), depth, width, height) in the link frame.  On a static link: a collision target.  On a
+    # moving link: a target for the vertices of OTHER links' cells, and its 8 corners are a cell of this link (after `shapes`)
     boxes: List[tuple] = field(default_factory=list)
+
+    def cells(self):
+        """Vertex clouds of a moving link in cell order: the shapes, then the corners of its box primitives."""
+        return list(self.shapes) + [box_verts(d, w, h, center=c) for (c, d, w, h) in self.boxes]
 
 
 @dataclass
 class ChainModel:
     name: str
     links: List[Link]
+    # pairs between the cells of this chain itself: the reference registers them until rkCDPairChainUnreg (every example
+    # program calls it); worlds built here default to the unregistered state
+    self_collide: bool = False
 
     @property
     def joint_size(self):
@@ -167,10 +175,30 @@ class World:
     def nl(self):
         return sum(len(c.links) for c in self.moving_chains())
 
+    def _ci_type(self, sa, sb):
+        for ci in self.contact_info:
+            if (ci.stuff_a, ci.stuff_b) in ((sa, sb), (sb, sa)):
+                return ci.type
+        return "rigid"                     # every solver's default contact info is rigid
+
     @property
     def nslot(self):
-        nv = sum(v.shape[0] for l in self.flat_links() for v in l.shapes)
-        return nv * len(self.boxes)
+        """Contact slots = sum over pairs of the cell's vertices: every cell of a moving link against every static box, and
+        against the box primitives of other moving links (other chains; the same chain only with `self_collide`; elastic
+        contact info only) - the rule of rkfd_model.cpp / the oracle's ork_world_finalize."""
+        links = self.flat_links()
+        n = sum(v.shape[0] for l in links for v in l.cells()) * len(self.boxes)
+        chain_of, self_col = [], []
+        for ci, chn in enumerate(self.moving_chains()):
+            chain_of += [ci] * len(chn.links); self_col.append(chn.self_collide)
+        for a, la in enumerate(links):
+            for b, lb in enumerate(links):
+                if a == b or not lb.boxes or (chain_of[a] == chain_of[b] and not self_col[chain_of[a]]):
+                    continue
+                if self._ci_type(la.stuff, lb.stuff) != "elastic":
+                    continue
+                n += sum(v.shape[0] for v in la.cells()) * len(lb.boxes)
+        return n
 
 
 def world_from_flat(desc):

@@ -113,8 +113,9 @@ extern "C" void rkJointMotorSetInput(rkJoint *j, double *val)
     catch(const std::exception &ex){ complain("rkJointMotorSetInput", ex.what()); }
   }
 }
-/* self-collision pairs of a chain: this engine only forms (moving cell x static box) pairs, so there is nothing to drop */
-extern "C" void rkCDPairChainUnreg(rkCD *cd, rkChain *chain){ (void)cd; (void)chain; }
+/* [EXT] RoKi rk_cd: drops the collision pairs between the cells of `chain` itself (registered by default, as in the reference:
+ * example/chain/boxdrop_test.c:37, arm_box_test.c:49).  Pairs are formed in rkFDUpdateInit: call it before. */
+extern "C" void rkCDPairChainUnreg(rkCD *cd, rkChain *chain){ (void)cd; if( CI(chain) ) CI(chain)->self_collide = false; }
 
 extern "C" void rkB200LinkDescInit(rkB200LinkDesc *d)
 {

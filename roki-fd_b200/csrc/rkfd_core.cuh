@@ -238,7 +238,7 @@ struct SpecSerialRevRolled {
   static RKFD_HD int sc(int i, const LinkDev &){ return RG_ ? PER*i + 9 : 4*(i-1); }
 };
 inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0, int GEN = 0){
-  if( m.nfw > 1 ) return false;
+  if( m.nfw > 1 || m.npair > m.npair_static ) return false;
   if( RG ? !( m.has_rigid && m.nrg == 1 && m.rigid_link == NL-1 ) : m.has_rigid ) return false;
   if( m.nl != NL || NL < 2 ) return false;
   for(int i=0;i<NL;i++){
@@ -253,7 +253,7 @@ inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0, 
 
 /* does the flattened model have the shape SpecSerialRev<.,NL,CLS> assumes? (host side) */
 inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
-  if( m.has_rigid || m.nl != NL || NL < 2 || m.nfw > 1 ) return false;
+  if( m.has_rigid || m.nl != NL || NL < 2 || m.nfw > 1 || m.npair > m.npair_static ) return false;
   for(int i=0;i<NL;i++){
     const LinkDev &L = m.link[i];
     if( i == 0 ){ if( L.parent >= 0 || L.jtype != J_FIXED || L.cell_end > L.cell_begin ) return false; continue; }
@@ -534,6 +534,71 @@ struct Core {
       }
     }
     return w;
+  }
+
+  /* ---- contacts between two MOVING links ([EXT A-10] extended: the vertices of a cell against a box primitive carried by
+   * another link; reference: rkFDChainPointRelativeVel rkfd_util.c:42-60 - the velocity of the vertex's link minus the box
+   * link's at the contact point - and rkFDContactForcePushWrench rkfd_util.c:268-282 - the force on the vertex's link, its
+   * opposite on the partner, both at the contact point).  Runs after pass 1, when every link frame of the evaluation is known
+   * (frame slots of the links involved).  Elastic pairs (rkFDSolverPenalty, rkfd_penalty.c:11-31); generic kernel only. */
+  RKFD_HD void contacts_moving(const ModelDev &m, bool ref){
+    for(int pi=m.npair_static; pi<m.npair; pi++){
+      const PairDev &pr = m.pair[pi]; const CellDev &cl = m.cell[pr.cell]; const MBoxDev &mb = m.mbox[pr.mbox];
+      const LinkDev &LA = m.link[cl.link], &LB = m.link[mb.link];
+      const int fa = Spec::frame_slot(cl.link, LA), fb = Spec::frame_slot(mb.link, LB), wa = Spec::wext_slot(cl.link, LA), wb = Spec::wext_slot(mb.link, LB);
+      const M3 Rw = ldm(fa); const V3 pw = ld3(fa+9);
+      const M3 RwB = ldm(fb); const V3 pwB = ld3(fb+9);
+      M3 Rl; Rl.xx=mb.R[0]; Rl.xy=mb.R[1]; Rl.xz=mb.R[2]; Rl.yx=mb.R[3]; Rl.yy=mb.R[4]; Rl.yz=mb.R[5]; Rl.zx=mb.R[6]; Rl.zy=mb.R[7]; Rl.zz=mb.R[8];
+      const M3 Rb = mm(RwB, Rl); const V3 pb = pwB + mul(RwB, v3(mb.p[0], mb.p[1], mb.p[2]));
+      BoxDev bx; for(int i=0;i<3;i++) bx.half[i] = mb.half[i];
+      const V3 vlw = mul(Rw, ld3(fa+12)), omw = mul(Rw, ld3(fa+15)), vlwB = mul(RwB, ld3(fb+12)), omwB = mul(RwB, ld3(fb+15));
+      V6 wA, wB; wA.l = wA.a = wB.l = wB.a = v3(0,0,0);
+      for(int c0=0; c0<cl.nvert; c0+=32){
+        const int nvc = cl.nvert - c0 < 32 ? cl.nvert - c0 : 32, sh = (pr.fofs + c0) & 31;
+        flag_select((pr.fofs + c0) >> 5);
+        unsigned in = 0;
+        for(int k=0;k<nvc;k++){
+          const int s = pr.sofs + c0 + k, vi = cl.vofs + c0 + k;
+          const V3 vb = tmul(Rb, pw + mul(Rw, v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2])) - pb);
+          const bool inside = (bx.half[0]-fabs(vb.x) > -ZTOL) && (bx.half[1]-fabs(vb.y) > -ZTOL) && (bx.half[2]-fabs(vb.z) > -ZTOL);
+          if( inside ) in |= 1u << k;
+          else { cfl &= ~(3ull << (2*(sh+k))); if( ref ){ c.gst(c.st.cf, 3*s, 0.0); c.gst(c.st.cf, 3*s+1, 0.0); c.gst(c.st.cf, 3*s+2, 0.0); } }
+        }
+        while( c.any(in != 0) ){
+          if( in == 0 ) continue;
+          const int k = RKFD_FFS32(in) - 1; in &= in - 1;
+          const int s = pr.sofs + c0 + k, vi = cl.vofs + c0 + k;
+          const unsigned long long abit = 1ull << (2*(sh+k)), kbit = 2ull << (2*(sh+k));
+          const V3 vw = pw + mul(Rw, v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2]));
+          const V3 vb = tmul(Rb, vw - pb);
+          V3 n, t1, t2, prob;
+          box_face(bx, Rb, vb, bx.half[0]-fabs(vb.x), bx.half[1]-fabs(vb.y), bx.half[2]-fabs(vb.z), n, t1, t2, prob);
+          V3 refb;
+          if( !(cfl & abit) ){ cfl = (cfl | abit) & ~kbit; refb = prob;
+            c.gst(c.st.cref, 3*s, refb.x); c.gst(c.st.cref, 3*s+1, refb.y); c.gst(c.st.cref, 3*s+2, refb.z);
+          } else refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
+          const V3 d = vw - (pb + mul(Rb, refb));
+          const V3 vr = (vlw + cross(omw, vw - pw)) - (vlwB + cross(omwB, vw - pwB));
+          V3 f = (-pr.E)*d + (-1.0*(pr.V + pr.E*m.dt))*vr;
+          if( dot(f,n) < 0.0 ){ if( ref ){ c.gst(c.st.cf,3*s,f.x); c.gst(c.st.cf,3*s+1,f.y); c.gst(c.st.cf,3*s+2,f.z); } continue; }
+          const double fn = dot(f,n), f1 = dot(f,t1), f2 = dot(f,t2);
+          const double fs = sqrt(f1*f1 + f2*f2);
+          const double mu = (cfl & kbit) ? pr.KF : pr.SF;
+          if( !(fabs(fs) < ZTOL) && fs > mu*fn ){
+            V3 v = vr + (-dot(vr,n))*n;
+            const double vs = norm(v);
+            f = fn*n;
+            if( !(fabs(vs) < ZTOL) ) f = f + ((-(1.0 - exp(-1.0*m.friction_weight*vs))*pr.KF*fn)/vs)*v;
+            if( ref ){ cfl |= kbit; c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
+          } else if( ref ) cfl &= ~kbit;
+          { const V3 pos = tmul(Rw, vw - pw), fl = tmul(Rw, f); wA.l = wA.l + fl; wA.a = wA.a + cross(pos, fl); }
+          { const V3 pos = tmul(RwB, vw - pwB), fl = tmul(RwB, v3(-f.x, -f.y, -f.z)); wB.l = wB.l + fl; wB.a = wB.a + cross(pos, fl); }
+          if( ref ){ c.gst(c.st.cf,3*s,f.x); c.gst(c.st.cf,3*s+1,f.y); c.gst(c.st.cf,3*s+2,f.z); }
+        }
+      }
+      c.S(wa) += wA.l.x; c.S(wa+1) += wA.l.y; c.S(wa+2) += wA.l.z; c.S(wa+3) += wA.a.x; c.S(wa+4) += wA.a.y; c.S(wa+5) += wA.a.z;
+      c.S(wb) += wB.l.x; c.S(wb+1) += wB.l.y; c.S(wb+2) += wB.l.z; c.S(wb+3) += wB.a.x; c.S(wb+4) += wB.a.y; c.S(wb+5) += wB.a.z;
+    }
   }
 
   /* ---- pass 1: outward kinematics + collision + penalty */
@@ -1910,6 +1975,7 @@ struct Core {
     c.phase_sync(1);
     c.tfence();               /* T-space stores of the previous pass are complete before this pass loads them */
     pass1(m, ref, stage == ST_K1 || stage >= ST_EVAL);
+    if constexpr ( Spec::NL == 0 ){ if( m.npair > m.npair_static ) contacts_moving(m, ref); }
     c.phase_sync(2);
     c.tfence();
     if( Ctx::RIGID ){

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 #include "rkfd_core.cuh"
@@ -38,8 +39,8 @@ void model_layout(ModelDev &m, bool tm)
       LinkDev &p = m.link[d.parent];
       if( p.branch_slot < 0 ){ p.branch_slot = slot; slot += BRANCH_SLOTS; p.accum_slot = slot; slot += ACCUM_SLOTS; }
     }
-    if( d.cell_end > d.cell_begin ){ d.wext_slot = slot; slot += WEXT_SLOTS;
-      if( m.has_rigid ){ d.frame_slot = slot; slot += FRAME_SLOTS; } }
+    if( d.cell_end > d.cell_begin || d.mcol ){ d.wext_slot = slot; slot += WEXT_SLOTS;
+      if( m.has_rigid || d.mcol ){ d.frame_slot = slot; slot += FRAME_SLOTS; } }
   }
   if( tm ){ m.rk_slot = t; t += 4*nq; m.ntspace = t; }
   else { m.rk_slot = slot; slot += 4*nq; m.ntspace = 0; }
@@ -80,7 +81,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
     for(int i=0;i<w.pyramid;i++, th+=dth){ m.sc_sin[i] = std::sin(th+off); m.sc_cos[i] = std::cos(th+off); }
   }
 
-  std::vector<std::string> link_stuff;
+  std::vector<std::string> link_stuff; std::vector<int> link_chain; std::vector<bool> chain_self;
   struct StatBox { BoxDev b; std::string stuff; };
   std::vector<StatBox> boxes;
 
@@ -109,6 +110,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
       continue;
     }
     const int base = nl;
+    chain_self.push_back(ch->self_collide);
     for(size_t i=0;i<ch->links.size();i++){
       const LinkHost &l = ch->links[i];
       if( nl >= MAX_LINKS ){ err = "too many links (MAX_LINKS)"; return false; }
@@ -151,7 +153,12 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
         std::memcpy(m.vert + 3*m.nvert, sh.data(), 3*nv*sizeof(double)); m.nvert += nv;
       }
       d.cell_end = m.ncell;
-      link_stuff.push_back(l.stuff);
+      for(const BoxShape &bs : l.boxes){         /* box primitives of a moving link: targets */
+        if( m.nmbox >= MAX_MBOXES ){ err = "too many boxes on moving links (MAX_MBOXES)"; return false; }
+        MBoxDev &mb = m.mbox[m.nmbox++]; std::memcpy(mb.R, bs.R, sizeof mb.R); std::memcpy(mb.p, bs.center, sizeof mb.p);
+        mb.half[0] = 0.5*bs.depth; mb.half[1] = 0.5*bs.width; mb.half[2] = 0.5*bs.height; mb.link = nl;
+      }
+      link_stuff.push_back(l.stuff); link_chain.push_back((int)chain_self.size() - 1);
       nl++;
     }
   }
@@ -177,9 +184,31 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
     }
     m.cell[c].pair_end = m.npair;
   }
-  m.nslot = sofs;
-  if( m.nslot > MAX_SLOTS ){ err = "too many contact slots (MAX_SLOTS)"; return false; }
-  /* flag positions: one word when everything fits 32 slots (position = slot), else whole words per pair */
+  for(int p=0;p<m.npair;p++) m.pair[p].mbox = -1;
+  m.npair_static = m.npair;
+  /* ---- moving-vs-moving pairs ([EXT A-10]: vertices of a cell against a box primitive carried by ANOTHER link - of another
+   * chain, or of the same chain while its self-collision pairs are registered, rkCDPairChainUnreg).  Elastic contact info
+   * only: rigid contact between two moving links (A coupling two chains, rkfd_vert.c:125-151) is not built; such pairs
+   * are left out and reported. */
+  { int dropped = 0;
+    for(int c=0;c<m.ncell;c++) for(int b=0;b<m.nmbox;b++){
+      const int la = m.cell[c].link, lb = m.mbox[b].link;
+      if( la == lb ) continue;
+      if( link_chain[la] == link_chain[lb] && !chain_self[link_chain[la]] ) continue;
+      const ContactInfoHost *ci = &w.cidef;
+      const std::string &sa = link_stuff[la], &sb = link_stuff[lb];
+      for(const auto &e : w.ci) if( (e.a==sa && e.b==sb) || (e.a==sb && e.b==sa) ){ ci = &e; break; }
+      if( ci->type != C_ELASTIC ){ dropped++; continue; }
+      if( m.npair >= MAX_PAIRS ){ err = "too many contact pairs (MAX_PAIRS)"; return false; }
+      PairDev &p = m.pair[m.npair++];
+      p.cell = c; p.box = -1; p.mbox = b; p.sofs = sofs; sofs += m.cell[c].nvert;
+      p.type = ci->type; p.K = ci->K; p.L = ci->L; p.E = ci->E; p.V = ci->V; p.SF = ci->SF; p.KF = ci->KF;
+      m.has_elastic = 1; m.link[la].mcol = 1; m.link[lb].mcol = 1;
+    }
+    if( dropped ) std::fprintf(stderr, "rokifd_b200: %d pair(s) of cells on two MOVING links have rigid contact info: not formed (moving-vs-moving "
+                                       "contact is built for elastic contact info only)\n", dropped);
+  }
+  m.nslot = sofs;  /* flag positions: one word when everything fits 32 slots (position = slot), else whole words per pair */
   if( m.nslot <= 32 ){ for(int p=0;p<m.npair;p++) m.pair[p].fofs = m.pair[p].sofs; m.nfw = 1; }
   else { int fo = 0; for(int p=0;p<m.npair;p++){ m.pair[p].fofs = fo; fo += (m.cell[m.pair[p].cell].nvert + 31) & ~31; } m.nfw = fo/32; }
   if( m.nfw > MAX_FWORDS ){ err = "too many contact flag words (MAX_FWORDS)"; return false; }

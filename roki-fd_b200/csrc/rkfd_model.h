@@ -42,6 +42,7 @@ struct ChainHost {
   std::vector<LinkHost> links;
   /* scalar-API mirror of the joint values ([EXT] rkJointGetDis/GetVel/MotorSetInput) */
   std::vector<double> dis, vel, acc, motor_in;
+  bool self_collide = true;      /* pairs between the cells of this chain are registered until rkCDPairChainUnreg ([EXT] RoKi rk_cd) */
   int joint_size() const { int n = 0; for(auto &l : links) n += jtype_ndof(l.jtype); return n; }
   bool is_static() const { return joint_size() == 0; }
   int link_qofs(int i) const { int n = 0; for(int k=0;k<i;k++) n += jtype_ndof(links[k].jtype); return n; }

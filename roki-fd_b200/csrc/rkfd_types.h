@@ -20,6 +20,7 @@ constexpr int MAX_LINKS = 32;
 constexpr int MAX_CELLS = 32;
 constexpr int MAX_VERTS = 768;
 constexpr int MAX_BOXES = 8;
+constexpr int MAX_MBOXES = 16;     /* box primitives on moving links: collision targets for the vertices of other links' cells */
 constexpr int MAX_PAIRS = 64;
 constexpr int MAX_SLOTS = 1024;    /* contact slots per env = sum over (cell, box) pairs of the cell's vertices */
 /* Contact flags: 2 bits per slot (active, kinetic) in 64-bit words of 32 slots.  Worlds with at most 32 slots keep them in
@@ -66,15 +67,21 @@ struct LinkDev {
   int wext_slot;       /* >=0: slots of the external wrench (6) (links that carry collision cells) */
   int frame_slot;      /* >=0 (worlds with rigid pairs, links with cells): Rw(9) pw(3) vl(3) w(3) a(6) = 24 slots */
   int cell_begin, cell_end;
+  int mcol, pad_;      /* 1: a cell or a box of this link takes part in a moving-vs-moving pair (frame + wrench slots) */
 };
 
 struct CellDev { int link, vofs, nvert, pair_begin, pair_end; };
 struct BoxDev { double R[9], p[3], half[3]; };
-struct PairDev { int cell, box, sofs, type; double K, L, E, V, SF, KF; int fofs, volbox; };   /* fofs: flag position of vertex 0 (word fofs>>5, bit pair fofs&31); volbox: the cell has the 8 corners of a box in sign-bit order (Volume solver) */
+struct MBoxDev { double R[9], p[3], half[3]; int link, pad_; };      /* frame in the carrying link */
+struct PairDev { int cell, box, sofs, type; double K, L, E, V, SF, KF; int fofs, volbox; int mbox, pad_; };   /* fofs: flag position of vertex 0 (word fofs>>5, bit pair fofs&31); volbox: the cell has the 8 corners of a box in sign-bit order (Volume solver);
+                                 * mbox >= 0: the target is box `mbox` on a moving link (then box = -1): elastic pairs only */
 
 struct ModelDev {
   int nl, nq, ncell, nbox, npair, nslot, nvert;
   int nfw;             /* contact flag words per environment */
+  int npair_static;    /* pairs [0, npair_static): against static boxes (walked link by link in pass 1); the rest: against boxes on
+                          moving links (walked after pass 1, Core::contacts_moving) */
+  int nmbox;
   int need_world;      /* any collision cell: world frames must be propagated */
   int has_rigid, has_elastic;
   int solver, pyramid, max_iter;
@@ -99,6 +106,7 @@ struct ModelDev {
   LinkDev link[MAX_LINKS];
   CellDev cell[MAX_CELLS];
   BoxDev box[MAX_BOXES];
+  MBoxDev mbox[MAX_MBOXES];
   PairDev pair[MAX_PAIRS];
   double vert[3 * MAX_VERTS];
 };

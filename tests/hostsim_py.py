@@ -65,12 +65,16 @@ class HostSim:
         self.h = L.hostsim_new(len(nls), nls.ctypes.data_as(_ip), li.ctypes.data_as(_ip), ld.ctypes.data_as(_dp))
         for c, chn in enumerate(world.chains):
             for k, l in enumerate(chn.links):
-                for v in l.shapes:
+                for v in (l.cells() if not chn.is_static else l.shapes):
                     v, pv = _d(v)
                     L.hostsim_add_cell(self.h, c, k, v.shape[0], pv)
                 for (ctr, d, w, ht) in l.boxes:
                     _, pc = _d(ctr)
                     L.hostsim_add_box(self.h, c, k, pc, d, w, ht)
+        L.hostsim_unreg_self_collision.argtypes = [C.c_void_p, C.c_int]
+        for c, chn in enumerate(world.chains):
+            if not chn.self_collide:
+                L.hostsim_unreg_self_collision(self.h, c)
         for ci in world.contact_info:
             L.hostsim_add_contact_info(self.h, world.stuff_id(ci.stuff_a), world.stuff_id(ci.stuff_b),
                                        CONTACT[ci.type], ci.K, ci.L, ci.E, ci.V, ci.SF, ci.KF)

@@ -755,3 +755,29 @@ def test_environment_resort_is_invisible(capi, name):
             assert np.array_equal(x * m, y * m)
         else:
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("kind", ["box_stack", "arm_pushes_box"])
+def test_moving_vs_moving_contact(capi, oracle, kind):
+    """cells of two MOVING links in contact (vertices of one against a box primitive of the other,
+    relative velocity of both links rkfd_util.c:42-60, force on one and its opposite on the other rkfd_util.c:268-282):
+    three free boxes landing on each other (example/chain/boxdrop_test.c) and an arm pushing a free box
+    (example/chain/arm_box_test.c), penalty contact, 200 free-running steps against the oracle."""
+    from test_kernel_core_host import mm_world, mm_states
+    w = mm_world(kind)
+    B = 512
+    q, qd, u = mm_states(kind, w, B)
+    fd = gpu_world(capi, w, q, qd, u)
+    assert fd.slot_num == w.nslot
+    fd.update_n(200)
+    gq, gqd, _ = fd.batch_get_state()
+    a, t, r, f = fd.batch_get_contact()
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=200)
+    nstat = sum(v.shape[0] for l in w.flat_links() for v in l.cells()) * len(w.boxes)
+    assert (fd.batch_get_status() == 0).all()
+    err = np.abs(gq - o[0]).max(1) / np.abs(o[0]).max(1)
+    same = (a == o[3]).all(1)
+    print("moving-vs-moving %s: %d/%d envs within 1e-8 after 200 steps (max %.2e), contact flags equal in %d, moving-pair contacts at the end: %d" % (
+        kind, (err < 1e-8).sum(), B, err.max(), same.sum(), o[3][:, nstat:].sum()))
+    assert (err < 1e-8).mean() >= 0.99 and same.mean() >= 0.99
+    fd.destroy()

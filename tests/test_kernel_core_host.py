@@ -545,3 +545,86 @@ def test_reference_models_step_like_the_oracle(oracle, name, soft):
     oq = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=20)[0]
     errq = np.abs(hq - oq).max(1) / np.abs(oq).max(1)
     assert (errq < 1e-7).mean() >= (1.0 if soft else 0.9), errq      # Volume: a mode flip at a zTOL-sized margin may split a trajectory
+
+
+# ---- moving-vs-moving collision: vertices of a cell against a box carried by another link ----------
+def mm_box(name, stuff="body"):
+    """box.ztk as a `type: box` shape: 8 collision vertices AND a box target for other bodies' vertices."""
+    return ch.ChainModel(name, [ch.Link(name="link#00", jtype="float", mass=0.5, stuff=stuff, inertia=np.eye(3) * 8.33e-4,
+                                        boxes=[((0.0, 0.0, 0.0), 0.1, 0.1, 0.1)])])
+
+
+MM_CI = [ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0, SF=0.5, KF=0.3),
+         ch.ContactInfo("body", "body", "elastic", E=2000.0, V=20.0, SF=0.5, KF=0.3)]
+
+
+def mm_world(kind):
+    if kind == "box_stack":          # example/chain/boxdrop_test.c: boxes landing on each other (self pairs unregistered)
+        return ch.World(chains=[mm_box("a"), mm_box("b"), mm_box("c"), ch.floor_soft()], contact_info=MM_CI)
+    arm = ch.arm_2dof()              # example/chain/arm_box_test.c: the arm pushes a free box lying on the floor
+    arm.links[2].boxes = [((0.2, 0.0, 0.0), 0.3, 0.1, 0.1)]
+    return ch.World(chains=[arm, mm_box("box"), ch.floor_soft()], contact_info=MM_CI)
+
+
+def mm_states(kind, w, B, seed=0):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((B, w.nq)); qd = np.zeros((B, w.nq)); u = np.zeros((B, w.nl))
+    if kind == "box_stack":
+        for k in range(3):
+            o = 6 * k
+            q[:, o:o + 2] = rng.uniform(-0.02, 0.02, (B, 2)); q[:, o + 2] = 0.05 + 0.105 * k + rng.uniform(0.0, 0.01, B)
+            q[:, o + 3:o + 6] = rng.uniform(-0.1, 0.1, (B, 3)); qd[:, o:o + 6] = rng.uniform(-0.2, 0.2, (B, 6))
+    else:
+        q[:, 0] = rng.uniform(-0.3, 0.3, B); q[:, 1] = rng.uniform(-0.3, 0.3, B); qd[:, :2] = rng.uniform(-1, 1, (B, 2))
+        # the free box starts in the path of the forearm's box primitive (link 2, centre (0.2, 0, 0) in its frame)
+        from oracle import oracle as orc
+        ow = orc.OracleWorld(w)
+        for b in range(B):
+            e = ow.env(); e.set_state(q[b], qd[b]); e.eval(False)
+            Rs, ps = e.link_frames(); R, p = Rs[2], ps[2]
+            q[b, 2:5] = p + R @ np.array([0.2, 0.0, 0.0]) + R @ np.array([0.0, 0.09, 0.0]) + rng.uniform(-0.005, 0.005, 3)
+        q[:, 5:8] = rng.uniform(-0.2, 0.2, (B, 3))
+        u[:, 1:3] = rng.uniform(-6, 6, (B, 2))
+    return q, qd, u
+
+
+@pytest.mark.parametrize("kind", ["box_stack", "arm_pushes_box"])
+def test_moving_vs_moving_contact_matches_oracle(oracle, kind):
+    w = mm_world(kind)
+    B = 16
+    q, qd, u = mm_states(kind, w, B)
+    hs = HostSim(w, B); hs.set_state(q, qd, u); hs.eval(ref=True)
+    assert hs.nslot == w.nslot == oracle.OracleWorld(w).nslot
+    hs.step(200)
+    hq, hqd, hqdd = hs.get_state(); a, t, r, f = hs.get_contact()
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=200)
+    ns_static = 8 * (3 if kind == "box_stack" else 2) * 1 if kind == "box_stack" else None
+    assert (a == o[3]).all() and (hs.get_status() == 0).all()
+    err = np.abs(hq - o[0]).max(1) / np.abs(o[0]).max(1)
+    assert (err < 1e-8).all(), err
+    # the moving-vs-moving slots saw contact in the course of the run and the partners felt each other
+    o50 = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=50)
+    nstat = sum(v.shape[0] for l in w.flat_links() for v in l.cells()) * len(w.boxes)
+    assert o50[3][:, nstat:].sum() + o[3][:, nstat:].sum() > 0
+
+
+def test_pair_chain_unreg_has_an_observable_effect(oracle):
+    """[EXT] rkCDPairChainUnreg: the pairs between the cells of ONE chain are registered by default (the reference's example
+    programs unregister them: boxdrop_test.c:37, arm_box_test.c:49).  A two-link chain whose forearm folds into its own
+    upper arm: with the self pairs the links push each other apart, without them they pass through each other."""
+    def world(self_collide):
+        up = ch.Link(name="upper", jtype="float", mass=1.0, stuff="body", inertia=np.eye(3) * 1e-2, boxes=[((0.15, 0.0, 0.0), 0.3, 0.08, 0.08)])
+        fore = ch.Link(name="fore", jtype="revolute", parent=0, mass=0.5, stuff="body", inertia=np.eye(3) * 5e-3, org_p=np.array([0.3, 0.0, 0.0]),
+                       com=np.array([0.15, 0, 0]), boxes=[((0.15, 0.0, 0.0), 0.3, 0.06, 0.06)])
+        return ch.World(chains=[ch.ChainModel("fold", [up, fore], self_collide=self_collide)], contact_info=MM_CI)
+    res = {}
+    for sc in (True, False):
+        w = world(sc)
+        q = np.zeros((1, 7)); q[0, 6] = 2.5; qd = np.zeros((1, 7)); qd[0, 6] = 4.0      # forearm folding back onto the upper arm
+        hs = HostSim(w, 1); hs.set_state(q, qd, np.zeros((1, 2))); hs.eval(ref=True); hs.step(100)
+        o = oracle.OracleWorld(w).batch_run_state(q, qd, np.zeros((1, 2)), nsteps=100)
+        assert hs.nslot == w.nslot == (16 if sc else 0)
+        assert np.abs(hs.get_state()[0] - o[0]).max() < 1e-9
+        res[sc] = o[0][0, 6]
+    print(res)
+    assert res[False] > 2.8 and res[True] < res[False] - 0.1       # folds through itself / is pushed back
