@@ -33,6 +33,8 @@
 
 #include <stdbool.h>
 #include <stddef.h>
+#include <stdio.h>      /* the reference's example programs rely on ZEDA's headers for FILE, BUFSIZ, sprintf, atoi */
+#include <stdlib.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -66,8 +68,19 @@ typedef zVecStruct *zVec;
 #define zRad2Deg(r)      ( (r) * 180.0 / 3.14159265358979323846 )
 __ROKI_FD_EXPORT zVec zVecAlloc(int size);
 __ROKI_FD_EXPORT void zVecFree(zVec v);
+__ROKI_FD_EXPORT void zVecFreeAtOnce(int n, ...);       /* [EXT] ZM: frees n vectors */
 __ROKI_FD_EXPORT zVec zVecZero(zVec v);
 __ROKI_FD_EXPORT zVec zVecCopy(zVec src, zVec dst);
+/* [EXT] ZM zVecFPrint: "<size> ( e0 e1 ... )\n" */
+__ROKI_FD_EXPORT void zVecFPrint(FILE *fp, zVec v);
+#define zVecPrint(v)     zVecFPrint( stdout, (v) )
+/* [EXT] ZEDA zRandInit / zRandF / zRandI: a uniform generator (splitmix64 here; ZEDA's Mersenne-twister stream is not
+ * reproduced).  zRandInit seeds from the clock, or from the environment variable ROKIFD_ZRAND_SEED when it is set. */
+__ROKI_FD_EXPORT void zRandInit(void);
+__ROKI_FD_EXPORT double zRandF(double min, double max);
+__ROKI_FD_EXPORT int zRandI(int min, int max);
+/* [EXT] ZEDA eprintf: formatted message on stderr */
+#define eprintf(...)     fprintf( stderr, __VA_ARGS__ )
 
 typedef struct { double e[3]; } zVec3D;
 

@@ -10,7 +10,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdarg>
 #include <cstring>
+#include <ctime>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -59,8 +61,24 @@ extern "C" zVec zVecAlloc(int size)
   return v;
 }
 extern "C" void zVecFree(zVec v){ if( v ){ std::free(v->buf); std::free(v); } }
+extern "C" void zVecFreeAtOnce(int n, ...){ va_list ap; va_start(ap, n); for(int i=0;i<n;i++) zVecFree(va_arg(ap, zVec)); va_end(ap); }
 extern "C" zVec zVecZero(zVec v){ if( v ) std::memset(v->buf, 0, v->size*sizeof(double)); return v; }
 extern "C" zVec zVecCopy(zVec s, zVec d){ if( !s || !d || s->size != d->size ) return NULL; std::memcpy(d->buf, s->buf, s->size*sizeof(double)); return d; }
+
+extern "C" void zVecFPrint(FILE *fp, zVec v)
+{
+  if( !fp ) return;
+  if( !v ){ std::fprintf(fp, "(null vector)\n"); return; }
+  std::fprintf(fp, "%d (", v->size);
+  for(int i=0;i<v->size;i++) std::fprintf(fp, " %.10g", v->buf[i]);
+  std::fprintf(fp, " )\n");
+}
+/* [EXT] ZEDA random numbers: splitmix64 */
+static unsigned long long g_rand_state = 0x9E3779B97F4A7C15ull;
+static unsigned long long rand_next(){ unsigned long long z = (g_rand_state += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30))*0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27))*0x94D049BB133111EBull; return z ^ (z >> 31); }
+extern "C" void zRandInit(void){ const char *s = std::getenv("ROKIFD_ZRAND_SEED"); g_rand_state = s ? std::strtoull(s, NULL, 10) : (unsigned long long)std::time(NULL); }
+extern "C" double zRandF(double min, double max){ return min + (max - min)*((double)(rand_next() >> 11)*(1.0/9007199254740992.0)); }
+extern "C" int zRandI(int min, int max){ return max <= min ? min : min + (int)(rand_next() % (unsigned long long)(max - min + 1)); }
 
 /* ---- chain stand-in ---------------------------------------------------------------------------- */
 extern "C" rkChain *rkChainInit(rkChain *c){ if( !c ) return NULL; ChainImpl *ci = new ChainImpl; ci->refresh(); c->_b200 = ci; return c; }

@@ -56,3 +56,70 @@ def test_c_caller_matches_oracle(tmp_path, oracle, solver, contacts, z0, cube):
         e.update()
     ref = e.get_state()[0]
     assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), (got, ref)
+
+
+# ---- the reference's own example programs, compiled UNMODIFIED ---------------------------------------------------------
+REF_EX = "/root/reference/example/chain"
+REF_BUILD = os.path.join(ROOT, "tests", "c_callers", "_ref_build")      # git-ignored; travels to the GPU box with the snapshot
+EXAMPLES = ["boxdrop_hardsoft_test", "boxdrop_test", "arm_box_test", "arm_box_trq_test", "arm_wall_test"]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EX), reason="reference tree not present")
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_reference_examples_compile_unmodified(name):
+    """example/chain/*.c of the reference, straight from /root/reference (nothing is copied into the repo), against
+    include/roki_fd/roki_fd.h and librokifd_b200.so: every type, macro and function they touch exists (rkFD by value,
+    rkFDSetSolver / rkFDODE2Assign* macros, rkChain / rkJoint accessors, zVec, zRandF, eprintf, zVecFPrint ...)."""
+    os.makedirs(REF_BUILD, exist_ok=True)
+    exe = os.path.join(REF_BUILD, name)
+    subprocess.check_call(["gcc", "-std=gnu99", "-I" + os.path.join(ROOT, "include"), os.path.join(REF_EX, name + ".c"),
+                           "-L" + LIBDIR, "-lrokifd_b200", "-Wl,-rpath," + LIBDIR, "-o", exe])
+    needed = subprocess.check_output(["readelf", "-d", exe], text=True)
+    assert "librokifd_b200.so" in needed and "libcuda" not in needed
+
+
+def _splitmix(seed):
+    s = seed
+    while True:
+        s = (s + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        yield ((z ^ (z >> 31)) >> 11) / 9007199254740992.0
+
+
+@pytest.mark.gpu
+def test_reference_boxdrop_hardsoft_runs_unmodified(oracle):
+    """The reference's example/chain/boxdrop_hardsoft_test.c (compiled unmodified in the container by the test above; the
+    binary travels with the snapshot) dropping ONE box (argv[1] = 1) on the hard/soft floor under the Volume solver: it opens
+    ../model/{contactinfo,box,floor_hardsoft}.ztk (builder-authored stand-ins with the reference's constants under
+    tests/c_callers/model), steps 5 s and prints the joint displacements every step; compared with the oracle."""
+    exe = os.path.join(REF_BUILD, "boxdrop_hardsoft_test")
+    if not os.path.exists(exe):
+        pytest.skip("built where the reference tree exists (tests/c_callers/_ref_build)")
+    cwd = os.path.join(ROOT, "tests", "c_callers", "chain")
+    seed = 12345
+    subprocess.run([exe, "1"], cwd=cwd, env=dict(os.environ, ROKIFD_ZRAND_SEED=str(seed)), check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    rows = [l.split() for l in open(os.path.join(cwd, "1.zvs"))]
+    traj = np.array([[float(x) for x in r[3:9]] for r in rows])           # "dt size ( q0 .. q5 )"
+    assert traj.shape == (5000, 6) and all(r[1] == "6" for r in rows[:3])
+    g = _splitmix(seed)
+    q = np.zeros(6); q[2] = 0.1
+    for k in (3, 4, 5):
+        q[k] = np.deg2rad(-90.0 + 180.0 * next(g))
+    w = ch.World(chains=[ch.ChainModel("box", [ch.Link(name="link#00", jtype="float", mass=0.5, stuff="body", inertia=np.eye(3) * 8.33e-4,
+                                                       boxes=[((0.0, 0.0, 0.0), 0.1, 0.1, 0.1)])]), ch.floor_hardsoft()],
+                 contact_info=[ch.ContactInfo("ground", "body", "rigid", K=1000.0, L=0.0001), ch.ContactInfo("body", "body", "rigid", K=1000.0, L=0.05),
+                               ch.ContactInfo("soft", "body", "elastic", E=100.0, V=1.0)], solver="Volume")
+    e = oracle.OracleWorld(w).env()
+    e.set_state(q, np.zeros(6)); e.set_motor_input(np.zeros(w.nl)); e.update_init()
+    ref = []
+    for _ in range(600):
+        e.update(); ref.append(e.get_state()[0].copy())
+    ref = np.array(ref)
+    err = np.abs(traj[:600] - ref).max(1)
+    print("boxdrop_hardsoft_test: max |q - q_oracle| over the first 100 / 300 / 600 steps: %.2e / %.2e / %.2e (printed with 10 digits)" % (
+        err[:100].max(), err[:300].max(), err.max()))
+    assert err[:300].max() < 1e-8
+    assert np.isfinite(traj).all() and abs(traj[-1, 2]) < 0.2          # after 5 s the box lies on the floor
