@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-JOINT = {"fixed": 0, "revolute": 1, "prismatic": 2, "spherical": 3, "float": 4}
+JOINT = {"fixed": 0, "revolute": 1, "prismatic": 2, "spherical": 3, "float": 4, "cylindrical": 5, "hooke": 6}
 MOTOR = {None: 0, "none": 0, "dc": 1, "trq": 2}
 CONTACT = {"rigid": 0, "elastic": 1}
 SOLVER = {"Vert": 0, "MLCP": 1, "Volume": 2}

@@ -163,6 +163,7 @@ struct ork_env {
 static int jtype_ndof(int jt)
 {
   switch(jt){ case ORK_JOINT_REVOL: case ORK_JOINT_PRISM: return 1;
+              case ORK_JOINT_CYLIN: case ORK_JOINT_HOOKE: return 2;
               case ORK_JOINT_SPHER: return 3; case ORK_JOINT_FLOAT: return 6; default: return 0; }
 }
 
@@ -424,6 +425,17 @@ static void eval_kinematics(ork_env *e, const double *q, const double *qd)
     case ORK_JOINT_FLOAT: v3_copy(qi,pJ); aa_to_mat(qi+3,RJ);
       for(r=0;r<3;r++) for(c=0;c<3;c++){ x->S[6*r+c] = RJ[3*c+r]; x->S[6*(3+r)+3+c] = RJ[3*c+r]; }
       m3_tmulv(RJ,qdi,vJ); m3_tmulv(RJ,qdi+3,vJ+3); break;
+    /* [EXT] RoKi rk_joint_cylin: slides along and turns about the joint's z axis; both motion axes are constant in the link */
+    case ORK_JOINT_CYLIN: { double s = sin(qi[1]), co = cos(qi[1]);
+      pJ[2]=qi[0]; RJ[0]=co; RJ[1]=-s; RJ[3]=s; RJ[4]=co;
+      x->S[6*2+0]=1.0; x->S[6*5+1]=1.0; vJ[2]=qdi[0]; vJ[5]=qdi[1]; } break;
+    /* [EXT] RoKi rk_joint_hooke: R = Rz(q0) Ry(q1); in the link frame the first axis is Ry(q1)^T z = (-sin q1, 0, cos q1), the
+     * second is y; the first axis moves in the link: its rate (-cos q1, 0, -sin q1) q1' q0' enters the bias acceleration */
+    case ORK_JOINT_HOOKE: { double s0 = sin(qi[0]), c0 = cos(qi[0]), s1 = sin(qi[1]), c1 = cos(qi[1]);
+      double Rz[9] = {c0,-s0,0, s0,c0,0, 0,0,1}, Ry[9] = {c1,0,s1, 0,1,0, -s1,0,c1};
+      m3_mul(Rz,Ry,RJ);
+      x->S[6*3+0]=-s1; x->S[6*5+0]=c1; x->S[6*4+1]=1.0;
+      vJ[3]=-s1*qdi[0]; vJ[4]=qdi[1]; vJ[5]=c1*qdi[0]; } break;
     default: break;
     }
     m3_mul(l->org_R,RJ,x->Rrel);
@@ -441,6 +453,7 @@ static void eval_kinematics(ork_env *e, const double *q, const double *qd)
     v3_cross(wp,x->prel,t1); v3_cross(wp,t1,t2); m3_tmulv(x->Rrel,t2,x->zeta);
     v3_cross(wpl,vJ,t1); v3_cat(x->zeta,2.0,t1);
     v3_cross(wpl,vJ+3,x->zeta+3);
+    if( l->jtype == ORK_JOINT_HOOKE ){ x->zeta[3] += -cos(qi[1])*qdi[0]*qdi[1]; x->zeta[5] += -sin(qi[1])*qdi[0]*qdi[1]; }   /* S' q' */
     /* acceleration transform X = [[R^T, -R^T [p x]],[0, R^T]] */
     { double P[9], RtP[9], Rt[9];
       for(r=0;r<3;r++) for(c=0;c<3;c++) Rt[3*r+c] = x->Rrel[3*c+r];

@@ -21,7 +21,9 @@ extern "C" {
 #endif
 
 enum { ORK_JOINT_FIXED = 0, ORK_JOINT_REVOL = 1, ORK_JOINT_PRISM = 2,
-       ORK_JOINT_SPHER = 3, ORK_JOINT_FLOAT = 4 };
+       ORK_JOINT_SPHER = 3, ORK_JOINT_FLOAT = 4,
+       ORK_JOINT_CYLIN = 5,   /* [EXT] cylindrical: dis = (translation along z, rotation about z) */
+       ORK_JOINT_HOOKE = 6 }; /* [EXT] hooke / universal: dis = (rotation about z, then about the new y): R = Rz(q0) Ry(q1) */
 enum { ORK_MOTOR_NONE = 0, ORK_MOTOR_DC = 1, ORK_MOTOR_TRQ = 2 };
 enum { ORK_CONTACT_RIGID = 0, ORK_CONTACT_ELASTIC = 1 };
 enum { ORK_SF = 0, ORK_KF = 1 };                     /* static / kinetic friction state */

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("ROKIFD_B200_LIB") or os.path.join(_HERE, "librokifd_b
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
-JOINT = {"fixed": 0, "revolute": 1, "prismatic": 2, "spherical": 3, "float": 4}
+JOINT = {"fixed": 0, "revolute": 1, "prismatic": 2, "spherical": 3, "float": 4, "cylindrical": 5, "hooke": 6}
 MOTOR = {None: 0, "none": 0, "dc": 1, "trq": 2}
 CONTACT = {"rigid": 0, "elastic": 1}
 SOLVER = {"Vert": 0, "MLCP": 1, "Volume": 2}

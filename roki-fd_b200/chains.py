@@ -11,7 +11,7 @@ from typing import List, Optional
 
 import numpy as np
 
-NDOF = {"fixed": 0, "revolute": 1, "prismatic": 1, "spherical": 3, "float": 6}
+NDOF = {"fixed": 0, "revolute": 1, "prismatic": 1, "spherical": 3, "float": 6, "cylindrical": 2, "hooke": 2}
 
 
 def rot_x(a):
@@ -207,7 +207,7 @@ def world_from_flat(desc):
     into one forest chain, every static box into its own all-fixed chain; the contact parameters of each (cell, box) pair
     come back through per-link / per-box `stuff` names.  Flattening the result again reproduces the description (the DC
     motor constants are folded in the description: an equivalent motor with gear ratio 1 is returned)."""
-    jt = {0: "fixed", 1: "revolute", 2: "prismatic", 3: "spherical", 4: "float"}
+    jt = {0: "fixed", 1: "revolute", 2: "prismatic", 3: "spherical", 4: "float", 5: "cylindrical", 6: "hooke"}
     nl, nq, ncell, nbox, npair, nslot, nvert = (int(v) for v in desc["dims"])
     solver, pyramid, max_iter, integ = (int(v) for v in desc["prp"][:4])
     dt, fw = desc["prp"][4], desc["prp"][5]

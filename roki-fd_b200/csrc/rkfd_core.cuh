@@ -52,6 +52,7 @@ RKFD_HD int link_slot_count(int jtype, int has_rigid){
   switch(jtype){
     case J_REVOL: case J_PRISM: return has_rigid ? 16 : 10;    /* w,gd->U (6), sin, cos, Dinv, u [, w,gd (6)] */
     case J_SPHER: return has_rigid ? 42 : 36;                  /* U (18, w/gd aliased), Dinv (6), u (3), Rrel (9) [, w,gd] */
+    case J_CYLIN: case J_HOOKE: return has_rigid ? 38 : 32;    /* U (12, w/gd aliased), Dinv (3), u (2), Rrel (9), prel (3), sin/cos q1 (2), pad [, w,gd] */
     case J_FLOAT: return has_rigid ? 45 : 18; /* a0 (6, w/gd aliased), Rrel (9), prel (3) [, IA^-1 (21), w,gd (6)] */
     default: return 6;                        /* w, gd */
   }
@@ -59,7 +60,7 @@ RKFD_HD int link_slot_count(int jtype, int has_rigid){
 /* offset of (w, gd) inside the link slots */
 RKFD_HD int link_w_offset(int jtype, int has_rigid){
   if( !has_rigid ) return 0;
-  switch(jtype){ case J_REVOL: case J_PRISM: return 10; case J_SPHER: return 36; case J_FLOAT: return 39; default: return 0; }
+  switch(jtype){ case J_REVOL: case J_PRISM: return 10; case J_SPHER: return 36; case J_FLOAT: return 39; case J_CYLIN: case J_HOOKE: return 32; default: return 0; }
 }
 constexpr int BRANCH_SLOTS = 15;   /* pass 1: Rw(9) pw(3) vl(3); pass 3: a(6) w(3) */
 constexpr int ACCUM_SLOTS = 27;    /* A(6) B(9) C(6) pf(3) pn(3) */
@@ -428,9 +429,34 @@ struct Core {
       const M3 Ro = org_R(L);
       if( VEL ){ vJ = tmul(x.R, mul(Ro, t3(qds))); wJ = tmul(x.R, mul(Ro, t3(qds+3))); }
     } break;
+    case J_CYLIN: case J_HOOKE: {
+      x.R = ldm(sl+17); x.p = ld3(sl+26); x.ptl = tmul(x.R, x.p);
+      if( VEL ){ const double v0 = T(qds), v1 = T(qds+1);
+        if( JT<Kt>(i,L) == J_CYLIN ){ vJ.z = v0; wJ.z = v1; }
+        else { const double s1 = c.S(sl+29), c1 = c.S(sl+30); wJ = v3(-s1*v0, v1, c1*v0); } }
+    } break;
     default: x.R = org_R(L); x.p = org_p(L); x.ptl = v3(L.pol[0],L.pol[1],L.pol[2]); break;
     }
     return x;
+  }
+  /* motion axes of the 2-DoF joints in the link frame ([EXT] cylindrical: (z; 0), (0; z); hooke: (0; Ry(q1)^T z), (0; y)) */
+  RKFD_HD void axes2(int jt, int sl, V3 &l0, V3 &a0, V3 &l1, V3 &a1){
+    if( jt == J_CYLIN ){ l0 = v3(0,0,1); a0 = v3(0,0,0); l1 = v3(0,0,0); a1 = v3(0,0,1); }
+    else { l0 = v3(0,0,0); a0 = v3(-c.S(sl+29), 0.0, c.S(sl+30)); l1 = v3(0,0,0); a1 = v3(0,1,0); }
+  }
+  /* bias-force change (dpf, dpn) at a 2-DoF joint: stores du = -S^T dp, returns the change handed to the parent side */
+  RKFD_HD void probe2_in(int jt, int sl, V3 dpf, V3 dpn, double (&du)[2], V3 &paf, V3 &pan){
+    V3 l0, a0, l1, a1; axes2(jt, sl, l0, a0, l1, a1);
+    du[0] = -(dot(l0,dpf) + dot(a0,dpn)); du[1] = -(dot(l1,dpf) + dot(a1,dpn));
+    const double k0 = c.S(sl+12)*du[0] + c.S(sl+13)*du[1], k1 = c.S(sl+13)*du[0] + c.S(sl+14)*du[1];
+    paf = dpf + k0*ld3(sl) + k1*ld3(sl+6); pan = dpn + k0*ld3(sl+3) + k1*ld3(sl+9);
+  }
+  /* acceleration response of a 2-DoF joint to du with the transformed parent acceleration (xl, xa) */
+  RKFD_HD void probe2_out(int jt, int sl, const double (&du)[2], V3 &xl, V3 &xa){
+    V3 l0, a0, l1, a1; axes2(jt, sl, l0, a0, l1, a1);
+    const double r0 = du[0] - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)), r1 = du[1] - (dot(ld3(sl+6),xl) + dot(ld3(sl+9),xa));
+    const double q0 = c.S(sl+12)*r0 + c.S(sl+13)*r1, q1 = c.S(sl+13)*r0 + c.S(sl+14)*r1;
+    xl = xl + q0*l0 + q1*l1; xa = xa + q0*a0 + q1*a1;
   }
 
   /* [EXT A-10] closest face of the box for a vertex inside it: first minimum depth over x,y,z; outward normal,
@@ -652,6 +678,20 @@ struct Core {
         stm(sl+6, x.R); st3(sl+15, x.p);
         vJ = tmul(x.R, mul(Ro, t3(qds+qo))); wJ = tmul(x.R, mul(Ro, t3(qds+qo+3)));
       } break;
+      case J_CYLIN: {
+        const M3 Ro = org_R(L); double sn, co; sincos(T(qs+qo+1), &sn, &co);
+        const V3 o0 = col0(Ro), o1 = col1(Ro);
+        x.R = from_cols(co*o0 + sn*o1, co*o1 - sn*o0, col2(Ro)); x.p = org_p(L) + T(qs+qo)*col2(Ro);
+        stm(sl+17, x.R); st3(sl+26, x.p);
+        vJ.z = T(qds+qo); wJ.z = T(qds+qo+1);
+      } break;
+      case J_HOOKE: {
+        const M3 Ro = org_R(L); double s0, c0, s1, c1; sincos(T(qs+qo), &s0, &c0); sincos(T(qs+qo+1), &s1, &c1);
+        M3 RJ; RJ.xx = c0*c1; RJ.xy = -s0; RJ.xz = c0*s1; RJ.yx = s0*c1; RJ.yy = c0; RJ.yz = s0*s1; RJ.zx = -s1; RJ.zy = 0.0; RJ.zz = c1;
+        x.R = mm(Ro, RJ); x.p = org_p(L);
+        stm(sl+17, x.R); st3(sl+26, x.p); c.S(sl+29) = s1; c.S(sl+30) = c1;
+        const double v0 = T(qds+qo), v1 = T(qds+qo+1); wJ = v3(-s1*v0, v1, c1*v0);
+      } break;
       default: x.R = org_R(L); x.p = org_p(L); break;
       }
       V3 om_n = xf_tmul(x, om);
@@ -764,7 +804,9 @@ struct Core {
       } else if( JT<Kt>(i,L) != J_FLOAT ){
         const V3 omp = om - wJ;
         const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
-        const V3 za = cross(omp, wJ);
+        V3 za = cross(omp, wJ);
+        if( JT<Kt>(i,L) == J_HOOKE ){ const double qq = T(rk0 + Spec::nq(m) + Spec::qofs(i,L))*T(rk0 + Spec::nq(m) + Spec::qofs(i,L) + 1);   /* S' q' */
+          za.x -= c.S(sl+30)*qq; za.z -= c.S(sl+29)*qq; }
         pf = madd(madd(pf, A, zl), B, za);
         pn = madd(maddt(pn, B, zl), C, za);
       }
@@ -809,6 +851,25 @@ struct Core {
         C.xx-=dC.xx; C.xy-=dC.xy; C.xz-=dC.xz; C.yy-=dC.yy; C.yz-=dC.yz; C.zz-=dC.zz;
         B.xx-=dB.xx; B.xy-=dB.xy; B.xz-=dB.xz; B.yx-=dB.yx; B.yy-=dB.yy; B.yz-=dB.yz; B.zx-=dB.zx; B.zy-=dB.zy; B.zz-=dB.zz;
         pf = pf + mul(Wl, u); pn = pn + mul(Wa, u);
+      } break;
+      case J_CYLIN: case J_HOOKE: {
+        /* two motion axes S_k = (l_k; a_k): U_k = IA S_k, D = S^T U (2x2), u = -S^T pA (no motor, no passive torque:
+         * rkFDJointFrictionAll with zero kinetic friction, rkfd_util.c:318-328) */
+        V3 l0, a0, l1, a1; axes2(JT<Kt>(i,L), sl, l0, a0, l1, a1);
+        const V3 Ul0 = mul(A, l0) + mul(B, a0), Ua0 = tmul(B, l0) + mul(C, a0);
+        const V3 Ul1 = mul(A, l1) + mul(B, a1), Ua1 = tmul(B, l1) + mul(C, a1);
+        const double d00 = dot(l0,Ul0) + dot(a0,Ua0), d01 = dot(l0,Ul1) + dot(a0,Ua1), d11 = dot(l1,Ul1) + dot(a1,Ua1);
+        const double idet = 1.0/(d00*d11 - d01*d01), i00 = d11*idet, i01 = -d01*idet, i11 = d00*idet;
+        const double u0 = -(dot(l0,pf) + dot(a0,pn)), u1 = -(dot(l1,pf) + dot(a1,pn));
+        st3(sl, Ul0); st3(sl+3, Ua0); st3(sl+6, Ul1); st3(sl+9, Ua1);
+        c.S(sl+12) = i00; c.S(sl+13) = i01; c.S(sl+14) = i11; c.S(sl+15) = u0; c.S(sl+16) = u1;
+        const V3 Wl0 = i00*Ul0 + i01*Ul1, Wa0 = i00*Ua0 + i01*Ua1, Wl1 = i01*Ul0 + i11*Ul1, Wa1 = i01*Ua0 + i11*Ua1;
+        A.xx-=Wl0.x*Ul0.x+Wl1.x*Ul1.x; A.xy-=Wl0.x*Ul0.y+Wl1.x*Ul1.y; A.xz-=Wl0.x*Ul0.z+Wl1.x*Ul1.z; A.yy-=Wl0.y*Ul0.y+Wl1.y*Ul1.y; A.yz-=Wl0.y*Ul0.z+Wl1.y*Ul1.z; A.zz-=Wl0.z*Ul0.z+Wl1.z*Ul1.z;
+        C.xx-=Wa0.x*Ua0.x+Wa1.x*Ua1.x; C.xy-=Wa0.x*Ua0.y+Wa1.x*Ua1.y; C.xz-=Wa0.x*Ua0.z+Wa1.x*Ua1.z; C.yy-=Wa0.y*Ua0.y+Wa1.y*Ua1.y; C.yz-=Wa0.y*Ua0.z+Wa1.y*Ua1.z; C.zz-=Wa0.z*Ua0.z+Wa1.z*Ua1.z;
+        B.xx-=Wl0.x*Ua0.x+Wl1.x*Ua1.x; B.xy-=Wl0.x*Ua0.y+Wl1.x*Ua1.y; B.xz-=Wl0.x*Ua0.z+Wl1.x*Ua1.z;
+        B.yx-=Wl0.y*Ua0.x+Wl1.y*Ua1.x; B.yy-=Wl0.y*Ua0.y+Wl1.y*Ua1.y; B.yz-=Wl0.y*Ua0.z+Wl1.y*Ua1.z;
+        B.zx-=Wl0.z*Ua0.x+Wl1.z*Ua1.x; B.zy-=Wl0.z*Ua0.y+Wl1.z*Ua1.y; B.zz-=Wl0.z*Ua0.z+Wl1.z*Ua1.z;
+        pf = pf + u0*Wl0 + u1*Wl1; pn = pn + u0*Wa0 + u1*Wa1;
       } break;
       case J_FLOAT: {
         /* free 6-DoF joint: a = -IA^-1 pA, nothing is transmitted to the parent */
@@ -989,6 +1050,23 @@ struct Core {
           rk_lin(m, k, stage, qds+2, pqd+2, c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs+2, acc.z);
         }
       } break;
+      case J_CYLIN: case J_HOOKE: {
+        if( JT<Kt>(i,L) == J_HOOKE ){ const double qq = T(rk0 + NQc + qo)*T(rk0 + NQc + qo + 1); za.x -= c.S(sl+30)*qq; za.z -= c.S(sl+29)*qq; }
+        V3 l0, a0, l1, a1; axes2(JT<Kt>(i,L), sl, l0, a0, l1, a1);
+        const double r0 = c.S(sl+15) - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)), r1 = c.S(sl+16) - (dot(ld3(sl+6),xl) + dot(ld3(sl+9),xa));
+        const double acc0 = c.S(sl+12)*r0 + c.S(sl+13)*r1, acc1 = c.S(sl+13)*r0 + c.S(sl+14)*r1;
+        al = xl + zl + acc0*l0 + acc1*l1; aa = xa + za + acc0*a0 + acc1*a1;
+        if( stage == ST_PROBE ){}
+        else if( stage >= ST_REF ){ c.gst(c.st.qdd, qo, acc0); c.gst(c.st.qdd, qo+1, acc1); if( !(fabs(acc0)+fabs(acc1) < 1.0e300) ) bad = 1; }
+        else {
+          const int qs = rk0 + qo, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
+          const double v0 = T(qds), v1 = T(qds+1);
+          rk_lin(m, k, stage, qs,   pq,   c.st.q[c.cur], c.st.q[c.cur^1], qo,   v0);
+          rk_lin(m, k, stage, qs+1, pq+1, c.st.q[c.cur], c.st.q[c.cur^1], qo+1, v1);
+          rk_lin(m, k, stage, qds,   pqd,   c.st.qd[c.cur], c.st.qd[c.cur^1], qo,   acc0);
+          rk_lin(m, k, stage, qds+1, pqd+1, c.st.qd[c.cur], c.st.qd[c.cur^1], qo+1, acc1);
+        }
+      } break;
       case J_FLOAT: {
         const V3 a0l = ld3(sl), a0a = ld3(sl+3);
         const M3 RJ = mm(transpose(org_R(L)), x.R);     /* S^-1 = blockdiag(RJ, RJ) */
@@ -1069,6 +1147,7 @@ struct Core {
         paf = dpf + mul(ldm(sl), k); pan = dpn + mul(ldm(sl+9), k);
       } break;
       case J_FLOAT: sw3(du0+6*i, dpf); sw3(du0+6*i+3, dpn); break;
+      case J_CYLIN: case J_HOOKE: { double d2[2]; probe2_in(L.jtype, sl, dpf, dpn, d2, paf, pan); c.W(du0+6*i) = d2[0]; c.W(du0+6*i+1) = d2[1]; } break;
       default: break;
       }
       if( L.parent < 0 || L.jtype == J_FLOAT ) break;
@@ -1099,6 +1178,7 @@ struct Core {
         for(int a=0;a<6;a++) for(int b=a;b<6;b++){ r[a] -= iv[k]*dp[b]; if( b != a ) r[b] -= iv[k]*dp[a]; k++; }
         xl = v3(r[0],r[1],r[2]); xa = v3(r[3],r[4],r[5]);
       } break;
+      case J_CYLIN: case J_HOOKE: { const double d2[2] = { c.W(du0+6*i), c.W(du0+6*i+1) }; probe2_out(L.jtype, sl, d2, xl, xa); } break;
       default: break;
       }
       sw3(da0+6*i, xl); sw3(da0+6*i+3, xa);
@@ -1143,6 +1223,7 @@ struct Core {
         paf = dpf + mul(ldm(sl), k); pan = dpn + mul(ldm(sl+9), k);
       } break;
       case J_FLOAT: du[6*np]=dpf.x; du[6*np+1]=dpf.y; du[6*np+2]=dpf.z; du[6*np+3]=dpn.x; du[6*np+4]=dpn.y; du[6*np+5]=dpn.z; break;
+      case J_CYLIN: case J_HOOKE: { double d2[2]; probe2_in(jt, sl, dpf, dpn, d2, paf, pan); du[6*np] = d2[0]; du[6*np+1] = d2[1]; } break;
       default: break;
       }
       np++;
@@ -1170,6 +1251,7 @@ struct Core {
         for(int a=0;a<6;a++) for(int b=a;b<6;b++){ const double iv = c.S(sl+18+k); r[a] -= iv*du[6*q+b]; if( b != a ) r[b] -= iv*du[6*q+a]; k++; }
         xl = v3(r[0],r[1],r[2]); xa = v3(r[3],r[4],r[5]);
       } break;
+      case J_CYLIN: case J_HOOKE: { const double d2[2] = { du[6*q], du[6*q+1] }; probe2_out(jt, sl, d2, xl, xa); } break;
       default: break;
       }
       al = xl; aa = xa;

@@ -34,7 +34,7 @@ struct LinkHost {
 };
 
 inline int jtype_ndof(int jt){
-  switch(jt){ case J_REVOL: case J_PRISM: return 1; case J_SPHER: return 3; case J_FLOAT: return 6; default: return 0; }
+  switch(jt){ case J_REVOL: case J_PRISM: return 1; case J_CYLIN: case J_HOOKE: return 2; case J_SPHER: return 3; case J_FLOAT: return 6; default: return 0; }
 }
 
 struct ChainHost {

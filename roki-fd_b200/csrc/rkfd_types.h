@@ -30,7 +30,9 @@ constexpr int MAX_FWORDS = 64;
 constexpr int RIGID_MAX_SLOTS = 32; /* the rigid VERTEX solvers (MLCP, Vert) address every rigid slot through one flag word */
 constexpr int MAX_PYRAMID = 16;
 
-enum JointType : int { J_FIXED = 0, J_REVOL = 1, J_PRISM = 2, J_SPHER = 3, J_FLOAT = 4 };
+enum JointType : int { J_FIXED = 0, J_REVOL = 1, J_PRISM = 2, J_SPHER = 3, J_FLOAT = 4,
+                       J_CYLIN = 5,      /* [EXT] cylindrical: (translation along z, rotation about z) */
+                       J_HOOKE = 6 };    /* [EXT] hooke / universal: R = Rz(q0) Ry(q1) */
 enum MotorType : int { M_NONE = 0, M_DC = 1, M_TRQ = 2 };
 enum ContactType : int { C_RIGID = 0, C_ELASTIC = 1 };
 enum FricType : int { F_SF = 0, F_KF = 1 };

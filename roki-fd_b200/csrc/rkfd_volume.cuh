@@ -234,6 +234,7 @@
         paf = dpf + mul(ldm(sl), k); pan = dpn + mul(ldm(sl+9), k);
       } break;
       case J_FLOAT: du[6*np]=dpf.x; du[6*np+1]=dpf.y; du[6*np+2]=dpf.z; du[6*np+3]=dpn.x; du[6*np+4]=dpn.y; du[6*np+5]=dpn.z; break;
+      case J_CYLIN: case J_HOOKE: { double d2[2]; probe2_in(jt, sl, dpf, dpn, d2, paf, pan); du[6*np] = d2[0]; du[6*np+1] = d2[1]; } break;
       default: break;
       }
       np++;
@@ -265,6 +266,7 @@
         for(int a=0;a<6;a++) for(int b=a;b<6;b++){ const double iv = c.S(sl+18+k); r[a] -= iv*d[b]; if( b != a ) r[b] -= iv*d[a]; k++; }
         xl = v3(r[0],r[1],r[2]); xa = v3(r[3],r[4],r[5]);
       } break;
+      case J_CYLIN: case J_HOOKE: { const double d2[2] = { d[0], d[1] }; probe2_out(jt, sl, d2, xl, xa); } break;
       default: break;
       }
       al = xl; aa = xa;

@@ -267,6 +267,7 @@ bool ztk_read_chain(const char *filename, ChainHost &chain, std::string &err)
       const std::string jt = word(s, "jointtype");
       if( jt == "fixed" || jt.empty() ) l.jtype = J_FIXED; else if( jt == "revolute" ) l.jtype = J_REVOL; else if( jt == "prismatic" ) l.jtype = J_PRISM;
       else if( jt == "spherical" ) l.jtype = J_SPHER; else if( jt == "float" ) l.jtype = J_FLOAT;
+      else if( jt == "cylindrical" ) l.jtype = J_CYLIN; else if( jt == "hooke" || jt == "universal" ) l.jtype = J_HOOKE;
       else { err = "joint type '" + jt + "' of link '" + l.name + "' is not supported"; return false; }
       if( const Field *f = find(s, "mass") ) l.mass = num(*f, 0);
       bool com_auto = false, inertia_auto = false; double density = 0.0;
@@ -330,7 +331,7 @@ bool ztk_read_chain(const char *filename, ChainHost &chain, std::string &err)
       const LinkHost &l = chain.links[it->second]; const int o = chain.link_qofs(it->second), n = jtype_ndof(l.jtype);
       for(int k=0;k<n;k++){
         double v = num(f, 1+k);
-        const bool angular = l.jtype == J_REVOL || l.jtype == J_SPHER || ( l.jtype == J_FLOAT && k >= 3 );
+        const bool angular = l.jtype == J_REVOL || l.jtype == J_SPHER || l.jtype == J_HOOKE || ( l.jtype == J_FLOAT && k >= 3 ) || ( l.jtype == J_CYLIN && k == 1 );
         chain.dis[o+k] = angular ? v*DEG : v;      /* [EXT] angles are written in degrees */
       }
     }

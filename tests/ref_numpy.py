@@ -5,7 +5,7 @@ dense solve) so that agreement is evidence, not tautology.  Test infrastructure 
 import numpy as np
 
 G = 9.80665
-NDOF = {"fixed": 0, "revolute": 1, "prismatic": 1, "spherical": 3, "float": 6}
+NDOF = {"fixed": 0, "revolute": 1, "prismatic": 1, "spherical": 3, "float": 6, "cylindrical": 2, "hooke": 2}
 
 
 def skew(p):
@@ -46,6 +46,18 @@ def rnea(links, q, qd, qdd, fext=None, gravity=True):
         elif l.jtype == "float":
             pJ = qi[:3].copy(); RJ = aa_to_mat(qi[3:]); vJ, dvJ = vi[:3].copy(), ai[:3].copy()
             wJ, dwJ = vi[3:].copy(), ai[3:].copy()
+        elif l.jtype == "cylindrical":      # slides along z (q0), turns about z (q1)
+            c, s = np.cos(qi[1]), np.sin(qi[1])
+            RJ = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]]); pJ = np.array([0, 0, qi[0]])
+            vJ, dvJ = np.array([0, 0, vi[0]]), np.array([0, 0, ai[0]])
+            wJ, dwJ = np.array([0, 0, vi[1]]), np.array([0, 0, ai[1]])
+        elif l.jtype == "hooke":            # R = Rz(q0) Ry(q1): angular velocity z q0' + (Rz y) q1' in the org frame
+            c0, s0, c1, s1 = np.cos(qi[0]), np.sin(qi[0]), np.cos(qi[1]), np.sin(qi[1])
+            Rz = np.array([[c0, -s0, 0], [s0, c0, 0], [0, 0, 1]]); Ry = np.array([[c1, 0, s1], [0, 1, 0], [-s1, 0, c1]])
+            RJ = Rz @ Ry
+            ez, y1 = np.array([0, 0, 1.0]), Rz @ np.array([0, 1.0, 0])
+            wJ = ez * vi[0] + y1 * vi[1]
+            dwJ = ez * ai[0] + y1 * ai[1] + np.cross(ez * vi[0], y1 * vi[1])
         r = Rp @ (np.asarray(l.org_p, float)) + Ro @ pJ
         R[i] = Ro @ RJ
         p[i] = pp + r
@@ -77,6 +89,11 @@ def rnea(links, q, qd, qdd, fext=None, gravity=True):
             tau[ofs[i]] = Ro[:, 2] @ f[i]
         elif l.jtype == "spherical":
             tau[ofs[i]:ofs[i + 1]] = Ro.T @ nn[i]
+        elif l.jtype == "cylindrical":
+            tau[ofs[i]] = Ro[:, 2] @ f[i]; tau[ofs[i] + 1] = Ro[:, 2] @ nn[i]
+        elif l.jtype == "hooke":
+            c0, s0 = np.cos(q[ofs[i]]), np.sin(q[ofs[i]])
+            tau[ofs[i]] = Ro[:, 2] @ nn[i]; tau[ofs[i] + 1] = (Ro @ np.array([-s0, c0, 0.0])) @ nn[i]
         elif l.jtype == "float":
             tau[ofs[i]:ofs[i] + 3] = Ro.T @ f[i]
             tau[ofs[i] + 3:ofs[i] + 6] = Ro.T @ nn[i]

@@ -132,9 +132,9 @@ def test_free_running_trajectory(capi, oracle, name, tol):
     fd.destroy()
 
 
-@pytest.mark.parametrize("kind", ["branching", "float_root_tree", "spherical", "prismatic_mix"])
+@pytest.mark.parametrize("kind", ["branching", "float_root_tree", "spherical", "prismatic_mix", "cylindrical_hooke"])
 def test_random_topologies(capi, oracle, kind):
-    rng = np.random.default_rng({"branching": 1, "float_root_tree": 2, "spherical": 3, "prismatic_mix": 4}[kind])
+    rng = np.random.default_rng({"branching": 1, "float_root_tree": 2, "spherical": 3, "prismatic_mix": 4, "cylindrical_hooke": 5}[kind])
     for trial in range(3):
         if kind == "branching":
             c = ch.random_chain(rng, 9, jtypes=("revolute", "prismatic"), branching=True, motors=True)
@@ -142,6 +142,8 @@ def test_random_topologies(capi, oracle, kind):
             c = ch.random_chain(rng, 8, jtypes=("revolute", "fixed", "spherical"), root="float", branching=True)
         elif kind == "spherical":
             c = ch.random_chain(rng, 5, jtypes=("spherical", "revolute"))
+        elif kind == "cylindrical_hooke":     # the remaining RoKi joint types
+            c = ch.random_chain(rng, 7, jtypes=("cylindrical", "hooke", "revolute"), root=("fixed", "float")[trial % 2], branching=trial == 2)
         else:
             c = ch.random_chain(rng, 6, jtypes=("revolute", "prismatic", "fixed"), motors=True)
         w = ch.World(chains=[c])

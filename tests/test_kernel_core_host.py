@@ -88,9 +88,9 @@ def test_steps_match_oracle(oracle, name):
         assert relerr(hqd[b, :w.nq], oqd) < 1e-7, (name, b)
 
 
-@pytest.mark.parametrize("kind", ["branching", "float_root_tree", "spherical", "prismatic_mix"])
+@pytest.mark.parametrize("kind", ["branching", "float_root_tree", "spherical", "prismatic_mix", "cylindrical_hooke"])
 def test_random_topologies_match_oracle(oracle, kind):
-    rng = np.random.default_rng({"branching": 1, "float_root_tree": 2, "spherical": 3, "prismatic_mix": 4}[kind])
+    rng = np.random.default_rng({"branching": 1, "float_root_tree": 2, "spherical": 3, "prismatic_mix": 4, "cylindrical_hooke": 5}[kind])
     for trial in range(4):
         if kind == "branching":
             c = ch.random_chain(rng, 9, jtypes=("revolute", "prismatic"), branching=True, motors=True)
@@ -98,6 +98,8 @@ def test_random_topologies_match_oracle(oracle, kind):
             c = ch.random_chain(rng, 8, jtypes=("revolute", "fixed", "spherical"), root="float", branching=True)
         elif kind == "spherical":
             c = ch.random_chain(rng, 5, jtypes=("spherical", "revolute"))
+        elif kind == "cylindrical_hooke":
+            c = ch.random_chain(rng, 7, jtypes=("cylindrical", "hooke", "revolute"), root=("fixed", "float")[trial % 2], branching=trial >= 2)
         else:
             c = ch.random_chain(rng, 6, jtypes=("revolute", "prismatic", "fixed"), motors=True)
         w = ch.World(chains=[c])
@@ -628,3 +630,26 @@ def test_pair_chain_unreg_has_an_observable_effect(oracle):
         res[sc] = o[0][0, 6]
     print(res)
     assert res[False] > 2.8 and res[True] < res[False] - 0.1       # folds through itself / is pushed back
+
+
+@pytest.mark.parametrize("solver", ["MLCP", "Vert", "Volume"])
+def test_two_dof_joints_under_the_rigid_contact_solvers(oracle, solver):
+    """A leg with a hooke hip and a cylindrical shank standing with a box foot on the rigid floor: the cached-ABA probes of the
+    contact solvers run through the 2-DoF joints (rkfd_util.c:149-181)."""
+    links = [ch.Link(name="trunk", jtype="float", mass=3.0, stuff="body", inertia=np.eye(3) * 0.03),
+             ch.Link(name="thigh", jtype="hooke", parent=0, mass=1.0, stuff="body", inertia=np.eye(3) * 0.01, org_p=np.array([0, 0, -0.1]), com=np.array([0, 0, -0.1])),
+             ch.Link(name="shank", jtype="cylindrical", parent=1, mass=0.8, stuff="body", inertia=np.eye(3) * 0.008, org_p=np.array([0, 0, -0.25]), com=np.array([0, 0, -0.1])),
+             ch.Link(name="foot", jtype="revolute", parent=2, mass=0.4, stuff="body", inertia=np.eye(3) * 0.002, org_p=np.array([0, 0, -0.2]),
+                     org_R=ch.rot_x(np.pi / 2), shapes=[ch.box_verts(0.16, 0.03, 0.08, center=(0.02, -0.03, 0.0))])]
+    w = ch.World(chains=[ch.ChainModel("leg", links), ch.floor()], solver=solver,
+                 contact_info=[ch.ContactInfo("ground", "body", "rigid", K=1000.0, L=0.01 if solver != "Volume" else 0.001, SF=0.5, KF=0.3)])
+    B = 12
+    rng = np.random.default_rng(2)
+    q = np.zeros((B, w.nq)); q[:, 2] = 0.59 + rng.uniform(-0.004, 0.004, B); q[:, 3:6] = rng.uniform(-0.03, 0.03, (B, 3))
+    q[:, 6:] = rng.uniform(-0.05, 0.05, (B, w.nq - 6)); qd = rng.uniform(-0.1, 0.1, (B, w.nq)); u = np.zeros((B, w.nl))
+    hs = HostSim(w, B); hs.set_state(q, qd, u); hs.eval(ref=True)
+    _, _, hqdd = hs.get_state(); a, t, r, f = hs.get_contact()
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=0)
+    assert (a == o[3]).all() and o[3].sum() > 0 and (hs.get_status() == 0).all()
+    err = np.abs(hqdd - o[2]).max(1) / np.maximum(np.abs(o[2]).max(1), 1e-12)
+    assert (err < 1e-8).all(), err

@@ -14,7 +14,7 @@ def _world(chain, **kw):
 
 
 @pytest.mark.parametrize("kind", ["serial_revolute", "mixed_1dof", "branching", "float_root",
-                                  "spherical", "float_branching_mixed"])
+                                  "spherical", "float_branching_mixed", "cylindrical_hooke"])
 def test_aba_matches_dense_newton_euler(oracle, kind):
     rng = np.random.default_rng(hash(kind) % 2**32)
     for trial in range(5):
@@ -28,6 +28,8 @@ def test_aba_matches_dense_newton_euler(oracle, kind):
             c = ch.random_chain(rng, 5, root="float")
         elif kind == "spherical":
             c = ch.random_chain(rng, 5, jtypes=("spherical", "revolute"))
+        elif kind == "cylindrical_hooke":
+            c = ch.random_chain(rng, 7, jtypes=("cylindrical", "hooke", "revolute"), root=("fixed", "float")[trial % 2], branching=trial >= 3)
         else:
             c = ch.random_chain(rng, 10, jtypes=("revolute", "prismatic", "spherical", "fixed"), root="float",
                                 branching=True)
