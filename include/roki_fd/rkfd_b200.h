@@ -110,7 +110,8 @@ __ROKI_FD_EXPORT void rkCDPairChainUnreg(rkCD *cd, rkChain *chain);
 
 /* programmatic chain construction (what rkChainReadZTK does from a file) */
 enum { RK_B200_JOINT_FIXED = 0, RK_B200_JOINT_REVOL = 1, RK_B200_JOINT_PRISM = 2,
-       RK_B200_JOINT_SPHER = 3, RK_B200_JOINT_FLOAT = 4 };
+       RK_B200_JOINT_SPHER = 3, RK_B200_JOINT_FLOAT = 4, RK_B200_JOINT_CYLIN = 5, RK_B200_JOINT_HOOKE = 6,
+       RK_B200_JOINT_BRFLOAT = 7 };
 enum { RK_B200_MOTOR_NONE = 0, RK_B200_MOTOR_DC = 1, RK_B200_MOTOR_TRQ = 2 };
 typedef struct {
   const char *name;           /* may be NULL */
@@ -125,6 +126,7 @@ typedef struct {
   double stiffness, viscosity, coulomb, staticfriction;   /* 1-DoF joint passive torque */
   int motortype;
   double motorconstant, admittance, gearratio, rotorinertia, gearinertia, minvoltage, maxvoltage;
+  double forcethreshold, torquethreshold;    /* breakable float (example/model/wall.ztk:51-95) */
 } rkB200LinkDesc;
 __ROKI_FD_EXPORT void rkB200LinkDescInit(rkB200LinkDesc *d);
 __ROKI_FD_EXPORT int rkChainB200SetName(rkChain *chain, const char *name);

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-JOINT = {"fixed": 0, "revolute": 1, "prismatic": 2, "spherical": 3, "float": 4, "cylindrical": 5, "hooke": 6}
+JOINT = {"fixed": 0, "revolute": 1, "prismatic": 2, "spherical": 3, "float": 4, "cylindrical": 5, "hooke": 6, "breakablefloat": 7}
 MOTOR = {None: 0, "none": 0, "dc": 1, "trq": 2}
 CONTACT = {"rigid": 0, "elastic": 1}
 SOLVER = {"Vert": 0, "MLCP": 1, "Volume": 2}
@@ -106,6 +106,8 @@ def pack_links(world, links):
         ld[k, 25:29] = (l.stiffness, l.viscosity, l.coulomb, l.sfriction)
         if m:
             ld[k, 29:36] = (m.k, m.admittance, m.gear, m.rotor_inertia, m.gear_inertia, m.min, m.max)
+        if l.jtype == "breakablefloat":        # thresholds in spare fields (tests/hostsim reads them there; the oracle gets them by call)
+            ld[k, 36], ld[k, 29] = l.break_force, l.break_torque
     return li, ld
 
 
@@ -121,6 +123,10 @@ class OracleWorld:
         _, pi = _i(li)
         _, pd = _d(ld)
         self.h = L.ork_world_new(nl, pi, pd)
+        L.ork_world_set_break.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        for k, l in enumerate(links):
+            if l.jtype == "breakablefloat":
+                L.ork_world_set_break(self.h, k, l.break_force, l.break_torque)
         L.ork_world_add_link_box.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
         L.ork_world_unreg_self_collision.argtypes = [C.c_void_p, C.c_int]
         for k, l in enumerate(links):

@@ -74,6 +74,7 @@ static void aa_to_mat(const double *aa, double *R)
 static void aa_cascade(double *aa, const double *w)
 {
   double q1[4], q2[4], q[4], th, s, n;
+  if( w[0] == 0.0 && w[1] == 0.0 && w[2] == 0.0 ) return;      /* no increment: the displacement is kept bit for bit (a held joint) */
   th = v3_norm(aa);
   if( th < 1.0e-12 ){ q1[0]=1.0; q1[1]=0.5*aa[0]; q1[2]=0.5*aa[1]; q1[3]=0.5*aa[2]; }
   else { s = sin(0.5*th)/th; q1[0]=cos(0.5*th); q1[1]=s*aa[0]; q1[2]=s*aa[1]; q1[3]=s*aa[2]; }
@@ -99,6 +100,7 @@ typedef struct {
   double stiffness, viscosity, coulomb, sfriction;
   double mk, madm, mgear, mrotor, mgearin, mmin, mmax;
   int qofs, ndof;
+  double brk_f, brk_t;      /* breakable float: thresholds */
   double M[36];   /* rigid-body 6x6 inertia at the link origin (A-4) */
 } ork_link;
 
@@ -148,6 +150,7 @@ struct ork_env {
   int *c_active, *c_type; double *c_ref, *c_f, *c_pro;   /* per contact slot */
   double *c_norm, *c_axis, *c_vert, *c_refw, *c_vel;     /* per slot, current evaluation */
   ork_lw *lw;
+  int *broken, *nd;           /* per link: breakable float broken? ; effective joint dofs of this evaluation */
   /* rigid system of the last evaluation */
   int rn; double *rA, *rb, *rf;
   /* test hook: the last Vert QP (ork_env_get_qp) */
@@ -164,7 +167,7 @@ static int jtype_ndof(int jt)
 {
   switch(jt){ case ORK_JOINT_REVOL: case ORK_JOINT_PRISM: return 1;
               case ORK_JOINT_CYLIN: case ORK_JOINT_HOOKE: return 2;
-              case ORK_JOINT_SPHER: return 3; case ORK_JOINT_FLOAT: return 6; default: return 0; }
+              case ORK_JOINT_SPHER: return 3; case ORK_JOINT_FLOAT: case ORK_JOINT_BRFLOAT: return 6; default: return 0; }
 }
 
 static void link_build_inertia(ork_link *l)
@@ -332,6 +335,8 @@ void ork_world_finalize(ork_world *w)
     w->npair = n; (void)dropped; }
   w->nslot = sofs;
 }
+void ork_world_set_break(ork_world *w, int link, double fth, double tth){ w->link[link].brk_f = fth; w->link[link].brk_t = tth; }
+void ork_env_get_broken(const ork_env *e, int *broken){ int i; for(i=0;i<e->w->nl;i++) broken[i] = e->broken[i]; }
 int ork_world_nq(const ork_world *w){ return w->nq; }
 int ork_world_nslot(const ork_world *w){ return w->nslot; }
 int ork_world_nl(const ork_world *w){ return w->nl; }
@@ -343,6 +348,7 @@ ork_env *ork_env_new(const ork_world *w)
   e->w = w; e->t = 0.0;
   e->q=(double*)calloc(nq,8); e->qd=(double*)calloc(nq,8); e->qdd=(double*)calloc(nq,8);
   e->min=(double*)calloc(w->nl,8);
+  e->broken=(int*)calloc(w->nl>0?w->nl:1,sizeof(int)); e->nd=(int*)calloc(w->nl>0?w->nl:1,sizeof(int));
   /* friction pivot init {SF, q, 0} (rkfd_sim.c:157-175) */
   e->piv_type=(int*)calloc(nq,sizeof(int)); e->piv_prev=(double*)calloc(nq,8);
   e->tf=(double*)calloc(nq,8); e->tdrive=(double*)calloc(nq,8); e->jm=(double*)calloc(nq,8);
@@ -365,7 +371,7 @@ void ork_env_free(ork_env *e)
   free(e->tf); free(e->tdrive); free(e->jm);
   free(e->c_active); free(e->c_type); free(e->c_ref); free(e->c_f); free(e->c_pro);
   free(e->c_norm); free(e->c_axis); free(e->c_vert); free(e->c_refw); free(e->c_vel);
-  free(e->lw); free(e->rA); free(e->rb); free(e->rf);
+  free(e->broken); free(e->nd); free(e->lw); free(e->rA); free(e->rb); free(e->rf);
   free(e->qp_Q); free(e->qp_c); free(e->qp_nf); free(e->qp_x); free(e->qp_idx);
   free(e->v_type); free(e->v_np); free(e->v_wrench); free(e->v_center); free(e->v_qc);
   for(i=0;i<4;i++) for(j=0;j<2;j++) free(e->k[i][j]);
@@ -415,6 +421,8 @@ static void eval_kinematics(ork_env *e, const double *q, const double *qd)
     double wp[3] = {0,0,0}, vp[3] = {0,0,0};     /* parent velocity in parent frame */
     double wpl[3], t1[3], t2[3];
     m3_ident(RJ); memset(x->S,0,sizeof x->S);
+    e->nd[i] = l->ndof;
+    if( l->jtype == ORK_JOINT_BRFLOAT && !e->broken[i] ) e->nd[i] = 0;      /* rigid: the displacement stays where it is */
     switch(l->jtype){
     case ORK_JOINT_REVOL: { double s = sin(qi[0]), co = cos(qi[0]);
       RJ[0]=co; RJ[1]=-s; RJ[3]=s; RJ[4]=co; x->S[6*5+0]=1.0; vJ[5]=qdi[0]; } break;
@@ -422,6 +430,9 @@ static void eval_kinematics(ork_env *e, const double *q, const double *qd)
     case ORK_JOINT_SPHER: aa_to_mat(qi,RJ);
       for(r=0;r<3;r++) for(c=0;c<3;c++) x->S[6*(3+r)+c] = RJ[3*c+r];   /* S = RJ^T (angular) */
       m3_tmulv(RJ,qdi,vJ+3); break;
+    case ORK_JOINT_BRFLOAT:
+      if( !e->broken[i] ){ v3_copy(qi,pJ); aa_to_mat(qi+3,RJ); break; }
+      /* fall through: broken = float */
     case ORK_JOINT_FLOAT: v3_copy(qi,pJ); aa_to_mat(qi+3,RJ);
       for(r=0;r<3;r++) for(c=0;c<3;c++){ x->S[6*r+c] = RJ[3*c+r]; x->S[6*(3+r)+3+c] = RJ[3*c+r]; }
       m3_tmulv(RJ,qdi,vJ); m3_tmulv(RJ,qdi+3,vJ+3); break;
@@ -689,7 +700,7 @@ static void aba_backward(ork_env *e)
     for(r=0;r<3;r++){ x->pA[r] -= fg[r] + x->wext[r]; x->pA[3+r] -= ng[r] + x->wext[3+r]; }
   }
   for(i=w->nl-1;i>=0;i--){
-    const ork_link *l = &w->link[i]; ork_lw *x = &e->lw[i]; int nd = l->ndof;
+    const ork_link *l = &w->link[i]; ork_lw *x = &e->lw[i]; int nd = e->nd[i];
     double pz[6], Ia[36], pa[6], t6[6];
     m6_mulv(x->IA,x->zeta,pz); for(r=0;r<6;r++) pz[r] += x->pA[r];     /* p' = pA + IA zeta */
     memcpy(Ia,x->IA,sizeof Ia); memcpy(pa,pz,sizeof pa);
@@ -723,14 +734,14 @@ static void aba_forward(ork_env *e, double *qdd, int use_du)
 {
   const ork_world *w = e->w; int i, j, k, r;
   for(i=0;i<w->nl;i++){
-    const ork_link *l = &w->link[i]; ork_lw *x = &e->lw[i]; int nd = l->ndof;
+    const ork_link *l = &w->link[i]; ork_lw *x = &e->lw[i]; int nd = e->nd[i];
     double ap[6] = {0,0,0,0,0,0}, rhs[6], qa[6] = {0,0,0,0,0,0};
     if( l->parent >= 0 ) m6_mulv(x->X,e->lw[l->parent].a,ap);
     for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += x->U[6*k+j]*ap[k];
       rhs[j] = x->u[j] + ( use_du ? x->du[j] : 0.0 ) - s; }
     for(j=0;j<nd;j++){ qa[j]=0; for(k=0;k<nd;k++) qa[j] += x->Dinv[6*j+k]*rhs[k]; }
     for(r=0;r<6;r++){ double s = ap[r] + x->zeta[r]; for(j=0;j<nd;j++) s += x->S[6*r+j]*qa[j]; x->a[r] = s; }
-    if( qdd ) for(j=0;j<nd;j++) qdd[l->qofs+j] = qa[j];
+    if( qdd ) for(j=0;j<l->ndof;j++) qdd[l->qofs+j] = j < nd ? qa[j] : 0.0;
   }
 }
 
@@ -743,7 +754,7 @@ static void aba_probe(ork_env *e, int link, const double *vert, const double *fw
   v3_sub(vert,x->pw,pos); m3_tmulv(x->Rw,pos,pos); m3_tmulv(x->Rw,fw,fl); v3_cross(pos,fl,n);
   for(r=0;r<3;r++){ x->dp[r] = -fl[r]; x->dp[3+r] = -n[r]; }
   for(i=link;i>=0;i=w->link[i].parent){
-    const ork_link *l = &w->link[i]; ork_lw *y = &e->lw[i]; int nd = l->ndof; double pa[6], t6[6];
+    const ork_link *l = &w->link[i]; ork_lw *y = &e->lw[i]; int nd = e->nd[i]; double pa[6], t6[6];
     memcpy(pa,y->dp,sizeof pa);
     for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += y->S[6*k+j]*y->dp[k]; y->du[j] = -s; }
     for(j=0;j<nd;j++){ t6[j]=0; for(k=0;k<nd;k++) t6[j] += y->Dinv[6*j+k]*y->du[k]; }
@@ -1256,7 +1267,7 @@ static void aba_probe6(ork_env *e, int link, const double *pos_w, const double *
   v3_sub(pos_w,x->pw,pos); m3_tmulv(x->Rw,pos,pos); m3_tmulv(x->Rw,f6,fl); m3_tmulv(x->Rw,f6+3,tl); v3_cross(pos,fl,n);
   for(r=0;r<3;r++){ x->dp[r] = -fl[r]; x->dp[3+r] = -(tl[r]+n[r]); }
   for(i=link;i>=0;i=w->link[i].parent){
-    const ork_link *l = &w->link[i]; ork_lw *y = &e->lw[i]; int nd = l->ndof; double pa[6], t6[6];
+    const ork_link *l = &w->link[i]; ork_lw *y = &e->lw[i]; int nd = e->nd[i]; double pa[6], t6[6];
     memcpy(pa,y->dp,sizeof pa);
     for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += y->S[6*k+j]*y->dp[k]; y->du[j] = -s; }
     for(j=0;j<nd;j++){ t6[j]=0; for(k=0;k<nd;k++) t6[j] += y->Dinv[6*j+k]*y->du[k]; }
@@ -1458,8 +1469,22 @@ static void eval_dynamics(ork_env *e, const double *q, const double *qd, double 
   if( has_rigid ){ if( w->solver == ORK_SOLVER_VOLUME ) solver_volume(e,do_up_ref); else solver_rigid(e,do_up_ref); }
   /* _rkFDUpdateAcc (:502-523) */
   aba_backward(e); aba_forward(e,qdd,0);
-  if( do_up_ref ) update_prev_driving_trq(e);         /* solver->_update_ref (:548) */
+  if( do_up_ref ){
+    int i, r, c;
+    update_prev_driving_trq(e);         /* solver->_update_ref (:548) */
+    /* [EXT A-17] breakable float: rkChainUpdateABIWrench (the committing evaluation only, rkfd_sim.c:511-514) forms the wrench
+     * every joint transmits, IA a + pA at the link origin in link axes; a rigid breakable joint whose force or torque
+     * exceeds its threshold is a float joint from the next evaluation on */
+    for(i=0;i<w->nl;i++) if( w->link[i].jtype == ORK_JOINT_BRFLOAT && !e->broken[i] ){
+      const ork_lw *x = &e->lw[i]; double wr[6];
+      for(r=0;r<6;r++){ wr[r] = x->pA[r]; for(c=0;c<6;c++) wr[r] += x->IA[6*r+c]*x->a[c]; }
+      if( v3_norm(wr) > w->link[i].brk_f || v3_norm(wr+3) > w->link[i].brk_t ) e->broken[i] = 1;
+    }
+  }
 }
+/* a rigid (unbroken) breakable-float joint holds its displacement: the velocity slope of its dofs is zero */
+static void hold_unbroken(const ork_env *e, double *vel)
+{ int i, j; for(i=0;i<e->w->nl;i++) if( e->w->link[i].jtype == ORK_JOINT_BRFLOAT && !e->broken[i] ) for(j=0;j<6;j++) vel[e->w->link[i].qofs+j] = 0.0; }
 
 void ork_env_eval(ork_env *e, int do_up_ref){ eval_dynamics(e,e->q,e->qd,e->qdd,do_up_ref); }
 void ork_env_update_init(ork_env *e){ eval_dynamics(e,e->q,e->qd,e->qdd,1); }
@@ -1471,7 +1496,7 @@ static void cat_dis(const ork_world *w, double *q, double k, const double *v)
   for(i=0;i<w->nl;i++){ const ork_link *l = &w->link[i]; double *qi = q+l->qofs; const double *vi = v+l->qofs;
     switch(l->jtype){
     case ORK_JOINT_SPHER: { double dw[3] = {k*vi[0],k*vi[1],k*vi[2]}; aa_cascade(qi,dw); } break;
-    case ORK_JOINT_FLOAT: { double dw[3] = {k*vi[3],k*vi[4],k*vi[5]};
+    case ORK_JOINT_FLOAT: case ORK_JOINT_BRFLOAT: { double dw[3] = {k*vi[3],k*vi[4],k*vi[5]};
       for(j=0;j<3;j++){ qi[j] += k*vi[j]; }
       aa_cascade(qi+3,dw); } break;
     default: for(j=0;j<l->ndof;j++) qi[j] += k*vi[j]; break; } }
@@ -1495,12 +1520,12 @@ void ork_env_update(ork_env *e)
     b[0] = 1.0/6.0; b[1] = (2.0-r2)/6.0; b[2] = (2.0+r2)/6.0; b[3] = 1.0/6.0; break;
   }
   for(s=0;s<ns;s++){
-    if( s == 0 ){ memcpy(e->k[0][0],e->qd,nq*8); eval_dynamics(e,e->q,e->qd,e->k[0][1],0); continue; }
+    if( s == 0 ){ memcpy(e->k[0][0],e->qd,nq*8); hold_unbroken(e,e->k[0][0]); eval_dynamics(e,e->q,e->qd,e->k[0][1],0); continue; }
     memcpy(xq,e->q,nq*8); memcpy(xv,e->qd,nq*8);
     for(j=0;j<s;j++) if( a[s][j] != 0.0 ){
       cat_dis(w,xq,a[s][j]*dt,e->k[j][0]);
       for(i=0;i<nq;i++) xv[i] += a[s][j]*dt*e->k[j][1][i]; }
-    memcpy(e->k[s][0],xv,nq*8); eval_dynamics(e,xq,xv,e->k[s][1],0);
+    memcpy(e->k[s][0],xv,nq*8); hold_unbroken(e,e->k[s][0]); eval_dynamics(e,xq,xv,e->k[s][1],0);
   }
   /* combination */
   for(s=0;s<ns;s++) cat_dis(w,e->q,b[s]*dt,e->k[s][0]);
@@ -1585,6 +1610,7 @@ int ork_batch_run_state(const ork_world *w, int B, double *q, double *qd, const 
       e->t = 0;
       for(i=0;i<nq;i++){ e->piv_type[i] = ORK_SF; e->piv_prev[i] = 0; e->tf[i] = 0; }
       for(i=0;i<ns;i++) e->c_active[i] = 0;
+      for(i=0;i<nl;i++) e->broken[i] = 0;
       ork_env_set_state(e,q+(size_t)nq*b,qd+(size_t)nq*b);
       if( u ) ork_env_set_motor_input(e,u+(size_t)nl*b); else memset(e->min,0,nl*8);
       ork_env_update_init(e);
@@ -1616,6 +1642,7 @@ int ork_batch_run(const ork_world *w, int B, double *q, double *qd, const double
       e->t = 0;
       for(i=0;i<nq;i++){ e->piv_type[i] = ORK_SF; e->piv_prev[i] = 0; e->tf[i] = 0; }
       for(i=0;i<w->nslot;i++) e->c_active[i] = 0;
+      for(i=0;i<nl;i++) e->broken[i] = 0;
       ork_env_set_state(e,q+(size_t)nq*b,qd+(size_t)nq*b);
       if( u ) ork_env_set_motor_input(e,u+(size_t)nl*b); else memset(e->min,0,nl*8);
       ork_env_update_init(e);

@@ -23,7 +23,9 @@ extern "C" {
 enum { ORK_JOINT_FIXED = 0, ORK_JOINT_REVOL = 1, ORK_JOINT_PRISM = 2,
        ORK_JOINT_SPHER = 3, ORK_JOINT_FLOAT = 4,
        ORK_JOINT_CYLIN = 5,   /* [EXT] cylindrical: dis = (translation along z, rotation about z) */
-       ORK_JOINT_HOOKE = 6 }; /* [EXT] hooke / universal: dis = (rotation about z, then about the new y): R = Rz(q0) Ry(q1) */
+       ORK_JOINT_HOOKE = 6,
+       ORK_JOINT_BRFLOAT = 7 };  /* [EXT A-17] breakable float (wall.ztk:51-95): rigid until the wrench it transmits exceeds its force or torque
+                                  * threshold in a committing evaluation, a float joint from then on */ /* [EXT] hooke / universal: dis = (rotation about z, then about the new y): R = Rz(q0) Ry(q1) */
 enum { ORK_MOTOR_NONE = 0, ORK_MOTOR_DC = 1, ORK_MOTOR_TRQ = 2 };
 enum { ORK_CONTACT_RIGID = 0, ORK_CONTACT_ELASTIC = 1 };
 enum { ORK_SF = 0, ORK_KF = 1 };                     /* static / kinetic friction state */
@@ -69,6 +71,10 @@ int ork_world_add_link_box(ork_world *w, int link, const double *R, const double
 void ork_world_unreg_self_collision(ork_world *w, int link);
 /* finish: builds (cell x box) pairs in registration order and associates contact info */
 void ork_world_finalize(ork_world *w);
+/* force / torque threshold of a breakable-float link */
+void ork_world_set_break(ork_world *w, int link, double fth, double tth);
+/* per link: 1 when its breakable-float joint has broken */
+void ork_env_get_broken(const ork_env *e, int *broken);
 int ork_world_nq(const ork_world *w);       /* total joint size */
 int ork_world_nslot(const ork_world *w);    /* contact slots = sum over pairs of nvert */
 int ork_world_nl(const ork_world *w);

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("ROKIFD_B200_LIB") or os.path.join(_HERE, "librokifd_b
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
-JOINT = {"fixed": 0, "revolute": 1, "prismatic": 2, "spherical": 3, "float": 4, "cylindrical": 5, "hooke": 6}
+JOINT = {"fixed": 0, "revolute": 1, "prismatic": 2, "spherical": 3, "float": 4, "cylindrical": 5, "hooke": 6, "breakablefloat": 7}
 MOTOR = {None: 0, "none": 0, "dc": 1, "trq": 2}
 CONTACT = {"rigid": 0, "elastic": 1}
 SOLVER = {"Vert": 0, "MLCP": 1, "Volume": 2}
@@ -35,7 +35,7 @@ class LinkDesc(C.Structure):
                 ("staticfriction", C.c_double), ("motortype", C.c_int),
                 ("motorconstant", C.c_double), ("admittance", C.c_double), ("gearratio", C.c_double),
                 ("rotorinertia", C.c_double), ("gearinertia", C.c_double), ("minvoltage", C.c_double),
-                ("maxvoltage", C.c_double)]
+                ("maxvoltage", C.c_double), ("forcethreshold", C.c_double), ("torquethreshold", C.c_double)]
 
 
 _LIB = None
@@ -129,6 +129,7 @@ class RkChain:
                 d.com[:] = list(np.asarray(l.com, float))
                 d.inertia[:] = list(np.asarray(l.inertia, float).reshape(9))
                 d.stiffness, d.viscosity, d.coulomb, d.staticfriction = l.stiffness, l.viscosity, l.coulomb, l.sfriction
+                d.forcethreshold, d.torquethreshold = getattr(l, "break_force", 0.0), getattr(l, "break_torque", 0.0)
                 if l.motor is not None:
                     m = l.motor
                     d.motortype = MOTOR[m.type]

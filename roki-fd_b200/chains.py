@@ -11,7 +11,7 @@ from typing import List, Optional
 
 import numpy as np
 
-NDOF = {"fixed": 0, "revolute": 1, "prismatic": 1, "spherical": 3, "float": 6, "cylindrical": 2, "hooke": 2}
+NDOF = {"fixed": 0, "revolute": 1, "prismatic": 1, "spherical": 3, "float": 6, "cylindrical": 2, "hooke": 2, "breakablefloat": 6}
 
 
 def rot_x(a):
@@ -65,6 +65,8 @@ class Link:
     coulomb: float = 0.0
     sfriction: float = 0.0
     motor: Optional[Motor] = None
+    break_force: float = 0.0       # breakablefloat: force / torque thresholds (ZTK `forcethreshold` / `torquethreshold`)
+    break_torque: float = 0.0
     shapes: List[np.ndarray] = field(default_factory=list)   # vertex clouds (n x 3, link frame)
     # box primitives as (center(3), depth, width, height) in the link frame.  On a static link: a collision target.  On a
     # moving link: a target for the vertices of OTHER links' cells, and its 8 corners are a cell of this link (after `shapes`)
@@ -207,7 +209,7 @@ def world_from_flat(desc):
     into one forest chain, every static box into its own all-fixed chain; the contact parameters of each (cell, box) pair
     come back through per-link / per-box `stuff` names.  Flattening the result again reproduces the description (the DC
     motor constants are folded in the description: an equivalent motor with gear ratio 1 is returned)."""
-    jt = {0: "fixed", 1: "revolute", 2: "prismatic", 3: "spherical", 4: "float", 5: "cylindrical", 6: "hooke"}
+    jt = {0: "fixed", 1: "revolute", 2: "prismatic", 3: "spherical", 4: "float", 5: "cylindrical", 6: "hooke", 7: "breakablefloat"}
     nl, nq, ncell, nbox, npair, nslot, nvert = (int(v) for v in desc["dims"])
     solver, pyramid, max_iter, integ = (int(v) for v in desc["prp"][:4])
     dt, fw = desc["prp"][4], desc["prp"][5]

@@ -149,6 +149,7 @@ extern "C" int rkChainB200AddLink(rkChain *c, const rkB200LinkDesc *d)
   std::memcpy(l.Ro, d->frame_R, sizeof l.Ro); std::memcpy(l.po, d->frame_p, sizeof l.po);
   l.mass = d->mass; std::memcpy(l.com, d->com, sizeof l.com); std::memcpy(l.inertia, d->inertia, sizeof l.inertia);
   l.stiffness = d->stiffness; l.viscosity = d->viscosity; l.coulomb = d->coulomb; l.sfriction = d->staticfriction;
+  l.brk_f = d->forcethreshold; l.brk_t = d->torquethreshold;
   l.motor.type = d->motortype; l.motor.k = d->motorconstant; l.motor.admittance = d->admittance; l.motor.gear = d->gearratio;
   l.motor.rotor_inertia = d->rotorinertia; l.motor.gear_inertia = d->gearinertia; l.motor.min = d->minvoltage; l.motor.max = d->maxvoltage;
   ci->links.push_back(l); ci->refresh();

@@ -54,13 +54,14 @@ RKFD_HD int link_slot_count(int jtype, int has_rigid){
     case J_SPHER: return has_rigid ? 42 : 36;                  /* U (18, w/gd aliased), Dinv (6), u (3), Rrel (9) [, w,gd] */
     case J_CYLIN: case J_HOOKE: return has_rigid ? 38 : 32;    /* U (12, w/gd aliased), Dinv (3), u (2), Rrel (9), prel (3), sin/cos q1 (2), pad [, w,gd] */
     case J_FLOAT: return has_rigid ? 45 : 18; /* a0 (6, w/gd aliased), Rrel (9), prel (3) [, IA^-1 (21), w,gd (6)] */
+    case J_BRFLOAT: return has_rigid ? 52 : 46; /* a0 (6), Rrel (9), prel (3), IA (rigid joint) or IA^-1 (broken) (21), pA (6), broken flag [, w,gd (6)] */
     default: return 6;                        /* w, gd */
   }
 }
 /* offset of (w, gd) inside the link slots */
 RKFD_HD int link_w_offset(int jtype, int has_rigid){
   if( !has_rigid ) return 0;
-  switch(jtype){ case J_REVOL: case J_PRISM: return 10; case J_SPHER: return 36; case J_FLOAT: return 39; case J_CYLIN: case J_HOOKE: return 32; default: return 0; }
+  switch(jtype){ case J_REVOL: case J_PRISM: return 10; case J_SPHER: return 36; case J_FLOAT: return 39; case J_CYLIN: case J_HOOKE: return 32; case J_BRFLOAT: return 46; default: return 0; }
 }
 constexpr int BRANCH_SLOTS = 15;   /* pass 1: Rw(9) pw(3) vl(3); pass 3: a(6) w(3) */
 constexpr int ACCUM_SLOTS = 27;    /* A(6) B(9) C(6) pf(3) pn(3) */
@@ -429,6 +430,11 @@ struct Core {
       const M3 Ro = org_R(L);
       if( VEL ){ vJ = tmul(x.R, mul(Ro, t3(qds))); wJ = tmul(x.R, mul(Ro, t3(qds+3))); }
     } break;
+    case J_BRFLOAT: {      /* frame as for the float joint; joint velocities only once it has broken (flag cached in the column by pass 1) */
+      x.R = ldm(sl+6); x.p = ld3(sl+15); x.ptl = tmul(x.R, x.p);
+      if( VEL ){ const M3 Ro = org_R(L); const V3 v = t3(qds), w = t3(qds+3);
+        if( c.S(sl+45) != 0.0 ){ vJ = tmul(x.R, mul(Ro, v)); wJ = tmul(x.R, mul(Ro, w)); } }
+    } break;
     case J_CYLIN: case J_HOOKE: {
       x.R = ldm(sl+17); x.p = ld3(sl+26); x.ptl = tmul(x.R, x.p);
       if( VEL ){ const double v0 = T(qds), v1 = T(qds+1);
@@ -438,6 +444,28 @@ struct Core {
     default: x.R = org_R(L); x.p = org_p(L); x.ptl = v3(L.pol[0],L.pol[1],L.pol[2]); break;
     }
     return x;
+  }
+  /* the joint type the ABA passes see: a breakable float is a fixed joint until it breaks, a float joint afterwards */
+  RKFD_HD int eff_jt(int jt, int sl){ return jt == J_BRFLOAT ? ( c.S(sl+45) != 0.0 ? (int)J_FLOAT : (int)J_FIXED ) : jt; }
+  /* free 6-DoF joint, inward pass: a0 = -IA^-1 pA into the column (and IA^-1 for the contact-solve probes) */
+  RKFD_HD void float_project(const S3 &A, const M3 &B, const S3 &C, V3 pf, V3 pn, int sl, bool keep_inverse){
+    double a[36];
+    a[0]=A.xx; a[1]=A.xy; a[2]=A.xz; a[6]=A.xy; a[7]=A.yy; a[8]=A.yz; a[12]=A.xz; a[13]=A.yz; a[14]=A.zz;
+    a[3]=B.xx; a[4]=B.xy; a[5]=B.xz; a[9]=B.yx; a[10]=B.yy; a[11]=B.yz; a[15]=B.zx; a[16]=B.zy; a[17]=B.zz;
+    a[18]=B.xx; a[19]=B.yx; a[20]=B.zx; a[24]=B.xy; a[25]=B.yy; a[26]=B.zy; a[30]=B.xz; a[31]=B.yz; a[32]=B.zz;
+    a[21]=C.xx; a[22]=C.xy; a[23]=C.xz; a[27]=C.xy; a[28]=C.yy; a[29]=C.yz; a[33]=C.xz; a[34]=C.yz; a[35]=C.zz;
+    spd6_inverse(a);
+    const double b[6] = {pf.x,pf.y,pf.z,pn.x,pn.y,pn.z};
+#pragma unroll
+    for(int r=0;r<6;r++){ double t = 0;
+#pragma unroll
+      for(int k=0;k<6;k++) t -= a[6*r+k]*b[k];
+      c.S(sl+r) = t; }
+    if( keep_inverse ){ int k = 0;
+#pragma unroll
+      for(int r=0;r<6;r++)
+#pragma unroll
+        for(int q=0;q<6;q++) if(q>=r){ c.S(sl+18+k) = a[6*r+q]; k++; } }
   }
   /* motion axes of the 2-DoF joints in the link frame ([EXT] cylindrical: (z; 0), (0; z); hooke: (0; Ry(q1)^T z), (0; y)) */
   RKFD_HD void axes2(int jt, int sl, V3 &l0, V3 &a0, V3 &l1, V3 &a1){
@@ -678,6 +706,13 @@ struct Core {
         stm(sl+6, x.R); st3(sl+15, x.p);
         vJ = tmul(x.R, mul(Ro, t3(qds+qo))); wJ = tmul(x.R, mul(Ro, t3(qds+qo+3)));
       } break;
+      case J_BRFLOAT: {
+        const M3 Ro = org_R(L); const bool brk = (piv >> qo) & 1u;
+        x.R = mm(Ro, aa_to_mat(t3(qs+qo+3))); x.p = org_p(L) + mul(Ro, t3(qs+qo));
+        stm(sl+6, x.R); st3(sl+15, x.p); c.S(sl+45) = brk ? 1.0 : 0.0;
+        const V3 v = t3(qds+qo), w = t3(qds+qo+3);
+        if( brk ){ vJ = tmul(x.R, mul(Ro, v)); wJ = tmul(x.R, mul(Ro, w)); }
+      } break;
       case J_CYLIN: {
         const M3 Ro = org_R(L); double sn, co; sincos(T(qs+qo+1), &sn, &co);
         const V3 o0 = col0(Ro), o1 = col1(Ro);
@@ -801,7 +836,7 @@ struct Core {
         pf = v3(fma(B.xy,zay,fma(B.xx,zax,pf.x)), fma(B.yy,zay,fma(B.yx,zax,pf.y)), fma(B.zy,zay,fma(B.zx,zax,pf.z)));
         pn = maddt(pn, B, zl);
         pn = v3(fma(C.xy,zay,fma(C.xx,zax,pn.x)), fma(C.yy,zay,fma(C.xy,zax,pn.y)), fma(C.yz,zay,fma(C.xz,zax,pn.z)));
-      } else if( JT<Kt>(i,L) != J_FLOAT ){
+      } else if( JT<Kt>(i,L) != J_FLOAT && !( JT<Kt>(i,L) == J_BRFLOAT && c.S(sl+45) != 0.0 ) ){
         const V3 omp = om - wJ;
         const V3 zl = cross(omp, cross(omp, x.ptl)) + 2.0*cross(omp, vJ);
         V3 za = cross(omp, wJ);
@@ -871,29 +906,23 @@ struct Core {
         B.zx-=Wl0.z*Ua0.x+Wl1.z*Ua1.x; B.zy-=Wl0.z*Ua0.y+Wl1.z*Ua1.y; B.zz-=Wl0.z*Ua0.z+Wl1.z*Ua1.z;
         pf = pf + u0*Wl0 + u1*Wl1; pn = pn + u0*Wa0 + u1*Wa1;
       } break;
-      case J_FLOAT: {
-        /* free 6-DoF joint: a = -IA^-1 pA, nothing is transmitted to the parent */
-        double a[36];
-        a[0]=A.xx; a[1]=A.xy; a[2]=A.xz; a[6]=A.xy; a[7]=A.yy; a[8]=A.yz; a[12]=A.xz; a[13]=A.yz; a[14]=A.zz;
-        a[3]=B.xx; a[4]=B.xy; a[5]=B.xz; a[9]=B.yx; a[10]=B.yy; a[11]=B.yz; a[15]=B.zx; a[16]=B.zy; a[17]=B.zz;
-        a[18]=B.xx; a[19]=B.yx; a[20]=B.zx; a[24]=B.xy; a[25]=B.yy; a[26]=B.zy; a[30]=B.xz; a[31]=B.yz; a[32]=B.zz;
-        a[21]=C.xx; a[22]=C.xy; a[23]=C.xz; a[27]=C.xy; a[28]=C.yy; a[29]=C.yz; a[33]=C.xz; a[34]=C.yz; a[35]=C.zz;
-        spd6_inverse(a);
-        const double b[6] = {pf.x,pf.y,pf.z,pn.x,pn.y,pn.z};
-#pragma unroll
-        for(int r=0;r<6;r++){ double s = 0;
-#pragma unroll
-          for(int k=0;k<6;k++) s -= a[6*r+k]*b[k];
-          c.S(sl+r) = s; }
-        if( m.has_rigid ){ int k = 0;
-#pragma unroll
-          for(int r=0;r<6;r++)
-#pragma unroll
-            for(int q=0;q<6;q++) if(q>=r){ c.S(sl+18+k) = a[6*r+q]; k++; } }
-      } break;
+      case J_FLOAT:       /* free 6-DoF joint: a = -IA^-1 pA, nothing is transmitted to the parent */
+        float_project(A, B, C, pf, pn, sl, m.has_rigid != 0);
+        break;
+      case J_BRFLOAT:
+        if( c.S(sl+45) != 0.0 ) float_project(A, B, C, pf, pn, sl, true);
+        else {             /* rigid: everything is handed to the parent; IA and p' are kept for the wrench test of pass 3 */
+          c.S(sl+18)=A.xx; c.S(sl+19)=A.xy; c.S(sl+20)=A.xz; c.S(sl+21)=A.yy; c.S(sl+22)=A.yz; c.S(sl+23)=A.zz;
+          stm(sl+24, B);
+          c.S(sl+33)=C.xx; c.S(sl+34)=C.xy; c.S(sl+35)=C.xz; c.S(sl+36)=C.yy; c.S(sl+37)=C.yz; c.S(sl+38)=C.zz;
+          st3(sl+39, pf); st3(sl+42, pn);
+        }
+        break;
       default: break;
       }
       if( ROOT<Kt>(i,L) || JT<Kt>(i,L) == J_FLOAT ) return;
+      if( JT<Kt>(i,L) == J_BRFLOAT && c.S(sl+45) != 0.0 ){    /* a broken joint transmits nothing (the lanes of a warp may differ here) */
+        A.xx=A.xy=A.xz=A.yy=A.yz=A.zz=0; C = A; B.xx=B.xy=B.xz=B.yx=B.yy=B.yz=B.zx=B.zy=B.zz=0; pf = v3(0,0,0); pn = pf; }
       /* X^T Ia X and X^T pa into the parent frame */
       const V3 p = x.p;
       const S3 Ar = xf_sym(x, A), Cr = xf_sym(x, C); const M3 Br = xf_gen(x, B);
@@ -1092,6 +1121,44 @@ struct Core {
           rk_lin(m, k, stage, qds+5, pqd+5, c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs+5, acca.z);
         }
       } break;
+      case J_BRFLOAT: {
+        /* broken: the float joint; rigid: the fixed joint whose six dofs are held (zero slopes), and in the committing
+         * evaluation the wrench it transmits, IA (X a_parent) + p' at the link origin ([EXT A-17]; rkChainUpdateABIWrench,
+         * rkfd_sim.c:511-514), is compared with its thresholds.  One code path for both: the integrator bookkeeping touches
+         * the T space, which only warp-uniform code may do. */
+        const bool brk = c.S(sl+45) != 0.0;
+        V3 accl = v3(0,0,0), acca = v3(0,0,0);
+        if( brk ){ const V3 a0l = ld3(sl), a0a = ld3(sl+3); const M3 RJ = mm(transpose(org_R(L)), x.R);
+          accl = mul(RJ, a0l - xl - zl); acca = mul(RJ, a0a - xa - za); al = a0l; aa = a0a; }
+        else { al = xl + zl; aa = xa + za; }
+        if( stage == ST_PROBE ){}
+        else if( stage >= ST_REF ){
+          c.gst(c.st.qdd,L.qofs,accl.x); c.gst(c.st.qdd,L.qofs+1,accl.y); c.gst(c.st.qdd,L.qofs+2,accl.z);
+          c.gst(c.st.qdd,L.qofs+3,acca.x); c.gst(c.st.qdd,L.qofs+4,acca.y); c.gst(c.st.qdd,L.qofs+5,acca.z);
+          if( !(fabs(accl.x)+fabs(accl.y)+fabs(accl.z)+fabs(acca.x)+fabs(acca.y)+fabs(acca.z) < 1.0e300) ) bad = 1;
+          if( !brk && ( stage == ST_REF || stage == ST_EVAL_REF ) ){
+            S3 A, C; A.xx=c.S(sl+18); A.xy=c.S(sl+19); A.xz=c.S(sl+20); A.yy=c.S(sl+21); A.yz=c.S(sl+22); A.zz=c.S(sl+23);
+            const M3 B = ldm(sl+24);
+            C.xx=c.S(sl+33); C.xy=c.S(sl+34); C.xz=c.S(sl+35); C.yy=c.S(sl+36); C.yz=c.S(sl+37); C.zz=c.S(sl+38);
+            const V3 f = ld3(sl+39) + mul(A, xl) + mul(B, xa), n = ld3(sl+42) + tmul(B, xl) + mul(C, xa);
+            if( norm(f) > L.brk_f || norm(n) > L.brk_t ) piv |= 1u << L.qofs;
+          }
+        } else {
+          const int qs = rk0 + L.qofs, qds = qs + m.nq, pq = qs + 2*m.nq, pqd = qs + 3*m.nq;
+          V3 v = t3(qds), w = t3(qds+3);
+          if( !brk ){ v = v3(0,0,0); w = v; }
+          rk_lin(m, k, stage, qs,   pq,   c.st.q[c.cur], c.st.q[c.cur^1], L.qofs,   v.x);
+          rk_lin(m, k, stage, qs+1, pq+1, c.st.q[c.cur], c.st.q[c.cur^1], L.qofs+1, v.y);
+          rk_lin(m, k, stage, qs+2, pq+2, c.st.q[c.cur], c.st.q[c.cur^1], L.qofs+2, v.z);
+          rk_rot(m, k, stage, qs+3, pq+3, c.st.q[c.cur], c.st.q[c.cur^1], L.qofs+3, w);
+          rk_lin(m, k, stage, qds,   pqd,   c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs,   accl.x);
+          rk_lin(m, k, stage, qds+1, pqd+1, c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs+1, accl.y);
+          rk_lin(m, k, stage, qds+2, pqd+2, c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs+2, accl.z);
+          rk_lin(m, k, stage, qds+3, pqd+3, c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs+3, acca.x);
+          rk_lin(m, k, stage, qds+4, pqd+4, c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs+4, acca.y);
+          rk_lin(m, k, stage, qds+5, pqd+5, c.st.qd[c.cur], c.st.qd[c.cur^1], L.qofs+5, acca.z);
+        }
+      } break;
       default: al = xl + zl; aa = xa + za; break;
       }
       if( JT<Kt>(i,L) == J_REVOL ) om = v3(omp.x, omp.y, omp.z + wJ.z); else om = omp + wJ;
@@ -1130,11 +1197,11 @@ struct Core {
     { const M3 Rw = ldm(m.link[Lc].frame_slot);
       const V3 fl = tmul(Rw, axis); dpf = -fl; dpn = -cross(rl, fl); }
     for(int i=Lc;;){
-      const LinkDev &L = m.link[i]; const int sl = L.slot;
+      const LinkDev &L = m.link[i]; const int sl = L.slot, ejt = eff_jt(L.jtype, sl);
       V3 paf = dpf, pan = dpn;
-      switch(L.jtype){
+      switch(ejt){
       case J_REVOL: case J_PRISM: {
-        const double du = L.jtype == J_REVOL ? -dpn.z : -dpf.z;
+        const double du = ejt == J_REVOL ? -dpn.z : -dpf.z;
         c.W(du0+6*i) = du;
         const double k = Q(Spec::sc(i,L)+2)*du;
         paf = dpf + k*ld3(sl); pan = dpn + k*ld3(sl+3);
@@ -1147,24 +1214,24 @@ struct Core {
         paf = dpf + mul(ldm(sl), k); pan = dpn + mul(ldm(sl+9), k);
       } break;
       case J_FLOAT: sw3(du0+6*i, dpf); sw3(du0+6*i+3, dpn); break;
-      case J_CYLIN: case J_HOOKE: { double d2[2]; probe2_in(L.jtype, sl, dpf, dpn, d2, paf, pan); c.W(du0+6*i) = d2[0]; c.W(du0+6*i+1) = d2[1]; } break;
+      case J_CYLIN: case J_HOOKE: { double d2[2]; probe2_in(ejt, sl, dpf, dpn, d2, paf, pan); c.W(du0+6*i) = d2[0]; c.W(du0+6*i+1) = d2[1]; } break;
       default: break;
       }
-      if( L.parent < 0 || L.jtype == J_FLOAT ) break;
+      if( L.parent < 0 || ejt == J_FLOAT ) break;
       V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
       dpf = xf_mul(x, paf); dpn = xf_mul(x, pan) + cross(x.p, dpf);
       i = L.parent;
     }
     for(int i=0;i<m.nl;i++){
-      const LinkDev &L = m.link[i]; const int sl = L.slot;
+      const LinkDev &L = m.link[i]; const int sl = L.slot, ejt = eff_jt(L.jtype, sl);
       V3 al = v3(0,0,0), aa = v3(0,0,0);
       if( L.parent >= 0 ){ al = w3(da0+6*L.parent); aa = w3(da0+6*L.parent+3); }
       V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
       V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
-      switch(L.jtype){
+      switch(ejt){
       case J_REVOL: case J_PRISM: {
         const double acc = Q(Spec::sc(i,L)+2)*( c.W(du0+6*i) - (dot(ld3(sl),xl) + dot(ld3(sl+3),xa)) );
-        if( L.jtype == J_REVOL ) xa.z += acc; else xl.z += acc;
+        if( ejt == J_REVOL ) xa.z += acc; else xl.z += acc;
       } break;
       case J_SPHER: {
         const V3 rhs = w3(du0+6*i) - (tmul(ldm(sl), xl) + tmul(ldm(sl+9), xa));
@@ -1178,7 +1245,7 @@ struct Core {
         for(int a=0;a<6;a++) for(int b=a;b<6;b++){ r[a] -= iv[k]*dp[b]; if( b != a ) r[b] -= iv[k]*dp[a]; k++; }
         xl = v3(r[0],r[1],r[2]); xa = v3(r[3],r[4],r[5]);
       } break;
-      case J_CYLIN: case J_HOOKE: { const double d2[2] = { c.W(du0+6*i), c.W(du0+6*i+1) }; probe2_out(L.jtype, sl, d2, xl, xa); } break;
+      case J_CYLIN: case J_HOOKE: { const double d2[2] = { c.W(du0+6*i), c.W(du0+6*i+1) }; probe2_out(ejt, sl, d2, xl, xa); } break;
       default: break;
       }
       sw3(da0+6*i, xl); sw3(da0+6*i+3, xa);
@@ -1205,7 +1272,7 @@ struct Core {
   RKFD_HD void probe_link(const ModelDev &m, int Lc, V3 dpf, V3 dpn, V3 &ral, V3 &raa){
     double du[6*MAX_LINKS]; int pth[MAX_LINKS]; int np = 0;
     for(int i=Lc;;){
-      const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = Spec::jtype(i,L);
+      const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = eff_jt(Spec::jtype(i,L), Spec::slot(i,L));
       pth[np] = i;
       V3 paf = dpf, pan = dpn;
       switch(jt){
@@ -1234,7 +1301,7 @@ struct Core {
     }
     V3 al = v3(0,0,0), aa = v3(0,0,0);
     for(int q=np-1;q>=0;q--){
-      const int i = pth[q]; const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = Spec::jtype(i,L);
+      const int i = pth[q]; const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = eff_jt(Spec::jtype(i,L), Spec::slot(i,L));
       V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
       V3 xl = xf_tmul(x, al + cross(aa, x.p)), xa = xf_tmul(x, aa);
       switch(jt){

@@ -199,6 +199,7 @@ RKFD_RARE M3 aa_to_mat(V3 aa){
 /* aa <- log( R(w) R(aa) ) through unit quaternions */
 RKFD_RARE V3 aa_cascade(V3 aa, V3 w){
   double th, s, q10, q20; V3 q1, q2;
+  if( w.x == 0.0 && w.y == 0.0 && w.z == 0.0 ) return aa;      /* no increment: the displacement is kept bit for bit (a held joint) */
   th = norm(aa);
   if( th < 1.0e-12 ){ q10 = 1.0; q1 = 0.5*aa; } else { s = sin(0.5*th)/th; q10 = cos(0.5*th); q1 = s*aa; }
   th = norm(w);

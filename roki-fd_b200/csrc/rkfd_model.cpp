@@ -134,6 +134,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
         d.Io[0]=Io[0]; d.Io[1]=0.5*(Io[1]+Io[3]); d.Io[2]=0.5*(Io[2]+Io[6]); d.Io[3]=Io[4]; d.Io[4]=0.5*(Io[5]+Io[7]); d.Io[5]=Io[8];
       }
       d.stiffness = l.stiffness; d.viscosity = l.viscosity; d.coulomb = l.coulomb; d.sfriction = l.sfriction;
+      d.brk_f = l.brk_f; d.brk_t = l.brk_t;
       d.mtype = l.motor.type;
       /* [EXT A-6] DC motor constants folded once on the host */
       d.m_tin = l.motor.gear*l.motor.k*l.motor.admittance;

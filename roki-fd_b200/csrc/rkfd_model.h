@@ -28,13 +28,14 @@ struct LinkHost {
   double com[3] = {0,0,0};
   double inertia[9] = {0,0,0, 0,0,0, 0,0,0};
   double stiffness = 0, viscosity = 0, coulomb = 0, sfriction = 0;
+  double brk_f = 0, brk_t = 0;               /* breakable float: force / torque thresholds */
   MotorHost motor;
   std::vector<std::vector<double>> shapes;   /* vertex clouds, 3 doubles per vertex, link frame */
   std::vector<BoxShape> boxes;               /* box primitives (kept for static links) */
 };
 
 inline int jtype_ndof(int jt){
-  switch(jt){ case J_REVOL: case J_PRISM: return 1; case J_CYLIN: case J_HOOKE: return 2; case J_SPHER: return 3; case J_FLOAT: return 6; default: return 0; }
+  switch(jt){ case J_REVOL: case J_PRISM: return 1; case J_CYLIN: case J_HOOKE: return 2; case J_SPHER: return 3; case J_FLOAT: case J_BRFLOAT: return 6; default: return 0; }
 }
 
 struct ChainHost {

@@ -32,7 +32,9 @@ constexpr int MAX_PYRAMID = 16;
 
 enum JointType : int { J_FIXED = 0, J_REVOL = 1, J_PRISM = 2, J_SPHER = 3, J_FLOAT = 4,
                        J_CYLIN = 5,      /* [EXT] cylindrical: (translation along z, rotation about z) */
-                       J_HOOKE = 6 };    /* [EXT] hooke / universal: R = Rz(q0) Ry(q1) */
+                       J_HOOKE = 6,      /* [EXT] hooke / universal: R = Rz(q0) Ry(q1) */
+                       J_BRFLOAT = 7 };  /* [EXT A-17] breakable float: rigid until the wrench it transmits exceeds a threshold in a committing
+                                          * evaluation, a float joint from then on (pivot bit of its first dof = broken) */
 enum MotorType : int { M_NONE = 0, M_DC = 1, M_TRQ = 2 };
 enum ContactType : int { C_RIGID = 0, C_ELASTIC = 1 };
 enum FricType : int { F_SF = 0, F_KF = 1 };
@@ -69,6 +71,7 @@ struct LinkDev {
   int wext_slot;       /* >=0: slots of the external wrench (6) (links that carry collision cells) */
   int frame_slot;      /* >=0 (worlds with rigid pairs, links with cells): Rw(9) pw(3) vl(3) w(3) a(6) = 24 slots */
   int cell_begin, cell_end;
+  double brk_f, brk_t; /* breakable float: force / torque thresholds */
   int mcol, pad_;      /* 1: a cell or a box of this link takes part in a moving-vs-moving pair (frame + wrench slots) */
 };
 

@@ -215,7 +215,7 @@
   RKFD_VOL_NI void vol_probe(const ModelDev &m, int Lc, V3 dpf, V3 dpn, int Lt, V3 &ral, V3 &raa){
     double du[6*MAX_LINKS]; int pth[MAX_LINKS]; int np = 0;
     for(int i=Lc;;){
-      const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = Spec::jtype(i,L);
+      const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = eff_jt(Spec::jtype(i,L), Spec::slot(i,L));
       pth[np] = i;
       V3 paf = dpf, pan = dpn;
       for(int k=0;k<6;k++) du[6*np+k] = 0.0;
@@ -244,10 +244,10 @@
       i = Spec::parent(i,L);
     }
     int pt[MAX_LINKS]; int nt = 0;
-    for(int i=Lt;;){ const LinkDev &L = m.link[i]; pt[nt++] = i; if( Spec::parent(i,L) < 0 || Spec::jtype(i,L) == J_FLOAT ) break; i = Spec::parent(i,L); }
+    for(int i=Lt;;){ const LinkDev &L = m.link[i]; pt[nt++] = i; if( Spec::parent(i,L) < 0 || eff_jt(Spec::jtype(i,L), Spec::slot(i,L)) == J_FLOAT ) break; i = Spec::parent(i,L); }
     V3 al = v3(0,0,0), aa = v3(0,0,0);
     for(int q=nt-1;q>=0;q--){
-      const int i = pt[q]; const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = Spec::jtype(i,L);
+      const int i = pt[q]; const LinkDev &L = m.link[i]; const int sl = Spec::slot(i,L), jt = eff_jt(Spec::jtype(i,L), Spec::slot(i,L));
       double d[6] = {0,0,0,0,0,0};
       for(int k=0;k<np;k++) if( pth[k] == i ) for(int r=0;r<6;r++) d[r] = du[6*k+r];
       V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);

@@ -267,6 +267,7 @@ bool ztk_read_chain(const char *filename, ChainHost &chain, std::string &err)
       const std::string jt = word(s, "jointtype");
       if( jt == "fixed" || jt.empty() ) l.jtype = J_FIXED; else if( jt == "revolute" ) l.jtype = J_REVOL; else if( jt == "prismatic" ) l.jtype = J_PRISM;
       else if( jt == "spherical" ) l.jtype = J_SPHER; else if( jt == "float" ) l.jtype = J_FLOAT;
+      else if( jt == "breakablefloat" ) l.jtype = J_BRFLOAT;
       else if( jt == "cylindrical" ) l.jtype = J_CYLIN; else if( jt == "hooke" || jt == "universal" ) l.jtype = J_HOOKE;
       else { err = "joint type '" + jt + "' of link '" + l.name + "' is not supported"; return false; }
       if( const Field *f = find(s, "mass") ) l.mass = num(*f, 0);
@@ -283,6 +284,9 @@ bool ztk_read_chain(const char *filename, ChainHost &chain, std::string &err)
         const double R[9] = { ct, -st, 0,  ca*st, ca*ct, -sa,  sa*st, sa*ct, ca };
         std::memcpy(l.Ro, R, sizeof R); l.po[0] = a; l.po[1] = -d*sa; l.po[2] = d*ca;
       }
+      if( const Field *f = find(s, "forcethreshold") ) l.brk_f = num(*f, 0);
+      if( const Field *f = find(s, "torquethreshold") ) l.brk_t = num(*f, 0);
+      if( const Field *f = find(s, "break") ){ l.brk_f = num(*f, 0); l.brk_t = num(*f, 1); }
       if( const Field *f = find(s, "stiffness") ) l.stiffness = num(*f, 0);
       if( const Field *f = find(s, "viscosity") ) l.viscosity = num(*f, 0);
       if( const Field *f = find(s, "coulomb") ) l.coulomb = num(*f, 0);
@@ -331,7 +335,7 @@ bool ztk_read_chain(const char *filename, ChainHost &chain, std::string &err)
       const LinkHost &l = chain.links[it->second]; const int o = chain.link_qofs(it->second), n = jtype_ndof(l.jtype);
       for(int k=0;k<n;k++){
         double v = num(f, 1+k);
-        const bool angular = l.jtype == J_REVOL || l.jtype == J_SPHER || l.jtype == J_HOOKE || ( l.jtype == J_FLOAT && k >= 3 ) || ( l.jtype == J_CYLIN && k == 1 );
+        const bool angular = l.jtype == J_REVOL || l.jtype == J_SPHER || l.jtype == J_HOOKE || ( ( l.jtype == J_FLOAT || l.jtype == J_BRFLOAT ) && k >= 3 ) || ( l.jtype == J_CYLIN && k == 1 );
         chain.dis[o+k] = angular ? v*DEG : v;      /* [EXT] angles are written in degrees */
       }
     }

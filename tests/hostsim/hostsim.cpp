@@ -70,6 +70,7 @@ HostSim *hostsim_new(int nchain, const int *chain_nl, const int *li, const doubl
       l.stiffness = d[25]; l.viscosity = d[26]; l.coulomb = d[27]; l.sfriction = d[28];
       l.motor.k = d[29]; l.motor.admittance = d[30]; l.motor.gear = d[31]; l.motor.rotor_inertia = d[32];
       l.motor.gear_inertia = d[33]; l.motor.min = d[34]; l.motor.max = d[35];
+      if( l.jtype == J_BRFLOAT ){ l.brk_f = d[36]; l.brk_t = d[29]; }     /* thresholds ride in spare fields (no motor on such a link) */
       ch->links.push_back(l);
     }
     h->chains.push_back(ch); h->world.chains.push_back(ch);

@@ -111,7 +111,8 @@ def test_ztk_reader_on_reference_models():
     """The reader accepts the reference's own model files unmodified."""
     d = "/root/reference/example/model"
     expect = {"box.ztk": (1, 6), "floor.ztk": (1, 0), "floor_hardsoft.ztk": (2, 0), "arm_2DoF.ztk": (3, 2),
-              "arm_2DoF_trq.ztk": (3, 2), "puma.ztk": (7, 6), "mighty.ztk": (25, 26), "arm.ztk": (6, 12), "dualarm.ztk": (None, None)}
+              "arm_2DoF_trq.ztk": (3, 2), "puma.ztk": (7, 6), "mighty.ztk": (25, 26), "arm.ztk": (6, 12), "dualarm.ztk": (None, None),
+              "wall.ztk": (4, 18), "crawler.ztk": (None, None), "box_small.ztk": (1, 6)}      # wall.ztk: three breakable float joints
     for f, (nl, nq) in expect.items():
         c = capi.RkChain(ztk=os.path.join(d, f))
         if nl is not None:

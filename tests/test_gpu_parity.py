@@ -783,3 +783,23 @@ def test_moving_vs_moving_contact(capi, oracle, kind):
         kind, (err < 1e-8).sum(), B, err.max(), same.sum(), o[3][:, nstat:].sum()))
     assert (err < 1e-8).mean() >= 0.99 and same.mean() >= 0.99
     fd.destroy()
+
+
+def test_breakable_float_joint(capi, oracle):
+    """the breakable float joint of example/model/wall.ztk:51-95 ([EXT A-17]): a cantilever of three
+    bricks whose middle joint gives way under gravity; 400 steps against the oracle."""
+    from test_kernel_core_host import brick_wall
+    w = ch.World(chains=[brick_wall([200.0, 4.0, 10.0], [200.0, 0.3, 10.0]), ch.floor_soft()],
+                 contact_info=[ch.ContactInfo("soft", "wall", "elastic", E=1000.0, V=10.0)])
+    B = 256
+    rng = np.random.default_rng(0)
+    q = np.zeros((B, w.nq)); qd = np.zeros((B, w.nq)); u = np.zeros((B, w.nl))
+    q[:, 9:12] = rng.uniform(-0.05, 0.05, (B, 3))
+    fd = gpu_world(capi, w, q, qd, u)
+    assert (fd.batch_get_pivot()[0][:, [0, 6, 12]] == [0, 1, 0]).all()        # broken flag = pivot bit of the joint's first dof
+    fd.update_n(400)
+    gq, gqd, _ = fd.batch_get_state()
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=400)
+    assert (fd.batch_get_status() == 0).all()
+    assert np.abs(gq - o[0]).max() < 1e-9 and (gq[:, 8] < -0.5).all() and (gq[:, :6] == q[:, :6]).all()
+    fd.destroy()

@@ -653,3 +653,40 @@ def test_two_dof_joints_under_the_rigid_contact_solvers(oracle, solver):
     assert (a == o[3]).all() and o[3].sum() > 0 and (hs.get_status() == 0).all()
     err = np.abs(hqdd - o[2]).max(1) / np.maximum(np.abs(o[2]).max(1), 1e-12)
     assert (err < 1e-8).all(), err
+
+
+def brick_wall(fth, tth):
+    """wall.ztk-like: a fixed base and three bricks sticking out sideways, held by breakable float joints (example/model/wall.ztk:51-95)."""
+    links = [ch.Link(name="base", jtype="fixed", mass=1.0, inertia=np.eye(3) * 1e-2, org_p=np.array([0, 0, 1.0]), stuff="wall")]
+    for k in range(3):
+        links.append(ch.Link(name="b%d" % k, jtype="breakablefloat", parent=k, mass=0.25, com=np.array([0.05, 0, 0]),
+                             inertia=np.diag([2.6e-4, 4.2e-4, 2.6e-4]), org_p=np.array([0.1, 0, 0]), stuff="wall",
+                             break_force=fth[k], break_torque=tth[k], shapes=[ch.box_verts(0.1, 0.05, 0.05, center=(0.05, 0, 0))]))
+    return ch.ChainModel("wall", links)
+
+
+def test_breakable_float_joint(oracle):
+    """[EXT A-17] breakable float: rigid while the wrench it transmits (IA a + pA in the committing evaluation) stays under its
+    thresholds, a float joint afterwards.  A cantilever of three bricks under gravity: the middle joint (0.3 N m) gives way at
+    the first committing evaluation - the two outer bricks fall as ONE body (the joint between them holds: 10 N m), the inner
+    brick stays.  The physics: the torque at the middle joint is the weight of two bricks at their lever arms."""
+    w = ch.World(chains=[brick_wall([200.0, 4.0, 10.0], [200.0, 0.3, 10.0]), ch.floor_soft()],
+                 contact_info=[ch.ContactInfo("soft", "wall", "elastic", E=1000.0, V=10.0)])
+    B = 6
+    rng = np.random.default_rng(0)
+    q = np.zeros((B, w.nq)); qd = np.zeros((B, w.nq)); u = np.zeros((B, w.nl))
+    q[:, 9:12] = rng.uniform(-0.05, 0.05, (B, 3))          # the middle brick mounted slightly turned
+    # static check of the threshold: torque about the middle joint = m g (0.05 + 0.15) = 0.49 N m > 0.3, force 2 m g = 4.9 N > 4
+    hs = HostSim(w, B); hs.set_state(q, qd, u); hs.eval(ref=True)
+    assert (hs.get_pivot()[0][:, [0, 6, 12]] == [0, 1, 0]).all()
+    for n in (1, 50, 400):
+        hs2 = HostSim(w, B); hs2.set_state(q, qd, u); hs2.eval(ref=True); hs2.step(n)
+        hq, hqd, _ = hs2.get_state()
+        o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=n)
+        assert np.abs(hq - o[0]).max() < 1e-9 and np.abs(hqd - o[1]).max() < 1e-8, n
+    assert (o[0][:, :6] == q[:, :6]).all() and (o[0][:, 12:] == q[:, 12:]).all()     # held joints keep their displacement bit for bit
+    assert (o[0][:, 8] < -0.5).all()                                                   # the broken one has fallen (onto the floor)
+    # with strong joints nothing moves
+    w2 = ch.World(chains=[brick_wall([200.0] * 3, [200.0] * 3)])
+    o2 = oracle.OracleWorld(w2).batch_run_state(q, qd, u, nsteps=50)
+    assert (o2[0] == q).all() and (o2[2] == 0).all()
