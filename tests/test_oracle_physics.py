@@ -507,3 +507,50 @@ def test_volume_wrench_respects_unilaterality_and_the_friction_cone(oracle):
             nkin += 1
             assert ft <= 0.3 * fn * (1 + 1e-9) + 1e-12
     assert nstat > 5 and nkin > 5
+
+
+def test_moving_vs_moving_contact_conserves_momentum_and_stacks(oracle):
+    """Oracle pin of the moving-vs-moving pairs ([EXT A-10] extended; rkfd_util.c:42-60, 268-282): (1) two free boxes colliding in
+    free fall exchange momentum - the total linear momentum changes by gravity only, the total angular momentum about the origin by
+    the gravity torque only (the contact force acts on one body, its opposite on the other AT THE SAME POINT); (2) a box resting on
+    another one on the soft floor: steady penetration m g / (4 E) of the upper box into the lower, 2 m g / (4 E) of the lower into
+    the floor (four corner vertices each; the upper box is the smaller one - corners of equal aligned boxes slide along each other's
+    faces and a vertex test never sees them)."""
+    def mbox(name, side=0.1):
+        return ch.ChainModel(name, [ch.Link(name="b", jtype="float", mass=0.5, stuff="body", inertia=np.eye(3) * 8.33e-4,
+                                            boxes=[((0.0, 0.0, 0.0), side, side, side)])])
+    ci = [ch.ContactInfo("body", "body", "elastic", E=2000.0, V=20.0, SF=0.5, KF=0.3), ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0, SF=0.5, KF=0.3)]
+    # (1) collision in free fall
+    w = ch.World(chains=[mbox("a"), mbox("b")], contact_info=ci)
+    e = oracle.OracleWorld(w).env()
+    q = np.zeros(12); q[0:3] = [-0.08, 0.01, 1.0]; q[6:9] = [0.08, -0.02, 1.03]; q[3:6] = [0.1, 0.2, 0.3]; q[9:12] = [-0.2, 0.1, 0.0]
+    qd = np.zeros(12); qd[0] = 1.0; qd[6] = -1.5; qd[4] = 2.0; qd[11] = -1.0
+    e.set_state(q, qd); e.update_init()
+    m, I, g = 0.5, 8.33e-4, 9.80665
+
+    def momenta():
+        qq, vv, _ = e.get_state()
+        P = m * (vv[0:3] + vv[6:9])
+        L = sum(np.cross(qq[o:o + 3], m * vv[o:o + 3]) + I * vv[o + 3:o + 6] for o in (0, 6))       # isotropic inertia: I w in any frame
+        return P, L, qq
+    P0, L0, q0 = momenta()
+    touched, Lg = False, np.zeros(3)
+    for k in range(300):
+        _, _, qq = momenta()
+        Lg += 0.001 * sum(np.cross(qq[o:o + 3], [0, 0, -m * g]) for o in (0, 6))          # gravity torque about the origin (rectangle rule)
+        e.update()
+        touched |= e.get_contact()[0].sum() > 0
+    P1, L1, _ = momenta()
+    assert touched
+    assert np.allclose(P1 - P0, [0, 0, -2 * m * g * 0.3], atol=1e-9)
+    assert np.allclose(L1 - L0, Lg, atol=2e-3 * max(1.0, np.abs(Lg).max()))       # quadrature of the gravity torque limits this check
+    # (2) resting stack
+    w = ch.World(chains=[mbox("lower"), mbox("upper", 0.08), ch.floor_soft()], contact_info=ci)
+    e = oracle.OracleWorld(w).env()
+    q = np.zeros(12); q[2] = 0.05; q[8] = 0.14
+    e.set_state(q, np.zeros(12)); e.update_init()
+    for _ in range(4000):
+        e.update()
+    qq, vv, _ = e.get_state()
+    assert np.abs(vv).max() < 1e-6
+    assert abs((0.05 - qq[2]) - 2 * m * g / (4 * 1000.0)) < 1e-6 and abs((0.09 - (qq[8] - qq[2])) - m * g / (4 * 2000.0)) < 1e-6
