@@ -326,9 +326,10 @@ void ork_world_finalize(ork_world *w)
       p.ci = w->cidef;
       for(i=0;i<w->nci;i++)
         if( (w->ci[i].sa==sa && w->ci[i].sb==sb) || (w->ci[i].sa==sb && w->ci[i].sb==sa) ){ p.ci = w->ci[i].ci; break; }
-      /* rigid contact between two MOVING links (A coupling two chains, rkfd_vert.c:125-151) is not restated: such pairs
-       * are not formed (the device side does the same and says so) */
-      if( w->box[b].link >= 0 && p.ci.type != ORK_CONTACT_ELASTIC ){ dropped++; continue; }
+      /* rigid contact between two MOVING links: the vertex solvers couple the two links / chains through A
+       * (rkfd_vert.c:125-185, rkfd_mlcp.c:76-142); the Volume solver's contact volume ([EXT A-15]) is formed against a static
+       * box only - such pairs are not formed under it (the device side does the same and says so) */
+      if( w->box[b].link >= 0 && p.ci.type != ORK_CONTACT_ELASTIC && w->solver == ORK_SOLVER_VOLUME ){ dropped++; continue; }
       p.sofs = sofs; sofs += w->cell[c].nvert;
       w->pair[n++] = p;
     }
@@ -747,23 +748,32 @@ static void aba_forward(ork_env *e, double *qdd, int use_du)
 
 /* [EXT A-5] rkChainUpdateCachedABIPair: unit test wrench (f at world point vert) on `link`;
  * bias-only inward propagation with the cached articulated inertias, then the outward pass */
-static void aba_probe(ork_env *e, int link, const double *vert, const double *fw)
+static void aba_probe2(ork_env *e, int link, int link2, const double *vert, const double *fw)
 {
-  const ork_world *w = e->w; int i, j, k, r; ork_lw *x = &e->lw[link]; double pos[3], fl[3], n[3];
+  const ork_world *w = e->w; int i, j, k, r, t;
   for(i=0;i<w->nl;i++){ memset(e->lw[i].du,0,sizeof e->lw[i].du); memset(e->lw[i].dp,0,sizeof e->lw[i].dp); }
-  v3_sub(vert,x->pw,pos); m3_tmulv(x->Rw,pos,pos); m3_tmulv(x->Rw,fw,fl); v3_cross(pos,fl,n);
-  for(r=0;r<3;r++){ x->dp[r] = -fl[r]; x->dp[3+r] = -n[r]; }
-  for(i=link;i>=0;i=w->link[i].parent){
-    const ork_link *l = &w->link[i]; ork_lw *y = &e->lw[i]; int nd = e->nd[i]; double pa[6], t6[6];
+  /* the test wrench on `link`, its opposite on the partner `link2` (a moving partner: rkfd_vert.c:166-175) */
+  for(t=0;t<2;t++){ int lk = t ? link2 : link; ork_lw *x; double pos[3], fl[3], n[3], sg = t ? -1.0 : 1.0;
+    if( lk < 0 ) continue;
+    x = &e->lw[lk];
+    v3_sub(vert,x->pw,pos); m3_tmulv(x->Rw,pos,pos); m3_tmulv(x->Rw,fw,fl); v3_cross(pos,fl,n);
+    for(r=0;r<3;r++){ x->dp[r] += -sg*fl[r]; x->dp[3+r] += -sg*n[r]; } }
+  /* bias-only inward pass: links in descending index order (parents precede their children), so that a link that
+   * collects the increments of two paths (the two links of one chain) is processed once, with their sum */
+  for(i=w->nl-1;i>=0;i--){
+    const ork_link *l = &w->link[i]; ork_lw *y = &e->lw[i]; int nd = e->nd[i]; double pa[6], t6[6], nz = 0;
+    for(r=0;r<6;r++) nz += fabs(y->dp[r]);
+    if( nz == 0.0 ) continue;
     memcpy(pa,y->dp,sizeof pa);
     for(j=0;j<nd;j++){ double s=0; for(k=0;k<6;k++) s += y->S[6*k+j]*y->dp[k]; y->du[j] = -s; }
     for(j=0;j<nd;j++){ t6[j]=0; for(k=0;k<nd;k++) t6[j] += y->Dinv[6*j+k]*y->du[k]; }
     for(r=0;r<6;r++) for(j=0;j<nd;j++) pa[r] += y->U[6*r+j]*t6[j];
-    if( l->parent < 0 ) break;
+    if( l->parent < 0 ) continue;
     m6_tmulv(y->X,pa,t6); for(r=0;r<6;r++) e->lw[l->parent].dp[r] += t6[r];
   }
   aba_forward(e,NULL,1);
 }
+static void aba_probe(ork_env *e, int link, const double *vert, const double *fw){ aba_probe2(e,link,-1,vert,fw); }
 
 /* ------------------------------------------------------------------------------------ */
 /* zLESolveMP restatement for a symmetric matrix: x = pinv(a) b through a cyclic Jacobi
@@ -889,28 +899,32 @@ static void solver_rigid(ork_env *e, int do_up_ref)
 {
   const ork_world *w = e->w; int pi, k, N = 0, n, i, j, col;
   int *slot = (int*)malloc((w->nslot>0?w->nslot:1)*sizeof(int)), *plink = (int*)malloc((w->nslot>0?w->nslot:1)*sizeof(int));
+  int *blink = (int*)malloc((w->nslot>0?w->nslot:1)*sizeof(int));      /* the partner's link when it moves, else -1 */
   const ork_cinfo **pci = (const ork_cinfo**)malloc((w->nslot>0?w->nslot:1)*sizeof(void*));
   double *A = e->rA, *b = e->rb, *f = e->rf, dt = w->dt;
   /* _rkFDSolverCountContacts (rkfd_vert.c:22-29): contacts in (pair, vertex) order */
   for(pi=0;pi<w->npair;pi++){
     const ork_pair *p = &w->pair[pi]; const ork_cell *cl = &w->cell[p->cell];
     if( p->ci.type != ORK_CONTACT_RIGID ) continue;
-    for(k=0;k<cl->nvert;k++) if( e->c_active[p->sofs+k] ){ slot[N]=p->sofs+k; plink[N]=cl->link; pci[N]=&p->ci; N++; }
+    for(k=0;k<cl->nvert;k++) if( e->c_active[p->sofs+k] ){ slot[N]=p->sofs+k; plink[N]=cl->link; blink[N]=w->box[p->box].link; pci[N]=&p->ci; N++; }
   }
   e->rn = 0;
-  if( N == 0 ){ free(slot); free(plink); free(pci); return; }
+  if( N == 0 ){ free(slot); free(plink); free(blink); free(pci); return; }
   n = 3*N; e->rn = n;
   /* rkFDUpdateAccBias (rkfd_util.c:149-161): full ABA with the friction / penalty wrenches, save */
   aba_backward(e); aba_forward(e,NULL,0);
   for(i=0;i<w->nl;i++) memcpy(e->lw[i].a0,e->lw[i].a,sizeof e->lw[i].a);
   /* _rkFDSolverBiasAcc (rkfd_vert.c:107-123 / rkfd_mlcp.c:58-74) */
+  /* rkFDChainPointRelativeAcc (rkfd_util.c:103-118): the vertex's link minus the partner's (0 for a static partner) */
   for(k=0;k<N;k++){ double av[3]; link_point_wld_acc(&e->lw[plink[k]],e->c_vert+3*slot[k],av);
+    if( blink[k] >= 0 ){ double ab[3]; link_point_wld_acc(&e->lw[blink[k]],e->c_vert+3*slot[k],ab); v3_sub(av,ab,av); }
     for(i=0;i<3;i++) b[3*k+i] = v3_dot(e->c_axis+9*slot[k]+3*i,av); }
   /* _rkFDSolverRelationAccForce (rkfd_vert.c:153-185 / rkfd_mlcp.c:104-142): 3N cached-ABA probes */
   for(k=0;k<N;k++) for(i=0;i<3;i++){
     col = 3*k+i;
-    aba_probe(e,plink[k],e->c_vert+3*slot[k],e->c_axis+9*slot[k]+3*i);
+    aba_probe2(e,plink[k],blink[k],e->c_vert+3*slot[k],e->c_axis+9*slot[k]+3*i);
     for(j=0;j<N;j++){ double av[3]; int ii; link_point_wld_acc(&e->lw[plink[j]],e->c_vert+3*slot[j],av);
+      if( blink[j] >= 0 ){ double ab[3]; link_point_wld_acc(&e->lw[blink[j]],e->c_vert+3*slot[j],ab); v3_sub(av,ab,av); }
       for(ii=0;ii<3;ii++) A[n*(3*j+ii)+col] = v3_dot(e->c_axis+9*slot[j]+3*ii,av) - b[3*j+ii]; }
   }
   /* rkFDChainRestoreABIAccBiasPair */
@@ -919,6 +933,7 @@ static void solver_rigid(ork_env *e, int do_up_ref)
   for(i=0;i<n;i++) b[i] *= dt;
   for(k=0;k<N;k++){ double *vel = e->c_vel+3*slot[k];
     link_point_wld_vel(&e->lw[plink[k]],e->c_vert+3*slot[k],vel);
+    if( blink[k] >= 0 ){ double vb[3]; link_point_wld_vel(&e->lw[blink[k]],e->c_vert+3*slot[k],vb); v3_sub(vel,vb,vel); }
     for(i=0;i<3;i++) b[3*k+i] += v3_dot(vel,e->c_axis+9*slot[k]+3*i); }
 
   if( w->solver == ORK_SOLVER_MLCP ){
@@ -957,6 +972,7 @@ static void solver_rigid(ork_env *e, int do_up_ref)
     for(k=0;k<N;k++){ int s = slot[k]; double *fw = e->c_f+3*s, fn, fss, mu;
       fw[0]=fw[1]=fw[2]=0; for(i=0;i<3;i++) v3_cat(fw,f[3*k+i],e->c_axis+9*s+3*i);
       push_wrench(e,plink[k],e->c_vert+3*s,fw);
+      if( blink[k] >= 0 ){ double fr[3] = { -fw[0], -fw[1], -fw[2] }; push_wrench(e,blink[k],e->c_vert+3*s,fr); }
       fn = fw[0]; fss = sqrt(fw[1]*fw[1]+fw[2]*fw[2]);
       mu = e->c_type[s]==ORK_SF ? pci[k]->SF : pci[k]->KF;
       if( fss > mu*fn - ORK_TOL ){ e->c_type[s] = ORK_KF; v3_copy(e->c_pro+3*s,e->c_ref+3*s); }
@@ -989,13 +1005,14 @@ static void solver_rigid(ork_env *e, int do_up_ref)
     for(k=0;k<N;k++){ int s = slot[k], flag = 0; double *fw = e->c_f+3*s;
       fw[0]=fw[1]=fw[2]=0; for(i=0;i<3;i++) v3_cat(fw,f[3*k+i],e->c_axis+9*s+3*i);
       push_wrench(e,plink[k],e->c_vert+3*s,fw);
+      if( blink[k] >= 0 ){ double fr[3] = { -fw[0], -fw[1], -fw[2] }; push_wrench(e,blink[k],e->c_vert+3*s,fr); }
       if( do_up_ref ){
         for(i=0;i<pyr;i++) if( idx[pyr*k+i] ){ flag = 1; break; }
         if( flag ){ e->c_type[s] = ORK_KF; v3_copy(e->c_pro+3*s,e->c_ref+3*s); }
         else e->c_type[s] = ORK_SF; } }
     free(nf); free(dz); free(Q); free(c); free(c2); free(init); free(idx);
   }
-  free(slot); free(plink); free(pci);
+  free(slot); free(plink); free(blink); free(pci);
 }
 
 /* ------------------------------------------------------------------------------------ */

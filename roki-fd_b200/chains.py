@@ -186,8 +186,8 @@ class World:
     @property
     def nslot(self):
         """Contact slots = sum over pairs of the cell's vertices: every cell of a moving link against every static box, and
-        against the box primitives of other moving links (other chains; the same chain only with `self_collide`; elastic
-        contact info only) - the rule of rkfd_model.cpp / the oracle's ork_world_finalize."""
+        against the box primitives of other moving links (other chains; the same chain only with `self_collide`; under the
+        Volume solver elastic contact info only) - the rule of rkfd_model.cpp / the oracle's ork_world_finalize."""
         links = self.flat_links()
         n = sum(v.shape[0] for l in links for v in l.cells()) * len(self.boxes)
         chain_of, self_col = [], []
@@ -197,7 +197,7 @@ class World:
             for b, lb in enumerate(links):
                 if a == b or not lb.boxes or (chain_of[a] == chain_of[b] and not self_col[chain_of[a]]):
                     continue
-                if self._ci_type(la.stuff, lb.stuff) != "elastic":
+                if self._ci_type(la.stuff, lb.stuff) != "elastic" and self.solver == "Volume":
                     continue
                 n += sum(v.shape[0] for v in la.cells()) * len(lb.boxes)
         return n

@@ -67,7 +67,7 @@ constexpr int BRANCH_SLOTS = 15;   /* pass 1: Rw(9) pw(3) vl(3); pass 3: a(6) w(
 constexpr int ACCUM_SLOTS = 27;    /* A(6) B(9) C(6) pf(3) pn(3) */
 constexpr int WEXT_SLOTS = 6;
 constexpr int FRAME_SLOTS = 24;    /* rigid worlds, links with cells: Rw(9) pw(3) vl(3) w(3) a(6) */
-constexpr int GEO_DOUBLES = 27;    /* per rigid contact: vw n t1 t2 d vel prob rl (8 x 3), slot, link, pair */
+constexpr int GEO_DOUBLES = 28;    /* per rigid contact: vw n t1 t2 d vel prob rl (8 x 3), slot, link, pair, partner link (-1: static) */
 /* per-environment workspace of the wrench-coordinate contact paths: Lambda (6x6, column-major) per group, then per contact
  * g (3x6) h (3x6) b (3) diag (3) f (3) rho (3) prob (3) mu slot */
 constexpr int MAX_RG = 4;                      /* contact groups (links in different chains) of the wrench-coordinate paths */
@@ -594,7 +594,8 @@ struct Core {
    * another link; reference: rkFDChainPointRelativeVel rkfd_util.c:42-60 - the velocity of the vertex's link minus the box
    * link's at the contact point - and rkFDContactForcePushWrench rkfd_util.c:268-282 - the force on the vertex's link, its
    * opposite on the partner, both at the contact point).  Runs after pass 1, when every link frame of the evaluation is known
-   * (frame slots of the links involved).  Elastic pairs (rkFDSolverPenalty, rkfd_penalty.c:11-31); generic kernel only. */
+   * (frame slots of the links involved).  Elastic pairs: rkFDSolverPenalty (rkfd_penalty.c:11-31); rigid pairs: detection and
+   * the persistent vertex state only, their forces come from the dense rigid path (rigid_solve).  Generic kernel only. */
   RKFD_HD void contacts_moving(const ModelDev &m, bool ref){
     for(int pi=m.npair_static; pi<m.npair; pi++){
       const PairDev &pr = m.pair[pi]; const CellDev &cl = m.cell[pr.cell]; const MBoxDev &mb = m.mbox[pr.mbox];
@@ -631,6 +632,7 @@ struct Core {
           if( !(cfl & abit) ){ cfl = (cfl | abit) & ~kbit; refb = prob;
             c.gst(c.st.cref, 3*s, refb.x); c.gst(c.st.cref, 3*s+1, refb.y); c.gst(c.st.cref, 3*s+2, refb.z);
           } else refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
+          if( pr.type != C_ELASTIC ) continue;     /* rigid pairs are solved by the rigid path */
           const V3 d = vw - (pb + mul(Rb, refb));
           const V3 vr = (vlw + cross(omw, vw - pw)) - (vlwB + cross(omwB, vw - pwB));
           V3 f = (-pr.E)*d + (-1.0*(pr.V + pr.E*m.dt))*vr;
@@ -1190,37 +1192,43 @@ struct Core {
   /* one probe: unit force `axis` (world) at vertex `rl` (link frame) of link `Lc`; fills the increments of the
    * link accelerations da[col][link] ([EXT A-5] rkChainUpdateCachedABIPair: bias-only inward pass along the
    * path to the root with the cached articulated inertias, then the outward pass) */
-  RKFD_HD void probe(const ModelDev &m, int col, int Lc, V3 rl, V3 axis){
+  RKFD_HD void probe(const ModelDev &m, int col, int Lc, V3 rl, V3 axis, int Lb = -1, V3 vw = V3()){
     const int du0 = m.ws_du + col*6*m.nl, da0 = m.ws_da + col*6*m.nl;
     for(int k=0;k<6*m.nl;k++) c.W(du0+k) = 0.0;
-    V3 dpf, dpn;
-    { const M3 Rw = ldm(m.link[Lc].frame_slot);
+    /* the unit force on the vertex's link and, when the partner moves, its opposite on the partner's link at the same world
+     * point (rkfd_vert.c:166-175): two bias-only inward walks; the joint-space increments of links on both paths add up */
+    for(int side=0; side<( Lb >= 0 ? 2 : 1 ); side++){
+    V3 dpf, dpn; int i0 = Lc;
+    if( side == 0 ){ const M3 Rw = ldm(m.link[Lc].frame_slot);
       const V3 fl = tmul(Rw, axis); dpf = -fl; dpn = -cross(rl, fl); }
-    for(int i=Lc;;){
+    else { const int fb = m.link[Lb].frame_slot; const M3 RwB = ldm(fb);
+      const V3 fl = tmul(RwB, axis), rb = tmul(RwB, vw - ld3(fb+9)); dpf = fl; dpn = cross(rb, fl); i0 = Lb; }
+    for(int i=i0;;){
       const LinkDev &L = m.link[i]; const int sl = L.slot, ejt = eff_jt(L.jtype, sl);
       V3 paf = dpf, pan = dpn;
       switch(ejt){
       case J_REVOL: case J_PRISM: {
         const double du = ejt == J_REVOL ? -dpn.z : -dpf.z;
-        c.W(du0+6*i) = du;
+        c.W(du0+6*i) += du;
         const double k = Q(Spec::sc(i,L)+2)*du;
         paf = dpf + k*ld3(sl); pan = dpn + k*ld3(sl+3);
       } break;
       case J_SPHER: {
         const M3 E = tmm(ldm(sl+27), org_R(L));
         const V3 du = -tmul(E, dpn);
-        sw3(du0+6*i, du);
+        sw3(du0+6*i, w3(du0+6*i) + du);
         const V3 k = mul(lds(sl+18), du);
         paf = dpf + mul(ldm(sl), k); pan = dpn + mul(ldm(sl+9), k);
       } break;
-      case J_FLOAT: sw3(du0+6*i, dpf); sw3(du0+6*i+3, dpn); break;
-      case J_CYLIN: case J_HOOKE: { double d2[2]; probe2_in(ejt, sl, dpf, dpn, d2, paf, pan); c.W(du0+6*i) = d2[0]; c.W(du0+6*i+1) = d2[1]; } break;
+      case J_FLOAT: sw3(du0+6*i, w3(du0+6*i) + dpf); sw3(du0+6*i+3, w3(du0+6*i+3) + dpn); break;
+      case J_CYLIN: case J_HOOKE: { double d2[2]; probe2_in(ejt, sl, dpf, dpn, d2, paf, pan); c.W(du0+6*i) += d2[0]; c.W(du0+6*i+1) += d2[1]; } break;
       default: break;
       }
       if( L.parent < 0 || ejt == J_FLOAT ) break;
       V3 vJ, wJ; const XF x = joint_xform<TagRT,false>(m, L, i, vJ, wJ);
       dpf = xf_mul(x, paf); dpn = xf_mul(x, pan) + cross(x.p, dpf);
       i = L.parent;
+    }
     }
     for(int i=0;i<m.nl;i++){
       const LinkDev &L = m.link[i]; const int sl = L.slot, ejt = eff_jt(L.jtype, sl);
@@ -1752,36 +1760,52 @@ struct Core {
       for(int k=lane;k<N;k+=nlanes){
         int s = 0, cnt = -1;
         for(;s<m.nslot;s++){ if( (fl & m.rigid_mask) >> (2*s) & 1ull ){ if( ++cnt == k ) break; } }
-        const PairDev &pr = m.pair[m.slot_pair[s]]; const CellDev &cl = m.cell[pr.cell]; const BoxDev &bx = m.box[pr.box];
+        const PairDev &pr = m.pair[m.slot_pair[s]]; const CellDev &cl = m.cell[pr.cell];
         const LinkDev &L = m.link[cl.link];
         const int vi = cl.vofs + m.slot_vert[s];
         const V3 rl = v3(m.vert[3*vi], m.vert[3*vi+1], m.vert[3*vi+2]);
         const M3 Rw = ldm(L.frame_slot); const V3 pw = ld3(L.frame_slot+9), vl = ld3(L.frame_slot+12), om = ld3(L.frame_slot+15);
         const V3 al = ld3(L.frame_slot+18), aa = ld3(L.frame_slot+21);
-        const M3 Rb = box_R(bx); const V3 pb = v3(bx.p[0],bx.p[1],bx.p[2]);
-        const V3 vw = pw + mul(Rw, rl), vb = tmul(Rb, vw - pb);
+        const V3 vw = pw + mul(Rw, rl);
+        /* the box: static, or carried by the partner link (its frame of this evaluation); rkFDChainPointRelativeVel / -Acc
+         * (rkfd_util.c:42-60, 103-118): the vertex's link minus the partner's at the contact point, 0 for a static partner */
+        BoxDev bx; M3 Rb; V3 pb, velB = v3(0,0,0), accB = v3(0,0,0); int Lb = -1;
+        if( pr.mbox >= 0 ){
+          const MBoxDev &mb = m.mbox[pr.mbox]; Lb = mb.link; const int fb = m.link[Lb].frame_slot;
+          const M3 RwB = ldm(fb); const V3 pwB = ld3(fb+9), vlB = ld3(fb+12), omB = ld3(fb+15), alB = ld3(fb+18), aaB = ld3(fb+21);
+          M3 Rl; Rl.xx=mb.R[0]; Rl.xy=mb.R[1]; Rl.xz=mb.R[2]; Rl.yx=mb.R[3]; Rl.yy=mb.R[4]; Rl.yz=mb.R[5]; Rl.zx=mb.R[6]; Rl.zy=mb.R[7]; Rl.zz=mb.R[8];
+          Rb = mm(RwB, Rl); pb = pwB + mul(RwB, v3(mb.p[0], mb.p[1], mb.p[2]));
+          for(int i=0;i<3;i++) bx.half[i] = mb.half[i];
+          const V3 rB = tmul(RwB, vw - pwB);
+          velB = mul(RwB, vlB) + cross(mul(RwB, omB), vw - pwB);
+          accB = mul(RwB, alB + cross(aaB, rB) + cross(omB, cross(omB, rB)));
+        } else { bx = m.box[pr.box]; Rb = box_R(bx); pb = v3(bx.p[0],bx.p[1],bx.p[2]); }
+        const V3 vb = tmul(Rb, vw - pb);
         V3 nn, t1, t2, prob;
         box_face(bx, Rb, vb, bx.half[0]-fabs(vb.x), bx.half[1]-fabs(vb.y), bx.half[2]-fabs(vb.z), nn, t1, t2, prob);
         const V3 refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
         const V3 d = vw - (pb + mul(Rb, refb));
-        const V3 vel = mul(Rw, vl) + cross(mul(Rw, om), vw - pw);
+        const V3 vel = mul(Rw, vl) + cross(mul(Rw, om), vw - pw) - velB;
         /* rkFDLinkPointWldAcc (rkfd_util.c:92-101): R ( a + alpha x r + w x (w x r) ) */
         const V3 r = tmul(Rw, vw - pw);
-        const V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r)));
+        const V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r))) - accB;
         sg3(m,k,0,vw); sg3(m,k,3,nn); sg3(m,k,6,t1); sg3(m,k,9,t2); sg3(m,k,12,d); sg3(m,k,15,vel); sg3(m,k,18,prob); sg3(m,k,21,rl);
-        G(m,k,24) = (double)s; G(m,k,25) = (double)cl.link; G(m,k,26) = (double)m.slot_pair[s];
+        G(m,k,24) = (double)s; G(m,k,25) = (double)cl.link; G(m,k,26) = (double)m.slot_pair[s]; G(m,k,27) = (double)Lb;
         c.W(ob+3*k) = dot(nn, accp); c.W(ob+3*k+1) = dot(t1, accp); c.W(ob+3*k+2) = dot(t2, accp);
       }
       c.gsync();
       /* ---- A: one probe per (contact, axis) column (rkfd_vert.c:153-185) */
       for(int col=lane;col<n;col+=nlanes){
         const int k = col/3, i = col - 3*k;
-        probe(m, col, (int)G(m,k,25), g3(m,k,21), g3(m,k,3+3*i));
+        probe(m, col, (int)G(m,k,25), g3(m,k,21), g3(m,k,3+3*i), (int)G(m,k,27), g3(m,k,0));
         const int da0 = m.ws_da + col*6*m.nl;
         for(int j=0;j<N;j++){
-          const int Lj = (int)G(m,j,25);
+          const int Lj = (int)G(m,j,25), Bj = (int)G(m,j,27);
           const V3 dl = w3(da0+6*Lj), dal = w3(da0+6*Lj+3), r = g3(m,j,21);
-          const V3 resp = mul(ldm(m.link[Lj].frame_slot), dl + cross(dal, r));
+          V3 resp = mul(ldm(m.link[Lj].frame_slot), dl + cross(dal, r));
+          if( Bj >= 0 ){ const int fb = m.link[Bj].frame_slot; const M3 RwB = ldm(fb);
+            const V3 rB = tmul(RwB, g3(m,j,0) - ld3(fb+9));
+            resp = resp - mul(RwB, w3(da0+6*Bj) + cross(w3(da0+6*Bj+3), rB)); }
           c.W(oA+(3*j)*n+col) = dot(g3(m,j,3), resp); c.W(oA+(3*j+1)*n+col) = dot(g3(m,j,6), resp); c.W(oA+(3*j+2)*n+col) = dot(g3(m,j,9), resp);
         }
       }
@@ -1870,6 +1894,13 @@ struct Core {
     const V3 t = cross(pos, fl);
     c.S(L.wext_slot) += fl.x; c.S(L.wext_slot+1) += fl.y; c.S(L.wext_slot+2) += fl.z;
     c.S(L.wext_slot+3) += t.x; c.S(L.wext_slot+4) += t.y; c.S(L.wext_slot+5) += t.z;
+    const int Lb = (int)G(m,k,27);
+    if( Lb >= 0 ){          /* the partner takes the opposite force at the same point (rkfd_util.c:276-278) */
+      const LinkDev &B = m.link[Lb]; const M3 RwB = ldm(B.frame_slot);
+      const V3 posB = tmul(RwB, g3(m,k,0) - ld3(B.frame_slot+9)), flB = tmul(RwB, v3(-fw.x, -fw.y, -fw.z)), tB = cross(posB, flB);
+      c.S(B.wext_slot) += flB.x; c.S(B.wext_slot+1) += flB.y; c.S(B.wext_slot+2) += flB.z;
+      c.S(B.wext_slot+3) += tB.x; c.S(B.wext_slot+4) += tB.y; c.S(B.wext_slot+5) += tB.z;
+    }
     if( ref ){ c.gst(c.st.cf,3*s,fw.x); c.gst(c.st.cf,3*s+1,fw.y); c.gst(c.st.cf,3*s+2,fw.z); }
   }
 

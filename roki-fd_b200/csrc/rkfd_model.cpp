@@ -188,9 +188,10 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   for(int p=0;p<m.npair;p++) m.pair[p].mbox = -1;
   m.npair_static = m.npair;
   /* ---- moving-vs-moving pairs ([EXT A-10]: vertices of a cell against a box primitive carried by ANOTHER link - of another
-   * chain, or of the same chain while its self-collision pairs are registered, rkCDPairChainUnreg).  Elastic contact info
-   * only: rigid contact between two moving links (A coupling two chains, rkfd_vert.c:125-151) is not built; such pairs
-   * are left out and reported. */
+   * chain, or of the same chain while its self-collision pairs are registered, rkCDPairChainUnreg).  Rigid contact info
+   * between two moving links goes through the dense vertex solvers (A couples the two links / chains: rkfd_vert.c:125-185,
+   * rkfd_mlcp.c:76-142); the Volume solver forms its contact volumes against static boxes only ([EXT A-15]): under it such
+   * pairs are left out and reported. */
   { int dropped = 0;
     for(int c=0;c<m.ncell;c++) for(int b=0;b<m.nmbox;b++){
       const int la = m.cell[c].link, lb = m.mbox[b].link;
@@ -199,15 +200,16 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
       const ContactInfoHost *ci = &w.cidef;
       const std::string &sa = link_stuff[la], &sb = link_stuff[lb];
       for(const auto &e : w.ci) if( (e.a==sa && e.b==sb) || (e.a==sb && e.b==sa) ){ ci = &e; break; }
-      if( ci->type != C_ELASTIC ){ dropped++; continue; }
+      if( ci->type != C_ELASTIC && w.solver == S_VOLUME ){ dropped++; continue; }
       if( m.npair >= MAX_PAIRS ){ err = "too many contact pairs (MAX_PAIRS)"; return false; }
       PairDev &p = m.pair[m.npair++];
       p.cell = c; p.box = -1; p.mbox = b; p.sofs = sofs; sofs += m.cell[c].nvert;
       p.type = ci->type; p.K = ci->K; p.L = ci->L; p.E = ci->E; p.V = ci->V; p.SF = ci->SF; p.KF = ci->KF;
-      m.has_elastic = 1; m.link[la].mcol = 1; m.link[lb].mcol = 1;
+      if( p.type == C_ELASTIC ) m.has_elastic = 1; else { m.has_rigid = 1; m.rigid_moving = 1; }
+      m.link[la].mcol = 1; m.link[lb].mcol = 1;
     }
-    if( dropped ) std::fprintf(stderr, "rokifd_b200: %d pair(s) of cells on two MOVING links have rigid contact info: not formed (moving-vs-moving "
-                                       "contact is built for elastic contact info only)\n", dropped);
+    if( dropped ) std::fprintf(stderr, "rokifd_b200: %d pair(s) of cells on two MOVING links have rigid contact info: not formed under the Volume "
+                                       "solver (its contact volumes are formed against static boxes)\n", dropped);
   }
   m.nslot = sofs;  /* flag positions: one word when everything fits 32 slots (position = slot), else whole words per pair */
   if( m.nslot <= 32 ){ for(int p=0;p<m.npair;p++) m.pair[p].fofs = m.pair[p].sofs; m.nfw = 1; }
@@ -224,7 +226,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   /* ---- rigid-contact tables: slot -> (pair, vertex), workspace layout per warp */
   m.rigid_mask = 0; int nrs = 0;
   if( m.has_rigid && m.solver != S_VOLUME && m.nslot > RIGID_MAX_SLOTS ){
-    err = "the rigid vertex solvers (MLCP, Vert) handle at most 32 contact slots per environment (cell vertices x static boxes)"; return false; }
+    err = "the rigid vertex solvers (MLCP, Vert) handle at most 32 contact slots per environment (cell vertices x boxes of static links and, for rigid contact info, of other moving links)"; return false; }
   for(int p=0;p<m.npair;p++) for(int k=0;k<m.cell[m.pair[p].cell].nvert;k++){
     const int sidx = m.pair[p].sofs + k;
     if( sidx < RIGID_MAX_SLOTS ){ m.slot_pair[sidx] = p; m.slot_vert[sidx] = k; }
@@ -246,6 +248,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
       for(int g=0;g<m.nrg;g++){ int r2 = m.rg_link[g]; while( m.link[r2].parent >= 0 ) r2 = m.link[r2].parent; if( r2 == root ) ok = false; }
       m.rg_link[m.nrg++] = l;
     }
+    if( m.rigid_moving ) ok = false;             /* a rigid pair of two moving links: the dense path (A couples them) */
     lk = ( ok && m.nrg > 0 ) ? m.rg_link[0] : -1;
     if( !ok ) m.nrg = 0;
     bool lpos = true;           /* the Vert path divides by the relaxation of every rigid pair */

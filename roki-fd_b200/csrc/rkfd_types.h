@@ -89,6 +89,7 @@ struct ModelDev {
   int nmbox;
   int need_world;      /* any collision cell: world frames must be propagated */
   int has_rigid, has_elastic;
+  int rigid_moving;    /* a rigid pair of two moving links exists: the dense rigid path (A couples the two links / chains) */
   int solver, pyramid, max_iter;
   int integrator;      /* 0 Runge-Kutta-Gill, 1 classical Runge-Kutta, 2 Euler, 3 Heun ([EXT] zODE2AssignRegular) */
   /* stage coefficients of the integrator times dt, folded on the host (constant-bank operands in the kernel) */

@@ -212,7 +212,9 @@ def test_ztk_shape_sugar_and_automatic_mass_properties():
     convex hull for the prism, closed forms for the primitives)."""
     from scipy.spatial import ConvexHull
     fd = capi.RkFD()
-    assert fd.chain_reg_file(os.path.join(GOLD, "sugar.ztk")) is not None
+    cell = fd.chain_reg_file(os.path.join(GOLD, "sugar.ztk"))
+    assert cell is not None
+    capi.lib().rkCDPairChainUnreg(None, cell.chain_handle)      # as the reference's example programs do: the self pairs of the chain (rigid by default) are not wanted here
     m = _flattened(fd)
     fd.destroy()
     verts = np.array([m["vert[%d]" % i] for i in range(int(m["dims"][6]))])

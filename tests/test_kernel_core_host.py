@@ -560,19 +560,28 @@ MM_CI = [ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0, SF=0.5, KF=
          ch.ContactInfo("body", "body", "elastic", E=2000.0, V=20.0, SF=0.5, KF=0.3)]
 
 
-def mm_world(kind):
-    if kind == "box_stack":          # example/chain/boxdrop_test.c: boxes landing on each other (self pairs unregistered)
-        return ch.World(chains=[mm_box("a"), mm_box("b"), mm_box("c"), ch.floor_soft()], contact_info=MM_CI)
+# the same bodies with RIGID contact info between them (what the reference's default contact info gives arm_box_test.c and
+# boxdrop_test.c): the pair couples two chains in A (rkfd_vert.c:125-185, rkfd_mlcp.c:76-142)
+MM_CI_RIGID = [ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0, SF=0.5, KF=0.3),
+               ch.ContactInfo("body", "body", "rigid", K=1000.0, L=0.01, SF=0.5, KF=0.3)]
+
+
+def mm_world(kind, solver="Vert"):
+    rigid = kind.endswith("_rigid")
+    ci = MM_CI_RIGID if rigid else MM_CI
+    if kind.startswith("box_stack"):          # example/chain/boxdrop_test.c: boxes landing on each other (self pairs unregistered)
+        nb = 2 if rigid else 3                # rigid: 2 boxes (3 x 8 x 2 + 16 = 32 slots is the limit of the vertex solvers)
+        return ch.World(chains=[mm_box(n) for n in "abc"[:nb]] + [ch.floor_soft()], contact_info=ci, solver=solver)
     arm = ch.arm_2dof()              # example/chain/arm_box_test.c: the arm pushes a free box lying on the floor
     arm.links[2].boxes = [((0.2, 0.0, 0.0), 0.3, 0.1, 0.1)]
-    return ch.World(chains=[arm, mm_box("box"), ch.floor_soft()], contact_info=MM_CI)
+    return ch.World(chains=[arm, mm_box("box"), ch.floor_soft()], contact_info=ci, solver=solver)
 
 
 def mm_states(kind, w, B, seed=0):
     rng = np.random.default_rng(seed)
     q = np.zeros((B, w.nq)); qd = np.zeros((B, w.nq)); u = np.zeros((B, w.nl))
-    if kind == "box_stack":
-        for k in range(3):
+    if kind.startswith("box_stack"):
+        for k in range(w.nq // 6):
             o = 6 * k
             q[:, o:o + 2] = rng.uniform(-0.02, 0.02, (B, 2)); q[:, o + 2] = 0.05 + 0.105 * k + rng.uniform(0.0, 0.01, B)
             q[:, o + 3:o + 6] = rng.uniform(-0.1, 0.1, (B, 3)); qd[:, o:o + 6] = rng.uniform(-0.2, 0.2, (B, 6))
@@ -588,6 +597,31 @@ def mm_states(kind, w, B, seed=0):
         q[:, 5:8] = rng.uniform(-0.2, 0.2, (B, 3))
         u[:, 1:3] = rng.uniform(-6, 6, (B, 2))
     return q, qd, u
+
+
+@pytest.mark.parametrize("kind,solver", [("box_stack_rigid", "MLCP"), ("box_stack_rigid", "Vert"), ("arm_pushes_box_rigid", "MLCP"), ("arm_pushes_box_rigid", "Vert")])
+def test_rigid_moving_vs_moving_contact_matches_oracle(oracle, kind, solver):
+    """Rigid contact info between two MOVING links: relative acceleration / velocity of the two links at the contact, probes with
+    the opposite unit force on the partner, A coupling the two chains, opposite wrenches."""
+    w = mm_world(kind, solver)
+    B = 8
+    q, qd, u = mm_states(kind, w, B, seed=3)
+    hs = HostSim(w, B); hs.set_state(q, qd, u); hs.eval(ref=True)
+    assert hs.nslot == w.nslot == oracle.OracleWorld(w).nslot
+    nstat = sum(v.shape[0] for l in w.flat_links() for v in l.cells()) * len(w.boxes)
+    seen = 0
+    ow = oracle.OracleWorld(w)
+    for n in (40, 80, 160):
+        hs2 = HostSim(w, B); hs2.set_state(q, qd, u); hs2.eval(ref=True); hs2.step(n)
+        hq, hqd, hqdd = hs2.get_state(); a, t, r, f = hs2.get_contact()
+        o = ow.batch_run_state(q, qd, u, nsteps=n)
+        ok = np.isfinite(o[0]).all(1)
+        err = np.abs(hq - o[0]).max(1) / np.maximum(np.abs(o[0]).max(1), 1e-12)
+        assert (err[ok] < 1e-7).mean() >= 0.75, (n, err)          # a mode flip at a zTOL-sized margin may split a trajectory
+        good = ok & (err < 1e-7)
+        assert (a[good] == o[3][good]).all()
+        seen += o[3][:, nstat:].sum()
+    assert seen > 0            # the rigid moving-vs-moving slots saw contact
 
 
 @pytest.mark.parametrize("kind", ["box_stack", "arm_pushes_box"])

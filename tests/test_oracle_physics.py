@@ -554,3 +554,38 @@ def test_moving_vs_moving_contact_conserves_momentum_and_stacks(oracle):
     qq, vv, _ = e.get_state()
     assert np.abs(vv).max() < 1e-6
     assert abs((0.05 - qq[2]) - 2 * m * g / (4 * 1000.0)) < 1e-6 and abs((0.09 - (qq[8] - qq[2])) - m * g / (4 * 2000.0)) < 1e-6
+
+
+@pytest.mark.parametrize("solver", ["MLCP", "Vert"])
+def test_rigid_moving_vs_moving_contact_conserves_momentum(oracle, solver):
+    """Oracle pin of RIGID contact between two moving links (rkfd_vert.c:125-185, rkfd_mlcp.c:76-142: A couples the two chains,
+    the test force acts on one link and its opposite on the other): two free boxes colliding in free fall change their total
+    linear momentum by gravity only, and they do not pass through each other; under the Vert solver a small box rests ON a larger
+    one (rigid: no penetration between them) which sinks 2 m g / (4 E) into the soft floor."""
+    def mbox(name, side=0.1):
+        return ch.ChainModel(name, [ch.Link(name="b", jtype="float", mass=0.5, stuff="body", inertia=np.eye(3) * 8.33e-4,
+                                            boxes=[((0.0, 0.0, 0.0), side, side, side)])])
+    ci = [ch.ContactInfo("body", "body", "rigid", K=1000.0, L=0.01, SF=0.5, KF=0.3), ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0, SF=0.5, KF=0.3)]
+    w = ch.World(chains=[mbox("a"), mbox("b")], contact_info=ci, solver=solver)
+    e = oracle.OracleWorld(w).env()
+    q = np.zeros(12); q[0:3] = [-0.08, 0.01, 1.0]; q[6:9] = [0.08, -0.02, 1.03]; q[3:6] = [0.1, 0.2, 0.3]; q[9:12] = [-0.2, 0.1, 0.0]
+    qd = np.zeros(12); qd[0] = 1.0; qd[6] = -1.5; qd[4] = 2.0; qd[11] = -1.0
+    e.set_state(q, qd); e.update_init()
+    m, g = 0.5, 9.80665
+    P0 = m * (qd[0:3] + qd[6:9]); touched = 0
+    for _ in range(300):
+        e.update(); touched += int(e.get_contact()[0].sum() > 0)
+    qq, vv, _ = e.get_state()
+    assert touched > 3
+    assert np.allclose(m * (vv[0:3] + vv[6:9]) - P0, [0, 0, -2 * m * g * 0.3], atol=1e-9)
+    assert vv[0] < 0.0 or vv[6] > vv[0] - 1e-9          # they bounced / stuck: box a no longer moves into box b
+    if solver == "Vert":
+        w = ch.World(chains=[mbox("lower"), mbox("upper", 0.08), ch.floor_soft()], contact_info=ci, solver=solver)
+        e = oracle.OracleWorld(w).env()
+        q = np.zeros(12); q[2] = 0.05; q[8] = 0.14
+        e.set_state(q, np.zeros(12)); e.update_init()
+        for _ in range(3000):
+            e.update()
+        qq, vv, _ = e.get_state()
+        assert np.abs(vv).max() < 1e-9
+        assert abs((0.05 - qq[2]) - 2 * m * g / (4 * 1000.0)) < 1e-7 and abs(0.09 - (qq[8] - qq[2])) < 1e-7

@@ -47,9 +47,9 @@ def _flat(name, soft, solver=None):
     return (w,) + tuple(flat_states(name, w, q0, B, seed=20260418))
 
 
-def _mm(kind):
+def _mm(kind, solver="Vert"):
     from test_kernel_core_host import mm_world, mm_states
-    w = mm_world(kind)
+    w = mm_world(kind, solver)
     return (w,) + tuple(mm_states(kind, w, B, seed=20260418))
 
 
@@ -66,6 +66,7 @@ WORLDS = {
     "arm7 + rigid floor, Vert QP (solver default contact info)": (lambda: _std(ch.World(chains=[ch.arm7(base_z=0.3, contact_cube=True), ch.floor()], solver="Vert")), 1e-9, 1e-6, 1.0),
     "three boxes landing on each other (moving-vs-moving, penalty)": (lambda: _mm("box_stack"), 1e-9, 1e-6, 1.0),
     "arm pushes a free box (moving-vs-moving, penalty)": (lambda: _mm("arm_pushes_box"), 1e-9, 1e-6, 1.0),
+    "arm pushes a free box (moving-vs-moving, RIGID pair, MLCP)": (lambda: _mm("arm_pushes_box_rigid", "MLCP"), 1e-9, 1e-6, 0.9),
 }
 
 
