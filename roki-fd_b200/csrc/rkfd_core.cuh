@@ -406,7 +406,7 @@ struct Core {
   RKFD_HD XF joint_xform(const ModelDev &m, const LinkDev &L, int i, V3 &vJ, V3 &wJ){
     const int sl = Spec::slot(i,L), qs = rk0 + Spec::qofs(i,L), qds = rk0 + Spec::nq(m) + Spec::qofs(i,L);
     XF x; x.fast = 0; x.cls = CLS<Kt>(i,L); x.sg = ro_sign(x.cls, L.rsg); x.c = 1.0; x.s = 0.0;
-    x.pz = ( JT<Kt>(i,L) == J_REVOL || JT<Kt>(i,L) == J_FIXED ) && L.po[0] == 0.0 && L.po[1] == 0.0;
+    x.pz = L.pz;      /* revolute / fixed joint with org position (0, 0, z): decided once on the host (rkfd_model.cpp) */
     vJ = v3(0,0,0); wJ = v3(0,0,0);
     switch(JT<Kt>(i,L)){
     case J_REVOL: {
@@ -682,7 +682,7 @@ struct Core {
         }
       }
       XF x; x.fast = 0; x.cls = CLS<Kt>(i,L); x.sg = ro_sign(x.cls, L.rsg); x.c = 1.0; x.s = 0.0;
-      x.pz = ( JT<Kt>(i,L) == J_REVOL || JT<Kt>(i,L) == J_FIXED ) && L.po[0] == 0.0 && L.po[1] == 0.0;
+      x.pz = L.pz;      /* revolute / fixed joint with org position (0, 0, z): decided once on the host (rkfd_model.cpp) */
       V3 vJ = v3(0,0,0), wJ = v3(0,0,0);
       switch(JT<Kt>(i,L)){
       case J_REVOL: {
@@ -766,15 +766,15 @@ struct Core {
         const double tin = L.m_tin*e, treg = L.m_reg*v;
         jm = L.m_jm; tdrive = tin - treg;
         tf = jm; tf *= -v * m.inv_dt; tf -= tin; tf += treg; tf += prev_in;
-        double fmax;
-        if( !(piv & (1u<<j)) ) fmax = L.sfriction;
-        else {
-          const double sg = v > 0 ? 1.0 : ( v < 0 ? -1.0 : 0.0 );
-          fmax = -L.stiffness*qj - L.viscosity*v - L.coulomb*sg;
-        }
-        fmax = fabs(fmax);
-        if( fabs(tf) > fmax ){ tf = tf > 0 ? fmax : -fmax; if( ref ) piv |= (1u<<j); }
-        else if( ref ) piv &= ~(1u<<j);
+        /* static / kinetic bound and the clamp as selects: the lanes of a warp differ in both, and the branches cost more than
+         * the three multiply-adds of the kinetic bound (same values as the branching form, bit for bit) */
+        const bool kin = (piv >> j) & 1u;
+        const double sg = v > 0 ? 1.0 : ( v < 0 ? -1.0 : 0.0 );
+        const double fk = fabs(-L.stiffness*qj - L.viscosity*v - L.coulomb*sg);
+        const double fmax = kin ? fk : fabs(L.sfriction);
+        const bool over = fabs(tf) > fmax;
+        tf = over ? ( tf > 0 ? fmax : -fmax ) : tf;
+        if( ref ) piv = over ? ( piv | (1u<<j) ) : ( piv & ~(1u<<j) );
       } else tdrive = e;
     }
     if( ref ) c.gst(c.st.piv_prev, j, tdrive + tf);     /* rkFDUpdateJointPrevDrivingTrq (rkfd_util.c:289-311) */

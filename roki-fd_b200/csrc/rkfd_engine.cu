@@ -285,6 +285,9 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     st.ws = ( model.ws_doubles > 0 && model.rigid_link < 0 ) ? dalloc<double>(*s, (size_t)(s->ld/32)*model.ws_doubles) : nullptr;
     st.ws1 = model.ws1_doubles > 0 ? dalloc<double>(*s, (size_t)model.ws1_doubles*s->ld) : nullptr;
     int nmax = nq; if( nl > nmax ) nmax = nl; if( 3*ns > nmax ) nmax = 3*ns;
+    /* the kernels index the per-environment arrays with 32-bit element offsets (row * ld + e) */
+    if( (unsigned long long)nmax*(unsigned long long)s->ld >= (1ull << 32) )
+      throw std::runtime_error("rokifd_b200: rows x environments per device exceed 2^32 elements - spread the batch over more devices (rkFDBatchSetDevices)");
     s->nstage = (size_t)nmax*s->B; if( s->nstage < 256 ) s->nstage = 256; s->dstage = dalloc<double>(*s, s->nstage);
     /* launch configuration: the block size that keeps most environments resident per SM; scratch in HBM
      * (gscr) only when no shared-memory variant fits */

@@ -79,8 +79,11 @@ struct DevCtx {
   __device__ __forceinline__ double &W(int i){ return st.ws[(size_t)(e0 >> 5)*wsd + i]; }
   __device__ __forceinline__ double &W1(int i){ return st.ws1[(size_t)i*st.ld + e]; }     /* element i of the selected environment */
   /* per-env state in HBM: element k of the selected environment (global address space asserted: LDG/STG, not generic) */
-  __device__ __forceinline__ double gld(const double *p, int k) const { const double *a = p + ((size_t)k*st.ld + e); __builtin_assume(__isGlobal(a)); return *a; }
-  __device__ __forceinline__ void gst(double *p, int k, double v){ double *a = p + ((size_t)k*st.ld + e); __builtin_assume(__isGlobal(a)); *a = v; }
+  /* the element index k*ld + e in 32 bits (one IMAD + one IMAD.WIDE per access instead of a 64-bit multiply-add chain: the
+   * address arithmetic of these accesses was 5 % of the executed instructions of the C3 step); the engine refuses batches whose
+   * largest row index times ld does not fit (Engine::Engine) */
+  __device__ __forceinline__ double gld(const double *p, int k) const { const double *a = p + ((unsigned)k*(unsigned)st.ld + (unsigned)e); __builtin_assume(__isGlobal(a)); return *a; }
+  __device__ __forceinline__ void gst(double *p, int k, double v){ double *a = p + ((unsigned)k*(unsigned)st.ld + (unsigned)e); __builtin_assume(__isGlobal(a)); *a = v; }
 };
 
 /* mode 0: nsteps x rkFDUpdate; 1: one non-committing evaluation; 2: one committing evaluation */
@@ -92,7 +95,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) rkfd_step_kernel(StateDev st, int
 {
   using Spec = typename SpecOf<SPEC>::type;
   constexpr bool TM = Spec::TM != 0;
-  const int e = blockIdx.x*BLOCK + threadIdx.x;
+  int e_ = blockIdx.x*BLOCK + threadIdx.x;
+  asm volatile("" : "+r"(e_));        /* opaque: kept in a register instead of being recomputed from the special registers at every use */
+  const int e = e_;
   /* the engine pads the environment count to whole blocks (ld): no thread exits early, which the block barriers
    * and the tensor-memory allocation below rely on; the padding environments hold a valid zero state */
   DevCtx<BLOCK,GSCR,RIGID,TM> ctx; ctx.st = st; ctx.e = ctx.e0 = e; ctx.cur = cur; ctx.tid = ctx.tid0 = threadIdx.x; ctx.wsd = c_model.ws_doubles;

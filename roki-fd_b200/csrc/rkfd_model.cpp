@@ -144,6 +144,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
       if( d.mtype == M_TRQ ){ d.m_jm = 0; }
       d.parent = l.parent >= 0 ? l.parent + base : -1;
       d.jtype = l.jtype; d.ndof = jtype_ndof(l.jtype); d.qofs = nq; nq += d.ndof;
+      d.pz = ( ( d.jtype == J_REVOL || d.jtype == J_FIXED ) && d.po[0] == 0.0 && d.po[1] == 0.0 ) ? 1 : 0;
       if( d.ndof != 1 ) d.mtype = M_NONE;
       d.cell_begin = m.ncell;
       for(const auto &sh : l.shapes){

@@ -72,7 +72,8 @@ struct LinkDev {
   int frame_slot;      /* >=0 (worlds with rigid pairs, links with cells): Rw(9) pw(3) vl(3) w(3) a(6) = 24 slots */
   int cell_begin, cell_end;
   double brk_f, brk_t; /* breakable float: force / torque thresholds */
-  int mcol, pad_;      /* 1: a cell or a box of this link takes part in a moving-vs-moving pair (frame + wrench slots) */
+  int mcol;            /* 1: a cell or a box of this link takes part in a moving-vs-moving pair (frame + wrench slots) */
+  int pz;              /* 1: revolute / fixed joint whose org position is (0, 0, z): the structured shifts of rkfd_math.cuh apply */
 };
 
 struct CellDev { int link, vofs, nvert, pair_begin, pair_end; };
