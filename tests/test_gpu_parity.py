@@ -103,7 +103,7 @@ def test_teacher_forced_steps_match_oracle(capi, oracle, name):
             opt[b], opp[b] = e.get_pivot()
         assert relerr(gq, oq) < 1e-9 and relerr(gqd, oqd) < 1e-9, (name, s)
         for b in range(B):
-            assert relerr(gqdd[b], oqdd[b]) < 1e-7, (name, s, b, relerr(gqdd[b], oqdd[b]))
+            assert relerr(gqdd[b], oqdd[b]) < 1e-9, (name, s, b, relerr(gqdd[b], oqdd[b]))      # north_star's 1e-9 (measured: 1e-13-class)
         # teacher forcing: put the oracle's full state on the device
         fd.batch_set_state(oq, oqd)
         fd.batch_set_pivot(opt, opp)
@@ -299,8 +299,8 @@ def test_vert_qp_relaxation_1e_4(capi, oracle, name):
 def test_rigid_evaluation_matches_oracle(capi, oracle, name):
     """Rigid contact (A,b by cached-ABA probes + solver) in one committing evaluation.  The Delassus matrix of
     N>DoF/3 contacts is rank deficient up to the 1e-4 relaxation, so rounding differences are amplified by
-    cond(A) ~ 1e4..1e6: q'' and contact forces are required within 1e-7 relative (1e-9 x that amplification
-    is the expectation; the measured maximum is printed)."""
+    cond(A) ~ 1e4..1e6; q'' and contact forces are nevertheless required within north_star's 1e-9 relative (measured
+    on the B200 in round 2: at most 6.4e-13 over the eight worlds; the measured maximum is printed)."""
     w = RIGID_WORLDS[name]()
     B = 256
     q, qd, u = ch.sample_state(w, B, seed=5)
@@ -322,9 +322,9 @@ def test_rigid_evaluation_matches_oracle(capi, oracle, name):
         nc += oa.sum()
         assert (a[b] == oa).all() and (t[b][oa == 1] == ot[oa == 1]).all(), (name, b)
         worst = max(worst, relerr(gqdd[b], ref))
-        assert np.allclose(f[b][oa == 1], of[oa == 1], rtol=1e-7, atol=1e-7 * max(1.0, np.abs(of).max()))
+        assert np.allclose(f[b][oa == 1], of[oa == 1], rtol=1e-9, atol=1e-9 * max(1.0, np.abs(of).max()))
     print("rigid %s: %d contacts, max rel err of q'' %.2e" % (name, nc, worst))
-    assert nc > 0 and worst < 1e-7
+    assert nc > 0 and worst < 1e-9
     fd.destroy()
 
 
@@ -623,8 +623,9 @@ def test_ragged_env_counts(capi, oracle, name, B):
     gq, gqd, gqdd = fd.batch_get_state()
     assert gq.shape == (B, w.nq) and (fd.batch_get_status() == 0).all()
     oq, oqd, oqdd, _ = oracle.OracleWorld(w).batch_run(q, qd, u, nsteps=5)
+    tq, tv = (1e-8, 1e-6) if name == "c4_volume" else (1e-9, 1e-8)      # Volume: the QP amplifies rounding (measured 1e-11-class per evaluation)
     for b in range(B):
-        assert relerr(gq[b], oq[b]) < 1e-8 and relerr(gqd[b], oqd[b]) < 1e-6, (name, B, b)
+        assert relerr(gq[b], oq[b]) < tq and relerr(gqd[b], oqd[b]) < tv, (name, B, b)
     fd.destroy()
 
 
