@@ -107,6 +107,13 @@ __ROKI_FD_EXPORT void rkJointGetVel(rkJoint *joint, double *val);
 __ROKI_FD_EXPORT void rkJointGetAcc(rkJoint *joint, double *val);
 __ROKI_FD_EXPORT void rkJointMotorSetInput(rkJoint *joint, double *val);
 __ROKI_FD_EXPORT void rkCDPairChainUnreg(rkCD *cd, rkChain *chain);
+/* collision shapes of a link ([EXT] Zeo zShape3D / RoKi rkCDCell: opaque here).  rkLinkShapeNum / rkLinkShape stand in for RoKi's
+ * shape list of a link: shape k of link `link` in the order of the model file (moving links: vertex clouds and box primitives
+ * in their file order; static links: their box primitives).  Handles stay valid as long as the chain lives. */
+typedef struct _zShape3D zShape3D;
+typedef struct _zShape3D rkCDCell;        /* one registered shape = one collision cell */
+__ROKI_FD_EXPORT int rkLinkShapeNum(rkChain *chain, int link);
+__ROKI_FD_EXPORT zShape3D *rkLinkShape(rkChain *chain, int link, int k);
 
 /* programmatic chain construction (what rkChainReadZTK does from a file) */
 enum { RK_B200_JOINT_FIXED = 0, RK_B200_JOINT_REVOL = 1, RK_B200_JOINT_PRISM = 2,
@@ -262,6 +269,17 @@ __ROKI_FD_EXPORT bool rkFDChainUnreg(rkFD *fd, rkFDCell *cell);
 __ROKI_FD_EXPORT void rkFDChainSetDis(rkFDCell *lc, zVec dis);
 __ROKI_FD_EXPORT void rkFDChainSetVel(rkFDCell *lc, zVec vel);
 __ROKI_FD_EXPORT bool rkFDContactInfoScanFile(rkFD *fd, char filename[]);
+/* for a fake-crawler (reference rkfd_sim.h:73-80, rkfd_sim.c:386-440): a cell in slide mode behaves like a belt running with
+ * `vel` about `axis` (frame of the cell's link): its surface velocity enters the relative contact velocity
+ * (rkFDLinkAddSlideVel, rkfd_util.c:26-40) and the anchors of sticking contacts ride on it (rkFDUpdateRefSlide, :218-237).
+ * The shape must belong to the chain of a registered cell (rkFDCellChain), and the calls must precede rkFDUpdateInit. */
+__ROKI_FD_EXPORT void rkFDCDCellSetSlideMode(rkCDCell *cell, bool mode);
+__ROKI_FD_EXPORT void rkFDCDCellSetSlideVel(rkCDCell *cell, double vel);
+__ROKI_FD_EXPORT void rkFDCDCellSetSlideAxis(rkCDCell *cell, zVec3D *axis);
+__ROKI_FD_EXPORT rkCDCell *rkFDShape3DGetCDCell(rkFD *fd, zShape3D *shape);
+__ROKI_FD_EXPORT rkCDCell *rkFDShape3DSetSlideMode(rkFD *fd, zShape3D *shape, bool mode);
+__ROKI_FD_EXPORT rkCDCell *rkFDShape3DSetSlideVel(rkFD *fd, zShape3D *shape, double vel);
+__ROKI_FD_EXPORT rkCDCell *rkFDShape3DSetSlideAxis(rkFD *fd, zShape3D *shape, zVec3D *axis);
 __ROKI_FD_EXPORT zVec rkFDODECatDefault(zVec x, double k, zVec v, zVec xnew, void *util);
 __ROKI_FD_EXPORT zVec rkFDODESubDefault(zVec x1, zVec x2, zVec dx, void *util);
 #define rkFDODE2Assign(f,t)        ( (f)->ode.form = RKFD_ODE2_##t )

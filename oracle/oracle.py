@@ -129,13 +129,24 @@ class OracleWorld:
                 L.ork_world_set_break(self.h, k, l.break_force, l.break_torque)
         L.ork_world_add_link_box.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
         L.ork_world_unreg_self_collision.argtypes = [C.c_void_p, C.c_int]
+        L.ork_world_set_slide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, _dp, C.c_int, _dp, _dp]
+        order = world.shape_order()
+        mlinks = [(chn, l) for chn in world.moving_chains() for l in chn.links]      # the originals of `links`, same order
+
+        def set_slide(is_box, idx, sl, ordv, lR=None, lp=None):
+            _, pa = _d(np.asarray(sl[1], float) if sl else np.zeros(3))
+            L.ork_world_set_slide(self.h, is_box, idx, 1 if sl else 0, float(sl[0]) if sl else 0.0, pa, ordv,
+                                  _d(np.asarray(lR, float).reshape(9))[1] if lR is not None else None, _d(np.asarray(lp, float))[1] if lp is not None else None)
         for k, l in enumerate(links):
-            for verts in l.cells():
+            chn, lo = mlinks[k]
+            for ci, verts in enumerate(l.cells()):
                 v, pv = _d(verts)
-                L.ork_world_add_cell(self.h, k, v.shape[0], pv)
-            for (ctr, d, w_, h_) in l.boxes:       # box primitives of a moving link: targets for other links' vertices
+                c_idx = L.ork_world_add_cell(self.h, k, v.shape[0], pv)
+                set_slide(0, c_idx, l.slides.get(ci), order[(id(chn), id(lo), ci)])
+            for bi, (ctr, d, w_, h_) in enumerate(l.boxes):       # box primitives of a moving link: targets for other links' vertices
                 _, pR = _d(np.eye(3).reshape(9)); _, pp = _d(np.asarray(ctr, float)); _, ph = _d(np.array([d / 2, w_ / 2, h_ / 2]))
-                L.ork_world_add_link_box(self.h, k, pR, pp, ph)
+                b_idx = L.ork_world_add_link_box(self.h, k, pR, pp, ph)
+                set_slide(1, b_idx, l.slides.get(len(l.shapes) + bi), order[(id(chn), id(lo), len(l.shapes) + bi)])
         base = 0
         for chn in world.moving_chains():
             if not chn.self_collide:
@@ -145,7 +156,8 @@ class OracleWorld:
             _, pR = _d(np.asarray(b.R, float).reshape(9))
             _, pp = _d(b.p)
             _, ph = _d(b.half)
-            L.ork_world_add_box(self.h, pR, pp, ph, world.stuff_id(b.stuff))
+            b_idx = L.ork_world_add_box(self.h, pR, pp, ph, world.stuff_id(b.stuff))
+            set_slide(1, b_idx, b.slide, b.order, b.link_R, b.link_p)
         L.ork_world_set_prp(self.h, world.dt, world.pyramid, world.friction_weight, world.max_iter)
         L.ork_world_set_integrator.argtypes = [C.c_void_p, C.c_int]
         L.ork_world_set_integrator(self.h, {"RKG": 0, "RK4": 1, "Euler": 2, "Heun": 3}[getattr(world, "integrator", "RKG")])

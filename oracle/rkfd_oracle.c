@@ -104,9 +104,12 @@ typedef struct {
   double M[36];   /* rigid-body 6x6 inertia at the link origin (A-4) */
 } ork_link;
 
-typedef struct { int link, nvert, vofs, volbox; } ork_cell;   /* volbox: the 8 corners of a parallelepiped in sign-bit order (Volume solver, A-15) */
+/* slide mode of a collision cell ("fake crawler", rkfd_sim.c:386-440): mode, belt speed, axis in the frame of the cell's link;
+ * ord = registration order of the shape in rkCD (decides which cell of a pair is pd->cell[0]) */
+typedef struct { int mode, ord; double vel, axis[3]; } ork_slide;
+typedef struct { int link, nvert, vofs, volbox; ork_slide sl; } ork_cell;   /* volbox: the 8 corners of a parallelepiped in sign-bit order (Volume solver, A-15) */
 /* link < 0: a static box, (R, p) its world frame; link >= 0: a box carried by that moving link, (R, p) its frame in the link */
-typedef struct { double R[9], p[3], half[3]; int stuff, link; } ork_box;
+typedef struct { double R[9], p[3], half[3]; int stuff, link; ork_slide sl; double lR[9], lp[3]; /* static box: world frame of its link */ } ork_box;
 typedef struct { int type; double K, L, E, V, SF, KF; } ork_cinfo;
 typedef struct { int sa, sb; ork_cinfo ci; } ork_cinfo_ent;
 typedef struct { int cell, box, sofs; ork_cinfo ci; } ork_pair;    /* vertices of `cell` against `box` (static, or on another moving link) */
@@ -217,6 +220,7 @@ int ork_world_add_cell(ork_world *w, int link, int nvert, const double *verts)
   w->cell = (ork_cell*)realloc(w->cell,(w->ncell+1)*sizeof(ork_cell));
   w->vert = (double*)realloc(w->vert,3*(w->nvert+nvert)*sizeof(double));
   w->cell[w->ncell].link = link; w->cell[w->ncell].nvert = nvert; w->cell[w->ncell].vofs = w->nvert; w->cell[w->ncell].volbox = 0;
+  memset(&w->cell[w->ncell].sl,0,sizeof(ork_slide)); w->cell[w->ncell].sl.ord = w->ncell;
   memcpy(w->vert+3*w->nvert, verts, 3*nvert*sizeof(double));
   w->nvert += nvert;
   return w->ncell++;
@@ -228,6 +232,8 @@ int ork_world_add_box(ork_world *w, const double *R, const double *p, const doub
   b = &w->box[w->nbox];
   memcpy(b->R,R,9*sizeof(double)); memcpy(b->p,p,3*sizeof(double)); memcpy(b->half,half,3*sizeof(double));
   b->stuff = stuff; b->link = -1;
+  memset(&b->sl,0,sizeof(ork_slide)); b->sl.ord = 1000000 + w->nbox;      /* default: static shapes registered after the moving ones */
+  m3_ident(b->lR); b->lp[0]=b->lp[1]=b->lp[2]=0.0;
   return w->nbox++;
 }
 /* a box primitive on a moving link (frame in the link): a collision TARGET for the vertices of cells on other links; its own
@@ -238,6 +244,14 @@ int ork_world_add_link_box(ork_world *w, int link, const double *R, const double
   int b = ork_world_add_box(w,R,p,half,w->link[link].stuff);
   w->box[b].link = link;
   return b;
+}
+/* slide mode (rkFDCDCellSetSlideMode/-Vel/-Axis, rkfd_sim.c:386-400) of a cell (is_box = 0) or of a box target (is_box = 1);
+ * ord: registration order of the shape; lR/lp: world frame of the link of a STATIC box (NULL: identity) */
+void ork_world_set_slide(ork_world *w, int is_box, int idx, int mode, double vel, const double *axis, int ord, const double *lR, const double *lp)
+{
+  ork_slide *sl = is_box ? &w->box[idx].sl : &w->cell[idx].sl;
+  sl->mode = mode; sl->vel = vel; memcpy(sl->axis,axis,3*sizeof(double)); sl->ord = ord;
+  if( is_box && lR ){ memcpy(w->box[idx].lR,lR,9*sizeof(double)); memcpy(w->box[idx].lp,lp,3*sizeof(double)); }
 }
 /* [EXT] rkCDPairChainUnreg: drops the pairs between cells of the chain that `link` belongs to (registered by default) */
 void ork_world_unreg_self_collision(ork_world *w, int link)
@@ -546,8 +560,56 @@ static void push_wrench(ork_env *e, int link, const double *vert, const double *
   v3_add(x->wext,fl,x->wext); v3_add(x->wext+3,n,x->wext+3);
 }
 
+/* frame (R, p) of the link that carries a cell / a box in this evaluation (static box: the fixed frame of its link) */
+static void slide_frame(const ork_env *e, int is_box, int idx, const double **R, const double **pw)
+{
+  const ork_world *w = e->w; int link = is_box ? w->box[idx].link : w->cell[idx].link;
+  if( link >= 0 ){ *R = e->lw[link].Rw; *pw = e->lw[link].pw; } else { *R = w->box[idx].lR; *pw = w->box[idx].lp; }
+}
+/* belt direction at world point p: (R axis) x (p - p_link) without its normal component; 0 when it vanishes.  Returns its norm */
+static double slide_dir(const ork_env *e, int is_box, int idx, const double *p, const double *n, double *sv)
+{
+  const ork_world *w = e->w; const ork_slide *sl = is_box ? &w->box[idx].sl : &w->cell[idx].sl;
+  const double *R, *pw; double r[3], ax[3];
+  slide_frame(e,is_box,idx,&R,&pw);
+  v3_sub(p,pw,r); m3_mulv(R,sl->axis,ax); v3_cross(ax,r,sv); v3_cat(sv,-v3_dot(sv,n),n);
+  return v3_norm(sv);
+}
+/* rkFDLinkAddSlideVel (rkfd_util.c:26-40) for the two cells of pair pi; v = relative velocity of the vertex's cell (in: without slide) */
+static void add_slide_vel(const ork_env *e, int pi, const double *p, const double *n, double *v)
+{
+  const ork_world *w = e->w; const ork_pair *pr = &w->pair[pi]; double sv[3], nv;
+  if( w->cell[pr->cell].sl.mode ){ nv = slide_dir(e,0,pr->cell,p,n,sv); if( !(fabs(nv) < ORK_TOL) ) v3_cat(v, w->cell[pr->cell].sl.vel/nv, sv); }
+  if( w->box[pr->box].sl.mode ){ nv = slide_dir(e,1,pr->box,p,n,sv); if( !(fabs(nv) < ORK_TOL) ) v3_cat(v, -w->box[pr->box].sl.vel/nv, sv); }
+}
+/* rkFDUpdateRefSlide (rkfd_util.c:218-237): the anchor of a sticking contact rides on the belt.  The reference adds
+ * R_k^T sv to _ref with k = pd->cell[1]'s link when the sliding cell is the vertex's cell, else pd->cell[0]'s link; _ref lives in
+ * the partner's frame, so the world shift is R_partner R_k^T sv (= sv whenever the sliding cell is pd->cell[0]) - mirrored.
+ * Our anchor is kept in the box frame (A-10): c_ref += Rbox_world^T (world shift). */
+static void update_ref_slide(ork_env *e, int pi, int s)
+{
+  const ork_world *w = e->w; const ork_pair *pr = &w->pair[pi]; int i;
+  const int vfirst = w->cell[pr->cell].sl.ord < w->box[pr->box].sl.ord;     /* the vertex's cell is pd->cell[0] */
+  const double *Rv, *pv, *Rp, *pp; double Rbw[9];
+  slide_frame(e,0,pr->cell,&Rv,&pv); slide_frame(e,1,pr->box,&Rp,&pp);
+  if( w->box[pr->box].link >= 0 ) m3_mul(Rp,w->box[pr->box].R,Rbw); else memcpy(Rbw,w->box[pr->box].R,sizeof Rbw);
+  for(i=0;i<2;i++){
+    const int is_vcell = vfirst ? i == 0 : i == 1;         /* pd->cell[i] is the vertex's cell */
+    const ork_slide *sl = is_vcell ? &w->cell[pr->cell].sl : &w->box[pr->box].sl;
+    double sv[3], nv, t[3], dw[3], db[3]; const double *Rk;
+    if( !sl->mode ) continue;
+    nv = slide_dir(e, is_vcell ? 0 : 1, is_vcell ? pr->cell : pr->box, e->c_vert+3*s, e->c_norm+3*s, sv);
+    if( fabs(nv) < ORK_TOL ) continue;
+    { double k = ( is_vcell ? -1.0 : 1.0 ) * w->dt * sl->vel / nv; sv[0]*=k; sv[1]*=k; sv[2]*=k; }
+    /* k-link: pd->cell[ is_vcell ? 1 : 0 ] */
+    { const int kcell_is_v = is_vcell ? !vfirst : vfirst; Rk = kcell_is_v ? Rv : Rp; }
+    m3_tmulv(Rk,sv,t); m3_mulv(Rp,t,dw);
+    m3_tmulv(Rbw,dw,db); v3_add(e->c_ref+3*s,db,e->c_ref+3*s);
+  }
+}
+
 /* rkFDContactForceModifyFriction (rkfd_util.c:239-266); v passed by value */
-static void modify_friction(ork_env *e, const ork_cinfo *ci, int s, const double *vin, int do_up_ref)
+static void modify_friction(ork_env *e, int pi, const ork_cinfo *ci, int s, const double *vin, int do_up_ref)
 {
   double *f = e->c_f+3*s, *ax = e->c_axis+9*s, v[3], fn, fs, vs, mu;
   v3_copy(vin,v);
@@ -564,7 +626,7 @@ static void modify_friction(ork_env *e, const ork_cinfo *ci, int s, const double
     }
     if( do_up_ref ){ e->c_type[s] = ORK_KF; v3_copy(e->c_pro+3*s,e->c_ref+3*s); }
   } else {
-    if( do_up_ref ) e->c_type[s] = ORK_SF;   /* rkFDUpdateRefSlide: slide mode out of scope */
+    if( do_up_ref ){ e->c_type[s] = ORK_SF; update_ref_slide(e,pi,s); }
   }
 }
 
@@ -581,10 +643,11 @@ static void solver_penalty(ork_env *e, int do_up_ref)
       v3_sub(e->c_vert+3*s,e->c_refw+3*s,d);
       link_point_wld_vel(&e->lw[cl->link],e->c_vert+3*s,vr);    /* rkFDChainPointRelativeVel (rkfd_util.c:42-60), STAT partner = 0 */
       if( w->box[p->box].link >= 0 ){ double vb[3]; link_point_wld_vel(&e->lw[w->box[p->box].link],e->c_vert+3*s,vb); v3_sub(vr,vb,vr); }
+      add_slide_vel(e,pi,e->c_vert+3*s,e->c_norm+3*s,vr);
       f[0] = -p->ci.E*d[0]; f[1] = -p->ci.E*d[1]; f[2] = -p->ci.E*d[2];
       v3_cat(f, -1.0*(p->ci.V + p->ci.E*w->dt), vr);
       if( v3_dot(f,e->c_axis+9*s) < 0.0 ) continue;
-      modify_friction(e,&p->ci,s,vr,do_up_ref);
+      modify_friction(e,pi,&p->ci,s,vr,do_up_ref);
       push_wrench(e,cl->link,e->c_vert+3*s,f);
       if( w->box[p->box].link >= 0 ){        /* the partner takes the opposite force at the same point (rkfd_util.c:276-278) */
         double fr[3] = { -f[0], -f[1], -f[2] }; push_wrench(e,w->box[p->box].link,e->c_vert+3*s,fr); }
@@ -900,16 +963,17 @@ static void solver_rigid(ork_env *e, int do_up_ref)
   const ork_world *w = e->w; int pi, k, N = 0, n, i, j, col;
   int *slot = (int*)malloc((w->nslot>0?w->nslot:1)*sizeof(int)), *plink = (int*)malloc((w->nslot>0?w->nslot:1)*sizeof(int));
   int *blink = (int*)malloc((w->nslot>0?w->nslot:1)*sizeof(int));      /* the partner's link when it moves, else -1 */
+  int *ppair = (int*)malloc((w->nslot>0?w->nslot:1)*sizeof(int));
   const ork_cinfo **pci = (const ork_cinfo**)malloc((w->nslot>0?w->nslot:1)*sizeof(void*));
   double *A = e->rA, *b = e->rb, *f = e->rf, dt = w->dt;
   /* _rkFDSolverCountContacts (rkfd_vert.c:22-29): contacts in (pair, vertex) order */
   for(pi=0;pi<w->npair;pi++){
     const ork_pair *p = &w->pair[pi]; const ork_cell *cl = &w->cell[p->cell];
     if( p->ci.type != ORK_CONTACT_RIGID ) continue;
-    for(k=0;k<cl->nvert;k++) if( e->c_active[p->sofs+k] ){ slot[N]=p->sofs+k; plink[N]=cl->link; blink[N]=w->box[p->box].link; pci[N]=&p->ci; N++; }
+    for(k=0;k<cl->nvert;k++) if( e->c_active[p->sofs+k] ){ slot[N]=p->sofs+k; plink[N]=cl->link; blink[N]=w->box[p->box].link; ppair[N]=pi; pci[N]=&p->ci; N++; }
   }
   e->rn = 0;
-  if( N == 0 ){ free(slot); free(plink); free(blink); free(pci); return; }
+  if( N == 0 ){ free(slot); free(plink); free(blink); free(ppair); free(pci); return; }
   n = 3*N; e->rn = n;
   /* rkFDUpdateAccBias (rkfd_util.c:149-161): full ABA with the friction / penalty wrenches, save */
   aba_backward(e); aba_forward(e,NULL,0);
@@ -934,6 +998,7 @@ static void solver_rigid(ork_env *e, int do_up_ref)
   for(k=0;k<N;k++){ double *vel = e->c_vel+3*slot[k];
     link_point_wld_vel(&e->lw[plink[k]],e->c_vert+3*slot[k],vel);
     if( blink[k] >= 0 ){ double vb[3]; link_point_wld_vel(&e->lw[blink[k]],e->c_vert+3*slot[k],vb); v3_sub(vel,vb,vel); }
+    add_slide_vel(e,ppair[k],e->c_vert+3*slot[k],e->c_norm+3*slot[k],vel);
     for(i=0;i<3;i++) b[3*k+i] += v3_dot(vel,e->c_axis+9*slot[k]+3*i); }
 
   if( w->solver == ORK_SOLVER_MLCP ){
@@ -976,7 +1041,7 @@ static void solver_rigid(ork_env *e, int do_up_ref)
       fn = fw[0]; fss = sqrt(fw[1]*fw[1]+fw[2]*fw[2]);
       mu = e->c_type[s]==ORK_SF ? pci[k]->SF : pci[k]->KF;
       if( fss > mu*fn - ORK_TOL ){ e->c_type[s] = ORK_KF; v3_copy(e->c_pro+3*s,e->c_ref+3*s); }
-      else e->c_type[s] = ORK_SF; }
+      else { e->c_type[s] = ORK_SF; update_ref_slide(e,ppair[k],s); } }       /* in EVERY evaluation, as the reference does (rkfd_mlcp.c:275-280) */
   } else {
     /* Vert: _rkFDSolverFrictionConstraint (rkfd_vert.c:73-103), _rkFDSolverCompensateDepth (:208-232),
      * _rkFDSolverQP (:258-283) */
@@ -1009,10 +1074,10 @@ static void solver_rigid(ork_env *e, int do_up_ref)
       if( do_up_ref ){
         for(i=0;i<pyr;i++) if( idx[pyr*k+i] ){ flag = 1; break; }
         if( flag ){ e->c_type[s] = ORK_KF; v3_copy(e->c_pro+3*s,e->c_ref+3*s); }
-        else e->c_type[s] = ORK_SF; } }
+        else { e->c_type[s] = ORK_SF; update_ref_slide(e,ppair[k],s); } } }
     free(nf); free(dz); free(Q); free(c); free(c2); free(init); free(idx);
   }
-  free(slot); free(plink); free(blink); free(pci);
+  free(slot); free(plink); free(blink); free(ppair); free(pci);
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -439,6 +439,21 @@ def create_world(world: World, B=None, devices=None):
     for chn, cell in zip(world.chains, cells):
         if not getattr(chn, "self_collide", False):        # as every example program of the reference does
             lib().rkCDPairChainUnreg(None, cell.chain_handle)
+        # slide mode of collision cells (the reference's fake crawler): through the shapes of the REGISTERED chain
+        L = lib()
+        L.rkLinkShape.restype = C.c_void_p; L.rkLinkShape.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        for f in ("rkFDShape3DSetSlideMode", "rkFDShape3DSetSlideVel", "rkFDShape3DSetSlideAxis"):
+            getattr(L, f).restype = C.c_void_p
+        L.rkFDShape3DSetSlideMode.argtypes = [C.c_void_p, C.c_void_p, C.c_bool]
+        L.rkFDShape3DSetSlideVel.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+        L.rkFDShape3DSetSlideAxis.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        for k, l in enumerate(chn.links):
+            for ci_, (vel, axis) in getattr(l, "slides", {}).items():
+                sh = L.rkLinkShape(cell.chain_handle, k, ci_)
+                ax = (C.c_double * 3)(*[float(a) for a in axis])
+                ok = sh and L.rkFDShape3DSetSlideMode(fd.h, sh, True) and L.rkFDShape3DSetSlideVel(fd.h, sh, float(vel)) and L.rkFDShape3DSetSlideAxis(fd.h, sh, ax)
+                if not ok:
+                    raise RuntimeError("rokifd_b200: slide mode: shape %d of link %d not found" % (ci_, k))
     fd.prp_set(world.dt, world.pyramid, world.friction_weight, world.max_iter)
     fd.set_solver(world.solver)
     fd.set_integrator(getattr(world, "integrator", "RKG"))

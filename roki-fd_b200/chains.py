@@ -71,6 +71,9 @@ class Link:
     # box primitives as (center(3), depth, width, height) in the link frame.  On a static link: a collision target.  On a
     # moving link: a target for the vertices of OTHER links' cells, and its 8 corners are a cell of this link (after `shapes`)
     boxes: List[tuple] = field(default_factory=list)
+    # slide mode ("fake crawler", rkFDCDCellSetSlideMode/-Vel/-Axis, rkfd_sim.c:386-440) per collision cell of the link:
+    # {cell index in the link (shapes first, then boxes): (belt speed, axis(3) in the link frame)}
+    slides: dict = field(default_factory=dict)
 
     def cells(self):
         """Vertex clouds of a moving link in cell order: the shapes, then the corners of its box primitives."""
@@ -100,6 +103,10 @@ class StaticBox:
     p: np.ndarray
     half: np.ndarray
     stuff: str
+    slide: Optional[tuple] = None          # (belt speed, axis(3) in the frame of the box's link)
+    link_R: np.ndarray = field(default_factory=lambda: np.eye(3))     # world frame of the (static) link that carries the box
+    link_p: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    order: int = 0                         # registration order of the shape among all shapes of the world
 
 
 @dataclass
@@ -164,9 +171,22 @@ class World:
                     Rp, pp = frames[l.parent]
                     R, p = Rp @ R, pp + Rp @ p
                 frames.append((R, p))
-                for (c, d, w, h) in l.boxes:
+                for bi, (c, d, w, h) in enumerate(l.boxes):
                     out.append(StaticBox(R=R, p=p + R @ np.asarray(c, float),
-                                         half=np.array([d / 2, w / 2, h / 2], float), stuff=l.stuff))
+                                         half=np.array([d / 2, w / 2, h / 2], float), stuff=l.stuff,
+                                         slide=l.slides.get(bi), link_R=R, link_p=p,
+                                         order=self.shape_order()[(id(ch), id(l), bi)]))
+        return out
+
+    def shape_order(self):
+        """Registration order of every collision shape: chains in the order of rkFDChainReg, links, shapes then boxes.  Decides
+        which cell of a pair is pd->cell[0] (rkFDUpdateRefSlide, rkfd_util.c:218-237)."""
+        out, n = {}, 0
+        for ch in self.chains:
+            for l in ch.links:
+                ncell = len(l.boxes) if ch.is_static else len(l.shapes) + len(l.boxes)
+                for k in range(ncell):
+                    out[(id(ch), id(l), k)] = n; n += 1
         return out
 
     @property

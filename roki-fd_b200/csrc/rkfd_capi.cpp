@@ -27,8 +27,14 @@ using namespace rkfd;
 struct _rkJoint { struct ChainImpl *chain; int link; };
 
 struct FDImpl;
+struct _zShape3D { struct ChainImpl *chain; int link, cell; };     /* a shape of a link = one collision cell */
 struct ChainImpl : ChainHost {
   std::vector<_rkJoint> joints;
+  std::vector<_zShape3D*> shapes;       /* handles given out by rkLinkShape (owned; a clone starts without any) */
+  ChainImpl() = default;
+  ChainImpl(const ChainImpl &o) : ChainHost(o), joints(o.joints), owner(o.owner), link_base(o.link_base), q_base(o.q_base) {}
+  ChainImpl &operator=(const ChainImpl &) = delete;
+  ~ChainImpl(){ for(_zShape3D *s : shapes) delete s; }
   FDImpl *owner = nullptr;     /* set for the clone held by a registered cell */
   int link_base = 0;           /* first global (moving) link index of this chain in the engine, -1 if static */
   int q_base = 0;
@@ -135,6 +141,39 @@ extern "C" void rkJointMotorSetInput(rkJoint *j, double *val)
  * example/chain/boxdrop_test.c:37, arm_box_test.c:49).  Pairs are formed in rkFDUpdateInit: call it before. */
 extern "C" void rkCDPairChainUnreg(rkCD *cd, rkChain *chain){ (void)cd; if( CI(chain) ) CI(chain)->self_collide = false; }
 
+/* ---- shapes / collision cells and their slide mode (reference rkfd_sim.c:386-440) ---------------- */
+static int link_cell_num(const ChainImpl *ci, int link){ const LinkHost &l = ci->links[link]; return ci->is_static() ? (int)l.boxes.size() : (int)l.shapes.size(); }
+extern "C" int rkLinkShapeNum(rkChain *chain, int link){ ChainImpl *ci = CI(chain); return ( ci && link >= 0 && link < (int)ci->links.size() ) ? link_cell_num(ci, link) : 0; }
+extern "C" zShape3D *rkLinkShape(rkChain *chain, int link, int k)
+{
+  ChainImpl *ci = CI(chain); if( !ci || link < 0 || link >= (int)ci->links.size() || k < 0 || k >= link_cell_num(ci, link) ) return NULL;
+  for(_zShape3D *s : ci->shapes) if( s->link == link && s->cell == k ) return s;
+  _zShape3D *s = new _zShape3D{ci, link, k}; ci->shapes.push_back(s); return s;
+}
+static LinkHost::Slide *cell_slide(rkCDCell *cell, const char *where)
+{
+  if( !cell || !cell->chain ) return nullptr;
+  ChainImpl *ci = cell->chain;
+  if( ci->owner && ci->owner->engine ){ complain(where, "slide mode must be set before rkFDUpdateInit"); return nullptr; }
+  LinkHost &l = ci->links[cell->link];
+  for(LinkHost::Slide &s : l.slides) if( s.cell == cell->cell ) return &s;
+  LinkHost::Slide s; s.cell = cell->cell; s.mode = false; s.vel = 0.0; s.axis[0] = s.axis[1] = s.axis[2] = 0.0;
+  l.slides.push_back(s); return &l.slides.back();
+}
+extern "C" void rkFDCDCellSetSlideMode(rkCDCell *cell, bool mode){ if( LinkHost::Slide *s = cell_slide(cell, "rkFDCDCellSetSlideMode") ) s->mode = mode; }
+extern "C" void rkFDCDCellSetSlideVel(rkCDCell *cell, double vel){ if( LinkHost::Slide *s = cell_slide(cell, "rkFDCDCellSetSlideVel") ) s->vel = vel; }
+extern "C" void rkFDCDCellSetSlideAxis(rkCDCell *cell, zVec3D *axis){ if( !axis ) return; if( LinkHost::Slide *s = cell_slide(cell, "rkFDCDCellSetSlideAxis") ){ s->axis[0] = axis->e[0]; s->axis[1] = axis->e[1]; s->axis[2] = axis->e[2]; } }
+
+extern "C" rkCDCell *rkFDShape3DGetCDCell(rkFD *fd, zShape3D *shape)
+{
+  FDImpl *fi = FI(fd); if( !fi || !shape ) return NULL;
+  for(rkFDCell *c : fi->cells) if( CI(&c->data.fc.chain) == shape->chain ) return shape;       /* the cell of a registered chain's shape */
+  return NULL;
+}
+extern "C" rkCDCell *rkFDShape3DSetSlideMode(rkFD *fd, zShape3D *shape, bool mode){ rkCDCell *c = rkFDShape3DGetCDCell(fd, shape); if( c ) rkFDCDCellSetSlideMode(c, mode); return c; }
+extern "C" rkCDCell *rkFDShape3DSetSlideVel(rkFD *fd, zShape3D *shape, double vel){ rkCDCell *c = rkFDShape3DGetCDCell(fd, shape); if( c ) rkFDCDCellSetSlideVel(c, vel); return c; }
+extern "C" rkCDCell *rkFDShape3DSetSlideAxis(rkFD *fd, zShape3D *shape, zVec3D *axis){ rkCDCell *c = rkFDShape3DGetCDCell(fd, shape); if( c ) rkFDCDCellSetSlideAxis(c, axis); return c; }
+
 extern "C" void rkB200LinkDescInit(rkB200LinkDesc *d)
 {
   std::memset(d, 0, sizeof *d); d->parent = -1; d->frame_R[0] = d->frame_R[4] = d->frame_R[8] = 1.0;
@@ -164,6 +203,7 @@ extern "C" int rkChainB200LinkAddBox(rkChain *c, int link, const double center[3
 {
   ChainImpl *ci = CI(c); if( !ci || link < 0 || link >= (int)ci->links.size() ) return 1;
   BoxShape b; std::memcpy(b.center, center, sizeof b.center); b.depth = depth; b.width = width; b.height = height;
+  b.cloud = (int)ci->links[link].shapes.size();
   ci->links[link].boxes.push_back(b);
   /* a box on a moving link collides through its 8 corners ([EXT] zeo box -> polyhedron) */
   std::vector<double> v;

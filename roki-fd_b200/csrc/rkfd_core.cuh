@@ -240,7 +240,7 @@ struct SpecSerialRevRolled {
   static RKFD_HD int sc(int i, const LinkDev &){ return RG_ ? PER*i + 9 : 4*(i-1); }
 };
 inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0, int GEN = 0){
-  if( m.nfw > 1 || m.npair > m.npair_static ) return false;
+  if( m.nfw > 1 || m.npair > m.npair_static || m.nslide > 0 ) return false;       /* slide mode: generic kernel only */
   if( RG ? !( m.has_rigid && m.nrg == 1 && m.rigid_link == NL-1 ) : m.has_rigid ) return false;
   if( m.nl != NL || NL < 2 ) return false;
   for(int i=0;i<NL;i++){
@@ -255,7 +255,7 @@ inline bool spec_serial_rev_rolled_match(const ModelDev &m, int NL, int RG = 0, 
 
 /* does the flattened model have the shape SpecSerialRev<.,NL,CLS> assumes? (host side) */
 inline bool spec_serial_rev_match(const ModelDev &m, int NL, unsigned CLS){
-  if( m.has_rigid || m.nl != NL || NL < 2 || m.nfw > 1 || m.npair > m.npair_static ) return false;
+  if( m.has_rigid || m.nl != NL || NL < 2 || m.nfw > 1 || m.npair > m.npair_static || m.nslide > 0 ) return false;
   for(int i=0;i<NL;i++){
     const LinkDev &L = m.link[i];
     if( i == 0 ){ if( L.parent >= 0 || L.jtype != J_FIXED || L.cell_end > L.cell_begin ) return false; continue; }
@@ -505,6 +505,46 @@ struct Core {
   }
   static RKFD_HD M3 box_R(const BoxDev &bx){ M3 Rb; Rb.xx=bx.R[0]; Rb.xy=bx.R[1]; Rb.xz=bx.R[2]; Rb.yx=bx.R[3]; Rb.yy=bx.R[4]; Rb.yz=bx.R[5]; Rb.zx=bx.R[6]; Rb.zy=bx.R[7]; Rb.zz=bx.R[8]; return Rb; }
 
+  /* does pair pr involve a cell in slide mode?  Always false in the model specialisations (they do not match such worlds): their
+   * kernels carry none of the slide code */
+  static RKFD_HD bool has_slide(const PairDev &pr){ if constexpr ( Spec::NL != 0 ) return false; else return (pr.slinfo & 0xffff) != 0; }
+  /* ---- slide mode of collision cells ("fake crawler": rkFDLinkAddSlideVel rkfd_util.c:26-40, rkFDUpdateRefSlide :218-237).
+   * Belt direction of slide entry sd, carried by the frame (R, pw), at world point p: (R axis) x (p - pw) without its normal
+   * component; returns its norm */
+  static RKFD_HD double slide_dir(const SlideDev &sd, const M3 &R, V3 pw, V3 p, V3 n, V3 &sv){
+    sv = cross(mul(R, v3(sd.axis[0], sd.axis[1], sd.axis[2])), p - pw); sv = sv + (-dot(sv, n))*n; return norm(sv); }
+  static RKFD_HD M3 slide_lR(const SlideDev &sd){ M3 r; r.xx=sd.lR[0]; r.xy=sd.lR[1]; r.xz=sd.lR[2]; r.yx=sd.lR[3]; r.yy=sd.lR[4]; r.yz=sd.lR[5]; r.zx=sd.lR[6]; r.zy=sd.lR[7]; r.zz=sd.lR[8]; return r; }
+  /* what the belts add to the relative velocity (vertex's cell minus partner) of pair pr at world point p with contact normal n;
+   * (Rv, pv): frame of the vertex's link; (Rp, pp): frame of a MOVING partner link (a static partner's frame is in its entry) */
+  static RKFD_HD V3 slide_vel(const ModelDev &m, const PairDev &pr, const M3 &Rv, V3 pv, const M3 &Rp, V3 pp, V3 p, V3 n){
+    V3 out = v3(0,0,0); const int sc = (pr.slinfo & 255) - 1, sb = ((pr.slinfo >> 8) & 255) - 1;
+    if( sc >= 0 ){ V3 sv; const double nv = slide_dir(m.slide[sc], Rv, pv, p, n, sv); if( !(fabs(nv) < ZTOL) ) out = out + (m.slide[sc].vel/nv)*sv; }
+    if( sb >= 0 ){ const SlideDev &sd = m.slide[sb]; V3 sv; const bool mov = pr.mbox >= 0;
+      const double nv = slide_dir(sd, mov ? Rp : slide_lR(sd), mov ? pp : v3(sd.lp[0], sd.lp[1], sd.lp[2]), p, n, sv);
+      if( !(fabs(nv) < ZTOL) ) out = out + (-sd.vel/nv)*sv; }
+    return out; }
+  /* the anchor of a sticking contact rides on the belt: shift of the anchor in the BOX frame (Rbw = world rotation of the box,
+   * Rpl = world rotation of the partner's link).  The reference adds R_k^T sv to _ref with k = pd->cell[1]'s link when the
+   * sliding cell is the vertex's cell, else pd->cell[0]'s link, and _ref lives in the partner's frame: world shift
+   * R_partner R_k^T sv (= sv whenever the sliding cell is pd->cell[0]) - mirrored */
+  static RKFD_HD V3 slide_ref_shift(const ModelDev &m, const PairDev &pr, const M3 &Rv, V3 pv, const M3 &Rpl, V3 pp, const M3 &Rbw, V3 p, V3 n){
+    V3 db = v3(0,0,0); const int sc = (pr.slinfo & 255) - 1, sb = ((pr.slinfo >> 8) & 255) - 1;
+    const bool vfirst = (pr.slinfo >> 16) & 1, mov = pr.mbox >= 0;
+    for(int i=0;i<2;i++){
+      const bool is_v = vfirst ? i == 0 : i == 1; const int idx = is_v ? sc : sb;
+      if( idx < 0 ) continue;
+      const SlideDev &sd = m.slide[idx]; V3 sv;
+      const double nv = is_v ? slide_dir(sd, Rv, pv, p, n, sv) : slide_dir(sd, mov ? Rpl : slide_lR(sd), mov ? pp : v3(sd.lp[0], sd.lp[1], sd.lp[2]), p, n, sv);
+      if( fabs(nv) < ZTOL ) continue;
+      const double k = ( is_v ? -1.0 : 1.0 )*m.dt*sd.vel/nv;
+      sv = k*sv;
+      const bool k_is_v = is_v ? !vfirst : vfirst;
+      const V3 dw = mul(Rpl, k_is_v ? tmul(Rv, sv) : tmul(Rpl, sv));
+      db = db + tmul(Rbw, dw);
+    }
+    return db; }
+  static RKFD_HD M3 box_lR(const BoxDev &bx){ M3 r; r.xx=bx.lR[0]; r.xy=bx.lR[1]; r.xz=bx.lR[2]; r.yx=bx.lR[3]; r.yy=bx.lR[4]; r.yz=bx.lR[5]; r.zx=bx.lR[6]; r.zy=bx.lR[7]; r.zz=bx.lR[8]; return r; }
+
   /* ---- contact of the cells carried by link i: vertex-in-box detection ([EXT A-10]), elastic pairs:
    * penalty force + Coulomb clamp + wrench accumulation (rkfd_penalty.c:11-31, rkfd_util.c:239-282).
    * Two phases per (cell, box) pair so that a warp does not walk through the expensive force code once per
@@ -562,7 +602,8 @@ struct Core {
           const V3 refw = pb + mul(Rb, refb);
           const V3 d = vw - refw;
           /* rkFDLinkPointWldVel (rkfd_util.c:14-24); the static partner contributes 0 */
-          const V3 vr = vlw + cross(omw, vw - pw);
+          V3 vr = vlw + cross(omw, vw - pw);
+          if( has_slide(pr) ) vr = vr + slide_vel(m, pr, Rw, pw, Rw, pw, vw, n);
           V3 f = (-pr.E)*d + (-1.0*(pr.V + pr.E*m.dt))*vr;
           if( dot(f,n) < 0.0 ){ if( ref ){ c.gst(c.st.cf,3*s,f.x); c.gst(c.st.cf,3*s+1,f.y); c.gst(c.st.cf,3*s+2,f.z); } continue; }
           /* rkFDContactForceModifyFriction */
@@ -577,7 +618,11 @@ struct Core {
               f = f + ((-(1.0 - exp(-1.0*m.friction_weight*vs))*pr.KF*fn)/vs)*v;
             }
             if( ref ){ cfl |= kbit; c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
-          } else if( ref ) cfl &= ~kbit;
+          } else if( ref ){
+            cfl &= ~kbit;
+            if( has_slide(pr) ){ const V3 nr = refb + slide_ref_shift(m, pr, Rw, pw, box_lR(bx), v3(0,0,0), Rb, vw, n);
+              c.gst(c.st.cref,3*s,nr.x); c.gst(c.st.cref,3*s+1,nr.y); c.gst(c.st.cref,3*s+2,nr.z); }
+          }
           /* rkFDContactForcePushWrench: (f, pos x f) at the link origin, link axes */
           const V3 pos = tmul(Rw, vw - pw);
           const V3 fl = tmul(Rw, f);
@@ -634,7 +679,8 @@ struct Core {
           } else refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
           if( pr.type != C_ELASTIC ) continue;     /* rigid pairs are solved by the rigid path */
           const V3 d = vw - (pb + mul(Rb, refb));
-          const V3 vr = (vlw + cross(omw, vw - pw)) - (vlwB + cross(omwB, vw - pwB));
+          V3 vr = (vlw + cross(omw, vw - pw)) - (vlwB + cross(omwB, vw - pwB));
+          if( has_slide(pr) ) vr = vr + slide_vel(m, pr, Rw, pw, RwB, pwB, vw, n);
           V3 f = (-pr.E)*d + (-1.0*(pr.V + pr.E*m.dt))*vr;
           if( dot(f,n) < 0.0 ){ if( ref ){ c.gst(c.st.cf,3*s,f.x); c.gst(c.st.cf,3*s+1,f.y); c.gst(c.st.cf,3*s+2,f.z); } continue; }
           const double fn = dot(f,n), f1 = dot(f,t1), f2 = dot(f,t2);
@@ -646,7 +692,11 @@ struct Core {
             f = fn*n;
             if( !(fabs(vs) < ZTOL) ) f = f + ((-(1.0 - exp(-1.0*m.friction_weight*vs))*pr.KF*fn)/vs)*v;
             if( ref ){ cfl |= kbit; c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
-          } else if( ref ) cfl &= ~kbit;
+          } else if( ref ){
+            cfl &= ~kbit;
+            if( has_slide(pr) ){ const V3 nr = refb + slide_ref_shift(m, pr, Rw, pw, RwB, pwB, Rb, vw, n);
+              c.gst(c.st.cref,3*s,nr.x); c.gst(c.st.cref,3*s+1,nr.y); c.gst(c.st.cref,3*s+2,nr.z); }
+          }
           { const V3 pos = tmul(Rw, vw - pw), fl = tmul(Rw, f); wA.l = wA.l + fl; wA.a = wA.a + cross(pos, fl); }
           { const V3 pos = tmul(RwB, vw - pwB), fl = tmul(RwB, v3(-f.x, -f.y, -f.z)); wB.l = wB.l + fl; wB.a = wB.a + cross(pos, fl); }
           if( ref ){ c.gst(c.st.cf,3*s,f.x); c.gst(c.st.cf,3*s+1,f.y); c.gst(c.st.cf,3*s+2,f.z); }
@@ -1391,7 +1441,8 @@ struct Core {
         const V3 refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
         const V3 d = vw - (pb + mul(Rb, refb));
         const V3 rho = vw - pw;
-        const V3 vel = vlw + cross(omw, rho);
+        V3 vel = vlw + cross(omw, rho);
+        if( has_slide(pr) ) vel = vel + slide_vel(m, pr, Rw, pw, Rw, pw, vw, ax[0]);
         /* rkFDLinkPointWldAcc (rkfd_util.c:92-101): R ( a + alpha x r + w x (w x r) ) */
         const V3 r = tmul(Rw, rho);
         V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r)));
@@ -1469,7 +1520,7 @@ struct Core {
       const double mu = c.W1(o+51);
       const bool kin = sqrt(fw.y*fw.y + fw.z*fw.z) > mu*fw.x - ZTOL;
       if( kin ){ nfl |= 2ull << (2*s); const V3 prob = w13(o+48); c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
-      else nfl &= ~(2ull << (2*s));
+      else { nfl &= ~(2ull << (2*s)); slide_commit_static(m, s, Rw, pw, pw + w13(o+45), w13(o+18)); }
       /* rkFDContactForcePushWrench (rkfd_util.c:268-282) */
       const V3 pos = tmul(Rw, w13(o+45)), fll = tmul(Rw, fw);
       wl = wl + fll; wa = wa + cross(pos, fll);
@@ -1557,7 +1608,8 @@ struct Core {
         const V3 refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
         const V3 d = vw - (pb + mul(Rb, refb));
         const V3 rho = vw - pw;
-        const V3 vel = vlw + cross(omw, rho);
+        V3 vel = vlw + cross(omw, rho);
+        if( has_slide(pr) ) vel = vel + slide_vel(m, pr, Rw, pw, Rw, pw, vw, ax[0]);
         const V3 r = tmul(Rw, rho);
         V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r)));
         if( grav_acc(m) ) accp.z -= GRAVITY;
@@ -1732,7 +1784,7 @@ struct Core {
       const bool flag = am[k] != 0;
       if( ref ){
         if( flag ){ nfl |= 2ull << (2*s); const V3 prob = w13(o+48); c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
-        else nfl &= ~(2ull << (2*s));
+        else { nfl &= ~(2ull << (2*s)); slide_commit_static(m, s, Rw, ld3(fsl+9), ld3(fsl+9) + w13(o+45), w13(o+18)); }
         c.gst(c.st.cf,3*s,fw.x); c.gst(c.st.cf,3*s+1,fw.y); c.gst(c.st.cf,3*s+2,fw.z);
       }
       const V3 pos = tmul(Rw, w13(o+45)), fll = tmul(Rw, fw);
@@ -1785,7 +1837,9 @@ struct Core {
         box_face(bx, Rb, vb, bx.half[0]-fabs(vb.x), bx.half[1]-fabs(vb.y), bx.half[2]-fabs(vb.z), nn, t1, t2, prob);
         const V3 refb = v3(c.gld(c.st.cref,3*s), c.gld(c.st.cref,3*s+1), c.gld(c.st.cref,3*s+2));
         const V3 d = vw - (pb + mul(Rb, refb));
-        const V3 vel = mul(Rw, vl) + cross(mul(Rw, om), vw - pw) - velB;
+        V3 vel = mul(Rw, vl) + cross(mul(Rw, om), vw - pw) - velB;
+        if( has_slide(pr) ){ const int fb = Lb >= 0 ? m.link[Lb].frame_slot : L.frame_slot;
+          vel = vel + slide_vel(m, pr, Rw, pw, ldm(fb), ld3(fb+9), vw, nn); }
         /* rkFDLinkPointWldAcc (rkfd_util.c:92-101): R ( a + alpha x r + w x (w x r) ) */
         const V3 r = tmul(Rw, vw - pw);
         const V3 accp = mul(Rw, al + cross(aa, r) + cross(om, cross(om, r))) - accB;
@@ -1875,6 +1929,7 @@ struct Core {
           if( lane == 0 ){
             push_rigid(m, k, fw, ref);
             if( kin ){ const V3 prob = g3(m,k,18); c.gst(c.st.cref,3*s,prob.x); c.gst(c.st.cref,3*s+1,prob.y); c.gst(c.st.cref,3*s+2,prob.z); }
+            else slide_commit_dense(m, k);
           }
         }
       } else {
@@ -1902,6 +1957,30 @@ struct Core {
       c.S(B.wext_slot+3) += tB.x; c.S(B.wext_slot+4) += tB.y; c.S(B.wext_slot+5) += tB.z;
     }
     if( ref ){ c.gst(c.st.cf,3*s,fw.x); c.gst(c.st.cf,3*s+1,fw.y); c.gst(c.st.cf,3*s+2,fw.z); }
+  }
+
+  /* a rigid contact committed as sticking: its anchor rides on the belts of the pair (rkFDUpdateRefSlide, rkfd_mlcp.c:279,
+   * rkfd_vert.c:318).  Static partner, vertex link frame (Rw, pw): the single-link paths */
+  RKFD_HD void slide_commit_static(const ModelDev &m, int s, const M3 &Rw, V3 pw, V3 vw, V3 n){
+    const PairDev &pr = m.pair[m.slot_pair[s]];
+    if( !has_slide(pr) ) return;
+    const BoxDev &bx = m.box[pr.box];
+    const V3 db = slide_ref_shift(m, pr, Rw, pw, box_lR(bx), v3(0,0,0), box_R(bx), vw, n);
+    c.gst(c.st.cref,3*s, c.gld(c.st.cref,3*s) + db.x); c.gst(c.st.cref,3*s+1, c.gld(c.st.cref,3*s+1) + db.y); c.gst(c.st.cref,3*s+2, c.gld(c.st.cref,3*s+2) + db.z);
+  }
+  /* the same for rigid contact k of the dense path (geometry record G; the partner may move) */
+  RKFD_HD void slide_commit_dense(const ModelDev &m, int k){
+    const PairDev &pr = m.pair[(int)G(m,k,26)];
+    if( !has_slide(pr) ) return;
+    const int s = (int)G(m,k,24), Lv = (int)G(m,k,25), Lb = (int)G(m,k,27);
+    const int fv = m.link[Lv].frame_slot; const M3 Rw = ldm(fv); const V3 pw = ld3(fv+9);
+    M3 Rpl, Rbw; V3 pp = v3(0,0,0);
+    if( Lb >= 0 ){ const MBoxDev &mb = m.mbox[pr.mbox]; const int fb = m.link[Lb].frame_slot; Rpl = ldm(fb); pp = ld3(fb+9);
+      M3 Rl; Rl.xx=mb.R[0]; Rl.xy=mb.R[1]; Rl.xz=mb.R[2]; Rl.yx=mb.R[3]; Rl.yy=mb.R[4]; Rl.yz=mb.R[5]; Rl.zx=mb.R[6]; Rl.zy=mb.R[7]; Rl.zz=mb.R[8];
+      Rbw = mm(Rpl, Rl); }
+    else { const BoxDev &bx = m.box[pr.box]; Rpl = box_lR(bx); Rbw = box_R(bx); }
+    const V3 db = slide_ref_shift(m, pr, Rw, pw, Rpl, pp, Rbw, g3(m,k,0), g3(m,k,3));
+    c.gst(c.st.cref,3*s, c.gld(c.st.cref,3*s) + db.x); c.gst(c.st.cref,3*s+1, c.gld(c.st.cref,3*s+1) + db.y); c.gst(c.st.cref,3*s+2, c.gld(c.st.cref,3*s+2) + db.z);
   }
 
   /* Vert: friction pyramid + least-squares QP by the active-set method (rkfd_vert.c:73-103, 208-324;
@@ -2124,6 +2203,7 @@ struct Core {
       if( lane == 0 ){
         push_rigid(m, k, fw, ref);
         if( ref && flag ){ const V3 prob = g3(m,k,18); c.gst(c.st.cref,3*sidx,prob.x); c.gst(c.st.cref,3*sidx+1,prob.y); c.gst(c.st.cref,3*sidx+2,prob.z); }
+        if( ref && !flag ) slide_commit_dense(m, k);
       }
     }
     return nfl;

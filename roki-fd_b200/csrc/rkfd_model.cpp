@@ -82,8 +82,17 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   }
 
   std::vector<std::string> link_stuff; std::vector<int> link_chain; std::vector<bool> chain_self;
-  struct StatBox { BoxDev b; std::string stuff; };
+  struct StatBox { BoxDev b; std::string stuff; int ord, slide; };
   std::vector<StatBox> boxes;
+  std::vector<int> cell_ord, cell_slide, mbox_ord, mbox_slide;      /* registration order / slide entry (-1: none) of every cell and moving box */
+  int ord = 0;                                                       /* shapes in the order of rkFDChainReg: chains, links, shapes then boxes */
+  auto add_slide = [&](const LinkHost::Slide *sl, const double *lR, const double *lp) -> int {
+    if( !sl ) return -1;
+    if( m.nslide >= MAX_SLIDES ) return -2;
+    SlideDev &d = m.slide[m.nslide]; d.vel = sl->vel; std::memcpy(d.axis, sl->axis, sizeof d.axis);
+    static const double I3[9] = {1,0,0, 0,1,0, 0,0,1}, Z3[3] = {0,0,0};
+    std::memcpy(d.lR, lR ? lR : I3, sizeof d.lR); std::memcpy(d.lp, lp ? lp : Z3, sizeof d.lp);
+    return m.nslide++; };
 
   /* ---- moving chains -> forest of links (registration order); static chains -> world boxes */
   int nl = 0, nq = 0;
@@ -99,12 +108,16 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
           mat3_mul(Rp, l.Ro, R); mat3_mulv(Rp, l.po, t); for(int k=0;k<3;k++) p[k] = pp[k] + t[k];
         }
         std::memcpy(fr[i].data(), R, sizeof R); std::memcpy(fr[i].data()+9, p, sizeof p);
+        int bidx = 0;
         for(const BoxShape &bs : l.boxes){
           StatBox sb; double c[3];
           mat3_mul(R, bs.R, sb.b.R); mat3_mulv(R, bs.center, c);
           for(int k=0;k<3;k++) sb.b.p[k] = p[k] + c[k];
           sb.b.half[0] = 0.5*bs.depth; sb.b.half[1] = 0.5*bs.width; sb.b.half[2] = 0.5*bs.height;
-          sb.stuff = l.stuff; boxes.push_back(sb);
+          std::memcpy(sb.b.lR, R, sizeof sb.b.lR);
+          sb.stuff = l.stuff; sb.ord = ord++; sb.slide = add_slide(l.slide_of(bidx++), R, p);
+          if( sb.slide == -2 ){ err = "too many cells in slide mode (MAX_SLIDES)"; return false; }
+          boxes.push_back(sb);
         }
       }
       continue;
@@ -147,18 +160,32 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
       d.pz = ( ( d.jtype == J_REVOL || d.jtype == J_FIXED ) && d.po[0] == 0.0 && d.po[1] == 0.0 ) ? 1 : 0;
       if( d.ndof != 1 ) d.mtype = M_NONE;
       d.cell_begin = m.ncell;
+      int cidx = 0;
       for(const auto &sh : l.shapes){
         const int nv = (int)sh.size()/3;
         if( m.ncell >= MAX_CELLS ){ err = "too many collision cells (MAX_CELLS)"; return false; }
         if( m.nvert + nv > MAX_VERTS ){ err = "too many collision vertices (MAX_VERTS)"; return false; }
         CellDev &c = m.cell[m.ncell++]; c.link = nl; c.vofs = m.nvert; c.nvert = nv;
         std::memcpy(m.vert + 3*m.nvert, sh.data(), 3*nv*sizeof(double)); m.nvert += nv;
+        /* every cell is one registered shape (a box primitive and its corner cloud are ONE shape of the reference) */
+        const int o = ord++;
+        const int sl = add_slide(l.slide_of(cidx), nullptr, nullptr);
+        if( sl == -2 ){ err = "too many cells in slide mode (MAX_SLIDES)"; return false; }
+        cell_ord.push_back(o); cell_slide.push_back(sl); cidx++;
       }
       d.cell_end = m.ncell;
       for(const BoxShape &bs : l.boxes){         /* box primitives of a moving link: targets */
         if( m.nmbox >= MAX_MBOXES ){ err = "too many boxes on moving links (MAX_MBOXES)"; return false; }
         MBoxDev &mb = m.mbox[m.nmbox++]; std::memcpy(mb.R, bs.R, sizeof mb.R); std::memcpy(mb.p, bs.center, sizeof mb.p);
         mb.half[0] = 0.5*bs.depth; mb.half[1] = 0.5*bs.width; mb.half[2] = 0.5*bs.height; mb.link = nl;
+        /* its corner cloud is cell `cloud` of the link (recorded by whoever added the box; else the clouds trail the shapes):
+         * the box shares registration order and slide entry with it */
+        const int k = (int)(&bs - &l.boxes[0]), nshape = (int)l.shapes.size() - (int)l.boxes.size();
+        const int cl = bs.cloud >= 0 ? bs.cloud : nshape + k;
+        int o = ord, sl = -1;
+        if( cl >= 0 && d.cell_begin + cl < (int)cell_ord.size() ){ o = cell_ord[d.cell_begin + cl]; sl = cell_slide[d.cell_begin + cl]; }
+        mbox_slide.push_back(sl);
+        mbox_ord.push_back(o);
       }
       link_stuff.push_back(l.stuff); link_chain.push_back((int)chain_self.size() - 1);
       nl++;
@@ -183,6 +210,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
       for(const auto &e : w.ci) if( (e.a==sa && e.b==sb) || (e.a==sb && e.b==sa) ){ ci = &e; break; }
       p.type = ci->type; p.K = ci->K; p.L = ci->L; p.E = ci->E; p.V = ci->V; p.SF = ci->SF; p.KF = ci->KF;
       if( p.type == C_ELASTIC ) m.has_elastic = 1; else m.has_rigid = 1;
+      p.slinfo = (cell_slide[c] + 1) | ((boxes[b].slide + 1) << 8) | ( cell_ord[c] < boxes[b].ord ? 1 << 16 : 0 );
     }
     m.cell[c].pair_end = m.npair;
   }
@@ -207,6 +235,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
       p.cell = c; p.box = -1; p.mbox = b; p.sofs = sofs; sofs += m.cell[c].nvert;
       p.type = ci->type; p.K = ci->K; p.L = ci->L; p.E = ci->E; p.V = ci->V; p.SF = ci->SF; p.KF = ci->KF;
       if( p.type == C_ELASTIC ) m.has_elastic = 1; else { m.has_rigid = 1; m.rigid_moving = 1; }
+      p.slinfo = (cell_slide[c] + 1) | ((mbox_slide[b] + 1) << 8) | ( cell_ord[c] < mbox_ord[b] ? 1 << 16 : 0 );
       m.link[la].mcol = 1; m.link[lb].mcol = 1;
     }
     if( dropped ) std::fprintf(stderr, "rokifd_b200: %d pair(s) of cells on two MOVING links have rigid contact info: not formed under the Volume "

@@ -16,7 +16,8 @@ struct MotorHost {
 };
 
 /* zeo box: depth along ax, width along ay, height along az; R = [ax ay az] (columns, row-major storage), identity by default */
-struct BoxShape { double center[3]; double depth, width, height; double R[9] = {1,0,0, 0,1,0, 0,0,1}; };
+struct BoxShape { double center[3]; double depth, width, height; double R[9] = {1,0,0, 0,1,0, 0,0,1};
+                  int cloud = -1;   /* moving link: index in LinkHost::shapes of the box's corner cloud (-1: the clouds trail the shapes) */ };
 
 struct LinkHost {
   std::string name, stuff;
@@ -32,6 +33,11 @@ struct LinkHost {
   MotorHost motor;
   std::vector<std::vector<double>> shapes;   /* vertex clouds, 3 doubles per vertex, link frame */
   std::vector<BoxShape> boxes;               /* box primitives (kept for static links) */
+  /* slide mode per collision cell of the link (rkFDCDCellSetSlideMode/-Vel/-Axis): cell = index among the link's cells (moving
+   * link: shapes, then the corner clouds of its boxes; static link: its boxes) */
+  struct Slide { int cell; bool mode; double vel; double axis[3]; };
+  std::vector<Slide> slides;
+  const Slide *slide_of(int cell) const { for(const Slide &s : slides) if( s.cell == cell && s.mode ) return &s; return nullptr; }
 };
 
 inline int jtype_ndof(int jt){

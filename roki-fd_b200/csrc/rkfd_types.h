@@ -77,9 +77,15 @@ struct LinkDev {
 };
 
 struct CellDev { int link, vofs, nvert, pair_begin, pair_end; };
-struct BoxDev { double R[9], p[3], half[3]; };
+struct BoxDev { double R[9], p[3], half[3]; double lR[9]; };     /* world frame of the box; lR: world rotation of the (static) link that carries it (slide mode) */
 struct MBoxDev { double R[9], p[3], half[3]; int link, pad_; };      /* frame in the carrying link */
-struct PairDev { int cell, box, sofs, type; double K, L, E, V, SF, KF; int fofs, volbox; int mbox, pad_; };   /* fofs: flag position of vertex 0 (word fofs>>5, bit pair fofs&31); volbox: the cell has the 8 corners of a box in sign-bit order (Volume solver);
+/* slide mode of a collision cell ("fake crawler", reference rkfd_sim.c:386-440): belt speed, axis in the frame of the cell's link;
+ * (lR, lp): world frame of the link of a STATIC box */
+struct SlideDev { double vel, axis[3], lR[9], lp[3]; };
+constexpr int MAX_SLIDES = 8;
+/* slinfo: bits 0-7 = 1 + slide entry of the vertex's cell (0: none), bits 8-15 = the same for the box, bit 16 = the vertex's
+ * cell was registered before the box's (it is pd->cell[0], rkFDUpdateRefSlide rkfd_util.c:218-237) */
+struct PairDev { int cell, box, sofs, type; double K, L, E, V, SF, KF; int fofs, volbox; int mbox, slinfo; };   /* fofs: flag position of vertex 0 (word fofs>>5, bit pair fofs&31); volbox: the cell has the 8 corners of a box in sign-bit order (Volume solver);
                                  * mbox >= 0: the target is box `mbox` on a moving link (then box = -1): elastic pairs only */
 
 struct ModelDev {
@@ -90,6 +96,7 @@ struct ModelDev {
   int nmbox;
   int need_world;      /* any collision cell: world frames must be propagated */
   int has_rigid, has_elastic;
+  int nslide; SlideDev slide[MAX_SLIDES];
   int rigid_moving;    /* a rigid pair of two moving links exists: the dense rigid path (A couples the two links / chains) */
   int solver, pyramid, max_iter;
   int integrator;      /* 0 Runge-Kutta-Gill, 1 classical Runge-Kutta, 2 Euler, 3 Heun ([EXT] zODE2AssignRegular) */

@@ -299,7 +299,7 @@ bool ztk_read_chain(const char *filename, ChainHost &chain, std::string &err)
       for(const Field &f : s.fields) if( f.key == "shape" && !f.val.empty() ){
         auto it = shapes.find(f.val[0]); if( it == shapes.end() ){ err = "unknown shape '" + f.val[0] + "'"; return false; }
         if( !it->second.verts.empty() ) l.shapes.push_back(it->second.verts);
-        if( it->second.is_box ) l.boxes.push_back(it->second.box);
+        if( it->second.is_box ){ BoxShape bx = it->second.box; bx.cloud = it->second.verts.empty() ? -1 : (int)l.shapes.size() - 1; l.boxes.push_back(bx); }
         if( it->second.has_mp ) lmp.add(it->second.mp); else if( com_auto || inertia_auto ) warn += "shape '" + f.val[0] + "' has no mass properties for COM/inertia: auto; ";
       }
       /* `COM: auto` / `inertia: auto` / `density:`: uniform density over the link's shapes ([EXT] Zeo; arm.ztk:79-80) */

@@ -83,6 +83,8 @@ void hostsim_add_cell(HostSim *h, int chain, int link, int nvert, const double *
 void hostsim_add_box(HostSim *h, int chain, int link, const double *center, double d, double w, double ht)
 { BoxShape b; std::memcpy(b.center, center, 24); b.depth = d; b.width = w; b.height = ht; h->chains[chain]->links[link].boxes.push_back(b); }
 void hostsim_unreg_self_collision(HostSim *h, int chain){ h->chains[chain]->self_collide = false; }
+void hostsim_set_slide(HostSim *h, int chain, int link, int cell, double vel, const double *axis)
+{ LinkHost::Slide s; s.cell = cell; s.mode = true; s.vel = vel; std::memcpy(s.axis, axis, sizeof s.axis); h->chains[chain]->links[link].slides.push_back(s); }
 void hostsim_add_contact_info(HostSim *h, int sa, int sb, int type, double K, double L, double E, double V, double SF, double KF)
 { ContactInfoHost c; c.a = "s"+std::to_string(sa); c.b = "s"+std::to_string(sb); c.type = type; c.K=K; c.L=L; c.E=E; c.V=V; c.SF=SF; c.KF=KF; h->world.ci.push_back(c); }
 void hostsim_set_prp(HostSim *h, double dt, int pyramid, double fw, int max_iter, int solver)

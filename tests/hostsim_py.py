@@ -71,6 +71,9 @@ class HostSim:
                 for (ctr, d, w, ht) in l.boxes:
                     _, pc = _d(ctr)
                     L.hostsim_add_box(self.h, c, k, pc, d, w, ht)
+                for cell, (vel, axis) in l.slides.items():
+                    L.hostsim_set_slide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, _dp]
+                    L.hostsim_set_slide(self.h, c, k, cell, float(vel), _d(np.asarray(axis, float))[1])
         L.hostsim_unreg_self_collision.argtypes = [C.c_void_p, C.c_int]
         for c, chn in enumerate(world.chains):
             if not chn.self_collide:

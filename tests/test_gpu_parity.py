@@ -825,6 +825,29 @@ def test_rigid_moving_vs_moving_contact(capi, oracle, kind, solver):
     fd.destroy()
 
 
+@pytest.mark.parametrize("name", ["belt_registered_second_penalty", "belt_registered_first_penalty", "crawler_box_on_plain_floor_penalty",
+                                  "belt_mlcp", "belt_registered_first_vert"])
+def test_slide_mode(capi, oracle, name):
+    """SURVEY.md section 8(f)4, the slide mode ("fake crawler", rkfd_sim.c:386-440): set through the reference's own calls
+    (rkFDShape3DSetSlideMode / -Vel / -Axis on a shape of the registered chain), belt velocity in the relative contact velocity
+    (rkfd_util.c:26-40), anchors of sticking contacts riding on the belt (:218-237); penalty, MLCP and Vert; 400 steps against
+    the oracle."""
+    from test_kernel_core_host import slide_worlds, slide_states
+    w = slide_worlds()[name]()
+    B = 256
+    q, qd, u = slide_states(w, B)
+    fd = gpu_world(capi, w, q, qd, u)
+    fd.update_n(400)
+    gq = fd.batch_get_state()[0]; a = fd.batch_get_contact()[0]
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=400)
+    err = np.abs(gq - o[0]).max(1) / np.maximum(np.abs(o[0]).max(1), 1e-12)
+    print("slide mode %s: max rel err of q after 400 steps %.2e, flags equal in %d/%d, mean x %.4f" % (name, err.max(), (a == o[3]).all(1).sum(), B, o[0][:, 0].mean()))
+    assert (fd.batch_get_status() == 0).all() and np.abs(o[0][:, 0]).mean() > 0.005
+    tol = 1e-9 if "vert" not in name else 1e-6
+    assert (err < tol).mean() >= (1.0 if "vert" not in name else 0.97) and (a == o[3]).all(1).mean() >= 0.97
+    fd.destroy()
+
+
 def test_breakable_float_joint(capi, oracle):
     """the breakable float joint of example/model/wall.ztk:51-95 ([EXT A-17]): a cantilever of three
     bricks whose middle joint gives way under gravity; 400 steps against the oracle."""

@@ -724,3 +724,48 @@ def test_breakable_float_joint(oracle):
     w2 = ch.World(chains=[brick_wall([200.0] * 3, [200.0] * 3)])
     o2 = oracle.OracleWorld(w2).batch_run_state(q, qd, u, nsteps=50)
     assert (o2[0] == q).all() and (o2[2] == 0).all()
+
+
+# ---- slide mode of collision cells (the "fake crawler" of rkfd_sim.c:386-440) -------------------------
+def slide_worlds():
+    def belt(stuff, vel):       # a conveyor: static box whose link origin lies far below it, belt axis y -> surface velocity +x
+        l = ch.Link(name="belt", jtype="fixed", stuff=stuff, org_p=np.array([0, 0, -100.0]), boxes=[((0, 0, 100 - 0.2), 50.0, 5.0, 0.4)])
+        l.slides = {0: (vel, (0.0, 1.0, 0.0))}
+        return ch.ChainModel("belt", [l])
+
+    def mbox(name, slide=None):
+        l = ch.Link(name="b", jtype="float", mass=0.5, stuff="body", inertia=np.eye(3) * 8.33e-4, shapes=[ch.box_verts(0.1, 0.1, 0.1)])
+        if slide:
+            l.slides = {0: slide}
+        return ch.ChainModel(name, [l])
+    el = [ch.ContactInfo("soft", "body", "elastic", E=1000.0, V=10.0, SF=0.5, KF=0.3)]
+    rg = [ch.ContactInfo("soft", "body", "rigid", K=1000.0, L=0.01, SF=0.5, KF=0.3)]
+    return {
+        "belt_registered_second_penalty": lambda: ch.World(chains=[mbox("box"), belt("soft", 0.5)], contact_info=el),
+        "belt_registered_first_penalty": lambda: ch.World(chains=[belt("soft", 0.5), mbox("box")], contact_info=el),
+        "crawler_box_on_plain_floor_penalty": lambda: ch.World(chains=[mbox("box", (0.3, (0.0, 1.0, 0.0))), ch.floor_soft()], contact_info=el),
+        "belt_mlcp": lambda: ch.World(chains=[mbox("box"), belt("soft", 0.5)], contact_info=rg, solver="MLCP"),
+        "belt_registered_first_vert": lambda: ch.World(chains=[belt("soft", 0.5), mbox("box")], contact_info=rg, solver="Vert"),
+    }
+
+
+def slide_states(w, B, seed=1):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((B, 6)); q[:, 2] = 0.05 + rng.uniform(0, 0.01, B); q[:, 3:6] = rng.uniform(-0.05, 0.05, (B, 3))
+    return q, rng.uniform(-0.2, 0.2, (B, 6)), np.zeros((B, w.nl))
+
+
+@pytest.mark.parametrize("name", list(slide_worlds()))
+def test_slide_mode_matches_oracle(oracle, name):
+    """Cells in slide mode: belt velocity in the relative contact velocity (rkFDLinkAddSlideVel, rkfd_util.c:26-40) and anchors of
+    sticking contacts riding on the belt (rkFDUpdateRefSlide, :218-237, with its choice of frame by the registration order of the
+    two cells) under the penalty, MLCP and Vert solvers; 400 steps against the oracle."""
+    w = slide_worlds()[name]()
+    B = 8
+    q, qd, u = slide_states(w, B)
+    hs = HostSim(w, B); hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(400)
+    hq = hs.get_state()[0]; a = hs.get_contact()[0]
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=400)
+    err = np.abs(hq - o[0]).max(1) / np.maximum(np.abs(o[0]).max(1), 1e-12)
+    assert (a == o[3]).all() and err.max() < (1e-9 if "vert" not in name else 1e-7), err
+    assert np.abs(o[0][:, 0]).mean() > 0.005        # the belt moved the box

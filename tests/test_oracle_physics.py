@@ -589,3 +589,27 @@ def test_rigid_moving_vs_moving_contact_conserves_momentum(oracle, solver):
         qq, vv, _ = e.get_state()
         assert np.abs(vv).max() < 1e-9
         assert abs((0.05 - qq[2]) - 2 * m * g / (4 * 1000.0)) < 1e-7 and abs(0.09 - (qq[8] - qq[2])) < 1e-7
+
+
+def test_slide_mode_conveyor_and_crawler(oracle):
+    """Oracle pin of the slide mode (rkfd_util.c:26-40, 218-237): (1) a box dropped on a conveyor (static box in slide mode, belt
+    speed 0.5 m/s, penalty contact) is dragged until it rides along at the belt speed and then STICKS (static friction: its
+    anchors ride on the belt); (2) a box whose own cell is in slide mode propels itself over a plain floor in the opposite
+    direction of its belt's surface velocity at the contact (a crawler), approaching the belt speed."""
+    from test_kernel_core_host import slide_worlds
+    W = slide_worlds()
+    e = oracle.OracleWorld(W["belt_registered_first_penalty"]()).env()
+    q = np.zeros(6); q[2] = 0.05
+    e.set_state(q, np.zeros(6)); e.update_init()
+    for _ in range(1500):
+        e.update()
+    qq, vv, _ = e.get_state()
+    act, typ = e.get_contact()[0], e.get_contact()[1]
+    # (a slow pitch rate remains: the anchors ride at exactly the belt speed, the bottom vertices a little slower)
+    assert abs(vv[0] - 0.5) < 2e-3 and np.abs(vv[[1, 2, 3, 5]]).max() < 1e-6 and abs(vv[4]) < 0.05 and act[:4].all() and (typ[:4] == 0).all()
+    e = oracle.OracleWorld(W["crawler_box_on_plain_floor_penalty"]()).env()
+    e.set_state(q, np.zeros(6)); e.update_init()
+    for _ in range(1500):
+        e.update()
+    qq, vv, _ = e.get_state()
+    assert abs(abs(vv[0]) - 0.3) < 5e-3 and qq[0] * vv[0] > 0
