@@ -306,7 +306,9 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
     m.ws_b = o;  o += n;
     m.ws_f = o;  o += n;
     m.ws_A = o;  o += n*n;
-    m.ws_du = o; o += n*nl;           /* per probe column: joint-space increments (scalar per link; multi-DoF joints use 6) */
+    m.ws_du = o; o += n*6*nl;         /* per probe column: joint-space increments, 6 per link (Core::probe indexes du0 + 6*link: with n*nl
+                                       * the columns >= n/6 overlapped the acceleration increments of other columns and were correct only
+                                       * in lockstep) */
     m.ws_da = o; o += n*6*nl;         /* per probe column: link acceleration increments */
     m.ws_qp = o;
     (void)nm;
