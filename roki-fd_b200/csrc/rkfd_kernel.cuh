@@ -53,7 +53,15 @@ struct DevCtx {
     }
   }
   /* scratch element k of this thread: shared-memory column [k*BLOCK + tid] (LDS/STS, conflict-free) */
+#ifdef RKFD_BOUNDS      /* debug build (compute-sanitizer is not available on the pool): the first out-of-range index is recorded
+                         * in the environment's status word (bit 30 set, bits 24-27 which accessor, bits 0-23 the index) */
+  int oob, bnd_ns, bnd_w1;
+  __device__ __forceinline__ int chk(int k, int n, int which){ if( (unsigned)k >= (unsigned)n ){ if( !oob ) oob = (1 << 30) | (which << 24) | (k & 0xffffff); return 0; } return k; }
+#endif
   __device__ __forceinline__ double &S(int k){
+#ifdef RKFD_BOUNDS
+    k = chk(k, bnd_ns, 1);
+#endif
     if( GSCR ) return st.scratch[(size_t)k*st.ld + e];
     return rkfd_smem[k*BLOCK + tid];
   }
@@ -77,7 +85,11 @@ struct DevCtx {
   /* level 1: once per evaluation, 2: per pass, 3: per link iteration */
   __device__ __forceinline__ void phase_sync(int level) const { if( level <= RKFD_SYNC_LEVEL ) __syncthreads(); }
   __device__ __forceinline__ double &W(int i){ return st.ws[(size_t)(e0 >> 5)*wsd + i]; }
-  __device__ __forceinline__ double &W1(int i){ return st.ws1[(size_t)i*st.ld + e]; }     /* element i of the selected environment */
+  __device__ __forceinline__ double &W1(int i){
+#ifdef RKFD_BOUNDS
+    i = chk(i, bnd_w1, 2);
+#endif
+    return st.ws1[(size_t)i*st.ld + e]; }     /* element i of the selected environment */
   /* per-env state in HBM: element k of the selected environment (global address space asserted: LDG/STG, not generic) */
   /* the element index k*ld + e in 32 bits (one IMAD + one IMAD.WIDE per access instead of a 64-bit multiply-add chain: the
    * address arithmetic of these accesses was 5 % of the executed instructions of the C3 step); the engine refuses batches whose
@@ -102,6 +114,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) rkfd_step_kernel(StateDev st, int
    * and the tensor-memory allocation below rely on; the padding environments hold a valid zero state */
   DevCtx<BLOCK,GSCR,RIGID,TM> ctx; ctx.st = st; ctx.e = ctx.e0 = e; ctx.cur = cur; ctx.tid = ctx.tid0 = threadIdx.x; ctx.wsd = c_model.ws_doubles;
   ctx.tbase = 0;
+#ifdef RKFD_BOUNDS
+  ctx.oob = 0; ctx.bnd_ns = c_model.nscratch; ctx.bnd_w1 = c_model.ws1_doubles > 0 ? c_model.ws1_doubles : 1;
+#endif
   constexpr unsigned TCOLS = Spec::TCOLS*((BLOCK + 127)/128);
   __shared__ unsigned tmem_addr;
   if( TM ){
@@ -119,6 +134,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) rkfd_step_kernel(StateDev st, int
   }
   Core<DevCtx<BLOCK,GSCR,RIGID,TM>, Spec> core(ctx);
   core.run(c_model, mode, nsteps);
+#ifdef RKFD_BOUNDS
+  if( ctx.oob ) st.status[ctx.e0] = ctx.oob;
+#endif
   if( TM ){
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
