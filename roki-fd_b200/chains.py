@@ -258,6 +258,16 @@ def world_from_flat(desc):
         h = desc["box.half[%d]" % b]
         chains.append(ChainModel("box%d" % b, [Link(name="box", jtype="fixed", stuff="B%d" % b, org_R=np.array(desc["box.R[%d]" % b]).reshape(3, 3),
                                                      org_p=np.array(desc["box.p[%d]" % b]), boxes=[((0.0, 0.0, 0.0), 2 * h[0], 2 * h[1], 2 * h[2])])]))
+    # slide mode of moving cells (rkFDShape3DSetSlide* before rkFDUpdateInit): back onto the links' cells
+    for p in range(npair):
+        sl = desc.get("pair.slide[%d]" % p)
+        if sl is None:
+            continue
+        if int(sl[1]) > 0:
+            raise NotImplementedError("world_from_flat: a static box in slide mode (its link frame is not part of the description)")
+        c = int(desc["pair[%d]" % p][0]); e = desc["slide[%d]" % (int(sl[0]) - 1)]
+        lk = cells[c][0]; first = int(desc["link.topo[%d]" % lk][5])
+        links[lk].slides[c - first] = (e[0], tuple(e[1:4]))
     ci, seen = [], set()
     for p in range(npair):
         v = desc["pair[%d]" % p]

@@ -573,6 +573,11 @@ extern "C" int rkFDB200DescribeModel(rkFD *fd, char *buf, int cap)
   for(int i=0;i<m.nbox;i++){ arr("box.R", i, m.box[i].R, 9); arr("box.p", i, m.box[i].p, 3); arr("box.half", i, m.box[i].half, 3); }
   for(int i=0;i<m.npair;i++){ const PairDev &p = m.pair[i]; const double v[10] = { (double)p.cell, (double)p.box, (double)p.sofs, (double)p.type, p.K, p.L, p.E, p.V, p.SF, p.KF }; arr("pair", i, v, 10); }
   for(int i=0;i<m.nvert;i++) arr("vert", i, m.vert + 3*i, 3);
+  /* slide mode: entries (speed, axis, frame of a static box's link) and, per pair that has one, (entry of the vertex's cell + 1, entry
+   * of the box + 1, the vertex's cell registered first) */
+  for(int i=0;i<m.nslide;i++){ const SlideDev &d = m.slide[i]; double v[16] = { d.vel, d.axis[0], d.axis[1], d.axis[2] };
+    for(int k=0;k<9;k++) v[4+k] = d.lR[k]; for(int k=0;k<3;k++) v[13+k] = d.lp[k]; arr("slide", i, v, 16); }
+  for(int i=0;i<m.npair;i++) if( m.pair[i].slinfo & 0xffff ){ const int si = m.pair[i].slinfo; const double v[3] = { (double)(si & 255), (double)((si >> 8) & 255), (double)((si >> 16) & 1) }; arr("pair.slide", i, v, 3); }
   if( fd->dis && fd->size > 0 ) arr("init.q", 0, fd->dis->buf, fd->size);      /* the registered initial displacements ([roki::chain::init]) */
   if( buf && cap > 0 ){ std::snprintf(buf, cap, "%s", s.c_str()); }
   return (int)s.size();

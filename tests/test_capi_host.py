@@ -159,7 +159,10 @@ REF_WORLDS = {   # the reference's example programs: model files, solver
     "arm2dof_on_floor": (["arm_2DoF.ztk", "floor.ztk"], "MLCP"),
     "arm_box_floor": (["arm_2DoF.ztk", "box.ztk", "floor.ztk"], "Volume"),     # example/chain/arm_box_test.c
     "mighty_on_floor": (["mighty.ztk", "floor.ztk"], "Volume"),                # BASELINE config C4's model
+    # the fake crawler (rkfd_sim.c:386-440): both tracks of crawler.ztk in slide mode, belt axis y, 0.3 m/s; over floor_hardsoft.ztk
+    "crawler_on_hardsoft": (["crawler.ztk", "floor_hardsoft.ztk"], "Volume"),
 }
+REF_SLIDES = {"crawler_on_hardsoft": [(0, 1, 0, 0.3, (0.0, 1.0, 0.0)), (0, 2, 0, 0.3, (0.0, 1.0, 0.0))]}     # (chain, link, shape, speed, axis)
 
 
 def reference_world_description(name):
@@ -167,8 +170,17 @@ def reference_world_description(name):
     files, solver = REF_WORLDS[name]
     fa = capi.RkFD()
     assert fa.contact_info_scan_file(os.path.join(d, "contactinfo.ztk"))
+    cells = []
     for f in files:
-        assert fa.chain_reg_file(os.path.join(d, f)) is not None, f
+        cells.append(fa.chain_reg_file(os.path.join(d, f)))
+        assert cells[-1] is not None, f
+    L = capi.lib()
+    L.rkLinkShape.restype = C.c_void_p; L.rkLinkShape.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    for fn, at in (("rkFDShape3DSetSlideMode", C.c_bool), ("rkFDShape3DSetSlideVel", C.c_double), ("rkFDShape3DSetSlideAxis", C.POINTER(C.c_double))):
+        getattr(L, fn).restype = C.c_void_p; getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, at]
+    for (c, link, k, vel, axis) in REF_SLIDES.get(name, []):       # the reference's own calls on a shape of the registered chain
+        sh = L.rkLinkShape(cells[c].chain_handle, link, k)
+        assert sh and L.rkFDShape3DSetSlideMode(fa.h, sh, True) and L.rkFDShape3DSetSlideVel(fa.h, sh, vel) and L.rkFDShape3DSetSlideAxis(fa.h, sh, (C.c_double * 3)(*axis))
     fa.set_solver(solver)
     desc = _flattened(fa)
     fa.destroy()

@@ -520,12 +520,33 @@ def flat_world(name, solver=None, soft=False):
 def flat_states(name, w, q0, B, seed=0):
     rng = np.random.default_rng(seed)
     q = np.tile(q0, (B, 1)); qd = rng.uniform(-0.05, 0.05, (B, w.nq)); u = np.zeros((B, w.nl))
-    if name.startswith("mighty"):          # the humanoid near its registered standing pose, soles on the floor
+    if name.startswith("crawler"):         # crawler.ztk on the SOFT half of floor_hardsoft.ztk (y < 0), tracks on the floor
+        q[:, 0:2] = np.array([0.0, -1.0]) + rng.uniform(-0.05, 0.05, (B, 2)); q[:, 2] = rng.uniform(-0.002, 0.004, B)    # (the body's frame: already holds z = 0.13)
+        q[:, 3:6] = rng.uniform(-0.02, 0.02, (B, 3))
+    elif name.startswith("mighty"):        # the humanoid near its registered standing pose, soles on the floor
         q[:, 6:] += 0.002 * rng.uniform(-1, 1, (B, w.nq - 6))
     else:                                  # arm_box_test.c: arm swung down towards the floor, box dropped next to it
         q[:, :2] = rng.uniform(-0.3, 0.3, (B, 2)) + np.array([np.pi / 2, 0.0]); qd[:, :2] = rng.uniform(-2, 2, (B, 2))
         q[:, 2:5] = np.array([0.0, 0.6, 0.06]) + rng.uniform(-0.02, 0.02, (B, 3)); q[:, 5:8] = rng.uniform(-0.3, 0.3, (B, 3))
     return q, qd, u
+
+
+def test_reference_crawler_drives_in_slide_mode(oracle):
+    """The reference's example/model/crawler.ztk (float body + two fixed track links, 20-vertex polyhedra) on floor_hardsoft.ztk with
+    both tracks in slide mode (set through rkFDShape3DSetSlideMode/-Vel/-Axis when tests/golden/flat_crawler_on_hardsoft.txt was
+    written): the kernel core against the oracle over 300 steps, and the crawler drives forward (+x: the belts run backwards under
+    the tracks) at about the belt speed."""
+    w, q0 = flat_world("crawler_on_hardsoft")
+    assert sum(len(l.slides) for c in w.chains for l in c.links) == 2
+    B = 6
+    q, qd, u = flat_states("crawler_on_hardsoft", w, q0, B)
+    qd[:] = 0.0
+    hs = HostSim(w, B); hs.set_state(q, qd, u); hs.eval(ref=True); hs.step(300)
+    hq, hqd, _ = hs.get_state()
+    o = oracle.OracleWorld(w).batch_run_state(q, qd, u, nsteps=300)
+    err = np.abs(hq - o[0]).max(1) / np.abs(o[0]).max(1)
+    assert err.max() < 1e-9 and (hs.get_status() == 0).all(), err
+    assert (o[1][:, 0] > 0.2).all() and (o[0][:, 0] - q[:, 0] > 0.03).all(), (o[1][:, 0], o[0][:, 0] - q[:, 0])
 
 
 @pytest.mark.parametrize("name,soft", [("mighty_on_floor", True), ("arm_box_floor", True), ("mighty_on_floor", False)])
