@@ -1022,10 +1022,12 @@ struct Core {
   /* sin/cos of a revolute joint carried from the stage angle qold to qnew = qold + d: angle addition with the
    * Taylor series of (sin d, cos d) (|d| <= 1/16: truncation below 1e-18), a full sincos otherwise.  A step
    * computes sincos once per joint (first stage) instead of five times; four chained rotations add a few ulp. */
-  RKFD_HD void rot_sincos(int sc, double s0, double c0, double qold, double qnew){
+  RKFD_HD void rot_sincos(const ModelDev &m, int sc, double s0, double c0, double qold, double qnew){
     const double d = qnew - qold, d2 = d*d;
-    const double sd = d*fma(d2, fma(d2, fma(d2, fma(d2, 1.0/362880.0, -1.0/5040.0), 1.0/120.0), -1.0/6.0), 1.0);
-    const double cd = fma(d2, fma(d2, fma(d2, fma(d2, 1.0/40320.0, -1.0/720.0), 1.0/24.0), -0.5), 1.0);
+    /* the coefficients 1/9!, -1/7!, 1/5!, -1/3!, 1/8!, -1/6! come from the model table (same values: operands of the multiply-adds
+     * instead of two moves each) */
+    const double sd = d*fma(d2, fma(d2, fma(d2, fma(d2, m.tay[0], m.tay[1]), m.tay[2]), m.tay[3]), 1.0);
+    const double cd = fma(d2, fma(d2, fma(d2, fma(d2, m.tay[4], m.tay[5]), 1.0/24.0), -0.5), 1.0);
     double sn = fma(s0, cd, c0*sd), co = fma(c0, cd, -(s0*sd));
     if( !(fabs(d) <= 0.0625) ) sincos(qnew, &sn, &co);
     Qw(sc, sn); Qw(sc+1, co);
@@ -1108,7 +1110,7 @@ struct Core {
           if( JT<Kt>(i,L) == J_REVOL ){
             const double qold = T(qs);
             const double qnew = rk_lin_pf(k, stage, qs,  pq,  c.st.q[c.cur^1],  j, vel, pfq[0], pfq[2]);
-            rot_sincos(Spec::sc(i,L), x.s, x.c, qold, qnew);
+            rot_sincos(m, Spec::sc(i,L), x.s, x.c, qold, qnew);
           } else rk_lin_pf(k, stage, qs,  pq,  c.st.q[c.cur^1],  j, vel, pfq[0], pfq[2]);
           rk_lin_pf(k, stage, qds, pqd, c.st.qd[c.cur^1], j, acc, pfq[1], pfq[3]);
         }

@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) rkfd_step_kernel(StateDev st, int
   const int e = e_;
   /* the engine pads the environment count to whole blocks (ld): no thread exits early, which the block barriers
    * and the tensor-memory allocation below rely on; the padding environments hold a valid zero state */
-  DevCtx<BLOCK,GSCR,RIGID,TM> ctx; ctx.st = st; ctx.e = ctx.e0 = e; ctx.cur = cur; ctx.tid = ctx.tid0 = threadIdx.x; ctx.wsd = c_model.ws_doubles;
+  int tid_ = threadIdx.x;
+  asm volatile("" : "+r"(tid_));      /* opaque, like e: the scratch-column index is not re-read from the special register at every access */
+  DevCtx<BLOCK,GSCR,RIGID,TM> ctx; ctx.st = st; ctx.e = ctx.e0 = e; ctx.cur = cur; ctx.tid = ctx.tid0 = tid_; ctx.wsd = c_model.ws_doubles;
   ctx.tbase = 0;
 #ifdef RKFD_BOUNDS
   ctx.oob = 0; ctx.bnd_ns = c_model.nscratch; ctx.bnd_w1 = c_model.ws1_doubles > 0 ? c_model.ws1_doubles : 1;

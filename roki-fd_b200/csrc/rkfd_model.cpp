@@ -75,6 +75,7 @@ bool build_model(const WorldHost &w, ModelDev &m, std::string &err)
   m.dt = w.dt; m.inv_dt = 1.0/w.dt; m.friction_weight = w.friction_weight; m.pyramid = w.pyramid; m.max_iter = w.max_iter; m.solver = w.solver; m.integrator = w.integrator;
   m.rk = rk_coef(w.dt, w.integrator);
   if( w.pyramid > MAX_PYRAMID || w.pyramid < 1 ){ err = "pyramid order out of range"; return false; }
+  m.tay[0] = 1.0/362880.0; m.tay[1] = -1.0/5040.0; m.tay[2] = 1.0/120.0; m.tay[3] = -1.0/6.0; m.tay[4] = 1.0/40320.0; m.tay[5] = -1.0/720.0;
   { /* rkFDCrateSinCosTable (reference rkfd_util.c:199-214) with the Vert offset -pi/pyramid (rkfd_vert.c:369); the Volume
      * solver's table has no offset (rkfd_volume.c:1000) */
     const double off = w.solver == S_VOLUME ? 0.0 : -M_PI / w.pyramid, dth = 2.0*M_PI / w.pyramid; double th = 0.0;

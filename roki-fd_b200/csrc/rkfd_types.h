@@ -117,6 +117,7 @@ struct ModelDev {
   double dt, friction_weight;
   double inv_dt;       /* 1/dt */
   double sc_sin[MAX_PYRAMID], sc_cos[MAX_PYRAMID];
+  double tay[6];       /* Taylor coefficients of Core::rot_sincos as constant-bank operands (a 64-bit literal costs two moves per use) */
   LinkDev link[MAX_LINKS];
   CellDev cell[MAX_CELLS];
   BoxDev box[MAX_BOXES];
