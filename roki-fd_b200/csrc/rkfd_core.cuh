@@ -341,6 +341,7 @@ struct Core {
   unsigned long long cfl;       /* contact flags, the word `cw` of them: bit 2f active, bit 2f+1 kinetic */
   int cw;
   int bad;
+  unsigned wk = 0;              /* work class of the last rigid solve (StateDev::work) */
   int rk0;                      /* first slot of the integrator stage state (QS, QDS, PQ, PQD) */
 
   RKFD_HD explicit Core(Ctx &ctx) : c(ctx), piv(0), cfl(0), cw(0), bad(0), rk0(0) {}
@@ -1772,6 +1773,7 @@ struct Core {
         nhist++;
       } else { bad |= 2; break; }
     }
+    wk = 1u + 12u*(unsigned)((N < 5 ? N : 5) - 1) + (unsigned)(nhist < 11 ? nhist : 11);      /* contacts x iterations: the re-sort key */
     /* f = x / dt ; forces, wrench, friction state from the final active set (rkfd_vert.c:282, 286-324) */
     unsigned long long nfl = fl;
     for(int g=0;g<ng;g++){
@@ -2223,7 +2225,8 @@ struct Core {
     return any;
   }
   RKFD_HD void load_flags(){ piv = c.st.piv_type[c.e]; cw = 0; cfl = c.st.cflags[c.e]; }
-  RKFD_HD void store_flags(){ c.st.piv_type[c.e] = piv; c.st.cflags[(size_t)(Spec::NL != 0 ? 0 : cw)*c.st.ld + c.e] = cfl; if( bad ) c.st.status[c.e] |= bad; }
+  RKFD_HD void store_flags(){ c.st.piv_type[c.e] = piv; c.st.cflags[(size_t)(Spec::NL != 0 ? 0 : cw)*c.st.ld + c.e] = cfl; if( bad ) c.st.status[c.e] |= bad;
+    if( Ctx::RIGID ){ if( c.st.work ) c.st.work[c.e] = (unsigned char)wk; } }
   /* committed state (buffer `cur`) -> stage state */
   RKFD_HD void load_stage_state(const ModelDev &m){
     const int NQc = Spec::nq(m);
@@ -2248,6 +2251,7 @@ struct Core {
        * contacts skips the work, not the barriers, so that the warps of an SM sit in the same piece of this very large
        * kernel (ncu: 10 instruction-fetch stall cycles per issued instruction when every warp goes its own way).  The
        * Volume solver has barriers inside its solve as well (rkfd_volume.cuh): every warp enters it. */
+      wk = 0;
       const unsigned act = c.ballot( rigid_active(m) );
       const bool volume = Spec::NL == 0 && m.solver == S_VOLUME;
       const bool blk = c.block_or(act != 0);

@@ -80,7 +80,7 @@ static void xp_gather(const double *src, double *dst, int B, int n, int ld, cuda
  * depend on the slot (bit-identical).  perm[slot] = environment, inv[environment] = slot; the host-side API maps through
  * them in the transposing copies. */
 constexpr int SORT_BINS = 64;
-__global__ void __launch_bounds__(256) rkfd_sort_key_kernel(const unsigned long long * __restrict__ cflags, int nfw, int ld, int B, unsigned char *key, int *bins)
+__global__ void __launch_bounds__(256) rkfd_sort_key_kernel(const unsigned long long * __restrict__ cflags, const unsigned char * __restrict__ work, int nfw, int ld, int B, unsigned char *key, int *bins)
 {
   __shared__ int h[SORT_BINS];
   if( threadIdx.x < SORT_BINS ) h[threadIdx.x] = 0;
@@ -89,6 +89,9 @@ __global__ void __launch_bounds__(256) rkfd_sort_key_kernel(const unsigned long 
   if( sl < B ){
     int na = 0;
     for(int w=0;w<nfw;w++) na += __popcll(cflags[(size_t)w*ld + sl] & 0x5555555555555555ull);
+    /* worlds under the Vert / Volume solver: the work class of the environment's last rigid solve (contacts or pairs x
+     * active-set iterations, written by the step kernel) - the lanes of a warp then leave the active-set loop together */
+    if( work && work[sl] ) na = work[sl];
     if( na > SORT_BINS-1 ) na = SORT_BINS-1;
     key[sl] = (unsigned char)na; atomicAdd(&h[na], 1);
   }
@@ -281,6 +284,7 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
     st.cref = dalloc<double>(*s, (size_t)3*ns*s->ld);
     st.cf = dalloc<double>(*s, (size_t)3*ns*s->ld);
     st.status = dalloc<int>(*s, s->ld);
+    st.work = ( std::getenv("RKFD_NO_WORK_SORT") == nullptr && model.has_rigid && model.solver != S_MLCP ) ? dalloc<unsigned char>(*s, s->ld) : nullptr;
     /* per-warp workspace of the dense warp-cooperative contact solve; the single-link paths use ws1 only */
     st.ws = ( model.ws_doubles > 0 && model.rigid_link < 0 ) ? dalloc<double>(*s, (size_t)(s->ld/32)*model.ws_doubles) : nullptr;
     st.ws1 = model.ws1_doubles > 0 ? dalloc<double>(*s, (size_t)model.ws1_doubles*s->ld) : nullptr;
@@ -404,7 +408,7 @@ void Engine::resort(Shard &s)
   }
   const int grid = (s.ld + 255)/256;
   CK(cudaMemsetAsync(s.bins, 0, SORT_BINS*sizeof(int), s.stream));
-  rkfd_sort_key_kernel<<<grid, 256, 0, s.stream>>>(s.st.cflags, nfw, s.ld, s.B, s.key, s.bins);
+  rkfd_sort_key_kernel<<<grid, 256, 0, s.stream>>>(s.st.cflags, s.st.work, nfw, s.ld, s.B, s.key, s.bins);
   rkfd_sort_offsets_kernel<<<1, 32, 0, s.stream>>>(s.bins);
   rkfd_sort_assign_kernel<<<grid, 256, 0, s.stream>>>(s.key, s.bins, s.newpos, s.B);
   CK(cudaGetLastError());

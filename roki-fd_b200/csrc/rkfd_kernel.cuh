@@ -78,6 +78,14 @@ struct DevCtx {
   __device__ __forceinline__ void select(int src){ tid = (tid0 & ~31) | src; e = (e0 & ~31) | src; }
   __device__ __forceinline__ void unselect(){ tid = tid0; e = e0; }
   __device__ __forceinline__ void gsync() const { __syncwarp(); }
+  /* Reconvergence that the compiler cannot drop: at a point it takes for convergent (the head of a loop with a warp-uniform
+   * trip count) it deletes __syncwarp() and issues the vote for the lanes that happen to be there - lanes that skipped a
+   * divergent body with calls in it then run ahead, through the block barriers as well (an aligned barrier counts a part of
+   * a warp as the warp), and overwrite the uniform registers of the lanes still in the body (seen on the B200 as "warp
+   * out-of-range address").  With a mask the compiler cannot evaluate (all ones for any valid launch) the warp barrier stays. */
+  __device__ __forceinline__ unsigned hmask() const { return ~(unsigned)(st.B >> 31); }
+  __device__ __forceinline__ void hsync() const { __syncwarp(hmask()); }
+  __device__ __forceinline__ bool hany(bool p) const { const unsigned fm = hmask(); __syncwarp(fm); return __any_sync(fm, p); }
   __device__ __forceinline__ bool block_or(bool p) const { return __syncthreads_or(p) != 0; }     /* block-uniform call sites only */
 #ifndef RKFD_SYNC_LEVEL
 #define RKFD_SYNC_LEVEL 2

@@ -144,6 +144,8 @@ struct StateDev {
   double *ws;             /* rigid-contact workspace, ws_doubles per warp (ld/32 warps) */
   double *ws1;            /* [ws1_doubles][ld] per-environment workspace of the single-link MLCP path */
   int *status;            /* [ld] per-env status word (bit0: non-finite acceleration) */
+  unsigned char *work;    /* [ld] or null: work class of the environment's last rigid solve (Vert / Volume: pairs or contacts and
+                           * active-set iterations), 0 = no solve; the engine's re-sort groups equal classes into warps */
 };
 
 }  // namespace rkfd

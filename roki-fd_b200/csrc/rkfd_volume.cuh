@@ -422,6 +422,7 @@ RKFD_VOL_U
       if( nhist < QP_HIST ){ hist_idx[nhist] = idx; hist_obj[nhist] = objv; nhist++; }
       if( iter == QP_MAXIT-1 ) bad |= 2;
     }
+    wk = (unsigned)nhist;
     idx_out = idx;
   }
 
@@ -570,7 +571,11 @@ RKFD_VOL_U
      * empty loops), with a block barrier between phases: the warps of an SM then execute the same few KB of code at any
      * time instead of eight different parts of the 350 KB solver (instruction-fetch stalls dominated the profile). */
     VolPair vp[VOL_P]; int P = 0;
-    /* ---- contact volumes (rkFDSolverColChk_Volume, [EXT A-15]) */
+    /* ---- contact volumes (rkFDSolverColChk_Volume, [EXT A-15]).  First the pairs of this environment that touch (16 bits
+     * each: pair, first vertex inside), then their volumes candidate by candidate with the lanes of the warp in lockstep: a
+     * lane whose left sole touches and a lane whose right sole touches clip their cells together, not one after the other. */
+    constexpr int VOL_CAND = 4;
+    unsigned long long cand = 0; int ncand = 0;
     for(int pi=0;pi<m.npair;pi++){
       const PairDev &pr = m.pair[pi]; if( pr.type != C_RIGID ) continue;
       const CellDev &cl = m.cell[pr.cell];
@@ -588,7 +593,15 @@ RKFD_VOL_U
       if( k0 >= 0 ) printf("VOLDBG pair %d k0 %d volbox %d P %d\n", pi, k0, pr.volbox, P);
 #endif
       if( k0 < 0 ) continue;
-      if( P >= VOL_P ){ bad |= 4; break; }
+      if( ncand < VOL_CAND ){ cand |= (unsigned long long)((pi << 4) | k0) << (16*ncand); ncand++; } else bad |= 4;
+    }
+#pragma unroll 1
+    for(int ci=0; ci<VOL_CAND; ci++){
+      if( !c.hany(ci < ncand) ) break;
+      if( ci < ncand && P >= VOL_P ){ bad |= 4; ncand = 0; }
+      if( ci < ncand ){
+      const int pi = (int)(cand >> (16*ci) & 0xffffull) >> 4, k0 = (int)(cand >> (16*ci) & 0xfull);
+      const PairDev &pr = m.pair[pi]; const CellDev &cl = m.cell[pr.cell];
       VolPair &v = vp[P];
       const LinkDev &L = m.link[cl.link]; const BoxDev &bx = m.box[pr.box];
       v.pair = pi; v.link = cl.link; v.fsl = Spec::frame_slot(cl.link, L); v.wsl = Spec::wext_slot(cl.link, L); v.npl = 0; v.sofs = pr.sofs; v.fofs = pr.fofs;
@@ -610,14 +623,14 @@ RKFD_VOL_U
 #ifdef RKFD_VOL_DEBUG
       printf("VOLDBG pair %d empty %d npl %d\n", pi, (int)empty, v.npl);
 #endif
-      if( empty ) continue;
       /* rkCDPlaneListQuickSort with __rk_fd_plane_cmp (:376-395): ascending angle key, ties keep their order */
-      { double th[VOL_PL];
+      if( !empty ){ double th[VOL_PL];
         for(int i=0;i<v.npl;i++){ const V3 t = cross(v.a1, v.pln[i]); const double y = norm(t); th[i] = atan2(dot(t, v.norm) > 0 ? -y : y, dot(v.a1, v.pln[i])); }
         for(int i=1;i<v.npl;i++){ const V3 tv = v.plv[i], tn = v.pln[i]; const double a = th[i]; int j = i-1;
           for(;j>=0 && !(fabs(th[j]-a) < ZTOL) && th[j] > a;j--){ v.plv[j+1] = v.plv[j]; v.pln[j+1] = v.pln[j]; th[j+1] = th[j]; }
-          v.plv[j+1] = tv; v.pln[j+1] = tn; th[j+1] = a; } }
-      P++;
+          v.plv[j+1] = tv; v.pln[j+1] = tn; th[j+1] = a; }
+        P++; }
+      }
     }
     c.phase_sync(1);
     const int n = 6*P;
@@ -697,7 +710,7 @@ RKFD_VOL_U
       for(int r=0;r<mrows;r++) nf[VOL_N*r+i] = 0.0; }
     unsigned idx = 0; VOL_STAT(6, 1);
     c.phase_sync(1);
-    if( P > 0 ) vol_asm(mrows, Qm, cv, nf, x, idx);
+    if( P > 0 ){ vol_asm(mrows, Qm, cv, nf, x, idx); wk = 1u + ((idx ^ (wk << 20) ^ ((unsigned)P << 27))*2654435761u >> 26)%63u; }      /* final active set, iterations, pairs (hashed): the re-sort key */
 #ifdef RKFD_VOL_DEBUG
     for(int k=0;k<P;k++){ printf("VOLDBG pair %d npl %d center %.6e %.6e %.6e x", vp[k].pair, vp[k].npl, vp[k].center.x, vp[k].center.y, vp[k].center.z); for(int i=0;i<6;i++) printf(" %.6e", x[6*k+i]); printf(" idx %x mrows %d bad %d c6", idx, mrows, bad); for(int i=0;i<6;i++) printf(" %.4e", vp[k].c6[i]); printf("\n"); }
 #endif
@@ -710,9 +723,17 @@ RKFD_VOL_U
         const V3 f = v3(v.w[0],v.w[1],v.w[2]);
         if( ( vtiny(f.x) && vtiny(f.y) && vtiny(f.z) ) || dot(f, v.norm) < ZTOL ) for(int i=0;i<6;i++) v.w[i] = 0.0;
         off += 6; } }
-    for(int k=0;k<P;k++){
-      VolPair &v = vp[k]; const int np = v.npl;
-      V3 wf = v3(v.w[0],v.w[1],v.w[2]), wt = v3(v.w[3],v.w[4],v.w[5]);
+    /* The pairs in lockstep (trip count VOL_P for every lane) with the lanes of a warp brought together before each of the
+     * two linear programs: reached from the nested decisions below lane by lane they ran with 3 of 32 lanes (ncu). */
+#pragma unroll 1
+    for(int k=0;k<VOL_P;k++){
+      const bool in = k < P;
+      VolPair &v = vp[in ? k : 0]; const int np = in ? v.npl : 0;
+      V3 wf = v3(0,0,0), wt = v3(0,0,0);
+      double wv[6] = {0,0,0,0,0,0};
+      int kinetic = 0; bool setforce = false, try_static = false, mod_w = false;
+      if( in ){
+      wf = v3(v.w[0],v.w[1],v.w[2]); wt = v3(v.w[3],v.w[4],v.w[5]);
       /* ---- _rkFDSolverModifyNormalForceCenter (:580-631) */
       { const double fn = dot(v.norm, wf);
         if( !(fn < ZTOL) && np >= 3 ){
@@ -742,12 +763,12 @@ RKFD_VOL_U
         } }
       /* ---- _rkFDSolverModifyWrench (:869-916) */
       if( np > 0 && !vtiny(dot(wf, v.norm)) ){
-        double wv[6] = { dot(wf, v.norm), dot(wf, v.a1), dot(wf, v.a2), dot(wt, v.norm), dot(wt, v.a1), dot(wt, v.a2) };
+        mod_w = true;
+        wv[0] = dot(wf, v.norm); wv[1] = dot(wf, v.a1); wv[2] = dot(wf, v.a2); wv[3] = dot(wt, v.norm); wv[4] = dot(wt, v.a1); wv[5] = dot(wt, v.a2);
         const double fn = wv[0], fs = sqrt(wv[1]*wv[1] + wv[2]*wv[2]);
         double tl = 0;
         for(int i=0;i<np;i++){ v.r[i][0] = dot(v.plv[i], v.a1); v.r[i][1] = dot(v.plv[i], v.a2);
           const double rl = sqrt(v.r[i][0]*v.r[i][0] + v.r[i][1]*v.r[i][1]); if( tl < rl ) tl = rl; }
-        int kinetic = 0; bool setforce = false;
         if( vtiny(tl) ){
           wv[3] = wv[4] = wv[5] = 0;
           if( !vtiny(fs) && fs > v.SF*fn ){
@@ -758,11 +779,16 @@ RKFD_VOL_U
           setforce = true;
         } else if( ( !vtiny(fs) && fs > v.SF*fn ) || fabs(wv[3]) > tl*wv[0] ){
           kinetic = 2;
-        } else {
-          /* static friction: the wrench inside the friction pyramids at the polygon corners? (:643-688) */
-          const double mb[6] = { wv[0], wv[4], wv[5], wv[1], wv[2], wv[3] };
-          if( !vol_static_feasible(m, v, np, mb) ) kinetic = 2;
-        }
+        } else try_static = true;
+      } }
+      c.hsync();
+      if( try_static ){
+        /* static friction: the wrench inside the friction pyramids at the polygon corners? (:643-688) */
+        const double mb[6] = { wv[0], wv[4], wv[5], wv[1], wv[2], wv[3] };
+        if( !vol_static_feasible(m, v, np, mb) ) kinetic = 2;
+      }
+      c.hsync();
+      if( mod_w ){
         if( kinetic == 2 ){
           /* kinetic friction: normal force redistributed over the polygon corners by an LP (:733-843) */
           double ma[3*VOL_LPN], mb[3], mc[VOL_PL], mf[VOL_PL], wn[3];
@@ -788,7 +814,7 @@ RKFD_VOL_U
         if( setforce ){ wf = wv[0]*v.norm + wv[1]*v.a1 + wv[2]*v.a2; wt = wv[3]*v.norm + wv[4]*v.a1 + wv[5]*v.a2; }
       }
       /* ---- _rkFDSolverPushWrench (:919-936) */
-      { const M3 Rw = ldm(v.fsl); const V3 pos = tmul(Rw, v.center - ld3(v.fsl+9));
+      if( in ){ const M3 Rw = ldm(v.fsl); const V3 pos = tmul(Rw, v.center - ld3(v.fsl+9));
         const V3 fl_ = tmul(Rw, wf), tl_ = tmul(Rw, wt) + cross(pos, fl_);
         c.S(v.wsl) += fl_.x; c.S(v.wsl+1) += fl_.y; c.S(v.wsl+2) += fl_.z;
         c.S(v.wsl+3) += tl_.x; c.S(v.wsl+4) += tl_.y; c.S(v.wsl+5) += tl_.z;

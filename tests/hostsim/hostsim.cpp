@@ -39,6 +39,8 @@ struct HostCtx {
   void select(int){}
   void unselect(){}
   void gsync(){}
+  void hsync(){}
+  bool hany(bool p) const { return p; }
   bool block_or(bool p) const { return p; }
   void phase_sync(int){}
   double &W(int i){ return wsp[i]; }
