@@ -79,7 +79,7 @@ static void xp_gather(const double *src, double *dst, int B, int n, int ld, cuda
  * barriers, and the rigid-contact solvers find their environments packed into few warps.  Results per environment do not
  * depend on the slot (bit-identical).  perm[slot] = environment, inv[environment] = slot; the host-side API maps through
  * them in the transposing copies. */
-constexpr int SORT_BINS = 64;
+constexpr int SORT_BINS = 256;     /* keys are bytes; the sort kernels run 256 threads per block */
 __global__ void __launch_bounds__(256) rkfd_sort_key_kernel(const unsigned long long * __restrict__ cflags, const unsigned char * __restrict__ work, int nfw, int ld, int B, unsigned char *key, int *bins)
 {
   __shared__ int h[SORT_BINS];
@@ -258,6 +258,10 @@ Engine::Engine(const ModelDev &model, int B, const std::vector<int> &devices) : 
    * Measured on one B200 over 256 settled steps, sorts included (tools/exp_resort.py): C3 0.538 ms per step without, 0.484 /
    * 0.481 / 0.489 / 0.503 ms at 8 / 16 / 32 / 64; C5 MLCP 1.88 -> 1.42, C5 Vert 6.97 -> 5.09 at 16 */
   resort_interval_ = model.npair > 0 ? 16 : 0;
+  /* worlds whose step is dominated by a data-dependent rigid solve re-sort more often (the sort costs ~0.1-0.2 ms): under the
+   * Volume solver every step (C4, 131,072 envs: 30.3 ms per step at 16, 22.6 at 4, 20.5 at 2, 18.8 at 1), under the Vert QP
+   * every 4 (C5: 4.39 -> 4.32 ms) */
+  if( model.npair > 0 && model.has_rigid ) resort_interval_ = model.solver == S_VOLUME ? 1 : ( model.solver == S_VERT ? 4 : 16 );
   if( const char *rs = std::getenv("RKFD_RESORT") ) resort_interval_ = std::atoi(rs);
   if( device_count() <= 0 ) throw std::runtime_error("rokifd_b200: no CUDA device (there is no CPU fallback)");
   std::vector<int> devs = devices;

@@ -710,7 +710,8 @@ RKFD_VOL_U
       for(int r=0;r<mrows;r++) nf[VOL_N*r+i] = 0.0; }
     unsigned idx = 0; VOL_STAT(6, 1);
     c.phase_sync(1);
-    if( P > 0 ){ vol_asm(mrows, Qm, cv, nf, x, idx); wk = 1u + ((idx ^ (wk << 20) ^ ((unsigned)P << 27))*2654435761u >> 26)%63u; }      /* final active set, iterations, pairs (hashed): the re-sort key */
+    unsigned wkey = 0;      /* the re-sort key: final active set, iterations, pairs, friction paths of the pairs (hashed) */
+    if( P > 0 ){ vol_asm(mrows, Qm, cv, nf, x, idx); wkey = idx ^ (wk << 20) ^ ((unsigned)P << 27); }
 #ifdef RKFD_VOL_DEBUG
     for(int k=0;k<P;k++){ printf("VOLDBG pair %d npl %d center %.6e %.6e %.6e x", vp[k].pair, vp[k].npl, vp[k].center.x, vp[k].center.y, vp[k].center.z); for(int i=0;i<6;i++) printf(" %.6e", x[6*k+i]); printf(" idx %x mrows %d bad %d c6", idx, mrows, bad); for(int i=0;i<6;i++) printf(" %.4e", vp[k].c6[i]); printf("\n"); }
 #endif
@@ -781,6 +782,7 @@ RKFD_VOL_U
           kinetic = 2;
         } else try_static = true;
       } }
+      wkey ^= ( try_static ? 1u : ( kinetic == 2 ? 2u : 0u ) ) << (29 + 2*(k & 1));
       c.hsync();
       if( try_static ){
         /* static friction: the wrench inside the friction pyramids at the polygon corners? (:643-688) */
@@ -825,5 +827,6 @@ RKFD_VOL_U
           c.gst(c.st.cf,3*s+6,v.center.x); c.gst(c.st.cf,3*s+7,v.center.y); c.gst(c.st.cf,3*s+8,v.center.z);
         } }
     }
+    wk = P > 0 ? 1u + (wkey*2654435761u >> 24)%255u : 0u;
     c.phase_sync(1);
   }
