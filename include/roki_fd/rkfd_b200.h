@@ -321,8 +321,10 @@ __ROKI_FD_EXPORT int rkFDBatchGetPivot(rkFD *fd, int *type, double *prev_trq);
 __ROKI_FD_EXPORT int rkFDBatchSetPivot(rkFD *fd, const int *type, const double *prev_trq);
 __ROKI_FD_EXPORT int rkFDBatchGetStatus(rkFD *fd, int *status);                 /* per env, bit0: non-finite acceleration */
 /* Environment re-sort.  The kernels address environments by slot (thread index) and environments never interact, so the
- * engine re-orders the slots by the number of active contact vertices every `steps` steps (default 16 in worlds with
- * contact pairs, RKFD_RESORT=<steps> overrides): warps then hold environments with the same amount of contact work.
+ * engine re-orders the slots by the number of active contact vertices - under the Vert / Volume solvers by the work class of
+ * the environment's last rigid solve - every `steps` steps (default in worlds with contact pairs: 16; rigid pairs under the
+ * Vert solver 4, under the Volume solver 1; RKFD_RESORT=<steps> overrides): warps then hold environments with the same
+ * amount of contact work.
  * Results per environment do not depend on it and every host-side call maps through the order; only callers of
  * rkFDBatchDevicePtr see slots: they read the order with rkFDBatchSlotMap (perm[slot] = environment of that shard, B
  * entries) or switch the re-sort off (steps = 0: slot = environment). */
