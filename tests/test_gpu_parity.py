@@ -722,27 +722,33 @@ def test_reference_model_files(capi, oracle, name, soft, solver):
     fd.destroy()
 
 
-@pytest.mark.parametrize("name", ["c3", "c5_mlcp", "arm_box_floor"])
+@pytest.mark.parametrize("name", ["c3", "c5_mlcp", "arm_box_floor", "c5_vert", "c4_volume"])
 def test_environment_resort_is_invisible(capi, name):
-    """The engine re-orders its slots by contact count while stepping (rkFDBatchSetResortInterval): every host-side result -
-    state, accelerations, contact flags / anchors / forces, friction pivots, status - is bit-identical to a run without it,
-    also when state and motor inputs are written between the sorts."""
+    """The engine re-orders its slots by contact count - under the Vert / Volume solvers by the work class the step kernel leaves
+    per environment (StateDev::work) - while stepping (rkFDBatchSetResortInterval): every host-side result - state, accelerations,
+    contact flags / anchors / forces, friction pivots, status - is bit-identical to a run without it, also when state and motor
+    inputs are written between the sorts.  The Volume world sorts every step (its default), the Vert world every 4."""
+    intervals = (0, 7)
     if name == "arm_box_floor":
         from test_kernel_core_host import flat_world, flat_states
         w, q0 = flat_world(name, soft=True)
         B = 3000
         q, qd, u = flat_states(name, w, q0, B)
+    elif name == "c4_volume":
+        w = ch.world_c4_volume(); B = 6000; intervals = (0, 1)
+        q, qd, u = ch.sample_c4_standing(w, B, seed=5)
     else:
-        w = ch.world_c3(base_z=0.3) if name == "c3" else ch.world_c5(base_z=0.3, solver="MLCP")
+        w = ch.world_c3(base_z=0.3) if name == "c3" else ch.world_c5(base_z=0.3, solver="MLCP" if name == "c5_mlcp" else "Vert")
         B = 20000
+        if name == "c5_vert": intervals = (0, 4)
         q, qd, u = ch.sample_state(w, B, seed=11)
     out = []
-    for interval in (0, 7):
+    for interval in intervals:
         fd, _ = capi.create_world(w, B=B)
         fd.batch_set_resort_interval(interval)
         fd.batch_set_state(q, qd); fd.batch_set_motor_input(u); fd.update_init()
         for seg in range(6):
-            for _ in range(20):
+            for _ in range(20 if name != "c4_volume" else 6):
                 fd.update()
             if seg == 2:       # inputs written mid-run go to the right environments
                 u2 = u.copy(); u2[::3] *= -1.0
