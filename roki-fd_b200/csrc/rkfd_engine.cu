@@ -440,7 +440,7 @@ void Engine::step(int nsteps)
   if( nsteps <= 0 ) return;
   int prev = 0; CK(cudaGetDevice(&prev));
   for(Shard *s : shards_){
-    if( resort_interval_ > 0 && s->steps_since_sort >= resort_interval_ ){ CK(cudaSetDevice(s->dev)); resort(*s); }
+    if( resort_interval_ > 0 && s->B > 32 && s->steps_since_sort >= resort_interval_ ){      /* one warp: nothing to group */ CK(cudaSetDevice(s->dev)); resort(*s); }
     s->steps_since_sort += nsteps;
     launch(*s, 0, nsteps);
   }
