@@ -381,6 +381,7 @@ def main():
     barrier()
     l0 = fd.launch_count
     r0 = fd.resort_count
+    rk0 = fd.resort_kernel_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record(stream)
     for s in range(args.steps):
@@ -389,6 +390,7 @@ def main():
     barrier()
     launches = fd.launch_count - l0
     resorts = fd.resort_count - r0
+    resort_kernels = fd.resort_kernel_count - rk0
     sampler.mark_end()
     if sampler.loaded_samples() == 0:
         # nvidia-smi delivered nothing inside the timed region (slow start): keep the same load on the device until it does
@@ -512,7 +514,11 @@ def main():
                          "asynchronous copies on their own streams.  value: pipelined caller (step k+1's inputs do not depend on step k's "
                          "outputs: transfers overlap the kernels); closed_loop_value: the caller waits for step k's state on the host before "
                          "sending step k+1's inputs" % (nl, " + state (q, q')" if args.e2e_upload_state else "", ", ".join(outs), nq)},
-           "gpu_launches": int(launches),
+           # every kernel of this repository launched inside the timed region: one rkfd_step_kernel per step plus the kernels of the
+           # environment re-sorts that fell into it (key / offsets / assign / row permutations / order; their device-to-device
+           # staging copies are cudaMemcpyAsync calls, not kernels)
+           "gpu_launches": int(launches + resort_kernels),
+           "gpu_launches_detail": {"rkfd_step_kernel": int(launches), "resort_kernels": int(resort_kernels), "resorts": int(resorts)},
            "clocks": clocks,
            "job_stats": job_stats,
            "roofline": binding, "roofline_hbm": hbm_roof, "roofline_fp64": fp64_roof}

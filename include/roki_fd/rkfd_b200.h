@@ -331,6 +331,7 @@ __ROKI_FD_EXPORT int rkFDBatchGetStatus(rkFD *fd, int *status);                 
 __ROKI_FD_EXPORT int rkFDBatchSetResortInterval(rkFD *fd, int steps);
 __ROKI_FD_EXPORT int rkFDBatchSlotMap(rkFD *fd, int shard, int *perm);
 __ROKI_FD_EXPORT long long rkFDBatchResortCount(rkFD *fd);
+__ROKI_FD_EXPORT long long rkFDBatchResortKernelCount(rkFD *fd);     /* kernels the re-sorts launched so far (beside rkFDBatchLaunchCount's step kernels) */
 /* end-of-run statistics of the batch, reduced on the device; sums: out[0] environments, [1] environments with an active
  * contact, [2] active contact vertices, [3] environments with a non-zero status word; maxima: [4] |q''|, [5] |q'|;
  * [6..7] reserved (0).  A one-process-per-GPU job all-reduces [0..3] with SUM and [4..5] with MAX (SURVEY.md section 8e:

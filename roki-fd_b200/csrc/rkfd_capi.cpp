@@ -537,6 +537,7 @@ extern "C" int rkFDBatchGetStatus(rkFD *fd, int *s){ BATCH_GUARD(fd); NEED_ENGIN
 extern "C" int rkFDBatchSetResortInterval(rkFD *fd, int steps){ BATCH_GUARD(fd); if( steps < 0 ) return fail("steps must be >= 0"); fi->resort = steps; if( fi->engine ) fi->engine->set_resort_interval(steps); return 0; }
 extern "C" int rkFDBatchSlotMap(rkFD *fd, int shard, int *perm){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->slot_map(shard, perm)); }
 extern "C" long long rkFDBatchResortCount(rkFD *fd){ FDImpl *fi = FI(fd); return ( fi && fi->engine ) ? fi->engine->resorts() : 0; }
+extern "C" long long rkFDBatchResortKernelCount(rkFD *fd){ FDImpl *fi = FI(fd); return ( fi && fi->engine ) ? fi->engine->resort_kernels() : 0; }
 /* end-of-run statistics of the whole batch, reduced on the device (what a multi-process job all-reduces) */
 extern "C" int rkFDBatchStats(rkFD *fd, double out[8]){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->stats(out)); }
 extern "C" int rkFDBatchEval(rkFD *fd, int ref){ BATCH_GUARD(fd); NEED_ENGINE(); TRY(fi->engine->eval(ref != 0)); }

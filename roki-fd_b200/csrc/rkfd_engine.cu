@@ -416,8 +416,10 @@ void Engine::resort(Shard &s)
   rkfd_sort_offsets_kernel<<<1, 32, 0, s.stream>>>(s.bins);
   rkfd_sort_assign_kernel<<<grid, 256, 0, s.stream>>>(s.key, s.bins, s.newpos, s.B);
   CK(cudaGetLastError());
+  resort_kernels_ += 4;      /* key, offsets, assign above; the composition of the order below */
   auto perm_rows = [&](void *base, size_t elem, int nrows){
     if( !base || nrows <= 0 ) return;
+    resort_kernels_++;
     const size_t bytes = (size_t)nrows*s.ld*elem;
     /* the padding slots [B, ld) keep their (valid, zero-state) content */
     CK(cudaMemcpyAsync(s.ptmp, base, bytes, cudaMemcpyDeviceToDevice, s.stream));

@@ -59,6 +59,7 @@ class Engine {
   void slot_map(int s, int *perm);
   long long resorts() const;
   long long launches() const { return launches_; }
+  long long resort_kernels() const { return resort_kernels_; }      /* kernels launched by the re-sorts (key, offsets, assign, row permutations, order) */
 
  private:
   void upload_model(Shard &s);
@@ -68,7 +69,7 @@ class Engine {
   ModelDev model_, model_tm_;     /* model_tm_: the same table with the tensor-memory scratch map (generic TM kernel) */
   int B_;
   std::vector<Shard*> shards_;
-  long long launches_ = 0;
+  long long launches_ = 0, resort_kernels_ = 0;
   int id_;
 };
 

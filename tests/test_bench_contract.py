@@ -49,7 +49,8 @@ def test_reference_arm_uses_every_host_thread_under_torchrun():
 @pytest.mark.parametrize("config", ["C2", "C5-mlcp", "C5-vert", "C4"])
 def test_gpu_arm_other_configs(config):
     d = run("--steps", "3", "--warmup", "3", "--config", config, "--envs", "8192", "--no-cpu-baseline")
-    assert d["config"]["name"] == config and d["value"] > 0 and d["gpu_launches"] == 3
+    assert d["config"]["name"] == config and d["value"] > 0 and d["gpu_launches_detail"]["rkfd_step_kernel"] == 3
+    assert d["gpu_launches"] == 3 + d["gpu_launches_detail"]["resort_kernels"] and ( config != "C4" or d["gpu_launches_detail"]["resorts"] == 3 )
     assert d["roofline_hbm"]["frac"] > 0 and d["e2e"]["value"] > 0
 
 
@@ -57,7 +58,8 @@ def test_gpu_arm_other_configs(config):
 def test_gpu_arm_json_line():
     d = run("--steps", "5", "--warmup", "3", "--envs", "32768")
     assert KEYS <= set(d) and d.get("impl") != "reference"
-    assert d["value"] > 0 and d["gpu_launches"] == 5 and d["steps"] == 5
+    assert d["value"] > 0 and d["gpu_launches_detail"]["rkfd_step_kernel"] == 5 and d["steps"] == 5
+    assert d["gpu_launches"] == 5 + d["gpu_launches_detail"]["resort_kernels"]
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     # the binding roof of this path is the fp64 pipe; the HBM roofline travels beside it
