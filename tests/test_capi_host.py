@@ -291,3 +291,19 @@ def test_ztk_reader_fills_the_gaps_of_the_reference_models():
     m = _flattened(fd); fd.destroy()
     Vs, Vc = 4 / 3 * np.pi * 0.02 ** 3, np.pi * 0.01 ** 2 * 0.11
     assert abs(m["link.mass[1]"][12] - Vc * 0.075 / (Vs + Vc)) < 1e-12 and m["link.mass[4]"][4] == pytest.approx(0.6 * 0.4 * 0.02 ** 2)
+
+
+def test_volume_kernel_keeps_its_warp_barriers():
+    """DESIGN.md section 3.1, "Reconvergence the compiler cannot delete": nvcc drops __syncwarp() / the sync of __any_sync at loop
+    heads it takes for convergent, and lanes that skipped a divergent body then run ahead through the block barriers (seen on
+    the B200 as a warp out-of-range address).  DevCtx::hsync()/hany() use a mask the compiler cannot evaluate; the SASS of the
+    Volume variant must therefore hold the guarded warp barrier (active mask compared with the mask, divergent branch to a
+    WARPSYNC) at the candidate loop and before the friction LPs.  Checked on the object file the build leaves in-tree."""
+    import shutil, subprocess
+    obj = os.path.join(os.path.dirname(capi.LIB_PATH), "csrc", "build", "rkfd_kernel_256_1_1_0_1.o")
+    if shutil.which("cuobjdump") is None or not os.path.exists(obj):
+        pytest.skip("no cuobjdump / no object file of the Volume variant")
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, timeout=300).stdout
+    assert sass.count("BRA.DIV") >= 3 and "WARPSYNC.EXCLUSIVE" in sass
+    src = open(os.path.join(os.path.dirname(capi.LIB_PATH), "csrc", "rkfd_volume.cuh")).read()
+    assert src.count("c.hsync()") >= 2 and "c.hany(ci < ncand)" in src
